@@ -1,0 +1,265 @@
+/*
+ * sbod.h — C ABI of libsbod.so, the B200 (sm_100a) detection box pipeline.
+ *
+ * This is the drop-in boundary for the hot path of shuaiqi361/shape_based_object_detection
+ * (SURVEY.md §8): prior<->GT IoU + best-match assignment, gcxgcy encode/decode, regression +
+ * classification losses with hard-negative mining, and decode + threshold + NMS + top-k.
+ * The reference has no FFI layer of its own (pure Python/PyTorch); every entry point below
+ * cites the reference function it replaces (paths relative to the reference root).
+ *
+ * Conventions
+ *   - all pointers are DEVICE pointers unless the name ends in _host;
+ *   - tensors are dense row-major fp32 / int64 / int32 / uint8 as stated;
+ *   - every call is asynchronous on `stream` (a cudaStream_t), never allocates or frees
+ *     caller memory, never throws; scratch comes from a caller-supplied workspace whose size
+ *     is returned by the matching *_workspace_bytes query;
+ *   - return value: 0 = ok, >0 = cudaError_t, <0 = SBOD_ERR_* validation code.
+ */
+#ifndef SBOD_H_
+#define SBOD_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* sbod_stream_t; /* cudaStream_t */
+
+#define SBOD_ABI_VERSION 1
+
+#define SBOD_OK 0
+#define SBOD_ERR_INVALID (-1)     /* bad argument (null pointer, negative size, unknown enum) */
+#define SBOD_ERR_WORKSPACE (-2)   /* workspace too small or misaligned */
+#define SBOD_ERR_UNSUPPORTED (-3) /* shape outside what the kernels support */
+#define SBOD_ERR_ALIGNMENT (-4)   /* a streamed tensor is not 16-byte aligned */
+
+int sbod_abi_version(void);
+const char* sbod_error_string(int code);
+
+/* ------------------------------------------------------------------------------------------
+ * Dense pairwise IoU.
+ *   SBOD_IOU_METRICS  : metrics.py:208-252 find_jaccard_overlap (EPS=1e-5 in the denominator,
+ *                       zero-size GT rows -> 0, zero-size anchors -> -1, anchor rule wins)
+ *   SBOD_IOU_JACCARD  : operators/iou_utils.py:215-233 jaccard (no EPS, no masks, 0/0 -> NaN)
+ * a: [A,4] xyxy, b: [B,4] xyxy, out: [A,B].
+ * ---------------------------------------------------------------------------------------- */
+#define SBOD_IOU_METRICS 0
+#define SBOD_IOU_JACCARD 1
+int sbod_iou_matrix(const float* a, int A, const float* b, int B, int mode, float* out,
+                    sbod_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Box format converters and gcxgcy codec, elementwise over n boxes.
+ *   dataset/transforms.py:26-83  xy_to_cxcy, cxcy_to_xy, cxcy_to_gcxgcy, gcxgcy_to_cxcy
+ *   operators/iou_utils.py:167-177 point_form (== cxcy_to_xy), :324-368 encode / decode
+ * For the codec ops `priors` is [n,4] cxcy; v0/v1 are the two variances: the transforms.py
+ * functions hard-code 1/10 and 1/5 (pass v0=0.1f, v1=0.2f and SBOD_CODEC_TRANSFORMS so the
+ * arithmetic order matches), iou_utils encode/decode take them as arguments.
+ * ---------------------------------------------------------------------------------------- */
+#define SBOD_BOX_XY_TO_CXCY 0
+#define SBOD_BOX_CXCY_TO_XY 1
+int sbod_box_convert(const float* in, float* out, int n, int op, sbod_stream_t stream);
+
+#define SBOD_CODEC_TRANSFORMS 0 /* transforms.py arithmetic: /(pwh/10), log(..)*5 */
+#define SBOD_CODEC_IOU_UTILS 1  /* iou_utils.py arithmetic: /(v0*pwh), log(..)/v1; decode -> xyxy */
+int sbod_box_encode(const float* boxes, const float* priors_cxcy, float* out, int n, int flavour,
+                    float v0, float v1, sbod_stream_t stream);
+int sbod_box_decode(const float* locs, const float* priors_cxcy, float* out, int n, int flavour,
+                    float v0, float v1, sbod_stream_t stream);
+
+/* RefineDet512.offset2bbox, models/RefineDet512.py:643-653: two-stage decode ARM -> ODM -> xyxy.
+ * arm/odm: [N,P,4], priors_cxcy: [P,4], out: [N,P,4]. */
+int sbod_offset2bbox(const float* arm_locs, const float* odm_locs, const float* priors_cxcy,
+                     float* out, int N, int P, sbod_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Paired (elementwise) IoU family, operators/iou_utils.py:6-164 bbox_overlaps_{iou,giou,diou,ciou}
+ * b1,b2: [M,4] xyxy -> out [M]. Backward: grad wrt b1 and b2 given grad_out [M] (CIoU treats
+ * alpha / v / arctan as constants exactly as the reference's no_grad block, :86-92).
+ * ---------------------------------------------------------------------------------------- */
+#define SBOD_PAIR_IOU 0
+#define SBOD_PAIR_GIOU 1
+#define SBOD_PAIR_DIOU 2
+#define SBOD_PAIR_CIOU 3
+int sbod_pair_iou_fwd(const float* b1, const float* b2, int M, int kind, float* out,
+                      sbod_stream_t stream);
+int sbod_pair_iou_bwd(const float* b1, const float* b2, const float* grad_out, int M, int kind,
+                      float* grad_b1, float* grad_b2, sbod_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Row losses used stand-alone by operators/Loss.py.
+ *   sbod_smooth_l1      : Loss.py:203-226 SmoothL1Loss elementwise term (pred,target [M,4] -> [M,4])
+ *   sbod_softmax_focal  : Loss.py:9-38 focal_loss per-row term (logits [M,C], target [M] int64);
+ *                         row_out[M] = loss of the target column (the only non-zero column),
+ *                         grad_logits (optional, may be NULL) = d(sum row_out)/d logits.
+ *   sbod_sigmoid_focal  : Loss.py:41-80 SigmoidFocalLoss (uses columns 1..C-1, class ids 1..C-1)
+ * ---------------------------------------------------------------------------------------- */
+int sbod_smooth_l1(const float* pred, const float* target, int n_elem, float beta, float* out,
+                   float* grad_pred /* nullable: d out / d pred */, sbod_stream_t stream);
+int sbod_softmax_focal(const float* logits, const int64_t* target, int M, int C, float alpha_fg,
+                       float alpha_bg, float gamma, float* row_out, float* grad_logits,
+                       sbod_stream_t stream);
+int sbod_sigmoid_focal(const float* logits, const int64_t* target, int M, int C, float alpha,
+                       float gamma, float* row_out, float* grad_logits, sbod_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Stand-alone greedy NMS == torchvision.ops.nms as called at models/utils.py:145,265 and
+ * detect_scripts/detect_tools.py:62,182,202,304,324 (stable descending score order; suppress
+ * iff inter/(area_i+area_j-inter) > thr), and operators/iou_utils.py:385-450 nms (top_k cap).
+ * boxes [n,4] xyxy, scores [n]; keep_out [n] int64 (indices into the input, kept order),
+ * count_out [1] int32. top_k <= 0 means no cap.
+ * ---------------------------------------------------------------------------------------- */
+size_t sbod_nms_workspace_bytes(int n);
+int sbod_nms(const float* boxes, const float* scores, int n, float iou_thr, int top_k,
+             int64_t* keep_out, int32_t* count_out, void* workspace, size_t workspace_bytes,
+             sbod_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Batched assignment (the loop inlined in every *Loss.forward: models/SSD300.py:501-542,
+ * SSD512.py:532-572, RetinaNet.py:409-449, RefineDet512.py:746-785 and :847-886).
+ * GT boxes/labels are packed CSR style: gt_boxes [T,4] xyxy, gt_labels [T] int64,
+ * gt_offsets [N+1] int32 (image i owns rows gt_offsets[i]..gt_offsets[i+1]).
+ * anchors_xy: [P,4] shared priors (per_image_anchors=0) or [N,P,4] (RefineDet ODM, =1).
+ * Outputs (all [N,P]): ov = overlap_for_each_prior after the forced-match fill,
+ * obj = object_for_each_prior (int32), cls = true_classes (int64, nullable),
+ * neg = true_neg_classes (int64, nullable).
+ * ---------------------------------------------------------------------------------------- */
+size_t sbod_assign_workspace_bytes(int N, int gmax);
+int sbod_assign(const float* gt_boxes, const int64_t* gt_labels, const int32_t* gt_offsets, int N,
+                int gmax, const float* anchors_xy, int per_image_anchors, int P, float thr_pos,
+                float thr_neg, float* ov_out, int32_t* obj_out, int64_t* cls_out,
+                int64_t* neg_out, void* workspace, size_t workspace_bytes, sbod_stream_t stream);
+
+/* SSD-pytorch style match, operators/iou_utils.py:236-321 (match / match_ious): jaccard without
+ * EPS/masks, best prior per GT forced with overlap 2 (no >0 filter, true GT ids),
+ * conf = labels[idx]+1, conf[ov<thr]=0. One image. priors_cxcy [P,4]; truths [G,4] xyxy;
+ * labels [G] int64. Writes loc_out [P,4] (encoded with variances v0,v1, or the matched xyxy
+ * boxes when encode_loc==0 == match_ious) and conf_out [P] int64. */
+size_t sbod_match_workspace_bytes(int G, int P);
+int sbod_match(float threshold, const float* truths, int G, const float* priors_cxcy, int P,
+               float v0, float v1, const int64_t* labels, int encode_loc, float* loc_out,
+               int64_t* conf_out, void* workspace, size_t workspace_bytes, sbod_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Fused train path: assignment + encode/decode + loc loss + classification loss + hard-negative
+ * mining, forward and backward. Replaces the bodies of MultiBoxLoss300.forward
+ * (models/SSD300.py:477-594), MultiBoxLoss512.forward (SSD512.py:508-626),
+ * RetinaFocalLoss.forward (RetinaNet.py:385-506), RefineDetLoss.compute_arm_loss /
+ * compute_odm_loss (RefineDet512.py:730-939).
+ * ---------------------------------------------------------------------------------------- */
+#define SBOD_REG_L1_ELEM_MEAN 0 /* nn.L1Loss(): sum|d| / (4*n_pos)            SSD300.py:465 */
+#define SBOD_REG_SMOOTH_L1 1    /* SmoothL1Loss(beta,'mean'): sum / n_pos rows Loss.py:203-226 */
+#define SBOD_REG_IOU 2          /* IouLoss('Corner','mean',losstype): sum(1-x)/n_pos Loss.py:164 */
+#define SBOD_REG_GIOU 3
+#define SBOD_REG_DIOU 4
+#define SBOD_REG_CIOU 5
+
+#define SBOD_CLS_CE_MINE_NONPOS 0 /* CE; per image, positives zeroed, top 3*n_pos   SSD512.py:597-623 */
+#define SBOD_CLS_CE_MINE_NEG 1    /* CE; per image, all but true_neg==-1 zeroed     RetinaNet.py:476-503 */
+#define SBOD_CLS_CE_MINE_BATCH 2  /* CE; batch-global over true_neg==-1 rows        SSD300.py:567-591 */
+#define SBOD_CLS_FOCAL_SUM 3      /* focal_loss(pos rows + neg rows), not normalised SSD512.py:587-593 */
+#define SBOD_CLS_FOCAL_NORM 4     /* same / sum(n_pos)                              RetinaNet.py:464-472 */
+
+typedef struct sbod_loss_desc {
+  /* ---- inputs ---- */
+  const float* locs;         /* [N,P,4] predicted gcxgcy offsets */
+  const float* scores;       /* [N,P,C] logits, 16-byte aligned base */
+  const float* priors_cxcy;  /* [P,4] */
+  const float* priors_xy;    /* [P,4] == cxcy_to_xy(priors_cxcy), as the reference ctor computes */
+  const float* anchors_xy;   /* NULL, or [N,P,4] xyxy per-image refined anchors (RefineDet ODM,
+                                RefineDet512.py:850-851); their cxcy form is derived on the fly */
+  const float* gt_boxes;     /* [T,4] xyxy */
+  const int64_t* gt_labels;  /* [T] */
+  const int32_t* gt_offsets; /* [N+1] */
+  const uint8_t* exclude;    /* NULL, or [N,P]: ARM easy negatives (RefineDet512.py:894-899,924) */
+  int32_t N, P, C, gmax;     /* gmax >= max GT per image (host knows it from the list lengths) */
+  float thr_pos, thr_neg;    /* float32(threshold), float32(threshold - 0.1) */
+  int32_t reg_kind, cls_kind;
+  int32_t binarize_labels;   /* RefineDet ARM: labels -> (label > 0)   RefineDet512.py:781 */
+  int32_t neg_pos_ratio;
+  float reg_weight;          /* config.reg_weights (alpha) */
+  float smooth_l1_beta;      /* 1/9 */
+  float focal_alpha, focal_gamma;
+  /* ---- per-prior state written by forward, read by backward; each [N,P] ---- */
+  float* ov;     /* overlap_for_each_prior (after forced-match fill) */
+  int32_t* obj;  /* object_for_each_prior */
+  float* lse;    /* log-sum-exp of the logits row */
+  float* ce;     /* cross entropy of the row against its true class */
+  uint8_t* sel;  /* bit0: positive, bit1: hard negative / focal negative */
+  /* ---- outputs ---- */
+  double* partials; /* [N,4]  per image: sum loc, sum conf over positives, sum conf over mined negatives, n_pos */
+  double* sums;     /* [4]    batch sums of the same (the only data that crosses GPUs) */
+  float* loss;      /* [4]    total, conf, loc, n_pos */
+  void* workspace;
+  size_t workspace_bytes;
+} sbod_loss_desc;
+
+size_t sbod_loss_workspace_bytes(const sbod_loss_desc* d);
+/* The workspace must be zeroed once before its first use (every call leaves it clean again);
+ * the same holds for the sbod_assign / sbod_detect workspaces. */
+int sbod_workspace_init(void* workspace, size_t bytes, sbod_stream_t stream);
+int sbod_loss_forward(const sbod_loss_desc* d, sbod_stream_t stream);
+/* Recompute d->loss from d->sums (after a cross-GPU all-reduce of d->sums). */
+int sbod_loss_finalize(const sbod_loss_desc* d, sbod_stream_t stream);
+/* grad_loss: device scalar (upstream gradient). grad_locs [N,P,4], grad_scores [N,P,C]. */
+int sbod_loss_backward(const sbod_loss_desc* d, const float* grad_loss, float* grad_locs,
+                       float* grad_scores, sbod_stream_t stream);
+/* Expand the per-prior state into the reference's int64 tensors (tests / debugging):
+ * true_classes, true_neg_classes [N,P]. */
+int sbod_loss_targets(const sbod_loss_desc* d, int64_t* cls_out, int64_t* neg_out,
+                      sbod_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Eval path: activation + decode + clamp + score threshold + per-class NMS + top-k, batched.
+ * Replaces detect (models/utils.py:181-297), detect_tools.detect (detect_scripts/detect_tools.py:
+ * 100-219) and detect_refine (:222-341).
+ * ---------------------------------------------------------------------------------------- */
+#define SBOD_ACT_SOFTMAX 0
+#define SBOD_ACT_SIGMOID 1
+#define SBOD_BOX_OFFSET 0 /* gcxgcy wrt priors */
+#define SBOD_BOX_CENTER 1 /* cxcy */
+#define SBOD_BOX_CORNER 2 /* xyxy (clamped in place in the reference, models/utils.py:224) */
+
+typedef struct sbod_detect_desc {
+  float* locs;               /* [N,P,4]; written only when clamp_inplace != 0 */
+  const float* scores;       /* [N,P,C] logits, 16-byte aligned base */
+  const float* priors_cxcy;  /* [P,4] (SBOD_BOX_OFFSET only) */
+  const uint8_t* prior_keep; /* NULL, or [N,P] prior_positives_idx */
+  int32_t N, P, C;
+  int32_t act_kind, box_kind, clamp_inplace;
+  float min_score, max_overlap;
+  int32_t top_k;
+  float second_nms_thr;      /* < 0: off; detect_tools: 0.7 class-agnostic second NMS */
+  int32_t pre_nms_topk;      /* <= 0: off; per-class candidate cap (BASELINE config 3) */
+  /* outputs; out_cap >= max(top_k, 1) rows per image */
+  float* out_boxes;    /* [N,out_cap,4] */
+  int64_t* out_labels; /* [N,out_cap] */
+  float* out_scores;   /* [N,out_cap] */
+  int32_t* out_prior;  /* [N,out_cap] prior index of each detection, -1 for the placeholder */
+  int32_t* out_counts; /* [N] */
+  int32_t out_cap;
+  void* workspace;
+  size_t workspace_bytes;
+} sbod_detect_desc;
+
+size_t sbod_detect_workspace_bytes(const sbod_detect_desc* d);
+/* leading bytes of the workspace that must be zero before the first call (sbod_workspace_init) */
+size_t sbod_detect_workspace_zero_bytes(const sbod_detect_desc* d);
+int sbod_detect(const sbod_detect_desc* d, sbod_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * End-to-end helpers with HOST buffers (pinned or pageable): copy the inputs to the device,
+ * run the device entry point above, copy the result back. Used by bench.py's e2e leg; the
+ * device scratch is the caller's (dev_arena, arena_bytes from the *_arena_bytes query).
+ * ---------------------------------------------------------------------------------------- */
+size_t sbod_loss_forward_host_arena_bytes(const sbod_loss_desc* d, int T);
+int sbod_loss_forward_host(const sbod_loss_desc* d_host /* input pointers are HOST pointers */,
+                           int T, float* loss_host /* [4] */, void* dev_arena, size_t arena_bytes,
+                           sbod_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SBOD_H_ */

@@ -1,0 +1,704 @@
+// detect.cu — the eval path (sm_100a): activation + decode + clamp + score threshold +
+// per-class NMS + top-k, batched, no host round trips.
+//
+//   detect_score_kernel  persistent; logits tiles streamed by bulk TMA (same ring as the train
+//                        kernel); one thread per prior row turns the row into probabilities in
+//                        place, and every (class, prior) above min_score is emitted as one 64-bit
+//                        key  [0x3F800000 - score_bits : 32][class : 12][prior : 20]  so that
+//                        ascending key order == (score desc, class asc, prior asc) == the order in
+//                        which the reference's per-class NMS + stable top-k sort consumes them.
+//                        A per-image histogram of the key's top digit is built on the fly.
+//   detect_nms_kernel    one CTA per image. The reference runs NMS over every candidate of every
+//                        class and only then keeps the top_k best (models/utils.py:245-290). Greedy
+//                        NMS is prefix-stable, so the first top_k+1 survivors in global key order
+//                        are all that is ever needed: candidates are pulled in key-ordered chunks
+//                        (histogram-guided, radix descent for oversized bins), sorted in smem,
+//                        suppressed per class by one warp per class (warp-ballot over the kept
+//                        list), and the loop stops as soon as top_k+1 boxes survive. If the
+//                        candidates run out first, everything is kept and emitted class-major,
+//                        exactly as the reference does.
+#include <math.h>
+
+#include "common.cuh"
+
+namespace sbod {
+
+constexpr int kDRows = 128;
+constexpr int kChunk = 1024;       // candidates per NMS round (== threads of detect_nms_kernel)
+constexpr int kNmsThreads = 1024;
+constexpr int kMaxBins = 2048;
+constexpr int kClassBits = 12, kPriorBits = 20;
+constexpr uint32_t kOneBits = 0x3F800000u;
+
+struct DetParams {
+  float* locs;
+  const float* scores;
+  const float4* priors_cxcy;
+  const uint8_t* prior_keep;
+  int N, P, C;
+  int act_kind, box_kind, clamp_inplace;
+  float min_score, max_overlap;
+  int top_k;
+  float second_thr;
+  int pre_nms_topk;
+  float* out_boxes;
+  int64_t* out_labels;
+  float* out_scores;
+  int32_t* out_prior;
+  int32_t* out_counts;
+  int out_cap;
+  // workspace
+  unsigned int* cand_count;     // [N]
+  unsigned int* hist;           // [N, n_bins]
+  unsigned long long* cand;     // [N, cand_cap]
+  unsigned int* class_seen;     // [N, C]  (pre-NMS per-class rank counters)
+  long long cand_cap;
+  int n_bins, shift0;           // level-0 digit = key >> shift0
+  int kcap;                     // kept-list capacity in smem
+  // tiling
+  int rows_per_tile, tiles_per_image, n_tiles, n_stages;
+  uint32_t stage_floats;
+};
+
+SBOD_DEVINL float4 decode_box(const DetParams& q, int n, int p) {
+  const float4 l = reinterpret_cast<const float4*>(q.locs)[size_t(n) * q.P + p];
+  float4 b;
+  if (q.box_kind == SBOD_BOX_OFFSET) {  // cxcy_to_xy(gcxgcy_to_cxcy(l, prior)), transforms.py:37-45,69-83
+    const float4 pr = q.priors_cxcy[p];
+    const float cx = l.x * pr.z / 10.f + pr.x, cy = l.y * pr.w / 10.f + pr.y;
+    const float w = expf(l.z / 5.f) * pr.z, h = expf(l.w / 5.f) * pr.w;
+    b = make_float4(cx - w / 2.f, cy - h / 2.f, cx + w / 2.f, cy + h / 2.f);
+  } else if (q.box_kind == SBOD_BOX_CENTER) {
+    b = make_float4(l.x - l.z / 2.f, l.y - l.w / 2.f, l.x + l.z / 2.f, l.y + l.w / 2.f);
+  } else {
+    b = l;
+  }
+  // clamp_(0, 1): torch.clamp maps NaN to NaN; fminf/fmaxf would not — NaN parity is out of scope
+  b.x = fminf(fmaxf(b.x, 0.f), 1.f);
+  b.y = fminf(fmaxf(b.y, 0.f), 1.f);
+  b.z = fminf(fmaxf(b.z, 0.f), 1.f);
+  b.w = fminf(fmaxf(b.w, 0.f), 1.f);
+  return b;
+}
+
+struct DTile {
+  int n, p0, rows;
+};
+SBOD_DEVINL DTile dtile(const DetParams& q, int tile) {
+  DTile t;
+  t.n = tile / q.tiles_per_image;
+  t.p0 = (tile - t.n * q.tiles_per_image) * q.rows_per_tile;
+  t.rows = min(q.rows_per_tile, q.P - t.p0);
+  return t;
+}
+
+SBOD_DEVINL void issue_dtile(const DetParams& q, int tile, float* stage, uint64_t* bar) {
+  const DTile t = dtile(q, tile);
+  const size_t first = (size_t(t.n) * q.P + t.p0) * size_t(q.C);
+  const size_t total = size_t(q.N) * q.P * size_t(q.C);
+  const TileSpan s = make_tile_span(q.scores, first, size_t(t.rows) * q.C, total);
+  for (uint32_t i = 0; i < s.tail_floats; ++i)
+    stage[s.bulk_bytes / 4 + i] = q.scores[(s.src16 - q.scores) + s.bulk_bytes / 4 + i];
+  if (s.bulk_bytes) {
+    mbar_arrive_expect_tx(bar, s.bulk_bytes);
+    tma_load_1d(stage, s.src16, s.bulk_bytes, bar);
+  } else {
+    mbar_arrive(bar);
+  }
+}
+
+__global__ void __launch_bounds__(kDRows) detect_score_kernel(const DetParams q) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  float* stages = reinterpret_cast<float*>(smem_raw);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + size_t(q.n_stages) * q.stage_floats * 4);
+  __shared__ unsigned int s_wtot[kDRows / 32];
+  __shared__ unsigned int s_base;
+
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int n_my = (q.n_tiles - int(blockIdx.x) + int(gridDim.x) - 1) / int(gridDim.x);
+  if (tid == 0) {
+    for (int s = 0; s < q.n_stages; ++s) mbar_init(&bars[s], 1);
+    fence_mbar_init();
+  }
+  __syncthreads();
+  if (tid == 0) {
+    for (int s = 0; s < q.n_stages && s < n_my; ++s)
+      issue_dtile(q, blockIdx.x + s * gridDim.x, stages + size_t(s) * q.stage_floats, &bars[s]);
+  }
+  int gcd = 1;
+  while (gcd < 32 && (q.C % (gcd * 2)) == 0) gcd *= 2;
+  const int rot = (lane * gcd) >> 5;
+  const int C = q.C;
+  const float INF = __int_as_float(0x7f800000);
+
+  for (int it = 0; it < n_my; ++it) {
+    const int tile = blockIdx.x + it * gridDim.x;
+    const DTile tc = dtile(q, tile);
+    const int n = tc.n;
+    const bool valid = tid < tc.rows;
+    const int p = tc.p0 + tid;
+    const size_t np = size_t(n) * q.P + (valid ? p : tc.p0);
+    const bool keep_row = valid && (q.prior_keep ? q.prior_keep[np] != 0 : true);
+
+    if (valid && q.clamp_inplace) {  // models/utils.py:224, detect_tools.py:264: clamp_ on the caller's tensor
+      float4* lp = reinterpret_cast<float4*>(q.locs) + np;
+      float4 b = *lp;
+      b.x = fminf(fmaxf(b.x, 0.f), 1.f); b.y = fminf(fmaxf(b.y, 0.f), 1.f);
+      b.z = fminf(fmaxf(b.z, 0.f), 1.f); b.w = fminf(fmaxf(b.w, 0.f), 1.f);
+      *lp = b;
+    }
+
+    const int s = it % q.n_stages;
+    float* stage = stages + size_t(s) * q.stage_floats;
+    mbar_wait(&bars[s], (it / q.n_stages) & 1);
+    const size_t first = (size_t(n) * q.P + tc.p0) * size_t(C);
+    float* row = stage + (first & 3) + size_t(tid) * C;
+    unsigned int cnt = 0;
+    if (keep_row) {
+      if (q.act_kind == SBOD_ACT_SOFTMAX) {
+        float m0 = -INF, m1 = -INF, m2 = -INF, m3 = -INF;
+        int k = rot;
+        for (; k + 3 < C; k += 4) {
+          m0 = fmaxf(m0, row[k]); m1 = fmaxf(m1, row[k + 1]);
+          m2 = fmaxf(m2, row[k + 2]); m3 = fmaxf(m3, row[k + 3]);
+        }
+        for (; k < C; ++k) m0 = fmaxf(m0, row[k]);
+        for (k = 0; k < rot; ++k) m1 = fmaxf(m1, row[k]);
+        const float mx = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
+        float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+        k = rot;
+        for (; k + 3 < C; k += 4) {
+          const float e0 = __expf(row[k] - mx), e1 = __expf(row[k + 1] - mx);
+          const float e2 = __expf(row[k + 2] - mx), e3 = __expf(row[k + 3] - mx);
+          row[k] = e0; row[k + 1] = e1; row[k + 2] = e2; row[k + 3] = e3;
+          s0 += e0; s1 += e1; s2 += e2; s3 += e3;
+        }
+        for (; k < C; ++k) { const float e = __expf(row[k] - mx); row[k] = e; s0 += e; }
+        for (k = 0; k < rot; ++k) { const float e = __expf(row[k] - mx); row[k] = e; s1 += e; }
+        const float inv = __frcp_rn((s0 + s1) + (s2 + s3));
+        for (int kk = 0; kk < C; ++kk) {
+          k = kk + rot; if (k >= C) k -= C;
+          const float pr = row[k] * inv;
+          row[k] = pr;
+          cnt += (k > 0 && pr > q.min_score) ? 1u : 0u;
+        }
+      } else {
+        for (int kk = 0; kk < C; ++kk) {
+          int k = kk + rot; if (k >= C) k -= C;
+          const float pr = __frcp_rn(1.f + __expf(-row[k]));
+          row[k] = pr;
+          cnt += (k > 0 && pr > q.min_score) ? 1u : 0u;
+        }
+      }
+    }
+    // block-exclusive scan of the per-row candidate counts, one atomic per tile
+    unsigned int inc = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const unsigned int t = __shfl_up_sync(0xffffffffu, inc, o);
+      if (lane >= o) inc += t;
+    }
+    if (lane == 31) s_wtot[wid] = inc;
+    __syncthreads();
+    unsigned int off = inc - cnt, tot = 0;
+    for (int w = 0; w < kDRows / 32; ++w) {
+      if (w < wid) off += s_wtot[w];
+      tot += s_wtot[w];
+    }
+    if (tid == 0) s_base = tot ? atomicAdd(&q.cand_count[n], tot) : 0u;
+    __syncthreads();
+    if (cnt) {
+      long long slot = (long long)s_base + off;
+      unsigned long long* dst = q.cand + size_t(n) * q.cand_cap;
+      unsigned int* hist = q.hist + size_t(n) * q.n_bins;
+      for (int k = 1; k < C; ++k) {  // ascending class order inside the row
+        const float pr = row[k];
+        if (pr > q.min_score) {
+          uint32_t bits = __float_as_uint(pr);
+          const uint32_t k32 = bits > kOneBits ? 0u : kOneBits - bits;
+          const unsigned long long key = (static_cast<unsigned long long>(k32) << 32) |
+                                         (static_cast<unsigned long long>(k) << kPriorBits) |
+                                         static_cast<unsigned long long>(p);
+          if (slot < q.cand_cap) dst[slot] = key;
+          ++slot;
+          int bin = int(key >> q.shift0);
+          if (bin >= q.n_bins) bin = q.n_bins - 1;
+          atomicAdd(&hist[bin], 1u);
+        }
+      }
+    }
+    fence_proxy_async();
+    __syncthreads();
+    if (tid == 0 && it + q.n_stages < n_my)
+      issue_dtile(q, blockIdx.x + (it + q.n_stages) * gridDim.x, stage, &bars[s]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// detect_nms_kernel
+// ------------------------------------------------------------------------------------------
+SBOD_DEVINL int key_class(unsigned long long k) { return int((k >> kPriorBits) & ((1u << kClassBits) - 1u)); }
+SBOD_DEVINL int key_prior(unsigned long long k) { return int(k & ((1u << kPriorBits) - 1u)); }
+SBOD_DEVINL float key_score(unsigned long long k) { return __uint_as_float(kOneBits - uint32_t(k >> 32)); }
+
+// torchvision nms criterion: inter / (area_i + area_j - inter) > thr
+SBOD_DEVINL bool overlaps(const float4 a, const float4 b, float thr) {
+  const float aa = box_area_rn(a), ab = box_area_rn(b);
+  return iou_plain_rn(a, aa, b, ab) > thr;
+}
+
+struct NmsSmem {
+  unsigned int hist[kMaxBins];
+  unsigned long long ckey[kChunk];
+  float4 cbox[kChunk];
+  uint16_t cidx[kChunk];   // chunk positions grouped by class (segments in key order)
+  uint16_t cnew[kChunk];   // per class segment: positions kept in this round
+  uint8_t cflag[kChunk];   // 1 = survives stage 1, 2 = survives stage 2 as well
+  unsigned int wscan[32];
+  int misc[16];
+};
+
+// radix levels below the level-0 digit: 11 bits each
+SBOD_DEVINL int level_shift(const DetParams& q, int level) {
+  const int s = q.shift0 - 11 * level;
+  return s > 0 ? s : 0;
+}
+SBOD_DEVINL int level_bins(const DetParams& q, int level) {
+  if (level == 0) return q.n_bins;
+  const int hi = level_shift(q, level - 1), lo = level_shift(q, level);
+  return 1 << (hi - lo);
+}
+
+__global__ void __launch_bounds__(kNmsThreads) detect_nms_kernel(const DetParams q) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  NmsSmem& S = *reinterpret_cast<NmsSmem*>(smem_raw);
+  unsigned char* dyn = smem_raw + ((sizeof(NmsSmem) + 127) & ~size_t(127));
+  unsigned long long* kkey = reinterpret_cast<unsigned long long*>(dyn);          // [kcap]
+  float4* kbox = reinterpret_cast<float4*>(dyn + size_t(q.kcap) * 8);             // [kcap]
+  uint8_t* kst2 = reinterpret_cast<uint8_t*>(dyn + size_t(q.kcap) * 24);          // [kcap]
+  unsigned int* cls_off = reinterpret_cast<unsigned int*>(dyn + size_t(q.kcap) * 25 + 128 - (size_t(q.kcap) * 25) % 128);  // [C+1]
+
+  const int n = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const bool two_stage = q.second_thr >= 0.f;
+  unsigned int* g_hist = q.hist + size_t(n) * q.n_bins;
+  unsigned int* g_seen = q.class_seen + size_t(n) * q.C;
+  const unsigned long long* g_cand = q.cand + size_t(n) * q.cand_cap;
+  const unsigned int raw_total = q.cand_count[n];
+  const long long total = raw_total < (unsigned long long)q.cand_cap ? raw_total : q.cand_cap;
+  const bool overflow = raw_total > (unsigned long long)q.cand_cap;
+
+  int kept_n = 0;   // stage-1 survivors so far (kept list length)
+  int kept2_n = 0;  // stage-2 survivors so far
+  int status = 0;   // 1 = kept-list capacity exceeded
+  unsigned long long lo_key = 0ull;
+  bool exhausted = total == 0;
+  const int stop_at = q.top_k + 1;
+
+  while (!exhausted && (two_stage ? kept2_n : kept_n) < stop_at && !status) {
+    // ---- choose [lo_key, hi_key) holding at most kChunk candidates -------------------------
+    int level = 0;
+    while (level_shift(q, level) > 0 && (lo_key & ((1ull << level_shift(q, level)) - 1ull)) != 0ull)
+      ++level;
+    unsigned long long hi_key = 0ull;
+    bool have_hi = false;
+    while (!have_hi) {
+      const int sh = level_shift(q, level);
+      const int nb = level_bins(q, level);
+      const int dlo = (level == 0) ? int(lo_key >> sh) : int((lo_key >> sh) & (unsigned(nb) - 1u));
+      // node = keys sharing lo_key's bits above this level's digit
+      const int up = (level == 0) ? 64 : level_shift(q, level - 1);
+      const unsigned long long node_base = (up >= 64) ? 0ull : (lo_key >> up) << up;
+      if (level == 0) {
+        for (int b = tid; b < nb; b += kNmsThreads) S.hist[b] = g_hist[b];
+      } else {
+        for (int b = tid; b < nb; b += kNmsThreads) S.hist[b] = 0u;
+        __syncthreads();
+        for (long long i = tid; i < total; i += kNmsThreads) {
+          const unsigned long long k = g_cand[i];
+          if (k >= lo_key && (up >= 64 || (k >> up) == (lo_key >> up)))
+            atomicAdd(&S.hist[(k >> sh) & (unsigned(nb) - 1u)], 1u);
+        }
+      }
+      __syncthreads();
+      if (tid == 0) {
+        unsigned int cum = 0;
+        int d = dlo;
+        while (d < nb && cum + S.hist[d] <= unsigned(kChunk)) cum += S.hist[d++];
+        // skip leading empty digits is implied (they add 0). If the first non-fitting digit is the
+        // first non-empty one, descend into it.
+        int first_nonempty = dlo;
+        while (first_nonempty < nb && S.hist[first_nonempty] == 0u) ++first_nonempty;
+        S.misc[0] = d;
+        S.misc[1] = (d == first_nonempty && d < nb) ? 1 : 0;  // descend
+        S.misc[2] = int(cum);
+      }
+      __syncthreads();
+      const int d_end = S.misc[0];
+      const bool descend = S.misc[1] != 0;
+      __syncthreads();
+      if (descend) {
+        // restart at the oversized digit, one level down (its keys all share this digit)
+        lo_key = lo_key > (node_base + (static_cast<unsigned long long>(d_end) << sh))
+                     ? lo_key
+                     : node_base + (static_cast<unsigned long long>(d_end) << sh);
+        ++level;
+        continue;
+      }
+      if (d_end >= nb) {
+        if (level == 0) { hi_key = ~0ull; exhausted = true; }   // everything that is left fits
+        else hi_key = node_base + (1ull << up);                  // end of this node
+        if (level != 0 && hi_key == 0ull) { hi_key = ~0ull; exhausted = true; }  // wrapped
+      } else {
+        hi_key = node_base + (static_cast<unsigned long long>(d_end) << sh);
+      }
+      have_hi = true;
+    }
+
+    // ---- gather the chunk -----------------------------------------------------------------
+    if (tid == 0) S.misc[3] = 0;
+    __syncthreads();
+    for (long long i = tid; i < total; i += kNmsThreads) {
+      const unsigned long long k = g_cand[i];
+      if (k >= lo_key && (k < hi_key || hi_key == ~0ull)) {
+        const int slot = atomicAdd(&S.misc[3], 1);
+        if (slot < kChunk) S.ckey[slot] = k;
+      }
+    }
+    __syncthreads();
+    const int m = min(S.misc[3], kChunk);
+    lo_key = hi_key;
+    if (m == 0) {
+      __syncthreads();
+      continue;
+    }
+    // ---- sort by key (bitonic, padded with ~0) ----------------------------------------------
+    if (tid >= m) S.ckey[tid] = ~0ull;
+    __syncthreads();
+    for (int k2 = 2; k2 <= kChunk; k2 <<= 1) {
+      for (int j = k2 >> 1; j > 0; j >>= 1) {
+        const int ixj = tid ^ j;
+        if (ixj > tid) {
+          const unsigned long long a = S.ckey[tid], b = S.ckey[ixj];
+          const bool up_dir = (tid & k2) == 0;
+          if ((a > b) == up_dir) { S.ckey[tid] = b; S.ckey[ixj] = a; }
+        }
+        __syncthreads();
+      }
+    }
+    // ---- decode boxes, group by class -------------------------------------------------------
+    for (int c = tid; c <= q.C; c += kNmsThreads) cls_off[c] = 0u;
+    __syncthreads();
+    if (tid < m) {
+      const unsigned long long k = S.ckey[tid];
+      S.cbox[tid] = decode_box(q, n, key_prior(k));
+      S.cflag[tid] = 0;
+      atomicAdd(&cls_off[key_class(k) + 1], 1u);
+    }
+    __syncthreads();
+    // exclusive scan of the class histogram (C+1 entries), by warp 0
+    if (wid == 0) {
+      unsigned int carry = 0;
+      for (int base = 0; base <= q.C; base += 32) {
+        const int c = base + lane;
+        const unsigned int v = c <= q.C ? cls_off[c] : 0u;
+        unsigned int inc = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const unsigned int t = __shfl_up_sync(0xffffffffu, inc, o);
+          if (lane >= o) inc += t;
+        }
+        if (c <= q.C) cls_off[c] = carry + inc;  // inclusive over the shifted histogram == start of class c+... see below
+        carry += __shfl_sync(0xffffffffu, inc, 31);
+      }
+    }
+    __syncthreads();
+    // cls_off[c] now holds the number of chunk entries with class < c ... (entry c+1 counted class c),
+    // i.e. segment of class c is [cls_off[c], cls_off[c+1]).
+
+    // ---- stage 1: per-class greedy suppression, one warp per class ---------------------------
+    for (int c = 1 + wid; c < q.C; c += kNmsThreads / 32) {
+      const unsigned int seg0 = cls_off[c], seg1 = cls_off[c + 1];
+      if (seg1 == seg0) continue;
+      // fill the segment with this class's chunk positions in key order
+      unsigned int w = seg0;
+      for (int base = 0; base < m; base += 32) {
+        const int i = base + lane;
+        const bool mine = i < m && key_class(S.ckey[i]) == c;
+        const unsigned bal = __ballot_sync(0xffffffffu, mine);
+        if (mine) S.cidx[w + __popc(bal & ((1u << lane) - 1u))] = uint16_t(i);
+        w += __popc(bal);
+      }
+      __syncwarp();
+      unsigned int seen = g_seen[c];  // candidates of this class consumed by earlier rounds
+      unsigned int nnew = 0;
+      for (unsigned int r = seg0; r < seg1; ++r) {
+        const int e = S.cidx[r];
+        if (q.pre_nms_topk > 0 && seen + (r - seg0) >= unsigned(q.pre_nms_topk)) break;
+        const float4 be = S.cbox[e];
+        bool sup = false;
+        for (int i = lane; i < kept_n && !sup; i += 32)
+          if (key_class(kkey[i]) == c && overlaps(kbox[i], be, q.max_overlap)) sup = true;
+        for (unsigned int i = lane; i < nnew && !sup; i += 32)
+          if (overlaps(S.cbox[S.cnew[seg0 + i]], be, q.max_overlap)) sup = true;
+        if (!__any_sync(0xffffffffu, sup)) {
+          if (lane == 0) {
+            S.cnew[seg0 + nnew] = uint16_t(e);
+            S.cflag[e] = 1;
+          }
+          ++nnew;
+          __syncwarp();
+        }
+      }
+      if (lane == 0) g_seen[c] = seen + (seg1 - seg0);
+    }
+    __syncthreads();
+
+    // ---- stage 2 (detect_tools): class-agnostic NMS over the stage-1 survivors, key order ----
+    if (two_stage) {
+      if (wid == 0) {
+        int nnew2 = 0;  // new stage-2 survivors, their chunk positions reuse S.cidx[0..)
+        for (int e = 0; e < m; ++e) {
+          if (S.cflag[e] != 1) continue;
+          const float4 be = S.cbox[e];
+          bool sup = false;
+          for (int i = lane; i < kept_n && !sup; i += 32)
+            if (kst2[i] && overlaps(kbox[i], be, q.second_thr)) sup = true;
+          for (int i = lane; i < nnew2 && !sup; i += 32)
+            if (overlaps(S.cbox[S.cidx[i]], be, q.second_thr)) sup = true;
+          if (!__any_sync(0xffffffffu, sup)) {
+            if (lane == 0) {
+              S.cidx[nnew2] = uint16_t(e);
+              S.cflag[e] = 2;
+            }
+            ++nnew2;
+            __syncwarp();
+          }
+        }
+        if (lane == 0) S.misc[5] = nnew2;
+      }
+      __syncthreads();
+    }
+
+    // ---- append the survivors to the kept list, in key order ---------------------------------
+    const bool keep_me = tid < m && S.cflag[tid] != 0;
+    const unsigned bal = __ballot_sync(0xffffffffu, keep_me);
+    if (lane == 0) S.wscan[wid] = __popc(bal);
+    __syncthreads();
+    int pos = kept_n + __popc(bal & ((1u << lane) - 1u));
+    int add = 0;
+    for (int w = 0; w < kNmsThreads / 32; ++w) {
+      if (w < wid) pos += S.wscan[w];
+      add += S.wscan[w];
+    }
+    if (kept_n + add > q.kcap) {
+      status = 1;
+    } else {
+      if (keep_me) {
+        kkey[pos] = S.ckey[tid];
+        kbox[pos] = S.cbox[tid];
+        kst2[pos] = S.cflag[tid] == 2 ? 1 : 0;
+      }
+      kept_n += add;
+      if (two_stage) kept2_n += S.misc[5];
+    }
+    __syncthreads();
+  }
+
+  // ---- leave the workspace clean for the next call ----------------------------------------
+  for (int b = tid; b < q.n_bins; b += kNmsThreads) g_hist[b] = 0u;
+  for (int c = tid; c < q.C; c += kNmsThreads) g_seen[c] = 0u;
+  if (tid == 0) q.cand_count[n] = 0u;
+
+  // ---- emit --------------------------------------------------------------------------------
+  float4* ob = reinterpret_cast<float4*>(q.out_boxes) + size_t(n) * q.out_cap;
+  int64_t* ol = q.out_labels + size_t(n) * q.out_cap;
+  float* os = q.out_scores + size_t(n) * q.out_cap;
+  int32_t* op = q.out_prior + size_t(n) * q.out_cap;
+  if (status || overflow) {
+    if (tid == 0) q.out_counts[n] = overflow ? -2 : -1;  // host raises: capacity exceeded
+    return;
+  }
+  if (kept_n == 0) {  // placeholder for 'background', models/utils.py:274-277
+    if (tid == 0) {
+      ob[0] = make_float4(0.f, 0.f, 1.f, 1.f);
+      ol[0] = 0;
+      os[0] = 0.f;
+      op[0] = -1;
+      q.out_counts[n] = 1;
+    }
+    return;
+  }
+  if (!two_stage) {
+    if (kept_n > q.top_k) {
+      // more than top_k survivors: the reference sorts by score (stable) and keeps the first top_k
+      for (int i = tid; i < q.top_k; i += kNmsThreads) {
+        const unsigned long long k = kkey[i];
+        ob[i] = kbox[i]; ol[i] = key_class(k); os[i] = key_score(k); op[i] = key_prior(k);
+      }
+      if (tid == 0) q.out_counts[n] = q.top_k;
+    } else {
+      // everything survives: class-major, NMS order inside a class (models/utils.py:245-281)
+      for (int i = tid; i < kept_n; i += kNmsThreads) {
+        const unsigned long long k = kkey[i];
+        const int c = key_class(k);
+        int dst = 0;
+        for (int j = 0; j < kept_n; ++j) {
+          const int cj = key_class(kkey[j]);
+          dst += (cj < c || (cj == c && j < i)) ? 1 : 0;
+        }
+        ob[dst] = kbox[i]; ol[dst] = c; os[dst] = key_score(k); op[dst] = key_prior(k);
+      }
+      if (tid == 0) q.out_counts[n] = kept_n;
+    }
+  } else {
+    // detect_tools.py:200-212: survivors of the second NMS in score order; truncated to top_k only
+    // when the FIRST stage produced more than top_k boxes.
+    const bool truncate = kept_n > q.top_k;
+    if (wid == 0) {
+      int w = 0;
+      for (int base = 0; base < kept_n; base += 32) {
+        const int i = base + lane;
+        const bool s2 = i < kept_n && kst2[i];
+        const unsigned bal = __ballot_sync(0xffffffffu, s2);
+        const int dst = w + __popc(bal & ((1u << lane) - 1u));
+        if (s2 && (!truncate || dst < q.top_k) && dst < q.out_cap) {
+          const unsigned long long k = kkey[i];
+          ob[dst] = kbox[i]; ol[dst] = key_class(k); os[dst] = key_score(k); op[dst] = key_prior(k);
+        }
+        w += __popc(bal);
+      }
+      if (lane == 0) q.out_counts[n] = truncate ? min(w, q.top_k) : min(w, q.out_cap);
+    }
+  }
+}
+
+static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+struct DTiling {
+  int rows, stages;
+  uint32_t stage_floats;
+  size_t smem;
+};
+static DTiling choose_dtiling(int C) {
+  DTiling t;
+  const size_t budget = 100 * 1024;
+  t.rows = kDRows;
+  while (t.rows > 4 && (size_t(t.rows) * C + 8) * 4 > budget) t.rows /= 2;
+  t.stage_floats = uint32_t(align_up(size_t(t.rows) * C + 8, 32));
+  t.stages = int(budget / (size_t(t.stage_floats) * 4));
+  if (t.stages > 4) t.stages = 4;
+  if (t.stages < 1) t.stages = 1;
+  t.smem = size_t(t.stages) * t.stage_floats * 4 + 4 * 8;
+  return t;
+}
+
+static void level0_layout(float min_score, int* shift0, int* n_bins) {
+  // keys: (0x3F800000 - score_bits) << 32 | ...; score in (min_score, 1]
+  uint32_t minbits = 0;
+  float ms = min_score > 0.f ? min_score : 0.f;
+  memcpy(&minbits, &ms, 4);
+  if (minbits > kOneBits) minbits = kOneBits;
+  const uint32_t range = kOneBits - minbits;  // max k32
+  int sh = 0;
+  while (((unsigned long long)range >> sh) + 1ull > (unsigned long long)kMaxBins) ++sh;
+  *shift0 = 32 + sh;
+  *n_bins = int(((unsigned long long)range >> sh) + 1ull);
+}
+
+static long long cand_capacity(const sbod_detect_desc* d) {
+  return (long long)d->P * (long long)(d->C > 1 ? d->C - 1 : 1);
+}
+
+static int kept_capacity(const sbod_detect_desc* d) {
+  if (d->second_nms_thr >= 0.f) return 4096 + kChunk;
+  return d->top_k + 1 + kChunk;
+}
+
+}  // namespace sbod
+
+using namespace sbod;
+
+extern "C" size_t sbod_detect_workspace_bytes(const sbod_detect_desc* d) {
+  if (!d) return 0;
+  int sh, nb;
+  level0_layout(d->min_score, &sh, &nb);
+  size_t b = 0;
+  b += align_up(size_t(d->N) * 4, 256);                       // cand_count
+  b += align_up(size_t(d->N) * kMaxBins * 4, 256);            // hist
+  b += align_up(size_t(d->N) * size_t(d->C) * 4, 256);        // class_seen
+  b += align_up(size_t(d->N) * size_t(cand_capacity(d)) * 8, 256);
+  return b;
+}
+
+// bytes at the start of the workspace that must be zero before the first call
+extern "C" size_t sbod_detect_workspace_zero_bytes(const sbod_detect_desc* d) {
+  if (!d) return 0;
+  return align_up(size_t(d->N) * 4, 256) + align_up(size_t(d->N) * kMaxBins * 4, 256) +
+         align_up(size_t(d->N) * size_t(d->C) * 4, 256);
+}
+
+extern "C" int sbod_detect(const sbod_detect_desc* d, sbod_stream_t stream) {
+  if (!d || !d->locs || !d->scores || !d->out_boxes || !d->out_labels || !d->out_scores ||
+      !d->out_prior || !d->out_counts)
+    return SBOD_ERR_INVALID;
+  if (d->N <= 0 || d->P <= 0 || d->C <= 1 || d->top_k <= 0) return SBOD_ERR_INVALID;
+  if (d->box_kind == SBOD_BOX_OFFSET && !d->priors_cxcy) return SBOD_ERR_INVALID;
+  if (d->box_kind < 0 || d->box_kind > SBOD_BOX_CORNER) return SBOD_ERR_INVALID;
+  if (d->act_kind != SBOD_ACT_SOFTMAX && d->act_kind != SBOD_ACT_SIGMOID) return SBOD_ERR_INVALID;
+  if (d->P > (1 << kPriorBits) || d->C > (1 << kClassBits)) return SBOD_ERR_UNSUPPORTED;
+  if (d->top_k > 4096) return SBOD_ERR_UNSUPPORTED;
+  if (d->out_cap < (d->top_k > 1 ? d->top_k : 1)) return SBOD_ERR_INVALID;
+  if (reinterpret_cast<uintptr_t>(d->scores) & 15) return SBOD_ERR_ALIGNMENT;
+  if (reinterpret_cast<uintptr_t>(d->locs) & 15) return SBOD_ERR_ALIGNMENT;
+  if (!d->workspace || d->workspace_bytes < sbod_detect_workspace_bytes(d)) return SBOD_ERR_WORKSPACE;
+  if (reinterpret_cast<uintptr_t>(d->workspace) & 255) return SBOD_ERR_WORKSPACE;
+
+  DetParams q;
+  q.locs = d->locs; q.scores = d->scores;
+  q.priors_cxcy = reinterpret_cast<const float4*>(d->priors_cxcy);
+  q.prior_keep = d->prior_keep;
+  q.N = d->N; q.P = d->P; q.C = d->C;
+  q.act_kind = d->act_kind; q.box_kind = d->box_kind; q.clamp_inplace = d->clamp_inplace;
+  q.min_score = d->min_score; q.max_overlap = d->max_overlap; q.top_k = d->top_k;
+  q.second_thr = d->second_nms_thr; q.pre_nms_topk = d->pre_nms_topk;
+  q.out_boxes = d->out_boxes; q.out_labels = d->out_labels; q.out_scores = d->out_scores;
+  q.out_prior = d->out_prior; q.out_counts = d->out_counts; q.out_cap = d->out_cap;
+  level0_layout(d->min_score, &q.shift0, &q.n_bins);
+  q.cand_cap = cand_capacity(d);
+  q.kcap = kept_capacity(d);
+  unsigned char* w = static_cast<unsigned char*>(d->workspace);
+  q.cand_count = reinterpret_cast<unsigned int*>(w); w += align_up(size_t(q.N) * 4, 256);
+  q.hist = reinterpret_cast<unsigned int*>(w);       w += align_up(size_t(q.N) * kMaxBins * 4, 256);
+  q.class_seen = reinterpret_cast<unsigned int*>(w); w += align_up(size_t(q.N) * size_t(q.C) * 4, 256);
+  q.cand = reinterpret_cast<unsigned long long*>(w);
+  // hist rows are n_bins wide inside the kMaxBins-strided allocation
+  const DTiling t = choose_dtiling(q.C);
+  q.rows_per_tile = t.rows;
+  q.tiles_per_image = (q.P + t.rows - 1) / t.rows;
+  q.n_tiles = q.tiles_per_image * q.N;
+  q.n_stages = t.stages;
+  q.stage_floats = t.stage_floats;
+
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  static bool attr_done = false;
+  if (!attr_done) {
+    SBOD_CUDA_TRY(cudaFuncSetAttribute(detect_score_kernel,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    SBOD_CUDA_TRY(cudaFuncSetAttribute(detect_nms_kernel,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+    attr_done = true;
+  }
+  int ctas_per_sm = int((220 * 1024) / (t.smem + 2 * 1024));
+  if (ctas_per_sm < 1) ctas_per_sm = 1;
+  if (ctas_per_sm > 8) ctas_per_sm = 8;
+  int grid = sm_count() * ctas_per_sm;
+  if (grid > q.n_tiles) grid = q.n_tiles;
+  detect_score_kernel<<<grid, kDRows, t.smem, st>>>(q);
+  SBOD_LAUNCH_CHECK();
+  const size_t nms_smem = ((sizeof(NmsSmem) + 127) & ~size_t(127)) + size_t(q.kcap) * 25 + 256 +
+                          size_t(q.C + 1) * 4;
+  if (nms_smem > 220 * 1024) return SBOD_ERR_UNSUPPORTED;
+  detect_nms_kernel<<<q.N, kNmsThreads, nms_smem, st>>>(q);
+  SBOD_LAUNCH_CHECK();
+  return SBOD_OK;
+}

@@ -1,0 +1,1175 @@
+// loss.cu — the fused train path: assignment + log-sum-exp + loc/conf losses + hard-negative
+// mining, forward and backward (sm_100a).
+//
+// Kernels
+//   match_lse_kernel   persistent, one thread per prior row; score tiles streamed HBM->smem by
+//                      1-D bulk TMA through an mbarrier ring; while a tile is in flight the same
+//                      threads compute prior<->GT IoU (GT staged in smem, warp-bbox culled),
+//                      both arg-maxes, then the row log-sum-exp and the CE of the provisional class.
+//   forced_match_kernel per image: the reference's "every object keeps its best prior" override,
+//                      including its filtered-index quirk (SSD512.py:546-553), patches <= G priors.
+//   mine_kernel        per image: positives, loc loss, radix-select top-k sum of negative CE
+//                      (hard-negative mining), selection bits; last block folds the batch.
+//   mine_batch_kernel  SSD300's batch-global mining (SSD300.py:580-588).
+//   loss_bwd_kernel    grad wrt logits (softmax - onehot on selected rows, zero elsewhere, tiles
+//                      written with bulk TMA stores) and wrt locs.
+#include <math.h>
+
+#include "common.cuh"
+#include "pair_iou.cuh"
+
+namespace sbod {
+
+constexpr int kRows = 128;      // threads per CTA == max rows per streamed tile
+constexpr int kGtChunk = 256;   // GT boxes staged in smem at a time
+constexpr int kMaxStages = 4;
+constexpr int kMineThreads = 1024;
+constexpr int kBins = 4096;     // radix-select digit = 12 bits
+
+struct LossParams {
+  const float* locs;
+  const float* scores;
+  const float4* priors_cxcy;
+  const float4* priors_xy;
+  const float4* anchors_xy;  // per image, or null
+  const float4* gt_boxes;
+  const int64_t* gt_labels;
+  const int32_t* gt_offsets;
+  const uint8_t* exclude;
+  int N, P, C, gmax;
+  float thr_pos, thr_neg;
+  int reg_kind, cls_kind, binarize, ratio;
+  float reg_weight, beta, falpha, fgamma;
+  float* ov;
+  int32_t* obj;
+  float* lse;
+  float* ce;
+  uint8_t* sel;
+  double* partials;
+  double* sums;
+  float* loss;
+  // workspace
+  unsigned long long* gtkey;  // [N, gmax]
+  float* cand;                // [N, P]
+  unsigned int* counters;     // [4]
+  // tiling
+  int rows_per_tile, tiles_per_image, n_tiles, n_stages;
+  uint32_t stage_floats;
+  int with_scores;
+};
+
+SBOD_DEVINL int64_t map_label(const LossParams& q, int64_t lab) {
+  return q.binarize ? (lab > 0 ? 1 : 0) : lab;
+}
+
+// ------------------------------------------------------------------------------------------
+// match_lse_kernel
+// ------------------------------------------------------------------------------------------
+struct TileCoord {
+  int n, p0, rows;
+};
+SBOD_DEVINL TileCoord tile_coord(const LossParams& q, int tile) {
+  TileCoord t;
+  t.n = tile / q.tiles_per_image;
+  t.p0 = (tile - t.n * q.tiles_per_image) * q.rows_per_tile;
+  t.rows = min(q.rows_per_tile, q.P - t.p0);
+  return t;
+}
+
+SBOD_DEVINL void issue_tile_load(const LossParams& q, int tile, float* stage, uint64_t* bar) {
+  const TileCoord t = tile_coord(q, tile);
+  const size_t first = (size_t(t.n) * q.P + t.p0) * size_t(q.C);
+  const size_t total = size_t(q.N) * q.P * size_t(q.C);
+  const TileSpan s = make_tile_span(q.scores, first, size_t(t.rows) * q.C, total);
+  for (uint32_t i = 0; i < s.tail_floats; ++i)
+    stage[s.bulk_bytes / 4 + i] = q.scores[(s.src16 - q.scores) + s.bulk_bytes / 4 + i];
+  if (s.bulk_bytes) {
+    mbar_arrive_expect_tx(bar, s.bulk_bytes);
+    tma_load_1d(stage, s.src16, s.bulk_bytes, bar);
+  } else {
+    mbar_arrive(bar);
+  }
+}
+
+__global__ void __launch_bounds__(kRows) match_lse_kernel(const LossParams q) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  float* stages = reinterpret_cast<float*>(smem_raw);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + size_t(q.n_stages) * q.stage_floats * 4);
+
+  __shared__ float4 s_gbox[kGtChunk];
+  __shared__ float s_garea[kGtChunk];
+  __shared__ unsigned long long s_gkey[kGtChunk];
+  __shared__ uint8_t s_gskip[kGtChunk];
+
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int n_my = (q.n_tiles - int(blockIdx.x) + int(gridDim.x) - 1) / int(gridDim.x);
+
+  if (q.with_scores) {
+    if (tid == 0) {
+      for (int s = 0; s < q.n_stages; ++s) mbar_init(&bars[s], 1);
+      fence_mbar_init();
+    }
+    __syncthreads();
+    if (tid == 0) {
+      for (int s = 0; s < q.n_stages && s < n_my; ++s)
+        issue_tile_load(q, blockIdx.x + s * gridDim.x, stages + size_t(s) * q.stage_floats, &bars[s]);
+    }
+  }
+
+  // rotation that makes the per-thread row walk bank-conflict free for even C
+  int gcd = 1;
+  while (gcd < 32 && (q.C % (gcd * 2)) == 0) gcd *= 2;
+  const int rot = (lane * gcd) >> 5;
+
+  for (int it = 0; it < n_my; ++it) {
+    const int tile = blockIdx.x + it * gridDim.x;
+    const TileCoord tc = tile_coord(q, tile);
+    const int n = tc.n;
+    const int g0 = q.gt_offsets[n];
+    const int G = q.gt_offsets[n + 1] - g0;
+    const bool valid = tid < tc.rows;
+    const int p = tc.p0 + tid;
+    const size_t np = size_t(n) * q.P + (valid ? p : tc.p0);
+
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (valid) a = q.anchors_xy ? q.anchors_xy[np] : q.priors_xy[p];
+    const float aa = box_area_rn(a);
+    const bool azero = anchor_is_zero(a);
+    const bool a_ok = (a.z >= a.x) && (a.w >= a.y);
+    const bool active = valid && !azero;
+
+    // warp bounding box of the active priors, for GT culling
+    const float INF = __int_as_float(0x7f800000);
+    const float bx1 = warp_min(active ? a.x : INF), by1 = warp_min(active ? a.y : INF);
+    const float bx2 = warp_max(active ? a.z : -INF), by2 = warp_max(active ? a.w : -INF);
+
+    // running arg-max over objects, first index wins (torch.max semantics, metrics/SSD512.py:538)
+    float best = -INF;
+    int bobj = 0;
+
+    for (int c0 = 0; c0 < G; c0 += kGtChunk) {
+      const int gc = min(kGtChunk, G - c0);
+      __syncthreads();
+      bool g_ok = true;
+      for (int i = tid; i < gc; i += kRows) {
+        const float4 g = q.gt_boxes[g0 + c0 + i];
+        s_gbox[i] = g;
+        s_garea[i] = box_area_rn(g);
+        s_gskip[i] = gt_is_zero(g) ? 1 : 0;
+        s_gkey[i] = 0ull;
+        g_ok = g_ok && (g.z >= g.x) && (g.w >= g.y);
+      }
+      // With non-negative widths/heights everywhere a pair that does not intersect is exactly +0,
+      // so objects outside the warp's bounding box can be skipped without changing any result.
+      const bool chunk_ok = __syncthreads_and(int(g_ok && (a_ok || !valid))) != 0;
+
+      if (chunk_ok) {
+        float cbest = azero ? -1.f : 0.f;  // value of every culled / zero-size object
+        int cidx = c0;
+        for (int base = 0; base < gc; base += 32) {
+          const int i = base + lane;
+          bool hit = false;
+          if (i < gc && !s_gskip[i]) {
+            const float4 g = s_gbox[i];
+            hit = (g.z > bx1) && (g.x < bx2) && (g.w > by1) && (g.y < by2);
+          }
+          unsigned m = __ballot_sync(0xffffffffu, hit);
+          while (m) {
+            const int j = base + (__ffs(m) - 1);
+            m &= m - 1;
+            if (active) {
+              const float iou = iou_metrics_rn(s_gbox[j], s_garea[j], a, aa);
+              if (iou > cbest) {
+                cbest = iou;
+                cidx = c0 + j;
+              }
+              if (iou > 0.f) {
+                const unsigned long long key =
+                    (static_cast<unsigned long long>(__float_as_uint(iou)) << 32) |
+                    (0xffffffffu - unsigned(p));
+                if (key > s_gkey[j]) atomicMax(&s_gkey[j], key);
+              }
+            }
+          }
+        }
+        if (cbest > best) {
+          best = cbest;
+          bobj = cidx;
+        }
+      } else if (valid) {
+        // general path: every pair, masks applied as the reference does (metrics.py:249-250)
+        for (int j = 0; j < gc; ++j) {
+          float iou = iou_metrics_rn(s_gbox[j], s_garea[j], a, aa);
+          if (s_gskip[j]) iou = 0.f;
+          if (azero) iou = -1.f;
+          if (iou > best) {
+            best = iou;
+            bobj = c0 + j;
+          }
+          if (iou > 0.f) {
+            const unsigned long long key =
+                (static_cast<unsigned long long>(__float_as_uint(iou)) << 32) |
+                (0xffffffffu - unsigned(p));
+            if (key > s_gkey[j]) atomicMax(&s_gkey[j], key);
+          }
+        }
+      }
+      __syncthreads();
+      for (int i = tid; i < gc; i += kRows) {
+        const unsigned long long k = s_gkey[i];
+        if (k) atomicMax(&q.gtkey[size_t(n) * q.gmax + c0 + i], k);
+      }
+    }
+    if (G == 0) {  // the reference raises on an image without objects; we define "all background"
+      best = 0.f;
+      bobj = 0;
+    }
+
+    if (!q.with_scores) {
+      if (valid) {
+        q.ov[np] = best;
+        q.obj[np] = bobj;
+      }
+      continue;
+    }
+
+    // ---- scores tile: log-sum-exp + CE against the provisional class ----
+    const int s = it % q.n_stages;
+    float* stage = stages + size_t(s) * q.stage_floats;
+    mbar_wait(&bars[s], (it / q.n_stages) & 1);
+    if (valid) {
+      const size_t first = (size_t(n) * q.P + tc.p0) * size_t(q.C);
+      const float* row = stage + (first & 3) + size_t(tid) * q.C;
+      const int C = q.C;
+      float m0 = -INF, m1 = -INF, m2 = -INF, m3 = -INF;
+      int k = rot;
+      for (; k + 3 < C; k += 4) {
+        m0 = fmaxf(m0, row[k]);
+        m1 = fmaxf(m1, row[k + 1]);
+        m2 = fmaxf(m2, row[k + 2]);
+        m3 = fmaxf(m3, row[k + 3]);
+      }
+      for (; k < C; ++k) m0 = fmaxf(m0, row[k]);
+      for (k = 0; k < rot; ++k) m1 = fmaxf(m1, row[k]);
+      const float mx = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
+      float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+      k = rot;
+      for (; k + 3 < C; k += 4) {
+        s0 += __expf(row[k] - mx);
+        s1 += __expf(row[k + 1] - mx);
+        s2 += __expf(row[k + 2] - mx);
+        s3 += __expf(row[k + 3] - mx);
+      }
+      for (; k < C; ++k) s0 += __expf(row[k] - mx);
+      for (k = 0; k < rot; ++k) s1 += __expf(row[k] - mx);
+      const float lg = logf((s0 + s1) + (s2 + s3));
+      int64_t lab = 0;
+      if (G > 0) lab = map_label(q, q.gt_labels[g0 + bobj]);
+      int cls = (best < q.thr_pos || G == 0) ? 0 : int(lab);
+      cls = min(max(cls, 0), C - 1);
+      const float xt = row[cls];
+      q.ov[np] = best;
+      q.obj[np] = bobj;
+      q.lse[np] = mx + lg;
+      q.ce[np] = (mx - xt) + lg;  // == -log_softmax[cls], torch's operation order
+    }
+    __syncthreads();  // every thread is done with stage s
+    if (tid == 0 && it + q.n_stages < n_my)
+      issue_tile_load(q, blockIdx.x + (it + q.n_stages) * gridDim.x, stage, &bars[s]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// forced_match_kernel: one CTA per image
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) forced_match_kernel(const LossParams q) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  uint32_t* s_prior = reinterpret_cast<uint32_t*>(smem_raw);  // [gmax]
+  int32_t* s_rank = reinterpret_cast<int32_t*>(s_prior + q.gmax);  // [gmax], -1 = filtered out
+  __shared__ int s_warp_tot[8];
+  __shared__ int s_carry;
+
+  const int n = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int g0 = q.gt_offsets[n];
+  const int G = q.gt_offsets[n + 1] - g0;
+  if (tid == 0) s_carry = 0;
+  __syncthreads();
+  // rank j of each object inside the filtered list "objects whose best overlap is > 0"
+  for (int base = 0; base < G; base += 256) {
+    const int g = base + tid;
+    unsigned long long key = 0ull;
+    if (g < G) {
+      key = q.gtkey[size_t(n) * q.gmax + g];
+      q.gtkey[size_t(n) * q.gmax + g] = 0ull;  // leave the workspace clean for the next call
+    }
+    const bool f = key != 0ull;
+    const unsigned bal = __ballot_sync(0xffffffffu, f);
+    const int in_warp = __popc(bal & ((1u << lane) - 1u));
+    if (lane == 0) s_warp_tot[wid] = __popc(bal);
+    __syncthreads();
+    int off = s_carry;
+    for (int w = 0; w < wid; ++w) off += s_warp_tot[w];
+    if (g < G) {
+      s_prior[g] = 0xffffffffu - uint32_t(key & 0xffffffffull);
+      s_rank[g] = f ? off + in_warp : -1;
+    }
+    __syncthreads();
+    if (tid == 0) {
+      int t = 0;
+      for (int w = 0; w < 8; ++w) t += s_warp_tot[w];
+      s_carry += t;
+    }
+    __syncthreads();
+  }
+  for (int g = tid; g < G; g += 256) {
+    const int j = s_rank[g];
+    if (j < 0) continue;
+    const uint32_t p = s_prior[g];
+    bool winner = true;  // "for j: obj[pr[j]] = j" -> the last j wins
+    for (int h = g + 1; h < G; ++h)
+      if (s_rank[h] >= 0 && s_prior[h] == p) {
+        winner = false;
+        break;
+      }
+    const size_t np = size_t(n) * q.P + p;
+    q.ov[np] = 1.0f;
+    if (winner) {
+      q.obj[np] = j;
+      if (q.with_scores) {
+        const int64_t lab = map_label(q, q.gt_labels[g0 + j]);
+        int cls = (1.0f < q.thr_pos) ? 0 : int(lab);
+        cls = min(max(cls, 0), q.C - 1);
+        q.ce[np] = q.lse[np] - q.scores[np * q.C + cls];
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// loc loss of one positive prior
+// ------------------------------------------------------------------------------------------
+struct LocTerm {
+  float loss;
+  float4 grad;  // d loss / d predicted loc (gcx, gcy, gw, gh)
+};
+
+template <bool WITH_GRAD>
+SBOD_DEVINL LocTerm loc_term(const LossParams& q, const float4 pred, const float4 pri /*cxcy*/,
+                             const float4 box /*xyxy*/) {
+  LocTerm r;
+  r.loss = 0.f;
+  r.grad = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (q.reg_kind == SBOD_REG_L1_ELEM_MEAN || q.reg_kind == SBOD_REG_SMOOTH_L1) {
+    // cxcy_to_gcxgcy(xy_to_cxcy(box), prior): transforms.py:26-34,48-66
+    const float cx = (box.z + box.x) / 2.f, cy = (box.w + box.y) / 2.f;
+    const float w = box.z - box.x, h = box.w - box.y;
+    float t[4] = {(cx - pri.x) / (pri.z / 10.f), (cy - pri.y) / (pri.w / 10.f),
+                  logf(w / pri.z) * 5.f, logf(h / pri.w) * 5.f};
+    const float pv[4] = {pred.x, pred.y, pred.z, pred.w};
+    float gv[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float d = pv[i] - t[i];
+      const float x = fabsf(d);
+      const float sgn = d > 0.f ? 1.f : (d < 0.f ? -1.f : 0.f);
+      if (q.reg_kind == SBOD_REG_L1_ELEM_MEAN) {
+        r.loss += x;
+        gv[i] = sgn;
+      } else if (x >= q.beta) {  // Loss.py:214-217
+        r.loss += x - 0.5f * q.beta;
+        gv[i] = sgn;
+      } else {
+        r.loss += 0.5f * x * x / q.beta;
+        gv[i] = d / q.beta;
+      }
+    }
+    if (WITH_GRAD) r.grad = make_float4(gv[0], gv[1], gv[2], gv[3]);
+  } else {
+    // decoded = cxcy_to_xy(gcxgcy_to_cxcy(pred, prior)): transforms.py:37-45,69-83
+    const float cx = pred.x * pri.z / 10.f + pri.x, cy = pred.y * pri.w / 10.f + pri.y;
+    const float w = __expf(pred.z / 5.f) * pri.z, h = __expf(pred.w / 5.f) * pri.w;
+    const float4 dec = make_float4(cx - w / 2.f, cy - h / 2.f, cx + w / 2.f, cy + h / 2.f);
+    const int kind = q.reg_kind - SBOD_REG_IOU;
+    PairGrad pg;
+    const float v = pair_overlap<WITH_GRAD>(dec, box, kind, &pg);
+    r.loss = 1.0f - v;
+    if (WITH_GRAD) {
+      const float4 d = make_float4(-pg.d1.x, -pg.d1.y, -pg.d1.z, -pg.d1.w);
+      r.grad.x = (d.x + d.z) * pri.z / 10.f;
+      r.grad.y = (d.y + d.w) * pri.w / 10.f;
+      r.grad.z = (d.z - d.x) * 0.5f * w / 5.f;
+      r.grad.w = (d.w - d.y) * 0.5f * h / 5.f;
+    }
+  }
+  return r;
+}
+
+SBOD_DEVINL float4 prior_cxcy_of(const LossParams& q, int n, int p) {
+  if (q.anchors_xy) {  // RefineDet ODM: xy_to_cxcy(decoded ARM box), RefineDet512.py:885-886
+    const float4 a = q.anchors_xy[size_t(n) * q.P + p];
+    return make_float4((a.z + a.x) / 2.f, (a.w + a.y) / 2.f, a.z - a.x, a.w - a.y);
+  }
+  return q.priors_cxcy[p];
+}
+
+// softmax focal terms as functions of ce = -log p_t (Loss.py:9-38)
+SBOD_DEVINL float focal_fg(const LossParams& q, float ce) {  // alpha * (1-p)^gamma * ce
+  const float pt = __expf(-ce);
+  return q.falpha * powf(1.f - pt, q.fgamma) * ce;
+}
+SBOD_DEVINL float focal_bg(const LossParams& q, float ce) {  // (1-alpha) * p0^gamma * ce  (Loss.py:32)
+  const float pt = __expf(-ce);
+  return (1.f - q.falpha) * powf(pt, q.fgamma) * ce;
+}
+
+// ------------------------------------------------------------------------------------------
+// radix select: sum of the k largest candidate values of vals[0..n) (candidates are >= 0,
+// non-candidates are < 0). Returns the sum in every thread; writes threshold bits / number of
+// ties to take so the caller can build the selection mask.
+// ------------------------------------------------------------------------------------------
+struct SelectResult {
+  double sum;
+  uint32_t thr_bits;  // value of the k-th largest
+  int take_ties;      // how many values == thr are part of the top-k
+  int n_ties;         // how many candidates == thr exist
+  int k_eff;
+};
+
+__device__ SelectResult topk_sum(const float* __restrict__ vals, int n, long long k_want,
+                                 unsigned int* s_hist /*[kBins]*/, double* s_red /*[34]*/,
+                                 int* s_misc /*[8]*/) {
+  const int tid = threadIdx.x, nt = blockDim.x;
+  SelectResult r;
+  r.sum = 0.0; r.thr_bits = 0; r.take_ties = 0; r.n_ties = 0; r.k_eff = 0;
+  // number of candidates
+  int cnt = 0;
+  for (int i = tid; i < n; i += nt) cnt += vals[i] >= 0.f ? 1 : 0;
+  const int n_cand = int(block_sum(double(cnt), s_red) + 0.5);
+  long long k = k_want < (long long)n_cand ? k_want : (long long)n_cand;
+  r.k_eff = int(k);
+  if (k <= 0) return r;
+
+  uint32_t prefix = 0, mask = 0;
+  int remaining = int(k);
+  const int shifts[3] = {20, 8, 0};
+  const int widths[3] = {12, 12, 8};
+  for (int pass = 0; pass < 3; ++pass) {
+    const int shift = shifts[pass];
+    const uint32_t dmask = (1u << widths[pass]) - 1u;
+    const int nb = 1 << widths[pass];
+    for (int b = tid; b < nb; b += nt) s_hist[b] = 0u;
+    __syncthreads();
+    for (int i = tid; i < n; i += nt) {
+      const float v = vals[i];
+      if (v >= 0.f) {
+        const uint32_t bits = __float_as_uint(v);
+        if ((bits & mask) == prefix) atomicAdd(&s_hist[(bits >> shift) & dmask], 1u);
+      }
+    }
+    __syncthreads();
+    // find digit d (from the top) with  count(>d) < remaining <= count(>=d)
+    // each thread owns a contiguous run of bins, highest bins first
+    const int per = (nb + nt - 1) / nt;
+    const int hi = nb - 1 - tid * per;  // my bins: hi, hi-1, ..., hi-per+1
+    unsigned int mine = 0;
+    for (int j = 0; j < per; ++j) {
+      const int b = hi - j;
+      if (b >= 0) mine += s_hist[b];
+    }
+    // exclusive prefix over threads (thread order == descending bins)
+    const int lane = tid & 31, wid = tid >> 5;
+    unsigned int inc = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const unsigned int t = __shfl_up_sync(0xffffffffu, inc, o);
+      if (lane >= o) inc += t;
+    }
+    unsigned int* s_wt = reinterpret_cast<unsigned int*>(s_red);  // [<=32]
+    __syncthreads();
+    if (lane == 31) s_wt[wid] = inc;
+    __syncthreads();
+    unsigned int before = inc - mine;
+    for (int w = 0; w < wid; ++w) before += s_wt[w];
+    if (before < unsigned(remaining) && unsigned(remaining) <= before + mine) {
+      unsigned int acc = before;
+      for (int j = 0; j < per; ++j) {
+        const int b = hi - j;
+        const unsigned int h = b >= 0 ? s_hist[b] : 0u;
+        if (acc < unsigned(remaining) && unsigned(remaining) <= acc + h) {
+          s_misc[0] = b;
+          s_misc[1] = remaining - int(acc);
+          s_misc[2] = int(h);
+          break;
+        }
+        acc += h;
+      }
+    }
+    __syncthreads();
+    prefix |= uint32_t(s_misc[0]) << shift;
+    mask |= dmask << shift;
+    remaining = s_misc[1];
+    r.n_ties = s_misc[2];
+    __syncthreads();
+  }
+  r.thr_bits = prefix;
+  r.take_ties = remaining;
+  const float thr = __uint_as_float(prefix);
+  double acc = 0.0;
+  for (int i = tid; i < n; i += nt) {
+    const float v = vals[i];
+    if (v > thr) acc += double(v);
+  }
+  r.sum = block_sum(acc, s_red) + double(remaining) * double(thr);
+  return r;
+}
+
+// mark selected negatives: v > thr, plus the first `take_ties` candidates equal to thr
+__device__ void mark_selected(const float* __restrict__ vals, uint8_t* __restrict__ sel, int n,
+                              const SelectResult& r, int* s_misc) {
+  if (r.k_eff <= 0) return;
+  const int tid = threadIdx.x, nt = blockDim.x;
+  const float thr = __uint_as_float(r.thr_bits);
+  const bool all_ties = r.take_ties >= r.n_ties;
+  for (int i = tid; i < n; i += nt) {
+    const float v = vals[i];
+    if (v > thr || (all_ties && v == thr)) sel[i] |= 2;
+  }
+  if (!all_ties) {  // rare: pick ties by ascending index (deterministic)
+    __syncthreads();
+    if (tid == 0) {
+      int left = r.take_ties;
+      for (int i = 0; i < n && left > 0; ++i)
+        if (vals[i] == thr) {
+          sel[i] |= 2;
+          --left;
+        }
+    }
+  }
+}
+
+SBOD_DEVINL void finalize_loss(const LossParams& q, const double* sums, float* loss) {
+  const double s_loc = sums[0], s_pos = sums[1], s_neg = sums[2], npos = sums[3];
+  double loc, conf;
+  if (q.reg_kind == SBOD_REG_L1_ELEM_MEAN) loc = s_loc / (4.0 * npos);
+  else loc = s_loc / npos;
+  if (q.cls_kind == SBOD_CLS_FOCAL_SUM) conf = s_pos + s_neg;
+  else conf = (s_pos + s_neg) / npos;
+  loss[0] = float(conf + double(q.reg_weight) * loc);
+  loss[1] = float(conf);
+  loss[2] = float(loc);
+  loss[3] = float(npos);
+}
+
+__global__ void __launch_bounds__(kMineThreads) mine_kernel(const LossParams q) {
+  __shared__ unsigned int s_hist[kBins];
+  __shared__ double s_red[34];
+  __shared__ int s_misc[8];
+  const int n = blockIdx.x, tid = threadIdx.x;
+  const int g0 = q.gt_offsets[n];
+  const int G = q.gt_offsets[n + 1] - g0;
+  const size_t base = size_t(n) * q.P;
+  const bool focal = q.cls_kind == SBOD_CLS_FOCAL_SUM || q.cls_kind == SBOD_CLS_FOCAL_NORM;
+
+  double a_loc = 0.0, a_pos = 0.0, a_neg = 0.0;
+  int npos = 0;
+  for (int p = tid; p < q.P; p += kMineThreads) {
+    const float ov = q.ov[base + p];
+    const int obj = q.obj[base + p];
+    const float ce = q.ce[base + p];
+    const bool ex = q.exclude ? q.exclude[base + p] != 0 : false;
+    int64_t lab = 0;
+    if (G > 0) lab = map_label(q, q.gt_labels[g0 + obj]);
+    const int64_t cls = (ov < q.thr_pos) ? 0 : lab;
+    const bool pos = cls > 0 && !ex;
+    const bool isneg = ov < q.thr_neg;
+    uint8_t selbits = 0;
+    float v = -1.f;
+    if (pos) {
+      selbits = 1;
+      ++npos;
+      a_pos += focal ? double(focal_fg(q, ce)) : double(ce);
+      const float4 pred = reinterpret_cast<const float4*>(q.locs)[base + p];
+      const LocTerm lt = loc_term<false>(q, pred, prior_cxcy_of(q, n, p), q.gt_boxes[g0 + obj]);
+      a_loc += double(lt.loss);
+    }
+    if (focal) {
+      if (isneg && !pos) {  // target class is 0 there (thr_neg < thr_pos)
+        selbits |= 2;
+        a_neg += double(focal_bg(q, ce));
+      }
+    } else if (q.cls_kind == SBOD_CLS_CE_MINE_NONPOS) {
+      if (!pos && !ex) v = ce;
+    } else {  // MINE_NEG, MINE_BATCH: only true_neg == -1 rows are candidates
+      if (isneg && !pos) v = ce;
+    }
+    q.sel[base + p] = selbits;
+    q.cand[base + p] = v;
+  }
+  const double t_loc = block_sum(a_loc, s_red);
+  const double t_pos = block_sum(a_pos, s_red);
+  const double t_npos = block_sum(double(npos), s_red);
+  double t_neg;
+  if (focal) {
+    t_neg = block_sum(a_neg, s_red);
+  } else if (q.cls_kind == SBOD_CLS_CE_MINE_BATCH) {
+    t_neg = 0.0;  // filled by mine_batch_kernel
+  } else {
+    __syncthreads();
+    const long long k = (long long)(q.ratio) * (long long)(t_npos + 0.5);
+    const SelectResult r = topk_sum(q.cand + base, q.P, k, s_hist, s_red, s_misc);
+    mark_selected(q.cand + base, q.sel + base, q.P, r, s_misc);
+    t_neg = r.sum;
+  }
+  if (tid == 0) {
+    q.partials[n * 4 + 0] = t_loc;
+    q.partials[n * 4 + 1] = t_pos;
+    q.partials[n * 4 + 2] = t_neg;
+    q.partials[n * 4 + 3] = t_npos;
+    __threadfence();
+    const unsigned int ticket = atomicAdd(&q.counters[0], 1u);
+    s_misc[7] = (ticket == unsigned(q.N) - 1u) ? 1 : 0;
+  }
+  __syncthreads();
+  if (s_misc[7] && tid < 4) {  // last block folds the batch in image order (deterministic)
+    __threadfence();
+    double acc = 0.0;
+    const volatile double* pp = q.partials;
+    for (int i = 0; i < q.N; ++i) acc += pp[i * 4 + tid];
+    q.sums[tid] = acc;
+  }
+  __syncthreads();
+  if (s_misc[7] && tid == 0) {
+    q.counters[0] = 0u;
+    if (q.cls_kind != SBOD_CLS_CE_MINE_BATCH) finalize_loss(q, q.sums, q.loss);
+  }
+}
+
+// SSD300's batch-global mining: top sum(3*n_pos) over every true_neg==-1 row of the batch
+__global__ void __launch_bounds__(kMineThreads) mine_batch_kernel(const LossParams q) {
+  __shared__ unsigned int s_hist[kBins];
+  __shared__ double s_red[34];
+  __shared__ int s_misc[8];
+  const long long total = (long long)q.N * q.P;
+  const long long k = (long long)(q.ratio) * (long long)(q.sums[3] + 0.5);
+  // (n = N*P fits int for every supported shape; checked on the host)
+  const SelectResult r = topk_sum(q.cand, int(total), k, s_hist, s_red, s_misc);
+  mark_selected(q.cand, q.sel, int(total), r, s_misc);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    q.sums[2] = r.sum;
+    finalize_loss(q, q.sums, q.loss);
+  }
+}
+
+__global__ void finalize_kernel(const LossParams q) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) finalize_loss(q, q.sums, q.loss);
+}
+
+// ------------------------------------------------------------------------------------------
+// loss_bwd_kernel: one CTA per tile of rows_per_tile priors.
+//   sparse mode (CE + mining): rows are zero except positives / mined negatives
+//   dense mode (focal): most rows carry gradient -> tile loaded with TMA, transformed in place
+// ------------------------------------------------------------------------------------------
+struct BwdParams {
+  LossParams q;
+  const float* grad_loss;
+  float* grad_locs;
+  float* grad_scores;
+  int dense;
+};
+
+__global__ void __launch_bounds__(kRows) loss_bwd_kernel(const BwdParams bp) {
+  const LossParams& q = bp.q;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  float* tilebuf = reinterpret_cast<float*>(smem_raw);
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw + size_t(q.stage_floats) * 4);
+  __shared__ int s_cls[kRows];
+  __shared__ uint8_t s_sel[kRows];
+
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const double npos_tot = q.sums[3];
+  const float gout = bp.grad_loss ? *bp.grad_loss : 1.f;
+  const bool focal = q.cls_kind == SBOD_CLS_FOCAL_SUM || q.cls_kind == SBOD_CLS_FOCAL_NORM;
+  const float conf_scale =
+      (q.cls_kind == SBOD_CLS_FOCAL_SUM) ? gout : float(double(gout) / npos_tot);
+  const float loc_scale = float(double(gout) * double(q.reg_weight) /
+                                (q.reg_kind == SBOD_REG_L1_ELEM_MEAN ? 4.0 * npos_tot : npos_tot));
+  if (bp.dense && tid == 0) {
+    mbar_init(bar, 1);
+    fence_mbar_init();
+  }
+  __syncthreads();
+
+  int phase = 0;
+  for (int tile = blockIdx.x; tile < q.n_tiles; tile += gridDim.x) {
+    const TileCoord tc = tile_coord(q, tile);
+    const int n = tc.n;
+    const int g0 = q.gt_offsets[n];
+    const int G = q.gt_offsets[n + 1] - g0;
+    const bool valid = tid < tc.rows;
+    const int p = tc.p0 + tid;
+    const size_t np = size_t(n) * q.P + (valid ? p : tc.p0);
+    const size_t first = (size_t(n) * q.P + tc.p0) * size_t(q.C);
+    const size_t n_elem = size_t(tc.rows) * q.C;
+    const size_t total = size_t(q.N) * q.P * size_t(q.C);
+    const uint32_t head = uint32_t(first & 3);
+
+    // the previous tile's bulk store must have finished reading smem before we overwrite it
+    if (tid == 0) tma_store_wait_read<0>();
+    __syncthreads();
+    if (bp.dense && tid == 0) {
+      const TileSpan s = make_tile_span(q.scores, first, n_elem, total);
+      for (uint32_t i = 0; i < s.tail_floats; ++i)
+        tilebuf[s.bulk_bytes / 4 + i] = q.scores[(s.src16 - q.scores) + s.bulk_bytes / 4 + i];
+      if (s.bulk_bytes) {
+        mbar_arrive_expect_tx(bar, s.bulk_bytes);
+        tma_load_1d(tilebuf, s.src16, s.bulk_bytes, bar);
+      } else {
+        mbar_arrive(bar);
+      }
+    }
+
+    // per-row bookkeeping + grad wrt locs
+    uint8_t selbits = 0;
+    int cls = 0;
+    if (valid) {
+      selbits = q.sel[np];
+      const float ov = q.ov[np];
+      const int obj = q.obj[np];
+      int64_t lab = 0;
+      if (G > 0) lab = map_label(q, q.gt_labels[g0 + obj]);
+      cls = (ov < q.thr_pos) ? 0 : int(lab);
+      cls = min(max(cls, 0), q.C - 1);
+      float4 gl = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (selbits & 1) {
+        const float4 pred = reinterpret_cast<const float4*>(q.locs)[np];
+        const LocTerm lt = loc_term<true>(q, pred, prior_cxcy_of(q, n, p), q.gt_boxes[g0 + obj]);
+        gl = make_float4(lt.grad.x * loc_scale, lt.grad.y * loc_scale, lt.grad.z * loc_scale,
+                         lt.grad.w * loc_scale);
+      }
+      if (bp.grad_locs) reinterpret_cast<float4*>(bp.grad_locs)[np] = gl;
+    }
+    s_sel[tid] = valid ? selbits : 0;
+    s_cls[tid] = cls;
+
+    if (!bp.grad_scores) continue;
+
+    if (!bp.dense) {
+      // zero the tile, then patch the selected rows (a warp per row, coalesced over classes)
+      float4* t4 = reinterpret_cast<float4*>(tilebuf);
+      const int n4 = int((head + n_elem + 3) / 4);
+      for (int i = tid; i < n4; i += kRows) t4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      __syncthreads();
+      for (int r = wid; r < tc.rows; r += kRows / 32) {
+        if (!s_sel[r]) continue;
+        const size_t rnp = size_t(n) * q.P + tc.p0 + r;
+        const float lse = q.lse[rnp];
+        const int rc = s_cls[r];
+        const float* x = q.scores + rnp * q.C;
+        float* o = tilebuf + head + size_t(r) * q.C;
+        for (int k = lane; k < q.C; k += 32)
+          o[k] = conf_scale * (__expf(x[k] - lse) - (k == rc ? 1.f : 0.f));
+      }
+    } else {
+      mbar_wait(bar, phase);
+      phase ^= 1;
+      if (valid) {
+        float* row = tilebuf + head + size_t(tid) * q.C;
+        const float lse = q.lse[np];
+        int gcd = 1;
+        while (gcd < 32 && (q.C % (gcd * 2)) == 0) gcd *= 2;
+        const int rot = (lane * gcd) >> 5;
+        float coef_soft = 0.f, coef_hot = 0.f;  // grad = coef_soft*softmax - coef_hot*onehot
+        if (selbits) {
+          if (focal) {
+            // L = A * w(pt)^g * ce ; ce = -log pt ; d ce/dx_k = softmax_k - onehot_k ; d pt/dx_k = -pt*(..)
+            const float pt = __expf(q.scores[np * q.C + cls] - lse);
+            const float ce = q.ce[np];
+            float dL_dce;
+            if (selbits & 1) {  // foreground: A=alpha, w = 1-pt  -> dw/dce = pt
+              const float w = 1.f - pt;
+              dL_dce = q.falpha * (powf(w, q.fgamma) +
+                                   ce * q.fgamma * powf(w, q.fgamma - 1.f) * pt);
+            } else {  // background: A=1-alpha, w = pt -> dw/dce = -pt
+              dL_dce = (1.f - q.falpha) * (powf(pt, q.fgamma) -
+                                           ce * q.fgamma * powf(pt, q.fgamma - 1.f) * pt);
+            }
+            coef_soft = coef_hot = conf_scale * dL_dce;
+          } else {
+            coef_soft = coef_hot = conf_scale;
+          }
+        }
+        for (int kk = 0; kk < q.C; ++kk) {
+          int k = kk + rot;
+          if (k >= q.C) k -= q.C;
+          const float sm = __expf(row[k] - lse);
+          row[k] = coef_soft * sm - (k == cls ? coef_hot : 0.f);
+        }
+      }
+    }
+    fence_proxy_async();
+    __syncthreads();
+    if (tid == 0) {
+      // aligned interior by bulk store; ragged head/tail by plain stores
+      const size_t e0 = first, e1 = first + n_elem;
+      const size_t a0 = (e0 + 3) & ~size_t(3), a1 = e1 & ~size_t(3);
+      const size_t s0 = e0 & ~size_t(3);  // smem index 0 <-> global element s0
+      if (a1 > a0) {
+        tma_store_1d(bp.grad_scores + a0, tilebuf + (a0 - s0), uint32_t((a1 - a0) * 4));
+        tma_store_commit();
+      }
+      for (size_t e = e0; e < (a0 < e1 ? a0 : e1); ++e) bp.grad_scores[e] = tilebuf[e - s0];
+      for (size_t e = (a1 > a0 ? a1 : (a0 < e1 ? a0 : e1)); e < e1; ++e)
+        bp.grad_scores[e] = tilebuf[e - s0];
+    }
+  }
+  if (tid == 0) tma_store_wait_all<0>();
+}
+
+// expand the per-prior state into the reference's int64 tensors
+__global__ void targets_kernel(const LossParams q, int64_t* cls_out, int64_t* neg_out) {
+  const size_t total = size_t(q.N) * q.P;
+  for (size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x; i < total;
+       i += size_t(gridDim.x) * blockDim.x) {
+    const int n = int(i / q.P);
+    const int g0 = q.gt_offsets[n];
+    const int G = q.gt_offsets[n + 1] - g0;
+    const float ov = q.ov[i];
+    int64_t lab_raw = 0;
+    if (G > 0) lab_raw = q.gt_labels[g0 + q.obj[i]];
+    int64_t lab = (ov < q.thr_pos) ? 0 : lab_raw;
+    if (q.binarize) lab = lab > 0 ? 1 : 0;  // RefineDet512.py:778-781: threshold first, then binarise
+    if (cls_out) cls_out[i] = lab;
+    if (neg_out) neg_out[i] = (ov < q.thr_neg) ? -1 : lab_raw;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------
+static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+struct Tiling {
+  int rows, stages;
+  uint32_t stage_floats;
+  size_t smem;
+};
+
+static Tiling choose_tiling(int C, int max_stages) {
+  Tiling t;
+  const size_t budget = 100 * 1024;  // two CTAs per SM
+  t.rows = kRows;
+  while (t.rows > 4 && (size_t(t.rows) * C + 8) * 4 > budget) t.rows /= 2;
+  t.stage_floats = uint32_t(align_up(size_t(t.rows) * C + 8, 32));
+  t.stages = int(budget / (size_t(t.stage_floats) * 4));
+  if (t.stages > max_stages) t.stages = max_stages;
+  if (t.stages < 1) t.stages = 1;
+  t.smem = size_t(t.stages) * t.stage_floats * 4 + kMaxStages * 8;
+  return t;
+}
+
+static int fill_params(const sbod_loss_desc* d, LossParams& q, bool need_scores) {
+  if (!d) return SBOD_ERR_INVALID;
+  if (d->N <= 0 || d->P <= 0 || d->gmax < 0) return SBOD_ERR_INVALID;
+  if (need_scores && (d->C <= 0 || !d->scores || !d->locs)) return SBOD_ERR_INVALID;
+  if (!d->gt_boxes || !d->gt_labels || !d->gt_offsets || !d->priors_xy || !d->priors_cxcy)
+    return SBOD_ERR_INVALID;
+  if (!d->ov || !d->obj) return SBOD_ERR_INVALID;
+  if (need_scores && (!d->lse || !d->ce || !d->sel || !d->partials || !d->sums || !d->loss))
+    return SBOD_ERR_INVALID;
+  if (need_scores && (reinterpret_cast<uintptr_t>(d->scores) & 15)) return SBOD_ERR_ALIGNMENT;
+  if (need_scores && (reinterpret_cast<uintptr_t>(d->locs) & 15)) return SBOD_ERR_ALIGNMENT;
+  if ((long long)d->N * d->P >= (1ll << 31)) return SBOD_ERR_UNSUPPORTED;
+  if (d->gmax > 8192) return SBOD_ERR_UNSUPPORTED;
+  if (need_scores && d->C > 16384) return SBOD_ERR_UNSUPPORTED;
+  if (d->reg_kind < 0 || d->reg_kind > SBOD_REG_CIOU) return SBOD_ERR_INVALID;
+  if (d->cls_kind < 0 || d->cls_kind > SBOD_CLS_FOCAL_NORM) return SBOD_ERR_INVALID;
+  q.locs = d->locs;
+  q.scores = d->scores;
+  q.priors_cxcy = reinterpret_cast<const float4*>(d->priors_cxcy);
+  q.priors_xy = reinterpret_cast<const float4*>(d->priors_xy);
+  q.anchors_xy = reinterpret_cast<const float4*>(d->anchors_xy);
+  q.gt_boxes = reinterpret_cast<const float4*>(d->gt_boxes);
+  q.gt_labels = d->gt_labels;
+  q.gt_offsets = d->gt_offsets;
+  q.exclude = d->exclude;
+  q.N = d->N; q.P = d->P; q.C = d->C; q.gmax = d->gmax > 0 ? d->gmax : 1;
+  q.thr_pos = d->thr_pos; q.thr_neg = d->thr_neg;
+  q.reg_kind = d->reg_kind; q.cls_kind = d->cls_kind;
+  q.binarize = d->binarize_labels; q.ratio = d->neg_pos_ratio;
+  q.reg_weight = d->reg_weight; q.beta = d->smooth_l1_beta;
+  q.falpha = d->focal_alpha; q.fgamma = d->focal_gamma;
+  q.ov = d->ov; q.obj = d->obj; q.lse = d->lse; q.ce = d->ce; q.sel = d->sel;
+  q.partials = d->partials; q.sums = d->sums; q.loss = d->loss;
+  // workspace carve-up
+  const size_t need = sbod_loss_workspace_bytes(d);
+  if (!d->workspace || d->workspace_bytes < need) return SBOD_ERR_WORKSPACE;
+  if (reinterpret_cast<uintptr_t>(d->workspace) & 255) return SBOD_ERR_WORKSPACE;
+  unsigned char* w = static_cast<unsigned char*>(d->workspace);
+  q.counters = reinterpret_cast<unsigned int*>(w);
+  w += 256;
+  q.gtkey = reinterpret_cast<unsigned long long*>(w);
+  w += align_up(size_t(q.N) * q.gmax * 8, 256);
+  q.cand = reinterpret_cast<float*>(w);
+  const Tiling t = choose_tiling(need_scores ? d->C : 1, kMaxStages);
+  q.rows_per_tile = t.rows;
+  q.tiles_per_image = (q.P + t.rows - 1) / t.rows;
+  q.n_tiles = q.tiles_per_image * q.N;
+  q.n_stages = t.stages;
+  q.stage_floats = t.stage_floats;
+  q.with_scores = need_scores ? 1 : 0;
+  return SBOD_OK;
+}
+
+}  // namespace sbod
+
+using namespace sbod;
+
+extern "C" size_t sbod_loss_workspace_bytes(const sbod_loss_desc* d) {
+  if (!d) return 0;
+  const int gmax = d->gmax > 0 ? d->gmax : 1;
+  return 256 + align_up(size_t(d->N) * gmax * 8, 256) + align_up(size_t(d->N) * d->P * 4, 256);
+}
+
+// Workspace contract: the first 256 bytes (counters) and the gtkey block must be zero on the
+// first call; every call leaves them zero again. sbod_workspace_init does the first zeroing.
+extern "C" int sbod_workspace_init(void* workspace, size_t bytes, sbod_stream_t stream) {
+  if (!workspace) return SBOD_ERR_INVALID;
+  SBOD_CUDA_TRY(cudaMemsetAsync(workspace, 0, bytes, static_cast<cudaStream_t>(stream)));
+  return SBOD_OK;
+}
+
+static int launch_match(const LossParams& q, cudaStream_t st) {
+  const Tiling t = choose_tiling(q.with_scores ? q.C : 1, kMaxStages);
+  const size_t smem = q.with_scores ? t.smem : 0;
+  static bool attr_done = false;
+  if (!attr_done) {
+    SBOD_CUDA_TRY(cudaFuncSetAttribute(match_lse_kernel,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    SBOD_CUDA_TRY(cudaFuncSetAttribute(loss_bwd_kernel,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    SBOD_CUDA_TRY(cudaFuncSetAttribute(forced_match_kernel,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    attr_done = true;
+  }
+  int ctas_per_sm = 2;
+  if (smem > 0) {
+    ctas_per_sm = int((220 * 1024) / (smem + 9 * 1024));
+    if (ctas_per_sm < 1) ctas_per_sm = 1;
+    if (ctas_per_sm > 8) ctas_per_sm = 8;
+  } else {
+    ctas_per_sm = 8;
+  }
+  int grid = sm_count() * ctas_per_sm;
+  if (grid > q.n_tiles) grid = q.n_tiles;
+  match_lse_kernel<<<grid, kRows, smem, st>>>(q);
+  SBOD_LAUNCH_CHECK();
+  forced_match_kernel<<<q.N, 256, size_t(q.gmax) * 8, st>>>(q);
+  SBOD_LAUNCH_CHECK();
+  return SBOD_OK;
+}
+
+extern "C" int sbod_loss_forward(const sbod_loss_desc* d, sbod_stream_t stream) {
+  LossParams q;
+  int rc = fill_params(d, q, true);
+  if (rc) return rc;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  rc = launch_match(q, st);
+  if (rc) return rc;
+  mine_kernel<<<q.N, kMineThreads, 0, st>>>(q);
+  SBOD_LAUNCH_CHECK();
+  if (q.cls_kind == SBOD_CLS_CE_MINE_BATCH) {
+    mine_batch_kernel<<<1, kMineThreads, 0, st>>>(q);
+    SBOD_LAUNCH_CHECK();
+  }
+  return SBOD_OK;
+}
+
+extern "C" int sbod_loss_finalize(const sbod_loss_desc* d, sbod_stream_t stream) {
+  LossParams q;
+  int rc = fill_params(d, q, true);
+  if (rc) return rc;
+  finalize_kernel<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(q);
+  SBOD_LAUNCH_CHECK();
+  return SBOD_OK;
+}
+
+extern "C" int sbod_loss_backward(const sbod_loss_desc* d, const float* grad_loss,
+                                  float* grad_locs, float* grad_scores, sbod_stream_t stream) {
+  LossParams q;
+  int rc = fill_params(d, q, true);
+  if (rc) return rc;
+  if (grad_scores && (reinterpret_cast<uintptr_t>(grad_scores) & 15)) return SBOD_ERR_ALIGNMENT;
+  if (grad_locs && (reinterpret_cast<uintptr_t>(grad_locs) & 15)) return SBOD_ERR_ALIGNMENT;
+  BwdParams bp;
+  const Tiling t = choose_tiling(q.C, 1);
+  q.n_stages = 1;
+  q.stage_floats = t.stage_floats;
+  q.rows_per_tile = t.rows;
+  q.tiles_per_image = (q.P + t.rows - 1) / t.rows;
+  q.n_tiles = q.tiles_per_image * q.N;
+  bp.q = q;
+  bp.grad_loss = grad_loss;
+  bp.grad_locs = grad_locs;
+  bp.grad_scores = grad_scores;
+  bp.dense = (q.cls_kind == SBOD_CLS_FOCAL_SUM || q.cls_kind == SBOD_CLS_FOCAL_NORM) ? 1 : 0;
+  const size_t smem = size_t(t.stage_floats) * 4 + 16;
+  static bool attr_done = false;
+  if (!attr_done) {
+    SBOD_CUDA_TRY(cudaFuncSetAttribute(loss_bwd_kernel,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    attr_done = true;
+  }
+  int ctas_per_sm = int((220 * 1024) / (smem + 4 * 1024));
+  if (ctas_per_sm < 1) ctas_per_sm = 1;
+  if (ctas_per_sm > 8) ctas_per_sm = 8;
+  int grid = sm_count() * ctas_per_sm;
+  if (grid > q.n_tiles) grid = q.n_tiles;
+  loss_bwd_kernel<<<grid, kRows, smem, static_cast<cudaStream_t>(stream)>>>(bp);
+  SBOD_LAUNCH_CHECK();
+  return SBOD_OK;
+}
+
+extern "C" int sbod_loss_targets(const sbod_loss_desc* d, int64_t* cls_out, int64_t* neg_out,
+                                 sbod_stream_t stream) {
+  LossParams q;
+  int rc = fill_params(d, q, false);
+  if (rc) return rc;
+  const size_t total = size_t(q.N) * q.P;
+  int grid = int((total + 255) / 256);
+  if (grid > sm_count() * 8) grid = sm_count() * 8;
+  targets_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(q, cls_out, neg_out);
+  SBOD_LAUNCH_CHECK();
+  return SBOD_OK;
+}
+
+// ---- stand-alone batched assignment (no scores) -------------------------------------------
+extern "C" size_t sbod_assign_workspace_bytes(int N, int gmax) {
+  if (gmax < 1) gmax = 1;
+  return 256 + align_up(size_t(N) * gmax * 8, 256);
+}
+
+extern "C" int sbod_assign(const float* gt_boxes, const int64_t* gt_labels,
+                           const int32_t* gt_offsets, int N, int gmax, const float* anchors_xy,
+                           int per_image_anchors, int P, float thr_pos, float thr_neg,
+                           float* ov_out, int32_t* obj_out, int64_t* cls_out, int64_t* neg_out,
+                           void* workspace, size_t workspace_bytes, sbod_stream_t stream) {
+  if (!gt_boxes || !gt_labels || !gt_offsets || !anchors_xy || !ov_out || !obj_out)
+    return SBOD_ERR_INVALID;
+  if (N <= 0 || P <= 0 || gmax < 0) return SBOD_ERR_INVALID;
+  if (gmax > 8192) return SBOD_ERR_UNSUPPORTED;
+  if ((long long)N * P >= (1ll << 31)) return SBOD_ERR_UNSUPPORTED;
+  if (!workspace || workspace_bytes < sbod_assign_workspace_bytes(N, gmax))
+    return SBOD_ERR_WORKSPACE;
+  if (reinterpret_cast<uintptr_t>(workspace) & 255) return SBOD_ERR_WORKSPACE;
+  LossParams q;
+  memset(&q, 0, sizeof(q));
+  q.gt_boxes = reinterpret_cast<const float4*>(gt_boxes);
+  q.gt_labels = gt_labels;
+  q.gt_offsets = gt_offsets;
+  q.priors_xy = reinterpret_cast<const float4*>(anchors_xy);
+  q.anchors_xy = per_image_anchors ? reinterpret_cast<const float4*>(anchors_xy) : nullptr;
+  q.N = N; q.P = P; q.C = 1; q.gmax = gmax > 0 ? gmax : 1;
+  q.thr_pos = thr_pos; q.thr_neg = thr_neg;
+  q.ov = ov_out; q.obj = obj_out;
+  unsigned char* w = static_cast<unsigned char*>(workspace);
+  q.counters = reinterpret_cast<unsigned int*>(w);
+  q.gtkey = reinterpret_cast<unsigned long long*>(w + 256);
+  q.rows_per_tile = kRows;
+  q.tiles_per_image = (P + kRows - 1) / kRows;
+  q.n_tiles = q.tiles_per_image * N;
+  q.n_stages = 1;
+  q.stage_floats = 0;
+  q.with_scores = 0;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  int rc = launch_match(q, st);
+  if (rc) return rc;
+  if (cls_out || neg_out) {
+    const size_t total = size_t(N) * P;
+    int grid = int((total + 255) / 256);
+    if (grid > sm_count() * 8) grid = sm_count() * 8;
+    targets_kernel<<<grid, 256, 0, st>>>(q, cls_out, neg_out);
+    SBOD_LAUNCH_CHECK();
+  }
+  return SBOD_OK;
+}
+
+// ---- end-to-end helper with HOST buffers (bench.py e2e leg) ----------------------------------
+namespace {
+struct HostArena {
+  size_t locs, scores, pcx, pxy, gtb, gtl, gto, ov, obj, lse, ce, sel, partials, sums, loss, ws, total;
+};
+HostArena host_arena_layout(const sbod_loss_desc* d, int T) {
+  HostArena a;
+  size_t o = 0;
+  auto take = [&](size_t bytes) { size_t at = o; o += align_up(bytes, 256); return at; };
+  const size_t NP = size_t(d->N) * d->P;
+  a.locs = take(NP * 16);
+  a.scores = take(NP * size_t(d->C) * 4);
+  a.pcx = take(size_t(d->P) * 16);
+  a.pxy = take(size_t(d->P) * 16);
+  a.gtb = take(size_t(T > 0 ? T : 1) * 16);
+  a.gtl = take(size_t(T > 0 ? T : 1) * 8);
+  a.gto = take(size_t(d->N + 1) * 4);
+  a.ov = take(NP * 4);
+  a.obj = take(NP * 4);
+  a.lse = take(NP * 4);
+  a.ce = take(NP * 4);
+  a.sel = take(NP);
+  a.partials = take(size_t(d->N) * 32);
+  a.sums = take(32);
+  a.loss = take(16);
+  a.ws = take(sbod_loss_workspace_bytes(d));
+  a.total = o;
+  return a;
+}
+}  // namespace
+
+extern "C" size_t sbod_loss_forward_host_arena_bytes(const sbod_loss_desc* d, int T) {
+  if (!d) return 0;
+  return host_arena_layout(d, T).total;
+}
+
+extern "C" int sbod_loss_forward_host(const sbod_loss_desc* h, int T, float* loss_host,
+                                      void* dev_arena, size_t arena_bytes, sbod_stream_t stream) {
+  if (!h || !loss_host || !dev_arena || T < 0) return SBOD_ERR_INVALID;
+  if (h->anchors_xy || h->exclude) return SBOD_ERR_UNSUPPORTED;
+  const HostArena a = host_arena_layout(h, T);
+  if (arena_bytes < a.total) return SBOD_ERR_WORKSPACE;
+  if (reinterpret_cast<uintptr_t>(dev_arena) & 255) return SBOD_ERR_WORKSPACE;
+  unsigned char* base = static_cast<unsigned char*>(dev_arena);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const size_t NP = size_t(h->N) * h->P;
+  SBOD_CUDA_TRY(cudaMemcpyAsync(base + a.locs, h->locs, NP * 16, cudaMemcpyHostToDevice, st));
+  SBOD_CUDA_TRY(cudaMemcpyAsync(base + a.scores, h->scores, NP * size_t(h->C) * 4, cudaMemcpyHostToDevice, st));
+  SBOD_CUDA_TRY(cudaMemcpyAsync(base + a.pcx, h->priors_cxcy, size_t(h->P) * 16, cudaMemcpyHostToDevice, st));
+  SBOD_CUDA_TRY(cudaMemcpyAsync(base + a.pxy, h->priors_xy, size_t(h->P) * 16, cudaMemcpyHostToDevice, st));
+  if (T > 0) {
+    SBOD_CUDA_TRY(cudaMemcpyAsync(base + a.gtb, h->gt_boxes, size_t(T) * 16, cudaMemcpyHostToDevice, st));
+    SBOD_CUDA_TRY(cudaMemcpyAsync(base + a.gtl, h->gt_labels, size_t(T) * 8, cudaMemcpyHostToDevice, st));
+  }
+  SBOD_CUDA_TRY(cudaMemcpyAsync(base + a.gto, h->gt_offsets, size_t(h->N + 1) * 4, cudaMemcpyHostToDevice, st));
+  SBOD_CUDA_TRY(cudaMemsetAsync(base + a.ws, 0, 256 + align_up(size_t(h->N) * (h->gmax > 0 ? h->gmax : 1) * 8, 256), st));
+  sbod_loss_desc d = *h;
+  d.locs = reinterpret_cast<const float*>(base + a.locs);
+  d.scores = reinterpret_cast<const float*>(base + a.scores);
+  d.priors_cxcy = reinterpret_cast<const float*>(base + a.pcx);
+  d.priors_xy = reinterpret_cast<const float*>(base + a.pxy);
+  d.gt_boxes = reinterpret_cast<const float*>(base + a.gtb);
+  d.gt_labels = reinterpret_cast<const int64_t*>(base + a.gtl);
+  d.gt_offsets = reinterpret_cast<const int32_t*>(base + a.gto);
+  d.ov = reinterpret_cast<float*>(base + a.ov);
+  d.obj = reinterpret_cast<int32_t*>(base + a.obj);
+  d.lse = reinterpret_cast<float*>(base + a.lse);
+  d.ce = reinterpret_cast<float*>(base + a.ce);
+  d.sel = reinterpret_cast<uint8_t*>(base + a.sel);
+  d.partials = reinterpret_cast<double*>(base + a.partials);
+  d.sums = reinterpret_cast<double*>(base + a.sums);
+  d.loss = reinterpret_cast<float*>(base + a.loss);
+  d.workspace = base + a.ws;
+  d.workspace_bytes = sbod_loss_workspace_bytes(h);
+  int rc = sbod_loss_forward(&d, stream);
+  if (rc) return rc;
+  SBOD_CUDA_TRY(cudaMemcpyAsync(loss_host, d.loss, 16, cudaMemcpyDeviceToHost, st));
+  return SBOD_OK;
+}
