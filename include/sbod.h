@@ -27,6 +27,12 @@ extern "C" {
 
 typedef void* sbod_stream_t; /* cudaStream_t */
 
+#if defined(__GNUC__)
+#define SBOD_API __attribute__((visibility("default")))
+#else
+#define SBOD_API
+#endif
+
 #define SBOD_ABI_VERSION 1
 
 #define SBOD_OK 0
@@ -35,8 +41,8 @@ typedef void* sbod_stream_t; /* cudaStream_t */
 #define SBOD_ERR_UNSUPPORTED (-3) /* shape outside what the kernels support */
 #define SBOD_ERR_ALIGNMENT (-4)   /* a streamed tensor is not 16-byte aligned */
 
-int sbod_abi_version(void);
-const char* sbod_error_string(int code);
+SBOD_API int sbod_abi_version(void);
+SBOD_API const char* sbod_error_string(int code);
 
 /* ------------------------------------------------------------------------------------------
  * Dense pairwise IoU.
@@ -47,7 +53,8 @@ const char* sbod_error_string(int code);
  * ---------------------------------------------------------------------------------------- */
 #define SBOD_IOU_METRICS 0
 #define SBOD_IOU_JACCARD 1
-int sbod_iou_matrix(const float* a, int A, const float* b, int B, int mode, float* out,
+#define SBOD_IOU_INTERSECT 2 /* operators/iou_utils.py:192-212 intersect: clamp(min-max,0) area */
+SBOD_API int sbod_iou_matrix(const float* a, int A, const float* b, int B, int mode, float* out,
                     sbod_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
@@ -60,19 +67,24 @@ int sbod_iou_matrix(const float* a, int A, const float* b, int B, int mode, floa
  * ---------------------------------------------------------------------------------------- */
 #define SBOD_BOX_XY_TO_CXCY 0
 #define SBOD_BOX_CXCY_TO_XY 1
-int sbod_box_convert(const float* in, float* out, int n, int op, sbod_stream_t stream);
+SBOD_API int sbod_box_convert(const float* in, float* out, int n, int op, sbod_stream_t stream);
 
 #define SBOD_CODEC_TRANSFORMS 0 /* transforms.py arithmetic: /(pwh/10), log(..)*5 */
 #define SBOD_CODEC_IOU_UTILS 1  /* iou_utils.py arithmetic: /(v0*pwh), log(..)/v1; decode -> xyxy */
-int sbod_box_encode(const float* boxes, const float* priors_cxcy, float* out, int n, int flavour,
+SBOD_API int sbod_box_encode(const float* boxes, const float* priors_cxcy, float* out, int n, int flavour,
                     float v0, float v1, sbod_stream_t stream);
-int sbod_box_decode(const float* locs, const float* priors_cxcy, float* out, int n, int flavour,
+SBOD_API int sbod_box_decode(const float* locs, const float* priors_cxcy, float* out, int n, int flavour,
                     float v0, float v1, sbod_stream_t stream);
 
 /* RefineDet512.offset2bbox, models/RefineDet512.py:643-653: two-stage decode ARM -> ODM -> xyxy.
  * arm/odm: [N,P,4], priors_cxcy: [P,4], out: [N,P,4]. */
-int sbod_offset2bbox(const float* arm_locs, const float* odm_locs, const float* priors_cxcy,
+SBOD_API int sbod_offset2bbox(const float* arm_locs, const float* odm_locs, const float* priors_cxcy,
                      float* out, int N, int P, sbod_stream_t stream);
+
+/* RefineDet ODM easy-negative mask: out[i] = softmax(arm_scores[i, :])[1] < theta, arm_scores
+ * [n_rows,2] (models/RefineDet512.py:894-895). */
+SBOD_API int sbod_arm_easy_negative(const float* arm_scores, long long n_rows, float theta, uint8_t* out,
+                           sbod_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * Paired (elementwise) IoU family, operators/iou_utils.py:6-164 bbox_overlaps_{iou,giou,diou,ciou}
@@ -83,9 +95,9 @@ int sbod_offset2bbox(const float* arm_locs, const float* odm_locs, const float* 
 #define SBOD_PAIR_GIOU 1
 #define SBOD_PAIR_DIOU 2
 #define SBOD_PAIR_CIOU 3
-int sbod_pair_iou_fwd(const float* b1, const float* b2, int M, int kind, float* out,
+SBOD_API int sbod_pair_iou_fwd(const float* b1, const float* b2, int M, int kind, float* out,
                       sbod_stream_t stream);
-int sbod_pair_iou_bwd(const float* b1, const float* b2, const float* grad_out, int M, int kind,
+SBOD_API int sbod_pair_iou_bwd(const float* b1, const float* b2, const float* grad_out, int M, int kind,
                       float* grad_b1, float* grad_b2, sbod_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
@@ -96,12 +108,12 @@ int sbod_pair_iou_bwd(const float* b1, const float* b2, const float* grad_out, i
  *                         grad_logits (optional, may be NULL) = d(sum row_out)/d logits.
  *   sbod_sigmoid_focal  : Loss.py:41-80 SigmoidFocalLoss (uses columns 1..C-1, class ids 1..C-1)
  * ---------------------------------------------------------------------------------------- */
-int sbod_smooth_l1(const float* pred, const float* target, int n_elem, float beta, float* out,
+SBOD_API int sbod_smooth_l1(const float* pred, const float* target, int n_elem, float beta, float* out,
                    float* grad_pred /* nullable: d out / d pred */, sbod_stream_t stream);
-int sbod_softmax_focal(const float* logits, const int64_t* target, int M, int C, float alpha_fg,
+SBOD_API int sbod_softmax_focal(const float* logits, const int64_t* target, int M, int C, float alpha_fg,
                        float alpha_bg, float gamma, float* row_out, float* grad_logits,
                        sbod_stream_t stream);
-int sbod_sigmoid_focal(const float* logits, const int64_t* target, int M, int C, float alpha,
+SBOD_API int sbod_sigmoid_focal(const float* logits, const int64_t* target, int M, int C, float alpha,
                        float gamma, float* row_out, float* grad_logits, sbod_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
@@ -111,8 +123,8 @@ int sbod_sigmoid_focal(const float* logits, const int64_t* target, int M, int C,
  * boxes [n,4] xyxy, scores [n]; keep_out [n] int64 (indices into the input, kept order),
  * count_out [1] int32. top_k <= 0 means no cap.
  * ---------------------------------------------------------------------------------------- */
-size_t sbod_nms_workspace_bytes(int n);
-int sbod_nms(const float* boxes, const float* scores, int n, float iou_thr, int top_k,
+SBOD_API size_t sbod_nms_workspace_bytes(int n);
+SBOD_API int sbod_nms(const float* boxes, const float* scores, int n, float iou_thr, int top_k,
              int64_t* keep_out, int32_t* count_out, void* workspace, size_t workspace_bytes,
              sbod_stream_t stream);
 
@@ -126,8 +138,8 @@ int sbod_nms(const float* boxes, const float* scores, int n, float iou_thr, int 
  * obj = object_for_each_prior (int32), cls = true_classes (int64, nullable),
  * neg = true_neg_classes (int64, nullable).
  * ---------------------------------------------------------------------------------------- */
-size_t sbod_assign_workspace_bytes(int N, int gmax);
-int sbod_assign(const float* gt_boxes, const int64_t* gt_labels, const int32_t* gt_offsets, int N,
+SBOD_API size_t sbod_assign_workspace_bytes(int N, int gmax);
+SBOD_API int sbod_assign(const float* gt_boxes, const int64_t* gt_labels, const int32_t* gt_offsets, int N,
                 int gmax, const float* anchors_xy, int per_image_anchors, int P, float thr_pos,
                 float thr_neg, float* ov_out, int32_t* obj_out, int64_t* cls_out,
                 int64_t* neg_out, void* workspace, size_t workspace_bytes, sbod_stream_t stream);
@@ -137,8 +149,8 @@ int sbod_assign(const float* gt_boxes, const int64_t* gt_labels, const int32_t* 
  * conf = labels[idx]+1, conf[ov<thr]=0. One image. priors_cxcy [P,4]; truths [G,4] xyxy;
  * labels [G] int64. Writes loc_out [P,4] (encoded with variances v0,v1, or the matched xyxy
  * boxes when encode_loc==0 == match_ious) and conf_out [P] int64. */
-size_t sbod_match_workspace_bytes(int G, int P);
-int sbod_match(float threshold, const float* truths, int G, const float* priors_cxcy, int P,
+SBOD_API size_t sbod_match_workspace_bytes(int G, int P);
+SBOD_API int sbod_match(float threshold, const float* truths, int G, const float* priors_cxcy, int P,
                float v0, float v1, const int64_t* labels, int encode_loc, float* loc_out,
                int64_t* conf_out, void* workspace, size_t workspace_bytes, sbod_stream_t stream);
 
@@ -196,19 +208,21 @@ typedef struct sbod_loss_desc {
   size_t workspace_bytes;
 } sbod_loss_desc;
 
-size_t sbod_loss_workspace_bytes(const sbod_loss_desc* d);
+SBOD_API size_t sbod_loss_workspace_bytes(const sbod_loss_desc* d);
 /* The workspace must be zeroed once before its first use (every call leaves it clean again);
  * the same holds for the sbod_assign / sbod_detect workspaces. */
-int sbod_workspace_init(void* workspace, size_t bytes, sbod_stream_t stream);
-int sbod_loss_forward(const sbod_loss_desc* d, sbod_stream_t stream);
+SBOD_API int sbod_workspace_init(void* workspace, size_t bytes, sbod_stream_t stream);
+SBOD_API int sbod_loss_forward(const sbod_loss_desc* d, sbod_stream_t stream);
+/* Profiling / bench hook: launch one stage of the forward (0 match_lse, 1 forced_match, 2 mine). */
+SBOD_API int sbod_loss_forward_stage(const sbod_loss_desc* d, int stage, sbod_stream_t stream);
 /* Recompute d->loss from d->sums (after a cross-GPU all-reduce of d->sums). */
-int sbod_loss_finalize(const sbod_loss_desc* d, sbod_stream_t stream);
+SBOD_API int sbod_loss_finalize(const sbod_loss_desc* d, sbod_stream_t stream);
 /* grad_loss: device scalar (upstream gradient). grad_locs [N,P,4], grad_scores [N,P,C]. */
-int sbod_loss_backward(const sbod_loss_desc* d, const float* grad_loss, float* grad_locs,
+SBOD_API int sbod_loss_backward(const sbod_loss_desc* d, const float* grad_loss, float* grad_locs,
                        float* grad_scores, sbod_stream_t stream);
 /* Expand the per-prior state into the reference's int64 tensors (tests / debugging):
  * true_classes, true_neg_classes [N,P]. */
-int sbod_loss_targets(const sbod_loss_desc* d, int64_t* cls_out, int64_t* neg_out,
+SBOD_API int sbod_loss_targets(const sbod_loss_desc* d, int64_t* cls_out, int64_t* neg_out,
                       sbod_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
@@ -244,18 +258,20 @@ typedef struct sbod_detect_desc {
   size_t workspace_bytes;
 } sbod_detect_desc;
 
-size_t sbod_detect_workspace_bytes(const sbod_detect_desc* d);
+SBOD_API size_t sbod_detect_workspace_bytes(const sbod_detect_desc* d);
 /* leading bytes of the workspace that must be zero before the first call (sbod_workspace_init) */
-size_t sbod_detect_workspace_zero_bytes(const sbod_detect_desc* d);
-int sbod_detect(const sbod_detect_desc* d, sbod_stream_t stream);
+SBOD_API size_t sbod_detect_workspace_zero_bytes(const sbod_detect_desc* d);
+SBOD_API int sbod_detect(const sbod_detect_desc* d, sbod_stream_t stream);
+/* Profiling / bench hook: stage 0 = score/candidate kernel only, 1 = NMS kernel only. */
+SBOD_API int sbod_detect_stage(const sbod_detect_desc* d, int stage, sbod_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * End-to-end helpers with HOST buffers (pinned or pageable): copy the inputs to the device,
  * run the device entry point above, copy the result back. Used by bench.py's e2e leg; the
  * device scratch is the caller's (dev_arena, arena_bytes from the *_arena_bytes query).
  * ---------------------------------------------------------------------------------------- */
-size_t sbod_loss_forward_host_arena_bytes(const sbod_loss_desc* d, int T);
-int sbod_loss_forward_host(const sbod_loss_desc* d_host /* input pointers are HOST pointers */,
+SBOD_API size_t sbod_loss_forward_host_arena_bytes(const sbod_loss_desc* d, int T);
+SBOD_API int sbod_loss_forward_host(const sbod_loss_desc* d_host /* input pointers are HOST pointers */,
                            int T, float* loss_host /* [4] */, void* dev_arena, size_t arena_bytes,
                            sbod_stream_t stream);
 

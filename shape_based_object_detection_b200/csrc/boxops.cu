@@ -44,8 +44,10 @@ __global__ void __launch_bounds__(256) iou_matrix_kernel(const float4* __restric
         v = iou_metrics_rn(s_a[i], s_area[i], bb, ab);
         if (s_zero[i]) v = 0.f;   // metrics.py:249
         if (bz) v = -1.f;         // metrics.py:250 (applied last)
-      } else {
+      } else if (mode == SBOD_IOU_JACCARD) {
         v = iou_plain_rn(s_a[i], s_area[i], bb, ab);
+      } else {
+        v = inter_rn(s_a[i], bb);
       }
       out[size_t(a0 + i) * B + j] = v;  // coalesced over j
     }
@@ -126,6 +128,17 @@ __global__ void offset2bbox_kernel(const float4* __restrict__ arm, const float4*
     const float cx = o.x * iw / 10.f + icx, cy = o.y * ih / 10.f + icy;
     const float w = expf(o.z / 5.f) * iw, h = expf(o.w / 5.f) * ih;
     out[i] = make_float4(cx - w / 2.f, cy - h / 2.f, cx + w / 2.f, cy + h / 2.f);
+  }
+}
+
+// ---- RefineDet: ARM easy-negative mask  softmax(arm_scores)[:, 1] < theta  (RefineDet512.py:894-895)
+__global__ void arm_easy_negative_kernel(const float2* __restrict__ arm_scores, size_t n, float theta,
+                                         uint8_t* __restrict__ out) {
+  for (size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x; i < n; i += size_t(gridDim.x) * blockDim.x) {
+    const float2 x = arm_scores[i];
+    const float m = fmaxf(x.x, x.y);
+    const float e0 = expf(x.x - m), e1 = expf(x.y - m);
+    out[i] = (e1 / (e0 + e1) < theta) ? 1 : 0;
   }
 }
 
@@ -430,7 +443,7 @@ extern "C" const char* sbod_error_string(int code) {
 
 extern "C" int sbod_iou_matrix(const float* a, int A, const float* b, int B, int mode, float* out,
                                sbod_stream_t stream) {
-  if (A < 0 || B < 0 || (mode != SBOD_IOU_METRICS && mode != SBOD_IOU_JACCARD)) return SBOD_ERR_INVALID;
+  if (A < 0 || B < 0 || mode < SBOD_IOU_METRICS || mode > SBOD_IOU_INTERSECT) return SBOD_ERR_INVALID;
   if (A == 0 || B == 0) return SBOD_OK;
   if (!a || !b || !out) return SBOD_ERR_INVALID;
   dim3 grid((B + 255) / 256, (A + kIouChunk - 1) / kIouChunk);
@@ -484,6 +497,17 @@ extern "C" int sbod_offset2bbox(const float* arm_locs, const float* odm_locs,
   offset2bbox_kernel<<<grid_for(size_t(N) * P, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       reinterpret_cast<const float4*>(arm_locs), reinterpret_cast<const float4*>(odm_locs),
       reinterpret_cast<const float4*>(priors_cxcy), reinterpret_cast<float4*>(out), N, P);
+  SBOD_LAUNCH_CHECK();
+  return SBOD_OK;
+}
+
+extern "C" int sbod_arm_easy_negative(const float* arm_scores, long long n_rows, float theta,
+                                      uint8_t* out, sbod_stream_t stream) {
+  if (n_rows < 0) return SBOD_ERR_INVALID;
+  if (n_rows == 0) return SBOD_OK;
+  if (!arm_scores || !out) return SBOD_ERR_INVALID;
+  arm_easy_negative_kernel<<<grid_for(size_t(n_rows), 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const float2*>(arm_scores), size_t(n_rows), theta, out);
   SBOD_LAUNCH_CHECK();
   return SBOD_OK;
 }

@@ -637,7 +637,7 @@ extern "C" size_t sbod_detect_workspace_zero_bytes(const sbod_detect_desc* d) {
          align_up(size_t(d->N) * size_t(d->C) * 4, 256);
 }
 
-extern "C" int sbod_detect(const sbod_detect_desc* d, sbod_stream_t stream) {
+static int detect_run(const sbod_detect_desc* d, sbod_stream_t stream, int stage_mask) {
   if (!d || !d->locs || !d->scores || !d->out_boxes || !d->out_labels || !d->out_scores ||
       !d->out_prior || !d->out_counts)
     return SBOD_ERR_INVALID;
@@ -693,12 +693,26 @@ extern "C" int sbod_detect(const sbod_detect_desc* d, sbod_stream_t stream) {
   if (ctas_per_sm > 8) ctas_per_sm = 8;
   int grid = sm_count() * ctas_per_sm;
   if (grid > q.n_tiles) grid = q.n_tiles;
-  detect_score_kernel<<<grid, kDRows, t.smem, st>>>(q);
-  SBOD_LAUNCH_CHECK();
+  if (stage_mask & 1) {
+    detect_score_kernel<<<grid, kDRows, t.smem, st>>>(q);
+    SBOD_LAUNCH_CHECK();
+  }
+  if (!(stage_mask & 2)) return SBOD_OK;
   const size_t nms_smem = ((sizeof(NmsSmem) + 127) & ~size_t(127)) + size_t(q.kcap) * 25 + 256 +
                           size_t(q.C + 1) * 4;
   if (nms_smem > 220 * 1024) return SBOD_ERR_UNSUPPORTED;
   detect_nms_kernel<<<q.N, kNmsThreads, nms_smem, st>>>(q);
   SBOD_LAUNCH_CHECK();
   return SBOD_OK;
+}
+
+extern "C" int sbod_detect(const sbod_detect_desc* d, sbod_stream_t stream) {
+  return detect_run(d, stream, 3);
+}
+
+// Profiling / bench hook: stage 0 = detect_score_kernel only, stage 1 = detect_nms_kernel only.
+// A stage-0 launch must be followed by a stage-1 launch before the next full sbod_detect.
+extern "C" int sbod_detect_stage(const sbod_detect_desc* d, int stage, sbod_stream_t stream) {
+  if (stage != 0 && stage != 1) return SBOD_ERR_INVALID;
+  return detect_run(d, stream, stage == 0 ? 1 : 2);
 }

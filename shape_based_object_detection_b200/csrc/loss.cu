@@ -939,7 +939,7 @@ extern "C" int sbod_workspace_init(void* workspace, size_t bytes, sbod_stream_t 
   return SBOD_OK;
 }
 
-static int launch_match(const LossParams& q, cudaStream_t st) {
+static int launch_match(const LossParams& q, cudaStream_t st, int stage_mask = 3) {
   const Tiling t = choose_tiling(q.with_scores ? q.C : 1, kMaxStages);
   const size_t smem = q.with_scores ? t.smem : 0;
   static bool attr_done = false;
@@ -962,10 +962,14 @@ static int launch_match(const LossParams& q, cudaStream_t st) {
   }
   int grid = sm_count() * ctas_per_sm;
   if (grid > q.n_tiles) grid = q.n_tiles;
-  match_lse_kernel<<<grid, kRows, smem, st>>>(q);
-  SBOD_LAUNCH_CHECK();
-  forced_match_kernel<<<q.N, 256, size_t(q.gmax) * 8, st>>>(q);
-  SBOD_LAUNCH_CHECK();
+  if (stage_mask & 1) {
+    match_lse_kernel<<<grid, kRows, smem, st>>>(q);
+    SBOD_LAUNCH_CHECK();
+  }
+  if (stage_mask & 2) {
+    forced_match_kernel<<<q.N, 256, size_t(q.gmax) * 8, st>>>(q);
+    SBOD_LAUNCH_CHECK();
+  }
   return SBOD_OK;
 }
 
@@ -976,6 +980,26 @@ extern "C" int sbod_loss_forward(const sbod_loss_desc* d, sbod_stream_t stream) 
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   rc = launch_match(q, st);
   if (rc) return rc;
+  mine_kernel<<<q.N, kMineThreads, 0, st>>>(q);
+  SBOD_LAUNCH_CHECK();
+  if (q.cls_kind == SBOD_CLS_CE_MINE_BATCH) {
+    mine_batch_kernel<<<1, kMineThreads, 0, st>>>(q);
+    SBOD_LAUNCH_CHECK();
+  }
+  return SBOD_OK;
+}
+
+// Profiling / bench hook: launch ONE stage of sbod_loss_forward (0 = match_lse_kernel, 1 =
+// forced_match_kernel, 2 = mine_kernel [+ mine_batch_kernel]). Stage 0 may be repeated; stage 1 must
+// follow before the workspace is used by a full forward again.
+extern "C" int sbod_loss_forward_stage(const sbod_loss_desc* d, int stage, sbod_stream_t stream) {
+  LossParams q;
+  int rc = fill_params(d, q, true);
+  if (rc) return rc;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (stage == 0) return launch_match(q, st, 1);
+  if (stage == 1) return launch_match(q, st, 2);
+  if (stage != 2) return SBOD_ERR_INVALID;
   mine_kernel<<<q.N, kMineThreads, 0, st>>>(q);
   SBOD_LAUNCH_CHECK();
   if (q.cls_kind == SBOD_CLS_CE_MINE_BATCH) {

@@ -70,7 +70,7 @@ SBOD_DEVINL float pair_overlap(const float4 p, const float4 q, int kind, PairGra
       val = iou - (d2 / c2 + alpha * ar);
     }
   }
-  const float out = fminf(fmaxf(val, lo), hi);
+  const float out = (val != val) ? val : fminf(fmaxf(val, lo), hi);  // torch.clamp keeps NaN
   if (!WITH_GRAD) return out;
 
   // ---- reverse mode ----

@@ -1,0 +1,331 @@
+"""GPU suite (-m gpu): the CUDA path, called through the C ABI, against the CPU oracle and the
+fixtures generated from the reference. Tolerances (BASELINE.json north_star): indices / labels /
+kept boxes bit-exact; encoded targets, losses, decoded boxes within 1e-5 relative; gradients within
+1e-4 relative."""
+import numpy as np
+import pytest
+import torch
+
+from cases import DETECT_CASES, LOSS_CASES, case_priors, operator_inputs
+from test_oracle_golden import T, _loss_inputs, close_nan, detect_inputs, eq_nan, refinedet_inputs
+
+pytestmark = pytest.mark.gpu
+
+RTOL_LOSS = 1e-5
+RTOL_GRAD = 1e-4
+
+
+class Cfg(dict):
+    __getattr__ = dict.__getitem__
+    __setattr__ = dict.__setitem__
+
+
+def cfg(reg="", cls="", n_classes=6, box_type="offset", focal_type="softmax"):
+    return Cfg(device=torch.device("cuda:0"), n_classes=n_classes, reg_weights=1.0, reg_loss=reg, cls_loss=cls,
+               model={"box_type": box_type}, focal_type=focal_type)
+
+
+@pytest.fixture(scope="module")
+def dev():
+    assert torch.cuda.is_available(), "the gpu suite needs a CUDA device"
+    return torch.device("cuda:0")
+
+
+def cu(x, dev):
+    return x.to(dev)
+
+
+# ---------------------------------------------------------------------------------------------
+# stand-alone operators
+# ---------------------------------------------------------------------------------------------
+def test_dense_iou_bit_exact(golden, dev):
+    from shape_based_object_detection_b200.metrics import find_jaccard_overlap
+    from shape_based_object_detection_b200.operators import iou_utils as U
+    I, G = operator_inputs(), golden["operators"]
+    got = find_jaccard_overlap(cu(I["boxes"], dev), cu(I["sub"], dev)).cpu()
+    assert torch.equal(got, T(G["iou_metrics"]))
+    assert eq_nan(U.jaccard(cu(I["boxes"][1:], dev), cu(I["sub"], dev)).cpu(), T(G["iou_jaccard"]))
+    assert torch.equal(U.intersect(cu(I["boxes"], dev), cu(I["sub"], dev)).cpu(), T(G["intersect"]))
+    # full-size: every SSD300 prior
+    from oracle import box_pipeline as O
+    want = O.find_jaccard_overlap(I["boxes"], I["pri_xy"])
+    assert torch.equal(find_jaccard_overlap(cu(I["boxes"], dev), cu(I["pri_xy"], dev)).cpu(), want)
+    # empty inputs
+    assert find_jaccard_overlap(torch.zeros((0, 4), device=dev), cu(I["sub"], dev)).shape == (0, I["sub"].size(0))
+
+
+def test_converters_and_codec(golden, dev):
+    from shape_based_object_detection_b200.dataset import transforms as TR
+    from shape_based_object_detection_b200.models.RefineDet512 import offset2bbox
+    from shape_based_object_detection_b200.operators import iou_utils as U
+    I, G = operator_inputs(), golden["operators"]
+    assert torch.equal(TR.xy_to_cxcy(cu(I["sub"], dev)).cpu(), T(G["xy_to_cxcy"]))
+    assert torch.equal(TR.cxcy_to_xy(cu(I["ppm"], dev)).cpu(), T(G["cxcy_to_xy"]))
+    assert torch.equal(U.point_form(cu(I["ppm"], dev)).cpu(), T(G["cxcy_to_xy"]))
+    ppm = cu(I["ppm"], dev)
+    enc = TR.cxcy_to_gcxgcy(TR.xy_to_cxcy(cu(I["b1"], dev)), ppm).cpu()
+    assert torch.allclose(enc, T(G["enc_t"]), rtol=1e-5, atol=1e-6)
+    assert torch.allclose(TR.gcxgcy_to_cxcy(cu(I["loc"], dev), ppm).cpu(), T(G["dec_t"]), rtol=1e-5, atol=1e-7)
+    assert torch.allclose(U.encode(cu(I["b1"], dev), ppm, [0.1, 0.2]).cpu(), T(G["enc_u"]), rtol=1e-5, atol=1e-6)
+    assert torch.allclose(U.decode(cu(I["loc"], dev), ppm, [0.1, 0.2]).cpu(), T(G["dec_u"]), rtol=1e-5, atol=1e-7)
+    o2b = offset2bbox(cu(I["loc"][None], dev), cu((I["loc"] * 0.5)[None], dev), ppm).cpu()
+    assert torch.allclose(o2b, T(G["offset2bbox"]), rtol=1e-5, atol=1e-7)
+    # round trip property at full size
+    pri = cu(I["pri"], dev)
+    rt = TR.xy_to_cxcy(TR.cxcy_to_xy(pri))
+    assert torch.allclose(rt, pri, rtol=1e-6, atol=1e-7)
+
+
+@pytest.mark.parametrize("kind", ["iou", "giou", "diou", "ciou"])
+def test_pair_overlaps_and_grads(golden, dev, kind):
+    from shape_based_object_detection_b200.operators import iou_utils as U
+    I, G = operator_inputs(), golden["operators"]
+    fn = getattr(U, "bbox_overlaps_" + kind)
+    x1 = cu(I["b1"], dev).requires_grad_(True)
+    x2 = cu(I["b2"], dev).requires_grad_(True)
+    v = fn(x1, x2)
+    (v * cu(I["wts"], dev)).sum().backward()
+    assert close_nan(v.detach().cpu(), T(G["pair_" + kind]), 1e-5, 1e-6)
+    assert close_nan(x1.grad.cpu(), T(G["pair_" + kind + "_g1"]), RTOL_GRAD, 1e-4)
+    assert close_nan(x2.grad.cpu(), T(G["pair_" + kind + "_g2"]), RTOL_GRAD, 1e-4)
+
+
+def test_row_losses(golden, dev):
+    from shape_based_object_detection_b200.operators import Loss as LS
+    I, G = operator_inputs(), golden["operators"]
+    x = cu(I["lg"], dev).requires_grad_(True)
+    fl = LS.focal_loss(x, cu(I["tg"], dev), device=dev)
+    fl.backward()
+    assert abs(fl.item() - float(G["focal"])) <= RTOL_LOSS * abs(float(G["focal"]))
+    assert torch.allclose(x.grad.cpu(), T(G["focal_g"]), rtol=RTOL_GRAD, atol=1e-6)
+    x = cu(I["lg"], dev).requires_grad_(True)
+    sf = LS.SigmoidFocalLoss(2.0, 0.25, cfg())(x, cu(I["tg"], dev))
+    sf.backward()
+    assert abs(sf.item() - float(G["sigfocal"])) <= RTOL_LOSS * abs(float(G["sigfocal"]))
+    assert torch.allclose(x.grad.cpu(), T(G["sigfocal_g"]), rtol=RTOL_GRAD, atol=1e-6)
+    x = cu(I["pr"], dev).requires_grad_(True)
+    s1 = LS.SmoothL1Loss()(x, cu(I["tgt"], dev))
+    s1.backward()
+    assert abs(s1.item() - float(G["smoothl1"])) <= RTOL_LOSS * abs(float(G["smoothl1"]))
+    assert torch.allclose(x.grad.cpu(), T(G["smoothl1_g"]), rtol=RTOL_GRAD, atol=1e-8)
+    for lt in ("Iou", "Giou", "Diou"):
+        got = LS.IouLoss(losstype=lt)(cu(I["b1"], dev), cu(I["b2"], dev)).item()
+        assert abs(got - float(G["iouloss_" + lt])) <= 1e-5
+
+
+@pytest.mark.parametrize("thr", [0.5, 0.6])
+def test_assignment_indices_bit_exact(golden, dev, thr):
+    import shape_based_object_detection_b200 as S
+    I, G = operator_inputs(), golden["operators"]
+    ov, obj, cls, neg = S.assign([cu(I["boxes"], dev)], [cu(I["labels"], dev)], cu(I["pri_xy"], dev), threshold=thr)
+    tag = "assign%02d_" % int(thr * 10)
+    assert torch.equal(ov[0].cpu(), T(G[tag + "ov"]))
+    assert torch.equal(obj[0].cpu().long(), T(G[tag + "obj"]).long())
+    assert torch.equal(cls[0].cpu(), T(G[tag + "cls"]).long())
+    assert torch.equal(neg[0].cpu(), T(G[tag + "neg"]).long())
+
+
+def test_match_and_nms(golden, dev):
+    from shape_based_object_detection_b200.operators import iou_utils as U
+    I, G = operator_inputs(), golden["operators"]
+    P = I["pri"].size(0)
+    for nm, fn in (("match", U.match), ("match_ious", U.match_ious)):
+        loc_t = torch.zeros((1, P, 4), device=dev)
+        conf_t = torch.zeros((1, P), dtype=torch.long, device=dev)
+        fn(0.5, cu(I["boxes"][1:], dev), cu(I["pri"], dev), [0.1, 0.2], cu(I["labels"][1:], dev), loc_t, conf_t, 0)
+        conf = conf_t[0].cpu()
+        assert torch.equal(conf, T(G[nm + "_conf"]).long())
+        assert torch.allclose(loc_t[0].cpu()[conf > 0], T(G[nm + "_loc_pos"]), rtol=1e-5, atol=1e-6)
+    keep = U.torchvision_nms(cu(I["nb"], dev), cu(I["ns"], dev), 0.45).cpu()
+    assert torch.equal(keep, T(G["tv_nms_keep"]).long())
+    k, cnt = U.nms(cu(I["nb"], dev), cu(I["ns"], dev), 0.45, 200)
+    assert torch.equal(k[:cnt].cpu(), T(G["nms_keep"]).long())
+    assert k.numel() == I["nb"].size(0) and int(k[cnt:].abs().sum()) == 0
+    # bigger random problem against the oracle's greedy NMS
+    from oracle import box_pipeline as O
+    g = torch.Generator().manual_seed(5)
+    c = torch.rand((3000, 2), generator=g)
+    wh = torch.rand((3000, 2), generator=g) * 0.2 + 0.01
+    b = torch.cat([c - wh / 2, c + wh / 2], 1)
+    s = torch.rand((3000,), generator=g)
+    s[100:110] = s[100]  # score ties -> lower index first
+    assert torch.equal(U.torchvision_nms(cu(b, dev), cu(s, dev), 0.3).cpu(), O.greedy_nms(b, s, 0.3))
+
+
+# ---------------------------------------------------------------------------------------------
+# loss modules
+# ---------------------------------------------------------------------------------------------
+def _module(variant):
+    from shape_based_object_detection_b200 import models as M
+    return {"s300": M.MultiBoxLoss300, "s512": M.MultiBoxLoss512, "ret": M.RetinaFocalLoss}[variant]
+
+
+@pytest.mark.parametrize("name", [k for k, c in LOSS_CASES.items() if c["variant"] != "rfd"])
+def test_loss_modules(golden, dev, name):
+    from oracle import box_pipeline as O
+    case, G = LOSS_CASES[name], golden["losses"]
+    pri, locs, scores, bx, lb = _loss_inputs(case)
+    crit = _module(case["variant"])(cu(pri, dev), cfg(case["reg"], case["cls"], case["C"]),
+                                    threshold=case.get("threshold", 0.5))
+    l_d = cu(locs, dev).requires_grad_(True)
+    s_d = cu(scores, dev).requires_grad_(True)
+    loss = crit(l_d, s_d, [cu(b, dev) for b in bx], [cu(l, dev) for l in lb])
+    loss.backward()
+    ref = float(G[name + "_loss"])
+    assert abs(loss.item() - ref) <= RTOL_LOSS * abs(ref), (loss.item(), ref)
+    # intermediates against the oracle (itself pinned to the reference by the CPU suite)
+    _, parts = O.multibox_loss(case["variant"], pri, locs, scores, bx, lb, reg_loss=case["reg"],
+                               cls_loss=case["cls"], threshold=case.get("threshold", 0.5), want_parts=True)
+    st = crit.last["state"]
+    cls, neg = st.targets()
+    assert torch.equal(st.obj.cpu().long(), parts["obj"])
+    assert torch.equal(st.ov.cpu(), parts["ov"])
+    assert torch.equal(cls.cpu(), parts["true_classes"])
+    assert torch.equal(neg.cpu(), parts["true_neg_classes"])
+    assert int(st.loss[3].item()) == int(parts["n_pos"].sum())
+    assert torch.allclose(l_d.grad.cpu(), T(G[name + "_g_locs"]), rtol=RTOL_GRAD, atol=1e-7)
+    assert torch.allclose(s_d.grad.cpu(), T(G[name + "_g_scores"]), rtol=RTOL_GRAD, atol=1e-7)
+
+
+def test_refinedet_loss(golden, dev):
+    from shape_based_object_detection_b200.models import RefineDetLoss
+    case, G = LOSS_CASES["rfd"], golden["losses"]
+    pri, arm_l, arm_s, odm_l, odm_s, bx, lb = refinedet_inputs(case)
+    crit = RefineDetLoss(cu(pri, dev), cfg(n_classes=case["C"]))
+    ts = [cu(t, dev).requires_grad_(True) for t in (arm_l, arm_s, odm_l, odm_s)]
+    loss = crit(*ts, [cu(b, dev) for b in bx], [cu(l, dev) for l in lb])
+    loss.backward()
+    ref = float(G["rfd_loss"])
+    assert abs(loss.item() - ref) <= RTOL_LOSS * abs(ref), (loss.item(), ref)
+    for t, k in zip(ts, ("g_arm_l", "g_arm_s", "g_odm_l", "g_odm_s")):
+        want = T(G["rfd_" + k])
+        if t.grad is None:
+            assert float(want.abs().max()) == 0.0
+        else:
+            assert torch.allclose(t.grad.cpu(), want, rtol=RTOL_GRAD, atol=1e-7), k
+
+
+def test_loss_at_ssd512_coco_shape(dev):
+    """P = 24 564, C = 81, G <= 100 (BASELINE config 2), N small enough for the CPU oracle."""
+    from oracle import box_pipeline as O
+    from shape_based_object_detection_b200 import priors as PR, synth
+    from shape_based_object_detection_b200.models import MultiBoxLoss512, RetinaFocalLoss
+    pri = PR.ssd512_canonical_priors()
+    locs, scores, bx, lb = synth.make_train_batch(pri, 3, 81, 100, 1234 + 2)
+    for Mod, variant, reg, cls in ((MultiBoxLoss512, "s512", "", ""), (RetinaFocalLoss, "ret", "DIOU", "FOCAL")):
+        l_c = locs.clone().requires_grad_(True)
+        s_c = scores.clone().requires_grad_(True)
+        want, parts = O.multibox_loss(variant, pri, l_c, s_c, bx, lb, reg_loss=reg, cls_loss=cls, want_parts=True)
+        want.backward()
+        crit = Mod(cu(pri, dev), cfg(reg, cls, 81))
+        l_d = cu(locs, dev).requires_grad_(True)
+        s_d = cu(scores, dev).requires_grad_(True)
+        loss = crit(l_d, s_d, [cu(b, dev) for b in bx], [cu(l, dev) for l in lb])
+        loss.backward()
+        st = crit.last["state"]
+        cls_t, neg_t = st.targets()
+        assert torch.equal(st.obj.cpu().long(), parts["obj"])
+        assert torch.equal(cls_t.cpu(), parts["true_classes"])
+        assert torch.equal(neg_t.cpu(), parts["true_neg_classes"])
+        assert abs(loss.item() - want.item()) <= RTOL_LOSS * abs(want.item()), (loss.item(), want.item())
+        assert torch.allclose(l_d.grad.cpu(), l_c.grad, rtol=RTOL_GRAD, atol=1e-7)
+        assert torch.allclose(s_d.grad.cpu(), s_c.grad, rtol=RTOL_GRAD, atol=1e-7)
+
+
+def test_loss_full_batch_properties(dev):
+    """BASELINE size (N=32, P=24 564, C=81): size-independent properties instead of the oracle —
+    the batch sums are the sums of the per-image partials, permuting the images leaves the loss
+    unchanged, and a half batch reproduces its own partial sums."""
+    from shape_based_object_detection_b200 import priors as PR, synth
+    from shape_based_object_detection_b200.models import MultiBoxLoss512
+    pri = PR.ssd512_canonical_priors()
+    locs, scores, bx, lb = synth.make_train_batch(pri, 32, 81, 100, 1234 + 2)
+    crit = MultiBoxLoss512(cu(pri, dev), cfg("", "", 81))
+    l_d, s_d = cu(locs, dev), cu(scores, dev)
+    bxd, lbd = [cu(b, dev) for b in bx], [cu(l, dev) for l in lb]
+    loss = crit(l_d, s_d, bxd, lbd)
+    st = crit.last["state"]
+    part, sums = st.partials.cpu(), st.sums.cpu()
+    assert torch.allclose(part.sum(0), sums, rtol=1e-12, atol=0)
+    perm = torch.randperm(32, generator=torch.Generator().manual_seed(3)).tolist()
+    loss_p = crit(l_d[perm].contiguous(), s_d[perm].contiguous(), [bxd[i] for i in perm], [lbd[i] for i in perm])
+    assert abs(loss_p.item() - loss.item()) <= 1e-6 * abs(loss.item())
+    assert torch.equal(crit.last["state"].partials.cpu(), part[perm])
+    crit(l_d[:16].contiguous(), s_d[:16].contiguous(), bxd[:16], lbd[:16])
+    assert torch.equal(crit.last["state"].partials.cpu(), part[:16])
+    # every image contributes at least one positive per object with overlap > 0 (forced match)
+    assert float(part[:, 3].min()) >= 1
+
+
+# ---------------------------------------------------------------------------------------------
+# eval path
+# ---------------------------------------------------------------------------------------------
+def _run_detect(case, pri, locs, scores, keep, bt, dev):
+    from shape_based_object_detection_b200.detect_scripts import detect_tools as DT
+    from shape_based_object_detection_b200.models import utils as MU
+    l_d, s_d, p_d = cu(locs, dev).contiguous(), cu(scores, dev), cu(pri, dev)
+    k_d = cu(keep, dev) if keep is not None else None
+    if case["fn"] == "utils.detect":
+        out = MU.detect(l_d, s_d, case["min_score"], case["max_overlap"], case["top_k"], p_d,
+                        cfg(n_classes=case["C"], box_type=bt, focal_type=case.get("focal_type", "softmax")),
+                        prior_positives_idx=k_d)
+    elif case["fn"] == "tools.detect":
+        out = DT.detect(l_d, s_d, case["min_score"], case["max_overlap"], case["top_k"], p_d)
+    else:
+        out = DT.detect_refine(l_d, s_d, case["min_score"], case["max_overlap"], case["top_k"], p_d,
+                               prior_positives_idx=k_d)
+    return out, l_d
+
+
+@pytest.mark.parametrize("name", list(DETECT_CASES))
+def test_detect(golden, dev, name):
+    case, G = DETECT_CASES[name], golden["detect"]
+    pri, locs, scores, keep, bt = detect_inputs(case)
+    (b, l, s), l_d = _run_detect(case, pri, locs, scores, keep, bt, dev)
+    for i in range(case["N"]):
+        want_l, want_s, want_b = T(G[f"{name}_l{i}"]).long(), T(G[f"{name}_s{i}"]), T(G[f"{name}_b{i}"])
+        assert l[i].shape == want_l.shape, (l[i].shape, want_l.shape)
+        assert torch.equal(l[i].cpu(), want_l)
+        assert torch.allclose(s[i].cpu(), want_s, rtol=1e-5, atol=1e-8)
+        assert torch.allclose(b[i].cpu(), want_b, rtol=1e-5, atol=1e-6)
+    if bt == "corner":  # the reference clamps the caller's tensor in place
+        assert float(l_d.min()) >= 0.0 and float(l_d.max()) <= 1.0
+
+
+def test_detect_at_ssd512_coco_shape(dev):
+    """P = 24 564, C = 81 (BASELINE config 2 eval), two images, against the oracle."""
+    from oracle import box_pipeline as O
+    from shape_based_object_detection_b200 import priors as PR, synth
+    from shape_based_object_detection_b200.models import utils as MU
+    import torchvision
+    pri = PR.ssd512_canonical_priors()
+    locs, scores = synth.make_eval_batch(pri, 2, 81, 1234 + 2)
+    want = O.detect(locs.clone(), scores, 0.01, 0.45, 200, pri, nms_fn=torchvision.ops.nms)
+    got = MU.detect(cu(locs, dev), cu(scores, dev), 0.01, 0.45, 200, cu(pri, dev), cfg(n_classes=81))
+    for i in range(2):
+        assert torch.equal(got[1][i].cpu(), want[1][i])
+        assert torch.allclose(got[2][i].cpu(), want[2][i], rtol=1e-5, atol=1e-8)
+        assert torch.allclose(got[0][i].cpu(), want[0][i], rtol=1e-5, atol=1e-6)
+
+
+def test_detect_full_batch_properties(dev):
+    """N = 32 at the BASELINE shape: outputs are score-sorted, within [0,1], at most top_k, and the
+    batch result equals the per-image results (images are independent)."""
+    import shape_based_object_detection_b200 as S
+    from shape_based_object_detection_b200 import priors as PR, synth
+    pri = PR.ssd512_canonical_priors()
+    locs, scores = synth.make_eval_batch(pri, 32, 81, 77)
+    l_d, s_d, p_d = cu(locs, dev), cu(scores, dev), cu(pri, dev)
+    ob, ol, osc, op, oc = S.detect_batched(l_d, s_d, 0.01, 0.45, 200, p_d)
+    counts = oc.cpu()
+    assert int(counts.min()) >= 1 and int(counts.max()) <= 200
+    for i in (0, 7, 31):
+        c = int(counts[i])
+        sc = osc[i, :c].cpu()
+        assert bool((sc[:-1] >= sc[1:]).all())
+        assert float(ob[i, :c].min()) >= 0 and float(ob[i, :c].max()) <= 1
+        b1, l1, s1, p1, c1 = S.detect_batched(l_d[i:i + 1].contiguous(), s_d[i:i + 1].contiguous(), 0.01, 0.45,
+                                              200, p_d)
+        assert int(c1[0]) == c
+        assert torch.equal(l1[0, :c], ol[i, :c]) and torch.equal(p1[0, :c], op[i, :c])
+        assert torch.equal(s1[0, :c], osc[i, :c])

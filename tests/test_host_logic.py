@@ -1,0 +1,77 @@
+"""CPU suite: host-side logic — GT packing, synthetic generators, and the multi-GPU combination rule
+(per-rank partial sums -> one all-reduce -> identical scalar on every rank), world_size 2 over gloo."""
+import os
+
+import numpy as np
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from cases import LOSS_CASES, case_priors
+from oracle import box_pipeline as O
+from shape_based_object_detection_b200 import core, synth
+from shape_based_object_detection_b200.parallel import combine_loss, shard_range
+
+
+def test_pack_ground_truth_csr():
+    boxes = [torch.rand(3, 4), torch.rand(0, 4), torch.rand(5, 4)]
+    labels = [torch.tensor([1, 2, 3]), torch.zeros(0, dtype=torch.long), torch.tensor([4, 4, 1, 2, 9])]
+    b, l, o, gmax = core.pack_ground_truth(boxes, labels, torch.device("cpu"))
+    assert o.tolist() == [0, 3, 3, 8] and gmax == 5 and o.dtype == torch.int32
+    assert torch.equal(b[3:], boxes[2]) and torch.equal(l[:3], labels[0]) and l.dtype == torch.int64
+    b, l, o, gmax = core.pack_ground_truth([torch.rand(0, 4)], [torch.zeros(0, dtype=torch.long)], torch.device("cpu"))
+    assert o.tolist() == [0, 0] and gmax == 0 and b.shape == (1, 4)
+
+
+def test_synthetic_batches_are_seeded_and_in_range():
+    pri = case_priors(LOSS_CASES["s512_sl1_ce"])
+    a = synth.make_train_batch(pri, 2, 6, 8, 5)
+    b = synth.make_train_batch(pri, 2, 6, 8, 5)
+    assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1]) and torch.equal(a[2][1], b[2][1])
+    for bx, lb in zip(a[2], a[3]):
+        assert 1 <= bx.size(0) <= 8 and float(bx.min()) >= 0 and float(bx.max()) <= 1
+        assert int(lb.min()) >= 1 and int(lb.max()) <= 5
+        assert bool((bx[:, 2:] > bx[:, :2]).all())
+
+
+def test_shard_range_covers_batch():
+    for n in (1, 7, 32, 33):
+        for w in (1, 2, 4, 8):
+            spans = [shard_range(n, r, w) for r in range(w)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(spans[i][1] == spans[i + 1][0] for i in range(w - 1))
+            assert max(b - a for a, b in spans) - min(b - a for a, b in spans) <= 1
+
+
+def _oracle_sums(case, lo, hi):
+    """[sum loc, sum conf_pos, sum conf_hardneg, n_pos] of images lo..hi, from the oracle's parts."""
+    pri = case_priors(case)
+    locs, scores, bx, lb = synth.make_train_batch(pri, case["N"], case["C"], case["gmax"], case["seed"])
+    total, parts = O.multibox_loss(case["variant"], pri, locs[lo:hi], scores[lo:hi], bx[lo:hi], lb[lo:hi],
+                                   want_parts=True)
+    n_pos = float(parts["n_pos"].sum())
+    loc_sum = float(parts["loc"]) * n_pos
+    conf_sum = float(parts["conf"]) * n_pos
+    return torch.tensor([loc_sum, conf_sum, 0.0, n_pos], dtype=torch.float64), float(total)
+
+
+def _worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    case = LOSS_CASES["s512_sl1_ce"]
+    lo, hi = shard_range(case["N"], rank, world)
+    sums, _ = _oracle_sums(case, lo, hi)
+    total = combine_loss(sums, reg_kind=1, cls_kind=0, reg_weight=1.0, group=dist.group.WORLD)
+    out[rank] = float(total[0])
+    dist.destroy_process_group()
+
+
+def test_two_rank_allreduce_reproduces_full_batch_loss():
+    case = LOSS_CASES["s512_sl1_ce"]
+    _, want = _oracle_sums(case, 0, case["N"])
+    mgr = mp.Manager()
+    out = mgr.dict()
+    port = 29500 + (os.getpid() % 2000)
+    mp.spawn(_worker, args=(2, port, out), nprocs=2, join=True)
+    assert abs(out[0] - out[1]) == 0.0
+    assert abs(out[0] - want) <= 1e-6 * abs(want)
