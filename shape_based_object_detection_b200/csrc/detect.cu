@@ -610,8 +610,9 @@ static long long cand_capacity(const sbod_detect_desc* d) {
 }
 
 static int kept_capacity(const sbod_detect_desc* d) {
+  // multiple of 16 so that the float4 / u64 arrays carved after each other stay aligned
   if (d->second_nms_thr >= 0.f) return 4096 + kChunk;
-  return d->top_k + 1 + kChunk;
+  return (d->top_k + 1 + kChunk + 15) & ~15;
 }
 
 }  // namespace sbod
