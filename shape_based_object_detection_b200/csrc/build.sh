@@ -8,5 +8,5 @@ NVCC="${NVCC:-/usr/local/cuda/bin/nvcc}"
 srcs=("$here"/*.cu)
 "$NVCC" -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 \
   -Xcompiler -fPIC -Xcompiler -fvisibility=hidden --shared \
-  -Xptxas -v "$@" -o "$out/libsbod.so" "${srcs[@]}"
+  "$@" -o "$out/libsbod.so" "${srcs[@]}"
 echo "built $out/libsbod.so"
