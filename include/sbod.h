@@ -213,7 +213,8 @@ SBOD_API size_t sbod_loss_workspace_bytes(const sbod_loss_desc* d);
  * the same holds for the sbod_assign / sbod_detect workspaces. */
 SBOD_API int sbod_workspace_init(void* workspace, size_t bytes, sbod_stream_t stream);
 SBOD_API int sbod_loss_forward(const sbod_loss_desc* d, sbod_stream_t stream);
-/* Profiling / bench hook: launch one stage of the forward (0 match_lse, 1 forced_match, 2 mine). */
+/* Profiling / bench hook: launch one stage of the forward (0 = match + log-sum-exp kernel,
+ * 1 = mine kernel: forced-match override + mining + batch reduction). */
 SBOD_API int sbod_loss_forward_stage(const sbod_loss_desc* d, int stage, sbod_stream_t stream);
 /* Recompute d->loss from d->sums (after a cross-GPU all-reduce of d->sums). */
 SBOD_API int sbod_loss_finalize(const sbod_loss_desc* d, sbod_stream_t stream);

@@ -20,6 +20,7 @@
 #include <math.h>
 
 #include "common.cuh"
+#include "row_stream.cuh"
 
 namespace sbod {
 
@@ -232,6 +233,173 @@ __global__ void __launch_bounds__(kDRows) detect_score_kernel(const DetParams q)
     if (tid == 0 && it + q.n_stages < n_my)
       issue_dtile(q, blockIdx.x + (it + q.n_stages) * gridDim.x, stage, &bars[s]);
   }
+}
+
+// ------------------------------------------------------------------------------------------
+// detect_score_fast_kernel — odd C <= 128, softmax or sigmoid. Two threads per row (row_stream.cuh),
+// contiguous tile ranges per CTA. Pass 2 of the softmax also builds, per thread, a bit mask of the
+// classes whose un-normalised exp already exceeds min_score (a superset of the candidates, since the
+// row sum is >= 1); only those few are re-evaluated exactly and emitted. The per-image histogram
+// of the key's top digit is accumulated in shared memory and flushed once per image.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kStreamThreads, 2) detect_score_fast_kernel(const DetParams q) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  float* stages = reinterpret_cast<float*>(smem_raw);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + size_t(q.n_stages) * q.stage_floats * 4);
+  __shared__ unsigned int s_hist[kMaxBins];
+  __shared__ unsigned int s_wtot[kStreamThreads / 32];
+  __shared__ unsigned int s_base;
+
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int C = q.C;
+  int t0, t1;
+  tile_range(q.n_tiles, blockIdx.x, gridDim.x, t0, t1);
+  const int n_my = t1 - t0;
+  if (tid == 0) {
+    for (int s = 0; s < q.n_stages; ++s) mbar_init(&bars[s], 1);
+    fence_mbar_init();
+  }
+  for (int b = tid; b < q.n_bins; b += kStreamThreads) s_hist[b] = 0u;
+  __syncthreads();
+  if (tid == 0) {
+    for (int s = 0; s < q.n_stages && s < n_my; ++s)
+      stream_issue(q.scores, q.N, q.P, C, stream_tile(t0 + s, q.tiles_per_image, kTileRows, q.P),
+                   stages + size_t(s) * q.stage_floats, &bars[s]);
+  }
+  int row, h;
+  stream_map(tid, row, h);
+  const int nh = (C + 1 - h) >> 1;
+  int hist_n = -1;
+
+  auto flush_hist = [&](int n) {
+    __syncthreads();
+    unsigned int* gh = q.hist + size_t(n) * q.n_bins;
+    for (int b = tid; b < q.n_bins; b += kStreamThreads) {
+      const unsigned int v = s_hist[b];
+      if (v) {
+        atomicAdd(&gh[b], v);
+        s_hist[b] = 0u;
+      }
+    }
+    __syncthreads();
+  };
+
+  for (int it = 0; it < n_my; ++it) {
+    const StreamTile tc = stream_tile(t0 + it, q.tiles_per_image, kTileRows, q.P);
+    const int n = tc.n;
+    if (n != hist_n) {
+      if (hist_n >= 0) flush_hist(hist_n);
+      hist_n = n;
+    }
+    const bool valid = row < tc.rows;
+    const int r = min(row, tc.rows - 1);
+    const int p = tc.p0 + r;
+    const size_t np = size_t(n) * q.P + p;
+    if (valid && h == 0 && q.clamp_inplace) {  // clamp_ on the caller's tensor (models/utils.py:224)
+      float4* lp = reinterpret_cast<float4*>(q.locs) + np;
+      float4 b = *lp;
+      b.x = fminf(fmaxf(b.x, 0.f), 1.f); b.y = fminf(fmaxf(b.y, 0.f), 1.f);
+      b.z = fminf(fmaxf(b.z, 0.f), 1.f); b.w = fminf(fmaxf(b.w, 0.f), 1.f);
+      *lp = b;
+    }
+    const bool keep_row = valid && (q.prior_keep ? q.prior_keep[np] != 0 : true);
+
+    const int s = it % q.n_stages;
+    float* stage = stages + size_t(s) * q.stage_floats;
+    mbar_wait(&bars[s], (it / q.n_stages) & 1);
+    const size_t first = (size_t(n) * q.P + tc.p0) * size_t(C);
+    const float* rp = stage + (first & 3) + size_t(r) * C + h;
+
+    uint32_t m0 = 0u, m1 = 0u;
+    float nmx2 = 0.f, inv = 1.f;
+    if (q.act_kind == SBOD_ACT_SOFTMAX) {
+      const float mx = half_row_max(rp, nh);
+      nmx2 = -mx * kLog2e;
+      const float sum = half_row_sumexp_mask(rp, nh, nmx2, q.min_score, m0, m1);
+      inv = __frcp_rn(sum);
+    } else {
+      // sigmoid(x) > t  <=>  x > logit(t); keep a small margin, the exact test follows
+      const float t = fminf(fmaxf(q.min_score, 1e-30f), 1.f - 1e-7f);
+      const float lim = logf(t / (1.f - t)) - 1e-3f;
+      for (int j = 0; j < nh; ++j)
+        if (rp[2 * j] > lim) {
+          if (j < 32) m0 |= 1u << j;
+          else m1 |= 1u << (j - 32);
+        }
+    }
+    if (h == 0) m0 &= ~1u;  // class 0 (background) never yields a detection
+    if (!keep_row) m0 = m1 = 0u;
+    // exact test of the few flagged classes: prob = e * (1/sum) > min_score, as the emitted score
+    unsigned int cnt = 0;
+    {
+      uint32_t mm = m0;
+      while (mm) {
+        const int j = __ffs(mm) - 1;
+        mm &= mm - 1;
+        const float x = rp[2 * j];
+        const float pr = q.act_kind == SBOD_ACT_SOFTMAX ? ex2_approx(fmaf(x, kLog2e, nmx2)) * inv
+                                                        : __frcp_rn(1.f + __expf(-x));
+        if (pr > q.min_score) ++cnt; else m0 &= ~(1u << j);
+      }
+      mm = m1;
+      while (mm) {
+        const int j = __ffs(mm) - 1;
+        mm &= mm - 1;
+        const float x = rp[2 * (j + 32)];
+        const float pr = q.act_kind == SBOD_ACT_SOFTMAX ? ex2_approx(fmaf(x, kLog2e, nmx2)) * inv
+                                                        : __frcp_rn(1.f + __expf(-x));
+        if (pr > q.min_score) ++cnt; else m1 &= ~(1u << j);
+      }
+    }
+    // block-exclusive scan of the per-thread counts, one global atomic per tile
+    unsigned int inc = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const unsigned int t = __shfl_up_sync(0xffffffffu, inc, o);
+      if (lane >= o) inc += t;
+    }
+    if (lane == 31) s_wtot[wid] = inc;
+    __syncthreads();
+    unsigned int off = inc - cnt, tot = 0;
+#pragma unroll
+    for (int w = 0; w < kStreamThreads / 32; ++w) {
+      if (w < wid) off += s_wtot[w];
+      tot += s_wtot[w];
+    }
+    if (tid == 0) s_base = tot ? atomicAdd(&q.cand_count[n], tot) : 0u;
+    __syncthreads();
+    if (cnt) {
+      long long slot = (long long)s_base + off;
+      unsigned long long* dst = q.cand + size_t(n) * q.cand_cap;
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        uint32_t mm = half ? m1 : m0;
+        while (mm) {
+          const int j = __ffs(mm) - 1 + 32 * half;
+          mm &= mm - 1;
+          const int k = 2 * j + h;
+          const float x = rp[2 * j];
+          const float pr = q.act_kind == SBOD_ACT_SOFTMAX ? ex2_approx(fmaf(x, kLog2e, nmx2)) * inv
+                                                          : __frcp_rn(1.f + __expf(-x));
+          const uint32_t bits = __float_as_uint(pr);
+          const uint32_t k32 = bits > kOneBits ? 0u : kOneBits - bits;
+          const unsigned long long key = (static_cast<unsigned long long>(k32) << 32) |
+                                         (static_cast<unsigned long long>(k) << kPriorBits) |
+                                         static_cast<unsigned long long>(p);
+          if (slot < q.cand_cap) dst[slot] = key;
+          ++slot;
+          int bin = int(key >> q.shift0);
+          if (bin >= q.n_bins) bin = q.n_bins - 1;
+          atomicAdd(&s_hist[bin], 1u);
+        }
+      }
+    }
+    __syncthreads();  // every thread is done with stage s (and with s_wtot / s_base)
+    if (tid == 0 && it + q.n_stages < n_my)
+      stream_issue(q.scores, q.N, q.P, C,
+                   stream_tile(t0 + it + q.n_stages, q.tiles_per_image, kTileRows, q.P), stage, &bars[s]);
+  }
+  if (hist_n >= 0) flush_hist(hist_n);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -685,6 +853,8 @@ static int detect_run(const sbod_detect_desc* d, sbod_stream_t stream, int stage
   if (!attr_done) {
     SBOD_CUDA_TRY(cudaFuncSetAttribute(detect_score_kernel,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    SBOD_CUDA_TRY(cudaFuncSetAttribute(detect_score_fast_kernel,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024));
     SBOD_CUDA_TRY(cudaFuncSetAttribute(detect_nms_kernel,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
     attr_done = true;
@@ -694,7 +864,28 @@ static int detect_run(const sbod_detect_desc* d, sbod_stream_t stream, int stage
   if (ctas_per_sm > 8) ctas_per_sm = 8;
   int grid = sm_count() * ctas_per_sm;
   if (grid > q.n_tiles) grid = q.n_tiles;
-  if (stage_mask & 1) {
+  const bool fast = (q.C & 1) && q.C <= 128;
+  if (fast) {
+    q.rows_per_tile = kTileRows;
+    q.stage_floats = uint32_t(align_up(size_t(kTileRows) * q.C + 8, 32));
+    const size_t sb = size_t(q.stage_floats) * 4;
+    int ctas = 2;
+    q.n_stages = int((96 * 1024) / sb);
+    if (q.n_stages < 2) {
+      q.n_stages = int((200 * 1024) / sb);
+      ctas = 1;
+    }
+    if (q.n_stages > 4) q.n_stages = 4;
+    q.tiles_per_image = (q.P + kTileRows - 1) / kTileRows;
+    q.n_tiles = q.tiles_per_image * q.N;
+    const size_t fsmem = size_t(q.n_stages) * sb + 4 * 8;
+    int fgrid = sm_count() * ctas;
+    if (fgrid > q.n_tiles) fgrid = q.n_tiles;
+    if (stage_mask & 1) {
+      detect_score_fast_kernel<<<fgrid, kStreamThreads, fsmem, st>>>(q);
+      SBOD_LAUNCH_CHECK();
+    }
+  } else if (stage_mask & 1) {
     detect_score_kernel<<<grid, kDRows, t.smem, st>>>(q);
     SBOD_LAUNCH_CHECK();
   }

@@ -14,9 +14,11 @@
 //   loss_bwd_kernel    grad wrt logits (softmax - onehot on selected rows, zero elsewhere, tiles
 //                      written with bulk TMA stores) and wrt locs.
 #include <math.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "pair_iou.cuh"
+#include "row_stream.cuh"
 
 namespace sbod {
 
@@ -56,6 +58,10 @@ struct LossParams {
   int rows_per_tile, tiles_per_image, n_tiles, n_stages;
   uint32_t stage_floats;
   int with_scores;
+  int mine_cache;  // mine_kernel keeps the P candidate values of its image in shared memory
+  int fast;        // odd C <= 128: warp-specialised two-threads-per-row kernels
+  int ctas_per_sm;
+  int debug_skip;  // SBOD_DEBUG_SKIP: bit0 = no stream role, bit1 = no match role (profiling only)
 };
 
 SBOD_DEVINL int64_t map_label(const LossParams& q, int64_t lab) {
@@ -263,15 +269,12 @@ __global__ void __launch_bounds__(kRows) match_lse_kernel(const LossParams q) {
       for (; k < C; ++k) s0 += __expf(row[k] - mx);
       for (k = 0; k < rot; ++k) s1 += __expf(row[k] - mx);
       const float lg = logf((s0 + s1) + (s2 + s3));
-      int64_t lab = 0;
-      if (G > 0) lab = map_label(q, q.gt_labels[g0 + bobj]);
-      int cls = (best < q.thr_pos || G == 0) ? 0 : int(lab);
-      cls = min(max(cls, 0), C - 1);
-      const float xt = row[cls];
       q.ov[np] = best;
       q.obj[np] = bobj;
       q.lse[np] = mx + lg;
-      q.ce[np] = (mx - xt) + lg;  // == -log_softmax[cls], torch's operation order
+      // CE against class 0 (background) == -log_softmax[0] in torch's operation order; the few
+      // positive rows are re-evaluated against their true class by mine_kernel.
+      q.ce[np] = (mx - row[0]) + lg;
     }
     __syncthreads();  // every thread is done with stage s
     if (tid == 0 && it + q.n_stages < n_my)
@@ -280,22 +283,255 @@ __global__ void __launch_bounds__(kRows) match_lse_kernel(const LossParams q) {
 }
 
 // ------------------------------------------------------------------------------------------
+// match_lse_fast_kernel — warp-specialised version for odd C <= 128 (C = 81, 21, ...).
+//   warps 0-7  (256 threads) "stream" role: consume the TMA ring, two threads per row,
+//              log-sum-exp + background CE per prior. Never touches the ground truth.
+//   warps 8-11 (128 threads) "match" role: prior<->GT IoU with warp-bbox culling, both arg-maxes.
+//              Never touches the logits. Per-object best priors are reduced with REDUX inside
+//              the warp and kept in a per-warp shared array (no shared atomics), flushed to
+//              global memory once per image (tiles of a CTA are contiguous).
+// The two roles share nothing but the SM: ALU-bound matching hides under the memory-bound stream.
+// ------------------------------------------------------------------------------------------
+constexpr int kMatchWarps = 8;
+constexpr int kMatchThreads = 32 * kMatchWarps;
+constexpr int kMatchChunk = 1024;  // priors per match work item
+constexpr int kFastThreads = kStreamThreads + kMatchThreads;
+
+__global__ void __launch_bounds__(kFastThreads, 2) match_lse_fast_kernel(const LossParams q) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  float* stages = reinterpret_cast<float*>(smem_raw);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + size_t(q.n_stages) * q.stage_floats * 4);
+  __shared__ float4 s_gbox[kGtChunk];
+  __shared__ float s_garea[kGtChunk];
+  __shared__ unsigned long long s_wkey[kMatchWarps][kGtChunk];
+  __shared__ uint8_t s_gskip[kGtChunk];
+  __shared__ int s_gok;
+  __shared__ int s_item;
+
+  const int tid = threadIdx.x, lane = tid & 31;
+  int t0, t1;
+  tile_range(q.n_tiles, blockIdx.x, gridDim.x, t0, t1);
+  const int n_my = t1 - t0;
+  const int C = q.C;
+  if (tid == 0) {
+    for (int s = 0; s < q.n_stages; ++s) mbar_init(&bars[s], 1);
+    fence_mbar_init();
+  }
+  __syncthreads();
+
+  if (tid < kStreamThreads) {
+    // =========================== stream role ===========================
+    if (q.debug_skip & 1) return;
+    if (tid == 0) {
+      for (int s = 0; s < q.n_stages && s < n_my; ++s)
+        stream_issue(q.scores, q.N, q.P, C, stream_tile(t0 + s, q.tiles_per_image, kTileRows, q.P),
+                     stages + size_t(s) * q.stage_floats, &bars[s]);
+    }
+    int row, h;
+    stream_map(tid, row, h);
+    const int nh = (C + 1 - h) >> 1;
+    for (int it = 0; it < n_my; ++it) {
+      const StreamTile tc = stream_tile(t0 + it, q.tiles_per_image, kTileRows, q.P);
+      const int s = it % q.n_stages;
+      float* stage = stages + size_t(s) * q.stage_floats;
+      mbar_wait(&bars[s], (it / q.n_stages) & 1);
+      const size_t first = (size_t(tc.n) * q.P + tc.p0) * size_t(C);
+      const int r = min(row, tc.rows - 1);  // keep every lane in the shuffles
+      const float* rbase = stage + (first & 3) + size_t(r) * C;
+      const float mx = half_row_max(rbase + h, nh);
+      const float sum = half_row_sumexp(rbase + h, nh, -mx * kLog2e);
+      if (h == 0 && row < tc.rows) {
+        const float lg = logf(sum);
+        const size_t np = size_t(tc.n) * q.P + tc.p0 + row;
+        q.lse[np] = mx + lg;
+        q.ce[np] = (mx - rbase[0]) + lg;  // background CE, torch's operation order
+      }
+      named_bar_sync(1, kStreamThreads);  // the stream group is done with stage s
+      if (tid == 0 && it + q.n_stages < n_my)
+        stream_issue(q.scores, q.N, q.P, C,
+                     stream_tile(t0 + it + q.n_stages, q.tiles_per_image, kTileRows, q.P), stage, &bars[s]);
+    }
+    return;
+  }
+
+  // =========================== match role ===========================
+  // Work items are (image, chunk of kMatchChunk priors), pulled from a global queue heaviest first
+  // (the large priors at the end of every image overlap almost every object), so the matching
+  // load is balanced across the whole grid independently of the tiles the stream role owns.
+  if (q.debug_skip & 2) return;
+  const int tm = tid - kStreamThreads, wm = tm >> 5;
+  const float INF = __int_as_float(0x7f800000);
+  const int chunks_per_image = (q.P + kMatchChunk - 1) / kMatchChunk;
+  const int n_items = chunks_per_image * q.N;
+  int prev_n = -1, g0 = 0, G = 0;
+  bool resident = false;
+
+  auto load_chunk = [&](int c0, int gc) {
+    named_bar_sync(2, kMatchThreads);
+    if (tm == 0) s_gok = 1;
+    named_bar_sync(2, kMatchThreads);
+    bool ok = true;
+    for (int i = tm; i < gc; i += kMatchThreads) {
+      const float4 g = q.gt_boxes[g0 + c0 + i];
+      s_gbox[i] = g;
+      s_garea[i] = box_area_rn(g);
+      s_gskip[i] = gt_is_zero(g) ? 1 : 0;
+      ok = ok && (g.z >= g.x) && (g.w >= g.y);
+#pragma unroll
+      for (int w = 0; w < kMatchWarps; ++w) s_wkey[w][i] = 0ull;
+    }
+    if (!ok) s_gok = 0;
+    named_bar_sync(2, kMatchThreads);
+  };
+  auto flush_chunk = [&](int n, int c0, int gc) {
+    named_bar_sync(2, kMatchThreads);
+    for (int i = tm; i < gc; i += kMatchThreads) {
+      unsigned long long k = s_wkey[0][i];
+#pragma unroll
+      for (int w = 1; w < kMatchWarps; ++w) k = max(k, s_wkey[w][i]);
+      if (k) atomicMax(&q.gtkey[size_t(n) * q.gmax + c0 + i], k);
+    }
+  };
+
+  for (;;) {
+    named_bar_sync(2, kMatchThreads);
+    if (tm == 0) s_item = int(atomicAdd(&q.counters[1], 1u));
+    named_bar_sync(2, kMatchThreads);
+    const int item = s_item;
+    if (item >= n_items) break;
+    const int n = item % q.N;
+    const int chunk = chunks_per_image - 1 - item / q.N;  // heaviest (last) chunks first
+    if (n != prev_n) {
+      if (prev_n >= 0 && resident) flush_chunk(prev_n, 0, G);
+      g0 = q.gt_offsets[n];
+      G = q.gt_offsets[n + 1] - g0;
+      resident = G <= kGtChunk;
+      if (resident) load_chunk(0, G);
+      prev_n = n;
+    }
+    const int pc0 = chunk * kMatchChunk;
+    const int pc1 = min(q.P, pc0 + kMatchChunk);
+
+    for (int c0 = 0; c0 < max(G, 1); c0 += kGtChunk) {
+      const int gc = min(kGtChunk, G - c0);
+      if (!resident) load_chunk(c0, gc);
+      const bool gok = s_gok != 0;
+      // every warp walks its share of the chunk's 32-prior slices
+      for (int ps = pc0 + 32 * wm; ps < pc1; ps += 32 * kMatchWarps) {
+        const int p = ps + lane;
+        const bool valid = p < pc1;
+        const size_t np = size_t(n) * q.P + (valid ? p : pc0);
+        float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (valid) a = q.anchors_xy ? q.anchors_xy[np] : q.priors_xy[p];
+        const float aa = box_area_rn(a);
+        const bool azero = anchor_is_zero(a);
+        const bool active = valid && !azero;
+        const bool warp_a_ok = __all_sync(0xffffffffu, ((a.z >= a.x) && (a.w >= a.y)) || !valid) != 0;
+        float best = -INF;
+        int bobj = 0;
+        if (c0 > 0 && valid) {  // continue the running arg-max of an earlier object chunk
+          best = q.ov[np];
+          bobj = q.obj[np];
+        }
+        if (gok && warp_a_ok) {
+          const float bx1 = warp_min(active ? a.x : INF), by1 = warp_min(active ? a.y : INF);
+          const float bx2 = warp_max(active ? a.z : -INF), by2 = warp_max(active ? a.w : -INF);
+          float cbest = azero ? -1.f : 0.f;
+          int cidx = c0;
+          for (int base = 0; base < gc; base += 32) {
+            const int i = base + lane;
+            bool hit = false;
+            if (i < gc && !s_gskip[i]) {
+              const float4 g = s_gbox[i];
+              hit = (g.z > bx1) && (g.x < bx2) && (g.w > by1) && (g.y < by2);
+            }
+            unsigned m = __ballot_sync(0xffffffffu, hit);
+            while (m) {
+              const int j = base + (__ffs(m) - 1);
+              m &= m - 1;
+              float iou = 0.f;
+              if (active) {
+                const float inner = inter_rn(s_gbox[j], a);
+                if (inner > 0.f)
+                  iou = __fdiv_rn(inner, __fadd_rn(__fsub_rn(__fadd_rn(s_garea[j], aa), inner), kEps));
+              }
+              if (iou > cbest) {
+                cbest = iou;
+                cidx = c0 + j;
+              }
+              // Best prior of object j seen by this warp so far (max IoU, then lowest prior index).
+              // The cross-lane reduction only runs when some lane beats the stored value.
+              const unsigned long long cur = s_wkey[wm][j];
+              const unsigned bits = __float_as_uint(iou);
+              const unsigned cur_bits = unsigned(cur >> 32);
+              const unsigned cur_p = 0xffffffffu - unsigned(cur & 0xffffffffull);
+              const bool better = bits > cur_bits || (bits == cur_bits && bits != 0u && unsigned(p) < cur_p);
+              if (__any_sync(0xffffffffu, better)) {
+                const unsigned mb = __reduce_max_sync(0xffffffffu, bits);
+                const unsigned pm = __reduce_min_sync(0xffffffffu, bits == mb ? unsigned(p) : 0xffffffffu);
+                if (lane == 0) s_wkey[wm][j] = (static_cast<unsigned long long>(mb) << 32) | (0xffffffffu - pm);
+              }
+            }
+          }
+          if (cbest > best) {
+            best = cbest;
+            bobj = cidx;
+          }
+        } else if (valid) {
+          for (int j = 0; j < gc; ++j) {
+            float iou = iou_metrics_rn(s_gbox[j], s_garea[j], a, aa);
+            if (s_gskip[j]) iou = 0.f;
+            if (azero) iou = -1.f;
+            if (iou > best) {
+              best = iou;
+              bobj = c0 + j;
+            }
+            if (iou > 0.f) {
+              const unsigned long long key =
+                  (static_cast<unsigned long long>(__float_as_uint(iou)) << 32) |
+                  (0xffffffffu - unsigned(p));
+              if (key > s_wkey[wm][j]) atomicMax(&s_wkey[wm][j], key);
+            }
+          }
+        }
+        if (G == 0) {
+          best = 0.f;
+          bobj = 0;
+        }
+        if (valid) {
+          q.ov[np] = best;
+          q.obj[np] = bobj;
+        }
+      }
+      if (!resident) flush_chunk(n, c0, gc);
+    }
+  }
+  if (prev_n >= 0 && resident) flush_chunk(prev_n, 0, G);
+  // the last match group to finish resets the queue for the next launch
+  named_bar_sync(2, kMatchThreads);
+  if (tm == 0) {
+    __threadfence();
+    if (atomicAdd(&q.counters[2], 1u) == gridDim.x - 1) {
+      q.counters[1] = 0u;
+      q.counters[2] = 0u;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
 // forced_match_kernel: one CTA per image
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) forced_match_kernel(const LossParams q) {
-  extern __shared__ __align__(128) unsigned char smem_raw[];
-  uint32_t* s_prior = reinterpret_cast<uint32_t*>(smem_raw);  // [gmax]
-  int32_t* s_rank = reinterpret_cast<int32_t*>(s_prior + q.gmax);  // [gmax], -1 = filtered out
-  __shared__ int s_warp_tot[8];
-  __shared__ int s_carry;
-
-  const int n = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+// Works for any block size that is a multiple of 32 (<= 1024). s_prior/s_rank: [gmax] each.
+__device__ void forced_match_phase(const LossParams& q, int n, uint32_t* s_prior, int32_t* s_rank,
+                                   int* s_warp_tot /*[32]*/, int* s_carry) {
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int nt = blockDim.x, nw = nt >> 5;
   const int g0 = q.gt_offsets[n];
   const int G = q.gt_offsets[n + 1] - g0;
-  if (tid == 0) s_carry = 0;
+  if (tid == 0) *s_carry = 0;
   __syncthreads();
   // rank j of each object inside the filtered list "objects whose best overlap is > 0"
-  for (int base = 0; base < G; base += 256) {
+  for (int base = 0; base < G; base += nt) {
     const int g = base + tid;
     unsigned long long key = 0ull;
     if (g < G) {
@@ -307,7 +543,7 @@ __global__ void __launch_bounds__(256) forced_match_kernel(const LossParams q) {
     const int in_warp = __popc(bal & ((1u << lane) - 1u));
     if (lane == 0) s_warp_tot[wid] = __popc(bal);
     __syncthreads();
-    int off = s_carry;
+    int off = *s_carry;
     for (int w = 0; w < wid; ++w) off += s_warp_tot[w];
     if (g < G) {
       s_prior[g] = 0xffffffffu - uint32_t(key & 0xffffffffull);
@@ -316,12 +552,12 @@ __global__ void __launch_bounds__(256) forced_match_kernel(const LossParams q) {
     __syncthreads();
     if (tid == 0) {
       int t = 0;
-      for (int w = 0; w < 8; ++w) t += s_warp_tot[w];
-      s_carry += t;
+      for (int w = 0; w < nw; ++w) t += s_warp_tot[w];
+      *s_carry += t;
     }
     __syncthreads();
   }
-  for (int g = tid; g < G; g += 256) {
+  for (int g = tid; g < G; g += nt) {
     const int j = s_rank[g];
     if (j < 0) continue;
     const uint32_t p = s_prior[g];
@@ -333,16 +569,17 @@ __global__ void __launch_bounds__(256) forced_match_kernel(const LossParams q) {
       }
     const size_t np = size_t(n) * q.P + p;
     q.ov[np] = 1.0f;
-    if (winner) {
-      q.obj[np] = j;
-      if (q.with_scores) {
-        const int64_t lab = map_label(q, q.gt_labels[g0 + j]);
-        int cls = (1.0f < q.thr_pos) ? 0 : int(lab);
-        cls = min(max(cls, 0), q.C - 1);
-        q.ce[np] = q.lse[np] - q.scores[np * q.C + cls];
-      }
-    }
+    if (winner) q.obj[np] = j;
   }
+}
+
+__global__ void __launch_bounds__(256) forced_match_kernel(const LossParams q) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  uint32_t* s_prior = reinterpret_cast<uint32_t*>(smem_raw);       // [gmax]
+  int32_t* s_rank = reinterpret_cast<int32_t*>(s_prior + q.gmax);  // [gmax], -1 = filtered out
+  __shared__ int s_warp_tot[32];
+  __shared__ int s_carry;
+  forced_match_phase(q, blockIdx.x, s_prior, s_rank, s_warp_tot, &s_carry);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -561,49 +798,85 @@ SBOD_DEVINL void finalize_loss(const LossParams& q, const double* sums, float* l
 }
 
 __global__ void __launch_bounds__(kMineThreads) mine_kernel(const LossParams q) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  uint32_t* s_prior = reinterpret_cast<uint32_t*>(smem_raw);       // [gmax]
+  int32_t* s_rank = reinterpret_cast<int32_t*>(s_prior + q.gmax);  // [gmax]
+  float* s_vals = reinterpret_cast<float*>(smem_raw + ((size_t(q.gmax) * 8 + 127) & ~size_t(127)));  // [P] if cached
   __shared__ unsigned int s_hist[kBins];
   __shared__ double s_red[34];
   __shared__ int s_misc[8];
+  __shared__ int s_warp_tot[32];
+  __shared__ int s_carry;
   const int n = blockIdx.x, tid = threadIdx.x;
   const int g0 = q.gt_offsets[n];
   const int G = q.gt_offsets[n + 1] - g0;
   const size_t base = size_t(n) * q.P;
   const bool focal = q.cls_kind == SBOD_CLS_FOCAL_SUM || q.cls_kind == SBOD_CLS_FOCAL_NORM;
+  const bool to_global = !q.mine_cache || q.cls_kind == SBOD_CLS_CE_MINE_BATCH;
+  float* vals = q.mine_cache ? s_vals : q.cand + base;
+
+  // phase 0: the forced-match override of this image (patches <= G entries of ov / obj)
+  forced_match_phase(q, n, s_prior, s_rank, s_warp_tot, &s_carry);
+  __threadfence();
+  __syncthreads();
 
   double a_loc = 0.0, a_pos = 0.0, a_neg = 0.0;
   int npos = 0;
-  for (int p = tid; p < q.P; p += kMineThreads) {
-    const float ov = q.ov[base + p];
-    const int obj = q.obj[base + p];
-    const float ce = q.ce[base + p];
-    const bool ex = q.exclude ? q.exclude[base + p] != 0 : false;
-    int64_t lab = 0;
-    if (G > 0) lab = map_label(q, q.gt_labels[g0 + obj]);
-    const int64_t cls = (ov < q.thr_pos) ? 0 : lab;
-    const bool pos = cls > 0 && !ex;
-    const bool isneg = ov < q.thr_neg;
-    uint8_t selbits = 0;
-    float v = -1.f;
-    if (pos) {
-      selbits = 1;
-      ++npos;
-      a_pos += focal ? double(focal_fg(q, ce)) : double(ce);
-      const float4 pred = reinterpret_cast<const float4*>(q.locs)[base + p];
-      const LocTerm lt = loc_term<false>(q, pred, prior_cxcy_of(q, n, p), q.gt_boxes[g0 + obj]);
-      a_loc += double(lt.loss);
+  constexpr int U = 4;
+  for (int p0 = tid; p0 < q.P; p0 += kMineThreads * U) {
+    float ov_[U], ce_[U];
+    int obj_[U];
+    uint8_t ex_[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int p = p0 + u * kMineThreads;
+      const bool in = p < q.P;
+      ov_[u] = in ? q.ov[base + p] : 0.f;
+      obj_[u] = in ? q.obj[base + p] : 0;
+      ce_[u] = in ? q.ce[base + p] : 0.f;
+      ex_[u] = (in && q.exclude) ? q.exclude[base + p] : uint8_t(0);
     }
-    if (focal) {
-      if (isneg && !pos) {  // target class is 0 there (thr_neg < thr_pos)
-        selbits |= 2;
-        a_neg += double(focal_bg(q, ce));
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int p = p0 + u * kMineThreads;
+      if (p >= q.P) continue;
+      const float ov = ov_[u];
+      const int obj = obj_[u];
+      float ce = ce_[u];
+      const bool ex = ex_[u] != 0;
+      int64_t cls = 0;
+      if (!(ov < q.thr_pos) && G > 0) cls = map_label(q, q.gt_labels[g0 + obj]);
+      const bool pos = cls > 0 && !ex;
+      const bool isneg = ov < q.thr_neg;
+      uint8_t selbits = 0;
+      float v = -1.f;
+      if (cls > 0) {  // CE of the row against its true class (the streamed value is the background CE)
+        const int c = min(int(cls), q.C - 1);
+        ce = q.lse[base + p] - q.scores[(base + p) * q.C + c];
+        q.ce[base + p] = ce;
       }
-    } else if (q.cls_kind == SBOD_CLS_CE_MINE_NONPOS) {
-      if (!pos && !ex) v = ce;
-    } else {  // MINE_NEG, MINE_BATCH: only true_neg == -1 rows are candidates
-      if (isneg && !pos) v = ce;
+      if (pos) {
+        selbits = 1;
+        ++npos;
+        a_pos += focal ? double(focal_fg(q, ce)) : double(ce);
+        const float4 pred = reinterpret_cast<const float4*>(q.locs)[base + p];
+        const LocTerm lt = loc_term<false>(q, pred, prior_cxcy_of(q, n, p), q.gt_boxes[g0 + obj]);
+        a_loc += double(lt.loss);
+      }
+      if (focal) {
+        if (isneg && !pos) {  // target class is 0 there (thr_neg < thr_pos)
+          selbits |= 2;
+          a_neg += double(focal_bg(q, ce));
+        }
+      } else if (q.cls_kind == SBOD_CLS_CE_MINE_NONPOS) {
+        if (!pos && !ex) v = ce;
+      } else {  // MINE_NEG, MINE_BATCH: only true_neg == -1 rows are candidates
+        if (isneg && !pos) v = ce;
+      }
+      q.sel[base + p] = selbits;
+      if (q.mine_cache) s_vals[p] = v;
+      if (to_global) q.cand[base + p] = v;
     }
-    q.sel[base + p] = selbits;
-    q.cand[base + p] = v;
   }
   const double t_loc = block_sum(a_loc, s_red);
   const double t_pos = block_sum(a_pos, s_red);
@@ -616,8 +889,8 @@ __global__ void __launch_bounds__(kMineThreads) mine_kernel(const LossParams q) 
   } else {
     __syncthreads();
     const long long k = (long long)(q.ratio) * (long long)(t_npos + 0.5);
-    const SelectResult r = topk_sum(q.cand + base, q.P, k, s_hist, s_red, s_misc);
-    mark_selected(q.cand + base, q.sel + base, q.P, r, s_misc);
+    const SelectResult r = topk_sum(vals, q.P, k, s_hist, s_red, s_misc);
+    mark_selected(vals, q.sel + base, q.P, r, s_misc);
     t_neg = r.sum;
   }
   if (tid == 0) {
@@ -911,13 +1184,32 @@ static int fill_params(const sbod_loss_desc* d, LossParams& q, bool need_scores)
   q.gtkey = reinterpret_cast<unsigned long long*>(w);
   w += align_up(size_t(q.N) * q.gmax * 8, 256);
   q.cand = reinterpret_cast<float*>(w);
-  const Tiling t = choose_tiling(need_scores ? d->C : 1, kMaxStages);
+  Tiling t = choose_tiling(need_scores ? d->C : 1, kMaxStages);
+  q.fast = (need_scores && (d->C & 1) && d->C <= 128) ? 1 : 0;
+  q.ctas_per_sm = 2;
+  if (q.fast) {  // 128-row tiles; two CTAs per SM whenever two stages fit in ~90 KB
+    t.rows = kTileRows;
+    t.stage_floats = uint32_t(align_up(size_t(kTileRows) * d->C + 8, 32));
+    const size_t sb = size_t(t.stage_floats) * 4;
+    t.stages = int((90 * 1024) / sb);
+    if (t.stages < 2) {
+      t.stages = int((190 * 1024) / sb);
+      q.ctas_per_sm = 1;
+    }
+    if (t.stages > kMaxStages) t.stages = kMaxStages;
+    t.smem = size_t(t.stages) * sb + kMaxStages * 8;
+  }
   q.rows_per_tile = t.rows;
   q.tiles_per_image = (q.P + t.rows - 1) / t.rows;
   q.n_tiles = q.tiles_per_image * q.N;
   q.n_stages = t.stages;
   q.stage_floats = t.stage_floats;
   q.with_scores = need_scores ? 1 : 0;
+  {
+    const char* e = getenv("SBOD_DEBUG_SKIP");
+    q.debug_skip = e ? atoi(e) : 0;
+  }
+  q.mine_cache = (size_t(q.P) * 4 + align_up(size_t(q.gmax) * 8, 128) <= 196 * 1024) ? 1 : 0;
   return SBOD_OK;
 }
 
@@ -939,35 +1231,52 @@ extern "C" int sbod_workspace_init(void* workspace, size_t bytes, sbod_stream_t 
   return SBOD_OK;
 }
 
-static int launch_match(const LossParams& q, cudaStream_t st, int stage_mask = 3) {
+static int set_kernel_attrs() {
+  static bool attr_done = false;
+  if (attr_done) return SBOD_OK;
+  SBOD_CUDA_TRY(cudaFuncSetAttribute(match_lse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  SBOD_CUDA_TRY(cudaFuncSetAttribute(match_lse_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  SBOD_CUDA_TRY(cudaFuncSetAttribute(loss_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  SBOD_CUDA_TRY(cudaFuncSetAttribute(forced_match_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+  SBOD_CUDA_TRY(cudaFuncSetAttribute(mine_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 205 * 1024));
+  attr_done = true;
+  return SBOD_OK;
+}
+
+static int launch_match(const LossParams& q, cudaStream_t st) {
+  int rc = set_kernel_attrs();
+  if (rc) return rc;
+  if (q.fast) {
+    const size_t smem = size_t(q.n_stages) * q.stage_floats * 4 + kMaxStages * 8;
+    int grid = sm_count() * q.ctas_per_sm;
+    if (grid > q.n_tiles) grid = q.n_tiles;
+    match_lse_fast_kernel<<<grid, kFastThreads, smem, st>>>(q);
+    SBOD_LAUNCH_CHECK();
+    return SBOD_OK;
+  }
   const Tiling t = choose_tiling(q.with_scores ? q.C : 1, kMaxStages);
   const size_t smem = q.with_scores ? t.smem : 0;
-  static bool attr_done = false;
-  if (!attr_done) {
-    SBOD_CUDA_TRY(cudaFuncSetAttribute(match_lse_kernel,
-                                       cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    SBOD_CUDA_TRY(cudaFuncSetAttribute(loss_bwd_kernel,
-                                       cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    SBOD_CUDA_TRY(cudaFuncSetAttribute(forced_match_kernel,
-                                       cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-    attr_done = true;
-  }
-  int ctas_per_sm = 2;
+  int ctas_per_sm = 8;
   if (smem > 0) {
     ctas_per_sm = int((220 * 1024) / (smem + 9 * 1024));
     if (ctas_per_sm < 1) ctas_per_sm = 1;
     if (ctas_per_sm > 8) ctas_per_sm = 8;
-  } else {
-    ctas_per_sm = 8;
   }
   int grid = sm_count() * ctas_per_sm;
   if (grid > q.n_tiles) grid = q.n_tiles;
-  if (stage_mask & 1) {
-    match_lse_kernel<<<grid, kRows, smem, st>>>(q);
-    SBOD_LAUNCH_CHECK();
-  }
-  if (stage_mask & 2) {
-    forced_match_kernel<<<q.N, 256, size_t(q.gmax) * 8, st>>>(q);
+  match_lse_kernel<<<grid, kRows, smem, st>>>(q);
+  SBOD_LAUNCH_CHECK();
+  return SBOD_OK;
+}
+
+static int launch_mine(const LossParams& q, cudaStream_t st) {
+  int rc = set_kernel_attrs();
+  if (rc) return rc;
+  const size_t smem = align_up(size_t(q.gmax) * 8, 128) + (q.mine_cache ? size_t(q.P) * 4 : 0);
+  mine_kernel<<<q.N, kMineThreads, smem, st>>>(q);
+  SBOD_LAUNCH_CHECK();
+  if (q.cls_kind == SBOD_CLS_CE_MINE_BATCH) {
+    mine_batch_kernel<<<1, kMineThreads, 0, st>>>(q);
     SBOD_LAUNCH_CHECK();
   }
   return SBOD_OK;
@@ -980,33 +1289,20 @@ extern "C" int sbod_loss_forward(const sbod_loss_desc* d, sbod_stream_t stream) 
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   rc = launch_match(q, st);
   if (rc) return rc;
-  mine_kernel<<<q.N, kMineThreads, 0, st>>>(q);
-  SBOD_LAUNCH_CHECK();
-  if (q.cls_kind == SBOD_CLS_CE_MINE_BATCH) {
-    mine_batch_kernel<<<1, kMineThreads, 0, st>>>(q);
-    SBOD_LAUNCH_CHECK();
-  }
-  return SBOD_OK;
+  return launch_mine(q, st);
 }
 
-// Profiling / bench hook: launch ONE stage of sbod_loss_forward (0 = match_lse_kernel, 1 =
-// forced_match_kernel, 2 = mine_kernel [+ mine_batch_kernel]). Stage 0 may be repeated; stage 1 must
-// follow before the workspace is used by a full forward again.
+// Profiling / bench hook: launch ONE stage of sbod_loss_forward: 0 = the match + log-sum-exp kernel,
+// 1 = mine_kernel (forced-match override + mining + reduction) [+ mine_batch_kernel]. Stage 0 may be
+// repeated; stage 1 must follow before the workspace is used by a full forward again.
 extern "C" int sbod_loss_forward_stage(const sbod_loss_desc* d, int stage, sbod_stream_t stream) {
   LossParams q;
   int rc = fill_params(d, q, true);
   if (rc) return rc;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (stage == 0) return launch_match(q, st, 1);
-  if (stage == 1) return launch_match(q, st, 2);
-  if (stage != 2) return SBOD_ERR_INVALID;
-  mine_kernel<<<q.N, kMineThreads, 0, st>>>(q);
-  SBOD_LAUNCH_CHECK();
-  if (q.cls_kind == SBOD_CLS_CE_MINE_BATCH) {
-    mine_batch_kernel<<<1, kMineThreads, 0, st>>>(q);
-    SBOD_LAUNCH_CHECK();
-  }
-  return SBOD_OK;
+  if (stage == 0) return launch_match(q, st);
+  if (stage == 1) return launch_mine(q, st);
+  return SBOD_ERR_INVALID;
 }
 
 extern "C" int sbod_loss_finalize(const sbod_loss_desc* d, sbod_stream_t stream) {
@@ -1106,8 +1402,13 @@ extern "C" int sbod_assign(const float* gt_boxes, const int64_t* gt_labels,
   q.stage_floats = 0;
   q.with_scores = 0;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  q.fast = 0;
+  q.mine_cache = 0;
+  q.ctas_per_sm = 8;
   int rc = launch_match(q, st);
   if (rc) return rc;
+  forced_match_kernel<<<q.N, 256, size_t(q.gmax) * 8, st>>>(q);
+  SBOD_LAUNCH_CHECK();
   if (cls_out || neg_out) {
     const size_t total = size_t(N) * P;
     int grid = int((total + 255) / 256);

@@ -56,8 +56,7 @@ st.forward()
 torch.cuda.synchronize()
 print("loss", st.loss.tolist())
 t = time_seq([lambda: L.check(lib.sbod_loss_forward_stage(C.byref(st.desc), 0, sp)),
-              lambda: L.check(lib.sbod_loss_forward_stage(C.byref(st.desc), 1, sp)),
-              lambda: L.check(lib.sbod_loss_forward_stage(C.byref(st.desc), 2, sp))])
+              lambda: L.check(lib.sbod_loss_forward_stage(C.byref(st.desc), 1, sp))])
 gl = torch.ones(1, device=dev)
 g_l = torch.empty_like(st.locs)
 g_s = torch.empty_like(st.scores)
@@ -87,6 +86,6 @@ td = time_seq([lambda: L.check(lib.sbod_detect_stage(C.byref(d), 0, sp)),
                lambda: L.check(lib.sbod_detect_stage(C.byref(d), 1, sp))])
 byt = N * P * Cn * 4
 print(f"shape {NAME} N={N} P={P} C={Cn} G<={G}  logits {byt/1e6:.1f} MB")
-for nm, ms in (("match_lse", t[0]), ("forced_match", t[1]), ("mine", t[2]), ("fwd (3 kernels, python call)", tf[0]),
+for nm, ms in (("match_lse", t[0]), ("mine (+forced)", t[1]), ("fwd (2 kernels, python call)", tf[0]),
                ("loss_bwd", tb[0]), ("detect_score", td[0]), ("detect_nms", td[1])):
     print(f"{nm:32s} {ms*1e3:9.1f} us   {byt/ms/1e6:8.1f} GB/s of logits")
