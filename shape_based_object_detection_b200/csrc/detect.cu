@@ -18,6 +18,7 @@
 //                        candidates run out first, everything is kept and emitted class-major,
 //                        exactly as the reference does.
 #include <math.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "row_stream.cuh"
@@ -56,6 +57,7 @@ struct DetParams {
   long long cand_cap;
   int n_bins, shift0;           // level-0 digit = key >> shift0
   int kcap;                     // kept-list capacity in smem
+  int debug_skip;               // SBOD_DEBUG_SKIP (profiling): bit0 no emission, bit1 no exact refine
   // tiling
   int rows_per_tile, tiles_per_image, n_tiles, n_stages;
   uint32_t stage_floats;
@@ -328,6 +330,7 @@ __global__ void __launch_bounds__(kStreamThreads, 2) detect_score_fast_kernel(co
         }
     }
     if (h == 0) m0 &= ~1u;  // class 0 (background) never yields a detection
+    if (q.debug_skip & 2) m0 = m1 = 0u;
     if (!keep_row) m0 = m1 = 0u;
     // exact test of the few flagged classes: prob = e * (1/sum) > min_score, as the emitted score
     unsigned int cnt = 0;
@@ -368,7 +371,7 @@ __global__ void __launch_bounds__(kStreamThreads, 2) detect_score_fast_kernel(co
     }
     if (tid == 0) s_base = tot ? atomicAdd(&q.cand_count[n], tot) : 0u;
     __syncthreads();
-    if (cnt) {
+    if (cnt && !(q.debug_skip & 1)) {
       long long slot = (long long)s_base + off;
       unsigned long long* dst = q.cand + size_t(n) * q.cand_cap;
 #pragma unroll
@@ -525,11 +528,21 @@ __global__ void __launch_bounds__(kNmsThreads) detect_nms_kernel(const DetParams
     // ---- gather the chunk -----------------------------------------------------------------
     if (tid == 0) S.misc[3] = 0;
     __syncthreads();
-    for (long long i = tid; i < total; i += kNmsThreads) {
-      const unsigned long long k = g_cand[i];
-      if (k >= lo_key && (k < hi_key || hi_key == ~0ull)) {
-        const int slot = atomicAdd(&S.misc[3], 1);
-        if (slot < kChunk) S.ckey[slot] = k;
+    // eight independent 8-byte loads in flight per thread (the list lives in L2 / HBM)
+    for (long long i0 = tid; i0 < total; i0 += 8LL * kNmsThreads) {
+      unsigned long long kk[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const long long i = i0 + (long long)u * kNmsThreads;
+        kk[u] = i < total ? g_cand[i] : ~0ull;
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const unsigned long long k = kk[u];
+        if (k != ~0ull && k >= lo_key && (k < hi_key || hi_key == ~0ull)) {
+          const int slot = atomicAdd(&S.misc[3], 1);
+          if (slot < kChunk) S.ckey[slot] = k;
+        }
       }
     }
     __syncthreads();
@@ -835,6 +848,10 @@ static int detect_run(const sbod_detect_desc* d, sbod_stream_t stream, int stage
   level0_layout(d->min_score, &q.shift0, &q.n_bins);
   q.cand_cap = cand_capacity(d);
   q.kcap = kept_capacity(d);
+  {
+    const char* e = getenv("SBOD_DEBUG_SKIP");
+    q.debug_skip = e ? atoi(e) : 0;
+  }
   unsigned char* w = static_cast<unsigned char*>(d->workspace);
   q.cand_count = reinterpret_cast<unsigned int*>(w); w += align_up(size_t(q.N) * 4, 256);
   q.hist = reinterpret_cast<unsigned int*>(w);       w += align_up(size_t(q.N) * kMaxBins * 4, 256);

@@ -53,6 +53,7 @@ struct LossParams {
   // workspace
   unsigned long long* gtkey;  // [N, gmax]
   float* cand;                // [N, P]
+  double* blockpart;          // [N, ceil(P/1024), 4]
   unsigned int* counters;     // [4]
   // tiling
   int rows_per_tile, tiles_per_image, n_tiles, n_stages;
@@ -797,97 +798,174 @@ SBOD_DEVINL void finalize_loss(const LossParams& q, const double* sums, float* l
   loss[3] = float(npos);
 }
 
-__global__ void __launch_bounds__(kMineThreads) mine_kernel(const LossParams q) {
+// ------------------------------------------------------------------------------------------
+// classify_kernel: grid (ceil(P/1024), N). Applies the forced-match override to its 1024 priors
+// (every CTA rebuilds the image's short forced list from the per-object keys — no cross-CTA
+// dependency), classifies them, evaluates the positives (true-class CE, loc loss), writes the
+// mining candidates and per-block partial sums.
+// ------------------------------------------------------------------------------------------
+constexpr int kClsThreads = 256;
+constexpr int kClsPriors = 1024;
+
+__global__ void __launch_bounds__(kClsThreads) classify_kernel(const LossParams q) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   uint32_t* s_prior = reinterpret_cast<uint32_t*>(smem_raw);       // [gmax]
-  int32_t* s_rank = reinterpret_cast<int32_t*>(s_prior + q.gmax);  // [gmax]
-  float* s_vals = reinterpret_cast<float*>(smem_raw + ((size_t(q.gmax) * 8 + 127) & ~size_t(127)));  // [P] if cached
+  int32_t* s_rank = reinterpret_cast<int32_t*>(s_prior + q.gmax);  // [gmax], -1 = filtered out
+  __shared__ float s_ov[kClsPriors];
+  __shared__ int s_obj[kClsPriors];
+  __shared__ double s_red[34];
+  __shared__ int s_warp_tot[kClsThreads / 32];
+  __shared__ int s_carry;
+
+  const int n = blockIdx.y, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int pb = blockIdx.x * kClsPriors;
+  const int g0 = q.gt_offsets[n];
+  const int G = q.gt_offsets[n + 1] - g0;
+  const size_t base = size_t(n) * q.P;
+  const bool focal = q.cls_kind == SBOD_CLS_FOCAL_SUM || q.cls_kind == SBOD_CLS_FOCAL_NORM;
+
+  // ---- forced list: rank j of each object inside "objects whose best overlap is > 0" ----
+  if (tid == 0) s_carry = 0;
+#pragma unroll
+  for (int u = 0; u < kClsPriors / kClsThreads; ++u) {
+    const int p = pb + u * kClsThreads + tid;
+    s_ov[u * kClsThreads + tid] = p < q.P ? q.ov[base + p] : 0.f;
+    s_obj[u * kClsThreads + tid] = p < q.P ? q.obj[base + p] : 0;
+  }
+  __syncthreads();
+  for (int gb = 0; gb < G; gb += kClsThreads) {
+    const int g = gb + tid;
+    const unsigned long long key = g < G ? q.gtkey[size_t(n) * q.gmax + g] : 0ull;
+    const bool f = key != 0ull;
+    const unsigned bal = __ballot_sync(0xffffffffu, f);
+    if (lane == 0) s_warp_tot[wid] = __popc(bal);
+    __syncthreads();
+    int off = s_carry;
+    for (int w = 0; w < wid; ++w) off += s_warp_tot[w];
+    if (g < G) {
+      s_prior[g] = 0xffffffffu - uint32_t(key & 0xffffffffull);
+      s_rank[g] = f ? off + __popc(bal & ((1u << lane) - 1u)) : -1;
+    }
+    __syncthreads();
+    if (tid == 0) {
+      int t = 0;
+      for (int w = 0; w < kClsThreads / 32; ++w) t += s_warp_tot[w];
+      s_carry += t;
+    }
+    __syncthreads();
+  }
+  for (int g = tid; g < G; g += kClsThreads) {
+    const int j = s_rank[g];
+    if (j < 0) continue;
+    const uint32_t p = s_prior[g];
+    if (p < uint32_t(pb) || p >= uint32_t(pb + kClsPriors)) continue;
+    bool winner = true;  // "for j: obj[pr[j]] = j" -> the last j wins (SSD512.py:552-553)
+    for (int h = g + 1; h < G; ++h)
+      if (s_rank[h] >= 0 && s_prior[h] == p) {
+        winner = false;
+        break;
+      }
+    s_ov[p - pb] = 1.0f;  // index_fill_(0, prior_for_each_object, 1.0)
+    q.ov[base + p] = 1.0f;
+    if (winner) {
+      s_obj[p - pb] = j;
+      q.obj[base + p] = j;
+    }
+  }
+  __syncthreads();
+
+  double a_loc = 0.0, a_pos = 0.0, a_neg = 0.0;
+  int npos = 0;
+#pragma unroll
+  for (int u = 0; u < kClsPriors / kClsThreads; ++u) {
+    const int p = pb + u * kClsThreads + tid;
+    if (p >= q.P) continue;
+    const float ov = s_ov[u * kClsThreads + tid];
+    const int obj = s_obj[u * kClsThreads + tid];
+    float ce = q.ce[base + p];
+    const bool ex = q.exclude ? q.exclude[base + p] != 0 : false;
+    int64_t cls = 0;
+    if (!(ov < q.thr_pos) && G > 0) cls = map_label(q, q.gt_labels[g0 + obj]);
+    const bool pos = cls > 0 && !ex;
+    const bool isneg = ov < q.thr_neg;
+    uint8_t selbits = 0;
+    float v = -1.f;
+    if (cls > 0) {  // CE against the true class (the streamed value is the background CE)
+      const int c = min(int(cls), q.C - 1);
+      ce = q.lse[base + p] - q.scores[(base + p) * q.C + c];
+      q.ce[base + p] = ce;
+    }
+    if (pos) {
+      selbits = 1;
+      ++npos;
+      a_pos += focal ? double(focal_fg(q, ce)) : double(ce);
+      const float4 pred = reinterpret_cast<const float4*>(q.locs)[base + p];
+      const LocTerm lt = loc_term<false>(q, pred, prior_cxcy_of(q, n, p), q.gt_boxes[g0 + obj]);
+      a_loc += double(lt.loss);
+    }
+    if (focal) {
+      if (isneg && !pos) {  // target class is 0 there (thr_neg < thr_pos)
+        selbits |= 2;
+        a_neg += double(focal_bg(q, ce));
+      }
+    } else if (q.cls_kind == SBOD_CLS_CE_MINE_NONPOS) {
+      if (!pos && !ex) v = ce;
+    } else {  // MINE_NEG, MINE_BATCH: only true_neg == -1 rows are candidates
+      if (isneg && !pos) v = ce;
+    }
+    q.sel[base + p] = selbits;
+    q.cand[base + p] = v;
+  }
+  const double t_loc = block_sum(a_loc, s_red);
+  const double t_pos = block_sum(a_pos, s_red);
+  const double t_neg = block_sum(a_neg, s_red);
+  const double t_npos = block_sum(double(npos), s_red);
+  if (tid == 0) {
+    double* bp = q.blockpart + (size_t(n) * gridDim.x + blockIdx.x) * 4;
+    bp[0] = t_loc; bp[1] = t_pos; bp[2] = t_neg; bp[3] = t_npos;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// mine_kernel: one CTA per image. Folds the block partials, selects the hard negatives
+// (radix-select top-k sum over the image's candidates, staged in shared memory), marks them,
+// and the last CTA folds the batch.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kMineThreads) mine_kernel(const LossParams q) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  float* s_vals = reinterpret_cast<float*>(smem_raw);  // [P] if cached
   __shared__ unsigned int s_hist[kBins];
   __shared__ double s_red[34];
+  __shared__ double s_tot[4];
   __shared__ int s_misc[8];
-  __shared__ int s_warp_tot[32];
-  __shared__ int s_carry;
   const int n = blockIdx.x, tid = threadIdx.x;
   const int g0 = q.gt_offsets[n];
   const int G = q.gt_offsets[n + 1] - g0;
   const size_t base = size_t(n) * q.P;
   const bool focal = q.cls_kind == SBOD_CLS_FOCAL_SUM || q.cls_kind == SBOD_CLS_FOCAL_NORM;
-  const bool to_global = !q.mine_cache || q.cls_kind == SBOD_CLS_CE_MINE_BATCH;
-  float* vals = q.mine_cache ? s_vals : q.cand + base;
+  const int nblk = (q.P + kClsPriors - 1) / kClsPriors;
 
-  // phase 0: the forced-match override of this image (patches <= G entries of ov / obj)
-  forced_match_phase(q, n, s_prior, s_rank, s_warp_tot, &s_carry);
-  __threadfence();
-  __syncthreads();
-
-  double a_loc = 0.0, a_pos = 0.0, a_neg = 0.0;
-  int npos = 0;
-  constexpr int U = 4;
-  for (int p0 = tid; p0 < q.P; p0 += kMineThreads * U) {
-    float ov_[U], ce_[U];
-    int obj_[U];
-    uint8_t ex_[U];
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const int p = p0 + u * kMineThreads;
-      const bool in = p < q.P;
-      ov_[u] = in ? q.ov[base + p] : 0.f;
-      obj_[u] = in ? q.obj[base + p] : 0;
-      ce_[u] = in ? q.ce[base + p] : 0.f;
-      ex_[u] = (in && q.exclude) ? q.exclude[base + p] : uint8_t(0);
-    }
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const int p = p0 + u * kMineThreads;
-      if (p >= q.P) continue;
-      const float ov = ov_[u];
-      const int obj = obj_[u];
-      float ce = ce_[u];
-      const bool ex = ex_[u] != 0;
-      int64_t cls = 0;
-      if (!(ov < q.thr_pos) && G > 0) cls = map_label(q, q.gt_labels[g0 + obj]);
-      const bool pos = cls > 0 && !ex;
-      const bool isneg = ov < q.thr_neg;
-      uint8_t selbits = 0;
-      float v = -1.f;
-      if (cls > 0) {  // CE of the row against its true class (the streamed value is the background CE)
-        const int c = min(int(cls), q.C - 1);
-        ce = q.lse[base + p] - q.scores[(base + p) * q.C + c];
-        q.ce[base + p] = ce;
-      }
-      if (pos) {
-        selbits = 1;
-        ++npos;
-        a_pos += focal ? double(focal_fg(q, ce)) : double(ce);
-        const float4 pred = reinterpret_cast<const float4*>(q.locs)[base + p];
-        const LocTerm lt = loc_term<false>(q, pred, prior_cxcy_of(q, n, p), q.gt_boxes[g0 + obj]);
-        a_loc += double(lt.loss);
-      }
-      if (focal) {
-        if (isneg && !pos) {  // target class is 0 there (thr_neg < thr_pos)
-          selbits |= 2;
-          a_neg += double(focal_bg(q, ce));
-        }
-      } else if (q.cls_kind == SBOD_CLS_CE_MINE_NONPOS) {
-        if (!pos && !ex) v = ce;
-      } else {  // MINE_NEG, MINE_BATCH: only true_neg == -1 rows are candidates
-        if (isneg && !pos) v = ce;
-      }
-      q.sel[base + p] = selbits;
-      if (q.mine_cache) s_vals[p] = v;
-      if (to_global) q.cand[base + p] = v;
-    }
+  // leave the per-object keys clean for the next call (every classify CTA has read them)
+  for (int g = tid; g < G; g += kMineThreads) q.gtkey[size_t(n) * q.gmax + g] = 0ull;
+  if (tid < 4) {  // block partials in block order (deterministic)
+    double acc = 0.0;
+    const double* bp = q.blockpart + size_t(n) * nblk * 4;
+    for (int b = 0; b < nblk; ++b) acc += bp[b * 4 + tid];
+    s_tot[tid] = acc;
   }
-  const double t_loc = block_sum(a_loc, s_red);
-  const double t_pos = block_sum(a_pos, s_red);
-  const double t_npos = block_sum(double(npos), s_red);
+  const float* vals = q.cand + base;
+  if (q.mine_cache && !focal && q.cls_kind != SBOD_CLS_CE_MINE_BATCH) {
+    for (int p = tid; p < q.P; p += kMineThreads) s_vals[p] = q.cand[base + p];
+    vals = s_vals;
+  }
+  __syncthreads();
+  const double t_loc = s_tot[0], t_pos = s_tot[1], t_npos = s_tot[3];
   double t_neg;
   if (focal) {
-    t_neg = block_sum(a_neg, s_red);
+    t_neg = s_tot[2];
   } else if (q.cls_kind == SBOD_CLS_CE_MINE_BATCH) {
     t_neg = 0.0;  // filled by mine_batch_kernel
   } else {
-    __syncthreads();
     const long long k = (long long)(q.ratio) * (long long)(t_npos + 0.5);
     const SelectResult r = topk_sum(vals, q.P, k, s_hist, s_red, s_misc);
     mark_selected(vals, q.sel + base, q.P, r, s_misc);
@@ -1099,6 +1177,117 @@ __global__ void __launch_bounds__(kRows) loss_bwd_kernel(const BwdParams bp) {
   if (tid == 0) tma_store_wait_all<0>();
 }
 
+// ------------------------------------------------------------------------------------------
+// Sparse backward (CE + hard-negative mining): only positives and mined negatives carry gradient
+// (about 4*n_pos rows of N*P), so grad_scores is written as
+//   zero_fill_kernel  : the whole tensor from one zeroed shared-memory tile with back-to-back bulk
+//                       TMA stores (the source never changes, so nothing waits until the end), then
+//   bwd_patch_kernel  : the selected rows (a warp per row, coalesced over classes) and grad_locs.
+// ------------------------------------------------------------------------------------------
+constexpr int kZeroTileBytes = 32 * 1024;
+
+__global__ void __launch_bounds__(128) zero_fill_kernel(float* __restrict__ dst, size_t n_floats) {
+  __shared__ __align__(128) unsigned char s_zero[kZeroTileBytes];
+  const int tid = threadIdx.x;
+  float4* z4 = reinterpret_cast<float4*>(s_zero);
+  for (int i = tid; i < kZeroTileBytes / 16; i += blockDim.x) z4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  fence_proxy_async();
+  __syncthreads();
+  // dst is 16-byte aligned; the bulk part covers floor16(bytes), the tail (< 16 B) is plain stores
+  const size_t total_bytes = n_floats * 4;
+  const size_t bulk_bytes = total_bytes & ~size_t(15);
+  const size_t n_chunks = (bulk_bytes + kZeroTileBytes - 1) / kZeroTileBytes;
+  if (tid == 0) {
+    unsigned char* base = reinterpret_cast<unsigned char*>(dst);
+    for (size_t c = blockIdx.x; c < n_chunks; c += gridDim.x) {
+      const size_t off = c * kZeroTileBytes;
+      const size_t len = (bulk_bytes - off) < size_t(kZeroTileBytes) ? (bulk_bytes - off) : size_t(kZeroTileBytes);
+      tma_store_1d(base + off, s_zero, uint32_t(len));
+      tma_store_commit();
+    }
+    tma_store_wait_all<0>();
+  }
+  if (blockIdx.x == 0 && tid < int((total_bytes - bulk_bytes) / 4)) dst[bulk_bytes / 4 + tid] = 0.f;
+}
+
+struct BwdParams;
+__global__ void __launch_bounds__(256) bwd_patch_kernel(const LossParams q, const float* __restrict__ grad_loss,
+                                                        float* __restrict__ grad_locs,
+                                                        float* __restrict__ grad_scores) {
+  const int lane = threadIdx.x & 31;
+  const size_t total = size_t(q.N) * q.P;
+  const double npos_tot = q.sums[3];
+  const float gout = grad_loss ? *grad_loss : 1.f;
+  const float conf_scale = float(double(gout) / npos_tot);
+  const float loc_scale = float(double(gout) * double(q.reg_weight) /
+                                (q.reg_kind == SBOD_REG_L1_ELEM_MEAN ? 4.0 * npos_tot : npos_tot));
+  const size_t warp0 = (size_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const size_t n_warps = (size_t(gridDim.x) * blockDim.x) >> 5;
+  for (size_t base = warp0 * 32; base < total; base += n_warps * 32) {
+    const size_t i = base + lane;
+    const bool in = i < total;
+    const uint8_t selbits = in ? q.sel[i] : uint8_t(0);
+    int cls = 0;
+    float lse = 0.f;
+    if (in && selbits) {
+      const int n = int(i / q.P);
+      const int p = int(i - size_t(n) * q.P);
+      const int g0 = q.gt_offsets[n];
+      const int G = q.gt_offsets[n + 1] - g0;
+      const float ov = q.ov[i];
+      const int obj = q.obj[i];
+      int64_t lab = 0;
+      if (G > 0) lab = map_label(q, q.gt_labels[g0 + obj]);
+      cls = (ov < q.thr_pos) ? 0 : int(lab);
+      cls = min(max(cls, 0), q.C - 1);
+      lse = q.lse[i];
+      if (grad_locs) {
+        float4 gl = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (selbits & 1) {
+          const float4 pred = reinterpret_cast<const float4*>(q.locs)[i];
+          const LocTerm lt = loc_term<true>(q, pred, prior_cxcy_of(q, n, p), q.gt_boxes[g0 + obj]);
+          gl = make_float4(lt.grad.x * loc_scale, lt.grad.y * loc_scale, lt.grad.z * loc_scale,
+                           lt.grad.w * loc_scale);
+        }
+        reinterpret_cast<float4*>(grad_locs)[i] = gl;
+      }
+    } else if (in && grad_locs) {
+      reinterpret_cast<float4*>(grad_locs)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    if (!grad_scores) continue;
+    unsigned m = __ballot_sync(0xffffffffu, selbits != 0);
+    // four selected rows per round so that their loads are in flight together
+    while (m) {
+      int src[4];
+      int rc[4];
+      float rl[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        src[u] = -1;
+        if (m) {
+          src[u] = __ffs(m) - 1;
+          m &= m - 1;
+        }
+        const int sl = src[u] < 0 ? 0 : src[u];
+        rc[u] = __shfl_sync(0xffffffffu, cls, sl);
+        rl[u] = __shfl_sync(0xffffffffu, lse, sl);
+      }
+      for (int kb = 0; kb < q.C; kb += 32) {
+        const int k = kb + lane;
+        float x[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+          x[u] = (src[u] >= 0 && k < q.C) ? q.scores[(base + src[u]) * q.C + k] : 0.f;
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+          if (src[u] >= 0 && k < q.C)
+            grad_scores[(base + src[u]) * q.C + k] =
+                conf_scale * (__expf(x[u] - rl[u]) - (k == rc[u] ? 1.f : 0.f));
+      }
+    }
+  }
+}
+
 // expand the per-prior state into the reference's int64 tensors
 __global__ void targets_kernel(const LossParams q, int64_t* cls_out, int64_t* neg_out) {
   const size_t total = size_t(q.N) * q.P;
@@ -1184,6 +1373,8 @@ static int fill_params(const sbod_loss_desc* d, LossParams& q, bool need_scores)
   q.gtkey = reinterpret_cast<unsigned long long*>(w);
   w += align_up(size_t(q.N) * q.gmax * 8, 256);
   q.cand = reinterpret_cast<float*>(w);
+  w += align_up(size_t(q.N) * q.P * 4, 256);
+  q.blockpart = reinterpret_cast<double*>(w);
   Tiling t = choose_tiling(need_scores ? d->C : 1, kMaxStages);
   q.fast = (need_scores && (d->C & 1) && d->C <= 128) ? 1 : 0;
   q.ctas_per_sm = 2;
@@ -1220,7 +1411,8 @@ using namespace sbod;
 extern "C" size_t sbod_loss_workspace_bytes(const sbod_loss_desc* d) {
   if (!d) return 0;
   const int gmax = d->gmax > 0 ? d->gmax : 1;
-  return 256 + align_up(size_t(d->N) * gmax * 8, 256) + align_up(size_t(d->N) * d->P * 4, 256);
+  return 256 + align_up(size_t(d->N) * gmax * 8, 256) + align_up(size_t(d->N) * d->P * 4, 256) +
+         align_up(size_t(d->N) * ((size_t(d->P) + 1023) / 1024) * 32, 256);
 }
 
 // Workspace contract: the first 256 bytes (counters) and the gtkey block must be zero on the
@@ -1239,6 +1431,7 @@ static int set_kernel_attrs() {
   SBOD_CUDA_TRY(cudaFuncSetAttribute(loss_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   SBOD_CUDA_TRY(cudaFuncSetAttribute(forced_match_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
   SBOD_CUDA_TRY(cudaFuncSetAttribute(mine_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 205 * 1024));
+  SBOD_CUDA_TRY(cudaFuncSetAttribute(classify_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
   attr_done = true;
   return SBOD_OK;
 }
@@ -1272,7 +1465,10 @@ static int launch_match(const LossParams& q, cudaStream_t st) {
 static int launch_mine(const LossParams& q, cudaStream_t st) {
   int rc = set_kernel_attrs();
   if (rc) return rc;
-  const size_t smem = align_up(size_t(q.gmax) * 8, 128) + (q.mine_cache ? size_t(q.P) * 4 : 0);
+  dim3 cgrid((q.P + kClsPriors - 1) / kClsPriors, q.N);
+  classify_kernel<<<cgrid, kClsThreads, size_t(q.gmax) * 8, st>>>(q);
+  SBOD_LAUNCH_CHECK();
+  const size_t smem = q.mine_cache ? size_t(q.P) * 4 : 0;
   mine_kernel<<<q.N, kMineThreads, smem, st>>>(q);
   SBOD_LAUNCH_CHECK();
   if (q.cls_kind == SBOD_CLS_CE_MINE_BATCH) {
@@ -1345,7 +1541,20 @@ extern "C" int sbod_loss_backward(const sbod_loss_desc* d, const float* grad_los
   if (ctas_per_sm > 8) ctas_per_sm = 8;
   int grid = sm_count() * ctas_per_sm;
   if (grid > q.n_tiles) grid = q.n_tiles;
-  loss_bwd_kernel<<<grid, kRows, smem, static_cast<cudaStream_t>(stream)>>>(bp);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (!bp.dense) {
+    if (grad_scores) {
+      zero_fill_kernel<<<sm_count() * 4, 128, 0, st>>>(grad_scores, size_t(q.N) * q.P * size_t(q.C));
+      SBOD_LAUNCH_CHECK();
+    }
+    const size_t rows = size_t(q.N) * q.P;
+    int pgrid = int((rows + 255) / 256);
+    if (pgrid > sm_count() * 8) pgrid = sm_count() * 8;
+    bwd_patch_kernel<<<pgrid, 256, 0, st>>>(q, grad_loss, grad_locs, grad_scores);
+    SBOD_LAUNCH_CHECK();
+    return SBOD_OK;
+  }
+  loss_bwd_kernel<<<grid, kRows, smem, st>>>(bp);
   SBOD_LAUNCH_CHECK();
   return SBOD_OK;
 }
