@@ -59,7 +59,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._pump, daemon=True).start()
         except Exception:
@@ -245,12 +245,26 @@ def run_ours(args, rank, world, local_rank):
     st = crit.last["state"]
     ms_fwd = timed(lambda: st.forward(), args.steps, sync)
     gl = torch.ones((), device=dev)
-    ms_bwd = timed(lambda: st.backward(gl), args.steps, sync)
+    g_locs_buf, g_scores_buf = torch.empty_like(st.locs), torch.empty_like(st.scores)
+    ms_bwd = timed(lambda: st.backward_into(gl, g_locs_buf, g_scores_buf), args.steps, sync)
     ms_det = timed(lambda: S.detect_batched(d_elocs, d_escores, NMS["min_score"], NMS["max_overlap"],
                                             NMS["top_k"], pri_d), args.steps, sync)
     stage = L.lib().sbod_loss_forward_stage
     ms_match = timed(lambda: L.check(stage(C.byref(st.desc), 0, L.stream_ptr())), args.steps, sync)
     L.check(stage(C.byref(st.desc), 1, L.stream_ptr()))  # leave the workspace clean
+    # the eval path's streaming kernel alone: build the descriptor once, then time stage 0 / stage 1 pairs
+    det_desc = S.core.make_detect_desc(d_elocs, d_escores, NMS["min_score"], NMS["max_overlap"], NMS["top_k"], pri_d)
+    dstage = L.lib().sbod_detect_stage
+    ms_dscore = 0.0
+    sync()
+    for _ in range(args.steps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        L.check(dstage(C.byref(det_desc["desc"]), 0, L.stream_ptr()))
+        e1.record()
+        L.check(dstage(C.byref(det_desc["desc"]), 1, L.stream_ptr()))
+        torch.cuda.synchronize()
+        ms_dscore += e0.elapsed_time(e1) / args.steps
 
     # ---- e2e: pinned host buffers in, results out, every step ----
     for _ in range(2):
@@ -258,10 +272,10 @@ def run_ours(args, rank, world, local_rank):
     e2e_steps = max(3, min(args.steps, 10))
     ms_e2e = timed(step_e2e, e2e_steps, sync)
 
-    t = torch.tensor([ms_step, ms_e2e, ms_fwd, ms_bwd, ms_det, ms_match], dtype=torch.float64, device=dev)
+    t = torch.tensor([ms_step, ms_e2e, ms_fwd, ms_bwd, ms_det, ms_match, ms_dscore], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_step, ms_e2e, ms_fwd, ms_bwd, ms_det, ms_match = t.tolist()
+    ms_step, ms_e2e, ms_fwd, ms_bwd, ms_det, ms_match, ms_dscore = t.tolist()
 
     if rank == 0:
         T = int(gt[0].size(0))
@@ -273,12 +287,23 @@ def run_ours(args, rank, world, local_rank):
         except Exception:
             pass
         peak = float(peaks.get("hbm_gbs", 6650.0))
-        alg_bytes = N * P * N_CLASSES * 4 + P * 16 + T * 24  # logits once + priors once + GT
-        achieved = alg_bytes / (ms_match * 1e-3) / 1e9
+        # algorithmic bytes per launch of the two streaming kernels (DESIGN.md "Kernels"):
+        #   train: logits once + priors once + GT;  eval: logits once
+        alg_match = N * P * N_CLASSES * 4 + P * 16 + T * 24
+        alg_dscore = N * P * N_CLASSES * 4
+        per_kernel = {
+            "match_lse_fast_kernel": {"ms": ms_match, "bytes": alg_match},
+            "detect_score_fast_kernel": {"ms": ms_dscore, "bytes": alg_dscore},
+        }
+        for v in per_kernel.values():
+            v["achieved_gbs"] = v["bytes"] / (v["ms"] * 1e-3) / 1e9
+            v["frac"] = v["achieved_gbs"] / peak
+        dom = max(per_kernel, key=lambda k: per_kernel[k]["ms"])  # the dominant kernel of the step
+        alg_bytes, ms_dom = per_kernel[dom]["bytes"], per_kernel[dom]["ms"]
+        achieved = per_kernel[dom]["achieved_gbs"]
         traffic = None
         try:
-            traffic = json.load(open(os.path.join(REPO, "profiles", "roofline_traffic.json"))).get(
-                "match_lse_kernel_dram_bytes_per_launch")
+            traffic = json.load(open(os.path.join(REPO, "profiles", "roofline_traffic.json"))).get(dom)
         except Exception:
             pass
         # CPU baseline beside it (bounded sample, all host cores)
@@ -300,12 +325,13 @@ def run_ours(args, rank, world, local_rank):
                        "images_per_s_detect": N * world / (ms_det * 1e-3)},
             "e2e": {"value": N * world / (ms_e2e * 1e-3), "unit": "images/s", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e},
-            "gpu_launches": 6 * args.steps,
+            "gpu_launches": 7 * args.steps,  # match_lse, classify, mine, zero_fill, bwd_patch, detect_score, detect_nms
             "clocks": clocks,
-            "roofline": {"bound": "hbm", "kernel": "match_lse_kernel", "achieved": achieved, "peak": peak,
+            "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured copy)" if peaks else "fallback 6650",
-                         "ms_per_launch": ms_match, "algorithmic_bytes_per_launch": alg_bytes},
+                         "ms_per_launch": ms_dom, "algorithmic_bytes_per_launch": alg_bytes,
+                         "streaming_kernels": per_kernel},
             "cpu_baseline": {"value": cpu_value, "unit": "images/s", "cores": cores, "kind": "port",
                              "sample": "2 train images (loss fwd+bwd) + 1 eval image (detect), oracle port of the "
                                        "reference on the host cores, second of two passes",

@@ -7,7 +7,7 @@ The sub-modules mirror the reference's module paths for that path only:
   detect_scripts.detect_tools.
 All numerics run in hand-written CUDA kernels behind the C ABI of include/sbod.h (lib/libsbod.so).
 """
-from . import _lib
+from . import _lib, core
 from .core import LossSpec, assign, detect_batched, fused_loss, pack_ground_truth, unpad_detections
 
 __all__ = ["LossSpec", "assign", "detect_batched", "fused_loss", "pack_ground_truth", "unpad_detections",

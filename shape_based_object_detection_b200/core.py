@@ -102,6 +102,12 @@ class LossState:
                                            L.stream_ptr()))
         return g_locs, g_scores
 
+    def backward_into(self, grad_loss, g_locs, g_scores):
+        """Backward into caller-owned buffers (no allocation)."""
+        L.check(L.lib().sbod_loss_backward(C.byref(self.desc), L.ptr(grad_loss), L.ptr(g_locs), L.ptr(g_scores),
+                                           L.stream_ptr()))
+        return g_locs, g_scores
+
     def targets(self):
         """(true_classes, true_neg_classes) as the reference materialises them — for tests."""
         dev = self.scores.device
@@ -185,11 +191,10 @@ def assign(boxes, labels, anchors_xy, threshold=0.5, neg_margin=0.1, want_classe
 # ---------------------------------------------------------------------------------------------
 # eval path
 # ---------------------------------------------------------------------------------------------
-def detect_batched(predicted_locs, predicted_scores, min_score, max_overlap, top_k, priors_cxcy=None,
-                   act="softmax", box_type="offset", clamp_inplace=False, prior_keep=None,
-                   second_nms_thr=-1.0, pre_nms_topk=0):
-    """Fused eval path. Returns padded outputs (boxes [N,K,4], labels [N,K], scores [N,K],
-    prior [N,K], counts [N]) — all on the device, no host synchronisation."""
+def make_detect_desc(predicted_locs, predicted_scores, min_score, max_overlap, top_k, priors_cxcy=None,
+                     act="softmax", box_type="offset", clamp_inplace=False, prior_keep=None,
+                     second_nms_thr=-1.0, pre_nms_topk=0):
+    """Allocate the outputs / workspace of one sbod_detect call and fill its descriptor."""
     L.need_cuda(predicted_locs, predicted_scores)
     dev = predicted_scores.device
     N, P, Cn = predicted_scores.shape
@@ -227,8 +232,19 @@ def detect_batched(predicted_locs, predicted_scores, min_score, max_overlap, top
     zbytes = L.lib().sbod_detect_workspace_zero_bytes(C.byref(d))
     ws = L.Workspace.get(dev, ("detect", N, P, Cn), nbytes, zero_bytes=zbytes)
     d.workspace, d.workspace_bytes = ws.data_ptr(), nbytes
-    L.check(L.lib().sbod_detect(C.byref(d), L.stream_ptr()))
-    return out_boxes, out_labels, out_scores, out_prior, out_counts
+    return {"desc": d, "outputs": (out_boxes, out_labels, out_scores, out_prior, out_counts),
+            "alive": (locs, scores, pri, keep, ws)}
+
+
+def detect_batched(predicted_locs, predicted_scores, min_score, max_overlap, top_k, priors_cxcy=None,
+                   act="softmax", box_type="offset", clamp_inplace=False, prior_keep=None,
+                   second_nms_thr=-1.0, pre_nms_topk=0):
+    """Fused eval path. Returns padded outputs (boxes [N,K,4], labels [N,K], scores [N,K],
+    prior [N,K], counts [N]) — all on the device, no host synchronisation."""
+    call = make_detect_desc(predicted_locs, predicted_scores, min_score, max_overlap, top_k, priors_cxcy, act,
+                            box_type, clamp_inplace, prior_keep, second_nms_thr, pre_nms_topk)
+    L.check(L.lib().sbod_detect(C.byref(call["desc"]), L.stream_ptr()))
+    return call["outputs"]
 
 
 def unpad_detections(out_boxes, out_labels, out_scores, out_counts):
