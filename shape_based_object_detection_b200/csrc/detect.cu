@@ -57,7 +57,14 @@ struct DetParams {
   long long cand_cap;
   int n_bins, shift0;           // level-0 digit = key >> shift0
   int kcap;                     // kept-list capacity in smem
-  int debug_skip;               // SBOD_DEBUG_SKIP (profiling): bit0 no emission, bit1 no exact refine
+  int debug_skip;               // SBOD_DEBUG_SKIP (profiling): bit0 no emission, bit1 no exact refine, bit2 no cutoff
+  // speculative per-image score cutoff (exact: images whose candidates run out are redone in full)
+  int mode;                     // 0 = main pass, 1 = sampling pass, 2 = fallback pass (flagged images only)
+  unsigned int* shist;          // [N, n_bins] histogram of the sampled tiles
+  unsigned int* cutoff_k32;     // [N] emit only keys with k32 < cutoff (0xffffffff = no cutoff)
+  float* cutoff_floor;          // [N] score just below the cutoff (mask floor)
+  unsigned int* flags;          // [N] 1 = the cutoff was too strict, redo this image in full
+  int sample_stride, sample_target;
   // tiling
   int rows_per_tile, tiles_per_image, n_tiles, n_stages;
   uint32_t stage_floats;
@@ -254,9 +261,26 @@ __global__ void __launch_bounds__(kStreamThreads, 2) detect_score_fast_kernel(co
 
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int C = q.C;
+  // tiles of this CTA: all of a contiguous range (modes 0, 2) or every sample_stride-th tile (mode 1)
+  const int stride = q.mode == 1 ? q.sample_stride : 1;
+  const int n_units = q.mode == 1 ? (q.n_tiles + stride - 1 - stride / 2) / stride : q.n_tiles;
   int t0, t1;
-  tile_range(q.n_tiles, blockIdx.x, gridDim.x, t0, t1);
+  tile_range(n_units, blockIdx.x, gridDim.x, t0, t1);
   const int n_my = t1 - t0;
+  auto tile_of = [&](int idx) { return (t0 + idx) * stride + (q.mode == 1 ? stride / 2 : 0); };
+  auto image_active = [&](int n) { return q.mode != 2 || q.flags[n] != 0u; };
+  if (n_my <= 0) return;
+  if (q.mode == 2) {  // nothing flagged in my range: leave at once
+    bool any = false;
+    for (int n = tile_of(0) / q.tiles_per_image; n <= tile_of(n_my - 1) / q.tiles_per_image; ++n)
+      any = any || q.flags[n] != 0u;
+    if (!any) return;
+  }
+  auto issue = [&](int idx, float* stage, uint64_t* bar) {
+    const StreamTile t = stream_tile(tile_of(idx), q.tiles_per_image, kTileRows, q.P);
+    if (image_active(t.n)) stream_issue(q.scores, q.N, q.P, C, t, stage, bar);
+    else mbar_arrive(bar);  // keep the ring's phase bookkeeping, move no data
+  };
   if (tid == 0) {
     for (int s = 0; s < q.n_stages; ++s) mbar_init(&bars[s], 1);
     fence_mbar_init();
@@ -264,18 +288,18 @@ __global__ void __launch_bounds__(kStreamThreads, 2) detect_score_fast_kernel(co
   for (int b = tid; b < q.n_bins; b += kStreamThreads) s_hist[b] = 0u;
   __syncthreads();
   if (tid == 0) {
-    for (int s = 0; s < q.n_stages && s < n_my; ++s)
-      stream_issue(q.scores, q.N, q.P, C, stream_tile(t0 + s, q.tiles_per_image, kTileRows, q.P),
-                   stages + size_t(s) * q.stage_floats, &bars[s]);
+    for (int s = 0; s < q.n_stages && s < n_my; ++s) issue(s, stages + size_t(s) * q.stage_floats, &bars[s]);
   }
   int row, h;
   stream_map(tid, row, h);
   const int nh = (C + 1 - h) >> 1;
   int hist_n = -1;
+  unsigned int cut_k32 = 0xffffffffu;
+  float cut_floor = q.min_score;
 
   auto flush_hist = [&](int n) {
     __syncthreads();
-    unsigned int* gh = q.hist + size_t(n) * q.n_bins;
+    unsigned int* gh = (q.mode == 1 ? q.shist : q.hist) + size_t(n) * q.n_bins;
     for (int b = tid; b < q.n_bins; b += kStreamThreads) {
       const unsigned int v = s_hist[b];
       if (v) {
@@ -287,17 +311,22 @@ __global__ void __launch_bounds__(kStreamThreads, 2) detect_score_fast_kernel(co
   };
 
   for (int it = 0; it < n_my; ++it) {
-    const StreamTile tc = stream_tile(t0 + it, q.tiles_per_image, kTileRows, q.P);
+    const StreamTile tc = stream_tile(tile_of(it), q.tiles_per_image, kTileRows, q.P);
     const int n = tc.n;
     if (n != hist_n) {
       if (hist_n >= 0) flush_hist(hist_n);
       hist_n = n;
+      if (q.mode == 0 && !(q.debug_skip & 4)) {
+        cut_k32 = q.cutoff_k32[n];
+        cut_floor = cut_k32 == 0xffffffffu ? q.min_score : q.cutoff_floor[n];
+      }
     }
-    const bool valid = row < tc.rows;
+    const bool act = image_active(n);
+    const bool valid = row < tc.rows && act;
     const int r = min(row, tc.rows - 1);
     const int p = tc.p0 + r;
     const size_t np = size_t(n) * q.P + p;
-    if (valid && h == 0 && q.clamp_inplace) {  // clamp_ on the caller's tensor (models/utils.py:224)
+    if (valid && h == 0 && q.clamp_inplace && q.mode == 0) {  // clamp_ on the caller's tensor (models/utils.py:224)
       float4* lp = reinterpret_cast<float4*>(q.locs) + np;
       float4 b = *lp;
       b.x = fminf(fmaxf(b.x, 0.f), 1.f); b.y = fminf(fmaxf(b.y, 0.f), 1.f);
@@ -317,11 +346,11 @@ __global__ void __launch_bounds__(kStreamThreads, 2) detect_score_fast_kernel(co
     if (q.act_kind == SBOD_ACT_SOFTMAX) {
       const float mx = half_row_max(rp, nh);
       nmx2 = -mx * kLog2e;
-      const float sum = half_row_sumexp_mask(rp, nh, nmx2, q.min_score, m0, m1);
+      const float sum = half_row_sumexp_mask(rp, nh, nmx2, cut_floor, m0, m1);
       inv = __frcp_rn(sum);
     } else {
       // sigmoid(x) > t  <=>  x > logit(t); keep a small margin, the exact test follows
-      const float t = fminf(fmaxf(q.min_score, 1e-30f), 1.f - 1e-7f);
+      const float t = fminf(fmaxf(cut_floor, 1e-30f), 1.f - 1e-7f);
       const float lim = logf(t / (1.f - t)) - 1e-3f;
       for (int j = 0; j < nh; ++j)
         if (rp[2 * j] > lim) {
@@ -342,7 +371,7 @@ __global__ void __launch_bounds__(kStreamThreads, 2) detect_score_fast_kernel(co
         const float x = rp[2 * j];
         const float pr = q.act_kind == SBOD_ACT_SOFTMAX ? ex2_approx(fmaf(x, kLog2e, nmx2)) * inv
                                                         : __frcp_rn(1.f + __expf(-x));
-        if (pr > q.min_score) ++cnt; else m0 &= ~(1u << j);
+        if (pr > q.min_score && (kOneBits - min(__float_as_uint(pr), kOneBits)) < cut_k32) ++cnt; else m0 &= ~(1u << j);
       }
       mm = m1;
       while (mm) {
@@ -351,7 +380,7 @@ __global__ void __launch_bounds__(kStreamThreads, 2) detect_score_fast_kernel(co
         const float x = rp[2 * (j + 32)];
         const float pr = q.act_kind == SBOD_ACT_SOFTMAX ? ex2_approx(fmaf(x, kLog2e, nmx2)) * inv
                                                         : __frcp_rn(1.f + __expf(-x));
-        if (pr > q.min_score) ++cnt; else m1 &= ~(1u << j);
+        if (pr > q.min_score && (kOneBits - min(__float_as_uint(pr), kOneBits)) < cut_k32) ++cnt; else m1 &= ~(1u << j);
       }
     }
     // block-exclusive scan of the per-thread counts, one global atomic per tile
@@ -369,7 +398,7 @@ __global__ void __launch_bounds__(kStreamThreads, 2) detect_score_fast_kernel(co
       if (w < wid) off += s_wtot[w];
       tot += s_wtot[w];
     }
-    if (tid == 0) s_base = tot ? atomicAdd(&q.cand_count[n], tot) : 0u;
+    if (tid == 0) s_base = (tot && q.mode != 1) ? atomicAdd(&q.cand_count[n], tot) : 0u;
     __syncthreads();
     if (cnt && !(q.debug_skip & 1)) {
       long long slot = (long long)s_base + off;
@@ -389,7 +418,7 @@ __global__ void __launch_bounds__(kStreamThreads, 2) detect_score_fast_kernel(co
           const unsigned long long key = (static_cast<unsigned long long>(k32) << 32) |
                                          (static_cast<unsigned long long>(k) << kPriorBits) |
                                          static_cast<unsigned long long>(p);
-          if (slot < q.cand_cap) dst[slot] = key;
+          if (q.mode != 1 && slot < q.cand_cap) dst[slot] = key;
           ++slot;
           int bin = int(key >> q.shift0);
           if (bin >= q.n_bins) bin = q.n_bins - 1;
@@ -398,11 +427,68 @@ __global__ void __launch_bounds__(kStreamThreads, 2) detect_score_fast_kernel(co
       }
     }
     __syncthreads();  // every thread is done with stage s (and with s_wtot / s_base)
-    if (tid == 0 && it + q.n_stages < n_my)
-      stream_issue(q.scores, q.N, q.P, C,
-                   stream_tile(t0 + it + q.n_stages, q.tiles_per_image, kTileRows, q.P), stage, &bars[s]);
+    if (tid == 0 && it + q.n_stages < n_my) issue(it + q.n_stages, stage, &bars[s]);
   }
   if (hist_n >= 0) flush_hist(hist_n);
+}
+
+// ------------------------------------------------------------------------------------------
+// detect_cutoff_kernel: one CTA per image. From the histogram of the sampled tiles pick the score
+// bin above which about sample_target candidates are expected, publish it as the emission cutoff
+// of the main pass, and clear the sample histogram.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) detect_cutoff_kernel(const DetParams q) {
+  __shared__ unsigned int s_w[8];
+  __shared__ int s_bin;
+  const int n = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  unsigned int* sh = q.shist + size_t(n) * q.n_bins;
+  if (tid == 0) s_bin = q.n_bins;
+  __syncthreads();
+  const int per = (q.n_bins + 255) / 256;  // contiguous bins per thread, ascending (best scores first)
+  unsigned int mine = 0;
+  for (int j = 0; j < per; ++j) {
+    const int b = tid * per + j;
+    if (b < q.n_bins) mine += sh[b];
+  }
+  unsigned int inc = mine;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const unsigned int t = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += t;
+  }
+  if (lane == 31) s_w[wid] = inc;
+  __syncthreads();
+  unsigned int before = inc - mine;
+  for (int w = 0; w < wid; ++w) before += s_w[w];
+  const unsigned int need = unsigned((q.sample_target + q.sample_stride - 1) / q.sample_stride);
+  if (before < need && before + mine >= need) {
+    unsigned int acc = before;
+    for (int j = 0; j < per; ++j) {
+      const int b = tid * per + j;
+      if (b >= q.n_bins) break;
+      acc += sh[b];
+      if (acc >= need) {
+        s_bin = b + 1;  // emit bins [0, b]
+        break;
+      }
+    }
+  }
+  __syncthreads();
+  for (int j = 0; j < per; ++j) {
+    const int b = tid * per + j;
+    if (b < q.n_bins) sh[b] = 0u;
+  }
+  if (tid == 0) {
+    const int cb = s_bin;
+    if (cb >= q.n_bins) {
+      q.cutoff_k32[n] = 0xffffffffu;
+      q.cutoff_floor[n] = q.min_score;
+    } else {
+      const unsigned int k32 = unsigned(cb) << (q.shift0 - 32);
+      q.cutoff_k32[n] = k32;
+      q.cutoff_floor[n] = fmaxf(q.min_score, __uint_as_float(kOneBits - min(k32, kOneBits)));
+    }
+  }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -450,6 +536,8 @@ __global__ void __launch_bounds__(kNmsThreads) detect_nms_kernel(const DetParams
   unsigned int* cls_off = reinterpret_cast<unsigned int*>(dyn + size_t(q.kcap) * 25 + 128 - (size_t(q.kcap) * 25) % 128);  // [C+1]
 
   const int n = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  if (q.mode == 2 && q.flags[n] == 0u) return;  // fallback pass: only the flagged images
+  const bool cutoff_active = q.mode == 0 && q.cutoff_k32[n] != 0xffffffffu && !(q.debug_skip & 4);
   const bool two_stage = q.second_thr >= 0.f;
   unsigned int* g_hist = q.hist + size_t(n) * q.n_bins;
   unsigned int* g_seen = q.class_seen + size_t(n) * q.C;
@@ -491,17 +579,32 @@ __global__ void __launch_bounds__(kNmsThreads) detect_nms_kernel(const DetParams
         }
       }
       __syncthreads();
-      if (tid == 0) {
-        unsigned int cum = 0;
-        int d = dlo;
-        while (d < nb && cum + S.hist[d] <= unsigned(kChunk)) cum += S.hist[d++];
-        // skip leading empty digits is implied (they add 0). If the first non-fitting digit is the
-        // first non-empty one, descend into it.
-        int first_nonempty = dlo;
-        while (first_nonempty < nb && S.hist[first_nonempty] == 0u) ++first_nonempty;
-        S.misc[0] = d;
-        S.misc[1] = (d == first_nonempty && d < nb) ? 1 : 0;  // descend
-        S.misc[2] = int(cum);
+      // d_end = first digit >= dlo whose inclusive running count exceeds kChunk (block-wide scan,
+      // two bins per thread); first_nonempty = first digit >= dlo with a non-zero count.
+      {
+        if (tid == 0) {
+          S.misc[0] = nb;  // d_end
+          S.misc[4] = nb;  // first non-empty
+        }
+        const int b0 = 2 * tid, b1 = 2 * tid + 1;
+        const unsigned int h0 = (b0 >= dlo && b0 < nb) ? S.hist[b0] : 0u;
+        const unsigned int h1 = (b1 >= dlo && b1 < nb) ? S.hist[b1] : 0u;
+        unsigned int inc = h0 + h1;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const unsigned int t = __shfl_up_sync(0xffffffffu, inc, o);
+          if (lane >= o) inc += t;
+        }
+        if (lane == 31) S.wscan[wid] = inc;
+        __syncthreads();
+        unsigned int before = inc - (h0 + h1);
+        for (int w = 0; w < wid; ++w) before += S.wscan[w];
+        if (h0 && before + h0 > unsigned(kChunk)) atomicMin(&S.misc[0], b0);
+        else if (h1 && before + h0 + h1 > unsigned(kChunk)) atomicMin(&S.misc[0], b1);
+        if (h0) atomicMin(&S.misc[4], b0);
+        else if (h1) atomicMin(&S.misc[4], b1);
+        __syncthreads();
+        if (tid == 0) S.misc[1] = (S.misc[0] == S.misc[4] && S.misc[0] < nb) ? 1 : 0;  // descend
       }
       __syncthreads();
       const int d_end = S.misc[0];
@@ -689,6 +792,16 @@ __global__ void __launch_bounds__(kNmsThreads) detect_nms_kernel(const DetParams
   for (int b = tid; b < q.n_bins; b += kNmsThreads) g_hist[b] = 0u;
   for (int c = tid; c < q.C; c += kNmsThreads) g_seen[c] = 0u;
   if (tid == 0) q.cand_count[n] = 0u;
+  if (q.mode == 2 && tid == 0) q.flags[n] = 0u;
+  // The candidates above the speculative cutoff ran out before top_k+1 boxes survived: the answer
+  // needs lower-scored candidates that were not emitted. Flag the image; the fallback pass redoes it.
+  if (cutoff_active && !status && !overflow && (two_stage ? kept2_n : kept_n) < stop_at) {
+    if (tid == 0) {
+      q.flags[n] = 1u;
+      q.out_counts[n] = -3;
+    }
+    return;
+  }
 
   // ---- emit --------------------------------------------------------------------------------
   float4* ob = reinterpret_cast<float4*>(q.out_boxes) + size_t(n) * q.out_cap;
@@ -808,6 +921,9 @@ extern "C" size_t sbod_detect_workspace_bytes(const sbod_detect_desc* d) {
   b += align_up(size_t(d->N) * 4, 256);                       // cand_count
   b += align_up(size_t(d->N) * kMaxBins * 4, 256);            // hist
   b += align_up(size_t(d->N) * size_t(d->C) * 4, 256);        // class_seen
+  b += align_up(size_t(d->N) * kMaxBins * 4, 256);            // shist
+  b += align_up(size_t(d->N) * 4, 256);                       // flags
+  b += align_up(size_t(d->N) * 4, 256) * 2;                   // cutoff_k32, cutoff_floor
   b += align_up(size_t(d->N) * size_t(cand_capacity(d)) * 8, 256);
   return b;
 }
@@ -816,7 +932,8 @@ extern "C" size_t sbod_detect_workspace_bytes(const sbod_detect_desc* d) {
 extern "C" size_t sbod_detect_workspace_zero_bytes(const sbod_detect_desc* d) {
   if (!d) return 0;
   return align_up(size_t(d->N) * 4, 256) + align_up(size_t(d->N) * kMaxBins * 4, 256) +
-         align_up(size_t(d->N) * size_t(d->C) * 4, 256);
+         align_up(size_t(d->N) * size_t(d->C) * 4, 256) + align_up(size_t(d->N) * kMaxBins * 4, 256) +
+         align_up(size_t(d->N) * 4, 256);
 }
 
 static int detect_run(const sbod_detect_desc* d, sbod_stream_t stream, int stage_mask) {
@@ -856,7 +973,14 @@ static int detect_run(const sbod_detect_desc* d, sbod_stream_t stream, int stage
   q.cand_count = reinterpret_cast<unsigned int*>(w); w += align_up(size_t(q.N) * 4, 256);
   q.hist = reinterpret_cast<unsigned int*>(w);       w += align_up(size_t(q.N) * kMaxBins * 4, 256);
   q.class_seen = reinterpret_cast<unsigned int*>(w); w += align_up(size_t(q.N) * size_t(q.C) * 4, 256);
+  q.shist = reinterpret_cast<unsigned int*>(w);      w += align_up(size_t(q.N) * kMaxBins * 4, 256);
+  q.flags = reinterpret_cast<unsigned int*>(w);      w += align_up(size_t(q.N) * 4, 256);
+  q.cutoff_k32 = reinterpret_cast<unsigned int*>(w); w += align_up(size_t(q.N) * 4, 256);
+  q.cutoff_floor = reinterpret_cast<float*>(w);      w += align_up(size_t(q.N) * 4, 256);
   q.cand = reinterpret_cast<unsigned long long*>(w);
+  q.mode = 0;
+  q.sample_stride = 13;
+  q.sample_target = 8 * (q.top_k + 1) + 2048;
   // hist rows are n_bins wide inside the kMaxBins-strided allocation
   const DTiling t = choose_dtiling(q.C);
   q.rows_per_tile = t.rows;
@@ -898,11 +1022,43 @@ static int detect_run(const sbod_detect_desc* d, sbod_stream_t stream, int stage
     const size_t fsmem = size_t(q.n_stages) * sb + 4 * 8;
     int fgrid = sm_count() * ctas;
     if (fgrid > q.n_tiles) fgrid = q.n_tiles;
+    // Speculation pays when the sampled histogram is cheap relative to the main pass.
+    const bool speculate = q.tiles_per_image >= 2 * q.sample_stride && !(q.debug_skip & 4);
     if (stage_mask & 1) {
+      if (speculate) {
+        DetParams qs = q;
+        qs.mode = 1;
+        int sgrid = (q.n_tiles / q.sample_stride + 1);
+        if (sgrid > fgrid) sgrid = fgrid;
+        detect_score_fast_kernel<<<sgrid, kStreamThreads, fsmem, st>>>(qs);
+        SBOD_LAUNCH_CHECK();
+        detect_cutoff_kernel<<<q.N, 256, 0, st>>>(q);
+        SBOD_LAUNCH_CHECK();
+      } else {
+        SBOD_CUDA_TRY(cudaMemsetAsync(q.cutoff_k32, 0xff, size_t(q.N) * 4, st));
+      }
       detect_score_fast_kernel<<<fgrid, kStreamThreads, fsmem, st>>>(q);
       SBOD_LAUNCH_CHECK();
     }
+    if (stage_mask & 2) {
+      const size_t nms_smem_f = ((sizeof(NmsSmem) + 127) & ~size_t(127)) + size_t(q.kcap) * 25 + 256 +
+                                size_t(q.C + 1) * 4;
+      if (nms_smem_f > 220 * 1024) return SBOD_ERR_UNSUPPORTED;
+      detect_nms_kernel<<<q.N, kNmsThreads, nms_smem_f, st>>>(q);
+      SBOD_LAUNCH_CHECK();
+      if (speculate) {  // exact fallback for the images whose candidates ran out (usually none)
+        DetParams qf = q;
+        qf.mode = 2;
+        detect_score_fast_kernel<<<fgrid, kStreamThreads, fsmem, st>>>(qf);
+        SBOD_LAUNCH_CHECK();
+        detect_nms_kernel<<<q.N, kNmsThreads, nms_smem_f, st>>>(qf);
+        SBOD_LAUNCH_CHECK();
+      }
+      return SBOD_OK;
+    }
+    if (!(stage_mask & 2)) return SBOD_OK;
   } else if (stage_mask & 1) {
+    SBOD_CUDA_TRY(cudaMemsetAsync(q.cutoff_k32, 0xff, size_t(q.N) * 4, st));  // no speculation here
     detect_score_kernel<<<grid, kDRows, t.smem, st>>>(q);
     SBOD_LAUNCH_CHECK();
   }

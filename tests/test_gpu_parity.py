@@ -329,3 +329,29 @@ def test_detect_full_batch_properties(dev):
         assert int(c1[0]) == c
         assert torch.equal(l1[0, :c], ol[i, :c]) and torch.equal(p1[0, :c], op[i, :c])
         assert torch.equal(s1[0, :c], osc[i, :c])
+
+
+def test_detect_speculative_cutoff_fallback(dev):
+    """Every prior decodes to the same box, so NMS keeps one box per class and the top-k is never
+    filled: the sampled score cutoff is too strict by construction and the exact fallback pass must
+    reproduce the reference (class-major, all survivors)."""
+    from oracle import box_pipeline as O
+    from shape_based_object_detection_b200 import priors as PR, synth
+    from shape_based_object_detection_b200.models import utils as MU
+    pri = PR.ssd300_priors()
+    _, scores = synth.make_eval_batch(pri, 3, 6, 99, bg_bias=3.0)
+    locs = torch.tensor([0.2, 0.25, 0.6, 0.7]).repeat(3, pri.size(0), 1).contiguous()
+    locs[2] += torch.rand((pri.size(0), 4), generator=torch.Generator().manual_seed(1)) * 0.3  # a normal image
+    want = O.detect(locs.clone(), scores, 0.01, 0.45, 200, pri, box_type="corner")
+    got = MU.detect(cu(locs.clone(), dev), cu(scores, dev), 0.01, 0.45, 200, cu(pri, dev),
+                    cfg(n_classes=6, box_type="corner"))
+    for i in range(3):
+        assert torch.equal(got[1][i].cpu(), want[1][i]), i
+        assert torch.allclose(got[2][i].cpu(), want[2][i], rtol=1e-5, atol=1e-8)
+        assert torch.allclose(got[0][i].cpu(), want[0][i], rtol=1e-5, atol=1e-6)
+    assert got[1][0].numel() <= 5
+    # the workspace is clean again: a second call gives the same answer
+    again = MU.detect(cu(locs.clone(), dev), cu(scores, dev), 0.01, 0.45, 200, cu(pri, dev),
+                      cfg(n_classes=6, box_type="corner"))
+    for i in range(3):
+        assert torch.equal(again[1][i], got[1][i]) and torch.equal(again[2][i], got[2][i])
