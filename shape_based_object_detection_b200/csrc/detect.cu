@@ -256,10 +256,8 @@ __global__ void __launch_bounds__(kStreamThreads, 2) detect_score_fast_kernel(co
   float* stages = reinterpret_cast<float*>(smem_raw);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + size_t(q.n_stages) * q.stage_floats * 4);
   __shared__ unsigned int s_hist[kMaxBins];
-  __shared__ unsigned int s_wtot[kStreamThreads / 32];
-  __shared__ unsigned int s_base;
 
-  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int tid = threadIdx.x, lane = tid & 31;
   const int C = q.C;
   // tiles of this CTA: all of a contiguous range (modes 0, 2) or every sample_stride-th tile (mode 1)
   const int stride = q.mode == 1 ? q.sample_stride : 1;
@@ -383,25 +381,23 @@ __global__ void __launch_bounds__(kStreamThreads, 2) detect_score_fast_kernel(co
         if (pr > q.min_score && (kOneBits - min(__float_as_uint(pr), kOneBits)) < cut_k32) ++cnt; else m1 &= ~(1u << j);
       }
     }
-    // block-exclusive scan of the per-thread counts, one global atomic per tile
+    // warp-exclusive scan of the per-thread counts; one global atomic per warp that has candidates
+    // (no CTA-wide barrier: while this warp waits for its slot the other warps keep streaming)
     unsigned int inc = cnt;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
       const unsigned int t = __shfl_up_sync(0xffffffffu, inc, o);
       if (lane >= o) inc += t;
     }
-    if (lane == 31) s_wtot[wid] = inc;
-    __syncthreads();
-    unsigned int off = inc - cnt, tot = 0;
-#pragma unroll
-    for (int w = 0; w < kStreamThreads / 32; ++w) {
-      if (w < wid) off += s_wtot[w];
-      tot += s_wtot[w];
+    const unsigned int wtot = __shfl_sync(0xffffffffu, inc, 31);
+    unsigned int wbase = 0u;
+    if (wtot && q.mode != 1) {
+      if (lane == 31) wbase = atomicAdd(&q.cand_count[n], wtot);
+      wbase = __shfl_sync(0xffffffffu, wbase, 31);
     }
-    if (tid == 0) s_base = (tot && q.mode != 1) ? atomicAdd(&q.cand_count[n], tot) : 0u;
-    __syncthreads();
+    const unsigned int off = inc - cnt;
     if (cnt && !(q.debug_skip & 1)) {
-      long long slot = (long long)s_base + off;
+      long long slot = (long long)wbase + off;
       unsigned long long* dst = q.cand + size_t(n) * q.cand_cap;
 #pragma unroll
       for (int half = 0; half < 2; ++half) {
@@ -426,7 +422,7 @@ __global__ void __launch_bounds__(kStreamThreads, 2) detect_score_fast_kernel(co
         }
       }
     }
-    __syncthreads();  // every thread is done with stage s (and with s_wtot / s_base)
+    __syncthreads();  // every thread is done with stage s
     if (tid == 0 && it + q.n_stages < n_my) issue(it + q.n_stages, stage, &bars[s]);
   }
   if (hist_n >= 0) flush_hist(hist_n);
@@ -980,7 +976,8 @@ static int detect_run(const sbod_detect_desc* d, sbod_stream_t stream, int stage
   q.cand = reinterpret_cast<unsigned long long*>(w);
   q.mode = 0;
   q.sample_stride = 13;
-  q.sample_target = 8 * (q.top_k + 1) + 2048;
+  q.sample_target = 4 * (q.top_k + 1) + 1024;
+  if (getenv("SBOD_TARGET")) q.sample_target = atoi(getenv("SBOD_TARGET"));
   // hist rows are n_bins wide inside the kMaxBins-strided allocation
   const DTiling t = choose_dtiling(q.C);
   q.rows_per_tile = t.rows;
