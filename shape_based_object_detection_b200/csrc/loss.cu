@@ -55,6 +55,7 @@ struct LossParams {
   float* cand;                // [N, P]
   double* blockpart;          // [N, ceil(P/1024), 4]
   unsigned int* counters;     // [4]
+  unsigned int* match_q;      // [N] per-image chunk queues of the match role
   // tiling
   int rows_per_tile, tiles_per_image, n_tiles, n_stages;
   uint32_t stage_floats;
@@ -295,19 +296,13 @@ __global__ void __launch_bounds__(kRows) match_lse_kernel(const LossParams q) {
 // ------------------------------------------------------------------------------------------
 constexpr int kMatchWarps = 8;
 constexpr int kMatchThreads = 32 * kMatchWarps;
-constexpr int kMatchChunk = 1024;  // priors per match work item
 constexpr int kFastThreads = kStreamThreads + kMatchThreads;
 
 __global__ void __launch_bounds__(kFastThreads, 2) match_lse_fast_kernel(const LossParams q) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   float* stages = reinterpret_cast<float*>(smem_raw);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + size_t(q.n_stages) * q.stage_floats * 4);
-  __shared__ float4 s_gbox[kGtChunk];
-  __shared__ float s_garea[kGtChunk];
   __shared__ unsigned long long s_wkey[kMatchWarps][kGtChunk];
-  __shared__ uint8_t s_gskip[kGtChunk];
-  __shared__ int s_gok;
-  __shared__ int s_item;
 
   const int tid = threadIdx.x, lane = tid & 31;
   int t0, t1;
@@ -356,164 +351,180 @@ __global__ void __launch_bounds__(kFastThreads, 2) match_lse_fast_kernel(const L
   }
 
   // =========================== match role ===========================
-  // Work items are (image, chunk of kMatchChunk priors), pulled from a global queue heaviest first
-  // (the large priors at the end of every image overlap almost every object), so the matching
-  // load is balanced across the whole grid independently of the tiles the stream role owns.
+  // Every match WARP works on its own: it pulls 32-prior slices from per-image queues (image affinity:
+  // a warp starts at its CTA's home image and moves on when that queue runs dry; heaviest slices —
+  // the large priors at the end of an image — first; the next slice index is requested before the
+  // current one is processed). Ground truth is read through L1 (an image's boxes are ~2 KB) and
+  // handed from lane to lane with shuffles, so the role needs no barrier at all.
   if (q.debug_skip & 2) return;
   const int tm = tid - kStreamThreads, wm = tm >> 5;
   const float INF = __int_as_float(0x7f800000);
-  const int chunks_per_image = (q.P + kMatchChunk - 1) / kMatchChunk;
-  const int n_items = chunks_per_image * q.N;
+  const int slices_per_image = (q.P + 31) / 32;
+  unsigned long long* wkey = s_wkey[wm];
   int prev_n = -1, g0 = 0, G = 0;
-  bool resident = false;
 
-  auto load_chunk = [&](int c0, int gc) {
-    named_bar_sync(2, kMatchThreads);
-    if (tm == 0) s_gok = 1;
-    named_bar_sync(2, kMatchThreads);
-    bool ok = true;
-    for (int i = tm; i < gc; i += kMatchThreads) {
-      const float4 g = q.gt_boxes[g0 + c0 + i];
-      s_gbox[i] = g;
-      s_garea[i] = box_area_rn(g);
-      s_gskip[i] = gt_is_zero(g) ? 1 : 0;
-      ok = ok && (g.z >= g.x) && (g.w >= g.y);
-#pragma unroll
-      for (int w = 0; w < kMatchWarps; ++w) s_wkey[w][i] = 0ull;
+  auto flush_keys = [&](int n) {
+    const int gl = min(G, kGtChunk);
+    for (int i = lane; i < gl; i += 32) {
+      const unsigned long long k = wkey[i];
+      if (k) atomicMax(&q.gtkey[size_t(n) * q.gmax + i], k);
+      wkey[i] = 0ull;
     }
-    if (!ok) s_gok = 0;
-    named_bar_sync(2, kMatchThreads);
+    __syncwarp();
   };
-  auto flush_chunk = [&](int n, int c0, int gc) {
-    named_bar_sync(2, kMatchThreads);
-    for (int i = tm; i < gc; i += kMatchThreads) {
-      unsigned long long k = s_wkey[0][i];
-#pragma unroll
-      for (int w = 1; w < kMatchWarps; ++w) k = max(k, s_wkey[w][i]);
-      if (k) atomicMax(&q.gtkey[size_t(n) * q.gmax + c0 + i], k);
-    }
-  };
+  for (int i = lane; i < kGtChunk; i += 32) wkey[i] = 0ull;
+  __syncwarp();
 
+  int img_i = 0;
+  int cur_n = int(blockIdx.x % q.N);
+  int nxt = 0;
+  if (lane == 0) nxt = int(atomicAdd(&q.match_q[cur_n], 1u));
   for (;;) {
-    named_bar_sync(2, kMatchThreads);
-    if (tm == 0) s_item = int(atomicAdd(&q.counters[1], 1u));
-    named_bar_sync(2, kMatchThreads);
-    const int item = s_item;
-    if (item >= n_items) break;
-    const int n = item % q.N;
-    const int chunk = chunks_per_image - 1 - item / q.N;  // heaviest (last) chunks first
-    if (n != prev_n) {
-      if (prev_n >= 0 && resident) flush_chunk(prev_n, 0, G);
-      g0 = q.gt_offsets[n];
-      G = q.gt_offsets[n + 1] - g0;
-      resident = G <= kGtChunk;
-      if (resident) load_chunk(0, G);
-      prev_n = n;
-    }
-    const int pc0 = chunk * kMatchChunk;
-    const int pc1 = min(q.P, pc0 + kMatchChunk);
-
-    for (int c0 = 0; c0 < max(G, 1); c0 += kGtChunk) {
-      const int gc = min(kGtChunk, G - c0);
-      if (!resident) load_chunk(c0, gc);
-      const bool gok = s_gok != 0;
-      // every warp walks its share of the chunk's 32-prior slices
-      for (int ps = pc0 + 32 * wm; ps < pc1; ps += 32 * kMatchWarps) {
-        const int p = ps + lane;
-        const bool valid = p < pc1;
-        const size_t np = size_t(n) * q.P + (valid ? p : pc0);
-        float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (valid) a = q.anchors_xy ? q.anchors_xy[np] : q.priors_xy[p];
-        const float aa = box_area_rn(a);
-        const bool azero = anchor_is_zero(a);
-        const bool active = valid && !azero;
-        const bool warp_a_ok = __all_sync(0xffffffffu, ((a.z >= a.x) && (a.w >= a.y)) || !valid) != 0;
-        float best = -INF;
-        int bobj = 0;
-        if (c0 > 0 && valid) {  // continue the running arg-max of an earlier object chunk
-          best = q.ov[np];
-          bobj = q.obj[np];
-        }
-        if (gok && warp_a_ok) {
-          const float bx1 = warp_min(active ? a.x : INF), by1 = warp_min(active ? a.y : INF);
-          const float bx2 = warp_max(active ? a.z : -INF), by2 = warp_max(active ? a.w : -INF);
-          float cbest = azero ? -1.f : 0.f;
-          int cidx = c0;
-          for (int base = 0; base < gc; base += 32) {
-            const int i = base + lane;
-            bool hit = false;
-            if (i < gc && !s_gskip[i]) {
-              const float4 g = s_gbox[i];
-              hit = (g.z > bx1) && (g.x < bx2) && (g.w > by1) && (g.y < by2);
-            }
-            unsigned m = __ballot_sync(0xffffffffu, hit);
-            while (m) {
-              const int j = base + (__ffs(m) - 1);
-              m &= m - 1;
-              float iou = 0.f;
-              if (active) {
-                const float inner = inter_rn(s_gbox[j], a);
-                if (inner > 0.f)
-                  iou = __fdiv_rn(inner, __fadd_rn(__fsub_rn(__fadd_rn(s_garea[j], aa), inner), kEps));
-              }
-              if (iou > cbest) {
-                cbest = iou;
-                cidx = c0 + j;
-              }
-              // Best prior of object j seen by this warp so far (max IoU, then lowest prior index).
-              // The cross-lane reduction only runs when some lane beats the stored value.
-              const unsigned long long cur = s_wkey[wm][j];
-              const unsigned bits = __float_as_uint(iou);
-              const unsigned cur_bits = unsigned(cur >> 32);
-              const unsigned cur_p = 0xffffffffu - unsigned(cur & 0xffffffffull);
-              const bool better = bits > cur_bits || (bits == cur_bits && bits != 0u && unsigned(p) < cur_p);
-              if (__any_sync(0xffffffffu, better)) {
-                const unsigned mb = __reduce_max_sync(0xffffffffu, bits);
-                const unsigned pm = __reduce_min_sync(0xffffffffu, bits == mb ? unsigned(p) : 0xffffffffu);
-                if (lane == 0) s_wkey[wm][j] = (static_cast<unsigned long long>(mb) << 32) | (0xffffffffu - pm);
-              }
-            }
-          }
-          if (cbest > best) {
-            best = cbest;
-            bobj = cidx;
-          }
-        } else if (valid) {
-          for (int j = 0; j < gc; ++j) {
-            float iou = iou_metrics_rn(s_gbox[j], s_garea[j], a, aa);
-            if (s_gskip[j]) iou = 0.f;
-            if (azero) iou = -1.f;
-            if (iou > best) {
-              best = iou;
-              bobj = c0 + j;
-            }
-            if (iou > 0.f) {
-              const unsigned long long key =
-                  (static_cast<unsigned long long>(__float_as_uint(iou)) << 32) |
-                  (0xffffffffu - unsigned(p));
-              if (key > s_wkey[wm][j]) atomicMax(&s_wkey[wm][j], key);
-            }
-          }
-        }
-        if (G == 0) {
-          best = 0.f;
-          bobj = 0;
-        }
-        if (valid) {
-          q.ov[np] = best;
-          q.obj[np] = bobj;
+    int item = __shfl_sync(0xffffffffu, nxt, 0);
+    while (item >= slices_per_image) {
+      // This image is drained. Look at 32 other queues at once (plain loads) and jump to the first
+      // one that still has work, instead of probing them one atomic at a time.
+      bool found = false;
+      while (!found) {
+        const int remaining = q.N - 1 - img_i;  // images after cur_n that were not visited yet
+        if (remaining <= 0) break;
+        const int span = min(32, remaining);
+        const int cand = (cur_n + 1 + lane) % q.N;
+        const bool has = lane < span && *reinterpret_cast<volatile unsigned int*>(&q.match_q[cand]) <
+                                            unsigned(slices_per_image);
+        const unsigned bal = __ballot_sync(0xffffffffu, has);
+        if (bal) {
+          const int skip = __ffs(bal) - 1;
+          cur_n = (cur_n + 1 + skip) % q.N;
+          img_i += skip + 1;
+          found = true;
+        } else {
+          cur_n = (cur_n + span) % q.N;
+          img_i += span;
         }
       }
-      if (!resident) flush_chunk(n, c0, gc);
+      if (!found) break;
+      if (lane == 0) nxt = int(atomicAdd(&q.match_q[cur_n], 1u));
+      item = __shfl_sync(0xffffffffu, nxt, 0);
+    }
+    if (item >= slices_per_image) break;
+    if (lane == 0) nxt = int(atomicAdd(&q.match_q[cur_n], 1u));  // prefetch the next slice index
+    const int n = cur_n;
+    if (n != prev_n) {
+      if (prev_n >= 0) flush_keys(prev_n);
+      g0 = q.gt_offsets[n];
+      G = q.gt_offsets[n + 1] - g0;
+      prev_n = n;
+    }
+    const int ps = (slices_per_image - 1 - item) * 32;  // heaviest (last) slices first
+    const int p = ps + lane;
+    const bool valid = p < q.P;
+    const size_t np = size_t(n) * q.P + (valid ? p : ps);
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (valid) a = q.anchors_xy ? q.anchors_xy[np] : q.priors_xy[p];
+    const float aa = box_area_rn(a);
+    const bool azero = anchor_is_zero(a);
+    const bool active = valid && !azero;
+    const bool warp_a_ok = __all_sync(0xffffffffu, ((a.z >= a.x) && (a.w >= a.y)) || !valid) != 0;
+    const float bx1 = warp_min(active ? a.x : INF), by1 = warp_min(active ? a.y : INF);
+    const float bx2 = warp_max(active ? a.z : -INF), by2 = warp_max(active ? a.w : -INF);
+    float best = -INF;  // running arg-max over objects, first index wins
+    int bobj = 0;
+
+    for (int base = 0; base < G; base += 32) {
+      const int gi = base + lane;
+      float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (gi < G) g = q.gt_boxes[g0 + gi];
+      const bool gskip = gi >= G || gt_is_zero(g);
+      const bool grp_ok = __all_sync(0xffffffffu, (g.z >= g.x) && (g.w >= g.y)) != 0;
+      if (grp_ok && warp_a_ok) {
+        // fast path: a pair that does not intersect is exactly +0, so only objects touching the
+        // warp's bounding box are evaluated
+        const bool hit = !gskip && (g.z > bx1) && (g.x < bx2) && (g.w > by1) && (g.y < by2);
+        unsigned m = __ballot_sync(0xffffffffu, hit);
+        float cbest = azero ? -1.f : 0.f;
+        int cidx = base;
+        while (m) {
+          const int src = __ffs(m) - 1;
+          m &= m - 1;
+          const int j = base + src;
+          float4 gj;
+          gj.x = __shfl_sync(0xffffffffu, g.x, src);
+          gj.y = __shfl_sync(0xffffffffu, g.y, src);
+          gj.z = __shfl_sync(0xffffffffu, g.z, src);
+          gj.w = __shfl_sync(0xffffffffu, g.w, src);
+          float iou = 0.f;
+          if (active) {
+            const float inner = inter_rn(gj, a);
+            if (inner > 0.f)
+              iou = __fdiv_rn(inner, __fadd_rn(__fsub_rn(__fadd_rn(box_area_rn(gj), aa), inner), kEps));
+          }
+          if (iou > cbest) {
+            cbest = iou;
+            cidx = j;
+          }
+          // best prior of object j seen by this warp (max IoU, then lowest prior index); the
+          // cross-lane reduction only runs when some lane beats the stored value
+          const unsigned bits = __float_as_uint(iou);
+          if (j < kGtChunk) {
+            const unsigned long long cur = wkey[j];
+            const unsigned cur_bits = unsigned(cur >> 32);
+            const unsigned cur_p = 0xffffffffu - unsigned(cur & 0xffffffffull);
+            const bool better = bits > cur_bits || (bits == cur_bits && bits != 0u && unsigned(p) < cur_p);
+            if (__any_sync(0xffffffffu, better)) {
+              const unsigned mb = __reduce_max_sync(0xffffffffu, bits);
+              const unsigned pm = __reduce_min_sync(0xffffffffu, bits == mb ? unsigned(p) : 0xffffffffu);
+              if (lane == 0) wkey[j] = (static_cast<unsigned long long>(mb) << 32) | (0xffffffffu - pm);
+              __syncwarp();
+            }
+          } else if (bits) {  // more objects than the per-warp table holds: straight to global memory
+            atomicMax(&q.gtkey[size_t(n) * q.gmax + j],
+                      (static_cast<unsigned long long>(bits) << 32) | (0xffffffffu - unsigned(p)));
+          }
+        }
+        if (cbest > best) {
+          best = cbest;
+          bobj = cidx;
+        }
+      } else {
+        // general path: every pair, masks applied as the reference does (metrics.py:249-250)
+        const int gcnt = min(32, G - base);
+        for (int src = 0; src < gcnt; ++src) {
+          float4 gj;
+          gj.x = __shfl_sync(0xffffffffu, g.x, src);
+          gj.y = __shfl_sync(0xffffffffu, g.y, src);
+          gj.z = __shfl_sync(0xffffffffu, g.z, src);
+          gj.w = __shfl_sync(0xffffffffu, g.w, src);
+          const bool sk = __shfl_sync(0xffffffffu, int(gskip), src) != 0;
+          float iou = iou_metrics_rn(gj, box_area_rn(gj), a, aa);
+          if (sk) iou = 0.f;
+          if (azero) iou = -1.f;
+          if (valid && iou > best) {
+            best = iou;
+            bobj = base + src;
+          }
+          if (valid && iou > 0.f)
+            atomicMax(&q.gtkey[size_t(n) * q.gmax + base + src],
+                      (static_cast<unsigned long long>(__float_as_uint(iou)) << 32) |
+                          (0xffffffffu - unsigned(p)));
+        }
+      }
+    }
+    if (G == 0) {
+      best = 0.f;
+      bobj = 0;
+    }
+    if (valid) {
+      q.ov[np] = best;
+      q.obj[np] = bobj;
     }
   }
-  if (prev_n >= 0 && resident) flush_chunk(prev_n, 0, G);
-  // the last match group to finish resets the queue for the next launch
-  named_bar_sync(2, kMatchThreads);
-  if (tm == 0) {
+  if (prev_n >= 0) flush_keys(prev_n);
+  // the last match warp of the grid resets the queues for the next launch
+  if (lane == 0) {
     __threadfence();
-    if (atomicAdd(&q.counters[2], 1u) == gridDim.x - 1) {
-      q.counters[1] = 0u;
+    if (atomicAdd(&q.counters[2], 1u) == gridDim.x * kMatchWarps - 1) {
+      for (int i = 0; i < q.N; ++i) q.match_q[i] = 0u;
       q.counters[2] = 0u;
     }
   }
@@ -1372,6 +1383,8 @@ static int fill_params(const sbod_loss_desc* d, LossParams& q, bool need_scores)
   w += 256;
   q.gtkey = reinterpret_cast<unsigned long long*>(w);
   w += align_up(size_t(q.N) * q.gmax * 8, 256);
+  q.match_q = reinterpret_cast<unsigned int*>(w);
+  w += align_up(size_t(q.N) * 4, 256);
   q.cand = reinterpret_cast<float*>(w);
   w += align_up(size_t(q.N) * q.P * 4, 256);
   q.blockpart = reinterpret_cast<double*>(w);
@@ -1411,7 +1424,8 @@ using namespace sbod;
 extern "C" size_t sbod_loss_workspace_bytes(const sbod_loss_desc* d) {
   if (!d) return 0;
   const int gmax = d->gmax > 0 ? d->gmax : 1;
-  return 256 + align_up(size_t(d->N) * gmax * 8, 256) + align_up(size_t(d->N) * d->P * 4, 256) +
+  return 256 + align_up(size_t(d->N) * gmax * 8, 256) + align_up(size_t(d->N) * 4, 256) +
+         align_up(size_t(d->N) * d->P * 4, 256) +
          align_up(size_t(d->N) * ((size_t(d->P) + 1023) / 1024) * 32, 256);
 }
 
@@ -1683,7 +1697,8 @@ extern "C" int sbod_loss_forward_host(const sbod_loss_desc* h, int T, float* los
     SBOD_CUDA_TRY(cudaMemcpyAsync(base + a.gtl, h->gt_labels, size_t(T) * 8, cudaMemcpyHostToDevice, st));
   }
   SBOD_CUDA_TRY(cudaMemcpyAsync(base + a.gto, h->gt_offsets, size_t(h->N + 1) * 4, cudaMemcpyHostToDevice, st));
-  SBOD_CUDA_TRY(cudaMemsetAsync(base + a.ws, 0, 256 + align_up(size_t(h->N) * (h->gmax > 0 ? h->gmax : 1) * 8, 256), st));
+  SBOD_CUDA_TRY(cudaMemsetAsync(base + a.ws, 0, 256 + align_up(size_t(h->N) * (h->gmax > 0 ? h->gmax : 1) * 8, 256) +
+                                                    align_up(size_t(h->N) * 4, 256), st));
   sbod_loss_desc d = *h;
   d.locs = reinterpret_cast<const float*>(base + a.locs);
   d.scores = reinterpret_cast<const float*>(base + a.scores);
