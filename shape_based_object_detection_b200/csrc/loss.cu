@@ -359,7 +359,8 @@ __global__ void __launch_bounds__(kFastThreads, 2) match_lse_fast_kernel(const L
   if (q.debug_skip & 2) return;
   const int tm = tid - kStreamThreads, wm = tm >> 5;
   const float INF = __int_as_float(0x7f800000);
-  const int slices_per_image = (q.P + 31) / 32;
+  constexpr int kSl = 1;  // 32-prior slices per warp and pass (2 was measured slower: the joint bounding box admits more objects)
+  const int slices_per_image = (q.P + 32 * kSl - 1) / (32 * kSl);
   unsigned long long* wkey = s_wkey[wm];
   int prev_n = -1, g0 = 0, G = 0;
 
@@ -416,20 +417,35 @@ __global__ void __launch_bounds__(kFastThreads, 2) match_lse_fast_kernel(const L
       G = q.gt_offsets[n + 1] - g0;
       prev_n = n;
     }
-    const int ps = (slices_per_image - 1 - item) * 32;  // heaviest (last) slices first
-    const int p = ps + lane;
-    const bool valid = p < q.P;
-    const size_t np = size_t(n) * q.P + (valid ? p : ps);
-    float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (valid) a = q.anchors_xy ? q.anchors_xy[np] : q.priors_xy[p];
-    const float aa = box_area_rn(a);
-    const bool azero = anchor_is_zero(a);
-    const bool active = valid && !azero;
-    const bool warp_a_ok = __all_sync(0xffffffffu, ((a.z >= a.x) && (a.w >= a.y)) || !valid) != 0;
-    const float bx1 = warp_min(active ? a.x : INF), by1 = warp_min(active ? a.y : INF);
-    const float bx2 = warp_max(active ? a.z : -INF), by2 = warp_max(active ? a.w : -INF);
-    float best = -INF;  // running arg-max over objects, first index wins
-    int bobj = 0;
+    // Two 32-prior slices per warp and pass (kSl): their IoU chains are independent (ILP), they share
+    // the object loads / shuffles, and one cross-lane reduction serves 64 priors.
+    const int ps = (slices_per_image - 1 - item) * (32 * kSl);  // heaviest (last) slices first
+    int p[kSl];
+    bool valid[kSl], azero[kSl], active[kSl];
+    float4 a[kSl];
+    float aa[kSl], best[kSl];
+    int bobj[kSl];
+    bool a_ok = true;
+    float bx1 = INF, by1 = INF, bx2 = -INF, by2 = -INF;
+#pragma unroll
+    for (int u = 0; u < kSl; ++u) {
+      p[u] = ps + 32 * u + lane;
+      valid[u] = p[u] < q.P;
+      a[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (valid[u]) a[u] = q.anchors_xy ? q.anchors_xy[size_t(n) * q.P + p[u]] : q.priors_xy[p[u]];
+      aa[u] = box_area_rn(a[u]);
+      azero[u] = anchor_is_zero(a[u]);
+      active[u] = valid[u] && !azero[u];
+      a_ok = a_ok && (((a[u].z >= a[u].x) && (a[u].w >= a[u].y)) || !valid[u]);
+      if (active[u]) {
+        bx1 = fminf(bx1, a[u].x); by1 = fminf(by1, a[u].y);
+        bx2 = fmaxf(bx2, a[u].z); by2 = fmaxf(by2, a[u].w);
+      }
+      best[u] = -INF;  // running arg-max over objects, first index wins
+      bobj[u] = 0;
+    }
+    const bool warp_a_ok = __all_sync(0xffffffffu, a_ok) != 0;
+    bx1 = warp_min(bx1); by1 = warp_min(by1); bx2 = warp_max(bx2); by2 = warp_max(by2);
 
     for (int base = 0; base < G; base += 32) {
       const int gi = base + lane;
@@ -442,8 +458,13 @@ __global__ void __launch_bounds__(kFastThreads, 2) match_lse_fast_kernel(const L
         // warp's bounding box are evaluated
         const bool hit = !gskip && (g.z > bx1) && (g.x < bx2) && (g.w > by1) && (g.y < by2);
         unsigned m = __ballot_sync(0xffffffffu, hit);
-        float cbest = azero ? -1.f : 0.f;
-        int cidx = base;
+        float cbest[kSl];
+        int cidx[kSl];
+#pragma unroll
+        for (int u = 0; u < kSl; ++u) {
+          cbest[u] = azero[u] ? -1.f : 0.f;
+          cidx[u] = base;
+        }
         while (m) {
           const int src = __ffs(m) - 1;
           m &= m - 1;
@@ -453,39 +474,54 @@ __global__ void __launch_bounds__(kFastThreads, 2) match_lse_fast_kernel(const L
           gj.y = __shfl_sync(0xffffffffu, g.y, src);
           gj.z = __shfl_sync(0xffffffffu, g.z, src);
           gj.w = __shfl_sync(0xffffffffu, g.w, src);
-          float iou = 0.f;
-          if (active) {
-            const float inner = inter_rn(gj, a);
-            if (inner > 0.f)
-              iou = __fdiv_rn(inner, __fadd_rn(__fsub_rn(__fadd_rn(box_area_rn(gj), aa), inner), kEps));
+          const float ga = box_area_rn(gj);
+          float iou[kSl];
+#pragma unroll
+          for (int u = 0; u < kSl; ++u) {
+            iou[u] = 0.f;
+            if (active[u]) {
+              const float inner = inter_rn(gj, a[u]);
+              if (inner > 0.f)
+                iou[u] = __fdiv_rn(inner, __fadd_rn(__fsub_rn(__fadd_rn(ga, aa[u]), inner), kEps));
+            }
           }
-          if (iou > cbest) {
-            cbest = iou;
-            cidx = j;
+          unsigned bits = 0u, pb = 0xffffffffu;
+#pragma unroll
+          for (int u = 0; u < kSl; ++u) {
+            if (iou[u] > cbest[u]) {
+              cbest[u] = iou[u];
+              cidx[u] = j;
+            }
+            const unsigned b = __float_as_uint(iou[u]);
+            if (b > bits) {  // strictly greater: ties keep the lower prior index (earlier slice)
+              bits = b;
+              pb = unsigned(p[u]);
+            }
           }
           // best prior of object j seen by this warp (max IoU, then lowest prior index); the
           // cross-lane reduction only runs when some lane beats the stored value
-          const unsigned bits = __float_as_uint(iou);
           if (j < kGtChunk) {
             const unsigned long long cur = wkey[j];
             const unsigned cur_bits = unsigned(cur >> 32);
             const unsigned cur_p = 0xffffffffu - unsigned(cur & 0xffffffffull);
-            const bool better = bits > cur_bits || (bits == cur_bits && bits != 0u && unsigned(p) < cur_p);
+            const bool better = bits > cur_bits || (bits == cur_bits && bits != 0u && pb < cur_p);
             if (__any_sync(0xffffffffu, better)) {
               const unsigned mb = __reduce_max_sync(0xffffffffu, bits);
-              const unsigned pm = __reduce_min_sync(0xffffffffu, bits == mb ? unsigned(p) : 0xffffffffu);
+              const unsigned pm = __reduce_min_sync(0xffffffffu, bits == mb ? pb : 0xffffffffu);
               if (lane == 0) wkey[j] = (static_cast<unsigned long long>(mb) << 32) | (0xffffffffu - pm);
               __syncwarp();
             }
           } else if (bits) {  // more objects than the per-warp table holds: straight to global memory
             atomicMax(&q.gtkey[size_t(n) * q.gmax + j],
-                      (static_cast<unsigned long long>(bits) << 32) | (0xffffffffu - unsigned(p)));
+                      (static_cast<unsigned long long>(bits) << 32) | (0xffffffffu - pb));
           }
         }
-        if (cbest > best) {
-          best = cbest;
-          bobj = cidx;
-        }
+#pragma unroll
+        for (int u = 0; u < kSl; ++u)
+          if (cbest[u] > best[u]) {
+            best[u] = cbest[u];
+            bobj[u] = cidx[u];
+          }
       } else {
         // general path: every pair, masks applied as the reference does (metrics.py:249-250)
         const int gcnt = min(32, G - base);
@@ -496,27 +532,33 @@ __global__ void __launch_bounds__(kFastThreads, 2) match_lse_fast_kernel(const L
           gj.z = __shfl_sync(0xffffffffu, g.z, src);
           gj.w = __shfl_sync(0xffffffffu, g.w, src);
           const bool sk = __shfl_sync(0xffffffffu, int(gskip), src) != 0;
-          float iou = iou_metrics_rn(gj, box_area_rn(gj), a, aa);
-          if (sk) iou = 0.f;
-          if (azero) iou = -1.f;
-          if (valid && iou > best) {
-            best = iou;
-            bobj = base + src;
+#pragma unroll
+          for (int u = 0; u < kSl; ++u) {
+            float iou = iou_metrics_rn(gj, box_area_rn(gj), a[u], aa[u]);
+            if (sk) iou = 0.f;
+            if (azero[u]) iou = -1.f;
+            if (valid[u] && iou > best[u]) {
+              best[u] = iou;
+              bobj[u] = base + src;
+            }
+            if (valid[u] && iou > 0.f)
+              atomicMax(&q.gtkey[size_t(n) * q.gmax + base + src],
+                        (static_cast<unsigned long long>(__float_as_uint(iou)) << 32) |
+                            (0xffffffffu - unsigned(p[u])));
           }
-          if (valid && iou > 0.f)
-            atomicMax(&q.gtkey[size_t(n) * q.gmax + base + src],
-                      (static_cast<unsigned long long>(__float_as_uint(iou)) << 32) |
-                          (0xffffffffu - unsigned(p)));
         }
       }
     }
-    if (G == 0) {
-      best = 0.f;
-      bobj = 0;
-    }
-    if (valid) {
-      q.ov[np] = best;
-      q.obj[np] = bobj;
+#pragma unroll
+    for (int u = 0; u < kSl; ++u) {
+      if (G == 0) {
+        best[u] = 0.f;
+        bobj[u] = 0;
+      }
+      if (valid[u]) {
+        q.ov[size_t(n) * q.P + p[u]] = best[u];
+        q.obj[size_t(n) * q.P + p[u]] = bobj[u];
+      }
     }
   }
   if (prev_n >= 0) flush_keys(prev_n);
