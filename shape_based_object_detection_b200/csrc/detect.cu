@@ -65,6 +65,7 @@ struct DetParams {
   float* cutoff_floor;          // [N] score just below the cutoff (mask floor)
   unsigned int* flags;          // [N] 1 = the cutoff was too strict, redo this image in full
   int sample_stride, sample_target;
+  int speculate;                // the sampling pass ran: cutoffs come from shist
   // tiling
   int rows_per_tile, tiles_per_image, n_tiles, n_stages;
   uint32_t stage_floats;
@@ -244,6 +245,56 @@ __global__ void __launch_bounds__(kDRows) detect_score_kernel(const DetParams q)
   }
 }
 
+// Per-image emission cutoff from the histogram of the sampled tiles: the score bin above which about
+// sample_target candidates are expected. Block-wide (any block size that is a multiple of 32);
+// every thread returns the same (k32 cutoff, score floor). scratch: >= 34 unsigned ints.
+__device__ void compute_cutoff(const DetParams& q, int n, unsigned int* scratch, unsigned int& k32_out,
+                               float& floor_out) {
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, nt = blockDim.x;
+  const unsigned int* sh = q.shist + size_t(n) * q.n_bins;
+  const int per = (q.n_bins + nt - 1) / nt;  // contiguous bins per thread, best scores first
+  unsigned int mine = 0;
+  for (int j = 0; j < per; ++j) {
+    const int b = tid * per + j;
+    if (b < q.n_bins) mine += sh[b];
+  }
+  unsigned int inc = mine;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const unsigned int t = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += t;
+  }
+  __syncthreads();
+  if (tid == 0) scratch[33] = unsigned(q.n_bins);
+  if (lane == 31) scratch[wid] = inc;
+  __syncthreads();
+  unsigned int before = inc - mine;
+  for (int w = 0; w < wid; ++w) before += scratch[w];
+  const unsigned int need = unsigned((q.sample_target + q.sample_stride - 1) / q.sample_stride);
+  if (before < need && before + mine >= need) {
+    unsigned int acc = before;
+    for (int j = 0; j < per; ++j) {
+      const int b = tid * per + j;
+      if (b >= q.n_bins) break;
+      acc += sh[b];
+      if (acc >= need) {
+        scratch[33] = unsigned(b + 1);  // emit bins [0, b]
+        break;
+      }
+    }
+  }
+  __syncthreads();
+  const int cb = int(scratch[33]);
+  if (cb >= q.n_bins) {
+    k32_out = 0xffffffffu;
+    floor_out = q.min_score;
+  } else {
+    k32_out = unsigned(cb) << (q.shift0 - 32);
+    floor_out = fmaxf(q.min_score, __uint_as_float(kOneBits - min(k32_out, kOneBits)));
+  }
+  __syncthreads();
+}
+
 // ------------------------------------------------------------------------------------------
 // detect_score_fast_kernel — odd C <= 128, softmax or sigmoid. Two threads per row (row_stream.cuh),
 // contiguous tile ranges per CTA. Pass 2 of the softmax also builds, per thread, a bit mask of the
@@ -255,7 +306,7 @@ __global__ void __launch_bounds__(kStreamThreads, 2) detect_score_fast_kernel(co
   extern __shared__ __align__(128) unsigned char smem_raw[];
   float* stages = reinterpret_cast<float*>(smem_raw);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + size_t(q.n_stages) * q.stage_floats * 4);
-  __shared__ unsigned int s_hist[kMaxBins];
+  __shared__ unsigned int s_hist[kMaxBins + 40];  // + scratch of compute_cutoff
 
   const int tid = threadIdx.x, lane = tid & 31;
   const int C = q.C;
@@ -314,10 +365,7 @@ __global__ void __launch_bounds__(kStreamThreads, 2) detect_score_fast_kernel(co
     if (n != hist_n) {
       if (hist_n >= 0) flush_hist(hist_n);
       hist_n = n;
-      if (q.mode == 0 && !(q.debug_skip & 4)) {
-        cut_k32 = q.cutoff_k32[n];
-        cut_floor = cut_k32 == 0xffffffffu ? q.min_score : q.cutoff_floor[n];
-      }
+      if (q.mode == 0 && q.speculate) compute_cutoff(q, n, s_hist + kMaxBins, cut_k32, cut_floor);
     }
     const bool act = image_active(n);
     const bool valid = row < tc.rows && act;
@@ -429,65 +477,6 @@ __global__ void __launch_bounds__(kStreamThreads, 2) detect_score_fast_kernel(co
 }
 
 // ------------------------------------------------------------------------------------------
-// detect_cutoff_kernel: one CTA per image. From the histogram of the sampled tiles pick the score
-// bin above which about sample_target candidates are expected, publish it as the emission cutoff
-// of the main pass, and clear the sample histogram.
-// ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) detect_cutoff_kernel(const DetParams q) {
-  __shared__ unsigned int s_w[8];
-  __shared__ int s_bin;
-  const int n = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-  unsigned int* sh = q.shist + size_t(n) * q.n_bins;
-  if (tid == 0) s_bin = q.n_bins;
-  __syncthreads();
-  const int per = (q.n_bins + 255) / 256;  // contiguous bins per thread, ascending (best scores first)
-  unsigned int mine = 0;
-  for (int j = 0; j < per; ++j) {
-    const int b = tid * per + j;
-    if (b < q.n_bins) mine += sh[b];
-  }
-  unsigned int inc = mine;
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    const unsigned int t = __shfl_up_sync(0xffffffffu, inc, o);
-    if (lane >= o) inc += t;
-  }
-  if (lane == 31) s_w[wid] = inc;
-  __syncthreads();
-  unsigned int before = inc - mine;
-  for (int w = 0; w < wid; ++w) before += s_w[w];
-  const unsigned int need = unsigned((q.sample_target + q.sample_stride - 1) / q.sample_stride);
-  if (before < need && before + mine >= need) {
-    unsigned int acc = before;
-    for (int j = 0; j < per; ++j) {
-      const int b = tid * per + j;
-      if (b >= q.n_bins) break;
-      acc += sh[b];
-      if (acc >= need) {
-        s_bin = b + 1;  // emit bins [0, b]
-        break;
-      }
-    }
-  }
-  __syncthreads();
-  for (int j = 0; j < per; ++j) {
-    const int b = tid * per + j;
-    if (b < q.n_bins) sh[b] = 0u;
-  }
-  if (tid == 0) {
-    const int cb = s_bin;
-    if (cb >= q.n_bins) {
-      q.cutoff_k32[n] = 0xffffffffu;
-      q.cutoff_floor[n] = q.min_score;
-    } else {
-      const unsigned int k32 = unsigned(cb) << (q.shift0 - 32);
-      q.cutoff_k32[n] = k32;
-      q.cutoff_floor[n] = fmaxf(q.min_score, __uint_as_float(kOneBits - min(k32, kOneBits)));
-    }
-  }
-}
-
-// ------------------------------------------------------------------------------------------
 // detect_nms_kernel
 // ------------------------------------------------------------------------------------------
 SBOD_DEVINL int key_class(unsigned long long k) { return int((k >> kPriorBits) & ((1u << kClassBits) - 1u)); }
@@ -507,7 +496,7 @@ struct NmsSmem {
   uint16_t cidx[kChunk];   // chunk positions grouped by class (segments in key order)
   uint16_t cnew[kChunk];   // per class segment: positions kept in this round
   uint8_t cflag[kChunk];   // 1 = survives stage 1, 2 = survives stage 2 as well
-  unsigned int wscan[32];
+  unsigned int wscan[40];
   int misc[16];
 };
 
@@ -533,7 +522,15 @@ __global__ void __launch_bounds__(kNmsThreads) detect_nms_kernel(const DetParams
 
   const int n = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   if (q.mode == 2 && q.flags[n] == 0u) return;  // fallback pass: only the flagged images
-  const bool cutoff_active = q.mode == 0 && q.cutoff_k32[n] != 0xffffffffu && !(q.debug_skip & 4);
+  bool cutoff_active = false;
+  if (q.mode == 0 && q.speculate) {
+    unsigned int ck = 0xffffffffu;
+    float cf = 0.f;
+    compute_cutoff(q, n, S.wscan, ck, cf);  // same function of the same histogram as the score pass
+    cutoff_active = ck != 0xffffffffu;
+    unsigned int* sh = q.shist + size_t(n) * q.n_bins;
+    for (int b = tid; b < q.n_bins; b += kNmsThreads) sh[b] = 0u;  // clean for the next call
+  }
   const bool two_stage = q.second_thr >= 0.f;
   unsigned int* g_hist = q.hist + size_t(n) * q.n_bins;
   unsigned int* g_seen = q.class_seen + size_t(n) * q.C;
@@ -667,6 +664,7 @@ __global__ void __launch_bounds__(kNmsThreads) detect_nms_kernel(const DetParams
     }
     // ---- decode boxes, group by class -------------------------------------------------------
     for (int c = tid; c <= q.C; c += kNmsThreads) cls_off[c] = 0u;
+    if (tid == 0) S.misc[6] = 1;  // next class to process (dynamic assignment to warps)
     __syncthreads();
     if (tid < m) {
       const unsigned long long k = S.ckey[tid];
@@ -696,7 +694,11 @@ __global__ void __launch_bounds__(kNmsThreads) detect_nms_kernel(const DetParams
     // i.e. segment of class c is [cls_off[c], cls_off[c+1]).
 
     // ---- stage 1: per-class greedy suppression, one warp per class ---------------------------
-    for (int c = 1 + wid; c < q.C; c += kNmsThreads / 32) {
+    for (;;) {
+      int c = 0;
+      if (lane == 0) c = atomicAdd(&S.misc[6], 1);
+      c = __shfl_sync(0xffffffffu, c, 0);
+      if (c >= q.C) break;
       const unsigned int seg0 = cls_off[c], seg1 = cls_off[c + 1];
       if (seg1 == seg0) continue;
       // fill the segment with this class's chunk positions in key order
@@ -975,7 +977,8 @@ static int detect_run(const sbod_detect_desc* d, sbod_stream_t stream, int stage
   q.cutoff_floor = reinterpret_cast<float*>(w);      w += align_up(size_t(q.N) * 4, 256);
   q.cand = reinterpret_cast<unsigned long long*>(w);
   q.mode = 0;
-  q.sample_stride = 13;
+  q.speculate = 0;
+  q.sample_stride = 26;
   q.sample_target = 4 * (q.top_k + 1) + 1024;
   if (getenv("SBOD_TARGET")) q.sample_target = atoi(getenv("SBOD_TARGET"));
   // hist rows are n_bins wide inside the kMaxBins-strided allocation
@@ -1021,19 +1024,18 @@ static int detect_run(const sbod_detect_desc* d, sbod_stream_t stream, int stage
     if (fgrid > q.n_tiles) fgrid = q.n_tiles;
     // Speculation pays when the sampled histogram is cheap relative to the main pass.
     const bool speculate = q.tiles_per_image >= 2 * q.sample_stride && !(q.debug_skip & 4);
-    if (stage_mask & 1) {
-      if (speculate) {
+    q.speculate = speculate ? 1 : 0;
+    if ((stage_mask & 1) && speculate) {
+      {
         DetParams qs = q;
         qs.mode = 1;
         int sgrid = (q.n_tiles / q.sample_stride + 1);
         if (sgrid > fgrid) sgrid = fgrid;
         detect_score_fast_kernel<<<sgrid, kStreamThreads, fsmem, st>>>(qs);
         SBOD_LAUNCH_CHECK();
-        detect_cutoff_kernel<<<q.N, 256, 0, st>>>(q);
-        SBOD_LAUNCH_CHECK();
-      } else {
-        SBOD_CUDA_TRY(cudaMemsetAsync(q.cutoff_k32, 0xff, size_t(q.N) * 4, st));
       }
+    }
+    if (stage_mask & 4) {
       detect_score_fast_kernel<<<fgrid, kStreamThreads, fsmem, st>>>(q);
       SBOD_LAUNCH_CHECK();
     }
@@ -1054,8 +1056,7 @@ static int detect_run(const sbod_detect_desc* d, sbod_stream_t stream, int stage
       return SBOD_OK;
     }
     if (!(stage_mask & 2)) return SBOD_OK;
-  } else if (stage_mask & 1) {
-    SBOD_CUDA_TRY(cudaMemsetAsync(q.cutoff_k32, 0xff, size_t(q.N) * 4, st));  // no speculation here
+  } else if (stage_mask & 4) {
     detect_score_kernel<<<grid, kDRows, t.smem, st>>>(q);
     SBOD_LAUNCH_CHECK();
   }
@@ -1069,12 +1070,14 @@ static int detect_run(const sbod_detect_desc* d, sbod_stream_t stream, int stage
 }
 
 extern "C" int sbod_detect(const sbod_detect_desc* d, sbod_stream_t stream) {
-  return detect_run(d, stream, 3);
+  return detect_run(d, stream, 7);
 }
 
-// Profiling / bench hook: stage 0 = detect_score_kernel only, stage 1 = detect_nms_kernel only.
-// A stage-0 launch must be followed by a stage-1 launch before the next full sbod_detect.
+// Profiling / bench hook. stage 0 = sampling pass + main score pass, 1 = NMS kernel (+ fallback
+// passes), 2 = sampling pass only, 3 = main score pass only. Score passes must be followed by a
+// stage-1 launch before the next full sbod_detect (it consumes and cleans the workspace).
 extern "C" int sbod_detect_stage(const sbod_detect_desc* d, int stage, sbod_stream_t stream) {
-  if (stage != 0 && stage != 1) return SBOD_ERR_INVALID;
-  return detect_run(d, stream, stage == 0 ? 1 : 2);
+  static const int masks[4] = {1 | 4, 2, 1, 4};
+  if (stage < 0 || stage > 3) return SBOD_ERR_INVALID;
+  return detect_run(d, stream, masks[stage]);
 }
