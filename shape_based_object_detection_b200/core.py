@@ -143,15 +143,17 @@ class _FusedLossFn(torch.autograd.Function):
 
 
 def fused_loss(spec, priors_cxcy, priors_xy, predicted_locs, predicted_scores, boxes, labels,
-               anchors_xy=None, exclude=None, group=None, holder=None):
-    """Run the fused train path. Returns a 0-dim fp32 tensor with grad_fn."""
+               anchors_xy=None, exclude=None, group=None, holder=None, packed_gt=None):
+    """Run the fused train path. Returns a 0-dim fp32 tensor with grad_fn.
+    packed_gt: optional result of pack_ground_truth() (CSR ground truth already on the device, e.g.
+    packed by the data loader) — then `boxes` / `labels` are ignored and no host work is done."""
     L.need_cuda(predicted_locs, predicted_scores, priors_cxcy)
     dev = predicted_scores.device
     if predicted_locs.dim() != 3 or predicted_scores.dim() != 3:
         raise ValueError("predicted_locs / predicted_scores must be [N,P,4] / [N,P,C]")
     n_priors = priors_cxcy.size(0)
     assert n_priors == predicted_locs.size(1) == predicted_scores.size(1)  # SSD512.py:523
-    gt = pack_ground_truth(boxes, labels, dev)
+    gt = packed_gt if packed_gt is not None else pack_ground_truth(boxes, labels, dev)
     holder = holder if holder is not None else {}
     holder["group"] = group
 
