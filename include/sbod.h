@@ -206,6 +206,10 @@ typedef struct sbod_loss_desc {
   float* loss;      /* [4]    total, conf, loc, n_pos */
   void* workspace;
   size_t workspace_bytes;
+  /* optional [N,P,C]: if set, sbod_loss_forward also zero-fills this buffer (bulk TMA stores riding
+   * under the logits stream). Passing the same pointer as grad_scores to sbod_loss_backward then
+   * skips the zero-fill pass of the sparse backward. */
+  float* grad_scores_prefill;
 } sbod_loss_desc;
 
 SBOD_API size_t sbod_loss_workspace_bytes(const sbod_loss_desc* d);

@@ -47,6 +47,7 @@ class LossDesc(C.Structure):
         ("ov", C.c_void_p), ("obj", C.c_void_p), ("lse", C.c_void_p), ("ce", C.c_void_p),
         ("sel", C.c_void_p), ("partials", C.c_void_p), ("sums", C.c_void_p), ("loss", C.c_void_p),
         ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t),
+        ("grad_scores_prefill", C.c_void_p),
     ]
 
 

@@ -46,7 +46,8 @@ class LossSpec:
 class LossState:
     """Per-call device state of one fused loss evaluation (kept alive for backward / inspection)."""
 
-    def __init__(self, spec, priors_cxcy, priors_xy, locs, scores, gt, anchors_xy=None, exclude=None):
+    def __init__(self, spec, priors_cxcy, priors_xy, locs, scores, gt, anchors_xy=None, exclude=None,
+                 prefill_grad=False):
         self.spec = spec
         dev = scores.device
         N, P, Cn = scores.shape
@@ -85,6 +86,9 @@ class LossState:
         nbytes = L.lib().sbod_loss_workspace_bytes(C.byref(d))
         self.ws = L.Workspace.get(dev, ("loss", N, P, d.gmax), nbytes)
         d.workspace, d.workspace_bytes = self.ws.data_ptr(), nbytes
+        # the gradient wrt the logits is zero almost everywhere: let the forward stream zero-fill it
+        self.grad_scores = torch.empty_like(scores) if prefill_grad else None
+        d.grad_scores_prefill = self.grad_scores.data_ptr() if prefill_grad else None
         self.desc = d
 
     def forward(self):
@@ -96,7 +100,9 @@ class LossState:
     def backward(self, grad_loss, want_locs=True, want_scores=True):
         dev = self.scores.device
         g_locs = torch.empty_like(self.locs) if want_locs else None
-        g_scores = torch.empty_like(self.scores) if want_scores else None
+        g_scores = None
+        if want_scores:
+            g_scores = self.grad_scores if self.grad_scores is not None else torch.empty_like(self.scores)
         gl = grad_loss.to(device=dev, dtype=torch.float32).reshape(1).contiguous()
         L.check(L.lib().sbod_loss_backward(C.byref(self.desc), L.ptr(gl), L.ptr(g_locs), L.ptr(g_scores),
                                            L.stream_ptr()))
@@ -159,7 +165,10 @@ def fused_loss(spec, priors_cxcy, priors_xy, predicted_locs, predicted_scores, b
 
     def make_state(locs, scores):
         return LossState(spec, priors_cxcy, priors_xy, L.f32c(locs.detach()), L.f32c(scores.detach()), gt,
-                         anchors_xy=anchors_xy, exclude=exclude)
+                         anchors_xy=anchors_xy, exclude=exclude,
+                         prefill_grad=bool(scores.requires_grad and torch.is_grad_enabled()
+                                           and spec.cls_kind in (L.CLS_CE_MINE_NONPOS, L.CLS_CE_MINE_NEG,
+                                                                 L.CLS_CE_MINE_BATCH)))
 
     holder["make_state"] = make_state
     return _FusedLossFn.apply(predicted_locs, predicted_scores, holder)

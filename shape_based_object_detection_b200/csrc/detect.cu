@@ -359,8 +359,19 @@ __global__ void __launch_bounds__(kStreamThreads, 2) detect_score_fast_kernel(co
     __syncthreads();
   };
 
+  // tile coordinates advance incrementally (no integer division in the loop)
+  int cur_n = tile_of(0) / q.tiles_per_image;
+  int cur_t = tile_of(0) - cur_n * q.tiles_per_image;
   for (int it = 0; it < n_my; ++it) {
-    const StreamTile tc = stream_tile(tile_of(it), q.tiles_per_image, kTileRows, q.P);
+    StreamTile tc;
+    tc.n = cur_n;
+    tc.p0 = cur_t * kTileRows;
+    tc.rows = min(kTileRows, q.P - tc.p0);
+    cur_t += stride;
+    while (cur_t >= q.tiles_per_image) {
+      cur_t -= q.tiles_per_image;
+      ++cur_n;
+    }
     const int n = tc.n;
     if (n != hist_n) {
       if (hist_n >= 0) flush_hist(hist_n);
@@ -384,8 +395,8 @@ __global__ void __launch_bounds__(kStreamThreads, 2) detect_score_fast_kernel(co
     const int s = it % q.n_stages;
     float* stage = stages + size_t(s) * q.stage_floats;
     mbar_wait(&bars[s], (it / q.n_stages) & 1);
-    const size_t first = (size_t(n) * q.P + tc.p0) * size_t(C);
-    const float* rp = stage + (first & 3) + size_t(r) * C + h;
+    const uint32_t head = ((uint32_t(n) * uint32_t(q.P) + uint32_t(tc.p0)) * uint32_t(C)) & 3u;
+    const float* rp = stage + head + r * C + h;
 
     uint32_t m0 = 0u, m1 = 0u;
     float nmx2 = 0.f, inv = 1.f;

@@ -64,6 +64,7 @@ struct LossParams {
   int fast;        // odd C <= 128: warp-specialised two-threads-per-row kernels
   int ctas_per_sm;
   int debug_skip;  // SBOD_DEBUG_SKIP: bit0 = no stream role, bit1 = no match role (profiling only)
+  float* prefill;  // grad wrt logits to zero-fill while streaming (or null)
 };
 
 SBOD_DEVINL int64_t map_label(const LossParams& q, int64_t lab) {
@@ -295,6 +296,7 @@ __global__ void __launch_bounds__(kRows) match_lse_kernel(const LossParams q) {
 // The two roles share nothing but the SM: ALU-bound matching hides under the memory-bound stream.
 // ------------------------------------------------------------------------------------------
 constexpr int kMatchWarps = 8;
+constexpr int kZeroFloats = 1024;  // 4 KB zero tile for the gradient prefill
 constexpr int kMatchThreads = 32 * kMatchWarps;
 constexpr int kFastThreads = kStreamThreads + kMatchThreads;
 
@@ -303,6 +305,7 @@ __global__ void __launch_bounds__(kFastThreads, 2) match_lse_fast_kernel(const L
   float* stages = reinterpret_cast<float*>(smem_raw);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + size_t(q.n_stages) * q.stage_floats * 4);
   __shared__ unsigned long long s_wkey[kMatchWarps][kGtChunk];
+  __shared__ __align__(128) float s_zero[kZeroFloats];  // source of the gradient zero-fill stores
 
   const int tid = threadIdx.x, lane = tid & 31;
   int t0, t1;
@@ -313,6 +316,8 @@ __global__ void __launch_bounds__(kFastThreads, 2) match_lse_fast_kernel(const L
     for (int s = 0; s < q.n_stages; ++s) mbar_init(&bars[s], 1);
     fence_mbar_init();
   }
+  for (int i = tid; i < kZeroFloats; i += kFastThreads) s_zero[i] = 0.f;
+  fence_proxy_async();
   __syncthreads();
 
   if (tid < kStreamThreads) {
@@ -326,14 +331,24 @@ __global__ void __launch_bounds__(kFastThreads, 2) match_lse_fast_kernel(const L
     int row, h;
     stream_map(tid, row, h);
     const int nh = (C + 1 - h) >> 1;
+    int cur_n = t0 / q.tiles_per_image;  // tile coordinates advance incrementally (no division in the loop)
+    int cur_t = t0 - cur_n * q.tiles_per_image;
+    int s = 0;
+    uint32_t parity = 0;
     for (int it = 0; it < n_my; ++it) {
-      const StreamTile tc = stream_tile(t0 + it, q.tiles_per_image, kTileRows, q.P);
-      const int s = it % q.n_stages;
+      StreamTile tc;
+      tc.n = cur_n;
+      tc.p0 = cur_t * kTileRows;
+      tc.rows = min(kTileRows, q.P - tc.p0);
+      if (++cur_t == q.tiles_per_image) {
+        cur_t = 0;
+        ++cur_n;
+      }
       float* stage = stages + size_t(s) * q.stage_floats;
-      mbar_wait(&bars[s], (it / q.n_stages) & 1);
-      const size_t first = (size_t(tc.n) * q.P + tc.p0) * size_t(C);
+      mbar_wait(&bars[s], parity);
+      const uint32_t head = ((uint32_t(tc.n) * uint32_t(q.P) + uint32_t(tc.p0)) * uint32_t(C)) & 3u;
       const int r = min(row, tc.rows - 1);  // keep every lane in the shuffles
-      const float* rbase = stage + (first & 3) + size_t(r) * C;
+      const float* rbase = stage + head + r * C;
       const float mx = half_row_max(rbase + h, nh);
       const float sum = half_row_sumexp(rbase + h, nh, -mx * kLog2e);
       if (h == 0 && row < tc.rows) {
@@ -346,7 +361,25 @@ __global__ void __launch_bounds__(kFastThreads, 2) match_lse_fast_kernel(const L
       if (tid == 0 && it + q.n_stages < n_my)
         stream_issue(q.scores, q.N, q.P, C,
                      stream_tile(t0 + it + q.n_stages, q.tiles_per_image, kTileRows, q.P), stage, &bars[s]);
+      if (tid == 32 && q.prefill) {
+        // zero-fill this tile of the gradient buffer: 16-byte aligned interior by bulk stores from
+        // the zero tile (fire and forget: the source never changes), ragged ends by plain stores
+        const size_t e0 = (size_t(tc.n) * q.P + tc.p0) * size_t(C), e1 = e0 + size_t(tc.rows) * C;
+        const size_t a0 = (e0 + 3) & ~size_t(3), a1 = e1 & ~size_t(3);
+        for (size_t e = e0; e < (a0 < e1 ? a0 : e1); ++e) q.prefill[e] = 0.f;
+        for (size_t e = (a1 > a0 ? a1 : (a0 < e1 ? a0 : e1)); e < e1; ++e) q.prefill[e] = 0.f;
+        for (size_t a = a0; a < a1; a += kZeroFloats) {
+          const size_t len = (a1 - a) < size_t(kZeroFloats) ? (a1 - a) : size_t(kZeroFloats);
+          tma_store_1d(q.prefill + a, s_zero, uint32_t(len * 4));
+        }
+        tma_store_commit();
+      }
+      if (++s == q.n_stages) {
+        s = 0;
+        parity ^= 1u;
+      }
     }
+    if (tid == 32 && q.prefill) tma_store_wait_all<0>();
     return;
   }
 
@@ -1416,6 +1449,8 @@ static int fill_params(const sbod_loss_desc* d, LossParams& q, bool need_scores)
   q.falpha = d->focal_alpha; q.fgamma = d->focal_gamma;
   q.ov = d->ov; q.obj = d->obj; q.lse = d->lse; q.ce = d->ce; q.sel = d->sel;
   q.partials = d->partials; q.sums = d->sums; q.loss = d->loss;
+  q.prefill = d->grad_scores_prefill;
+  if (q.prefill && (reinterpret_cast<uintptr_t>(q.prefill) & 15)) return SBOD_ERR_ALIGNMENT;
   // workspace carve-up
   const size_t need = sbod_loss_workspace_bytes(d);
   if (!d->workspace || d->workspace_bytes < need) return SBOD_ERR_WORKSPACE;
@@ -1599,7 +1634,8 @@ extern "C" int sbod_loss_backward(const sbod_loss_desc* d, const float* grad_los
   if (grid > q.n_tiles) grid = q.n_tiles;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (!bp.dense) {
-    if (grad_scores) {
+    const bool prefilled = q.fast && grad_scores && grad_scores == q.prefill;  // zeroed by the forward
+    if (grad_scores && !prefilled) {
       zero_fill_kernel<<<sm_count() * 4, 128, 0, st>>>(grad_scores, size_t(q.N) * q.P * size_t(q.C));
       SBOD_LAUNCH_CHECK();
     }
@@ -1742,6 +1778,7 @@ extern "C" int sbod_loss_forward_host(const sbod_loss_desc* h, int T, float* los
   SBOD_CUDA_TRY(cudaMemsetAsync(base + a.ws, 0, 256 + align_up(size_t(h->N) * (h->gmax > 0 ? h->gmax : 1) * 8, 256) +
                                                     align_up(size_t(h->N) * 4, 256), st));
   sbod_loss_desc d = *h;
+  d.grad_scores_prefill = nullptr;
   d.locs = reinterpret_cast<const float*>(base + a.locs);
   d.scores = reinterpret_cast<const float*>(base + a.scores);
   d.priors_cxcy = reinterpret_cast<const float*>(base + a.pcx);

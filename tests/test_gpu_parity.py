@@ -339,19 +339,94 @@ def test_detect_speculative_cutoff_fallback(dev):
     from shape_based_object_detection_b200 import priors as PR, synth
     from shape_based_object_detection_b200.models import utils as MU
     pri = PR.ssd300_priors()
-    _, scores = synth.make_eval_batch(pri, 3, 6, 99, bg_bias=3.0)
+    _, scores = synth.make_eval_batch(pri, 3, 7, 99, bg_bias=3.0)  # odd C: the fast (speculating) kernels
     locs = torch.tensor([0.2, 0.25, 0.6, 0.7]).repeat(3, pri.size(0), 1).contiguous()
     locs[2] += torch.rand((pri.size(0), 4), generator=torch.Generator().manual_seed(1)) * 0.3  # a normal image
     want = O.detect(locs.clone(), scores, 0.01, 0.45, 200, pri, box_type="corner")
     got = MU.detect(cu(locs.clone(), dev), cu(scores, dev), 0.01, 0.45, 200, cu(pri, dev),
-                    cfg(n_classes=6, box_type="corner"))
+                    cfg(n_classes=7, box_type="corner"))
     for i in range(3):
         assert torch.equal(got[1][i].cpu(), want[1][i]), i
         assert torch.allclose(got[2][i].cpu(), want[2][i], rtol=1e-5, atol=1e-8)
         assert torch.allclose(got[0][i].cpu(), want[0][i], rtol=1e-5, atol=1e-6)
-    assert got[1][0].numel() <= 5
+    assert got[1][0].numel() <= 6
     # the workspace is clean again: a second call gives the same answer
     again = MU.detect(cu(locs.clone(), dev), cu(scores, dev), 0.01, 0.45, 200, cu(pri, dev),
-                      cfg(n_classes=6, box_type="corner"))
+                      cfg(n_classes=7, box_type="corner"))
     for i in range(3):
         assert torch.equal(again[1][i], got[1][i]) and torch.equal(again[2][i], got[2][i])
+
+
+def test_detect_fast_kernels_all_variants(dev):
+    """Odd class count (C = 21, the fast two-threads-per-row kernels with the speculative cutoff):
+    per-class detect, top_k truncation, sigmoid scores, prior filter and the detect_tools second NMS,
+    each against the oracle."""
+    from oracle import box_pipeline as O
+    from shape_based_object_detection_b200 import priors as PR, synth
+    from shape_based_object_detection_b200.detect_scripts import detect_tools as DT
+    from shape_based_object_detection_b200.models import utils as MU
+    pri = PR.ssd300_priors()
+    locs, scores = synth.make_eval_batch(pri, 2, 21, 321, bg_bias=5.0)
+    keep = scores[:, :, 1] > -1.0
+    p_d = cu(pri, dev)
+
+    def check(got, want):
+        for i in range(2):
+            assert torch.equal(got[1][i].cpu(), want[1][i])
+            assert torch.allclose(got[2][i].cpu(), want[2][i], rtol=1e-5, atol=1e-8)
+            assert torch.allclose(got[0][i].cpu(), want[0][i], rtol=1e-5, atol=1e-6)
+
+    for top_k in (200, 17):
+        check(MU.detect(cu(locs, dev), cu(scores, dev), 0.01, 0.45, top_k, p_d, cfg(n_classes=21)),
+              O.detect(locs.clone(), scores, 0.01, 0.45, top_k, pri))
+    check(MU.detect(cu(locs, dev), cu(scores, dev), 0.9, 0.45, 200, p_d, cfg(n_classes=21, focal_type="sigmoid")),
+          O.detect(locs.clone(), scores, 0.9, 0.45, 200, pri, focal_type="sigmoid"))
+    check(MU.detect(cu(locs, dev), cu(scores, dev), 0.01, 0.45, 200, p_d, cfg(n_classes=21),
+                    prior_positives_idx=cu(keep, dev)),
+          O.detect(locs.clone(), scores, 0.01, 0.45, 200, pri, prior_keep=keep))
+    check(DT.detect(cu(locs, dev), cu(scores, dev), 0.01, 0.45, 200, p_d),
+          O.detect(locs.clone(), scores, 0.01, 0.45, 200, pri, second_nms=0.7))
+
+
+def test_forward_packed_and_host_entry(dev):
+    """forward_packed (GT packed once) equals forward; the HOST-buffer C entry point
+    sbod_loss_forward_host gives the same scalar."""
+    import ctypes as C
+    import shape_based_object_detection_b200 as S
+    from shape_based_object_detection_b200 import _lib as L
+    from shape_based_object_detection_b200 import priors as PR, synth
+    from shape_based_object_detection_b200.models import MultiBoxLoss512
+    pri = PR.ssd512_priors()
+    locs, scores, bx, lb = synth.make_train_batch(pri, 4, 21, 12, 55)
+    crit = MultiBoxLoss512(cu(pri, dev), cfg("", "", 21))
+    bxd, lbd = [cu(b, dev) for b in bx], [cu(l, dev) for l in lb]
+    l_d = cu(locs, dev).requires_grad_(True)
+    s_d = cu(scores, dev).requires_grad_(True)
+    a = crit(l_d, s_d, bxd, lbd)
+    a.backward()
+    ga, gb = l_d.grad.clone(), s_d.grad.clone()
+    l_d.grad = s_d.grad = None
+    packed = S.pack_ground_truth(bxd, lbd, dev)
+    b = crit.forward_packed(l_d, s_d, packed)
+    b.backward()
+    assert a.item() == b.item()
+    assert torch.equal(ga, l_d.grad) and torch.equal(gb, s_d.grad)
+    # host entry point
+    st = crit.last["state"]
+    gt_b, gt_l, gt_o, gmax = [t.cpu() if hasattr(t, "cpu") else t for t in packed]
+    h = L.LossDesc()
+    keep_alive = [locs.contiguous(), scores.contiguous(), pri.contiguous(), crit.priors_xy.cpu().contiguous(),
+                  gt_b.contiguous(), gt_l.contiguous(), gt_o.contiguous()]
+    for name, t in zip(("locs", "scores", "priors_cxcy", "priors_xy", "gt_boxes", "gt_labels", "gt_offsets"), keep_alive):
+        setattr(h, name, t.data_ptr())
+    for f in ("N", "P", "C", "gmax", "thr_pos", "thr_neg", "reg_kind", "cls_kind", "binarize_labels", "neg_pos_ratio",
+              "reg_weight", "smooth_l1_beta", "focal_alpha", "focal_gamma"):
+        setattr(h, f, getattr(st.desc, f))
+    T = int(gt_b.size(0))
+    nbytes = L.lib().sbod_loss_forward_host_arena_bytes(C.byref(h), T)
+    arena = torch.zeros(int(nbytes) + 256, dtype=torch.uint8, device=dev)
+    out = torch.zeros(4, dtype=torch.float32).pin_memory()
+    L.check(L.lib().sbod_loss_forward_host(C.byref(h), T, C.c_void_p(out.data_ptr()), L.ptr(arena),
+                                           C.c_size_t(nbytes), L.stream_ptr()))
+    torch.cuda.synchronize()
+    assert abs(out[0].item() - a.item()) <= 1e-6 * abs(a.item())

@@ -25,7 +25,7 @@ from shape_based_object_detection_b200.dataset.transforms import cxcy_to_xy  # n
 pxy = cxcy_to_xy(pri_d)
 gt = core.pack_ground_truth([b.to(dev) for b in bx], [l.to(dev) for l in lb], dev)
 spec = core.LossSpec(reg_kind=L.REG_SMOOTH_L1, cls_kind=L.CLS_CE_MINE_NONPOS)
-st = core.LossState(spec, pri_d, pxy, locs.to(dev), scores.to(dev), gt)
+st = core.LossState(spec, pri_d, pxy, locs.to(dev), scores.to(dev), gt, prefill_grad=bool(int(os.environ.get("KB_PREFILL", "0"))))
 lib = L.lib()
 sp = L.stream_ptr()
 
