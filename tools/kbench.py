@@ -24,7 +24,9 @@ pri_d = pri.to(dev)
 from shape_based_object_detection_b200.dataset.transforms import cxcy_to_xy  # noqa: E402
 pxy = cxcy_to_xy(pri_d)
 gt = core.pack_ground_truth([b.to(dev) for b in bx], [l.to(dev) for l in lb], dev)
-spec = core.LossSpec(reg_kind=L.REG_SMOOTH_L1, cls_kind=L.CLS_CE_MINE_NONPOS)
+REG = int(os.environ.get("KB_REG", L.REG_SMOOTH_L1))
+CLS = int(os.environ.get("KB_CLS", L.CLS_CE_MINE_NONPOS))
+spec = core.LossSpec(reg_kind=REG, cls_kind=CLS)
 st = core.LossState(spec, pri_d, pxy, locs.to(dev), scores.to(dev), gt, prefill_grad=bool(int(os.environ.get("KB_PREFILL", "0"))))
 lib = L.lib()
 sp = L.stream_ptr()
