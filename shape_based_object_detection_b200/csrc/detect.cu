@@ -29,6 +29,7 @@ constexpr int kDRows = 128;
 constexpr int kChunk = 1024;       // candidates per NMS round (== threads of detect_nms_kernel)
 constexpr int kNmsThreads = 1024;
 constexpr int kMaxBins = 2048;
+constexpr int kBigSeg = 64;        // class segments longer than this use the bitmask path
 constexpr int kClassBits = 12, kPriorBits = 20;
 constexpr uint32_t kOneBits = 0x3F800000u;
 
@@ -64,6 +65,7 @@ struct DetParams {
   unsigned int* cutoff_k32;     // [N] emit only keys with k32 < cutoff (0xffffffff = no cutoff)
   float* cutoff_floor;          // [N] score just below the cutoff (mask floor)
   unsigned int* flags;          // [N] 1 = the cutoff was too strict, redo this image in full
+  unsigned int* nms_mask;       // [N, kChunk, kChunk/32] suppression bits of large class segments
   int sample_stride, sample_target;
   int speculate;                // the sampling pass ran: cutoffs come from shist
   // tiling
@@ -508,6 +510,8 @@ struct NmsSmem {
   uint16_t cnew[kChunk];   // per class segment: positions kept in this round
   uint8_t cflag[kChunk];   // 1 = survives stage 1, 2 = survives stage 2 as well
   unsigned int wscan[40];
+  uint16_t big_seg0[kChunk / kBigSeg + 1];  // large class segments of the round (start, length)
+  uint16_t big_len[kChunk / kBigSeg + 1];
   int misc[16];
 };
 
@@ -675,7 +679,10 @@ __global__ void __launch_bounds__(kNmsThreads) detect_nms_kernel(const DetParams
     }
     // ---- decode boxes, group by class -------------------------------------------------------
     for (int c = tid; c <= q.C; c += kNmsThreads) cls_off[c] = 0u;
-    if (tid == 0) S.misc[6] = 1;  // next class to process (dynamic assignment to warps)
+    if (tid == 0) {
+      S.misc[6] = 1;  // next class to process (dynamic assignment to warps)
+      S.misc[8] = 0;  // number of large class segments of this round
+    }
     __syncthreads();
     if (tid < m) {
       const unsigned long long k = S.ckey[tid];
@@ -704,7 +711,23 @@ __global__ void __launch_bounds__(kNmsThreads) detect_nms_kernel(const DetParams
     // cls_off[c] now holds the number of chunk entries with class < c ... (entry c+1 counted class c),
     // i.e. segment of class c is [cls_off[c], cls_off[c+1]).
 
-    // ---- stage 1: per-class greedy suppression, one warp per class ---------------------------
+    // ---- stage 1a: every candidate against the boxes kept in EARLIER rounds, one thread each ----
+    // (parallel over the whole CTA whatever the number of classes; flag 3 = already suppressed)
+    if (tid < m && kept_n > 0) {
+      const int c = key_class(S.ckey[tid]);
+      const float4 be = S.cbox[tid];
+      bool sup = false;
+      for (int i = 0; i < kept_n && !sup; ++i)
+        if (key_class(kkey[i]) == c && overlaps(kbox[i], be, q.max_overlap)) sup = true;
+      if (sup) S.cflag[tid] = 3;
+    }
+    __syncthreads();
+    // ---- stage 1b: greedy suppression inside the chunk -------------------------------------------
+    // Small class segments (<= kBigSeg candidates): one warp per class walks its segment and tests
+    // each candidate against the boxes it kept so far (warp ballot).
+    // Large segments (few classes, dense scenes): the pairwise suppression bits of the segment are
+    // built by ALL warps (one warp per (row, 32-column word), upper triangle only) and one warp then
+    // resolves the greedy order by scanning the bit rows — the classic bitmask NMS, per class.
     for (;;) {
       int c = 0;
       if (lane == 0) c = atomicAdd(&S.misc[6], 1);
@@ -722,15 +745,27 @@ __global__ void __launch_bounds__(kNmsThreads) detect_nms_kernel(const DetParams
         w += __popc(bal);
       }
       __syncwarp();
-      unsigned int seen = g_seen[c];  // candidates of this class consumed by earlier rounds
+      const unsigned int seen = g_seen[c];  // candidates of this class consumed by earlier rounds
+      if (lane == 0) g_seen[c] = seen + (seg1 - seg0);
+      unsigned int lim = seg1;               // pre-NMS per-class cap: later candidates are dropped
+      if (q.pre_nms_topk > 0) {
+        const unsigned int room = seen >= unsigned(q.pre_nms_topk) ? 0u : unsigned(q.pre_nms_topk) - seen;
+        lim = min(seg1, seg0 + room);
+      }
+      if (lim - seg0 > unsigned(kBigSeg)) {  // leave it to the bitmask path below
+        if (lane == 0) {
+          const int slot = atomicAdd(&S.misc[8], 1);
+          S.big_seg0[slot] = uint16_t(seg0);
+          S.big_len[slot] = uint16_t(lim - seg0);
+        }
+        continue;
+      }
       unsigned int nnew = 0;
-      for (unsigned int r = seg0; r < seg1; ++r) {
+      for (unsigned int r = seg0; r < lim; ++r) {
         const int e = S.cidx[r];
-        if (q.pre_nms_topk > 0 && seen + (r - seg0) >= unsigned(q.pre_nms_topk)) break;
+        if (S.cflag[e] == 3) continue;  // suppressed by a box of an earlier round (stage 1a)
         const float4 be = S.cbox[e];
         bool sup = false;
-        for (int i = lane; i < kept_n && !sup; i += 32)
-          if (key_class(kkey[i]) == c && overlaps(kbox[i], be, q.max_overlap)) sup = true;
         for (unsigned int i = lane; i < nnew && !sup; i += 32)
           if (overlaps(S.cbox[S.cnew[seg0 + i]], be, q.max_overlap)) sup = true;
         if (!__any_sync(0xffffffffu, sup)) {
@@ -742,9 +777,59 @@ __global__ void __launch_bounds__(kNmsThreads) detect_nms_kernel(const DetParams
           __syncwarp();
         }
       }
-      if (lane == 0) g_seen[c] = seen + (seg1 - seg0);
     }
     __syncthreads();
+    const int n_big = S.misc[8];
+    if (n_big > 0) {
+      unsigned int* gmask = q.nms_mask + size_t(n) * (kChunk * (kChunk / 32));  // row r: words [r*32, r*32+32)
+      // (1) suppression bits, upper triangle: task = (segment, row, word)
+      for (int b = 0; b < n_big; ++b) {
+        const int seg0 = S.big_seg0[b], L = S.big_len[b];
+        const int W = (L + 31) >> 5;
+        for (int task = wid; task < L * W; task += kNmsThreads / 32) {
+          const int row = task / W, word = task - row * W;
+          if (word < (row >> 5)) continue;  // below the diagonal
+          const int col = word * 32 + lane;
+          const int er = S.cidx[seg0 + row];
+          bool bit = false;
+          if (col > row && col < L && S.cflag[er] != 3) {
+            const int ec = S.cidx[seg0 + col];
+            bit = S.cflag[ec] != 3 && overlaps(S.cbox[er], S.cbox[ec], q.max_overlap);
+          }
+          const unsigned bal = __ballot_sync(0xffffffffu, bit);
+          if (lane == 0) gmask[size_t(seg0 + row) * 32 + word] = bal;
+        }
+      }
+      __threadfence_block();
+      __syncthreads();
+      // (2) greedy order: one warp per big segment; lane w owns word w of the "removed" set
+      for (int b = wid; b < n_big; b += kNmsThreads / 32) {
+        const int seg0 = S.big_seg0[b], L = S.big_len[b];
+        const int W = (L + 31) >> 5;
+        unsigned int removed = 0u;
+        for (int r0 = 0; r0 < L; r0 += 8) {  // eight bit rows in flight
+          unsigned int rows[8];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            const int r = r0 + u;
+            rows[u] = (r < L && lane < W && lane >= (r >> 5)) ? gmask[size_t(seg0 + r) * 32 + lane] : 0u;
+          }
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            const int r = r0 + u;
+            if (r >= L) break;
+            const int e = S.cidx[seg0 + r];
+            const unsigned int remw = __shfl_sync(0xffffffffu, removed, r >> 5);
+            const bool dead = ((remw >> (r & 31)) & 1u) || S.cflag[e] == 3;
+            if (!dead) {
+              if (lane == 0) S.cflag[e] = 1;
+              removed |= rows[u];
+            }
+          }
+        }
+      }
+      __syncthreads();
+    }
 
     // ---- stage 2 (detect_tools): class-agnostic NMS over the stage-1 survivors, key order ----
     if (two_stage) {
@@ -773,7 +858,7 @@ __global__ void __launch_bounds__(kNmsThreads) detect_nms_kernel(const DetParams
     }
 
     // ---- append the survivors to the kept list, in key order ---------------------------------
-    const bool keep_me = tid < m && S.cflag[tid] != 0;
+    const bool keep_me = tid < m && (S.cflag[tid] == 1 || S.cflag[tid] == 2);
     const unsigned bal = __ballot_sync(0xffffffffu, keep_me);
     if (lane == 0) S.wscan[wid] = __popc(bal);
     __syncthreads();
@@ -933,6 +1018,7 @@ extern "C" size_t sbod_detect_workspace_bytes(const sbod_detect_desc* d) {
   b += align_up(size_t(d->N) * kMaxBins * 4, 256);            // shist
   b += align_up(size_t(d->N) * 4, 256);                       // flags
   b += align_up(size_t(d->N) * 4, 256) * 2;                   // cutoff_k32, cutoff_floor
+  b += align_up(size_t(d->N) * kChunk * (kChunk / 32) * 4, 256);  // nms_mask
   b += align_up(size_t(d->N) * size_t(cand_capacity(d)) * 8, 256);
   return b;
 }
@@ -986,6 +1072,7 @@ static int detect_run(const sbod_detect_desc* d, sbod_stream_t stream, int stage
   q.flags = reinterpret_cast<unsigned int*>(w);      w += align_up(size_t(q.N) * 4, 256);
   q.cutoff_k32 = reinterpret_cast<unsigned int*>(w); w += align_up(size_t(q.N) * 4, 256);
   q.cutoff_floor = reinterpret_cast<float*>(w);      w += align_up(size_t(q.N) * 4, 256);
+  q.nms_mask = reinterpret_cast<unsigned int*>(w);   w += align_up(size_t(q.N) * kChunk * (kChunk / 32) * 4, 256);
   q.cand = reinterpret_cast<unsigned long long*>(w);
   q.mode = 0;
   q.speculate = 0;
@@ -1016,7 +1103,7 @@ static int detect_run(const sbod_detect_desc* d, sbod_stream_t stream, int stage
   if (ctas_per_sm > 8) ctas_per_sm = 8;
   int grid = sm_count() * ctas_per_sm;
   if (grid > q.n_tiles) grid = q.n_tiles;
-  const bool fast = (q.C & 1) && q.C <= 128;
+  const bool fast = q.C >= 2 && q.C <= 128;  // odd C is bank-conflict free, even C only slower in smem
   if (fast) {
     q.rows_per_tile = kTileRows;
     q.stage_floats = uint32_t(align_up(size_t(kTileRows) * q.C + 8, 32));

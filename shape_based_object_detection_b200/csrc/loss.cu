@@ -1466,7 +1466,8 @@ static int fill_params(const sbod_loss_desc* d, LossParams& q, bool need_scores)
   w += align_up(size_t(q.N) * q.P * 4, 256);
   q.blockpart = reinterpret_cast<double*>(w);
   Tiling t = choose_tiling(need_scores ? d->C : 1, kMaxStages);
-  q.fast = (need_scores && (d->C & 1) && d->C <= 128) ? 1 : 0;
+  // the two-threads-per-row layout is bank-conflict free only for odd C; even C is merely slower in smem
+  q.fast = (need_scores && d->C >= 2 && d->C <= 128) ? 1 : 0;
   q.ctas_per_sm = 2;
   if (q.fast) {  // 128-row tiles; two CTAs per SM whenever two stages fit in ~90 KB
     t.rows = kTileRows;
