@@ -237,6 +237,7 @@ SBOD_API int sbod_loss_targets(const sbod_loss_desc* d, int64_t* cls_out, int64_
  * ---------------------------------------------------------------------------------------- */
 #define SBOD_ACT_SOFTMAX 0
 #define SBOD_ACT_SIGMOID 1
+#define SBOD_ACT_NONE 2    /* scores are probabilities already (FCOS.postprocess output) */
 #define SBOD_BOX_OFFSET 0 /* gcxgcy wrt priors */
 #define SBOD_BOX_CENTER 1 /* cxcy */
 #define SBOD_BOX_CORNER 2 /* xyxy (clamped in place in the reference, models/utils.py:224) */
@@ -269,6 +270,44 @@ SBOD_API size_t sbod_detect_workspace_zero_bytes(const sbod_detect_desc* d);
 SBOD_API int sbod_detect(const sbod_detect_desc* d, sbod_stream_t stream);
 /* Profiling / bench hook: stage 0 = score/candidate kernel only, 1 = NMS kernel only. */
 SBOD_API int sbod_detect_stage(const sbod_detect_desc* d, int stage, sbod_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Anchor-free (FCOS) targets + loss + post-processing. The reference's FCOSLoss / FCOS.postprocess
+ * (models/FCOSDet.py:253-270, 311-544) do not run (SURVEY.md §8 a-F); these entry points implement
+ * what that file specifies (constants :333-335, centre sampling / min-area assignment :343-474,
+ * centerness target :479-486, loss composition :527-544) with the canonical FCOS meaning where a
+ * line cannot execute. PARITY UNPINNED with respect to the reference (pinned to oracle/ only).
+ *   loss = SigmoidFocal(scores, labels)/(n_pos + N) + reg_weight * sum((1-DIoU)*ctr)/sum(ctr)
+ *          + BCEWithLogits(centerness[pos], ctr)
+ * locations [P,2] cell centres; loc_aux [P,3] = (stride*radius, size-of-interest lo, hi) per location.
+ * ---------------------------------------------------------------------------------------- */
+typedef struct sbod_fcos_desc {
+  const float* locs;        /* [N,P,4] predicted l,t,r,b distances (normalised) */
+  const float* scores;      /* [N,P,C] logits; column 0 is unused (Loss.py:51-58) */
+  const float* centerness;  /* [N,P] logits */
+  const float* locations;   /* [P,2] */
+  const float* loc_aux;     /* [P,3] */
+  const float* gt_boxes;    /* [T,4] xyxy */
+  const int64_t* gt_labels; /* [T] */
+  const int32_t* gt_offsets;/* [N+1] */
+  int32_t N, P, C;
+  int32_t center_sample;
+  float reg_weight, focal_alpha, focal_gamma;
+  int32_t* lab;   /* [N,P] label target, 0 = background (written by forward) */
+  float* tgt;     /* [N,P,4] l,t,r,b target of the assigned object */
+  double* sums;   /* [5] focal, sum((1-diou)*w), sum(w), bce, n_pos */
+  float* loss;    /* [4] total, conf, loc, center */
+  void* workspace;
+  size_t workspace_bytes;
+} sbod_fcos_desc;
+SBOD_API size_t sbod_fcos_workspace_bytes(const sbod_fcos_desc* d);
+SBOD_API int sbod_fcos_forward(const sbod_fcos_desc* d, sbod_stream_t stream);
+SBOD_API int sbod_fcos_backward(const sbod_fcos_desc* d, const float* grad_loss, float* grad_locs,
+                       float* grad_scores, float* grad_center, sbod_stream_t stream);
+/* FCOS.postprocess: out_scores = sigmoid(cls) * sigmoid(center)[..., None]; out_locs = xyxy boxes */
+SBOD_API int sbod_fcos_postprocess(const float* box_pred, const float* cls_pred, const float* center_pred,
+                          const float* locations, int N, int P, int C, float* out_locs,
+                          float* out_scores, sbod_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * End-to-end helpers with HOST buffers (pinned or pageable): copy the inputs to the device,

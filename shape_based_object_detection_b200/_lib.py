@@ -19,7 +19,7 @@ CODEC_TRANSFORMS, CODEC_IOU_UTILS = 0, 1
 PAIR_IOU, PAIR_GIOU, PAIR_DIOU, PAIR_CIOU = 0, 1, 2, 3
 REG_L1_ELEM_MEAN, REG_SMOOTH_L1, REG_IOU, REG_GIOU, REG_DIOU, REG_CIOU = 0, 1, 2, 3, 4, 5
 CLS_CE_MINE_NONPOS, CLS_CE_MINE_NEG, CLS_CE_MINE_BATCH, CLS_FOCAL_SUM, CLS_FOCAL_NORM = 0, 1, 2, 3, 4
-ACT_SOFTMAX, ACT_SIGMOID = 0, 1
+ACT_SOFTMAX, ACT_SIGMOID, ACT_NONE = 0, 1, 2
 BOX_OFFSET, BOX_CENTER, BOX_CORNER = 0, 1, 2
 
 EXPORTS = [
@@ -31,6 +31,7 @@ EXPORTS = [
     "sbod_loss_forward", "sbod_loss_forward_stage", "sbod_detect_stage", "sbod_loss_finalize", "sbod_loss_backward", "sbod_loss_targets",
     "sbod_detect_workspace_bytes", "sbod_detect_workspace_zero_bytes", "sbod_detect",
     "sbod_loss_forward_host_arena_bytes", "sbod_loss_forward_host",
+    "sbod_fcos_workspace_bytes", "sbod_fcos_forward", "sbod_fcos_backward", "sbod_fcos_postprocess",
 ]
 
 
@@ -61,6 +62,17 @@ class DetectDesc(C.Structure):
         ("second_nms_thr", C.c_float), ("pre_nms_topk", C.c_int32),
         ("out_boxes", C.c_void_p), ("out_labels", C.c_void_p), ("out_scores", C.c_void_p),
         ("out_prior", C.c_void_p), ("out_counts", C.c_void_p), ("out_cap", C.c_int32),
+        ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t),
+    ]
+
+
+class FcosDesc(C.Structure):
+    _fields_ = [
+        ("locs", C.c_void_p), ("scores", C.c_void_p), ("centerness", C.c_void_p), ("locations", C.c_void_p),
+        ("loc_aux", C.c_void_p), ("gt_boxes", C.c_void_p), ("gt_labels", C.c_void_p), ("gt_offsets", C.c_void_p),
+        ("N", C.c_int32), ("P", C.c_int32), ("C", C.c_int32), ("center_sample", C.c_int32),
+        ("reg_weight", C.c_float), ("focal_alpha", C.c_float), ("focal_gamma", C.c_float),
+        ("lab", C.c_void_p), ("tgt", C.c_void_p), ("sums", C.c_void_p), ("loss", C.c_void_p),
         ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t),
     ]
 
@@ -102,6 +114,9 @@ def _declare(lib):
         "sbod_loss_targets": [C.POINTER(LossDesc), vp, vp, vp],
         "sbod_detect": [C.POINTER(DetectDesc), vp],
         "sbod_loss_forward_host": [C.POINTER(LossDesc), i32, vp, vp, sz, vp],
+        "sbod_fcos_forward": [C.POINTER(FcosDesc), vp],
+        "sbod_fcos_backward": [C.POINTER(FcosDesc), vp, vp, vp, vp, vp],
+        "sbod_fcos_postprocess": [vp, vp, vp, vp, i32, i32, i32, vp, vp, vp],
     }
     for name, args in sigs.items():
         fn = getattr(lib, name)
@@ -115,6 +130,7 @@ def _declare(lib):
         "sbod_detect_workspace_bytes": [C.POINTER(DetectDesc)],
         "sbod_detect_workspace_zero_bytes": [C.POINTER(DetectDesc)],
         "sbod_loss_forward_host_arena_bytes": [C.POINTER(LossDesc), i32],
+        "sbod_fcos_workspace_bytes": [C.POINTER(FcosDesc)],
     }.items():
         fn = getattr(lib, name)
         fn.argtypes = args

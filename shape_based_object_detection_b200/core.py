@@ -233,7 +233,7 @@ def make_detect_desc(predicted_locs, predicted_scores, min_score, max_overlap, t
     d.priors_cxcy = pri.data_ptr() if pri is not None else None
     d.prior_keep = keep.data_ptr() if keep is not None else None
     d.N, d.P, d.C = N, P, Cn
-    d.act_kind = L.ACT_SIGMOID if act == "sigmoid" else L.ACT_SOFTMAX
+    d.act_kind = {"sigmoid": L.ACT_SIGMOID, "none": L.ACT_NONE}.get(act, L.ACT_SOFTMAX)
     d.box_kind, d.clamp_inplace = box_kind, 1 if clamp_inplace else 0
     d.min_score, d.max_overlap, d.top_k = float(min_score), float(max_overlap), int(top_k)
     d.second_nms_thr, d.pre_nms_topk = float(second_nms_thr), int(pre_nms_topk)

@@ -198,7 +198,7 @@ __global__ void __launch_bounds__(kDRows) detect_score_kernel(const DetParams q)
       } else {
         for (int kk = 0; kk < C; ++kk) {
           int k = kk + rot; if (k >= C) k -= C;
-          const float pr = __frcp_rn(1.f + __expf(-row[k]));
+          const float pr = q.act_kind == SBOD_ACT_NONE ? row[k] : __frcp_rn(1.f + __expf(-row[k]));
           row[k] = pr;
           cnt += (k > 0 && pr > q.min_score) ? 1u : 0u;
         }
@@ -410,7 +410,7 @@ __global__ void __launch_bounds__(kStreamThreads, 2) detect_score_fast_kernel(co
     } else {
       // sigmoid(x) > t  <=>  x > logit(t); keep a small margin, the exact test follows
       const float t = fminf(fmaxf(cut_floor, 1e-30f), 1.f - 1e-7f);
-      const float lim = logf(t / (1.f - t)) - 1e-3f;
+      const float lim = q.act_kind == SBOD_ACT_NONE ? cut_floor * (1.f - 1e-6f) : logf(t / (1.f - t)) - 1e-3f;
       for (int j = 0; j < nh; ++j)
         if (rp[2 * j] > lim) {
           if (j < 32) m0 |= 1u << j;
@@ -429,7 +429,7 @@ __global__ void __launch_bounds__(kStreamThreads, 2) detect_score_fast_kernel(co
         mm &= mm - 1;
         const float x = rp[2 * j];
         const float pr = q.act_kind == SBOD_ACT_SOFTMAX ? ex2_approx(fmaf(x, kLog2e, nmx2)) * inv
-                                                        : __frcp_rn(1.f + __expf(-x));
+                         : (q.act_kind == SBOD_ACT_NONE ? x : __frcp_rn(1.f + __expf(-x)));
         if (pr > q.min_score && (kOneBits - min(__float_as_uint(pr), kOneBits)) < cut_k32) ++cnt; else m0 &= ~(1u << j);
       }
       mm = m1;
@@ -438,7 +438,7 @@ __global__ void __launch_bounds__(kStreamThreads, 2) detect_score_fast_kernel(co
         mm &= mm - 1;
         const float x = rp[2 * (j + 32)];
         const float pr = q.act_kind == SBOD_ACT_SOFTMAX ? ex2_approx(fmaf(x, kLog2e, nmx2)) * inv
-                                                        : __frcp_rn(1.f + __expf(-x));
+                         : (q.act_kind == SBOD_ACT_NONE ? x : __frcp_rn(1.f + __expf(-x)));
         if (pr > q.min_score && (kOneBits - min(__float_as_uint(pr), kOneBits)) < cut_k32) ++cnt; else m1 &= ~(1u << j);
       }
     }
@@ -469,7 +469,7 @@ __global__ void __launch_bounds__(kStreamThreads, 2) detect_score_fast_kernel(co
           const int k = 2 * j + h;
           const float x = rp[2 * j];
           const float pr = q.act_kind == SBOD_ACT_SOFTMAX ? ex2_approx(fmaf(x, kLog2e, nmx2)) * inv
-                                                          : __frcp_rn(1.f + __expf(-x));
+                           : (q.act_kind == SBOD_ACT_NONE ? x : __frcp_rn(1.f + __expf(-x)));
           const uint32_t bits = __float_as_uint(pr);
           const uint32_t k32 = bits > kOneBits ? 0u : kOneBits - bits;
           const unsigned long long key = (static_cast<unsigned long long>(k32) << 32) |
@@ -1038,7 +1038,7 @@ static int detect_run(const sbod_detect_desc* d, sbod_stream_t stream, int stage
   if (d->N <= 0 || d->P <= 0 || d->C <= 1 || d->top_k <= 0) return SBOD_ERR_INVALID;
   if (d->box_kind == SBOD_BOX_OFFSET && !d->priors_cxcy) return SBOD_ERR_INVALID;
   if (d->box_kind < 0 || d->box_kind > SBOD_BOX_CORNER) return SBOD_ERR_INVALID;
-  if (d->act_kind != SBOD_ACT_SOFTMAX && d->act_kind != SBOD_ACT_SIGMOID) return SBOD_ERR_INVALID;
+  if (d->act_kind < SBOD_ACT_SOFTMAX || d->act_kind > SBOD_ACT_NONE) return SBOD_ERR_INVALID;
   if (d->P > (1 << kPriorBits) || d->C > (1 << kClassBits)) return SBOD_ERR_UNSUPPORTED;
   if (d->top_k > 4096) return SBOD_ERR_UNSUPPORTED;
   if (d->out_cap < (d->top_k > 1 ? d->top_k : 1)) return SBOD_ERR_INVALID;

@@ -430,3 +430,56 @@ def test_forward_packed_and_host_entry(dev):
                                            C.c_size_t(nbytes), L.stream_ptr()))
     torch.cuda.synchronize()
     assert abs(out[0].item() - a.item()) <= 1e-6 * abs(a.item())
+
+
+def test_fcos_loss_and_postprocess(dev):
+    """FCOS (parity unpinned w.r.t. the reference, pinned to the oracle's corrected restatement):
+    label / box targets bit-exact, loss 1e-5, gradients 1e-4, post-process + detect vs the oracle."""
+    from oracle import box_pipeline as O
+    from shape_based_object_detection_b200 import synth
+    from shape_based_object_detection_b200.core import detect_batched, unpad_detections
+    from shape_based_object_detection_b200.models import FCOSLoss, compute_location, fcos_postprocess
+    locations = O.fcos_locations()
+    mine = compute_location()
+    assert all(torch.equal(a, b) for a, b in zip(locations, mine))
+    P = sum(l.size(0) for l in locations)
+    gen = torch.Generator().manual_seed(404)
+    N, Cn = 3, 9
+    bx, lb = synth.make_gt(N, 12, Cn, gen)
+    bx[1] = torch.cat([bx[1], torch.tensor([[0.1, 0.1, 0.9, 0.9], [0.45, 0.45, 0.47, 0.47]])])  # large + tiny
+    lb[1] = torch.cat([lb[1], torch.tensor([3, 5])])
+    locs = torch.rand((N, P, 4), generator=gen) * 0.3 + 0.01
+    scores = torch.randn((N, P, Cn), generator=gen)
+    ctr = torch.randn((N, P), generator=gen)
+    for cs in (True, False):
+        l_c, s_c, c_c = [t.clone().requires_grad_(True) for t in (locs, scores, ctr)]
+        want, parts = O.fcos_loss(locations, l_c, s_c, c_c, bx, lb, alpha=1.5, center_sample=cs, want_parts=True)
+        want.backward()
+        crit = FCOSLoss([cu(l, dev) for l in locations], cfg(n_classes=Cn) | {"reg_weights": 1.5},
+                        center_sample=cs)
+        l_d, s_d, c_d = [cu(t, dev).requires_grad_(True) for t in (locs, scores, ctr)]
+        loss = crit(l_d, s_d, c_d, [cu(b, dev) for b in bx], [cu(l, dev) for l in lb])
+        loss.backward()
+        assert torch.equal(crit.last["labels"].cpu().long(), parts["labels"])
+        posm = parts["labels"] > 0
+        assert int(posm.sum()) > 20
+        assert torch.equal(crit.last["targets"].cpu()[posm], parts["targets"][posm])
+        assert abs(loss.item() - want.item()) <= RTOL_LOSS * abs(want.item()), (loss.item(), want.item())
+        assert torch.allclose(l_d.grad.cpu(), l_c.grad, rtol=RTOL_GRAD, atol=1e-6)
+        assert torch.allclose(s_d.grad.cpu(), s_c.grad, rtol=RTOL_GRAD, atol=1e-7)
+        assert torch.allclose(c_d.grad.cpu(), c_c.grad, rtol=RTOL_GRAD, atol=1e-7)
+    # eval side
+    escores = scores * 2.0 - 2.0
+    want_l, want_s = O.fcos_postprocess(locs, escores, ctr, locations)
+    got_l, got_s = fcos_postprocess(cu(locs, dev), cu(escores, dev), cu(ctr, dev), [cu(l, dev) for l in locations])
+    assert torch.allclose(got_l.cpu(), want_l, rtol=1e-6, atol=1e-7)
+    assert torch.allclose(got_s.cpu(), want_s, rtol=1e-5, atol=1e-8)
+    # detection on the oracle's probabilities (identical inputs on both sides), activation 'none'
+    ref = O.detect(want_l.clone(), want_s, 0.05, 0.45, 100, None, box_type="corner", focal_type="none_is_identity")
+    out = detect_batched(cu(want_l, dev).contiguous(), cu(want_s, dev), 0.05, 0.45, 100, None, act="none",
+                         box_type="corner", clamp_inplace=True)
+    got = unpad_detections(out[0], out[1], out[2], out[4])
+    for i in range(N):
+        assert torch.equal(got[1][i].cpu(), ref[1][i])
+        assert torch.equal(got[2][i].cpu(), ref[2][i])
+        assert torch.allclose(got[0][i].cpu(), ref[0][i], rtol=1e-6, atol=1e-7)
