@@ -11,7 +11,7 @@ def install(reference_root=None):
     from . import metrics as m
     from .dataset import transforms as t
     from .detect_scripts import detect_tools as dt
-    from .models import RefineDet512, RetinaNet, SSD300, SSD512, utils as mu
+    from .models import FCOSDet, RefineDet512, RetinaNet, SSD300, SSD512, utils as mu
     from .operators import Loss as lo, iou_utils as iu
 
     plan = [
@@ -23,6 +23,7 @@ def install(reference_root=None):
         ("models.SSD512", SSD512, ["MultiBoxLoss512"]),
         ("models.RetinaNet", RetinaNet, ["RetinaFocalLoss"]),
         ("models.RefineDet512", RefineDet512, ["RefineDetLoss"]),
+        ("models.FCOSDet", FCOSDet, ["FCOSLoss"]),
         ("models.utils", mu, ["detect", "detect_objects"]),
         ("models", None, []),
         ("detect_scripts.detect_tools", dt, ["detect", "detect_refine", "detect_objects"]),
@@ -40,7 +41,8 @@ def install(reference_root=None):
     try:
         ref_models = importlib.import_module("models")
         for cls_name, ours in (("MultiBoxLoss300", SSD300), ("MultiBoxLoss512", SSD512),
-                               ("RetinaFocalLoss", RetinaNet), ("RefineDetLoss", RefineDet512)):
+                               ("RetinaFocalLoss", RetinaNet), ("RefineDetLoss", RefineDet512),
+                               ("FCOSLoss", FCOSDet)):
             if hasattr(ref_models, cls_name):
                 setattr(ref_models, cls_name, getattr(ours, cls_name))
                 patched.append(f"models.{cls_name}")
