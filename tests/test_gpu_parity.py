@@ -483,3 +483,54 @@ def test_fcos_loss_and_postprocess(dev):
         assert torch.equal(got[1][i].cpu(), ref[1][i])
         assert torch.equal(got[2][i].cpu(), ref[2][i])
         assert torch.allclose(got[0][i].cpu(), ref[0][i], rtol=1e-6, atol=1e-7)
+
+
+def test_ragged_shapes_and_many_objects(dev):
+    """Edge cases of the streaming kernels: P not a multiple of the tile (or of 4: every tile start is
+    mis-aligned, the last tile ends off a 16-byte boundary), a single image, an image with 300 objects
+    (more than the per-warp object table), an image without objects next to normal ones."""
+    from oracle import box_pipeline as O
+    from shape_based_object_detection_b200 import priors as PR, synth
+    from shape_based_object_detection_b200.models import MultiBoxLoss512, RetinaFocalLoss
+    from shape_based_object_detection_b200.models import utils as MU
+    pri = PR.ssd512_priors()[:1003].contiguous()  # 1003 * 5 floats per image: odd everything
+    gen = torch.Generator().manual_seed(9)
+    for N, Cn, gmax, Mod, variant, reg, cls in ((3, 5, 8, MultiBoxLoss512, "s512", "", ""),
+                                                (1, 7, 8, RetinaFocalLoss, "ret", "DIOU", "FOCAL"),
+                                                (2, 5, 300, MultiBoxLoss512, "s512", "", "")):
+        locs, scores, bx, lb = synth.make_train_batch(pri, N, Cn, gmax, 100 + N)
+        if gmax == 300:
+            bx[0], lb[0] = synth.make_gt(1, 300, Cn, gen, gmin=300)
+            bx[0], lb[0] = bx[0][0], lb[0][0]
+        l_c, s_c = locs.clone().requires_grad_(True), scores.clone().requires_grad_(True)
+        want, parts = O.multibox_loss(variant, pri, l_c, s_c, bx, lb, reg_loss=reg, cls_loss=cls, want_parts=True)
+        want.backward()
+        crit = Mod(cu(pri, dev), cfg(reg, cls, Cn))
+        l_d, s_d = cu(locs, dev).requires_grad_(True), cu(scores, dev).requires_grad_(True)
+        loss = crit(l_d, s_d, [cu(b, dev) for b in bx], [cu(l, dev) for l in lb])
+        loss.backward()
+        st = crit.last["state"]
+        assert torch.equal(st.obj.cpu().long(), parts["obj"]), (N, Cn, gmax)
+        assert torch.equal(st.targets()[0].cpu(), parts["true_classes"])
+        assert abs(loss.item() - want.item()) <= RTOL_LOSS * abs(want.item()), (loss.item(), want.item())
+        assert torch.allclose(l_d.grad.cpu(), l_c.grad, rtol=RTOL_GRAD, atol=1e-7)
+        assert torch.allclose(s_d.grad.cpu(), s_c.grad, rtol=RTOL_GRAD, atol=1e-7)
+    # an image without objects: defined as "all background" (the reference raises); the other images
+    # must be unaffected, i.e. the batch sums equal those of the batch without that image
+    locs, scores, bx, lb = synth.make_train_batch(pri, 3, 5, 8, 321)
+    crit = MultiBoxLoss512(cu(pri, dev), cfg("", "", 5))
+    bx2 = [bx[0], torch.zeros((0, 4)), bx[2]]
+    lb2 = [lb[0], torch.zeros((0,), dtype=torch.long), lb[2]]
+    crit(cu(locs, dev), cu(scores, dev), [cu(b, dev) for b in bx2], [cu(l, dev) for l in lb2])
+    part = crit.last["state"].partials.cpu()
+    assert float(part[1, 3]) == 0.0 and float(part[1, 0]) == 0.0 and float(part[1, 2]) == 0.0
+    crit(cu(locs[[0, 2]], dev).contiguous(), cu(scores[[0, 2]], dev).contiguous(),
+         [cu(bx[0], dev), cu(bx[2], dev)], [cu(lb[0], dev), cu(lb[2], dev)])
+    assert torch.equal(crit.last["state"].partials.cpu(), part[[0, 2]])
+    # eval path on the same ragged shape
+    elocs, escores = synth.make_eval_batch(pri, 3, 5, 11, bg_bias=3.0)
+    want = O.detect(elocs.clone(), escores, 0.01, 0.45, 50, pri)
+    got = MU.detect(cu(elocs, dev), cu(escores, dev), 0.01, 0.45, 50, cu(pri, dev), cfg(n_classes=5))
+    for i in range(3):
+        assert torch.equal(got[1][i].cpu(), want[1][i])
+        assert torch.allclose(got[2][i].cpu(), want[2][i], rtol=1e-5, atol=1e-8)
