@@ -81,6 +81,13 @@ SBOD_API int sbod_box_decode(const float* locs, const float* priors_cxcy, float*
 SBOD_API int sbod_offset2bbox(const float* arm_locs, const float* odm_locs, const float* priors_cxcy,
                      float* out, int N, int P, sbod_stream_t stream);
 
+/* Self-test of the device-side correctly rounded division the matching kernel uses instead of
+ * div.rn (no reference counterpart; metrics.py:247 is a plain torch division): out[i] = a[i] / b[i]
+ * by the fast sequence, ref[i] by div.rn, fast_ok[i] = 1 where the kernel would take the fast
+ * sequence. All pointers are device pointers. */
+SBOD_API int sbod_selftest_div(const float* a, const float* b, long long n, float* out, float* ref,
+                               uint8_t* fast_ok, sbod_stream_t stream);
+
 /* RefineDet ODM easy-negative mask: out[i] = softmax(arm_scores[i, :])[1] < theta, arm_scores
  * [n_rows,2] (models/RefineDet512.py:894-895). */
 SBOD_API int sbod_arm_easy_negative(const float* arm_scores, long long n_rows, float theta, uint8_t* out,

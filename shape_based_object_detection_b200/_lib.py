@@ -32,6 +32,7 @@ EXPORTS = [
     "sbod_detect_workspace_bytes", "sbod_detect_workspace_zero_bytes", "sbod_detect",
     "sbod_loss_forward_host_arena_bytes", "sbod_loss_forward_host",
     "sbod_fcos_workspace_bytes", "sbod_fcos_forward", "sbod_fcos_backward", "sbod_fcos_postprocess",
+    "sbod_selftest_div",
 ]
 
 
@@ -97,6 +98,7 @@ def _declare(lib):
         "sbod_box_decode": [vp, vp, vp, i32, i32, f32, f32, vp],
         "sbod_offset2bbox": [vp, vp, vp, vp, i32, i32, vp],
         "sbod_arm_easy_negative": [vp, C.c_longlong, f32, vp, vp],
+        "sbod_selftest_div": [vp, vp, C.c_longlong, vp, vp, vp, vp],
         "sbod_pair_iou_fwd": [vp, vp, i32, i32, vp, vp],
         "sbod_pair_iou_bwd": [vp, vp, vp, i32, i32, vp, vp, vp],
         "sbod_smooth_l1": [vp, vp, i32, f32, vp, vp, vp],

@@ -501,6 +501,27 @@ extern "C" int sbod_offset2bbox(const float* arm_locs, const float* odm_locs,
   return SBOD_OK;
 }
 
+namespace sbod {
+__global__ void selftest_div_kernel(const float* a, const float* b, long long n, float* out, float* ref,
+                                    uint8_t* fast_ok) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  out[i] = div_rn_fast(a[i], b[i]);
+  ref[i] = __fdiv_rn(a[i], b[i]);
+  fast_ok[i] = div_fast_ok(a[i], b[i]) ? 1 : 0;
+}
+}  // namespace sbod
+
+extern "C" int sbod_selftest_div(const float* a, const float* b, long long n, float* out, float* ref,
+                                 uint8_t* fast_ok, sbod_stream_t stream) {
+  if (!a || !b || !out || !ref || !fast_ok || n < 0) return SBOD_ERR_INVALID;
+  if (n == 0) return SBOD_OK;
+  sbod::selftest_div_kernel<<<unsigned((n + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(a, b, n, out, ref,
+                                                                                                  fast_ok);
+  SBOD_LAUNCH_CHECK();
+  return SBOD_OK;
+}
+
 extern "C" int sbod_arm_easy_negative(const float* arm_scores, long long n_rows, float theta,
                                       uint8_t* out, sbod_stream_t stream) {
   if (n_rows < 0) return SBOD_ERR_INVALID;

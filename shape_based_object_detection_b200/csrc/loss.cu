@@ -289,29 +289,32 @@ __global__ void __launch_bounds__(kRows) match_lse_kernel(const LossParams q) {
 // match_lse_fast_kernel — warp-specialised version for odd C <= 128 (C = 81, 21, ...).
 //   warps 0-7  (256 threads) "stream" role: consume the TMA ring, two threads per row,
 //              log-sum-exp + background CE per prior. Never touches the ground truth.
-//   warps 8-11 (128 threads) "match" role: prior<->GT IoU with warp-bbox culling, both arg-maxes.
-//              Never touches the logits. Per-object best priors are reduced with REDUX inside
-//              the warp and kept in a per-warp shared array (no shared atomics), flushed to
-//              global memory once per image (tiles of a CTA are contiguous).
+//   warps 8-15 (256 threads) "match" role: prior<->GT IoU with slice-bbox culling, both arg-maxes.
+//              Never touches the logits. The object group is staged in a per-warp shared buffer and
+//              consumed two objects at a time; an object's best prior inside a slice is one REDUX +
+//              one ballot and is kept as a key in a register of the lane that owns the object.
 // The two roles share nothing but the SM: ALU-bound matching hides under the memory-bound stream.
 // ------------------------------------------------------------------------------------------
 constexpr int kMatchWarps = 8;
+constexpr int kKeyGroups = 4;  // object keys kept in registers: 32 * kKeyGroups objects per image
 constexpr int kZeroFloats = 1024;  // 4 KB zero tile for the gradient prefill
 constexpr int kMatchThreads = 32 * kMatchWarps;
 constexpr int kFastThreads = kStreamThreads + kMatchThreads;
 
+template <int kC>  // kC > 0: the class count is a compile-time constant (unrolled stream role)
 __global__ void __launch_bounds__(kFastThreads, 2) match_lse_fast_kernel(const LossParams q) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   float* stages = reinterpret_cast<float*>(smem_raw);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + size_t(q.n_stages) * q.stage_floats * 4);
-  __shared__ unsigned long long s_wkey[kMatchWarps][kGtChunk];
+  __shared__ __align__(16) float4 s_gt[kMatchWarps][32];
+  __shared__ float s_ga[kMatchWarps][32];
   __shared__ __align__(128) float s_zero[kZeroFloats];  // source of the gradient zero-fill stores
 
   const int tid = threadIdx.x, lane = tid & 31;
   int t0, t1;
   tile_range(q.n_tiles, blockIdx.x, gridDim.x, t0, t1);
   const int n_my = t1 - t0;
-  const int C = q.C;
+  const int C = kC ? kC : q.C;
   if (tid == 0) {
     for (int s = 0; s < q.n_stages; ++s) mbar_init(&bars[s], 1);
     fence_mbar_init();
@@ -349,13 +352,22 @@ __global__ void __launch_bounds__(kFastThreads, 2) match_lse_fast_kernel(const L
       const uint32_t head = ((uint32_t(tc.n) * uint32_t(q.P) + uint32_t(tc.p0)) * uint32_t(C)) & 3u;
       const int r = min(row, tc.rows - 1);  // keep every lane in the shuffles
       const float* rbase = stage + head + r * C;
-      const float mx = half_row_max(rbase + h, nh);
-      const float sum = half_row_sumexp(rbase + h, nh, -mx * kLog2e);
+      // One pass: shift by the row's own background logit, whose term is then 1, so the sum cannot
+      // underflow; when it overflows (some logit > background + 88) the warp redoes the row with the
+      // usual max shift.
+      const float x0 = rbase[0];
+      float sum = kC ? pair_row_sumexp_fixed<kC>(rbase, h, -x0 * kLog2e)
+                     : half_row_sumexp(rbase + h, nh, -x0 * kLog2e);
+      float shift = x0;
+      if (__any_sync(0xffffffffu, !(sum < __int_as_float(0x7f800000)))) {
+        shift = half_row_max(rbase + h, nh);
+        sum = half_row_sumexp(rbase + h, nh, -shift * kLog2e);
+      }
       if (h == 0 && row < tc.rows) {
         const float lg = logf(sum);
         const size_t np = size_t(tc.n) * q.P + tc.p0 + row;
-        q.lse[np] = mx + lg;
-        q.ce[np] = (mx - rbase[0]) + lg;  // background CE, torch's operation order
+        q.lse[np] = shift + lg;
+        q.ce[np] = (shift - x0) + lg;  // background CE
       }
       named_bar_sync(1, kStreamThreads);  // the stream group is done with stage s
       if (tid == 0 && it + q.n_stages < n_my)
@@ -390,24 +402,26 @@ __global__ void __launch_bounds__(kFastThreads, 2) match_lse_fast_kernel(const L
   // current one is processed). Ground truth is read through L1 (an image's boxes are ~2 KB) and
   // handed from lane to lane with shuffles, so the role needs no barrier at all.
   if (q.debug_skip & 2) return;
-  const int tm = tid - kStreamThreads, wm = tm >> 5;
+  const int wm = (tid - kStreamThreads) >> 5;
   const float INF = __int_as_float(0x7f800000);
-  constexpr int kSl = 1;  // 32-prior slices per warp and pass (2 was measured slower: the joint bounding box admits more objects)
-  const int slices_per_image = (q.P + 32 * kSl - 1) / (32 * kSl);
-  unsigned long long* wkey = s_wkey[wm];
+  const int slices_per_image = (q.P + 31) / 32;
+  float4* sgt = s_gt[wm];  // this warp's staging of one group of 32 objects (+ their areas)
+  float* sga = s_ga[wm];
   int prev_n = -1, g0 = 0, G = 0;
+  // Best prior of object 32*u + lane seen by this warp in the current image, as a sortable key
+  // (IoU bits : ~prior) held in a register of lane `lane`; flushed with one atomicMax per object
+  // when the warp moves to another image. Objects beyond 32*kKeyGroups go straight to global memory.
+  unsigned long long kreg[kKeyGroups];
+#pragma unroll
+  for (int u = 0; u < kKeyGroups; ++u) kreg[u] = 0ull;
 
   auto flush_keys = [&](int n) {
-    const int gl = min(G, kGtChunk);
-    for (int i = lane; i < gl; i += 32) {
-      const unsigned long long k = wkey[i];
-      if (k) atomicMax(&q.gtkey[size_t(n) * q.gmax + i], k);
-      wkey[i] = 0ull;
+#pragma unroll
+    for (int u = 0; u < kKeyGroups; ++u) {
+      if (kreg[u]) atomicMax(&q.gtkey[size_t(n) * q.gmax + 32 * u + lane], kreg[u]);
+      kreg[u] = 0ull;
     }
-    __syncwarp();
   };
-  for (int i = lane; i < kGtChunk; i += 32) wkey[i] = 0ull;
-  __syncwarp();
 
   int img_i = 0;
   int cur_n = int(blockIdx.x % q.N);
@@ -450,37 +464,24 @@ __global__ void __launch_bounds__(kFastThreads, 2) match_lse_fast_kernel(const L
       G = q.gt_offsets[n + 1] - g0;
       prev_n = n;
     }
-    // Two 32-prior slices per warp and pass (kSl): their IoU chains are independent (ILP), they share
-    // the object loads / shuffles, and one cross-lane reduction serves 64 priors.
-    const int ps = (slices_per_image - 1 - item) * (32 * kSl);  // heaviest (last) slices first
-    int p[kSl];
-    bool valid[kSl], azero[kSl], active[kSl];
-    float4 a[kSl];
-    float aa[kSl], best[kSl];
-    int bobj[kSl];
-    bool a_ok = true;
-    float bx1 = INF, by1 = INF, bx2 = -INF, by2 = -INF;
-#pragma unroll
-    for (int u = 0; u < kSl; ++u) {
-      p[u] = ps + 32 * u + lane;
-      valid[u] = p[u] < q.P;
-      a[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (valid[u]) a[u] = q.anchors_xy ? q.anchors_xy[size_t(n) * q.P + p[u]] : q.priors_xy[p[u]];
-      aa[u] = box_area_rn(a[u]);
-      azero[u] = anchor_is_zero(a[u]);
-      active[u] = valid[u] && !azero[u];
-      a_ok = a_ok && (((a[u].z >= a[u].x) && (a[u].w >= a[u].y)) || !valid[u]);
-      if (active[u]) {
-        bx1 = fminf(bx1, a[u].x); by1 = fminf(by1, a[u].y);
-        bx2 = fmaxf(bx2, a[u].z); by2 = fmaxf(by2, a[u].w);
-      }
-      best[u] = -INF;  // running arg-max over objects, first index wins
-      bobj[u] = 0;
-    }
+    const int ps = (slices_per_image - 1 - item) * 32;  // heaviest (last) slices first
+    const int p = ps + lane;
+    const bool valid = p < q.P;
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (valid) a = q.anchors_xy ? q.anchors_xy[size_t(n) * q.P + p] : q.priors_xy[p];
+    const float aa = box_area_rn(a);
+    const bool azero = anchor_is_zero(a);
+    const bool active = valid && !azero;
+    const bool a_ok = ((a.z >= a.x) && (a.w >= a.y)) || !valid;
     const bool warp_a_ok = __all_sync(0xffffffffu, a_ok) != 0;
-    bx1 = warp_min(bx1); by1 = warp_min(by1); bx2 = warp_max(bx2); by2 = warp_max(by2);
+    // bounding box of the warp's priors
+    const float bx1 = warp_min_redux(active ? a.x : INF), by1 = warp_min_redux(active ? a.y : INF);
+    const float bx2 = warp_max_redux(active ? a.z : -INF), by2 = warp_max_redux(active ? a.w : -INF);
+    float best = -INF;  // running arg-max over objects, first index wins
+    int bobj = 0;
 
-    for (int base = 0; base < G; base += 32) {
+    // one group of 32 objects; `kr` is the key register of the group (in_reg) or unused
+    auto do_group = [&](int base, unsigned long long& kr, bool in_reg) {
       const int gi = base + lane;
       float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
       if (gi < G) g = q.gt_boxes[g0 + gi];
@@ -488,73 +489,67 @@ __global__ void __launch_bounds__(kFastThreads, 2) match_lse_fast_kernel(const L
       const bool grp_ok = __all_sync(0xffffffffu, (g.z >= g.x) && (g.w >= g.y)) != 0;
       if (grp_ok && warp_a_ok) {
         // fast path: a pair that does not intersect is exactly +0, so only objects touching the
-        // warp's bounding box are evaluated
+        // warp's bounding box are evaluated, two at a time (independent dependency chains)
         const bool hit = !gskip && (g.z > bx1) && (g.x < bx2) && (g.w > by1) && (g.y < by2);
         unsigned m = __ballot_sync(0xffffffffu, hit);
-        float cbest[kSl];
-        int cidx[kSl];
-#pragma unroll
-        for (int u = 0; u < kSl; ++u) {
-          cbest[u] = azero[u] ? -1.f : 0.f;
-          cidx[u] = base;
+        float cbest = azero ? -1.f : 0.f;
+        int cidx = base;
+        if (m) {
+          sgt[lane] = g;
+          sga[lane] = box_area_rn(g);
+          __syncwarp();
+          while (m) {
+            const int sA = __ffs(m) - 1;
+            m &= m - 1;
+            const int sB = m ? __ffs(m) - 1 : sA;  // odd count: the last object twice (idempotent)
+            m &= m - 1;
+            const float4 gA = sgt[sA], gB = sgt[sB];
+            const float gaA = sga[sA], gaB = sga[sB];
+            // straight-line code (both boxes of a pair have w, h >= 0 here, so the denominator is
+            // >= eps and an empty intersection gives exactly +0, as in the reference)
+            const float inA = inter_rn(gA, a), inB = inter_rn(gB, a);
+            const float dA = __fadd_rn(__fsub_rn(__fadd_rn(gaA, aa), inA), kEps);
+            const float dB = __fadd_rn(__fsub_rn(__fadd_rn(gaB, aa), inB), kEps);
+            float qA, qB;
+            if (__all_sync(0xffffffffu, div_fast_ok(inA, dA) && div_fast_ok(inB, dB))) {
+              qA = div_rn_fast(inA, dA);
+              qB = div_rn_fast(inB, dB);
+            } else {
+              qA = __fdiv_rn(inA, dA);
+              qB = __fdiv_rn(inB, dB);
+            }
+            const float idle = azero ? -1.f : 0.f;
+            const float iouA = active ? qA : idle, iouB = active ? qB : idle;
+            if (iouA > cbest) {
+              cbest = iouA;
+              cidx = base + sA;
+            }
+            if (iouB > cbest) {
+              cbest = iouB;
+              cidx = base + sB;
+            }
+            // best prior of each object inside this slice: max IoU bits, then the lowest lane
+            const unsigned bA = active ? __float_as_uint(iouA) : 0u, bB = active ? __float_as_uint(iouB) : 0u;
+            const unsigned mA = __reduce_max_sync(0xffffffffu, bA), mB = __reduce_max_sync(0xffffffffu, bB);
+            const unsigned vA = __ballot_sync(0xffffffffu, bA == mA), vB = __ballot_sync(0xffffffffu, bB == mB);
+            const unsigned long long kA =
+                (static_cast<unsigned long long>(mA) << 32) | (0xffffffffu - unsigned(ps + __ffs(vA) - 1));
+            const unsigned long long kB =
+                (static_cast<unsigned long long>(mB) << 32) | (0xffffffffu - unsigned(ps + __ffs(vB) - 1));
+            if (in_reg) {
+              if (lane == sA && mA && kA > kr) kr = kA;
+              if (lane == sB && mB && kB > kr) kr = kB;
+            } else {
+              if (lane == 0 && mA) atomicMax(&q.gtkey[size_t(n) * q.gmax + base + sA], kA);
+              if (lane == 1 && mB) atomicMax(&q.gtkey[size_t(n) * q.gmax + base + sB], kB);
+            }
+          }
+          __syncwarp();  // the staging is free for the next group
         }
-        while (m) {
-          const int src = __ffs(m) - 1;
-          m &= m - 1;
-          const int j = base + src;
-          float4 gj;
-          gj.x = __shfl_sync(0xffffffffu, g.x, src);
-          gj.y = __shfl_sync(0xffffffffu, g.y, src);
-          gj.z = __shfl_sync(0xffffffffu, g.z, src);
-          gj.w = __shfl_sync(0xffffffffu, g.w, src);
-          const float ga = box_area_rn(gj);
-          float iou[kSl];
-#pragma unroll
-          for (int u = 0; u < kSl; ++u) {
-            iou[u] = 0.f;
-            if (active[u]) {
-              const float inner = inter_rn(gj, a[u]);
-              if (inner > 0.f)
-                iou[u] = __fdiv_rn(inner, __fadd_rn(__fsub_rn(__fadd_rn(ga, aa[u]), inner), kEps));
-            }
-          }
-          unsigned bits = 0u, pb = 0xffffffffu;
-#pragma unroll
-          for (int u = 0; u < kSl; ++u) {
-            if (iou[u] > cbest[u]) {
-              cbest[u] = iou[u];
-              cidx[u] = j;
-            }
-            const unsigned b = __float_as_uint(iou[u]);
-            if (b > bits) {  // strictly greater: ties keep the lower prior index (earlier slice)
-              bits = b;
-              pb = unsigned(p[u]);
-            }
-          }
-          // best prior of object j seen by this warp (max IoU, then lowest prior index); the
-          // cross-lane reduction only runs when some lane beats the stored value
-          if (j < kGtChunk) {
-            const unsigned long long cur = wkey[j];
-            const unsigned cur_bits = unsigned(cur >> 32);
-            const unsigned cur_p = 0xffffffffu - unsigned(cur & 0xffffffffull);
-            const bool better = bits > cur_bits || (bits == cur_bits && bits != 0u && pb < cur_p);
-            if (__any_sync(0xffffffffu, better)) {
-              const unsigned mb = __reduce_max_sync(0xffffffffu, bits);
-              const unsigned pm = __reduce_min_sync(0xffffffffu, bits == mb ? pb : 0xffffffffu);
-              if (lane == 0) wkey[j] = (static_cast<unsigned long long>(mb) << 32) | (0xffffffffu - pm);
-              __syncwarp();
-            }
-          } else if (bits) {  // more objects than the per-warp table holds: straight to global memory
-            atomicMax(&q.gtkey[size_t(n) * q.gmax + j],
-                      (static_cast<unsigned long long>(bits) << 32) | (0xffffffffu - pb));
-          }
+        if (cbest > best) {
+          best = cbest;
+          bobj = cidx;
         }
-#pragma unroll
-        for (int u = 0; u < kSl; ++u)
-          if (cbest[u] > best[u]) {
-            best[u] = cbest[u];
-            bobj[u] = cidx[u];
-          }
       } else {
         // general path: every pair, masks applied as the reference does (metrics.py:249-250)
         const int gcnt = min(32, G - base);
@@ -565,33 +560,34 @@ __global__ void __launch_bounds__(kFastThreads, 2) match_lse_fast_kernel(const L
           gj.z = __shfl_sync(0xffffffffu, g.z, src);
           gj.w = __shfl_sync(0xffffffffu, g.w, src);
           const bool sk = __shfl_sync(0xffffffffu, int(gskip), src) != 0;
-#pragma unroll
-          for (int u = 0; u < kSl; ++u) {
-            float iou = iou_metrics_rn(gj, box_area_rn(gj), a[u], aa[u]);
-            if (sk) iou = 0.f;
-            if (azero[u]) iou = -1.f;
-            if (valid[u] && iou > best[u]) {
-              best[u] = iou;
-              bobj[u] = base + src;
-            }
-            if (valid[u] && iou > 0.f)
-              atomicMax(&q.gtkey[size_t(n) * q.gmax + base + src],
-                        (static_cast<unsigned long long>(__float_as_uint(iou)) << 32) |
-                            (0xffffffffu - unsigned(p[u])));
+          float iou = iou_metrics_rn(gj, box_area_rn(gj), a, aa);
+          if (sk) iou = 0.f;
+          if (azero) iou = -1.f;
+          if (valid && iou > best) {
+            best = iou;
+            bobj = base + src;
           }
+          if (valid && iou > 0.f)
+            atomicMax(&q.gtkey[size_t(n) * q.gmax + base + src],
+                      (static_cast<unsigned long long>(__float_as_uint(iou)) << 32) | (0xffffffffu - unsigned(p)));
         }
       }
-    }
+    };
+
 #pragma unroll
-    for (int u = 0; u < kSl; ++u) {
-      if (G == 0) {
-        best[u] = 0.f;
-        bobj[u] = 0;
-      }
-      if (valid[u]) {
-        q.ov[size_t(n) * q.P + p[u]] = best[u];
-        q.obj[size_t(n) * q.P + p[u]] = bobj[u];
-      }
+    for (int u = 0; u < kKeyGroups; ++u)
+      if (32 * u < G) do_group(32 * u, kreg[u], true);
+    for (int base = 32 * kKeyGroups; base < G; base += 32) {
+      unsigned long long dummy = 0ull;
+      do_group(base, dummy, false);
+    }
+    if (G == 0) {
+      best = 0.f;
+      bobj = 0;
+    }
+    if (valid) {
+      q.ov[size_t(n) * q.P + p] = best;
+      q.obj[size_t(n) * q.P + p] = bobj;
     }
   }
   if (prev_n >= 0) flush_keys(prev_n);
@@ -1519,7 +1515,9 @@ static int set_kernel_attrs() {
   static bool attr_done = false;
   if (attr_done) return SBOD_OK;
   SBOD_CUDA_TRY(cudaFuncSetAttribute(match_lse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-  SBOD_CUDA_TRY(cudaFuncSetAttribute(match_lse_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  SBOD_CUDA_TRY(cudaFuncSetAttribute(match_lse_fast_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  SBOD_CUDA_TRY(cudaFuncSetAttribute(match_lse_fast_kernel<81>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  SBOD_CUDA_TRY(cudaFuncSetAttribute(match_lse_fast_kernel<21>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   SBOD_CUDA_TRY(cudaFuncSetAttribute(loss_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   SBOD_CUDA_TRY(cudaFuncSetAttribute(forced_match_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
   SBOD_CUDA_TRY(cudaFuncSetAttribute(mine_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 205 * 1024));
@@ -1535,7 +1533,9 @@ static int launch_match(const LossParams& q, cudaStream_t st) {
     const size_t smem = size_t(q.n_stages) * q.stage_floats * 4 + kMaxStages * 8;
     int grid = sm_count() * q.ctas_per_sm;
     if (grid > q.n_tiles) grid = q.n_tiles;
-    match_lse_fast_kernel<<<grid, kFastThreads, smem, st>>>(q);
+    if (q.C == 81) match_lse_fast_kernel<81><<<grid, kFastThreads, smem, st>>>(q);       // COCO
+    else if (q.C == 21) match_lse_fast_kernel<21><<<grid, kFastThreads, smem, st>>>(q);  // VOC
+    else match_lse_fast_kernel<0><<<grid, kFastThreads, smem, st>>>(q);
     SBOD_LAUNCH_CHECK();
     return SBOD_OK;
   }

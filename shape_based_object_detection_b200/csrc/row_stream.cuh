@@ -71,6 +71,26 @@ SBOD_DEVINL float half_row_sumexp(const float* rp, int nh, float nmx2) {
   return s + __shfl_xor_sync(0xffffffffu, s, 1);
 }
 
+// Compile-time C: sum of exp(x - shift) over one row shared by the two threads of a pair, fully
+// unrolled (no loop control, immediate offsets). rbase = first logit of the row, h = element parity
+// of this thread, nshift2 = -shift * log2(e). The caller checks the result for overflow.
+template <int kC>
+SBOD_DEVINL float pair_row_sumexp_fixed(const float* rbase, int h, float nshift2) {
+  constexpr int kBoth = kC / 2;  // elements both parities own; an odd C gives parity 0 one more
+  const float* rp = rbase + h;
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll
+  for (int j = 0; j < kBoth; j += 4) {
+    s0 += ex2_approx(fmaf(rp[2 * j], kLog2e, nshift2));
+    if (j + 1 < kBoth) s1 += ex2_approx(fmaf(rp[2 * j + 2], kLog2e, nshift2));
+    if (j + 2 < kBoth) s2 += ex2_approx(fmaf(rp[2 * j + 4], kLog2e, nshift2));
+    if (j + 3 < kBoth) s3 += ex2_approx(fmaf(rp[2 * j + 6], kLog2e, nshift2));
+  }
+  if ((kC & 1) && h == 0) s1 += ex2_approx(fmaf(rp[2 * kBoth], kLog2e, nshift2));
+  const float s = (s0 + s1) + (s2 + s3);
+  return s + __shfl_xor_sync(0xffffffffu, s, 1);
+}
+
 // As above, and additionally records in (m0, m1) which of this thread's elements (bit j, j < 64)
 // have exp(x - mx) > floor. Since the row sum is >= 1, prob = e/sum <= e, so the mask is a
 // superset of the classes whose probability exceeds `floor`.

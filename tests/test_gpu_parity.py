@@ -534,3 +534,30 @@ def test_ragged_shapes_and_many_objects(dev):
     for i in range(3):
         assert torch.equal(got[1][i].cpu(), want[1][i])
         assert torch.allclose(got[2][i].cpu(), want[2][i], rtol=1e-5, atol=1e-8)
+
+
+def test_fast_division_is_correctly_rounded(dev):
+    """The matching kernel divides with its own reciprocal + FMA sequence (csrc/common.cuh:div_rn_fast)
+    wherever div_fast_ok holds; it must equal IEEE division bit for bit there."""
+    import ctypes as C
+    from shape_based_object_detection_b200 import _lib as L
+    gen = torch.Generator().manual_seed(77)
+    n = 1 << 22
+    # IoU-shaped operands, wide-exponent operands, zeros and tiny numerators
+    inter = torch.rand(n, generator=gen) * torch.rand(n, generator=gen)
+    union = inter + torch.rand(n, generator=gen) + 1e-5
+    a = torch.cat([inter, torch.exp2(torch.rand(n, generator=gen) * 130 - 65), torch.zeros(1024),
+                   torch.rand(1024, generator=gen) * 1e-30])
+    b = torch.cat([union, torch.exp2(torch.rand(n, generator=gen) * 130 - 65), torch.rand(1024, generator=gen) + 0.1,
+                   torch.rand(1024, generator=gen) + 0.1])
+    a_d, b_d = a.to(dev), b.to(dev)
+    out, ref = torch.empty_like(a_d), torch.empty_like(a_d)
+    ok = torch.empty(a_d.numel(), dtype=torch.uint8, device=dev)
+    L.check(L.lib().sbod_selftest_div(L.ptr(a_d), L.ptr(b_d), C.c_longlong(a_d.numel()), L.ptr(out), L.ptr(ref),
+                                      L.ptr(ok), L.stream_ptr()))
+    torch.cuda.synchronize()
+    okb = ok.bool()
+    assert okb[:n].all() and okb[2 * n:2 * n + 1024].all()      # IoU-shaped operands and zeros take the fast sequence
+    assert not okb[2 * n + 1024:].any()                         # tiny numerators do not
+    assert torch.equal(out[okb].view(torch.int32), ref[okb].view(torch.int32))
+    assert torch.equal(ref.cpu(), a / b)                        # div.rn itself == torch's division
