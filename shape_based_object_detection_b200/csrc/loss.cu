@@ -852,7 +852,7 @@ __device__ void mark_selected(const float* __restrict__ vals, uint8_t* __restric
   const bool all_ties = r.take_ties >= r.n_ties;
   for (int i = tid; i < n; i += nt) {
     const float v = vals[i];
-    if (v > thr || (all_ties && v == thr)) sel[i] |= 2;
+    if (v > thr || (all_ties && v == thr)) sel[i] = 2;  // a candidate is never a positive: no read-modify-write
   }
   if (!all_ties) {  // rare: pick ties by ascending index (deterministic)
     __syncthreads();
@@ -860,7 +860,7 @@ __device__ void mark_selected(const float* __restrict__ vals, uint8_t* __restric
       int left = r.take_ties;
       for (int i = 0; i < n && left > 0; ++i)
         if (vals[i] == thr) {
-          sel[i] |= 2;
+          sel[i] = 2;
           --left;
         }
     }
@@ -895,6 +895,7 @@ __global__ void __launch_bounds__(kClsThreads) classify_kernel(const LossParams 
   int32_t* s_rank = reinterpret_cast<int32_t*>(s_prior + q.gmax);  // [gmax], -1 = filtered out
   __shared__ float s_ov[kClsPriors];
   __shared__ int s_obj[kClsPriors];
+  __shared__ double s_red4[4 * 32];
   __shared__ double s_red[34];
   __shared__ int s_warp_tot[kClsThreads / 32];
   __shared__ int s_carry;
@@ -998,13 +999,11 @@ __global__ void __launch_bounds__(kClsThreads) classify_kernel(const LossParams 
     q.sel[base + p] = selbits;
     q.cand[base + p] = v;
   }
-  const double t_loc = block_sum(a_loc, s_red);
-  const double t_pos = block_sum(a_pos, s_red);
-  const double t_neg = block_sum(a_neg, s_red);
-  const double t_npos = block_sum(double(npos), s_red);
+  double tot[4] = {a_loc, a_pos, a_neg, double(npos)};
+  block_sum4_to_thread0(tot, s_red4);
   if (tid == 0) {
     double* bp = q.blockpart + (size_t(n) * gridDim.x + blockIdx.x) * 4;
-    bp[0] = t_loc; bp[1] = t_pos; bp[2] = t_neg; bp[3] = t_npos;
+    bp[0] = tot[0]; bp[1] = tot[1]; bp[2] = tot[2]; bp[3] = tot[3];
   }
 }
 
@@ -1338,7 +1337,8 @@ __global__ void __launch_bounds__(256) bwd_patch_kernel(const LossParams q, cons
     }
     if (!grad_scores) continue;
     unsigned m = __ballot_sync(0xffffffffu, selbits != 0);
-    // four selected rows per round so that their loads are in flight together
+    // four selected rows per round, every 32-class chunk of them loaded before anything is stored
+    // (loads and stores may alias as far as the compiler knows): up to 16 loads in flight per lane
     while (m) {
       int src[4];
       int rc[4];
@@ -1354,17 +1354,37 @@ __global__ void __launch_bounds__(256) bwd_patch_kernel(const LossParams q, cons
         rc[u] = __shfl_sync(0xffffffffu, cls, sl);
         rl[u] = __shfl_sync(0xffffffffu, lse, sl);
       }
-      for (int kb = 0; kb < q.C; kb += 32) {
-        const int k = kb + lane;
-        float x[4];
+      if (q.C <= 4 * 32) {
+        float x[4][4];
 #pragma unroll
-        for (int u = 0; u < 4; ++u)
-          x[u] = (src[u] >= 0 && k < q.C) ? q.scores[(base + src[u]) * q.C + k] : 0.f;
+        for (int c = 0; c < 4; ++c) {
+          const int k = 32 * c + lane;
 #pragma unroll
-        for (int u = 0; u < 4; ++u)
-          if (src[u] >= 0 && k < q.C)
-            grad_scores[(base + src[u]) * q.C + k] =
-                conf_scale * (__expf(x[u] - rl[u]) - (k == rc[u] ? 1.f : 0.f));
+          for (int u = 0; u < 4; ++u)
+            x[c][u] = (src[u] >= 0 && k < q.C) ? ld_stream_f32(q.scores + (base + src[u]) * q.C + k) : 0.f;
+        }
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const int k = 32 * c + lane;
+#pragma unroll
+          for (int u = 0; u < 4; ++u)
+            if (src[u] >= 0 && k < q.C)
+              grad_scores[(base + src[u]) * q.C + k] =
+                  conf_scale * (__expf(x[c][u] - rl[u]) - (k == rc[u] ? 1.f : 0.f));
+        }
+      } else {
+        for (int kb = 0; kb < q.C; kb += 32) {
+          const int k = kb + lane;
+          float x[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u)
+            x[u] = (src[u] >= 0 && k < q.C) ? q.scores[(base + src[u]) * q.C + k] : 0.f;
+#pragma unroll
+          for (int u = 0; u < 4; ++u)
+            if (src[u] >= 0 && k < q.C)
+              grad_scores[(base + src[u]) * q.C + k] =
+                  conf_scale * (__expf(x[u] - rl[u]) - (k == rc[u] ? 1.f : 0.f));
+        }
       }
     }
   }
