@@ -1304,33 +1304,40 @@ __global__ void __launch_bounds__(256) bwd_patch_kernel(const LossParams q, cons
                                 (q.reg_kind == SBOD_REG_L1_ELEM_MEAN ? 4.0 * npos_tot : npos_tot));
   const size_t warp0 = (size_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
   const size_t n_warps = (size_t(gridDim.x) * blockDim.x) >> 5;
+  // the selection flags and log-sum-exps of the next group are requested one iteration ahead
+  uint8_t sel_next = 0;
+  float lse_next = 0.f;
+  if (warp0 * 32 + lane < total) {
+    sel_next = q.sel[warp0 * 32 + lane];
+    lse_next = q.lse[warp0 * 32 + lane];
+  }
   for (size_t base = warp0 * 32; base < total; base += n_warps * 32) {
     const size_t i = base + lane;
     const bool in = i < total;
-    const uint8_t selbits = in ? q.sel[i] : uint8_t(0);
+    const uint8_t selbits = sel_next;
+    const float lse = lse_next;
+    {
+      const size_t inext = i + n_warps * 32;
+      sel_next = 0;
+      if (inext < total) {
+        sel_next = q.sel[inext];
+        lse_next = q.lse[inext];
+      }
+    }
+    // a mined negative has target class 0; only positives need their object's label and box
     int cls = 0;
-    float lse = 0.f;
-    if (in && selbits) {
+    if (in && (selbits & 1)) {
       const int n = int(i / q.P);
       const int p = int(i - size_t(n) * q.P);
       const int g0 = q.gt_offsets[n];
-      const int G = q.gt_offsets[n + 1] - g0;
-      const float ov = q.ov[i];
       const int obj = q.obj[i];
-      int64_t lab = 0;
-      if (G > 0) lab = map_label(q, q.gt_labels[g0 + obj]);
-      cls = (ov < q.thr_pos) ? 0 : int(lab);
+      cls = int(map_label(q, q.gt_labels[g0 + obj]));
       cls = min(max(cls, 0), q.C - 1);
-      lse = q.lse[i];
       if (grad_locs) {
-        float4 gl = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (selbits & 1) {
-          const float4 pred = reinterpret_cast<const float4*>(q.locs)[i];
-          const LocTerm lt = loc_term<true>(q, pred, prior_cxcy_of(q, n, p), q.gt_boxes[g0 + obj]);
-          gl = make_float4(lt.grad.x * loc_scale, lt.grad.y * loc_scale, lt.grad.z * loc_scale,
-                           lt.grad.w * loc_scale);
-        }
-        reinterpret_cast<float4*>(grad_locs)[i] = gl;
+        const float4 pred = reinterpret_cast<const float4*>(q.locs)[i];
+        const LocTerm lt = loc_term<true>(q, pred, prior_cxcy_of(q, n, p), q.gt_boxes[g0 + obj]);
+        reinterpret_cast<float4*>(grad_locs)[i] = make_float4(lt.grad.x * loc_scale, lt.grad.y * loc_scale,
+                                                             lt.grad.z * loc_scale, lt.grad.w * loc_scale);
       }
     } else if (in && grad_locs) {
       reinterpret_cast<float4*>(grad_locs)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
