@@ -309,6 +309,9 @@ __global__ void __launch_bounds__(kStreamThreads, 2) detect_score_fast_kernel(co
   float* stages = reinterpret_cast<float*>(smem_raw);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + size_t(q.n_stages) * q.stage_floats * 4);
   __shared__ unsigned int s_hist[kMaxBins + 40];  // + scratch of compute_cutoff
+  constexpr int kKeyBuf = 1024, kKeyFlush = 512;  // shared key buffer (see the slot reservation below)
+  __shared__ unsigned long long s_keys[kKeyBuf];
+  __shared__ unsigned int s_ncand, s_gbase;
 
   const int tid = threadIdx.x, lane = tid & 31;
   const int C = q.C;
@@ -337,6 +340,7 @@ __global__ void __launch_bounds__(kStreamThreads, 2) detect_score_fast_kernel(co
     fence_mbar_init();
   }
   for (int b = tid; b < q.n_bins; b += kStreamThreads) s_hist[b] = 0u;
+  if (tid == 0) s_ncand = 0u;
   __syncthreads();
   if (tid == 0) {
     for (int s = 0; s < q.n_stages && s < n_my; ++s) issue(s, stages + size_t(s) * q.stage_floats, &bars[s]);
@@ -451,14 +455,22 @@ __global__ void __launch_bounds__(kStreamThreads, 2) detect_score_fast_kernel(co
       if (lane >= o) inc += t;
     }
     const unsigned int wtot = __shfl_sync(0xffffffffu, inc, 31);
-    unsigned int wbase = 0u;
+    // Slots: the warp's keys go to a CTA-wide shared buffer (one shared-memory atomic per warp and
+    // tile) that is handed to global memory with ONE global atomic per flush; a warp never waits for
+    // a global atomic's round trip unless the buffer overflows (then the excess goes out directly).
+    unsigned int wbase = 0u, fits = 0u, gbase = 0u;
     if (wtot && q.mode != 1) {
-      if (lane == 31) wbase = atomicAdd(&q.cand_count[n], wtot);
+      if (lane == 31) wbase = atomicAdd(&s_ncand, wtot);
       wbase = __shfl_sync(0xffffffffu, wbase, 31);
+      fits = wbase >= unsigned(kKeyBuf) ? 0u : min(wtot, unsigned(kKeyBuf) - wbase);
+      if (fits < wtot) {
+        if (lane == 31) gbase = atomicAdd(&q.cand_count[n], wtot - fits);
+        gbase = __shfl_sync(0xffffffffu, gbase, 31);
+      }
     }
     const unsigned int off = inc - cnt;
     if (cnt && !(q.debug_skip & 1)) {
-      long long slot = (long long)wbase + off;
+      unsigned int rank = off;  // position inside the warp's block of wtot keys
       unsigned long long* dst = q.cand + size_t(n) * q.cand_cap;
 #pragma unroll
       for (int half = 0; half < 2; ++half) {
@@ -475,8 +487,15 @@ __global__ void __launch_bounds__(kStreamThreads, 2) detect_score_fast_kernel(co
           const unsigned long long key = (static_cast<unsigned long long>(k32) << 32) |
                                          (static_cast<unsigned long long>(k) << kPriorBits) |
                                          static_cast<unsigned long long>(p);
-          if (q.mode != 1 && slot < q.cand_cap) dst[slot] = key;
-          ++slot;
+          if (q.mode != 1) {
+            if (rank < fits) {
+              s_keys[wbase + rank] = key;
+            } else {
+              const long long slot = (long long)gbase + (rank - fits);
+              if (slot < q.cand_cap) dst[slot] = key;
+            }
+          }
+          ++rank;
           int bin = int(key >> q.shift0);
           if (bin >= q.n_bins) bin = q.n_bins - 1;
           atomicAdd(&s_hist[bin], 1u);
@@ -485,6 +504,21 @@ __global__ void __launch_bounds__(kStreamThreads, 2) detect_score_fast_kernel(co
     }
     __syncthreads();  // every thread is done with stage s
     if (tid == 0 && it + q.n_stages < n_my) issue(it + q.n_stages, stage, &bars[s]);
+    // hand the buffered keys over when the buffer fills up, the image changes or the CTA is done
+    // (s_ncand is stable here: the barrier above is behind every append of this tile)
+    const unsigned int have = min(s_ncand, unsigned(kKeyBuf));
+    if (have && (have >= unsigned(kKeyFlush) || it == n_my - 1 || cur_n != n)) {
+      if (tid == 0) s_gbase = atomicAdd(&q.cand_count[n], have);
+      __syncthreads();
+      unsigned long long* dst = q.cand + size_t(n) * q.cand_cap;
+      for (unsigned int i = tid; i < have; i += kStreamThreads) {
+        const long long slot = (long long)s_gbase + i;
+        if (slot < q.cand_cap) dst[slot] = s_keys[i];
+      }
+      __syncthreads();
+      if (tid == 0) s_ncand = 0u;
+      __syncthreads();
+    }
   }
   if (hist_n >= 0) flush_hist(hist_n);
 }
