@@ -322,11 +322,16 @@ def run_ours(args, rank, world, local_rank):
             pass
         peak = float(peaks.get("hbm_gbs", 6650.0))
         # algorithmic bytes per launch of the two streaming kernels (DESIGN.md "Kernels"):
-        #   train: logits once + priors once + GT;  eval: logits once
-        alg_match = N * P * N_CLASSES * 4 + P * 16 + T * 24
+        #   train: logits once + priors once + GT, plus - when the backward follows - the zero-fill of
+        #          the logits' gradient, which this kernel writes on the way (no separate fill kernel);
+        #   eval:  logits once
+        prefill = st.grad_scores is not None or bool(st.desc.grad_scores_prefill)
+        alg_logits = N * P * N_CLASSES * 4 + P * 16 + T * 24
+        alg_match = alg_logits + (N * P * N_CLASSES * 4 if prefill else 0)
         alg_dscore = N * P * N_CLASSES * 4
         per_kernel = {
-            "match_lse_fast_kernel": {"ms": ms_match, "bytes": alg_match},
+            "match_lse_fast_kernel": {"ms": ms_match, "bytes": alg_match, "bytes_logits_only": alg_logits,
+                                      "writes_gradient_zero_fill": prefill},
             "detect_score_fast_kernel": {"ms": ms_dscore, "bytes": alg_dscore},
         }
         for v in per_kernel.values():
@@ -337,7 +342,8 @@ def run_ours(args, rank, world, local_rank):
         achieved = per_kernel[dom]["achieved_gbs"]
         traffic = None
         try:
-            traffic = json.load(open(os.path.join(REPO, "profiles", "roofline_traffic.json"))).get(dom)
+            tj = json.load(open(os.path.join(REPO, "profiles", "roofline_traffic.json")))
+            traffic = tj.get(dom + ("+zero_fill" if dom.startswith("match_lse") and prefill else ""), tj.get(dom))
         except Exception:
             pass
         # CPU baseline beside it (bounded sample, all host cores)
@@ -361,9 +367,9 @@ def run_ours(args, rank, world, local_rank):
                        "images_per_s_detect": N * world / (ms_det * 1e-3)},
             "e2e": {"value": N * world / (ms_e2e * 1e-3), "unit": "images/s", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e},
-            # match_lse, classify, mine, zero_fill, bwd_patch, detect sample, detect score, detect nms,
-            # + the two (normally empty) fallback launches
-            "gpu_launches": 10 * args.steps,
+            # match_lse (+ gradient zero-fill), classify, mine, bwd_patch, detect sample, detect score,
+            # detect nms, + the two (normally empty) fallback launches
+            "gpu_launches": 9 * args.steps,
             "clocks": clocks,
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,

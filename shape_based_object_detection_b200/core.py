@@ -102,7 +102,11 @@ class LossState:
         g_locs = torch.empty_like(self.locs) if want_locs else None
         g_scores = None
         if want_scores:
-            g_scores = self.grad_scores if self.grad_scores is not None else torch.empty_like(self.scores)
+            # the prefilled buffer is handed over (autograd can then keep it as .grad without a copy);
+            # a second backward through the same state gets a fresh buffer and the full zero-fill
+            g_scores, self.grad_scores = self.grad_scores, None
+            if g_scores is None:
+                g_scores = torch.empty_like(self.scores)
         gl = grad_loss.to(device=dev, dtype=torch.float32).reshape(1).contiguous()
         L.check(L.lib().sbod_loss_backward(C.byref(self.desc), L.ptr(gl), L.ptr(g_locs), L.ptr(g_scores),
                                            L.stream_ptr()))
@@ -162,13 +166,14 @@ def fused_loss(spec, priors_cxcy, priors_xy, predicted_locs, predicted_scores, b
     gt = packed_gt if packed_gt is not None else pack_ground_truth(boxes, labels, dev)
     holder = holder if holder is not None else {}
     holder["group"] = group
+    # decided here: inside autograd.Function.forward grad mode is off. With CE + mining the gradient of
+    # the logits is zero except on a few rows, and the forward's streaming kernel zero-fills it on the way.
+    prefill = bool(predicted_scores.requires_grad and torch.is_grad_enabled()
+                   and spec.cls_kind in (L.CLS_CE_MINE_NONPOS, L.CLS_CE_MINE_NEG, L.CLS_CE_MINE_BATCH))
 
     def make_state(locs, scores):
         return LossState(spec, priors_cxcy, priors_xy, L.f32c(locs.detach()), L.f32c(scores.detach()), gt,
-                         anchors_xy=anchors_xy, exclude=exclude,
-                         prefill_grad=bool(scores.requires_grad and torch.is_grad_enabled()
-                                           and spec.cls_kind in (L.CLS_CE_MINE_NONPOS, L.CLS_CE_MINE_NEG,
-                                                                 L.CLS_CE_MINE_BATCH)))
+                         anchors_xy=anchors_xy, exclude=exclude, prefill_grad=prefill)
 
     holder["make_state"] = make_state
     return _FusedLossFn.apply(predicted_locs, predicted_scores, holder)
