@@ -275,7 +275,12 @@ SBOD_API size_t sbod_detect_workspace_bytes(const sbod_detect_desc* d);
 /* leading bytes of the workspace that must be zero before the first call (sbod_workspace_init) */
 SBOD_API size_t sbod_detect_workspace_zero_bytes(const sbod_detect_desc* d);
 SBOD_API int sbod_detect(const sbod_detect_desc* d, sbod_stream_t stream);
-/* Profiling / bench hook: stage 0 = score/candidate kernel only, 1 = NMS kernel only. */
+/* Stages of sbod_detect, for profiling and for callers that want to enqueue the cheap sampling pass
+ * early (e.g. on a side stream, overlapped with unrelated work):
+ *   0 = sampling pass + main score pass, 1 = NMS (+ exact fallback for flagged images),
+ *   2 = sampling pass only (reads 1/26 of the logits, writes the per-image score-cutoff histogram),
+ *   3 = main score pass only, 4 = main score pass + NMS (+ fallback), i.e. everything after stage 2.
+ * sbod_detect == stage 2 followed by stage 4 in stream order. */
 SBOD_API int sbod_detect_stage(const sbod_detect_desc* d, int stage, sbod_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------

@@ -8,9 +8,10 @@ The sub-modules mirror the reference's module paths for that path only:
 All numerics run in hand-written CUDA kernels behind the C ABI of include/sbod.h (lib/libsbod.so).
 """
 from . import _lib, core
-from .core import LossSpec, assign, detect_batched, fused_loss, pack_ground_truth, unpad_detections
+from .core import (LossSpec, assign, detect_batched, detect_begin, detect_end, fused_loss, pack_ground_truth,
+                   unpad_detections)
 
-__all__ = ["LossSpec", "assign", "detect_batched", "fused_loss", "pack_ground_truth", "unpad_detections",
+__all__ = ["LossSpec", "assign", "detect_batched", "detect_begin", "detect_end", "fused_loss", "pack_ground_truth", "unpad_detections",
            "install", "_lib"]
 
 

@@ -263,6 +263,32 @@ def detect_batched(predicted_locs, predicted_scores, min_score, max_overlap, top
     return call["outputs"]
 
 
+def detect_begin(predicted_locs, predicted_scores, min_score, max_overlap, top_k, priors_cxcy=None,
+                 act="softmax", box_type="offset", clamp_inplace=False, prior_keep=None,
+                 second_nms_thr=-1.0, pre_nms_topk=0, side_stream=None):
+    """Split-phase detect_batched: enqueue the sampling pass (the 1/26 of the tiles that fixes each
+    image's speculative score cutoff) on `side_stream` now, so that it overlaps whatever the caller runs
+    on the current stream before detect_end(). Same arguments / results as detect_batched."""
+    call = make_detect_desc(predicted_locs, predicted_scores, min_score, max_overlap, top_k, priors_cxcy, act,
+                            box_type, clamp_inplace, prior_keep, second_nms_thr, pre_nms_topk)
+    cur = torch.cuda.current_stream(predicted_scores.device)
+    side = side_stream if side_stream is not None else cur
+    if side is not cur:
+        side.wait_stream(cur)
+    with torch.cuda.stream(side):
+        L.check(L.lib().sbod_detect_stage(C.byref(call["desc"]), 2, L.stream_ptr()))
+    call["side"] = side if side is not cur else None
+    return call
+
+
+def detect_end(call):
+    """Second half of detect_begin: main score pass + NMS on the current stream."""
+    if call.get("side") is not None:
+        torch.cuda.current_stream().wait_stream(call["side"])
+    L.check(L.lib().sbod_detect_stage(C.byref(call["desc"]), 4, L.stream_ptr()))
+    return call["outputs"]
+
+
 def unpad_detections(out_boxes, out_labels, out_scores, out_counts):
     """Padded device outputs -> the reference's three python lists of per-image tensors.
     One D2H read of the N counts (the reference syncs N*(C-1) times, models/utils.py:252)."""

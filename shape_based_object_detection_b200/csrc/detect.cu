@@ -1209,7 +1209,7 @@ extern "C" int sbod_detect(const sbod_detect_desc* d, sbod_stream_t stream) {
 // passes), 2 = sampling pass only, 3 = main score pass only. Score passes must be followed by a
 // stage-1 launch before the next full sbod_detect (it consumes and cleans the workspace).
 extern "C" int sbod_detect_stage(const sbod_detect_desc* d, int stage, sbod_stream_t stream) {
-  static const int masks[4] = {1 | 4, 2, 1, 4};
-  if (stage < 0 || stage > 3) return SBOD_ERR_INVALID;
+  static const int masks[5] = {1 | 4, 2, 1, 4, 4 | 2};
+  if (stage < 0 || stage > 4) return SBOD_ERR_INVALID;
   return detect_run(d, stream, masks[stage]);
 }
