@@ -259,9 +259,9 @@ def run_ours(args, rank, world, local_rank):
         step_resident()
     # The resident step is a fixed sequence of kernel launches: replay it as one CUDA graph so that the
     # Python / launch overhead (~0.5 ms per step, more than the kernels themselves) leaves the timed loop.
-    graph = None
+    graph = g = None
     eager_step = step_resident
-    if args.graph and world == 1 and not args.overlap:
+    if args.graph and not args.overlap:
         try:
             torch.cuda.synchronize()
             g = torch.cuda.CUDAGraph()
@@ -390,8 +390,12 @@ def run_ours(args, rank, world, local_rank):
                                        "reference on the host cores, second of two passes",
                              "ms_per_image_loss_fwd_bwd": a * 1e3, "ms_per_image_detect": b * 1e3},
         }
-        print(json.dumps(line))
+        print(json.dumps(line), flush=True)
     if world > 1:
+        # the captured step holds NCCL kernel nodes: release the graph before the communicator goes away
+        step_resident = eager_step
+        graph = g = None
+        torch.cuda.synchronize()
         dist.barrier()
         dist.destroy_process_group()
 
