@@ -561,3 +561,34 @@ def test_fast_division_is_correctly_rounded(dev):
     assert not okb[2 * n + 1024:].any()                         # tiny numerators do not
     assert torch.equal(out[okb].view(torch.int32), ref[okb].view(torch.int32))
     assert torch.equal(ref.cpu(), a / b)                        # div.rn itself == torch's division
+
+
+@pytest.mark.parametrize("shape", ["ssd512_32", "retina640_6", "many_objects", "one_object"])
+def test_fused_assignment_equals_generic_kernel_at_full_size(dev, shape):
+    """The warp-specialised match role (ticket queues, staged object pairs, register keys) against the
+    generic one-thread-per-prior assignment kernel (sbod_assign, itself pinned to the oracle on small
+    cases) at sizes the CPU oracle cannot do: overlaps and object indices after the forced-match
+    override must be bit-identical, whatever the ticket geometry."""
+    import shape_based_object_detection_b200 as S
+    from shape_based_object_detection_b200 import priors as PR, synth
+    from shape_based_object_detection_b200.dataset.transforms import cxcy_to_xy
+    from shape_based_object_detection_b200.models import MultiBoxLoss512
+    name, N, gmax, gmin = {"ssd512_32": ("ssd512_canonical", 32, 100, 1), "retina640_6": ("retinanet640", 6, 100, 1),
+                           "many_objects": ("ssd512_canonical", 3, 300, 129),
+                           "one_object": ("ssd512_canonical", 8, 1, 1)}[shape]
+    pri = PR.PRIOR_TABLES[name]()
+    gen = torch.Generator().manual_seed({"ssd512_32": 41, "retina640_6": 42, "many_objects": 43, "one_object": 44}[shape])
+    bx, lb = synth.make_gt(N, gmax, 81, gen, gmin=gmin)
+    P = pri.size(0)
+    locs = torch.randn((N, P, 4), generator=gen) * 0.1
+    scores = torch.randn((N, P, 81), generator=gen)
+    pri_d = cu(pri, dev)
+    bxd, lbd = [cu(b, dev) for b in bx], [cu(l, dev) for l in lb]
+    crit = MultiBoxLoss512(pri_d, cfg("", "", 81))
+    crit(cu(locs, dev), cu(scores, dev), bxd, lbd)
+    st = crit.last["state"]
+    ov, obj, cls, neg = S.assign(bxd, lbd, cxcy_to_xy(pri_d), threshold=0.5)
+    assert torch.equal(st.obj, obj)
+    assert torch.equal(st.ov.view(torch.int32), ov.view(torch.int32))
+    cls_f, neg_f = st.targets()
+    assert torch.equal(cls_f, cls)
