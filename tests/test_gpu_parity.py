@@ -592,3 +592,20 @@ def test_fused_assignment_equals_generic_kernel_at_full_size(dev, shape):
     assert torch.equal(st.ov.view(torch.int32), ov.view(torch.int32))
     cls_f, neg_f = st.targets()
     assert torch.equal(cls_f, cls)
+
+
+def test_split_phase_detect_equals_detect_batched(dev):
+    """detect_begin (sampling pass on a side stream) + detect_end == detect_batched."""
+    import shape_based_object_detection_b200 as S
+    from shape_based_object_detection_b200 import priors as PR, synth
+    pri = PR.ssd512_canonical_priors()
+    elocs, escores = synth.make_eval_batch(pri, 4, 81, 99)
+    l_d, s_d, p_d = cu(elocs, dev), cu(escores, dev), cu(pri, dev)
+    want = S.detect_batched(l_d, s_d, 0.01, 0.45, 200, p_d)
+    side = torch.cuda.Stream(device=dev)
+    call = S.detect_begin(l_d, s_d, 0.01, 0.45, 200, p_d, side_stream=side)
+    torch.cuda._sleep(200000)  # unrelated work on the main stream in between
+    got = S.detect_end(call)
+    torch.cuda.synchronize()
+    for a, b in zip(got, want):
+        assert torch.equal(a, b)
