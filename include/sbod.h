@@ -322,6 +322,24 @@ SBOD_API int sbod_fcos_postprocess(const float* box_pred, const float* cls_pred,
                           float* out_scores, sbod_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
+ * metrics.calculate_mAP (metrics.py:8-145): VOC07 11-point interpolated average precision per class
+ * of a set of detections against the ground truth, greedy matching in descending-score order.
+ * Detections and objects are CSR by image (det_offsets / gt_offsets: [n_images + 1] int32); labels
+ * int64 in 1..n_classes-1; true_difficulties uint8; gmax = max objects per image; threshold = IoU a
+ * match must exceed (0.5); recall_thresholds11 = HOST array of the 11 recall levels as fp32
+ * (torch.arange(0, 1.1, .1)). out_ap: [n_classes-1] device floats, class c at index c-1; the mean is
+ * left to the caller. Score ties are ordered by detection index (the reference's unstable sort
+ * leaves them unspecified). All other pointers are device pointers.
+ * ---------------------------------------------------------------------------------------- */
+SBOD_API size_t sbod_map_workspace_bytes(int n_detections);
+SBOD_API int sbod_map(const float* det_boxes, const int64_t* det_labels, const float* det_scores,
+             const int32_t* det_offsets, int n_detections, const float* true_boxes,
+             const int64_t* true_labels, const uint8_t* true_difficulties, const int32_t* gt_offsets,
+             int n_objects, int n_images, int gmax, int n_classes, double threshold,
+             const float* recall_thresholds11, float* out_ap, void* workspace, size_t workspace_bytes,
+             sbod_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
  * End-to-end helpers with HOST buffers (pinned or pageable): copy the inputs to the device,
  * run the device entry point above, copy the result back. Used by bench.py's e2e leg; the
  * device scratch is the caller's (dev_arena, arena_bytes from the *_arena_bytes query).

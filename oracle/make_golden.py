@@ -13,7 +13,9 @@ import numpy as np
 import torch
 
 REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-REF = sys.argv[1] if len(sys.argv) > 1 else "/root/reference"
+_args = [a for a in sys.argv[1:] if not a.startswith("--")]
+REF = _args[0] if _args else "/root/reference"
+ONLY_MAP = "--only-map" in sys.argv  # regenerate tests/golden/map.npz and nothing else
 sys.path.insert(0, REPO)
 sys.path.insert(0, REF)
 warnings.filterwarnings("ignore")
@@ -41,9 +43,27 @@ class Stub:
     device = torch.device("cpu")
 
 
+def golden_map():
+    """metrics.calculate_mAP (metrics.py:8-145) on CPU for tests/cases.py:MAP_CASES."""
+    sys.path.insert(0, os.path.join(REPO, "tests"))
+    from cases import MAP_CASES, map_inputs  # noqa: E402
+    import metrics as ref_metrics
+    out = {}
+    for name, case in MAP_CASES.items():
+        label_map = {("background" if i == 0 else "c%d" % i): i for i in range(case["n_classes"])}
+        aps, mean_ap = ref_metrics.calculate_mAP(*map_inputs(case), case["threshold"], label_map, device="cpu")
+        out[name + "_ap"] = np.array([aps["c%d" % i] for i in range(1, case["n_classes"])], dtype=np.float32)
+        out[name + "_map"] = np.array(mean_ap, dtype=np.float64)
+    np.savez_compressed(os.path.join(OUT, "map.npz"), **out)
+    print("map ok", {k: float(v) for k, v in out.items() if k.endswith("_map")})
+
+
 def main():
     torch.manual_seed(0)
     torch.set_num_threads(4)
+    if ONLY_MAP:
+        golden_map()
+        return
     sys.path.insert(0, os.path.join(REPO, "tests"))
     from cases import LOSS_CASES, DETECT_CASES, case_priors  # noqa: E402
 
@@ -224,6 +244,7 @@ def main():
             dout[f"{name}_s{i}"] = s[i].numpy()
     np.savez_compressed(os.path.join(OUT, "detect.npz"), **dout)
     print("detect ok", {k: v.shape for k, v in dout.items() if "_s" in k})
+    golden_map()
 
 
 if __name__ == "__main__":

@@ -32,7 +32,7 @@ EXPORTS = [
     "sbod_detect_workspace_bytes", "sbod_detect_workspace_zero_bytes", "sbod_detect",
     "sbod_loss_forward_host_arena_bytes", "sbod_loss_forward_host",
     "sbod_fcos_workspace_bytes", "sbod_fcos_forward", "sbod_fcos_backward", "sbod_fcos_postprocess",
-    "sbod_selftest_div",
+    "sbod_selftest_div", "sbod_map_workspace_bytes", "sbod_map",
 ]
 
 
@@ -99,6 +99,8 @@ def _declare(lib):
         "sbod_offset2bbox": [vp, vp, vp, vp, i32, i32, vp],
         "sbod_arm_easy_negative": [vp, C.c_longlong, f32, vp, vp],
         "sbod_selftest_div": [vp, vp, C.c_longlong, vp, vp, vp, vp],
+        "sbod_map": [vp, vp, vp, vp, C.c_int, vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double,
+                     C.POINTER(C.c_float), vp, vp, C.c_size_t, vp],
         "sbod_pair_iou_fwd": [vp, vp, i32, i32, vp, vp],
         "sbod_pair_iou_bwd": [vp, vp, vp, i32, i32, vp, vp, vp],
         "sbod_smooth_l1": [vp, vp, i32, f32, vp, vp, vp],
@@ -133,6 +135,7 @@ def _declare(lib):
         "sbod_detect_workspace_zero_bytes": [C.POINTER(DetectDesc)],
         "sbod_loss_forward_host_arena_bytes": [C.POINTER(LossDesc), i32],
         "sbod_fcos_workspace_bytes": [C.POINTER(FcosDesc)],
+        "sbod_map_workspace_bytes": [i32],
     }.items():
         fn = getattr(lib, name)
         fn.argtypes = args

@@ -58,4 +58,13 @@ def install(reference_root=None):
                 patched.append(f"{mod_name}.find_jaccard_overlap")
         except Exception:
             pass
+    # metrics.calculate_mAP (train_*.py / eval.py import it by name after install): only this
+    # function of metrics.py is replaced
+    try:
+        ref_metrics = importlib.import_module("metrics")
+        if hasattr(ref_metrics, "calculate_mAP"):
+            setattr(ref_metrics, "calculate_mAP", m.calculate_mAP)
+            patched.append("metrics.calculate_mAP")
+    except Exception:
+        pass
     return patched

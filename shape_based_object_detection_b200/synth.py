@@ -50,3 +50,33 @@ def adversarial_gt(priors_xy, n_classes):
     boxes = torch.stack([degenerate, normal, normal.clone(), mid, far, tiny_a, tiny_b]).clamp_(0, 1)
     labels = (torch.arange(boxes.size(0)) % (n_classes - 1) + 1).to(torch.int64)
     return boxes, labels
+
+
+def make_map_case(n_images, n_classes, gmax, dets_per_image, seed, p_difficult=0.15, ties=False):
+    """Ground truth + detections for metrics.calculate_mAP: a share of the detections are jittered
+    copies of objects (some twice, so that duplicates and second-best matches occur), the rest random
+    boxes; the last class has no detections. ties=True adds exact score ties (their order is
+    unspecified in the reference, whose sort is unstable; the oracle and the kernels take them in the
+    order of the concatenated lists)."""
+    gen = torch.Generator().manual_seed(seed)
+    true_boxes, true_labels = make_gt(n_images, gmax, n_classes - 1, gen)   # labels 1..n_classes-2: last class unused
+    true_diff = [(torch.rand((b.size(0),), generator=gen) < p_difficult).to(torch.uint8) for b in true_boxes]
+    det_boxes, det_labels, det_scores = [], [], []
+    for i in range(n_images):
+        g = true_boxes[i].size(0)
+        k = int(torch.randint(0, dets_per_image + 1, (1,), generator=gen))
+        src = torch.randint(0, g, (k,), generator=gen)
+        near = torch.rand((k,), generator=gen) < 0.6
+        jit = (torch.rand((k, 4), generator=gen) - 0.5) * 0.08
+        b = torch.where(near[:, None], true_boxes[i][src] + jit, torch.rand((k, 4), generator=gen))
+        b = torch.cat([torch.minimum(b[:, :2], b[:, 2:]), torch.maximum(b[:, :2], b[:, 2:])], 1).clamp_(0, 1)
+        lab = torch.where(torch.rand((k,), generator=gen) < 0.8, true_labels[i][src],
+                          torch.randint(1, n_classes - 1, (k,), generator=gen))
+        sc = torch.rand((k,), generator=gen)
+        if ties and k >= 4:
+            sc[1] = sc[0]  # exact ties
+            sc[3] = sc[2]
+        det_boxes.append(b)
+        det_labels.append(lab.to(torch.int64))
+        det_scores.append(sc)
+    return det_boxes, det_labels, det_scores, true_boxes, true_labels, true_diff

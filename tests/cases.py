@@ -67,3 +67,17 @@ def operator_inputs():
     ns = torch.rand((nb.size(0),), generator=g)
     return dict(pri=pri, pri_xy=pri_xy, boxes=boxes, labels=labels, sub=sub, b1=b1, b2=b2, ppm=ppm, loc=loc,
                 lg=lg, tg=tg, pr=pr_, tgt=tg_, nb=nb, ns=ns, wts=torch.linspace(0.5, 1.5, m))
+
+
+# metrics.calculate_mAP: synth.make_map_case arguments + IoU threshold
+MAP_CASES = {
+    "small": dict(n_images=6, n_classes=7, gmax=8, dets=40, seed=5, threshold=0.5),
+    "voc_like": dict(n_images=40, n_classes=21, gmax=12, dets=120, seed=6, threshold=0.5),
+    "strict": dict(n_images=25, n_classes=11, gmax=20, dets=200, seed=7, threshold=0.75),
+    "sparse": dict(n_images=12, n_classes=81, gmax=6, dets=15, seed=8, threshold=0.5),
+}
+
+
+def map_inputs(case):
+    from shape_based_object_detection_b200 import synth
+    return synth.make_map_case(case["n_images"], case["n_classes"], case["gmax"], case["dets"], case["seed"])

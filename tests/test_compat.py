@@ -17,6 +17,7 @@ def test_install_patches_reference_modules():
         assert "models.utils.detect" in patched
         assert "operators.iou_utils.jaccard" in patched
         assert "detect_scripts.detect_tools.detect_refine" in patched
+        assert "metrics.calculate_mAP" in patched
         import models  # noqa: F401
         ref_ssd512 = sys.modules["models.SSD512"]  # (models.SSD512 the attribute is the class, models/__init__.py:1)
         from shape_based_object_detection_b200.models.SSD512 import MultiBoxLoss512

@@ -609,3 +609,48 @@ def test_split_phase_detect_equals_detect_batched(dev):
     torch.cuda.synchronize()
     for a, b in zip(got, want):
         assert torch.equal(a, b)
+
+
+# ---------------------------------------------------------------------------------------------
+# metrics.calculate_mAP: the consumer of detect()'s output
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["small", "voc_like", "strict", "sparse"])
+def test_map_matches_reference_fixture(golden, dev, name):
+    from cases import MAP_CASES, map_inputs
+    from shape_based_object_detection_b200.metrics import calculate_mAP
+    case = MAP_CASES[name]
+    label_map = {("background" if i == 0 else "c%d" % i): i for i in range(case["n_classes"])}
+    args = [[cu(t, dev) for t in lst] for lst in map_inputs(case)]
+    aps, mean_ap = calculate_mAP(*args, case["threshold"], label_map, device="cuda:0")
+    got = torch.tensor([aps["c%d" % i] for i in range(1, case["n_classes"])], dtype=torch.float32)
+    want = T(golden["map"][name + "_ap"])
+    assert torch.allclose(got, want, rtol=1e-6, atol=1e-7), (got - want).abs().max()
+    assert abs(mean_ap - float(golden["map"][name + "_map"])) <= 1e-6
+
+
+def test_map_large_and_edge_cases(dev):
+    """Against the oracle at a size the Python reference needs minutes for, plus: no detections at all,
+    images without objects, a class that only has difficult objects."""
+    from oracle import box_pipeline as O
+    from shape_based_object_detection_b200 import synth
+    from shape_based_object_detection_b200.metrics import calculate_mAP
+    n_classes = 21
+    label_map = {("background" if i == 0 else "c%d" % i): i for i in range(n_classes)}
+    case = list(synth.make_map_case(150, n_classes, 15, 200, 77, ties=True))
+    case[3][5] = torch.zeros((0, 4))                      # an image without objects (its detections are FPs)
+    case[4][5] = torch.zeros((0,), dtype=torch.int64)
+    case[5][5] = torch.zeros((0,), dtype=torch.uint8)
+    for i in range(len(case[4])):                         # class 3 only has difficult objects
+        case[5][i] = torch.where(case[4][i] == 3, torch.ones_like(case[5][i]), case[5][i])
+    want_ap, want_map = O.calculate_mAP(*case, 0.5, n_classes)
+    aps, mean_ap = calculate_mAP(*[[cu(t, dev) for t in lst] for lst in case], 0.5, label_map)
+    got = torch.tensor([aps["c%d" % i] for i in range(1, n_classes)], dtype=torch.float32)
+    assert torch.allclose(got, want_ap, rtol=1e-6, atol=1e-7), (got - want_ap).abs().max()
+    assert abs(mean_ap - want_map) <= 1e-6
+    assert aps["c3"] == 0.0 and aps["c20"] == 0.0
+    # no detections
+    empty = [[torch.zeros((0, 4), device=dev)] * 3, [torch.zeros((0,), dtype=torch.int64, device=dev)] * 3,
+             [torch.zeros((0,), device=dev)] * 3]
+    gt = [[cu(t, dev) for t in lst[:3]] for lst in case[3:]]
+    aps, mean_ap = calculate_mAP(*empty, *gt, 0.5, label_map)
+    assert mean_ap == 0.0 and all(v == 0.0 for v in aps.values())

@@ -187,3 +187,16 @@ def test_detect_matches_reference(golden, name):
         assert torch.equal(l[i], T(G[f"{name}_l{i}"]).long())
         assert torch.equal(s[i], T(G[f"{name}_s{i}"]))
         assert torch.equal(b[i], T(G[f"{name}_b{i}"]))
+
+
+# ---------------------------------------------------------------------------------------------
+# metrics.calculate_mAP
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["small", "voc_like", "strict", "sparse"])
+def test_oracle_map_matches_reference(golden, name):
+    from cases import MAP_CASES, map_inputs
+    from oracle import box_pipeline as O
+    case = MAP_CASES[name]
+    ap, mean_ap = O.calculate_mAP(*map_inputs(case), case["threshold"], case["n_classes"])
+    assert torch.equal(ap, T(golden["map"][name + "_ap"]))
+    assert mean_ap == float(golden["map"][name + "_map"])
