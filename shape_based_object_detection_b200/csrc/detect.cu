@@ -536,6 +536,8 @@ SBOD_DEVINL bool overlaps(const float4 a, const float4 b, float thr) {
   return iou_plain_rn(a, aa, b, ab) > thr;
 }
 
+constexpr int kClsGrouped = 128;  // up to this many classes the chunk is grouped by class in one pass
+
 struct NmsSmem {
   unsigned int hist[kMaxBins];
   unsigned long long ckey[kChunk];
@@ -547,6 +549,7 @@ struct NmsSmem {
   uint16_t big_seg0[kChunk / kBigSeg + 1];  // large class segments of the round (start, length)
   uint16_t big_len[kChunk / kBigSeg + 1];
   int misc[16];
+  uint16_t wcnt[(kChunk / 32) * (kClsGrouped + 1)];  // per warp and class: entries of the class in the warp's 32 chunk positions
 };
 
 // radix levels below the level-0 digit: 11 bits each
@@ -744,6 +747,26 @@ __global__ void __launch_bounds__(kNmsThreads) detect_nms_kernel(const DetParams
     __syncthreads();
     // cls_off[c] now holds the number of chunk entries with class < c ... (entry c+1 counted class c),
     // i.e. segment of class c is [cls_off[c], cls_off[c+1]).
+    // Chunk positions grouped by class, key order inside a class: position = segment start + entries
+    // of the class in earlier warps + rank among the warp's own peers (match_any), one pass for all
+    // classes instead of one scan of the chunk per class.
+    const bool grouped = q.C <= kClsGrouped;
+    if (grouped) {
+      const int cw = q.C + 1;
+      for (int i = tid; i < (kChunk / 32) * cw; i += kNmsThreads) S.wcnt[i] = 0;
+      __syncthreads();
+      const int c = tid < m ? key_class(S.ckey[tid]) : q.C;  // padding joins a dummy class
+      const unsigned peers = __match_any_sync(0xffffffffu, c);
+      const int r = __popc(peers & ((1u << lane) - 1u));
+      if (r == 0) S.wcnt[wid * cw + c] = uint16_t(__popc(peers));
+      __syncthreads();
+      if (tid < m) {
+        unsigned int before = 0;
+        for (int w2 = 0; w2 < wid; ++w2) before += S.wcnt[w2 * cw + c];
+        S.cidx[cls_off[c] + before + r] = uint16_t(tid);
+      }
+      // (visible to the class warps after the barrier that ends stage 1a)
+    }
 
     // ---- stage 1a: every candidate against the boxes kept in EARLIER rounds, one thread each ----
     // (parallel over the whole CTA whatever the number of classes; flag 3 = already suppressed)
@@ -769,16 +792,17 @@ __global__ void __launch_bounds__(kNmsThreads) detect_nms_kernel(const DetParams
       if (c >= q.C) break;
       const unsigned int seg0 = cls_off[c], seg1 = cls_off[c + 1];
       if (seg1 == seg0) continue;
-      // fill the segment with this class's chunk positions in key order
-      unsigned int w = seg0;
-      for (int base = 0; base < m; base += 32) {
-        const int i = base + lane;
-        const bool mine = i < m && key_class(S.ckey[i]) == c;
-        const unsigned bal = __ballot_sync(0xffffffffu, mine);
-        if (mine) S.cidx[w + __popc(bal & ((1u << lane) - 1u))] = uint16_t(i);
-        w += __popc(bal);
+      if (!grouped) {  // many classes: fill the segment with this class's chunk positions in key order
+        unsigned int w = seg0;
+        for (int base = 0; base < m; base += 32) {
+          const int i = base + lane;
+          const bool mine = i < m && key_class(S.ckey[i]) == c;
+          const unsigned bal = __ballot_sync(0xffffffffu, mine);
+          if (mine) S.cidx[w + __popc(bal & ((1u << lane) - 1u))] = uint16_t(i);
+          w += __popc(bal);
+        }
+        __syncwarp();
       }
-      __syncwarp();
       const unsigned int seen = g_seen[c];  // candidates of this class consumed by earlier rounds
       if (lane == 0) g_seen[c] = seen + (seg1 - seg0);
       unsigned int lim = seg1;               // pre-NMS per-class cap: later candidates are dropped
