@@ -537,6 +537,7 @@ SBOD_DEVINL bool overlaps(const float4 a, const float4 b, float thr) {
 }
 
 constexpr int kClsGrouped = 128;  // up to this many classes the chunk is grouped by class in one pass
+constexpr int kKeptGrouped = 1024; // ... and the kept list too, while it is not longer than this
 
 struct NmsSmem {
   unsigned int hist[kMaxBins];
@@ -550,6 +551,8 @@ struct NmsSmem {
   uint16_t big_len[kChunk / kBigSeg + 1];
   int misc[16];
   uint16_t wcnt[(kChunk / 32) * (kClsGrouped + 1)];  // per warp and class: entries of the class in the warp's 32 chunk positions
+  unsigned int kc_off[kClsGrouped + 3];  // kept list grouped by class: segment bounds ...
+  uint16_t kc_idx[kKeptGrouped];         // ... and kept-list positions
 };
 
 // radix levels below the level-0 digit: 11 bits each
@@ -677,7 +680,8 @@ __global__ void __launch_bounds__(kNmsThreads) detect_nms_kernel(const DetParams
     if (tid == 0) S.misc[3] = 0;
     __syncthreads();
     // eight independent 8-byte loads in flight per thread (the list lives in L2 / HBM)
-    for (long long i0 = tid; i0 < total; i0 += 8LL * kNmsThreads) {
+    for (long long r0 = 0; r0 < total; r0 += 8LL * kNmsThreads) {  // CTA-uniform trip count (ballots inside)
+      const long long i0 = r0 + tid;
       unsigned long long kk[8];
 #pragma unroll
       for (int u = 0; u < 8; ++u) {
@@ -687,9 +691,14 @@ __global__ void __launch_bounds__(kNmsThreads) detect_nms_kernel(const DetParams
 #pragma unroll
       for (int u = 0; u < 8; ++u) {
         const unsigned long long k = kk[u];
-        if (k != ~0ull && k >= lo_key && (k < hi_key || hi_key == ~0ull)) {
-          const int slot = atomicAdd(&S.misc[3], 1);
-          if (slot < kChunk) S.ckey[slot] = k;
+        const bool in = k != ~0ull && k >= lo_key && (k < hi_key || hi_key == ~0ull);
+        const unsigned bal = __ballot_sync(0xffffffffu, in);  // (the loop bounds are warp-uniform)
+        if (bal) {
+          int base = 0;
+          if (lane == __ffs(bal) - 1) base = atomicAdd(&S.misc[3], __popc(bal));
+          base = __shfl_sync(0xffffffffu, base, __ffs(bal) - 1);
+          const int slot = base + __popc(bal & ((1u << lane) - 1u));
+          if (in && slot < kChunk) S.ckey[slot] = k;
         }
       }
     }
@@ -701,18 +710,35 @@ __global__ void __launch_bounds__(kNmsThreads) detect_nms_kernel(const DetParams
       continue;
     }
     // ---- sort by key (bitonic, padded with ~0) ----------------------------------------------
-    if (tid >= m) S.ckey[tid] = ~0ull;
-    __syncthreads();
-    for (int k2 = 2; k2 <= kChunk; k2 <<= 1) {
-      for (int j = k2 >> 1; j > 0; j >>= 1) {
-        const int ixj = tid ^ j;
-        if (ixj > tid) {
-          const unsigned long long a = S.ckey[tid], b = S.ckey[ixj];
-          const bool up_dir = (tid & k2) == 0;
-          if ((a > b) == up_dir) { S.ckey[tid] = b; S.ckey[ixj] = a; }
+    // Each thread keeps its element in a register; partners less than 32 apart are reached by
+    // shuffles (40 of the 55 steps, no block barrier), the others through shared memory, alternating
+    // between ckey and the not yet used cbox array so that one barrier per step suffices.
+    {
+      unsigned long long v = tid < m ? S.ckey[tid] : ~0ull;
+      unsigned long long* bufA = S.ckey;
+      unsigned long long* bufB = reinterpret_cast<unsigned long long*>(S.cbox);
+      __syncthreads();
+      for (int k2 = 2; k2 <= kChunk; k2 <<= 1) {
+        for (int j = k2 >> 1; j > 0; j >>= 1) {
+          unsigned long long o;
+          if (j >= 32) {
+            bufA[tid] = v;
+            __syncthreads();
+            o = bufA[tid ^ j];
+            unsigned long long* t = bufA;
+            bufA = bufB;
+            bufB = t;
+          } else {
+            o = __shfl_xor_sync(0xffffffffu, v, j);
+          }
+          const bool up_dir = (tid & k2) == 0, lower = (tid & j) == 0;
+          const unsigned long long mn = v < o ? v : o, mx = v < o ? o : v;
+          v = (lower == up_dir) ? mn : mx;
         }
-        __syncthreads();
       }
+      __syncthreads();  // every read of the exchange buffers is done
+      S.ckey[tid] = v;
+      __syncthreads();
     }
     // ---- decode boxes, group by class -------------------------------------------------------
     for (int c = tid; c <= q.C; c += kNmsThreads) cls_off[c] = 0u;
@@ -769,8 +795,46 @@ __global__ void __launch_bounds__(kNmsThreads) detect_nms_kernel(const DetParams
     }
 
     // ---- stage 1a: every candidate against the boxes kept in EARLIER rounds, one thread each ----
-    // (parallel over the whole CTA whatever the number of classes; flag 3 = already suppressed)
-    if (tid < m && kept_n > 0) {
+    // (parallel over the whole CTA whatever the number of classes; flag 3 = already suppressed).
+    // With few classes the kept list is first grouped by class (counting sort in shared memory), so a
+    // candidate only meets the kept boxes of its own class instead of walking the whole list.
+    if (grouped && kept_n > 0 && kept_n <= kKeptGrouped) {
+      for (int c = tid; c <= q.C + 1; c += kNmsThreads) S.kc_off[c] = 0;
+      __syncthreads();
+      for (int i = tid; i < kept_n; i += kNmsThreads) atomicAdd(&S.kc_off[key_class(kkey[i]) + 2], 1u);
+      __syncthreads();
+      if (wid == 0) {  // kc_off[c + 1] = kept boxes with class < c (filled as a cursor below), C + 2 entries
+        unsigned int carry = 0;
+        for (int base = 0; base <= q.C + 1; base += 32) {
+          const int c = base + lane;
+          const unsigned int v = c <= q.C + 1 ? S.kc_off[c] : 0u;
+          unsigned int inc = v;
+#pragma unroll
+          for (int o = 1; o < 32; o <<= 1) {
+            const unsigned int t = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += t;
+          }
+          if (c <= q.C + 1) S.kc_off[c] = carry + inc;
+          carry += __shfl_sync(0xffffffffu, inc, 31);
+        }
+      }
+      __syncthreads();
+      // now kc_off[c + 1] = start of class c; scatter advances it to the end of class c = start of c + 1,
+      // so afterwards class c occupies [kc_off[c], kc_off[c + 1])
+      for (int i = tid; i < kept_n; i += kNmsThreads) {
+        const unsigned int at = atomicAdd(&S.kc_off[key_class(kkey[i]) + 1], 1u);
+        S.kc_idx[at] = uint16_t(i);
+      }
+      __syncthreads();
+      if (tid < m) {
+        const int c = key_class(S.ckey[tid]);
+        const float4 be = S.cbox[tid];
+        bool sup = false;
+        for (unsigned int r = S.kc_off[c]; r < S.kc_off[c + 1] && !sup; ++r)
+          if (overlaps(kbox[S.kc_idx[r]], be, q.max_overlap)) sup = true;
+        if (sup) S.cflag[tid] = 3;
+      }
+    } else if (tid < m && kept_n > 0) {
       const int c = key_class(S.ckey[tid]);
       const float4 be = S.cbox[tid];
       bool sup = false;
