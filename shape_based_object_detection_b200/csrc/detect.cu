@@ -882,6 +882,32 @@ __global__ void __launch_bounds__(kNmsThreads) detect_nms_kernel(const DetParams
         }
         continue;
       }
+      if (lim - seg0 <= 32u) {
+        // up to 32 candidates (the usual case): lane i owns candidate i. All pairwise tests run in
+        // parallel - bit j of sup_by says "candidate j (earlier in key order) overlaps me" - and the
+        // greedy order is then resolved on the bit masks alone.
+        const int L = int(lim - seg0);
+        const int e = lane < L ? int(S.cidx[seg0 + lane]) : -1;
+        const bool alive = e >= 0 && S.cflag[e] != 3;  // 3: suppressed by a box of an earlier round
+        const float4 b = e >= 0 ? S.cbox[e] : make_float4(0.f, 0.f, 0.f, 0.f);
+        unsigned int sup_by = 0u;
+        for (int j = 0; j + 1 < L; ++j) {
+          float4 bj;
+          bj.x = __shfl_sync(0xffffffffu, b.x, j);
+          bj.y = __shfl_sync(0xffffffffu, b.y, j);
+          bj.z = __shfl_sync(0xffffffffu, b.z, j);
+          bj.w = __shfl_sync(0xffffffffu, b.w, j);
+          if (lane > j && lane < L && overlaps(bj, b, q.max_overlap)) sup_by |= 1u << j;
+        }
+        const unsigned int alive_mask = __ballot_sync(0xffffffffu, alive);
+        unsigned int kept = 0u;
+        for (int i = 0; i < L; ++i) {
+          const unsigned int mi = __shfl_sync(0xffffffffu, sup_by, i);
+          if (((alive_mask >> i) & 1u) && !(mi & kept)) kept |= 1u << i;
+        }
+        if (alive && ((kept >> lane) & 1u)) S.cflag[e] = 1;
+        continue;
+      }
       unsigned int nnew = 0;
       for (unsigned int r = seg0; r < lim; ++r) {
         const int e = S.cidx[r];
