@@ -601,8 +601,16 @@ __global__ void __launch_bounds__(kNmsThreads) detect_nms_kernel(const DetParams
   bool exhausted = total == 0;
   const int stop_at = q.top_k + 1;
 
+  // The first round only takes about twice as many candidates as boxes are wanted (a power of two):
+  // when suppression is moderate that is enough, and sorting / decoding / grouping a short chunk is
+  // cheaper; if it is not enough the following rounds take full chunks.
+  int chunk_cap = kChunk;
+  if (!two_stage) {
+    chunk_cap = 256;
+    while (chunk_cap < 2 * stop_at && chunk_cap < kChunk) chunk_cap <<= 1;
+  }
   while (!exhausted && (two_stage ? kept2_n : kept_n) < stop_at && !status) {
-    // ---- choose [lo_key, hi_key) holding at most kChunk candidates -------------------------
+    // ---- choose [lo_key, hi_key) holding at most chunk_cap candidates ----------------------
     int level = 0;
     while (level_shift(q, level) > 0 && (lo_key & ((1ull << level_shift(q, level)) - 1ull)) != 0ull)
       ++level;
@@ -647,8 +655,8 @@ __global__ void __launch_bounds__(kNmsThreads) detect_nms_kernel(const DetParams
         __syncthreads();
         unsigned int before = inc - (h0 + h1);
         for (int w = 0; w < wid; ++w) before += S.wscan[w];
-        if (h0 && before + h0 > unsigned(kChunk)) atomicMin(&S.misc[0], b0);
-        else if (h1 && before + h0 + h1 > unsigned(kChunk)) atomicMin(&S.misc[0], b1);
+        if (h0 && before + h0 > unsigned(chunk_cap)) atomicMin(&S.misc[0], b0);
+        else if (h1 && before + h0 + h1 > unsigned(chunk_cap)) atomicMin(&S.misc[0], b1);
         if (h0) atomicMin(&S.misc[4], b0);
         else if (h1) atomicMin(&S.misc[4], b1);
         __syncthreads();
@@ -698,13 +706,14 @@ __global__ void __launch_bounds__(kNmsThreads) detect_nms_kernel(const DetParams
           if (lane == __ffs(bal) - 1) base = atomicAdd(&S.misc[3], __popc(bal));
           base = __shfl_sync(0xffffffffu, base, __ffs(bal) - 1);
           const int slot = base + __popc(bal & ((1u << lane) - 1u));
-          if (in && slot < kChunk) S.ckey[slot] = k;
+          if (in && slot < chunk_cap) S.ckey[slot] = k;
         }
       }
     }
     __syncthreads();
-    const int m = min(S.misc[3], kChunk);
+    const int m = min(S.misc[3], chunk_cap);
     lo_key = hi_key;
+    chunk_cap = kChunk;  // later rounds take full chunks
     if (m == 0) {
       __syncthreads();
       continue;
@@ -718,7 +727,9 @@ __global__ void __launch_bounds__(kNmsThreads) detect_nms_kernel(const DetParams
       unsigned long long* bufA = S.ckey;
       unsigned long long* bufB = reinterpret_cast<unsigned long long*>(S.cbox);
       __syncthreads();
-      for (int k2 = 2; k2 <= kChunk; k2 <<= 1) {
+      int sort_n = 2;
+      while (sort_n < m) sort_n <<= 1;
+      for (int k2 = 2; k2 <= sort_n; k2 <<= 1) {
         for (int j = k2 >> 1; j > 0; j >>= 1) {
           unsigned long long o;
           if (j >= 32) {
