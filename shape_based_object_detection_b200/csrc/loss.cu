@@ -1315,7 +1315,7 @@ __global__ void __launch_bounds__(128) zero_fill_kernel(float* __restrict__ dst,
 }
 
 struct BwdParams;
-__global__ void __launch_bounds__(256) bwd_patch_kernel(const LossParams q, const float* __restrict__ grad_loss,
+__global__ void __launch_bounds__(256, 4) bwd_patch_kernel(const LossParams q, const float* __restrict__ grad_loss,
                                                         float* __restrict__ grad_locs,
                                                         float* __restrict__ grad_scores) {
   const int lane = threadIdx.x & 31;
@@ -1390,12 +1390,16 @@ __global__ void __launch_bounds__(256) bwd_patch_kernel(const LossParams q, cons
         for (int c = 0; c < 4; ++c) {
           const int k = 32 * c + lane;
 #pragma unroll
-          for (int u = 0; u < 4; ++u)
-            x[c][u] = (src[u] >= 0 && k < q.C) ? ld_stream_f32(q.scores + (base + src[u]) * q.C + k) : 0.f;
+          for (int u = 0; u < 4; ++u) {
+            x[c][u] = 0.f;
+            if (32 * c < q.C && src[u] >= 0 && k < q.C)  // (first test warp-uniform: C = 81 uses three chunks)
+              x[c][u] = ld_stream_f32(q.scores + (base + src[u]) * q.C + k);
+          }
         }
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
           const int k = 32 * c + lane;
+          if (32 * c >= q.C) break;
 #pragma unroll
           for (int u = 0; u < 4; ++u)
             if (src[u] >= 0 && k < q.C)
