@@ -922,6 +922,8 @@ __global__ void __launch_bounds__(kClsThreads) classify_kernel(const LossParams 
   __shared__ double s_red[34];
   __shared__ int s_warp_tot[kClsThreads / 32];
   __shared__ int s_carry;
+  __shared__ uint16_t s_lidx[kClsPriors], s_lcls[kClsPriors];  // rows with a foreground class: local index, class
+  __shared__ uint16_t s_cnt[(kClsPriors / kClsThreads) * (kClsThreads / 32)];
 
   const int n = blockIdx.y, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int pb = blockIdx.x * kClsPriors;
@@ -980,47 +982,83 @@ __global__ void __launch_bounds__(kClsThreads) classify_kernel(const LossParams 
   }
   __syncthreads();
 
+  // Phase A, every prior: class, selection bits, mining candidate. Rows with a foreground class
+  // (2-3 % of the priors) are only recorded: their true-class CE and box term need dependent loads and
+  // ~200 instructions, which would otherwise run divergently in more than half of the warps.
+  // Phase B walks the recorded rows densely. The list order is deterministic (ballot ranks + a fixed
+  // order of the per-warp counts), so the per-thread partial sums are reproducible run to run.
+  constexpr int kPer = kClsPriors / kClsThreads;
   double a_loc = 0.0, a_pos = 0.0, a_neg = 0.0;
   int npos = 0;
+  int rec[kPer], rrank[kPer];  // recorded class (bit 15: positive) / rank inside the warp's ballot
 #pragma unroll
-  for (int u = 0; u < kClsPriors / kClsThreads; ++u) {
+  for (int u = 0; u < kPer; ++u) {
     const int p = pb + u * kClsThreads + tid;
-    if (p >= q.P) continue;
-    const float ov = s_ov[u * kClsThreads + tid];
-    const int obj = s_obj[u * kClsThreads + tid];
-    float ce = q.ce[base + p];
-    const bool ex = q.exclude ? q.exclude[base + p] != 0 : false;
-    int64_t cls = 0;
-    if (!(ov < q.thr_pos) && G > 0) cls = map_label(q, q.gt_labels[g0 + obj]);
-    const bool pos = cls > 0 && !ex;
-    const bool isneg = ov < q.thr_neg;
-    uint8_t selbits = 0;
-    float v = -1.f;
-    if (cls > 0) {  // CE against the true class (the streamed value is the background CE)
-      const int c = min(int(cls), q.C - 1);
-      ce = q.lse[base + p] - q.scores[(base + p) * q.C + c];
-      q.ce[base + p] = ce;
-    }
-    if (pos) {
-      selbits = 1;
-      ++npos;
-      a_pos += focal ? double(focal_fg(q, ce)) : double(ce);
-      const float4 pred = reinterpret_cast<const float4*>(q.locs)[base + p];
-      const LocTerm lt = loc_term<false>(q, pred, prior_cxcy_of(q, n, p), q.gt_boxes[g0 + obj]);
-      a_loc += double(lt.loss);
-    }
-    if (focal) {
-      if (isneg && !pos) {  // target class is 0 there (thr_neg < thr_pos)
-        selbits |= 2;
-        a_neg += double(focal_bg(q, ce));
+    rec[u] = 0;
+    if (p < q.P) {
+      const float ov = s_ov[u * kClsThreads + tid];
+      const int obj = s_obj[u * kClsThreads + tid];
+      const float ce = q.ce[base + p];  // background CE from the streaming kernel
+      const bool ex = q.exclude ? q.exclude[base + p] != 0 : false;
+      int64_t cls = 0;
+      if (!(ov < q.thr_pos) && G > 0) cls = map_label(q, q.gt_labels[g0 + obj]);
+      const bool pos = cls > 0 && !ex;
+      const bool isneg = ov < q.thr_neg;
+      uint8_t selbits = pos ? 1 : 0;
+      float v = -1.f;
+      if (cls > 0) {
+        rec[u] = min(int(cls), q.C - 1) | (pos ? 0x8000 : 0);  // C <= 4096 elsewhere; classes fit 15 bits
+      } else if (focal) {
+        if (isneg) {  // target class is 0 there (thr_neg < thr_pos)
+          selbits |= 2;
+          a_neg += double(focal_bg(q, ce));
+        }
+      } else if (q.cls_kind == SBOD_CLS_CE_MINE_NONPOS) {
+        if (!ex) v = ce;
+      } else {  // MINE_NEG, MINE_BATCH: only true_neg == -1 rows are candidates
+        if (isneg) v = ce;
       }
-    } else if (q.cls_kind == SBOD_CLS_CE_MINE_NONPOS) {
-      if (!pos && !ex) v = ce;
-    } else {  // MINE_NEG, MINE_BATCH: only true_neg == -1 rows are candidates
-      if (isneg && !pos) v = ce;
+      q.sel[base + p] = selbits;
+      q.cand[base + p] = v;
     }
-    q.sel[base + p] = selbits;
-    q.cand[base + p] = v;
+    const unsigned bal = __ballot_sync(0xffffffffu, rec[u] != 0);
+    rrank[u] = __popc(bal & ((1u << lane) - 1u));
+    if (lane == 0) s_cnt[u * (kClsThreads / 32) + wid] = uint16_t(__popc(bal));
+  }
+  __syncthreads();
+  {
+    int before = 0;
+#pragma unroll
+    for (int u = 0; u < kPer; ++u) {
+      // entries of earlier (u, warp) pairs in the fixed order u-major, warp-minor
+      int mine_base = before;
+      for (int w2 = 0; w2 < kClsThreads / 32; ++w2) {
+        const int c2 = s_cnt[u * (kClsThreads / 32) + w2];
+        if (w2 < wid) mine_base += c2;
+        before += c2;
+      }
+      if (rec[u]) {
+        s_lidx[mine_base + rrank[u]] = uint16_t(u * kClsThreads + tid);
+        s_lcls[mine_base + rrank[u]] = uint16_t(rec[u]);
+      }
+    }
+    // `before` is now the length of the list (same value in every thread)
+    __syncthreads();
+    for (int i = tid; i < before; i += kClsThreads) {
+      const int local = s_lidx[i];
+      const int p = pb + local;
+      const int c = s_lcls[i] & 0x7fff;
+      const bool pos = (s_lcls[i] & 0x8000) != 0;
+      const float ce = q.lse[base + p] - q.scores[(base + p) * q.C + c];  // CE against the true class
+      q.ce[base + p] = ce;
+      if (pos) {
+        ++npos;
+        a_pos += focal ? double(focal_fg(q, ce)) : double(ce);
+        const float4 pred = reinterpret_cast<const float4*>(q.locs)[base + p];
+        const LocTerm lt = loc_term<false>(q, pred, prior_cxcy_of(q, n, p), q.gt_boxes[g0 + s_obj[local]]);
+        a_loc += double(lt.loss);
+      }
+    }
   }
   double tot[4] = {a_loc, a_pos, a_neg, double(npos)};
   block_sum4_to_thread0(tot, s_red4);
