@@ -780,14 +780,20 @@ struct SelectResult {
 
 __device__ SelectResult topk_sum(const float* __restrict__ vals, int n, long long k_want,
                                  unsigned int* s_hist /*[kBins]*/, double* s_red /*[34]*/,
-                                 int* s_misc /*[8]*/) {
+                                 int* s_misc /*[8]*/, long long n_cand_known = -1 /* < 0: count here */,
+                                 uint8_t* __restrict__ sel_out = nullptr /* marks the selection in the same pass */) {
   const int tid = threadIdx.x, nt = blockDim.x;
   SelectResult r;
   r.sum = 0.0; r.thr_bits = 0; r.take_ties = 0; r.n_ties = 0; r.k_eff = 0;
-  // number of candidates
-  int cnt = 0;
-  for (int i = tid; i < n; i += nt) cnt += vals[i] >= 0.f ? 1 : 0;
-  const int n_cand = int(block_sum(double(cnt), s_red) + 0.5);
+  // number of candidates (classify_kernel already counted them per block when it wrote them)
+  int n_cand;
+  if (n_cand_known >= 0) {
+    n_cand = int(n_cand_known);
+  } else {
+    int cnt = 0;
+    for (int i = tid; i < n; i += nt) cnt += vals[i] >= 0.f ? 1 : 0;
+    n_cand = int(block_sum(double(cnt), s_red) + 0.5);
+  }
   long long k = k_want < (long long)n_cand ? k_want : (long long)n_cand;
   r.k_eff = int(k);
   if (k <= 0) return r;
@@ -857,12 +863,26 @@ __device__ SelectResult topk_sum(const float* __restrict__ vals, int n, long lon
   r.thr_bits = prefix;
   r.take_ties = remaining;
   const float thr = __uint_as_float(prefix);
+  const bool all_ties = r.take_ties >= r.n_ties;
   double acc = 0.0;
   for (int i = tid; i < n; i += nt) {
     const float v = vals[i];
     if (v > thr) acc += double(v);
+    // selected negatives: v > thr plus (normally all) the candidates equal to thr; a candidate is
+    // never a positive, so the flag byte is written without reading it
+    if (sel_out && (v > thr || (all_ties && v == thr))) sel_out[i] = 2;
   }
   r.sum = block_sum(acc, s_red) + double(remaining) * double(thr);
+  if (sel_out && !all_ties) {  // rare: pick the ties by ascending index (deterministic)
+    if (tid == 0) {
+      int left = r.take_ties;
+      for (int i = 0; i < n && left > 0; ++i)
+        if (vals[i] == thr) {
+          sel_out[i] = 2;
+          --left;
+        }
+    }
+  }
   return r;
 }
 
@@ -1018,6 +1038,7 @@ __global__ void __launch_bounds__(kClsThreads) classify_kernel(const LossParams 
       } else {  // MINE_NEG, MINE_BATCH: only true_neg == -1 rows are candidates
         if (isneg) v = ce;
       }
+      if (!focal && v >= 0.f) a_neg += 1.0;  // mining modes: this partial counts the candidates (see mine_kernel)
       q.sel[base + p] = selbits;
       q.cand[base + p] = v;
     }
@@ -1109,8 +1130,8 @@ __global__ void __launch_bounds__(kMineThreads) mine_kernel(const LossParams q) 
     t_neg = 0.0;  // filled by mine_batch_kernel
   } else {
     const long long k = (long long)(q.ratio) * (long long)(t_npos + 0.5);
-    const SelectResult r = topk_sum(vals, q.P, k, s_hist, s_red, s_misc);
-    mark_selected(vals, q.sel + base, q.P, r, s_misc);
+    // the third block partial holds the number of candidates in the mining modes (NaN CEs are not candidates)
+    const SelectResult r = topk_sum(vals, q.P, k, s_hist, s_red, s_misc, (long long)(s_tot[2] + 0.5), q.sel + base);
     t_neg = r.sum;
   }
   if (tid == 0) {
