@@ -729,22 +729,25 @@ __global__ void __launch_bounds__(kNmsThreads) detect_nms_kernel(const DetParams
       __syncthreads();
       int sort_n = 2;
       while (sort_n < m) sort_n <<= 1;
+      const bool in_net = (tid & ~31) < sort_n;  // warps beyond the network only keep the barriers company
       for (int k2 = 2; k2 <= sort_n; k2 <<= 1) {
         for (int j = k2 >> 1; j > 0; j >>= 1) {
-          unsigned long long o;
+          unsigned long long o = 0ull;
           if (j >= 32) {
-            bufA[tid] = v;
+            if (in_net) bufA[tid] = v;
             __syncthreads();
-            o = bufA[tid ^ j];
+            if (in_net) o = bufA[tid ^ j];
             unsigned long long* t = bufA;
             bufA = bufB;
             bufB = t;
-          } else {
+          } else if (in_net) {
             o = __shfl_xor_sync(0xffffffffu, v, j);
           }
-          const bool up_dir = (tid & k2) == 0, lower = (tid & j) == 0;
-          const unsigned long long mn = v < o ? v : o, mx = v < o ? o : v;
-          v = (lower == up_dir) ? mn : mx;
+          if (in_net) {
+            const bool up_dir = (tid & k2) == 0, lower = (tid & j) == 0;
+            const unsigned long long mn = v < o ? v : o, mx = v < o ? o : v;
+            v = (lower == up_dir) ? mn : mx;
+          }
         }
       }
       __syncthreads();  // every read of the exchange buffers is done
