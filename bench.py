@@ -10,6 +10,9 @@ same 32 images-per-GPU size. value = images/sec of the whole job with inputs res
 e2e = the same through the public Python API with pinned HOST buffers (H2D of every input and D2H
 of the results inside the timed region). Multi-GPU: one process per GPU (torchrun), batch sharded
 by image, the only exchange is one all-reduce of four loss sums per step ("weak" scaling).
+The resident step is replayed as one CUDA graph (--no-graph: eager launches) with the train half and
+the eval half on two streams inside it (--no-overlap: one stream); both halves, all nine kernel
+launches and the all-reduce are inside the timed region either way.
 
 --impl reference times the CPU oracle port of the reference (oracle/box_pipeline.py — the reference
 is pure Python/PyTorch and is not present on the GPU box) on the host cores, on a bounded sample.
