@@ -304,6 +304,7 @@ __device__ void compute_cutoff(const DetParams& q, int n, unsigned int* scratch,
 // row sum is >= 1); only those few are re-evaluated exactly and emitted. The per-image histogram
 // of the key's top digit is accumulated in shared memory and flushed once per image.
 // ------------------------------------------------------------------------------------------
+template <int kC>  // kC > 0: compile-time class count (unrolled softmax passes)
 __global__ void __launch_bounds__(kStreamThreads, 2) detect_score_fast_kernel(const DetParams q) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   float* stages = reinterpret_cast<float*>(smem_raw);
@@ -314,7 +315,7 @@ __global__ void __launch_bounds__(kStreamThreads, 2) detect_score_fast_kernel(co
   __shared__ unsigned int s_ncand, s_gbase;
 
   const int tid = threadIdx.x, lane = tid & 31;
-  const int C = q.C;
+  const int C = kC ? kC : q.C;
   // tiles of this CTA: all of a contiguous range (modes 0, 2) or every sample_stride-th tile (mode 1)
   const int stride = q.mode == 1 ? q.sample_stride : 1;
   const int n_units = q.mode == 1 ? (q.n_tiles + stride - 1 - stride / 2) / stride : q.n_tiles;
@@ -407,9 +408,10 @@ __global__ void __launch_bounds__(kStreamThreads, 2) detect_score_fast_kernel(co
     uint32_t m0 = 0u, m1 = 0u;
     float nmx2 = 0.f, inv = 1.f;
     if (q.act_kind == SBOD_ACT_SOFTMAX) {
-      const float mx = half_row_max(rp, nh);
+      const float mx = kC ? pair_row_max_fixed<kC>(rp - h, h) : half_row_max(rp, nh);
       nmx2 = -mx * kLog2e;
-      const float sum = half_row_sumexp_mask(rp, nh, nmx2, cut_floor, m0, m1);
+      const float sum = kC ? pair_row_sumexp_mask_fixed<kC>(rp - h, h, nmx2, cut_floor, m0, m1)
+                           : half_row_sumexp_mask(rp, nh, nmx2, cut_floor, m0, m1);
       inv = __frcp_rn(sum);
     } else {
       // sigmoid(x) > t  <=>  x > logit(t); keep a small margin, the exact test follows
@@ -1254,7 +1256,9 @@ static int detect_run(const sbod_detect_desc* d, sbod_stream_t stream, int stage
   if (!attr_done) {
     SBOD_CUDA_TRY(cudaFuncSetAttribute(detect_score_kernel,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    SBOD_CUDA_TRY(cudaFuncSetAttribute(detect_score_fast_kernel,
+    SBOD_CUDA_TRY(cudaFuncSetAttribute(detect_score_fast_kernel<81>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    SBOD_CUDA_TRY(cudaFuncSetAttribute(detect_score_fast_kernel<21>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    SBOD_CUDA_TRY(cudaFuncSetAttribute(detect_score_fast_kernel<0>,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024));
     SBOD_CUDA_TRY(cudaFuncSetAttribute(detect_nms_kernel,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
@@ -1282,6 +1286,11 @@ static int detect_run(const sbod_detect_desc* d, sbod_stream_t stream, int stage
     const size_t fsmem = size_t(q.n_stages) * sb + 4 * 8;
     int fgrid = sm_count() * ctas;
     if (fgrid > q.n_tiles) fgrid = q.n_tiles;
+    auto launch_score = [&](int g, const DetParams& qq) {
+      if (qq.C == 81) detect_score_fast_kernel<81><<<g, kStreamThreads, fsmem, st>>>(qq);       // COCO
+      else if (qq.C == 21) detect_score_fast_kernel<21><<<g, kStreamThreads, fsmem, st>>>(qq);  // VOC
+      else detect_score_fast_kernel<0><<<g, kStreamThreads, fsmem, st>>>(qq);
+    };
     // Speculation pays when the sampled histogram is cheap relative to the main pass.
     const bool speculate = q.tiles_per_image >= 2 * q.sample_stride && !(q.debug_skip & 4);
     q.speculate = speculate ? 1 : 0;
@@ -1291,12 +1300,12 @@ static int detect_run(const sbod_detect_desc* d, sbod_stream_t stream, int stage
         qs.mode = 1;
         int sgrid = (q.n_tiles / q.sample_stride + 1);
         if (sgrid > fgrid) sgrid = fgrid;
-        detect_score_fast_kernel<<<sgrid, kStreamThreads, fsmem, st>>>(qs);
+        launch_score(sgrid, qs);
         SBOD_LAUNCH_CHECK();
       }
     }
     if (stage_mask & 4) {
-      detect_score_fast_kernel<<<fgrid, kStreamThreads, fsmem, st>>>(q);
+      launch_score(fgrid, q);
       SBOD_LAUNCH_CHECK();
     }
     if (stage_mask & 2) {
@@ -1308,7 +1317,7 @@ static int detect_run(const sbod_detect_desc* d, sbod_stream_t stream, int stage
       if (speculate) {  // exact fallback for the images whose candidates ran out (usually none)
         DetParams qf = q;
         qf.mode = 2;
-        detect_score_fast_kernel<<<fgrid, kStreamThreads, fsmem, st>>>(qf);
+        launch_score(fgrid, qf);
         SBOD_LAUNCH_CHECK();
         detect_nms_kernel<<<q.N, kNmsThreads, nms_smem_f, st>>>(qf);
         SBOD_LAUNCH_CHECK();

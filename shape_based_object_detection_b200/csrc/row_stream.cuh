@@ -91,6 +91,59 @@ SBOD_DEVINL float pair_row_sumexp_fixed(const float* rbase, int h, float nshift2
   return s + __shfl_xor_sync(0xffffffffu, s, 1);
 }
 
+// Compile-time C variants of half_row_max / half_row_sumexp_mask for the eval path: fully unrolled over
+// the kC / 2 elements both parities own (+ one more for parity 0 when kC is odd), immediate offsets and
+// immediate mask bits. rbase = first logit of the row, h = element parity of this thread.
+template <int kC>
+SBOD_DEVINL float pair_row_max_fixed(const float* rbase, int h) {
+  constexpr int kBoth = kC / 2;
+  const float NEG = -__int_as_float(0x7f800000);
+  const float* rp = rbase + h;
+  float a0 = NEG, a1 = NEG, a2 = NEG, a3 = NEG;
+#pragma unroll
+  for (int j = 0; j < kBoth; j += 4) {
+    a0 = fmaxf(a0, rp[2 * j]);
+    if (j + 1 < kBoth) a1 = fmaxf(a1, rp[2 * j + 2]);
+    if (j + 2 < kBoth) a2 = fmaxf(a2, rp[2 * j + 4]);
+    if (j + 3 < kBoth) a3 = fmaxf(a3, rp[2 * j + 6]);
+  }
+  if ((kC & 1) && h == 0) a1 = fmaxf(a1, rp[2 * kBoth]);
+  const float m = fmaxf(fmaxf(a0, a1), fmaxf(a2, a3));
+  return fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 1));
+}
+
+template <int kC>
+SBOD_DEVINL float pair_row_sumexp_mask_fixed(const float* rbase, int h, float nmx2, float floor_e, uint32_t& m0,
+                                             uint32_t& m1) {
+  constexpr int kBoth = kC / 2;
+  const float* rp = rbase + h;
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+  m0 = 0u;
+  m1 = 0u;
+#pragma unroll
+  for (int j = 0; j < kBoth; ++j) {
+    const float e = ex2_approx(fmaf(rp[2 * j], kLog2e, nmx2));
+    if ((j & 3) == 0) s0 += e;
+    else if ((j & 3) == 1) s1 += e;
+    else if ((j & 3) == 2) s2 += e;
+    else s3 += e;
+    if (e > floor_e) {
+      if (j < 32) m0 |= 1u << j;
+      else m1 |= 1u << (j - 32);
+    }
+  }
+  if ((kC & 1) && h == 0) {
+    const float e = ex2_approx(fmaf(rp[2 * kBoth], kLog2e, nmx2));
+    s1 += e;
+    if (e > floor_e) {
+      if (kBoth < 32) m0 |= 1u << kBoth;
+      else m1 |= 1u << (kBoth - 32);
+    }
+  }
+  const float s = (s0 + s1) + (s2 + s3);
+  return s + __shfl_xor_sync(0xffffffffu, s, 1);
+}
+
 // As above, and additionally records in (m0, m1) which of this thread's elements (bit j, j < 64)
 // have exp(x - mx) > floor. Since the row sum is >= 1, prob = e/sum <= e, so the mask is a
 // superset of the classes whose probability exceeds `floor`.
