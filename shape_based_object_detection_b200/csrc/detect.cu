@@ -369,6 +369,8 @@ __global__ void __launch_bounds__(kStreamThreads, 2) detect_score_fast_kernel(co
   // tile coordinates advance incrementally (no integer division in the loop)
   int cur_n = tile_of(0) / q.tiles_per_image;
   int cur_t = tile_of(0) - cur_n * q.tiles_per_image;
+  int ring_s = 0;
+  uint32_t ring_parity = 0;
   for (int it = 0; it < n_my; ++it) {
     StreamTile tc;
     tc.n = cur_n;
@@ -399,9 +401,13 @@ __global__ void __launch_bounds__(kStreamThreads, 2) detect_score_fast_kernel(co
     }
     const bool keep_row = valid && (q.prior_keep ? q.prior_keep[np] != 0 : true);
 
-    const int s = it % q.n_stages;
+    const int s = ring_s;  // stage / phase advance incrementally (no integer division per tile)
     float* stage = stages + size_t(s) * q.stage_floats;
-    mbar_wait(&bars[s], (it / q.n_stages) & 1);
+    mbar_wait(&bars[s], ring_parity);
+    if (++ring_s == q.n_stages) {
+      ring_s = 0;
+      ring_parity ^= 1u;
+    }
     const uint32_t head = ((uint32_t(n) * uint32_t(q.P) + uint32_t(tc.p0)) * uint32_t(C)) & 3u;
     const float* rp = stage + head + r * C + h;
 
