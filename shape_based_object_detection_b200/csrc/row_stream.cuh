@@ -195,44 +195,6 @@ SBOD_DEVINL float half_row_sumexp_mask(const float* rp, int nh, float nmx2, floa
   return s + __shfl_xor_sync(0xffffffffu, s, 1);
 }
 
-// Single-pass variant: exp(x - shift) with a caller-chosen shift (the row's background logit: its own
-// term is then exactly 1, so the row sum is >= 1 without a max pass), summed over this thread's
-// elements and combined with the partner lane. Element 0 of the thread is handled on its own (for
-// the even-parity thread it is the background class): bit 31 of `gmask` flags it; bit g (g < 16)
-// is set when any of the thread's elements 4g+1 .. 4g+4 exceeds `floor_e` — a coarse superset of
-// the candidates that the caller refines exactly. The caller must fall back to the max-shifted
-// path when the returned sum is not finite.
-SBOD_DEVINL float half_row_sumexp_groupmask(const float* rp, int nh, float nshift2, float floor_e,
-                                            uint32_t& gmask) {
-  const float ef = ex2_approx(fmaf(rp[0], kLog2e, nshift2));
-  float s0 = ef, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-  gmask = ef > floor_e ? 0x80000000u : 0u;
-  const float* r1 = rp + 2;  // element j (>= 1) lives at r1[2*(j-1)]
-  const int n1 = nh - 1;
-  int j = 0;
-  for (; j + 8 <= n1; j += 8) {
-    const float e0 = ex2_approx(fmaf(r1[2 * j], kLog2e, nshift2));
-    const float e1 = ex2_approx(fmaf(r1[2 * j + 2], kLog2e, nshift2));
-    const float e2 = ex2_approx(fmaf(r1[2 * j + 4], kLog2e, nshift2));
-    const float e3 = ex2_approx(fmaf(r1[2 * j + 6], kLog2e, nshift2));
-    const float e4 = ex2_approx(fmaf(r1[2 * j + 8], kLog2e, nshift2));
-    const float e5 = ex2_approx(fmaf(r1[2 * j + 10], kLog2e, nshift2));
-    const float e6 = ex2_approx(fmaf(r1[2 * j + 12], kLog2e, nshift2));
-    const float e7 = ex2_approx(fmaf(r1[2 * j + 14], kLog2e, nshift2));
-    s0 += e0 + e1; s1 += e2 + e3; s2 += e4 + e5; s3 += e6 + e7;
-    const int g = j >> 2;
-    if (fmaxf(fmaxf(e0, e1), fmaxf(e2, e3)) > floor_e) gmask |= 1u << g;
-    if (fmaxf(fmaxf(e4, e5), fmaxf(e6, e7)) > floor_e) gmask |= 2u << g;
-  }
-  for (; j < n1; ++j) {
-    const float e = ex2_approx(fmaf(r1[2 * j], kLog2e, nshift2));
-    s1 += e;
-    if (e > floor_e) gmask |= 1u << (j >> 2);
-  }
-  const float s = (s0 + s1) + (s2 + s3);
-  return s + __shfl_xor_sync(0xffffffffu, s, 1);
-}
-
 // generic tile geometry shared by the streaming kernels
 struct StreamTile {
   int n, p0, rows;
