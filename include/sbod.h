@@ -114,6 +114,8 @@ SBOD_API int sbod_pair_iou_bwd(const float* b1, const float* b2, const float* gr
  *                         row_out[M] = loss of the target column (the only non-zero column),
  *                         grad_logits (optional, may be NULL) = d(sum row_out)/d logits.
  *   sbod_sigmoid_focal  : Loss.py:41-80 SigmoidFocalLoss (uses columns 1..C-1, class ids 1..C-1)
+ *   sbod_bce_focal      : Loss.py:83-103 FocalLoss (one-hot over all C columns, clamped sigmoid,
+ *                         BCE-with-logits); row_out[M] = row sums, grad_logits optional
  * ---------------------------------------------------------------------------------------- */
 SBOD_API int sbod_smooth_l1(const float* pred, const float* target, int n_elem, float beta, float* out,
                    float* grad_pred /* nullable: d out / d pred */, sbod_stream_t stream);
@@ -122,6 +124,8 @@ SBOD_API int sbod_softmax_focal(const float* logits, const int64_t* target, int 
                        sbod_stream_t stream);
 SBOD_API int sbod_sigmoid_focal(const float* logits, const int64_t* target, int M, int C, float alpha,
                        float gamma, float* row_out, float* grad_logits, sbod_stream_t stream);
+SBOD_API int sbod_bce_focal(const float* logits, const int64_t* target, int M, int C, float alpha,
+                   float gamma, float* row_out, float* grad_logits, sbod_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * Stand-alone greedy NMS == torchvision.ops.nms as called at models/utils.py:145,265 and

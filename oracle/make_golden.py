@@ -16,6 +16,7 @@ REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 _args = [a for a in sys.argv[1:] if not a.startswith("--")]
 REF = _args[0] if _args else "/root/reference"
 ONLY_MAP = "--only-map" in sys.argv  # regenerate tests/golden/map.npz and nothing else
+ONLY_EXTRAS = "--only-extras" in sys.argv  # regenerate tests/golden/extras.npz and nothing else
 sys.path.insert(0, REPO)
 sys.path.insert(0, REF)
 warnings.filterwarnings("ignore")
@@ -58,11 +59,31 @@ def golden_map():
     print("map ok", {k: float(v) for k, v in out.items() if k.endswith("_map")})
 
 
+def golden_extras():
+    """Functions of the path that the reference defines but never calls."""
+    sys.path.insert(0, os.path.join(REPO, "tests"))
+    from cases import operator_inputs  # noqa: E402
+    from operators import Loss as ref_loss
+    I = operator_inputs()
+    out = {}
+    for tag, lg in (("", I["lg"]), ("_wide", I["lg"] * 6.0)):  # the wide logits reach the probability clamp
+        x = lg.clone().requires_grad_(True)
+        fl = ref_loss.FocalLoss(0.25, 2)(x, I["tg"])
+        fl.backward()
+        out["bcefocal" + tag] = np.float64(fl.item())
+        out["bcefocal" + tag + "_g"] = x.grad.numpy()
+    np.savez_compressed(os.path.join(OUT, "extras.npz"), **out)
+    print("extras ok", {k: float(v) for k, v in out.items() if not k.endswith("_g")})
+
+
 def main():
     torch.manual_seed(0)
     torch.set_num_threads(4)
     if ONLY_MAP:
         golden_map()
+        return
+    if ONLY_EXTRAS:
+        golden_extras()
         return
     sys.path.insert(0, os.path.join(REPO, "tests"))
     from cases import LOSS_CASES, DETECT_CASES, case_priors  # noqa: E402
@@ -245,6 +266,7 @@ def main():
     np.savez_compressed(os.path.join(OUT, "detect.npz"), **dout)
     print("detect ok", {k: v.shape for k, v in dout.items() if "_s" in k})
     golden_map()
+    golden_extras()
 
 
 if __name__ == "__main__":

@@ -239,6 +239,40 @@ __global__ void sigmoid_focal_kernel(const float* __restrict__ x, const int64_t*
   }
 }
 
+// Loss.py:83-103 FocalLoss: one-hot targets over ALL columns (class ids 0..C-1),
+//   p = clamp(sigmoid(z), 1e-4, 1 - 1e-4); ce = BCE-with-logits(z, y); a = y ? alpha : 1 - alpha;
+//   pt = y ? p : 1 - p;  loss = a * (1 - pt)^gamma * ce, summed. Gradient through the clamp is zero
+//   outside (1e-4, 1 - 1e-4) as in torch; d ce / d z = sigmoid(z) - y.
+__global__ void bce_focal_kernel(const float* __restrict__ x, const int64_t* __restrict__ tgt, int M, int C,
+                                 float alpha, float gamma, float* __restrict__ row_out,
+                                 float* __restrict__ grad) {
+  const int lane = threadIdx.x & 31;
+  const int warps = (gridDim.x * blockDim.x) >> 5;
+  for (int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < M; r += warps) {
+    const float* row = x + size_t(r) * C;
+    const int64_t t = tgt[r];
+    float acc = 0.f;
+    for (int k = lane; k < C; k += 32) {
+      const float z = row[k];
+      const bool y = t == k;
+      const float ps = 1.f / (1.f + expf(-z));
+      const float p = fminf(fmaxf(ps, 1e-4f), 1.f - 1e-4f);
+      const float ce = fmaxf(z, 0.f) - (y ? z : 0.f) + log1pf(expf(-fabsf(z)));
+      const float a = y ? alpha : 1.f - alpha;
+      const float om = y ? 1.f - p : p;  // 1 - pt
+      const float wgt = powf(om, gamma);
+      acc += a * wgt * ce;
+      if (grad) {
+        const float dp = (ps >= 1e-4f && ps <= 1.f - 1e-4f) ? ps * (1.f - ps) : 0.f;  // d clamp(sigmoid) / dz
+        const float dom = y ? -dp : dp;                                               // d (1 - pt) / dz
+        grad[size_t(r) * C + k] = a * (gamma * powf(om, gamma - 1.f) * dom * ce + wgt * (ps - (y ? 1.f : 0.f)));
+      }
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) row_out[r] = acc;
+  }
+}
+
 // ---- stand-alone NMS ---------------------------------------------------------------------------
 // order key: score descending, index ascending (stable), NaN-free scores assumed
 SBOD_DEVINL unsigned long long nms_key(float s, int i) {
@@ -586,6 +620,17 @@ extern "C" int sbod_sigmoid_focal(const float* logits, const int64_t* target, in
   if (M == 0) return SBOD_OK;
   if (!logits || !target || !row_out) return SBOD_ERR_INVALID;
   sigmoid_focal_kernel<<<grid_for(size_t(M) * 32, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      logits, target, M, C, alpha, gamma, row_out, grad_logits);
+  SBOD_LAUNCH_CHECK();
+  return SBOD_OK;
+}
+
+extern "C" int sbod_bce_focal(const float* logits, const int64_t* target, int M, int C, float alpha,
+                              float gamma, float* row_out, float* grad_logits, sbod_stream_t stream) {
+  if (M < 0 || C <= 0) return SBOD_ERR_INVALID;
+  if (M == 0) return SBOD_OK;
+  if (!logits || !target || !row_out) return SBOD_ERR_INVALID;
+  bce_focal_kernel<<<grid_for(size_t(M) * 32, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       logits, target, M, C, alpha, gamma, row_out, grad_logits);
   SBOD_LAUNCH_CHECK();
   return SBOD_OK;

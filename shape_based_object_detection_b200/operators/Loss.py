@@ -23,6 +23,9 @@ class _RowLoss(torch.autograd.Function):
         if kind == "softmax":
             L.check(L.lib().sbod_softmax_focal(L.ptr(x), L.ptr(t), M, Cn, a0, a1, gamma, L.ptr(row),
                                                L.ptr(grad), L.stream_ptr()))
+        elif kind == "bce":
+            L.check(L.lib().sbod_bce_focal(L.ptr(x), L.ptr(t), M, Cn, a0, gamma, L.ptr(row),
+                                           L.ptr(grad), L.stream_ptr()))
         else:
             L.check(L.lib().sbod_sigmoid_focal(L.ptr(x), L.ptr(t), M, Cn, a0, gamma, L.ptr(row),
                                                L.ptr(grad), L.stream_ptr()))
@@ -65,8 +68,8 @@ class SigmoidFocalLoss(nn.Module):
 
 
 class FocalLoss(nn.Module):
-    """Loss.py:83-103 — imported by the reference but never instantiated (SURVEY §8 a12);
-    kept for API completeness, outside the accelerated path."""
+    """Loss.py:83-103 (imported by the reference, never instantiated — SURVEY §8 a12): sigmoid focal
+    loss with BCE-with-logits over a one-hot target of all columns, clamped probabilities, summed."""
 
     def __init__(self, alpha=0.25, gamma=2):
         super().__init__()
@@ -74,7 +77,10 @@ class FocalLoss(nn.Module):
         self.gamma = gamma
 
     def forward(self, pred_logits, targets):
-        raise NotImplementedError("FocalLoss (sigmoid/BCE variant) is never used by the reference models")
+        L.need_cuda(pred_logits)
+        if pred_logits.shape[0] == 0:
+            return pred_logits.sum() * 0.0
+        return _RowLoss.apply(pred_logits, targets, "bce", float(self.alpha), 0.0, float(self.gamma)).sum()
 
 
 class IouLoss(nn.Module):

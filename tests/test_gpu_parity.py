@@ -654,3 +654,16 @@ def test_map_large_and_edge_cases(dev):
     gt = [[cu(t, dev) for t in lst[:3]] for lst in case[3:]]
     aps, mean_ap = calculate_mAP(*empty, *gt, 0.5, label_map)
     assert mean_ap == 0.0 and all(v == 0.0 for v in aps.values())
+
+
+def test_bce_focal_loss(golden, dev):
+    """operators.Loss.FocalLoss (Loss.py:83-103) against the reference fixture, value and gradient."""
+    from shape_based_object_detection_b200.operators import Loss as LS
+    I, G = operator_inputs(), golden["extras"]
+    for tag, scale in (("", 1.0), ("_wide", 6.0)):
+        x = cu(I["lg"] * scale, dev).requires_grad_(True)
+        fl = LS.FocalLoss(0.25, 2)(x, cu(I["tg"], dev))
+        fl.backward()
+        want = float(G["bcefocal" + tag])
+        assert abs(fl.item() - want) <= RTOL_LOSS * abs(want), (fl.item(), want)
+        assert torch.allclose(x.grad.cpu(), T(G["bcefocal" + tag + "_g"]), rtol=RTOL_GRAD, atol=1e-6)

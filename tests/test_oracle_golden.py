@@ -200,3 +200,14 @@ def test_oracle_map_matches_reference(golden, name):
     ap, mean_ap = O.calculate_mAP(*map_inputs(case), case["threshold"], case["n_classes"])
     assert torch.equal(ap, T(golden["map"][name + "_ap"]))
     assert mean_ap == float(golden["map"][name + "_map"])
+
+
+def test_oracle_bce_focal_matches_reference(golden):
+    """Loss.py:83-103 FocalLoss (a12: defined by the reference, never called)."""
+    I, G = operator_inputs(), golden["extras"]
+    for tag, scale in (("", 1.0), ("_wide", 6.0)):
+        x = (I["lg"] * scale).clone().requires_grad_(True)
+        fl = O.bce_focal_loss(x, I["tg"], 0.25, 2)
+        fl.backward()
+        assert abs(fl.item() - float(G["bcefocal" + tag])) <= 1e-6 * abs(float(G["bcefocal" + tag]))
+        assert torch.allclose(x.grad, T(G["bcefocal" + tag + "_g"]), rtol=1e-5, atol=1e-7)
