@@ -138,6 +138,11 @@ SBOD_API size_t sbod_nms_workspace_bytes(int n);
 SBOD_API int sbod_nms(const float* boxes, const float* scores, int n, float iou_thr, int top_k,
              int64_t* keep_out, int32_t* count_out, void* workspace, size_t workspace_bytes,
              sbod_stream_t stream);
+/* operators/iou_utils.py:453-530 diounms as written (criterion IoU - (d/c)^beta1 with the centre
+ * term of :507); same outputs and workspace as sbod_nms. */
+SBOD_API int sbod_diou_nms(const float* boxes, const float* scores, int n, float thr, int top_k, float beta1,
+                  int64_t* keep_out, int32_t* count_out, void* workspace, size_t workspace_bytes,
+                  sbod_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * Batched assignment (the loop inlined in every *Loss.forward: models/SSD300.py:501-542,

@@ -72,8 +72,12 @@ def golden_extras():
         fl.backward()
         out["bcefocal" + tag] = np.float64(fl.item())
         out["bcefocal" + tag + "_g"] = x.grad.numpy()
+    from operators import iou_utils as ref_iu
+    for beta in (1.0, 0.6):
+        keep, cnt = ref_iu.diounms(I["nb"].clone(), I["ns"].clone(), 0.45, 200, beta)
+        out["diounms_b%02d" % int(beta * 10)] = keep[:cnt].numpy().astype(np.int32)
     np.savez_compressed(os.path.join(OUT, "extras.npz"), **out)
-    print("extras ok", {k: float(v) for k, v in out.items() if not k.endswith("_g")})
+    print("extras ok", {k: (float(v) if v.ndim == 0 else v.shape) for k, v in out.items() if not k.endswith("_g")})
 
 
 def main():

@@ -32,7 +32,7 @@ EXPORTS = [
     "sbod_detect_workspace_bytes", "sbod_detect_workspace_zero_bytes", "sbod_detect",
     "sbod_loss_forward_host_arena_bytes", "sbod_loss_forward_host",
     "sbod_fcos_workspace_bytes", "sbod_fcos_forward", "sbod_fcos_backward", "sbod_fcos_postprocess",
-    "sbod_selftest_div", "sbod_map_workspace_bytes", "sbod_map", "sbod_bce_focal",
+    "sbod_selftest_div", "sbod_map_workspace_bytes", "sbod_map", "sbod_bce_focal", "sbod_diou_nms",
 ]
 
 
@@ -108,6 +108,7 @@ def _declare(lib):
         "sbod_sigmoid_focal": [vp, vp, i32, i32, f32, f32, vp, vp, vp],
         "sbod_bce_focal": [vp, vp, i32, i32, f32, f32, vp, vp, vp],
         "sbod_nms": [vp, vp, i32, f32, i32, vp, vp, vp, sz, vp],
+        "sbod_diou_nms": [vp, vp, i32, f32, i32, f32, vp, vp, vp, sz, vp],
         "sbod_assign": [vp, vp, vp, i32, i32, vp, i32, i32, f32, f32, vp, vp, vp, vp, vp, sz, vp],
         "sbod_match": [f32, vp, i32, vp, i32, f32, f32, vp, i32, vp, vp, vp, sz, vp],
         "sbod_workspace_init": [vp, sz, vp],

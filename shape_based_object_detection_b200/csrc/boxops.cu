@@ -299,10 +299,32 @@ __global__ void __launch_bounds__(256) nms_rank_kernel(const float* __restrict__
   if (i < n) order[rank] = i;
 }
 
+// iou_utils.diounms (iou_utils.py:453-530) as written: box i is kept, box j a lower-scored candidate.
+//   value = inter / ((area_j - inter) + area_i) - (d / c) ** beta1,  suppress j unless value <= thr
+//   d = (cx_i - cx_j)^2 + (cy_i - y2_j)^2   (:507 takes y2 of the candidate where its centre was meant)
+//   c = squared diagonal of the enclosing box.
+SBOD_DEVINL bool diou_suppresses(const float4 bi, float ai, const float4 bj, float thr, float beta1) {
+  const float w = fmaxf(__fsub_rn(fminf(bj.z, bi.z), fmaxf(bj.x, bi.x)), 0.f);
+  const float h = fmaxf(__fsub_rn(fminf(bj.w, bi.w), fmaxf(bj.y, bi.y)), 0.f);
+  const float inter = __fmul_rn(w, h);
+  const float dx = __fsub_rn(__fdiv_rn(__fadd_rn(bi.x, bi.z), 2.f), __fdiv_rn(__fadd_rn(bj.x, bj.z), 2.f));
+  const float dy = __fsub_rn(__fdiv_rn(__fadd_rn(bi.y, bi.w), 2.f), __fdiv_rn(__fadd_rn(bj.w, bj.w), 2.f));
+  const float d = __fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy));
+  const float ex = __fsub_rn(fmaxf(bj.z, bi.z), fminf(bj.x, bi.x));
+  const float ey = __fsub_rn(fmaxf(bj.w, bi.w), fminf(bj.y, bi.y));
+  const float c = __fadd_rn(__fmul_rn(ex, ex), __fmul_rn(ey, ey));
+  const float u = __fdiv_rn(d, c);
+  const float pen = beta1 == 1.f ? u : powf(u, beta1);
+  const float aj = box_area_rn(bj);
+  const float v = __fsub_rn(__fdiv_rn(inter, __fadd_rn(__fsub_rn(aj, inter), ai)), pen);
+  return !(v <= thr);  // IoU.le(overlap) keeps; NaN is dropped like in the reference
+}
+
+template <bool kDiou>
 __global__ void __launch_bounds__(64) nms_mask_kernel(const float4* __restrict__ boxes,
                                                       const int* __restrict__ order, int m,
                                                       float thr, unsigned long long* __restrict__ mask,
-                                                      int words) {
+                                                      int words, float beta1) {
   const int rb = blockIdx.y, cb = blockIdx.x;
   if (cb < rb) return;  // only j > i matters
   __shared__ float4 s_b[64];
@@ -315,8 +337,11 @@ __global__ void __launch_bounds__(64) nms_mask_kernel(const float4* __restrict__
     const float ai = box_area_rn(bi);
     unsigned long long bits = 0ull;
     const int start = (rb == cb) ? threadIdx.x + 1 : 0;
-    for (int t = start; t < cn; ++t)
-      if (iou_plain_rn(bi, ai, s_b[t], box_area_rn(s_b[t])) > thr) bits |= 1ull << t;
+    for (int t = start; t < cn; ++t) {
+      const bool sup = kDiou ? diou_suppresses(bi, ai, s_b[t], thr, beta1)
+                             : iou_plain_rn(bi, ai, s_b[t], box_area_rn(s_b[t])) > thr;
+      if (sup) bits |= 1ull << t;
+    }
     mask[size_t(i) * words + cb] = bits;
   }
 }
@@ -642,9 +667,26 @@ extern "C" size_t sbod_nms_workspace_bytes(int n) {
   return align_up(size_t(n) * 4, 256) + align_up(words * 8, 256) + align_up(size_t(n) * words * 8, 256);
 }
 
+static int nms_run(const float* boxes, const float* scores, int n, float iou_thr, int top_k, int64_t* keep_out,
+                   int32_t* count_out, void* workspace, size_t workspace_bytes, sbod_stream_t stream, bool diou,
+                   float beta1);
+
 extern "C" int sbod_nms(const float* boxes, const float* scores, int n, float iou_thr, int top_k,
                         int64_t* keep_out, int32_t* count_out, void* workspace,
                         size_t workspace_bytes, sbod_stream_t stream) {
+  return nms_run(boxes, scores, n, iou_thr, top_k, keep_out, count_out, workspace, workspace_bytes, stream, false,
+                 1.f);
+}
+
+extern "C" int sbod_diou_nms(const float* boxes, const float* scores, int n, float thr, int top_k, float beta1,
+                             int64_t* keep_out, int32_t* count_out, void* workspace, size_t workspace_bytes,
+                             sbod_stream_t stream) {
+  return nms_run(boxes, scores, n, thr, top_k, keep_out, count_out, workspace, workspace_bytes, stream, true, beta1);
+}
+
+static int nms_run(const float* boxes, const float* scores, int n, float iou_thr, int top_k, int64_t* keep_out,
+                   int32_t* count_out, void* workspace, size_t workspace_bytes, sbod_stream_t stream, bool diou,
+                   float beta1) {
   if (n < 0 || !count_out) return SBOD_ERR_INVALID;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (n == 0) {
@@ -665,8 +707,12 @@ extern "C" int sbod_nms(const float* boxes, const float* scores, int n, float io
   nms_rank_kernel<<<(n + 255) / 256, 256, 0, st>>>(scores, n, order);
   SBOD_LAUNCH_CHECK();
   dim3 grid(words, words);
-  nms_mask_kernel<<<grid, 64, 0, st>>>(reinterpret_cast<const float4*>(boxes), order, m, iou_thr,
-                                       mask, words);
+  if (diou)
+    nms_mask_kernel<true><<<grid, 64, 0, st>>>(reinterpret_cast<const float4*>(boxes), order, m, iou_thr, mask,
+                                               words, beta1);
+  else
+    nms_mask_kernel<false><<<grid, 64, 0, st>>>(reinterpret_cast<const float4*>(boxes), order, m, iou_thr, mask,
+                                                words, beta1);
   SBOD_LAUNCH_CHECK();
   nms_reduce_kernel<<<1, 1024, 0, st>>>(mask, order, m, words, keep_out, count_out, removed);
   SBOD_LAUNCH_CHECK();

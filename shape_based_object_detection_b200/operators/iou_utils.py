@@ -152,7 +152,7 @@ def log_sum_exp(x):
     return torch.log(torch.sum(torch.exp(x - x_max), 1, keepdim=True)) + x_max
 
 
-def _nms_device(boxes, scores, overlap, top_k):
+def _nms_device(boxes, scores, overlap, top_k, diou_beta=None):
     L.need_cuda(boxes, scores)
     n = scores.size(0)
     b, s = L.f32c(boxes), L.f32c(scores)
@@ -160,8 +160,12 @@ def _nms_device(boxes, scores, overlap, top_k):
     count = torch.zeros((1,), dtype=torch.int32, device=scores.device)
     nbytes = L.lib().sbod_nms_workspace_bytes(n)
     ws = L.Workspace.get(scores.device, ("nms", n), nbytes, zero_bytes=0)
-    L.check(L.lib().sbod_nms(L.ptr(b), L.ptr(s), n, float(overlap), int(top_k), L.ptr(keep), L.ptr(count),
-                             L.ptr(ws), C.c_size_t(nbytes), L.stream_ptr()))
+    if diou_beta is None:
+        L.check(L.lib().sbod_nms(L.ptr(b), L.ptr(s), n, float(overlap), int(top_k), L.ptr(keep), L.ptr(count),
+                                 L.ptr(ws), C.c_size_t(nbytes), L.stream_ptr()))
+    else:
+        L.check(L.lib().sbod_diou_nms(L.ptr(b), L.ptr(s), n, float(overlap), int(top_k), float(diou_beta),
+                                      L.ptr(keep), L.ptr(count), L.ptr(ws), C.c_size_t(nbytes), L.stream_ptr()))
     return keep, count
 
 
@@ -175,9 +179,13 @@ def nms(boxes, scores, overlap=0.5, top_k=200):
 
 
 def diounms(boxes, scores, overlap=0.5, top_k=200, beta1=1.0):
-    """iou_utils.py:453-530 is DIoU-NMS with a centre typo (:507) and is not called anywhere in the
-    reference; out of the hot path — not provided on the device."""
-    raise NotImplementedError("diounms is outside the accelerated path (unused by the reference)")
+    """iou_utils.py:453-530 as written (never called by the reference): greedy NMS among the top_k
+    best-scored boxes with the criterion IoU - (d / c) ** beta1 <= overlap, d using the candidate's
+    y2 where its centre was meant (:507). Returns (keep [n] zero padded, count)."""
+    if boxes.numel() == 0:
+        return scores.new(scores.size(0)).zero_().long()  # bare tensor, as the reference does (:467-468)
+    keep, count = _nms_device(boxes, scores, overlap, top_k, diou_beta=beta1)
+    return keep, int(count.item())
 
 
 def torchvision_nms(boxes, scores, iou_threshold):

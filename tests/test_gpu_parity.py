@@ -667,3 +667,23 @@ def test_bce_focal_loss(golden, dev):
         want = float(G["bcefocal" + tag])
         assert abs(fl.item() - want) <= RTOL_LOSS * abs(want), (fl.item(), want)
         assert torch.allclose(x.grad.cpu(), T(G["bcefocal" + tag + "_g"]), rtol=RTOL_GRAD, atol=1e-6)
+
+
+def test_diounms(golden, dev):
+    """operators.iou_utils.diounms against the reference fixture, and a bigger random problem against
+    the oracle."""
+    from oracle import box_pipeline as O
+    from shape_based_object_detection_b200.operators import iou_utils as U
+    I, G = operator_inputs(), golden["extras"]
+    for beta in (1.0, 0.6):
+        k, cnt = U.diounms(cu(I["nb"], dev), cu(I["ns"], dev), 0.45, 200, beta)
+        assert torch.equal(k[:cnt].cpu(), T(G["diounms_b%02d" % int(beta * 10)]).long())
+        assert int(k[cnt:].abs().sum()) == 0
+    g = torch.Generator().manual_seed(15)
+    c = torch.rand((2000, 2), generator=g)
+    wh = torch.rand((2000, 2), generator=g) * 0.2 + 0.01
+    b = torch.cat([c - wh / 2, c + wh / 2], 1)
+    s = torch.rand((2000,), generator=g)
+    want, wcnt = O.diounms(b, s, 0.4, 500, 1.0)
+    k, cnt = U.diounms(cu(b, dev), cu(s, dev), 0.4, 500, 1.0)
+    assert cnt == wcnt and torch.equal(k[:cnt].cpu(), want[:wcnt])

@@ -211,3 +211,11 @@ def test_oracle_bce_focal_matches_reference(golden):
         fl.backward()
         assert abs(fl.item() - float(G["bcefocal" + tag])) <= 1e-6 * abs(float(G["bcefocal" + tag]))
         assert torch.allclose(x.grad, T(G["bcefocal" + tag + "_g"]), rtol=1e-5, atol=1e-7)
+
+
+def test_oracle_diounms_matches_reference(golden):
+    """iou_utils.diounms (a20: defined by the reference, never called)."""
+    I, G = operator_inputs(), golden["extras"]
+    for beta in (1.0, 0.6):
+        keep, cnt = O.diounms(I["nb"], I["ns"], 0.45, 200, beta)
+        assert torch.equal(keep[:cnt], T(G["diounms_b%02d" % int(beta * 10)]).long())
