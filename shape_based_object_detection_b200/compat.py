@@ -17,8 +17,8 @@ def install(reference_root=None):
     plan = [
         ("operators.iou_utils", iu, ["bbox_overlaps_iou", "bbox_overlaps_giou", "bbox_overlaps_diou",
                                      "bbox_overlaps_ciou", "point_form", "center_size", "intersect", "jaccard",
-                                     "match", "match_ious", "encode", "decode", "nms"]),
-        ("operators.Loss", lo, ["focal_loss", "SigmoidFocalLoss", "IouLoss", "SmoothL1Loss"]),
+                                     "match", "match_ious", "encode", "decode", "nms", "diounms"]),
+        ("operators.Loss", lo, ["focal_loss", "SigmoidFocalLoss", "FocalLoss", "IouLoss", "SmoothL1Loss"]),
         ("models.SSD300", SSD300, ["MultiBoxLoss300"]),
         ("models.SSD512", SSD512, ["MultiBoxLoss512"]),
         ("models.RetinaNet", RetinaNet, ["RetinaFocalLoss"]),
