@@ -75,3 +75,26 @@ def test_two_rank_allreduce_reproduces_full_batch_loss():
     mp.spawn(_worker, args=(2, port, out), nprocs=2, join=True)
     assert abs(out[0] - out[1]) == 0.0
     assert abs(out[0] - want) <= 1e-6 * abs(want)
+
+
+def test_bench_reference_arm_json_contract():
+    """bench.py --impl reference (the CPU arm the driver runs beside ours) prints one JSON line with the
+    contract's keys; it needs no GPU."""
+    import json
+    import subprocess
+    import sys
+    repo = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(repo, "bench.py"), "--impl", "reference", "--steps", "1",
+                          "--warmup", "0"], capture_output=True, text=True, timeout=600, cwd=repo)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["metric"] == "images/sec for assign+loss+NMS"
+    for key in ("value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+                "vs_baseline", "dtype", "data", "config", "e2e", "cpu_baseline"):
+        assert key in line, key
+    assert line["unit"] == "images/s" and line["higher_is_better"] is True and line["value"] > 0
+    assert "workload" in line["config"]
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0
+    assert line["e2e"]["value"] == line["value"] and line["e2e"]["unit"] == line["unit"]
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    assert line["cpu_baseline"]["value"] == line["value"]
