@@ -1,8 +1,11 @@
 // detect.cu — the eval path (sm_100a): activation + decode + clamp + score threshold +
 // per-class NMS + top-k, batched, no host round trips.
 //
-//   detect_score_kernel  persistent; logits tiles streamed by bulk TMA (same ring as the train
-//                        kernel); one thread per prior row turns the row into probabilities in
+//   detect_score_fast_kernel<C>  2 <= C <= 128 (C = 81 / 21 compile-time): two threads per row, a
+//                        sampling pass fixes a per-image score cutoff, the main pass emits only the
+//                        candidates above it (exact: flagged images are redone without cutoff).
+//   detect_score_kernel  generic (C > 128); persistent; logits tiles streamed by bulk TMA (same ring as
+//                        the train kernel); one thread per prior row turns the row into probabilities in
 //                        place, and every (class, prior) above min_score is emitted as one 64-bit
 //                        key  [0x3F800000 - score_bits : 32][class : 12][prior : 20]  so that
 //                        ascending key order == (score desc, class asc, prior asc) == the order in

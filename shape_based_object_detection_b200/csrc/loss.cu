@@ -1,18 +1,24 @@
 // loss.cu — the fused train path: assignment + log-sum-exp + loc/conf losses + hard-negative
 // mining, forward and backward (sm_100a).
 //
-// Kernels
-//   match_lse_kernel   persistent, one thread per prior row; score tiles streamed HBM->smem by
-//                      1-D bulk TMA through an mbarrier ring; while a tile is in flight the same
-//                      threads compute prior<->GT IoU (GT staged in smem, warp-bbox culled),
-//                      both arg-maxes, then the row log-sum-exp and the CE of the provisional class.
-//   forced_match_kernel per image: the reference's "every object keeps its best prior" override,
-//                      including its filtered-index quirk (SSD512.py:546-553), patches <= G priors.
-//   mine_kernel        per image: positives, loc loss, radix-select top-k sum of negative CE
-//                      (hard-negative mining), selection bits; last block folds the batch.
+// Kernels (forward = match_lse* -> classify -> mine; backward = bwd_patch, or loss_bwd for focal)
+//   match_lse_fast_kernel<C>  2 <= C <= 128 (C = 81 / 21 compile-time): warp-specialised, persistent.
+//                      Stream warps: logits tiles HBM->smem by 1-D bulk TMA through an mbarrier ring,
+//                      one-pass log-sum-exp + background CE, optional zero-fill of the logits gradient.
+//                      Match warps (match role): prior<->GT IoU with slice-bbox culling, both arg-maxes,
+//                      ticket queues per image.
+//   match_lse_kernel   generic fallback (C > 128, or no logits: sbod_assign): one thread per prior row.
+//   forced_match_kernel (sbod_assign) per image: the reference's "every object keeps its best prior"
+//                      override, including its filtered-index quirk (SSD512.py:546-553).
+//   classify_kernel    per 1024 priors: forced-match list rebuilt from the per-object keys and applied,
+//                      classes, true-class CE + loc term of the foreground rows (dense second phase),
+//                      mining candidates, block partials.
+//   mine_kernel        per image: radix-select top-k sum of the candidate CEs (hard-negative mining),
+//                      selection bits; the last block folds the batch and finalises the loss.
 //   mine_batch_kernel  SSD300's batch-global mining (SSD300.py:580-588).
-//   loss_bwd_kernel    grad wrt logits (softmax - onehot on selected rows, zero elsewhere, tiles
-//                      written with bulk TMA stores) and wrt locs.
+//   bwd_patch_kernel   sparse backward (CE + mining): softmax - onehot on the selected rows of a
+//                      zero-filled gradient (zero_fill_kernel when the forward did not fill it), grad wrt locs.
+//   loss_bwd_kernel    dense backward (focal): tile in by TMA, transformed in place, out by TMA store.
 #include <math.h>
 #include <stdlib.h>
 
