@@ -98,3 +98,33 @@ def test_bench_reference_arm_json_contract():
     assert line["e2e"]["value"] == line["value"] and line["e2e"]["unit"] == line["unit"]
     assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
     assert line["cpu_baseline"]["value"] == line["value"]
+
+
+def test_coco_format_results_matches_the_reference_loop():
+    """eval.py:185-213 restated literally (per image, per box) against the batched formatter."""
+    from shape_based_object_detection_b200.eval_results import coco_format_results
+    g = torch.Generator().manual_seed(21)
+    counts = [5, 0, 17, 1]
+    boxes = [torch.rand((n, 4), generator=g) for n in counts]
+    labels = [torch.randint(1, 81, (n,), generator=g) for n in counts]
+    scores = [torch.rand((n,), generator=g) for n in counts]
+    ids = [139, 285, 632, 724]
+    sizes = [(640, 426), (586, 640), (640, 483), (375, 500)]
+    cat = {i: 1000 + i for i in range(1, 81)}
+    want = []
+    for j in range(len(ids)):
+        width, height = sizes[j][0] * 1., sizes[j][1] * 1.
+        bb = boxes[j].clone()
+        bb[:, 2] -= bb[:, 0]
+        bb[:, 3] -= bb[:, 1]
+        bb[:, 0] *= width
+        bb[:, 2] *= width
+        bb[:, 1] *= height
+        bb[:, 3] *= height
+        for k in range(bb.size(0)):
+            want.append({'image_id': ids[j], 'category_id': cat[int(labels[j][k])], 'score': float(scores[j][k]),
+                         'bbox': bb[k, :].tolist()})
+    got = coco_format_results(boxes, labels, scores, ids, sizes, cat)
+    assert got == want
+    assert coco_format_results([torch.zeros((0, 4))], [torch.zeros((0,), dtype=torch.long)], [torch.zeros((0,))],
+                               [1], [(10, 10)], cat) == []
