@@ -44,6 +44,11 @@ typedef void* sbod_stream_t; /* cudaStream_t */
 SBOD_API int sbod_abi_version(void);
 SBOD_API const char* sbod_error_string(int code);
 
+/* Process-wide switches for A/B measurements (no reference counterpart). Defaults: all on. */
+#define SBOD_OPT_PDL 0           /* programmatic dependent launch between the kernels of one call */
+#define SBOD_OPT_PEER_EXCHANGE 1 /* one-shot NVLink exchange of the loss sums (sbod_comm_*) instead of the caller's all-reduce */
+SBOD_API int sbod_set_option(int key, int value);
+
 /* ------------------------------------------------------------------------------------------
  * Dense pairwise IoU.
  *   SBOD_IOU_METRICS  : metrics.py:208-252 find_jaccard_overlap (EPS=1e-5 in the denominator,
@@ -75,6 +80,13 @@ SBOD_API int sbod_box_encode(const float* boxes, const float* priors_cxcy, float
                     float v0, float v1, sbod_stream_t stream);
 SBOD_API int sbod_box_decode(const float* locs, const float* priors_cxcy, float* out, int n, int flavour,
                     float v0, float v1, sbod_stream_t stream);
+
+/* Backward of the six functions above with respect to their first argument (in the reference they are
+ * differentiable torch expressions: IouLoss(pred_mode='Center') back-propagates through decode,
+ * operators/Loss.py:176-178). op: 0 xy_to_cxcy, 1 cxcy_to_xy, 2 cxcy_to_gcxgcy, 3 encode,
+ * 4 gcxgcy_to_cxcy, 5 decode; `in` = the forward input (unused for ops 0 and 1), grad_out / grad_in [n,4]. */
+SBOD_API int sbod_box_op_bwd(int op, const float* in, const float* priors_cxcy, const float* grad_out,
+                    float* grad_in, int n, float v0, float v1, sbod_stream_t stream);
 
 /* RefineDet512.offset2bbox, models/RefineDet512.py:643-653: two-stage decode ARM -> ODM -> xyxy.
  * arm/odm: [N,P,4], priors_cxcy: [P,4], out: [N,P,4]. */
@@ -229,8 +241,11 @@ typedef struct sbod_loss_desc {
 } sbod_loss_desc;
 
 SBOD_API size_t sbod_loss_workspace_bytes(const sbod_loss_desc* d);
-/* The workspace must be zeroed once before its first use (every call leaves it clean again);
- * the same holds for the sbod_assign / sbod_detect workspaces. */
+/* Leading bytes of the loss workspace that must be zero before the first call with a given (N, gmax)
+ * (counters, per-object keys, ticket queues); every call leaves them zero again. The rest is scratch. */
+SBOD_API size_t sbod_loss_workspace_zero_bytes(const sbod_loss_desc* d);
+/* The zero region of a workspace must be cleared once before its first use (every call leaves it clean
+ * again); the same holds for the sbod_assign / sbod_detect workspaces. */
 SBOD_API int sbod_workspace_init(void* workspace, size_t bytes, sbod_stream_t stream);
 SBOD_API int sbod_loss_forward(const sbod_loss_desc* d, sbod_stream_t stream);
 /* Profiling / bench hook: launch one stage of the forward (0 = match + log-sum-exp kernel,
@@ -300,14 +315,18 @@ SBOD_API int sbod_detect_stage(const sbod_detect_desc* d, int stage, sbod_stream
  * line cannot execute. PARITY UNPINNED with respect to the reference (pinned to oracle/ only).
  *   loss = SigmoidFocal(scores, labels)/(n_pos + N) + reg_weight * sum((1-DIoU)*ctr)/sum(ctr)
  *          + BCEWithLogits(centerness[pos], ctr)
- * locations [P,2] cell centres; loc_aux [P,3] = (stride*radius, size-of-interest lo, hi) per location.
+ * locations [P,2] cell centres (normalised image coordinates); loc_aux [P,4] = (centre-sampling radius
+ * in x, in y, size-of-interest lo, hi) per location - two radii because a rectangular input (800 x 1333,
+ * BASELINE config 5) has different strides in the two normalised axes.
+ * Sharding by image: sums[6] = [focal, sum((1-diou)*w), sum(w), bce, n_pos, n_images] is the only data that
+ * crosses GPUs - all-reduce it, then sbod_fcos_finalize on every rank (backward reads the reduced sums).
  * ---------------------------------------------------------------------------------------- */
 typedef struct sbod_fcos_desc {
   const float* locs;        /* [N,P,4] predicted l,t,r,b distances (normalised) */
   const float* scores;      /* [N,P,C] logits; column 0 is unused (Loss.py:51-58) */
   const float* centerness;  /* [N,P] logits */
   const float* locations;   /* [P,2] */
-  const float* loc_aux;     /* [P,3] */
+  const float* loc_aux;     /* [P,4], 16-byte aligned */
   const float* gt_boxes;    /* [T,4] xyxy */
   const int64_t* gt_labels; /* [T] */
   const int32_t* gt_offsets;/* [N+1] */
@@ -316,13 +335,15 @@ typedef struct sbod_fcos_desc {
   float reg_weight, focal_alpha, focal_gamma;
   int32_t* lab;   /* [N,P] label target, 0 = background (written by forward) */
   float* tgt;     /* [N,P,4] l,t,r,b target of the assigned object */
-  double* sums;   /* [5] focal, sum((1-diou)*w), sum(w), bce, n_pos */
+  double* sums;   /* [6] focal, sum((1-diou)*w), sum(w), bce, n_pos, n_images */
   float* loss;    /* [4] total, conf, loc, center */
   void* workspace;
   size_t workspace_bytes;
 } sbod_fcos_desc;
 SBOD_API size_t sbod_fcos_workspace_bytes(const sbod_fcos_desc* d);
 SBOD_API int sbod_fcos_forward(const sbod_fcos_desc* d, sbod_stream_t stream);
+/* Recompute d->loss from d->sums (after a cross-GPU all-reduce of d->sums). */
+SBOD_API int sbod_fcos_finalize(const sbod_fcos_desc* d, sbod_stream_t stream);
 SBOD_API int sbod_fcos_backward(const sbod_fcos_desc* d, const float* grad_loss, float* grad_locs,
                        float* grad_scores, float* grad_center, sbod_stream_t stream);
 /* FCOS.postprocess: out_scores = sigmoid(cls) * sigmoid(center)[..., None]; out_locs = xyxy boxes */

@@ -24,14 +24,15 @@ BOX_OFFSET, BOX_CENTER, BOX_CORNER = 0, 1, 2
 
 EXPORTS = [
     "sbod_abi_version", "sbod_error_string", "sbod_iou_matrix", "sbod_box_convert",
-    "sbod_box_encode", "sbod_box_decode", "sbod_offset2bbox", "sbod_arm_easy_negative", "sbod_pair_iou_fwd",
+    "sbod_box_encode", "sbod_box_decode", "sbod_box_op_bwd", "sbod_offset2bbox", "sbod_arm_easy_negative", "sbod_pair_iou_fwd",
     "sbod_pair_iou_bwd", "sbod_smooth_l1", "sbod_softmax_focal", "sbod_sigmoid_focal",
     "sbod_nms_workspace_bytes", "sbod_nms", "sbod_assign_workspace_bytes", "sbod_assign",
-    "sbod_match_workspace_bytes", "sbod_match", "sbod_loss_workspace_bytes", "sbod_workspace_init",
+    "sbod_match_workspace_bytes", "sbod_match", "sbod_loss_workspace_bytes", "sbod_loss_workspace_zero_bytes",
+    "sbod_workspace_init", "sbod_set_option",
     "sbod_loss_forward", "sbod_loss_forward_stage", "sbod_detect_stage", "sbod_loss_finalize", "sbod_loss_backward", "sbod_loss_targets",
     "sbod_detect_workspace_bytes", "sbod_detect_workspace_zero_bytes", "sbod_detect",
     "sbod_loss_forward_host_arena_bytes", "sbod_loss_forward_host",
-    "sbod_fcos_workspace_bytes", "sbod_fcos_forward", "sbod_fcos_backward", "sbod_fcos_postprocess",
+    "sbod_fcos_workspace_bytes", "sbod_fcos_forward", "sbod_fcos_finalize", "sbod_fcos_backward", "sbod_fcos_postprocess",
     "sbod_selftest_div", "sbod_map_workspace_bytes", "sbod_map", "sbod_bce_focal", "sbod_diou_nms",
 ]
 
@@ -96,6 +97,7 @@ def _declare(lib):
         "sbod_box_convert": [vp, vp, i32, i32, vp],
         "sbod_box_encode": [vp, vp, vp, i32, i32, f32, f32, vp],
         "sbod_box_decode": [vp, vp, vp, i32, i32, f32, f32, vp],
+        "sbod_box_op_bwd": [i32, vp, vp, vp, vp, i32, f32, f32, vp],
         "sbod_offset2bbox": [vp, vp, vp, vp, i32, i32, vp],
         "sbod_arm_easy_negative": [vp, C.c_longlong, f32, vp, vp],
         "sbod_selftest_div": [vp, vp, C.c_longlong, vp, vp, vp, vp],
@@ -112,6 +114,7 @@ def _declare(lib):
         "sbod_assign": [vp, vp, vp, i32, i32, vp, i32, i32, f32, f32, vp, vp, vp, vp, vp, sz, vp],
         "sbod_match": [f32, vp, i32, vp, i32, f32, f32, vp, i32, vp, vp, vp, sz, vp],
         "sbod_workspace_init": [vp, sz, vp],
+        "sbod_set_option": [i32, i32],
         "sbod_loss_forward": [C.POINTER(LossDesc), vp],
         "sbod_loss_finalize": [C.POINTER(LossDesc), vp],
         "sbod_loss_forward_stage": [C.POINTER(LossDesc), i32, vp],
@@ -121,6 +124,7 @@ def _declare(lib):
         "sbod_detect": [C.POINTER(DetectDesc), vp],
         "sbod_loss_forward_host": [C.POINTER(LossDesc), i32, vp, vp, sz, vp],
         "sbod_fcos_forward": [C.POINTER(FcosDesc), vp],
+        "sbod_fcos_finalize": [C.POINTER(FcosDesc), vp],
         "sbod_fcos_backward": [C.POINTER(FcosDesc), vp, vp, vp, vp, vp],
         "sbod_fcos_postprocess": [vp, vp, vp, vp, i32, i32, i32, vp, vp, vp],
     }
@@ -133,6 +137,7 @@ def _declare(lib):
         "sbod_assign_workspace_bytes": [i32, i32],
         "sbod_match_workspace_bytes": [i32, i32],
         "sbod_loss_workspace_bytes": [C.POINTER(LossDesc)],
+        "sbod_loss_workspace_zero_bytes": [C.POINTER(LossDesc)],
         "sbod_detect_workspace_bytes": [C.POINTER(DetectDesc)],
         "sbod_detect_workspace_zero_bytes": [C.POINTER(DetectDesc)],
         "sbod_loss_forward_host_arena_bytes": [C.POINTER(LossDesc), i32],
@@ -167,8 +172,10 @@ def check(rc):
         raise SbodError(f"libsbod: {lib().sbod_error_string(rc).decode()} (code {rc})")
 
 
-def stream_ptr():
-    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+def stream_ptr(device=None):
+    """cudaStream_t of torch's current stream on `device` (default: the current device). Entry points
+    run under on_device(), so "current device" is the device of the tensors they were handed."""
+    return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
 
 
 def ptr(t):
@@ -184,6 +191,42 @@ def need_cuda(*tensors):
                             f"{t.device} tensor")
 
 
+def _cuda_devices(obj, found):
+    if isinstance(obj, torch.Tensor):
+        if obj.is_cuda:
+            found.add(obj.device.index)
+    elif isinstance(obj, (list, tuple)):
+        for o in obj:
+            _cuda_devices(o, found)
+
+
+def device_of(*objs):
+    """The one CUDA device the tensors in `objs` (tensors, nested lists / tuples) live on, or None when
+    there is no CUDA tensor among them. Mixed devices are rejected: every sbod_* kernel takes raw
+    pointers and launches on a single device."""
+    found = set()
+    _cuda_devices(objs, found)
+    if len(found) > 1:
+        raise SbodError("sbod operators need all tensors on ONE CUDA device; got devices %s" % sorted(found))
+    return torch.device("cuda", found.pop()) if found else None
+
+
+def on_device(fn):
+    """Decorator of the public entry points: run `fn` with the tensors' device as the current CUDA device,
+    so that stream_ptr(), the allocations and every kernel launch of the call target that device
+    (the reference picks cuda:1 when config.device == 1, train_anchor.py:66-67)."""
+    import functools
+
+    @functools.wraps(fn)
+    def wrapper(*args, **kwargs):
+        dev = device_of(args, tuple(kwargs.values()))
+        if dev is None or dev.index == torch.cuda.current_device():
+            return fn(*args, **kwargs)
+        with torch.cuda.device(dev):
+            return fn(*args, **kwargs)
+    return wrapper
+
+
 def f32c(t):
     """fp32, contiguous, 16-byte aligned view/copy of t."""
     if t.dtype != torch.float32:
@@ -195,19 +238,41 @@ def f32c(t):
     return t
 
 
+def bucket(n):
+    """Next power of two >= max(n, 1): data-dependent sizes (objects per image, boxes per NMS call) are
+    rounded up before they size a workspace, so a training run sees a handful of layouts, not one per batch."""
+    n = max(int(n), 1)
+    return 1 << (n - 1).bit_length()
+
+
 class Workspace:
-    """Grow-only, zero-initialised device scratch, one per (device, tag)."""
+    """Grow-only device scratch, ONE buffer per (device, stream, tag).
+
+    * Per stream: two calls of the same operator on two streams (the train and the eval half of a step,
+      ARM and ODM criteria on side streams) never share scratch, and the zero-initialisation is enqueued
+      on the stream that uses the buffer.
+    * Zero contract (sbod.h): the leading `zero_bytes` of a workspace must be zero before the first call
+      with a given layout; every call leaves them zero again. `layout` names what the carve-up depends
+      on; when it changes (or the buffer grows) the zero region is cleared again on the current stream.
+    """
 
     _cache = {}
 
     @classmethod
-    def get(cls, device, tag, nbytes, zero_bytes=None):
-        key = (device.index if device.index is not None else torch.cuda.current_device(), tag)
-        buf = cls._cache.get(key)
-        if buf is None or buf.numel() < nbytes:
-            buf = torch.empty(int(nbytes) + 256, dtype=torch.uint8, device=device)
+    def get(cls, device, tag, nbytes, zero_bytes=None, layout=None):
+        index = device.index if device.index is not None else torch.cuda.current_device()
+        stream = torch.cuda.current_stream(device)
+        key = (index, stream.cuda_stream, tag)
+        ent = cls._cache.get(key)
+        z = int(nbytes if zero_bytes is None else zero_bytes)
+        layout = () if layout is None else layout
+        if ent is None or ent[0].numel() < int(nbytes) + 256:
             # torch's allocator returns >=512-byte aligned blocks
-            z = nbytes if zero_bytes is None else zero_bytes
-            check(lib().sbod_workspace_init(ptr(buf), C.c_size_t(int(z)), stream_ptr()))
-            cls._cache[key] = buf
-        return buf
+            buf = torch.empty(int(nbytes) + 256, dtype=torch.uint8, device=device)
+            ent = [buf, None]  # None never equals a layout: the fresh buffer is cleared below
+            cls._cache[key] = ent
+        if ent[1] != layout:
+            if z > 0:
+                check(lib().sbod_workspace_init(ptr(ent[0]), C.c_size_t(z), C.c_void_p(stream.cuda_stream)))
+            ent[1] = layout
+        return ent[0]

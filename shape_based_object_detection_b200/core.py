@@ -71,7 +71,9 @@ class LossState:
         d.gt_boxes, d.gt_labels, d.gt_offsets = (self.gt_boxes.data_ptr(), self.gt_labels.data_ptr(),
                                                  self.gt_offsets.data_ptr())
         d.exclude = exclude.data_ptr() if exclude is not None else None
-        d.N, d.P, d.C, d.gmax = N, P, Cn, max(self.gmax, 1)
+        # objects per image change from batch to batch: the per-object tables are sized for the next power
+        # of two, so a run sees a handful of workspace layouts instead of one per distinct maximum
+        d.N, d.P, d.C, d.gmax = N, P, Cn, L.bucket(self.gmax)
         # python-float thresholds are compared in fp32 by torch (SURVEY §8a''): cast here
         d.thr_pos = float(np.float32(spec.threshold))
         d.thr_neg = float(np.float32(spec.threshold - spec.neg_margin))
@@ -84,7 +86,8 @@ class LossState:
                                            self.ce.data_ptr(), self.sel.data_ptr())
         d.partials, d.sums, d.loss = self.partials.data_ptr(), self.sums.data_ptr(), self.loss.data_ptr()
         nbytes = L.lib().sbod_loss_workspace_bytes(C.byref(d))
-        self.ws = L.Workspace.get(dev, ("loss", N, P, d.gmax), nbytes)
+        zbytes = L.lib().sbod_loss_workspace_zero_bytes(C.byref(d))
+        self.ws = L.Workspace.get(dev, "loss", nbytes, zero_bytes=zbytes, layout=(N, P, d.gmax))
         d.workspace, d.workspace_bytes = self.ws.data_ptr(), nbytes
         # the gradient wrt the logits is zero almost everywhere: let the forward stream zero-fill it
         self.grad_scores = torch.empty_like(scores) if prefill_grad else None
@@ -92,10 +95,12 @@ class LossState:
         self.desc = d
 
     def forward(self):
-        L.check(L.lib().sbod_loss_forward(C.byref(self.desc), L.stream_ptr()))
+        with torch.cuda.device(self.scores.device):
+            L.check(L.lib().sbod_loss_forward(C.byref(self.desc), L.stream_ptr()))
 
     def finalize(self):
-        L.check(L.lib().sbod_loss_finalize(C.byref(self.desc), L.stream_ptr()))
+        with torch.cuda.device(self.scores.device):
+            L.check(L.lib().sbod_loss_finalize(C.byref(self.desc), L.stream_ptr()))
 
     def backward(self, grad_loss, want_locs=True, want_scores=True):
         dev = self.scores.device
@@ -108,14 +113,16 @@ class LossState:
             if g_scores is None:
                 g_scores = torch.empty_like(self.scores)
         gl = grad_loss.to(device=dev, dtype=torch.float32).reshape(1).contiguous()
-        L.check(L.lib().sbod_loss_backward(C.byref(self.desc), L.ptr(gl), L.ptr(g_locs), L.ptr(g_scores),
-                                           L.stream_ptr()))
+        with torch.cuda.device(dev):
+            L.check(L.lib().sbod_loss_backward(C.byref(self.desc), L.ptr(gl), L.ptr(g_locs), L.ptr(g_scores),
+                                               L.stream_ptr()))
         return g_locs, g_scores
 
     def backward_into(self, grad_loss, g_locs, g_scores):
         """Backward into caller-owned buffers (no allocation)."""
-        L.check(L.lib().sbod_loss_backward(C.byref(self.desc), L.ptr(grad_loss), L.ptr(g_locs), L.ptr(g_scores),
-                                           L.stream_ptr()))
+        with torch.cuda.device(self.scores.device):
+            L.check(L.lib().sbod_loss_backward(C.byref(self.desc), L.ptr(grad_loss), L.ptr(g_locs), L.ptr(g_scores),
+                                               L.stream_ptr()))
         return g_locs, g_scores
 
     def targets(self):
@@ -123,7 +130,8 @@ class LossState:
         dev = self.scores.device
         cls = torch.empty((self.N, self.P), dtype=torch.int64, device=dev)
         neg = torch.empty((self.N, self.P), dtype=torch.int64, device=dev)
-        L.check(L.lib().sbod_loss_targets(C.byref(self.desc), L.ptr(cls), L.ptr(neg), L.stream_ptr()))
+        with torch.cuda.device(dev):
+            L.check(L.lib().sbod_loss_targets(C.byref(self.desc), L.ptr(cls), L.ptr(neg), L.stream_ptr()))
         return cls, neg
 
 
@@ -152,6 +160,7 @@ class _FusedLossFn(torch.autograd.Function):
         return g_locs, g_scores, None
 
 
+@L.on_device
 def fused_loss(spec, priors_cxcy, priors_xy, predicted_locs, predicted_scores, boxes, labels,
                anchors_xy=None, exclude=None, group=None, holder=None, packed_gt=None):
     """Run the fused train path. Returns a 0-dim fp32 tensor with grad_fn.
@@ -164,6 +173,11 @@ def fused_loss(spec, priors_cxcy, priors_xy, predicted_locs, predicted_scores, b
     n_priors = priors_cxcy.size(0)
     assert n_priors == predicted_locs.size(1) == predicted_scores.size(1)  # SSD512.py:523
     gt = packed_gt if packed_gt is not None else pack_ground_truth(boxes, labels, dev)
+    if group is not None and spec.cls_kind == L.CLS_CE_MINE_BATCH:
+        # SSD300 mines its hard negatives over the WHOLE batch (SSD300.py:580-588): a rank's own top-k cannot
+        # be rebuilt from per-rank sums, so this variant does not shard ("replicas only")
+        raise L.SbodError("MultiBoxLoss300's batch-global hard-negative mining cannot be sharded by image: "
+                          "run it with process_group=None (one replica per GPU)")
     holder = holder if holder is not None else {}
     holder["group"] = group
     # decided here: inside autograd.Function.forward grad mode is off. With CE + mining the gradient of
@@ -182,6 +196,7 @@ def fused_loss(spec, priors_cxcy, priors_xy, predicted_locs, predicted_scores, b
 # ---------------------------------------------------------------------------------------------
 # stand-alone batched assignment
 # ---------------------------------------------------------------------------------------------
+@L.on_device
 def assign(boxes, labels, anchors_xy, threshold=0.5, neg_margin=0.1, want_classes=True):
     """Batched assignment; anchors_xy [P,4] or [N,P,4]. Returns ov, obj(int32), true_classes, true_neg."""
     L.need_cuda(anchors_xy)
@@ -195,9 +210,10 @@ def assign(boxes, labels, anchors_xy, threshold=0.5, neg_margin=0.1, want_classe
     obj = torch.empty((N, P), dtype=torch.int32, device=dev)
     cls = torch.empty((N, P), dtype=torch.int64, device=dev) if want_classes else None
     neg = torch.empty((N, P), dtype=torch.int64, device=dev) if want_classes else None
-    nbytes = L.lib().sbod_assign_workspace_bytes(N, max(gmax, 1))
-    ws = L.Workspace.get(dev, ("assign", N, max(gmax, 1)), nbytes)
-    L.check(L.lib().sbod_assign(L.ptr(gt_b), L.ptr(gt_l), L.ptr(gt_o), N, max(gmax, 1), L.ptr(a),
+    gmax = L.bucket(gmax)
+    nbytes = L.lib().sbod_assign_workspace_bytes(N, gmax)
+    ws = L.Workspace.get(dev, "assign", nbytes, layout=(N, gmax))
+    L.check(L.lib().sbod_assign(L.ptr(gt_b), L.ptr(gt_l), L.ptr(gt_o), N, gmax, L.ptr(a),
                                 1 if per_image else 0, P, float(np.float32(threshold)),
                                 float(np.float32(threshold - neg_margin)), L.ptr(ov), L.ptr(obj),
                                 L.ptr(cls), L.ptr(neg), L.ptr(ws), C.c_size_t(nbytes), L.stream_ptr()))
@@ -207,6 +223,7 @@ def assign(boxes, labels, anchors_xy, threshold=0.5, neg_margin=0.1, want_classe
 # ---------------------------------------------------------------------------------------------
 # eval path
 # ---------------------------------------------------------------------------------------------
+@L.on_device
 def make_detect_desc(predicted_locs, predicted_scores, min_score, max_overlap, top_k, priors_cxcy=None,
                      act="softmax", box_type="offset", clamp_inplace=False, prior_keep=None,
                      second_nms_thr=-1.0, pre_nms_topk=0):
@@ -246,12 +263,13 @@ def make_detect_desc(predicted_locs, predicted_scores, min_score, max_overlap, t
     d.out_prior, d.out_counts, d.out_cap = out_prior.data_ptr(), out_counts.data_ptr(), cap
     nbytes = L.lib().sbod_detect_workspace_bytes(C.byref(d))
     zbytes = L.lib().sbod_detect_workspace_zero_bytes(C.byref(d))
-    ws = L.Workspace.get(dev, ("detect", N, P, Cn), nbytes, zero_bytes=zbytes)
+    ws = L.Workspace.get(dev, "detect", nbytes, zero_bytes=zbytes, layout=(N, P, Cn, float(min_score)))
     d.workspace, d.workspace_bytes = ws.data_ptr(), nbytes
     return {"desc": d, "outputs": (out_boxes, out_labels, out_scores, out_prior, out_counts),
             "alive": (locs, scores, pri, keep, ws)}
 
 
+@L.on_device
 def detect_batched(predicted_locs, predicted_scores, min_score, max_overlap, top_k, priors_cxcy=None,
                    act="softmax", box_type="offset", clamp_inplace=False, prior_keep=None,
                    second_nms_thr=-1.0, pre_nms_topk=0):
@@ -263,6 +281,7 @@ def detect_batched(predicted_locs, predicted_scores, min_score, max_overlap, top
     return call["outputs"]
 
 
+@L.on_device
 def detect_begin(predicted_locs, predicted_scores, min_score, max_overlap, top_k, priors_cxcy=None,
                  act="softmax", box_type="offset", clamp_inplace=False, prior_keep=None,
                  second_nms_thr=-1.0, pre_nms_topk=0, side_stream=None):
@@ -283,9 +302,10 @@ def detect_begin(predicted_locs, predicted_scores, min_score, max_overlap, top_k
 
 def detect_end(call):
     """Second half of detect_begin: main score pass + NMS on the current stream."""
-    if call.get("side") is not None:
-        torch.cuda.current_stream().wait_stream(call["side"])
-    L.check(L.lib().sbod_detect_stage(C.byref(call["desc"]), 4, L.stream_ptr()))
+    with torch.cuda.device(call["outputs"][0].device):
+        if call.get("side") is not None:
+            torch.cuda.current_stream().wait_stream(call["side"])
+        L.check(L.lib().sbod_detect_stage(C.byref(call["desc"]), 4, L.stream_ptr()))
     return call["outputs"]
 
 

@@ -115,6 +115,40 @@ __global__ void box_decode_kernel(const float4* __restrict__ locs, const float4*
   }
 }
 
+// Backward of the converters / codec with respect to their FIRST argument (the boxes or offsets; the
+// priors are constants on the path). op: 0 xy_to_cxcy, 1 cxcy_to_xy, 2 encode (transforms), 3 encode
+// (iou_utils), 4 decode (transforms), 5 decode (iou_utils). `in` is the forward input.
+__global__ void box_op_bwd_kernel(int op, const float4* __restrict__ in, const float4* __restrict__ pri,
+                                  const float4* __restrict__ go, float4* __restrict__ gi, int n, float v0,
+                                  float v1) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const float4 g = go[i];
+    float4 r;
+    if (op == 0) {  // out = ((x2+x1)/2, (y2+y1)/2, x2-x1, y2-y1)
+      r = make_float4(0.5f * g.x - g.z, 0.5f * g.y - g.w, 0.5f * g.x + g.z, 0.5f * g.y + g.w);
+    } else if (op == 1) {  // out = (cx - w/2, cy - h/2, cx + w/2, cy + h/2)
+      r = make_float4(g.x + g.z, g.y + g.w, 0.5f * (g.z - g.x), 0.5f * (g.w - g.y));
+    } else {
+      const float4 a = in[i], p = pri[i];
+      if (op == 2) {  // ((c - pc) / (pwh / 10), log(wh / pwh) * 5)
+        r = make_float4(g.x * 10.f / p.z, g.y * 10.f / p.w, g.z * 5.f / a.z, g.w * 5.f / a.w);
+      } else if (op == 3) {  // (((x1+x2)/2 - pc) / (v0 pwh), log((x2-x1) / pwh) / v1)
+        const float cx = g.x / (2.f * v0 * p.z), cy = g.y / (2.f * v0 * p.w);
+        const float sw = g.z / (v1 * (a.z - a.x)), sh = g.w / (v1 * (a.w - a.y));
+        r = make_float4(cx - sw, cy - sh, cx + sw, cy + sh);
+      } else if (op == 4) {  // (l_c * pwh / 10 + pc, exp(l_wh / 5) * pwh)
+        r = make_float4(g.x * p.z / 10.f, g.y * p.w / 10.f, g.z * expf(a.z / 5.f) * p.z / 5.f,
+                        g.w * expf(a.w / 5.f) * p.w / 5.f);
+      } else {  // c = pc + l_c v0 pwh; wh = pwh exp(l_wh v1); out = (c - wh/2, c + wh/2)
+        const float w = p.z * expf(a.z * v1), h = p.w * expf(a.w * v1);
+        r = make_float4((g.x + g.z) * v0 * p.z, (g.y + g.w) * v0 * p.w, 0.5f * (g.z - g.x) * w * v1,
+                        0.5f * (g.w - g.y) * h * v1);
+      }
+    }
+    gi[i] = r;
+  }
+}
+
 __global__ void offset2bbox_kernel(const float4* __restrict__ arm, const float4* __restrict__ odm,
                                    const float4* __restrict__ pri, float4* __restrict__ out, int N,
                                    int P) {
@@ -547,6 +581,18 @@ extern "C" int sbod_box_decode(const float* locs, const float* priors_cxcy, floa
   return SBOD_OK;
 }
 
+extern "C" int sbod_box_op_bwd(int op, const float* in, const float* priors_cxcy, const float* grad_out,
+                               float* grad_in, int n, float v0, float v1, sbod_stream_t stream) {
+  if (n < 0 || !grad_out || !grad_in || op < 0 || op > 5) return SBOD_ERR_INVALID;
+  if (op >= 2 && (!in || !priors_cxcy)) return SBOD_ERR_INVALID;
+  if (n == 0) return SBOD_OK;
+  box_op_bwd_kernel<<<grid_for(n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      op, reinterpret_cast<const float4*>(in), reinterpret_cast<const float4*>(priors_cxcy),
+      reinterpret_cast<const float4*>(grad_out), reinterpret_cast<float4*>(grad_in), n, v0, v1);
+  SBOD_LAUNCH_CHECK();
+  return SBOD_OK;
+}
+
 extern "C" int sbod_offset2bbox(const float* arm_locs, const float* odm_locs,
                                 const float* priors_cxcy, float* out, int N, int P,
                                 sbod_stream_t stream) {
@@ -743,11 +789,11 @@ extern "C" int sbod_match(float threshold, const float* truths, int G, const flo
   w += align_up(size_t(P) * 4, 256);
   int* best_idx = reinterpret_cast<int*>(w);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  static bool attr_done = false;
-  if (!attr_done) {
+  static DeviceOnce attr_once;
+  if (attr_once.pending()) {
     SBOD_CUDA_TRY(cudaFuncSetAttribute(match_best_kernel,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-    attr_done = true;
+    attr_once.mark();
   }
   match_best_kernel<<<grid_for(P, 256), 256, size_t(G) * 16, st>>>(
       reinterpret_cast<const float4*>(truths), G, reinterpret_cast<const float4*>(priors_cxcy), P,

@@ -1233,10 +1233,13 @@ static int detect_run(const sbod_detect_desc* d, sbod_stream_t stream, int stage
   level0_layout(d->min_score, &q.shift0, &q.n_bins);
   q.cand_cap = cand_capacity(d);
   q.kcap = kept_capacity(d);
+  q.debug_skip = 0;
+#ifdef SBOD_DEBUG_HOOKS  // profiling builds only: release builds never read the environment
   {
     const char* e = getenv("SBOD_DEBUG_SKIP");
     q.debug_skip = e ? atoi(e) : 0;
   }
+#endif
   unsigned char* w = static_cast<unsigned char*>(d->workspace);
   q.cand_count = reinterpret_cast<unsigned int*>(w); w += align_up(size_t(q.N) * 4, 256);
   q.hist = reinterpret_cast<unsigned int*>(w);       w += align_up(size_t(q.N) * kMaxBins * 4, 256);
@@ -1251,7 +1254,9 @@ static int detect_run(const sbod_detect_desc* d, sbod_stream_t stream, int stage
   q.speculate = 0;
   q.sample_stride = 26;
   q.sample_target = 4 * (q.top_k + 1) + 1024;
+#ifdef SBOD_DEBUG_HOOKS
   if (getenv("SBOD_TARGET")) q.sample_target = atoi(getenv("SBOD_TARGET"));
+#endif
   // hist rows are n_bins wide inside the kMaxBins-strided allocation
   const DTiling t = choose_dtiling(q.C);
   q.rows_per_tile = t.rows;
@@ -1261,8 +1266,8 @@ static int detect_run(const sbod_detect_desc* d, sbod_stream_t stream, int stage
   q.stage_floats = t.stage_floats;
 
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  static bool attr_done = false;
-  if (!attr_done) {
+  static DeviceOnce attr_once;
+  if (attr_once.pending()) {
     SBOD_CUDA_TRY(cudaFuncSetAttribute(detect_score_kernel,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     SBOD_CUDA_TRY(cudaFuncSetAttribute(detect_score_fast_kernel<81>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
@@ -1271,7 +1276,7 @@ static int detect_run(const sbod_detect_desc* d, sbod_stream_t stream, int stage
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024));
     SBOD_CUDA_TRY(cudaFuncSetAttribute(detect_nms_kernel,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
-    attr_done = true;
+    attr_once.mark();
   }
   int ctas_per_sm = int((220 * 1024) / (t.smem + 2 * 1024));
   if (ctas_per_sm < 1) ctas_per_sm = 1;

@@ -21,7 +21,7 @@ struct FcosParams {
   const float* scores;       // [N,P,C] logits
   const float* centerness;   // [N,P] logits
   const float2* locations;   // [P] cell centres
-  const float* aux;          // [P,3]: centre-sampling radius, size-of-interest lo, hi
+  const float* aux;          // [P,4]: centre-sampling radius in x and in y, size-of-interest lo, hi
   const float4* gt_boxes;
   const int64_t* gt_labels;
   const int32_t* gt_offsets;
@@ -31,7 +31,7 @@ struct FcosParams {
   int32_t* lab;              // [N,P]
   float4* tgt;               // [N,P] ltrb target
   double* blockpart;         // [N, nblk, 5]
-  double* sums;              // [5]: focal, sum(l*w), sum(w), bce, n_pos
+  double* sums;              // [6]: focal, sum(l*w), sum(w), bce, n_pos, n_images
   float* loss;               // [4]: total, conf, loc, center
 };
 
@@ -44,12 +44,14 @@ __global__ void __launch_bounds__(256) fcos_assign_kernel(const FcosParams q) {
   const int G = q.gt_offsets[n + 1] - g0;
   const bool valid = p < q.P;
   float2 xy = make_float2(0.f, 0.f);
-  float rad = 0.f, lo = 0.f, hi = 0.f;
+  float rad_x = 0.f, rad_y = 0.f, lo = 0.f, hi = 0.f;
   if (valid) {
     xy = q.locations[p];
-    rad = q.aux[p * 3 + 0];
-    lo = q.aux[p * 3 + 1];
-    hi = q.aux[p * 3 + 2];
+    const float4 a = reinterpret_cast<const float4*>(q.aux)[p];
+    rad_x = a.x;
+    rad_y = a.y;
+    lo = a.z;
+    hi = a.w;
   }
   float best_area = kFcosInf;  // locs_gt_area.min(dim=1): first index among ties (FCOSDet.py:416)
   int best = 0;
@@ -71,8 +73,8 @@ __global__ void __launch_bounds__(256) fcos_assign_kernel(const FcosParams q) {
       bool inside;
       if (q.center_sample) {  // FCOSDet.py:424-474: the object's centre box of half-size stride*radius, clipped to the object
         const float cx = __fdiv_rn(__fadd_rn(b.x, b.z), 2.f), cy = __fdiv_rn(__fadd_rn(b.y, b.w), 2.f);
-        const float x0 = __fsub_rn(cx, rad), y0 = __fsub_rn(cy, rad);
-        const float x1 = __fadd_rn(cx, rad), y1 = __fadd_rn(cy, rad);
+        const float x0 = __fsub_rn(cx, rad_x), y0 = __fsub_rn(cy, rad_y);
+        const float x1 = __fadd_rn(cx, rad_x), y1 = __fadd_rn(cy, rad_y);
         const float bx0 = x0 > b.x ? x0 : b.x, by0 = y0 > b.y ? y0 : b.y;
         const float bx1 = x1 < b.z ? x1 : b.z, by1 = y1 < b.w ? y1 : b.w;
         const float m = fminf(fminf(__fsub_rn(xy.x, bx0), __fsub_rn(xy.y, by0)),
@@ -133,7 +135,7 @@ __global__ void __launch_bounds__(128) fcos_terms_kernel(const FcosParams q, con
   if (BACKWARD) {
     const double npos = q.sums[4], sw = q.sums[2];
     const float gout = grad_loss ? *grad_loss : 1.f;
-    s_conf = float(double(gout) / (npos + double(q.N)));
+    s_conf = float(double(gout) / (npos + q.sums[5]));  // sums[5]: images of the whole (possibly sharded) batch
     weighted = sw > 1e-6;  // IouLoss: weights branch only if their sum is > 1e-6 (Loss.py:192-199)
     s_loc = npos > 0.0 ? float(double(gout) * double(q.reg_weight) / (weighted ? sw : npos)) : 0.f;
     s_ctr = npos > 0.0 ? float(double(gout) / npos) : 0.f;
@@ -203,29 +205,39 @@ __global__ void __launch_bounds__(128) fcos_terms_kernel(const FcosParams q, con
   }
 }
 
-// fold the block partials in a fixed order and form the loss (FCOSDet.py:527-544)
+// loss from the six sums (FCOSDet.py:527-544); the sums may have been all-reduced over the ranks
+SBOD_DEVINL void fcos_finalize(const FcosParams& q, const double* tot) {
+  const double npos = tot[4];
+  const double conf = tot[0] / (npos + tot[5]);
+  double loc = 0.0, ctr = 0.0;
+  if (npos > 0.0) {
+    loc = tot[2] > 1e-6 ? tot[1] / tot[2] : tot[1] / npos;
+    ctr = tot[3] / npos;
+  }
+  q.loss[0] = float(conf + double(q.reg_weight) * loc + ctr);
+  q.loss[1] = float(conf);
+  q.loss[2] = float(loc);
+  q.loss[3] = float(ctr);
+}
+
+// fold the block partials in a fixed order and form the loss
 __global__ void __launch_bounds__(256) fcos_finalize_kernel(const FcosParams q, int n_parts) {
   __shared__ double s_red[34];
   double acc[5] = {0, 0, 0, 0, 0};
   // each thread sums a strided subset, then a block sum: the order is fixed by the launch shape
   for (int i = threadIdx.x; i < n_parts; i += blockDim.x)
     for (int k = 0; k < 5; ++k) acc[k] += q.blockpart[size_t(i) * 5 + k];
-  double tot[5];
+  double tot[6];
   for (int k = 0; k < 5; ++k) tot[k] = block_sum(acc[k], s_red);
+  tot[5] = double(q.N);
   if (threadIdx.x == 0) {
-    for (int k = 0; k < 5; ++k) q.sums[k] = tot[k];
-    const double npos = tot[4];
-    const double conf = tot[0] / (npos + double(q.N));
-    double loc = 0.0, ctr = 0.0;
-    if (npos > 0.0) {
-      loc = tot[2] > 1e-6 ? tot[1] / tot[2] : tot[1] / npos;
-      ctr = tot[3] / npos;
-    }
-    q.loss[0] = float(conf + double(q.reg_weight) * loc + ctr);
-    q.loss[1] = float(conf);
-    q.loss[2] = float(loc);
-    q.loss[3] = float(ctr);
+    for (int k = 0; k < 6; ++k) q.sums[k] = tot[k];
+    fcos_finalize(q, tot);
   }
+}
+
+__global__ void fcos_refinalize_kernel(const FcosParams q) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) fcos_finalize(q, q.sums);
 }
 
 // ---- FCOS.postprocess (FCOSDet.py:253-270) -------------------------------------------------------
@@ -255,6 +267,7 @@ static int fill_fcos(const sbod_fcos_desc* d, FcosParams& q, int* nblk) {
   const size_t need = align_up(size_t(d->N) * *nblk * 5 * 8, 256);
   if (!d->workspace || d->workspace_bytes < need) return SBOD_ERR_WORKSPACE;
   if (reinterpret_cast<uintptr_t>(d->workspace) & 255) return SBOD_ERR_WORKSPACE;
+  if (reinterpret_cast<uintptr_t>(d->loc_aux) & 15) return SBOD_ERR_ALIGNMENT;
   q.locs = reinterpret_cast<const float4*>(d->locs);
   q.scores = d->scores;
   q.centerness = d->centerness;
@@ -296,6 +309,16 @@ extern "C" int sbod_fcos_forward(const sbod_fcos_desc* d, sbod_stream_t stream) 
   fcos_terms_kernel<false><<<gt, 128, 0, st>>>(q, nullptr, nullptr, nullptr, nullptr);
   SBOD_LAUNCH_CHECK();
   fcos_finalize_kernel<<<1, 256, 0, st>>>(q, nblk * q.N);
+  SBOD_LAUNCH_CHECK();
+  return SBOD_OK;
+}
+
+extern "C" int sbod_fcos_finalize(const sbod_fcos_desc* d, sbod_stream_t stream) {
+  FcosParams q;
+  int nblk = 0;
+  int rc = fill_fcos(d, q, &nblk);
+  if (rc) return rc;
+  fcos_refinalize_kernel<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(q);
   SBOD_LAUNCH_CHECK();
   return SBOD_OK;
 }

@@ -1,7 +1,7 @@
 // loss.cu — the fused train path: assignment + log-sum-exp + loc/conf losses + hard-negative
 // mining, forward and backward (sm_100a).
 //
-// Kernels (forward = match_lse* -> classify -> mine; backward = bwd_patch, or loss_bwd for focal)
+// Kernels (forward = match_lse* -> classify_mine; backward = bwd_patch, or loss_bwd for focal)
 //   match_lse_fast_kernel<C>  2 <= C <= 128 (C = 81 / 21 compile-time): warp-specialised, persistent.
 //                      Stream warps: logits tiles HBM->smem by 1-D bulk TMA through an mbarrier ring,
 //                      one-pass log-sum-exp + background CE, optional zero-fill of the logits gradient.
@@ -10,28 +10,31 @@
 //   match_lse_kernel   generic fallback (C > 128, or no logits: sbod_assign): one thread per prior row.
 //   forced_match_kernel (sbod_assign) per image: the reference's "every object keeps its best prior"
 //                      override, including its filtered-index quirk (SSD512.py:546-553).
-//   classify_kernel    per 1024 priors: forced-match list rebuilt from the per-object keys and applied,
-//                      classes, true-class CE + loc term of the foreground rows (dense second phase),
-//                      mining candidates, block partials.
-//   mine_kernel        per image: radix-select top-k sum of the candidate CEs (hard-negative mining),
-//                      selection bits; the last block folds the batch and finalises the loss.
-//   mine_batch_kernel  SSD300's batch-global mining (SSD300.py:580-588).
+//   classify_mine_kernel  one thread-block cluster per image: forced-match list rebuilt from the per-object keys
+//                      and applied, classes, true-class CE + loc term of the foreground rows, mining
+//                      candidates in shared memory, cluster-wide radix select (distributed shared memory
+//                      histograms) of the top-k candidate CEs, selection bits; the last image folds the
+//                      batch and finalises the loss. Programmatic dependent launch behind the match kernel.
+//   mine_batch_kernel  SSD300's batch-global mining (SSD300.py:580-588), one cluster of 8 CTAs.
 //   bwd_patch_kernel   sparse backward (CE + mining): softmax - onehot on the selected rows of a
 //                      zero-filled gradient (zero_fill_kernel when the forward did not fill it), grad wrt locs.
 //   loss_bwd_kernel    dense backward (focal): tile in by TMA, transformed in place, out by TMA store.
 #include <math.h>
 #include <stdlib.h>
 
+#include <cooperative_groups.h>
+
 #include "common.cuh"
 #include "pair_iou.cuh"
 #include "row_stream.cuh"
+
+namespace cg = cooperative_groups;
 
 namespace sbod {
 
 constexpr int kRows = 128;      // threads per CTA == max rows per streamed tile
 constexpr int kGtChunk = 256;   // GT boxes staged in smem at a time
 constexpr int kMaxStages = 4;
-constexpr int kMineThreads = 1024;
 constexpr int kBins = 4096;     // radix-select digit = 12 bits
 
 struct LossParams {
@@ -59,14 +62,14 @@ struct LossParams {
   // workspace
   unsigned long long* gtkey;  // [N, gmax]
   float* cand;                // [N, P]
-  double* blockpart;          // [N, ceil(P/1024), 4]
   unsigned int* counters;     // [4]
   unsigned int* match_q;      // [N] per-image chunk queues of the match role
   // tiling
   int rows_per_tile, tiles_per_image, n_tiles, n_stages;
   uint32_t stage_floats;
   int with_scores;
-  int mine_cache;  // mine_kernel keeps the P candidate values of its image in shared memory
+  int mine_cache;  // classify_mine_kernel keeps the candidate values of its slice in shared memory
+  int cm_cluster;  // CTAs per image of classify_mine_kernel
   int fast;        // odd C <= 128: warp-specialised two-threads-per-row kernels
   int ctas_per_sm;
   int debug_skip;  // SBOD_DEBUG_SKIP: bit0 = no stream role, bit1 = no match role (profiling only)
@@ -118,6 +121,7 @@ __global__ void __launch_bounds__(kRows) match_lse_kernel(const LossParams q) {
 
   const int tid = threadIdx.x, lane = tid & 31;
   const int n_my = (q.n_tiles - int(blockIdx.x) + int(gridDim.x) - 1) / int(gridDim.x);
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");  // the next kernel may start its prologue
 
   if (q.with_scores) {
     if (tid == 0) {
@@ -282,7 +286,7 @@ __global__ void __launch_bounds__(kRows) match_lse_kernel(const LossParams q) {
       q.obj[np] = bobj;
       q.lse[np] = mx + lg;
       // CE against class 0 (background) == -log_softmax[0] in torch's operation order; the few
-      // positive rows are re-evaluated against their true class by mine_kernel.
+      // positive rows are re-evaluated against their true class by classify_mine_kernel.
       q.ce[np] = (mx - row[0]) + lg;
     }
     __syncthreads();  // every thread is done with stage s
@@ -321,6 +325,7 @@ __global__ void __launch_bounds__(kFastThreads, 2) match_lse_fast_kernel(const L
   tile_range(q.n_tiles, blockIdx.x, gridDim.x, t0, t1);
   const int n_my = t1 - t0;
   const int C = kC ? kC : q.C;
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");  // the next kernel may start its prologue
   if (tid == 0) {
     for (int s = 0; s < q.n_stages; ++s) mbar_init(&bars[s], 1);
     fence_mbar_init();
@@ -772,117 +777,142 @@ SBOD_DEVINL float focal_bg(const LossParams& q, float ce) {  // (1-alpha) * p0^g
 }
 
 // ------------------------------------------------------------------------------------------
-// radix select: sum of the k largest candidate values of vals[0..n) (candidates are >= 0,
-// non-candidates are < 0). Returns the sum in every thread; writes threshold bits / number of
-// ties to take so the caller can build the selection mask.
+// Cluster-wide radix select: sum of the k largest candidate values of an array that is split over the
+// CTAs of a thread-block cluster (candidates are >= 0, non-candidates < 0). MSD radix 12 + 12 + 8 bits;
+// every CTA histograms its own slice in shared memory, one cluster barrier later every CTA reads all
+// the slices' histograms through distributed shared memory and finds the digit on its own (same
+// integers, same result in every CTA: nothing has to be broadcast). Two histogram buffers alternate,
+// so one cluster barrier per pass is enough.
 // ------------------------------------------------------------------------------------------
+struct ClusterSelect {
+  unsigned int hist[2][kBins];  // this CTA's digit histograms (read by the peers)
+  double sumv;                  // this CTA's sum of the values above the threshold (read by rank 0)
+  unsigned int ties;            // this CTA's number of candidates equal to the threshold
+  int misc[4];
+  unsigned int wt[32];
+  double red[34];
+};
+
 struct SelectResult {
-  double sum;
+  double sum;         // valid in rank 0 only (whole cluster); other ranks hold their local part
   uint32_t thr_bits;  // value of the k-th largest
   int take_ties;      // how many values == thr are part of the top-k
   int n_ties;         // how many candidates == thr exist
-  int k_eff;
+  long long k_eff;
 };
 
-__device__ SelectResult topk_sum(const float* __restrict__ vals, int n, long long k_want,
-                                 unsigned int* s_hist /*[kBins]*/, double* s_red /*[34]*/,
-                                 int* s_misc /*[8]*/, long long n_cand_known = -1 /* < 0: count here */,
-                                 uint8_t* __restrict__ sel_out = nullptr /* marks the selection in the same pass */) {
-  const int tid = threadIdx.x, nt = blockDim.x;
+// vals: this CTA's slice (shared or global memory), n_local values; sel_out (may be null): selection
+// flags of the slice, bit 1 is set on the selected values (a candidate is never a positive, so the flag
+// byte is written without reading it). All threads of all CTAs of the cluster must call this.
+__device__ SelectResult cluster_topk_sum(cg::cluster_group& cluster, ClusterSelect& S, const float* vals,
+                                         int n_local, long long k_want, long long n_cand,
+                                         uint8_t* __restrict__ sel_out) {
+  const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, wid = tid >> 5;
+  const unsigned int n_ranks = cluster.num_blocks(), my_rank = cluster.block_rank();
   SelectResult r;
-  r.sum = 0.0; r.thr_bits = 0; r.take_ties = 0; r.n_ties = 0; r.k_eff = 0;
-  // number of candidates (classify_kernel already counted them per block when it wrote them)
-  int n_cand;
-  if (n_cand_known >= 0) {
-    n_cand = int(n_cand_known);
-  } else {
-    int cnt = 0;
-    for (int i = tid; i < n; i += nt) cnt += vals[i] >= 0.f ? 1 : 0;
-    n_cand = int(block_sum(double(cnt), s_red) + 0.5);
+  r.sum = 0.0; r.thr_bits = 0; r.take_ties = 0; r.n_ties = 0;
+  const long long k = k_want < n_cand ? k_want : n_cand;
+  r.k_eff = k;
+  if (k <= 0) {  // cluster-uniform: nothing is selected
+    if (tid == 0) { S.sumv = 0.0; S.ties = 0u; }
+    return r;
   }
-  long long k = k_want < (long long)n_cand ? k_want : (long long)n_cand;
-  r.k_eff = int(k);
-  if (k <= 0) return r;
-
   uint32_t prefix = 0, mask = 0;
-  int remaining = int(k);
+  long long remaining = k;
   const int shifts[3] = {20, 8, 0};
   const int widths[3] = {12, 12, 8};
   for (int pass = 0; pass < 3; ++pass) {
     const int shift = shifts[pass];
     const uint32_t dmask = (1u << widths[pass]) - 1u;
     const int nb = 1 << widths[pass];
-    for (int b = tid; b < nb; b += nt) s_hist[b] = 0u;
+    unsigned int* hist = S.hist[pass & 1];
+    for (int b = tid; b < nb; b += nt) hist[b] = 0u;
     __syncthreads();
-    for (int i = tid; i < n; i += nt) {
+    for (int i = tid; i < n_local; i += nt) {
       const float v = vals[i];
       if (v >= 0.f) {
         const uint32_t bits = __float_as_uint(v);
-        if ((bits & mask) == prefix) atomicAdd(&s_hist[(bits >> shift) & dmask], 1u);
+        if ((bits & mask) == prefix) atomicAdd(&hist[(bits >> shift) & dmask], 1u);
       }
     }
-    __syncthreads();
-    // find digit d (from the top) with  count(>d) < remaining <= count(>=d)
-    // each thread owns a contiguous run of bins, highest bins first
+    cluster.sync();  // every slice's histogram of this pass is complete
+    // digit d (from the top) with  count(> d) < remaining <= count(>= d); each thread owns a contiguous
+    // run of bins, highest bins first, summed over the slices through distributed shared memory
     const int per = (nb + nt - 1) / nt;
-    const int hi = nb - 1 - tid * per;  // my bins: hi, hi-1, ..., hi-per+1
+    const int hi = nb - 1 - tid * per;
+    unsigned int cnt[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};  // per <= 8: callers run >= 512 threads (kBins / 8)
     unsigned int mine = 0;
-    for (int j = 0; j < per; ++j) {
-      const int b = hi - j;
-      if (b >= 0) mine += s_hist[b];
+    for (unsigned int rk = 0; rk < n_ranks; ++rk) {
+      const unsigned int* rh = cluster.map_shared_rank(hist, rk);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int b = hi - j;
+        if (j < per && b >= 0) {
+          const unsigned int h = rh[b];
+          cnt[j] += h;
+          mine += h;
+        }
+      }
     }
-    // exclusive prefix over threads (thread order == descending bins)
-    const int lane = tid & 31, wid = tid >> 5;
     unsigned int inc = mine;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
       const unsigned int t = __shfl_up_sync(0xffffffffu, inc, o);
       if (lane >= o) inc += t;
     }
-    unsigned int* s_wt = reinterpret_cast<unsigned int*>(s_red);  // [<=32]
+    if (lane == 31) S.wt[wid] = inc;
     __syncthreads();
-    if (lane == 31) s_wt[wid] = inc;
-    __syncthreads();
-    unsigned int before = inc - mine;
-    for (int w = 0; w < wid; ++w) before += s_wt[w];
-    if (before < unsigned(remaining) && unsigned(remaining) <= before + mine) {
-      unsigned int acc = before;
-      for (int j = 0; j < per; ++j) {
+    unsigned long long before = inc - mine;
+    for (int w = 0; w < wid; ++w) before += S.wt[w];
+    if (before < (unsigned long long)remaining && (unsigned long long)remaining <= before + mine) {
+      unsigned long long acc = before;
+      bool found = false;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
         const int b = hi - j;
-        const unsigned int h = b >= 0 ? s_hist[b] : 0u;
-        if (acc < unsigned(remaining) && unsigned(remaining) <= acc + h) {
-          s_misc[0] = b;
-          s_misc[1] = remaining - int(acc);
-          s_misc[2] = int(h);
-          break;
+        const unsigned int h = (j < per && b >= 0) ? cnt[j] : 0u;
+        if (!found && acc < (unsigned long long)remaining && (unsigned long long)remaining <= acc + h) {
+          S.misc[0] = b;
+          S.misc[1] = int((unsigned long long)remaining - acc);
+          S.misc[2] = int(h);
+          found = true;
         }
         acc += h;
       }
     }
     __syncthreads();
-    prefix |= uint32_t(s_misc[0]) << shift;
+    prefix |= uint32_t(S.misc[0]) << shift;
     mask |= dmask << shift;
-    remaining = s_misc[1];
-    r.n_ties = s_misc[2];
+    remaining = S.misc[1];
+    r.n_ties = S.misc[2];
     __syncthreads();
   }
   r.thr_bits = prefix;
-  r.take_ties = remaining;
+  r.take_ties = int(remaining);
   const float thr = __uint_as_float(prefix);
   const bool all_ties = r.take_ties >= r.n_ties;
   double acc = 0.0;
-  for (int i = tid; i < n; i += nt) {
+  unsigned int my_ties = 0;
+  for (int i = tid; i < n_local; i += nt) {
     const float v = vals[i];
     if (v > thr) acc += double(v);
-    // selected negatives: v > thr plus (normally all) the candidates equal to thr; a candidate is
-    // never a positive, so the flag byte is written without reading it
+    if (v == thr) ++my_ties;
     if (sel_out && (v > thr || (all_ties && v == thr))) sel_out[i] = 2;
   }
-  r.sum = block_sum(acc, s_red) + double(remaining) * double(thr);
-  if (sel_out && !all_ties) {  // rare: pick the ties by ascending index (deterministic)
-    if (tid == 0) {
-      int left = r.take_ties;
-      for (int i = 0; i < n && left > 0; ++i)
+  const double local = block_sum(acc, S.red);
+  const double nties_local = block_sum(double(my_ties), S.red);
+  if (tid == 0) {
+    S.sumv = local;
+    S.ties = unsigned(nties_local + 0.5);
+  }
+  r.sum = local;
+  if (!all_ties) {  // rare (cluster-uniform): the ties that belong to the top-k are the first ones by index
+    cluster.sync();
+    if (tid == 0 && sel_out) {
+      long long before = 0;
+      for (unsigned int rk = 0; rk < my_rank; ++rk) before += *cluster.map_shared_rank(&S.ties, rk);
+      long long left = (long long)r.take_ties - before;
+      for (int i = 0; i < n_local && left > 0; ++i)
         if (vals[i] == thr) {
           sel_out[i] = 2;
           --left;
@@ -890,30 +920,6 @@ __device__ SelectResult topk_sum(const float* __restrict__ vals, int n, long lon
     }
   }
   return r;
-}
-
-// mark selected negatives: v > thr, plus the first `take_ties` candidates equal to thr
-__device__ void mark_selected(const float* __restrict__ vals, uint8_t* __restrict__ sel, int n,
-                              const SelectResult& r, int* s_misc) {
-  if (r.k_eff <= 0) return;
-  const int tid = threadIdx.x, nt = blockDim.x;
-  const float thr = __uint_as_float(r.thr_bits);
-  const bool all_ties = r.take_ties >= r.n_ties;
-  for (int i = tid; i < n; i += nt) {
-    const float v = vals[i];
-    if (v > thr || (all_ties && v == thr)) sel[i] = 2;  // a candidate is never a positive: no read-modify-write
-  }
-  if (!all_ties) {  // rare: pick ties by ascending index (deterministic)
-    __syncthreads();
-    if (tid == 0) {
-      int left = r.take_ties;
-      for (int i = 0; i < n && left > 0; ++i)
-        if (vals[i] == thr) {
-          sel[i] = 2;
-          --left;
-        }
-    }
-  }
 }
 
 SBOD_DEVINL void finalize_loss(const LossParams& q, const double* sums, float* loss) {
@@ -930,52 +936,69 @@ SBOD_DEVINL void finalize_loss(const LossParams& q, const double* sums, float* l
 }
 
 // ------------------------------------------------------------------------------------------
-// classify_kernel: grid (ceil(P/1024), N). Applies the forced-match override to its 1024 priors
-// (every CTA rebuilds the image's short forced list from the per-object keys — no cross-CTA
-// dependency), classifies them, evaluates the positives (true-class CE, loc loss), writes the
-// mining candidates and per-block partial sums.
+// classify_mine_kernel: one thread-block CLUSTER per image (cluster size 1 / 2 / 4 / 8 CTAs, chosen so
+// that the whole batch is co-resident; each CTA owns a contiguous slice of the image's priors).
+//   1. every CTA rebuilds the image's short forced-match list from the per-object keys and applies it
+//      to its slice (rank inside the FILTERED list, last write wins - SSD512.py:546-553);
+//   2. per 512 priors: classes, selection bits, mining candidates (kept in shared memory); the rows with
+//      a foreground class are recorded and evaluated densely (true-class CE, loc term);
+//   3. the slices' partial sums meet through distributed shared memory -> n_pos of the image;
+//   4. hard-negative mining = cluster-wide radix select of the 3 * n_pos largest candidate CEs
+//      (SSD512.py:610-619 consumes only their sum), selection bits by plain stores;
+//   5. rank 0 writes the image's partial sums; the last image folds the batch in image order
+//      (deterministic) and finalises the loss.
+// Launched with programmatic dependent launch after the match kernel: the prologue (list of the
+// image's objects, shared-memory setup) overlaps the tail of the streaming kernel.
 // ------------------------------------------------------------------------------------------
-constexpr int kClsThreads = 256;
-constexpr int kClsPriors = 1024;
+constexpr int kCmThreads = 512;
+constexpr int kCmMaxCluster = 8;
 
-__global__ void __launch_bounds__(kClsThreads) classify_kernel(const LossParams q) {
+struct CmShared {
+  ClusterSelect sel;
+  double red4[4 * 32];
+  double part[4];  // this CTA's partial sums: loc, conf over positives, candidates (mining) / focal negatives, n_pos
+  int warp_tot[kCmThreads / 32];
+  int carry;
+  int last;
+  uint16_t lidx[kCmThreads], lcls[kCmThreads];  // rows with a foreground class: local index, class (bit 15: positive)
+  uint16_t cnt[kCmThreads / 32];
+};
+
+__global__ void __launch_bounds__(kCmThreads) classify_mine_kernel(const LossParams q) {
+  cg::cluster_group cluster = cg::this_cluster();
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  uint32_t* s_prior = reinterpret_cast<uint32_t*>(smem_raw);       // [gmax]
+  CmShared& S = *reinterpret_cast<CmShared*>(smem_raw);
+  unsigned char* dyn = smem_raw + ((sizeof(CmShared) + 127) & ~size_t(127));
+  uint32_t* s_prior = reinterpret_cast<uint32_t*>(dyn);            // [gmax]
   int32_t* s_rank = reinterpret_cast<int32_t*>(s_prior + q.gmax);  // [gmax], -1 = filtered out
-  __shared__ float s_ov[kClsPriors];
-  __shared__ int s_obj[kClsPriors];
-  __shared__ double s_red4[4 * 32];
-  __shared__ double s_red[34];
-  __shared__ int s_warp_tot[kClsThreads / 32];
-  __shared__ int s_carry;
-  __shared__ uint16_t s_lidx[kClsPriors], s_lcls[kClsPriors];  // rows with a foreground class: local index, class
-  __shared__ uint16_t s_cnt[(kClsPriors / kClsThreads) * (kClsThreads / 32)];
+  float* s_vals = reinterpret_cast<float*>(dyn + ((size_t(q.gmax) * 8 + 127) & ~size_t(127)));  // [slice] if cached
 
-  const int n = blockIdx.y, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-  const int pb = blockIdx.x * kClsPriors;
-  const int g0 = q.gt_offsets[n];
-  const int G = q.gt_offsets[n + 1] - g0;
+  const unsigned int n_ranks = cluster.num_blocks(), rank = cluster.block_rank();
+  const int n = blockIdx.x / n_ranks, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int slice = (q.P + n_ranks - 1) / n_ranks;
+  const int p_lo = min(q.P, int(rank) * slice), p_hi = min(q.P, p_lo + slice);
+  const int n_local = p_hi - p_lo;
   const size_t base = size_t(n) * q.P;
   const bool focal = q.cls_kind == SBOD_CLS_FOCAL_SUM || q.cls_kind == SBOD_CLS_FOCAL_NORM;
+  const bool cached = q.mine_cache != 0;
+  if (tid == 0) S.carry = 0;
 
-  // ---- forced list: rank j of each object inside "objects whose best overlap is > 0" ----
-  if (tid == 0) s_carry = 0;
-#pragma unroll
-  for (int u = 0; u < kClsPriors / kClsThreads; ++u) {
-    const int p = pb + u * kClsThreads + tid;
-    s_ov[u * kClsThreads + tid] = p < q.P ? q.ov[base + p] : 0.f;
-    s_obj[u * kClsThreads + tid] = p < q.P ? q.obj[base + p] : 0;
-  }
+  // everything above is independent of the match kernel's results; from here on they are needed
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+
+  const int g0 = q.gt_offsets[n];
+  const int G = q.gt_offsets[n + 1] - g0;
   __syncthreads();
-  for (int gb = 0; gb < G; gb += kClsThreads) {
+  // ---- forced list: rank j of each object inside "objects whose best overlap is > 0" ----
+  for (int gb = 0; gb < G; gb += kCmThreads) {
     const int g = gb + tid;
     const unsigned long long key = g < G ? q.gtkey[size_t(n) * q.gmax + g] : 0ull;
     const bool f = key != 0ull;
     const unsigned bal = __ballot_sync(0xffffffffu, f);
-    if (lane == 0) s_warp_tot[wid] = __popc(bal);
+    if (lane == 0) S.warp_tot[wid] = __popc(bal);
     __syncthreads();
-    int off = s_carry;
-    for (int w = 0; w < wid; ++w) off += s_warp_tot[w];
+    int off = S.carry;
+    for (int w = 0; w < wid; ++w) off += S.warp_tot[w];
     if (g < G) {
       s_prior[g] = 0xffffffffu - uint32_t(key & 0xffffffffull);
       s_rank[g] = f ? off + __popc(bal & ((1u << lane) - 1u)) : -1;
@@ -983,57 +1006,47 @@ __global__ void __launch_bounds__(kClsThreads) classify_kernel(const LossParams 
     __syncthreads();
     if (tid == 0) {
       int t = 0;
-      for (int w = 0; w < kClsThreads / 32; ++w) t += s_warp_tot[w];
-      s_carry += t;
+      for (int w = 0; w < kCmThreads / 32; ++w) t += S.warp_tot[w];
+      S.carry += t;
     }
     __syncthreads();
   }
-  for (int g = tid; g < G; g += kClsThreads) {
+  for (int g = tid; g < G; g += kCmThreads) {
     const int j = s_rank[g];
     if (j < 0) continue;
     const uint32_t p = s_prior[g];
-    if (p < uint32_t(pb) || p >= uint32_t(pb + kClsPriors)) continue;
+    if (p < uint32_t(p_lo) || p >= uint32_t(p_hi)) continue;
     bool winner = true;  // "for j: obj[pr[j]] = j" -> the last j wins (SSD512.py:552-553)
     for (int h = g + 1; h < G; ++h)
       if (s_rank[h] >= 0 && s_prior[h] == p) {
         winner = false;
         break;
       }
-    s_ov[p - pb] = 1.0f;  // index_fill_(0, prior_for_each_object, 1.0)
-    q.ov[base + p] = 1.0f;
-    if (winner) {
-      s_obj[p - pb] = j;
-      q.obj[base + p] = j;
-    }
+    q.ov[base + p] = 1.0f;  // index_fill_(0, prior_for_each_object, 1.0)
+    if (winner) q.obj[base + p] = j;
   }
-  __syncthreads();
+  __syncthreads();  // the patched overlaps / objects are visible to the whole CTA
 
-  // Phase A, every prior: class, selection bits, mining candidate. Rows with a foreground class
-  // (2-3 % of the priors) are only recorded: their true-class CE and box term need dependent loads and
-  // ~200 instructions, which would otherwise run divergently in more than half of the warps.
-  // Phase B walks the recorded rows densely. The list order is deterministic (ballot ranks + a fixed
-  // order of the per-warp counts), so the per-thread partial sums are reproducible run to run.
-  constexpr int kPer = kClsPriors / kClsThreads;
+  // ---- phase A / B per 512 priors ----
   double a_loc = 0.0, a_pos = 0.0, a_neg = 0.0;
   int npos = 0;
-  int rec[kPer], rrank[kPer];  // recorded class (bit 15: positive) / rank inside the warp's ballot
-#pragma unroll
-  for (int u = 0; u < kPer; ++u) {
-    const int p = pb + u * kClsThreads + tid;
-    rec[u] = 0;
-    if (p < q.P) {
-      const float ov = s_ov[u * kClsThreads + tid];
-      const int obj = s_obj[u * kClsThreads + tid];
+  for (int pb = p_lo; pb < p_hi; pb += kCmThreads) {
+    const int p = pb + tid;
+    int rec = 0;
+    int my_obj = 0;
+    if (p < p_hi) {
+      const float ov = q.ov[base + p];
+      my_obj = q.obj[base + p];
       const float ce = q.ce[base + p];  // background CE from the streaming kernel
       const bool ex = q.exclude ? q.exclude[base + p] != 0 : false;
       int64_t cls = 0;
-      if (!(ov < q.thr_pos) && G > 0) cls = map_label(q, q.gt_labels[g0 + obj]);
+      if (!(ov < q.thr_pos) && G > 0) cls = map_label(q, q.gt_labels[g0 + my_obj]);
       const bool pos = cls > 0 && !ex;
       const bool isneg = ov < q.thr_neg;
       uint8_t selbits = pos ? 1 : 0;
       float v = -1.f;
       if (cls > 0) {
-        rec[u] = min(int(cls), q.C - 1) | (pos ? 0x8000 : 0);  // C <= 4096 elsewhere; classes fit 15 bits
+        rec = min(int(cls), q.C - 1) | (pos ? 0x8000 : 0);  // C <= 16384 elsewhere; classes fit 15 bits
       } else if (focal) {
         if (isneg) {  // target class is 0 there (thr_neg < thr_pos)
           selbits |= 2;
@@ -1044,113 +1057,91 @@ __global__ void __launch_bounds__(kClsThreads) classify_kernel(const LossParams 
       } else {  // MINE_NEG, MINE_BATCH: only true_neg == -1 rows are candidates
         if (isneg) v = ce;
       }
-      if (!focal && v >= 0.f) a_neg += 1.0;  // mining modes: this partial counts the candidates (see mine_kernel)
+      if (!focal && v >= 0.f) a_neg += 1.0;  // mining modes: this partial counts the candidates (NaN CEs are none)
       q.sel[base + p] = selbits;
       q.cand[base + p] = v;
+      if (cached) s_vals[p - p_lo] = v;
     }
-    const unsigned bal = __ballot_sync(0xffffffffu, rec[u] != 0);
-    rrank[u] = __popc(bal & ((1u << lane) - 1u));
-    if (lane == 0) s_cnt[u * (kClsThreads / 32) + wid] = uint16_t(__popc(bal));
-  }
-  __syncthreads();
-  {
-    int before = 0;
-#pragma unroll
-    for (int u = 0; u < kPer; ++u) {
-      // entries of earlier (u, warp) pairs in the fixed order u-major, warp-minor
-      int mine_base = before;
-      for (int w2 = 0; w2 < kClsThreads / 32; ++w2) {
-        const int c2 = s_cnt[u * (kClsThreads / 32) + w2];
-        if (w2 < wid) mine_base += c2;
-        before += c2;
-      }
-      if (rec[u]) {
-        s_lidx[mine_base + rrank[u]] = uint16_t(u * kClsThreads + tid);
-        s_lcls[mine_base + rrank[u]] = uint16_t(rec[u]);
-      }
-    }
-    // `before` is now the length of the list (same value in every thread)
+    // rows with a foreground class (2-3 % of the priors): recorded, then evaluated densely. The list order is
+    // deterministic (ballot ranks, warps in order), so the per-thread partial sums are reproducible.
+    const unsigned bal = __ballot_sync(0xffffffffu, rec != 0);
+    const int rrank = __popc(bal & ((1u << lane) - 1u));
+    if (lane == 0) S.cnt[wid] = uint16_t(__popc(bal));
     __syncthreads();
-    for (int i = tid; i < before; i += kClsThreads) {
-      const int local = s_lidx[i];
-      const int p = pb + local;
-      const int c = s_lcls[i] & 0x7fff;
-      const bool pos = (s_lcls[i] & 0x8000) != 0;
-      const float ce = q.lse[base + p] - q.scores[(base + p) * q.C + c];  // CE against the true class
-      q.ce[base + p] = ce;
+    int mine_base = 0, total = 0;
+    for (int w2 = 0; w2 < kCmThreads / 32; ++w2) {
+      const int c2 = S.cnt[w2];
+      if (w2 < wid) mine_base += c2;
+      total += c2;
+    }
+    if (rec) {
+      S.lidx[mine_base + rrank] = uint16_t(tid);
+      S.lcls[mine_base + rrank] = uint16_t(rec);
+    }
+    __syncthreads();
+    for (int i = tid; i < total; i += kCmThreads) {
+      const int pp = pb + S.lidx[i];
+      const int c = S.lcls[i] & 0x7fff;
+      const bool pos = (S.lcls[i] & 0x8000) != 0;
+      const float ce = q.lse[base + pp] - q.scores[(base + pp) * q.C + c];  // CE against the true class
+      q.ce[base + pp] = ce;
       if (pos) {
         ++npos;
         a_pos += focal ? double(focal_fg(q, ce)) : double(ce);
-        const float4 pred = reinterpret_cast<const float4*>(q.locs)[base + p];
-        const LocTerm lt = loc_term<false>(q, pred, prior_cxcy_of(q, n, p), q.gt_boxes[g0 + s_obj[local]]);
+        const float4 pred = reinterpret_cast<const float4*>(q.locs)[base + pp];
+        const LocTerm lt = loc_term<false>(q, pred, prior_cxcy_of(q, n, pp), q.gt_boxes[g0 + q.obj[base + pp]]);
         a_loc += double(lt.loss);
       }
     }
+    __syncthreads();  // the lists are free for the next 512 priors
   }
   double tot[4] = {a_loc, a_pos, a_neg, double(npos)};
-  block_sum4_to_thread0(tot, s_red4);
+  block_sum4_to_thread0(tot, S.red4);
   if (tid == 0) {
-    double* bp = q.blockpart + (size_t(n) * gridDim.x + blockIdx.x) * 4;
-    bp[0] = tot[0]; bp[1] = tot[1]; bp[2] = tot[2]; bp[3] = tot[3];
+    S.part[0] = tot[0]; S.part[1] = tot[1]; S.part[2] = tot[2]; S.part[3] = tot[3];
   }
-}
+  cluster.sync();  // every slice's partial sums are published; every CTA has read the object keys
+  double img[4] = {0.0, 0.0, 0.0, 0.0};
+  for (unsigned int rk = 0; rk < n_ranks; ++rk) {  // rank order: the same sums in every CTA
+    const double* pp = cluster.map_shared_rank(S.part, rk);
+    img[0] += pp[0]; img[1] += pp[1]; img[2] += pp[2]; img[3] += pp[3];
+  }
+  // leave the per-object keys clean for the next call
+  if (rank == 0)
+    for (int g = tid; g < G; g += kCmThreads) q.gtkey[size_t(n) * q.gmax + g] = 0ull;
 
-// ------------------------------------------------------------------------------------------
-// mine_kernel: one CTA per image. Folds the block partials, selects the hard negatives
-// (radix-select top-k sum over the image's candidates, staged in shared memory), marks them,
-// and the last CTA folds the batch.
-// ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kMineThreads) mine_kernel(const LossParams q) {
-  extern __shared__ __align__(128) unsigned char smem_raw[];
-  float* s_vals = reinterpret_cast<float*>(smem_raw);  // [P] if cached
-  __shared__ unsigned int s_hist[kBins];
-  __shared__ double s_red[34];
-  __shared__ double s_tot[4];
-  __shared__ int s_misc[8];
-  const int n = blockIdx.x, tid = threadIdx.x;
-  const int g0 = q.gt_offsets[n];
-  const int G = q.gt_offsets[n + 1] - g0;
-  const size_t base = size_t(n) * q.P;
-  const bool focal = q.cls_kind == SBOD_CLS_FOCAL_SUM || q.cls_kind == SBOD_CLS_FOCAL_NORM;
-  const int nblk = (q.P + kClsPriors - 1) / kClsPriors;
-
-  // leave the per-object keys clean for the next call (every classify CTA has read them)
-  for (int g = tid; g < G; g += kMineThreads) q.gtkey[size_t(n) * q.gmax + g] = 0ull;
-  if (tid < 4) {  // block partials in block order (deterministic)
-    double acc = 0.0;
-    const double* bp = q.blockpart + size_t(n) * nblk * 4;
-    for (int b = 0; b < nblk; ++b) acc += bp[b * 4 + tid];
-    s_tot[tid] = acc;
+  double t_neg = 0.0;
+  SelectResult r;
+  r.take_ties = 0; r.thr_bits = 0; r.k_eff = 0;
+  const bool select = !focal && q.cls_kind != SBOD_CLS_CE_MINE_BATCH;
+  if (select) {
+    const long long k = (long long)(q.ratio) * (long long)(img[3] + 0.5);
+    const float* vals = cached ? s_vals : q.cand + base + p_lo;
+    r = cluster_topk_sum(cluster, S.sel, vals, n_local, k, (long long)(img[2] + 0.5), q.sel + base + p_lo);
+  } else if (tid == 0) {
+    S.sel.sumv = 0.0;
   }
-  const float* vals = q.cand + base;
-  if (q.mine_cache && !focal && q.cls_kind != SBOD_CLS_CE_MINE_BATCH) {
-    for (int p = tid; p < q.P; p += kMineThreads) s_vals[p] = q.cand[base + p];
-    vals = s_vals;
-  }
-  __syncthreads();
-  const double t_loc = s_tot[0], t_pos = s_tot[1], t_npos = s_tot[3];
-  double t_neg;
-  if (focal) {
-    t_neg = s_tot[2];
-  } else if (q.cls_kind == SBOD_CLS_CE_MINE_BATCH) {
-    t_neg = 0.0;  // filled by mine_batch_kernel
-  } else {
-    const long long k = (long long)(q.ratio) * (long long)(t_npos + 0.5);
-    // the third block partial holds the number of candidates in the mining modes (NaN CEs are not candidates)
-    const SelectResult r = topk_sum(vals, q.P, k, s_hist, s_red, s_misc, (long long)(s_tot[2] + 0.5), q.sel + base);
-    t_neg = r.sum;
-  }
-  if (tid == 0) {
-    q.partials[n * 4 + 0] = t_loc;
-    q.partials[n * 4 + 1] = t_pos;
+  cluster.sync();  // the slices' selected sums are published
+  if (rank == 0 && tid == 0) {
+    if (focal) {
+      t_neg = img[2];
+    } else if (q.cls_kind == SBOD_CLS_CE_MINE_BATCH) {
+      t_neg = img[2];  // number of candidates of the image; mine_batch_kernel turns the batch total into the mined sum
+    } else {
+      for (unsigned int rk = 0; rk < n_ranks; ++rk) t_neg += *cluster.map_shared_rank(&S.sel.sumv, rk);
+      if (r.k_eff > 0) t_neg += double(r.take_ties) * double(__uint_as_float(r.thr_bits));
+    }
+    q.partials[n * 4 + 0] = img[0];
+    q.partials[n * 4 + 1] = img[1];
     q.partials[n * 4 + 2] = t_neg;
-    q.partials[n * 4 + 3] = t_npos;
+    q.partials[n * 4 + 3] = img[3];
     __threadfence();
     const unsigned int ticket = atomicAdd(&q.counters[0], 1u);
-    s_misc[7] = (ticket == unsigned(q.N) - 1u) ? 1 : 0;
+    S.last = (ticket == unsigned(q.N) - 1u) ? 1 : 0;
   }
-  __syncthreads();
-  if (s_misc[7] && tid < 4) {  // last block folds the batch in image order (deterministic)
+  cluster.sync();  // rank 0 is done reading its peers' shared memory: they may exit
+  if (rank != 0) return;
+  if (S.last && tid < 4) {  // the last image folds the batch in image order (deterministic)
     __threadfence();
     double acc = 0.0;
     const volatile double* pp = q.partials;
@@ -1158,27 +1149,34 @@ __global__ void __launch_bounds__(kMineThreads) mine_kernel(const LossParams q) 
     q.sums[tid] = acc;
   }
   __syncthreads();
-  if (s_misc[7] && tid == 0) {
+  if (S.last && tid == 0) {
     q.counters[0] = 0u;
     if (q.cls_kind != SBOD_CLS_CE_MINE_BATCH) finalize_loss(q, q.sums, q.loss);
   }
 }
 
-// SSD300's batch-global mining: top sum(3*n_pos) over every true_neg==-1 row of the batch
-__global__ void __launch_bounds__(kMineThreads) mine_batch_kernel(const LossParams q) {
-  __shared__ unsigned int s_hist[kBins];
-  __shared__ double s_red[34];
-  __shared__ int s_misc[8];
-  const long long total = (long long)q.N * q.P;
+// SSD300's batch-global mining (SSD300.py:580-588): the sum(3 * n_pos) largest CEs over every true_neg == -1
+// row of the BATCH. One cluster of 8 CTAs; each owns a contiguous slice of the N*P candidate values.
+__global__ void __launch_bounds__(1024) mine_batch_kernel(const LossParams q) {
+  cg::cluster_group cluster = cg::this_cluster();
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  ClusterSelect& S = *reinterpret_cast<ClusterSelect*>(smem_raw);
+  const unsigned int n_ranks = cluster.num_blocks(), rank = cluster.block_rank();
+  const long long total = (long long)q.N * q.P;  // fits int for every supported shape (checked on the host)
+  const long long slice = (total + n_ranks - 1) / n_ranks;
+  const long long lo = min(total, (long long)rank * slice), hi = min(total, lo + slice);
   const long long k = (long long)(q.ratio) * (long long)(q.sums[3] + 0.5);
-  // (n = N*P fits int for every supported shape; checked on the host)
-  const SelectResult r = topk_sum(q.cand, int(total), k, s_hist, s_red, s_misc);
-  mark_selected(q.cand, q.sel, int(total), r, s_misc);
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    q.sums[2] = r.sum;
+  const long long n_cand = (long long)(q.sums[2] + 0.5);  // candidates of the batch, counted by classify_mine_kernel
+  const SelectResult r = cluster_topk_sum(cluster, S, q.cand + lo, int(hi - lo), k, n_cand, q.sel + lo);
+  cluster.sync();
+  if (rank == 0 && threadIdx.x == 0) {
+    double t = 0.0;
+    for (unsigned int rk = 0; rk < n_ranks; ++rk) t += *cluster.map_shared_rank(&S.sumv, rk);
+    if (r.k_eff > 0) t += double(r.take_ties) * double(__uint_as_float(r.thr_bits));
+    q.sums[2] = t;
     finalize_loss(q, q.sums, q.loss);
   }
+  cluster.sync();
 }
 
 __global__ void finalize_kernel(const LossParams q) {
@@ -1531,6 +1529,11 @@ static Tiling choose_tiling(int C, int max_stages) {
   return t;
 }
 
+static size_t cm_smem_bytes(const LossParams& q, bool cached) {
+  const size_t slice = (size_t(q.P) + q.cm_cluster - 1) / q.cm_cluster;
+  return ((sizeof(CmShared) + 127) & ~size_t(127)) + align_up(size_t(q.gmax) * 8, 128) + (cached ? slice * 4 : 0) + 128;
+}
+
 static int fill_params(const sbod_loss_desc* d, LossParams& q, bool need_scores) {
   if (!d) return SBOD_ERR_INVALID;
   if (d->N <= 0 || d->P <= 0 || d->gmax < 0) return SBOD_ERR_INVALID;
@@ -1578,8 +1581,6 @@ static int fill_params(const sbod_loss_desc* d, LossParams& q, bool need_scores)
   q.match_q = reinterpret_cast<unsigned int*>(w);
   w += align_up(size_t(q.N) * 4, 256);
   q.cand = reinterpret_cast<float*>(w);
-  w += align_up(size_t(q.N) * q.P * 4, 256);
-  q.blockpart = reinterpret_cast<double*>(w);
   Tiling t = choose_tiling(need_scores ? d->C : 1, kMaxStages);
   // the two-threads-per-row layout is bank-conflict free only for odd C; even C is merely slower in smem
   q.fast = (need_scores && d->C >= 2 && d->C <= 128) ? 1 : 0;
@@ -1602,11 +1603,18 @@ static int fill_params(const sbod_loss_desc* d, LossParams& q, bool need_scores)
   q.n_stages = t.stages;
   q.stage_floats = t.stage_floats;
   q.with_scores = need_scores ? 1 : 0;
+  q.debug_skip = 0;
+#ifdef SBOD_DEBUG_HOOKS  // profiling builds only (tools/): release builds never read the environment
   {
     const char* e = getenv("SBOD_DEBUG_SKIP");
     q.debug_skip = e ? atoi(e) : 0;
   }
-  q.mine_cache = (size_t(q.P) * 4 + align_up(size_t(q.gmax) * 8, 128) <= 196 * 1024) ? 1 : 0;
+#endif
+  // classify_mine_kernel: a cluster of CTAs per image, as large as keeps the whole batch co-resident
+  q.cm_cluster = 1;
+  while (q.cm_cluster < kCmMaxCluster && q.N * q.cm_cluster * 2 <= sm_count() && q.P / (q.cm_cluster * 2) >= 2048)
+    q.cm_cluster *= 2;
+  q.mine_cache = (cm_smem_bytes(q, true) <= 200 * 1024) ? 1 : 0;
   return SBOD_OK;
 }
 
@@ -1618,8 +1626,24 @@ extern "C" size_t sbod_loss_workspace_bytes(const sbod_loss_desc* d) {
   if (!d) return 0;
   const int gmax = d->gmax > 0 ? d->gmax : 1;
   return 256 + align_up(size_t(d->N) * gmax * 8, 256) + align_up(size_t(d->N) * 4, 256) +
-         align_up(size_t(d->N) * d->P * 4, 256) +
-         align_up(size_t(d->N) * ((size_t(d->P) + 1023) / 1024) * 32, 256);
+         align_up(size_t(d->N) * d->P * 4, 256);
+}
+
+// leading bytes of the loss workspace that carry the zero contract: counters, per-object keys, ticket queues
+extern "C" size_t sbod_loss_workspace_zero_bytes(const sbod_loss_desc* d) {
+  if (!d) return 0;
+  const int gmax = d->gmax > 0 ? d->gmax : 1;
+  return 256 + align_up(size_t(d->N) * gmax * 8, 256) + align_up(size_t(d->N) * 4, 256);
+}
+
+// Process-wide switches (A/B measurements; defaults are the fast settings).
+static int g_opt_pdl = 1;           // programmatic dependent launch between the kernels of one call
+static int g_opt_peer_exchange = 1; // one-shot NVLink exchange of the loss sums when a communicator is attached
+extern "C" int sbod_set_option(int key, int value) {
+  if (key == SBOD_OPT_PDL) g_opt_pdl = value ? 1 : 0;
+  else if (key == SBOD_OPT_PEER_EXCHANGE) g_opt_peer_exchange = value ? 1 : 0;
+  else return SBOD_ERR_INVALID;
+  return SBOD_OK;
 }
 
 // Workspace contract: the first 256 bytes (counters) and the gtkey block must be zero on the
@@ -1631,17 +1655,17 @@ extern "C" int sbod_workspace_init(void* workspace, size_t bytes, sbod_stream_t 
 }
 
 static int set_kernel_attrs() {
-  static bool attr_done = false;
-  if (attr_done) return SBOD_OK;
+  static DeviceOnce attr_once;
+  if (!attr_once.pending()) return SBOD_OK;
   SBOD_CUDA_TRY(cudaFuncSetAttribute(match_lse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   SBOD_CUDA_TRY(cudaFuncSetAttribute(match_lse_fast_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   SBOD_CUDA_TRY(cudaFuncSetAttribute(match_lse_fast_kernel<81>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   SBOD_CUDA_TRY(cudaFuncSetAttribute(match_lse_fast_kernel<21>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   SBOD_CUDA_TRY(cudaFuncSetAttribute(loss_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   SBOD_CUDA_TRY(cudaFuncSetAttribute(forced_match_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-  SBOD_CUDA_TRY(cudaFuncSetAttribute(mine_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 205 * 1024));
-  SBOD_CUDA_TRY(cudaFuncSetAttribute(classify_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-  attr_done = true;
+  SBOD_CUDA_TRY(cudaFuncSetAttribute(classify_mine_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024));
+  SBOD_CUDA_TRY(cudaFuncSetAttribute(mine_batch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+  attr_once.mark();
   return SBOD_OK;
 }
 
@@ -1676,15 +1700,37 @@ static int launch_match(const LossParams& q, cudaStream_t st) {
 static int launch_mine(const LossParams& q, cudaStream_t st) {
   int rc = set_kernel_attrs();
   if (rc) return rc;
-  dim3 cgrid((q.P + kClsPriors - 1) / kClsPriors, q.N);
-  classify_kernel<<<cgrid, kClsThreads, size_t(q.gmax) * 8, st>>>(q);
-  SBOD_LAUNCH_CHECK();
-  const size_t smem = q.mine_cache ? size_t(q.P) * 4 : 0;
-  mine_kernel<<<q.N, kMineThreads, smem, st>>>(q);
-  SBOD_LAUNCH_CHECK();
+  {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(unsigned(q.N) * unsigned(q.cm_cluster), 1, 1);
+    cfg.blockDim = dim3(kCmThreads, 1, 1);
+    cfg.dynamicSmemBytes = cm_smem_bytes(q, q.mine_cache != 0);
+    cfg.stream = st;
+    cudaLaunchAttribute attrs[2];
+    attrs[0].id = cudaLaunchAttributeClusterDimension;
+    attrs[0].val.clusterDim.x = unsigned(q.cm_cluster);
+    attrs[0].val.clusterDim.y = 1;
+    attrs[0].val.clusterDim.z = 1;
+    attrs[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attrs[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attrs;
+    cfg.numAttrs = g_opt_pdl ? 2 : 1;
+    SBOD_CUDA_TRY(cudaLaunchKernelEx(&cfg, classify_mine_kernel, q));
+  }
   if (q.cls_kind == SBOD_CLS_CE_MINE_BATCH) {
-    mine_batch_kernel<<<1, kMineThreads, 0, st>>>(q);
-    SBOD_LAUNCH_CHECK();
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(kCmMaxCluster, 1, 1);
+    cfg.blockDim = dim3(1024, 1, 1);
+    cfg.dynamicSmemBytes = sizeof(ClusterSelect);
+    cfg.stream = st;
+    cudaLaunchAttribute attrs[1];
+    attrs[0].id = cudaLaunchAttributeClusterDimension;
+    attrs[0].val.clusterDim.x = kCmMaxCluster;
+    attrs[0].val.clusterDim.y = 1;
+    attrs[0].val.clusterDim.z = 1;
+    cfg.attrs = attrs;
+    cfg.numAttrs = 1;
+    SBOD_CUDA_TRY(cudaLaunchKernelEx(&cfg, mine_batch_kernel, q));
   }
   return SBOD_OK;
 }
@@ -1700,7 +1746,7 @@ extern "C" int sbod_loss_forward(const sbod_loss_desc* d, sbod_stream_t stream) 
 }
 
 // Profiling / bench hook: launch ONE stage of sbod_loss_forward: 0 = the match + log-sum-exp kernel,
-// 1 = mine_kernel (forced-match override + mining + reduction) [+ mine_batch_kernel]. Stage 0 may be
+// 1 = classify_mine_kernel (forced-match override + classification + mining + reduction) [+ mine_batch_kernel]. Stage 0 may be
 // repeated; stage 1 must follow before the workspace is used by a full forward again.
 extern "C" int sbod_loss_forward_stage(const sbod_loss_desc* d, int stage, sbod_stream_t stream) {
   LossParams q;
@@ -1741,11 +1787,11 @@ extern "C" int sbod_loss_backward(const sbod_loss_desc* d, const float* grad_los
   bp.grad_scores = grad_scores;
   bp.dense = (q.cls_kind == SBOD_CLS_FOCAL_SUM || q.cls_kind == SBOD_CLS_FOCAL_NORM) ? 1 : 0;
   const size_t smem = size_t(t.stage_floats) * 4 + 16;
-  static bool attr_done = false;
-  if (!attr_done) {
+  static DeviceOnce attr_once;
+  if (attr_once.pending()) {
     SBOD_CUDA_TRY(cudaFuncSetAttribute(loss_bwd_kernel,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    attr_done = true;
+    attr_once.mark();
   }
   int ctas_per_sm = int((220 * 1024) / (smem + 4 * 1024));
   if (ctas_per_sm < 1) ctas_per_sm = 1;

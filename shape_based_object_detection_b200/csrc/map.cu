@@ -272,10 +272,10 @@ extern "C" int sbod_map(const float* det_boxes, const int64_t* det_labels, const
   q.idx_out = reinterpret_cast<uint32_t*>(w + l.idx_out);
   q.out_ap = out_ap;
   if (n_detections > 0 && n_images > 0) {
-    static bool attr_done = false;
-    if (!attr_done) {
+    static DeviceOnce attr_once;
+    if (attr_once.pending()) {
       SBOD_CUDA_TRY(cudaFuncSetAttribute(map_match_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-      attr_done = true;
+      attr_once.mark();
     }
     map_match_kernel<<<n_images, kMapThreads, size_t(gmax > 0 ? gmax : 1), st>>>(q);
     SBOD_LAUNCH_CHECK();

@@ -9,6 +9,7 @@ from . import _lib as L
 EPS = 1e-5
 
 
+@L.on_device
 def find_jaccard_overlap(gt_boxes, anchors):
     """[k,4] x [n,4] (xyxy) -> [k,n] IoU with the reference's EPS and zero-box masking
     (zero-size GT rows -> 0, zero-size anchors -> -1; metrics.py:235-250)."""
@@ -60,7 +61,8 @@ def calculate_mAP(det_boxes, det_labels, det_scores, true_boxes, true_labels, tr
     recall_thresholds = torch.arange(start=0, end=1.1, step=.1)  # metrics.py:128, fp32
     thr = (C.c_float * 11)(*[float(v) for v in recall_thresholds.tolist()])
     nbytes = L.lib().sbod_map_workspace_bytes(D)
-    ws = L.Workspace.get(dev, ("map",), nbytes, zero_bytes=0)
+    with torch.cuda.device(dev):
+        ws = L.Workspace.get(dev, "map", nbytes, zero_bytes=0)
     with torch.cuda.device(dev):
         L.check(L.lib().sbod_map(L.ptr(db), L.ptr(dl), L.ptr(ds), L.ptr(d_off), D, L.ptr(tb), L.ptr(tl), L.ptr(td),
                                  L.ptr(g_off), T, n_images, gmax, n_classes, float(threshold), thr, L.ptr(ap),

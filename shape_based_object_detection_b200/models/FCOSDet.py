@@ -28,12 +28,26 @@ SIZES = ((0., 0.08), (0.08, 0.16), (0.16, 0.32), (0.32, 0.64), (0.64, 1.))  # :3
 RADIUS = 1.5                                                           # :335
 
 
-def compute_location(fmap_dims=FMAP_DIMS, device="cpu"):
-    """List (one tensor [d*d, 2] per pyramid level) of cell centres, FCOSDet.py:235-251."""
+PIXEL_STRIDES = (8, 16, 32, 64, 128)
+
+
+def compute_location(fmap_dims=FMAP_DIMS, device="cpu", image_size=None):
+    """List (one tensor [cells, 2] per pyramid level) of cell centres, FCOSDet.py:235-251 (square 512 input:
+    d x d cells at ((j + .5) / d, (i + .5) / d)). image_size=(H, W) gives the rectangular generalisation the
+    reference's hard-coded 512 grid lacks (BASELINE config 5, 800 x 1333 -> 22 300 locations): level k has
+    ceil(H / s_k) x ceil(W / s_k) cells centred at ((j + .5) s_k / W, (i + .5) s_k / H)."""
     out = []
-    for d in fmap_dims:
-        idx = (np.arange(d, dtype=np.float64) + 0.5) / d
-        cy, cx = np.meshgrid(idx, idx, indexing="ij")
+    if image_size is None:
+        for d in fmap_dims:
+            idx = (np.arange(d, dtype=np.float64) + 0.5) / d
+            cy, cx = np.meshgrid(idx, idx, indexing="ij")
+            out.append(torch.tensor(np.stack([cx.ravel(), cy.ravel()], 1).astype(np.float32)).to(device))
+        return out
+    H, W = image_size
+    for s in PIXEL_STRIDES:
+        ys = (np.arange(-(-H // s), dtype=np.float64) + 0.5) * s / H
+        xs = (np.arange(-(-W // s), dtype=np.float64) + 0.5) * s / W
+        cy, cx = np.meshgrid(ys, xs, indexing="ij")
         out.append(torch.tensor(np.stack([cx.ravel(), cy.ravel()], 1).astype(np.float32)).to(device))
     return out
 
@@ -56,7 +70,7 @@ class _FcosFn(torch.autograd.Function):
         l_, s_, c_ = L.f32c(locs.detach()), L.f32c(scores.detach()), L.f32c(centerness.detach())
         lab = torch.empty((N, P), dtype=torch.int32, device=dev)
         tgt = torch.empty((N, P, 4), dtype=torch.float32, device=dev)
-        sums = torch.empty((5,), dtype=torch.float64, device=dev)
+        sums = torch.empty((6,), dtype=torch.float64, device=dev)
         loss = torch.empty((4,), dtype=torch.float32, device=dev)
         d = L.FcosDesc()
         d.locs, d.scores, d.centerness = l_.data_ptr(), s_.data_ptr(), c_.data_ptr()
@@ -67,9 +81,15 @@ class _FcosFn(torch.autograd.Function):
         d.reg_weight, d.focal_alpha, d.focal_gamma = float(mod.alpha), 0.25, 2.0
         d.lab, d.tgt, d.sums, d.loss = lab.data_ptr(), tgt.data_ptr(), sums.data_ptr(), loss.data_ptr()
         nbytes = L.lib().sbod_fcos_workspace_bytes(C.byref(d))
-        ws = L.Workspace.get(dev, ("fcos", N, P), nbytes, zero_bytes=0)
+        ws = L.Workspace.get(dev, "fcos", nbytes, zero_bytes=0)
         d.workspace, d.workspace_bytes = ws.data_ptr(), nbytes
-        L.check(L.lib().sbod_fcos_forward(C.byref(d), L.stream_ptr()))
+        with torch.cuda.device(dev):
+            L.check(L.lib().sbod_fcos_forward(C.byref(d), L.stream_ptr()))
+            if mod.process_group is not None:
+                # sharded by image: [focal, sum((1-diou)*w), sum(w), bce, n_pos, n_images] is all that crosses GPUs
+                import torch.distributed as dist
+                dist.all_reduce(sums, op=dist.ReduceOp.SUM, group=mod.process_group)
+                L.check(L.lib().sbod_fcos_finalize(C.byref(d), L.stream_ptr()))
         ctx.keep = (d, l_, s_, c_, lab, tgt, sums, loss, ws, gt)
         mod.last = {"labels": lab, "targets": tgt, "sums": sums, "loss": loss}
         return loss[0].clone()
@@ -81,15 +101,18 @@ class _FcosFn(torch.autograd.Function):
         g_l = torch.empty_like(l_) if ctx.needs_input_grad[0] else None
         g_s = torch.empty_like(s_) if ctx.needs_input_grad[1] else None
         g_c = torch.empty_like(c_) if ctx.needs_input_grad[2] else None
-        L.check(L.lib().sbod_fcos_backward(C.byref(d), L.ptr(gl), L.ptr(g_l), L.ptr(g_s), L.ptr(g_c),
-                                           L.stream_ptr()))
+        with torch.cuda.device(s_.device):
+            L.check(L.lib().sbod_fcos_backward(C.byref(d), L.ptr(gl), L.ptr(g_l), L.ptr(g_s), L.ptr(g_c),
+                                               L.stream_ptr()))
         return g_l, g_s, g_c, None, None
 
 
 class FCOSLoss(nn.Module):
     """FCOSLoss(locations, config, threshold=0.5, center_sample=True) — FCOSDet.py:311-544."""
 
-    def __init__(self, locations, config, threshold=0.5, center_sample=True):
+    def __init__(self, locations, config, threshold=0.5, center_sample=True, image_size=None):
+        """image_size=(H, W): locations come from compute_location(image_size=...) and the strides are
+        s / W in x and s / H in y; default: the reference's square 512 grid (strides s / 512)."""
         super().__init__()
         self.threshold = threshold
         self.alpha = _cfg(config, "reg_weights", 1.0)
@@ -105,11 +128,18 @@ class FCOSLoss(nn.Module):
         L.need_cuda(*locations)
         self.all_locations = L.f32c(torch.cat(list(locations), 0))
         aux = []
-        for lvl, loc in enumerate(locations):  # per location: sampling radius, size-of-interest range
-            row = torch.tensor([np.float32(self.fpn_strides[lvl]) * np.float32(self.radius),
+        for lvl, loc in enumerate(locations):  # per location: sampling radius (x, y), size-of-interest range
+            if image_size is None:
+                sx = sy = np.float32(self.fpn_strides[lvl])
+            else:
+                sx = np.float32(PIXEL_STRIDES[lvl] / image_size[1])
+                sy = np.float32(PIXEL_STRIDES[lvl] / image_size[0])
+            row = torch.tensor([sx * np.float32(self.radius), sy * np.float32(self.radius),
                                 self.sizes[lvl][0], self.sizes[lvl][1]], dtype=torch.float32)
-            aux.append(row[None].expand(loc.size(0), 3))
-        self.loc_aux = torch.cat(aux, 0).contiguous().to(self.all_locations.device)
+            aux.append(row[None].expand(loc.size(0), 4))
+        self.loc_aux = L.f32c(torch.cat(aux, 0).contiguous().to(self.all_locations.device))
+        self.image_size = image_size
+        self.process_group = None  # set to a torch.distributed group to shard the batch by image
         self.last = {}
 
     def increase_threshold(self, increment=0.1):  # FCOSDet.py:337-341
@@ -134,6 +164,7 @@ def postprocess(box_pred, cls_pred, center_pred, locations):
     N, P, Cn = c.shape
     out_l = torch.empty((N, P, 4), dtype=torch.float32, device=c.device)
     out_s = torch.empty((N, P, Cn), dtype=torch.float32, device=c.device)
-    L.check(L.lib().sbod_fcos_postprocess(L.ptr(b), L.ptr(c), L.ptr(z), L.ptr(loc), N, P, Cn, L.ptr(out_l),
-                                          L.ptr(out_s), L.stream_ptr()))
+    with torch.cuda.device(c.device):
+        L.check(L.lib().sbod_fcos_postprocess(L.ptr(b), L.ptr(c), L.ptr(z), L.ptr(loc), N, P, Cn, L.ptr(out_l),
+                                              L.ptr(out_s), L.stream_ptr()))
     return out_l, out_s

@@ -7,6 +7,7 @@ from ..core import LossSpec, fused_loss
 from ._multibox import _cfg
 
 
+@L.on_device
 def offset2bbox(arm_locs, odm_locs, priors_cxcy):
     """Two-stage decode ARM -> ODM -> xyxy for the whole batch (RefineDet512.py:643-653)."""
     L.need_cuda(arm_locs, odm_locs, priors_cxcy)
@@ -65,8 +66,9 @@ class RefineDetLoss(nn.Module):
         a_sc = L.f32c(arm_scores.detach())
         assert a_sc.size(2) == 2
         exclude = torch.empty(a_sc.shape[:2], dtype=torch.uint8, device=a_sc.device)
-        L.check(L.lib().sbod_arm_easy_negative(L.ptr(a_sc), a_sc.size(0) * a_sc.size(1), float(self.theta),
-                                               L.ptr(exclude), L.stream_ptr()))
+        with torch.cuda.device(a_sc.device):
+            L.check(L.lib().sbod_arm_easy_negative(L.ptr(a_sc), a_sc.size(0) * a_sc.size(1), float(self.theta),
+                                                   L.ptr(exclude), L.stream_ptr()))
         self.last_odm = {}
         return fused_loss(self._spec(False), self.priors_cxcy, self.priors_xy, odm_locs, odm_scores, boxes,
                           labels, anchors_xy=anchors_xy, exclude=exclude, group=self.process_group,

@@ -28,6 +28,11 @@ class FusedAnchorLoss(nn.Module):
     #: (mining variant for the CE branch, focal variant for the FOCAL branch)
     ce_kind = L.CLS_CE_MINE_NONPOS
     focal_kind = L.CLS_FOCAL_SUM
+    #: The reference only special-cases reg_loss == 'DIOU' (SSD512.py:578-583, RetinaNet.py:461-466): any other
+    #: value, 'GIOU' included, trains with the plain loc loss. Setting this attribute (or the config key
+    #: 'sbod_extended_reg_losses') to True is the explicit opt-in that lets 'GIOU' / 'IOU' / 'CIOU' select the
+    #: corresponding IouLoss flavour of operators/Loss.py:164-200 on the fused path (BASELINE config 3).
+    extended_reg_losses = False
 
     def __init__(self, priors_cxcy, config, threshold=0.5, neg_pos_ratio=3):
         super().__init__()
@@ -52,8 +57,10 @@ class FusedAnchorLoss(nn.Module):
     def _spec(self):
         reg = str(_cfg(self.config, "reg_loss", "")).upper()
         cls = str(_cfg(self.config, "cls_loss", "")).upper()
-        reg_kind = {"DIOU": L.REG_DIOU, "GIOU": L.REG_GIOU, "IOU": L.REG_IOU, "CIOU": L.REG_CIOU}.get(
-            reg, self.plain_reg_kind)
+        kinds = {"DIOU": L.REG_DIOU}
+        if self.extended_reg_losses or _cfg(self.config, "sbod_extended_reg_losses", False):
+            kinds.update({"GIOU": L.REG_GIOU, "IOU": L.REG_IOU, "CIOU": L.REG_CIOU})
+        reg_kind = kinds.get(reg, self.plain_reg_kind)
         cls_kind = self.focal_kind if cls == "FOCAL" else self.ce_kind
         return LossSpec(reg_kind=reg_kind, cls_kind=cls_kind, threshold=self.threshold,
                         neg_pos_ratio=self.neg_pos_ratio, reg_weight=float(self.alpha))

@@ -20,15 +20,16 @@ class _RowLoss(torch.autograd.Function):
         M, Cn = x.shape
         row = torch.empty((M,), dtype=torch.float32, device=x.device)
         grad = torch.empty_like(x) if logits.requires_grad else None
-        if kind == "softmax":
-            L.check(L.lib().sbod_softmax_focal(L.ptr(x), L.ptr(t), M, Cn, a0, a1, gamma, L.ptr(row),
+        with torch.cuda.device(x.device):
+            if kind == "softmax":
+                L.check(L.lib().sbod_softmax_focal(L.ptr(x), L.ptr(t), M, Cn, a0, a1, gamma, L.ptr(row),
+                                                   L.ptr(grad), L.stream_ptr()))
+            elif kind == "bce":
+                L.check(L.lib().sbod_bce_focal(L.ptr(x), L.ptr(t), M, Cn, a0, gamma, L.ptr(row),
                                                L.ptr(grad), L.stream_ptr()))
-        elif kind == "bce":
-            L.check(L.lib().sbod_bce_focal(L.ptr(x), L.ptr(t), M, Cn, a0, gamma, L.ptr(row),
-                                           L.ptr(grad), L.stream_ptr()))
-        else:
-            L.check(L.lib().sbod_sigmoid_focal(L.ptr(x), L.ptr(t), M, Cn, a0, gamma, L.ptr(row),
-                                               L.ptr(grad), L.stream_ptr()))
+            else:
+                L.check(L.lib().sbod_sigmoid_focal(L.ptr(x), L.ptr(t), M, Cn, a0, gamma, L.ptr(row),
+                                                   L.ptr(grad), L.stream_ptr()))
         ctx.grad = grad
         return row
 
@@ -121,8 +122,10 @@ class _SmoothL1(torch.autograd.Function):
         p, t = L.f32c(pred.detach()), L.f32c(target.detach())
         out = torch.empty_like(p)
         grad = torch.empty_like(p) if pred.requires_grad else None
-        L.check(L.lib().sbod_smooth_l1(L.ptr(p), L.ptr(t), p.numel(), float(beta), L.ptr(out), L.ptr(grad),
-                                       L.stream_ptr()))
+        L.device_of(p, t)
+        with torch.cuda.device(p.device):
+            L.check(L.lib().sbod_smooth_l1(L.ptr(p), L.ptr(t), p.numel(), float(beta), L.ptr(out), L.ptr(grad),
+                                           L.stream_ptr()))
         ctx.grad = grad
         return out
 

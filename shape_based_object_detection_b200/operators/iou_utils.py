@@ -7,6 +7,7 @@ import ctypes as C
 
 import torch
 
+from .. import _boxops as B
 from .. import _lib as L
 
 
@@ -15,7 +16,8 @@ class _PairOverlap(torch.autograd.Function):
     def forward(ctx, b1, b2, kind):
         a, b = L.f32c(b1.detach()), L.f32c(b2.detach())
         out = torch.empty((a.size(0),), dtype=torch.float32, device=a.device)
-        L.check(L.lib().sbod_pair_iou_fwd(L.ptr(a), L.ptr(b), a.size(0), kind, L.ptr(out), L.stream_ptr()))
+        with torch.cuda.device(a.device):
+            L.check(L.lib().sbod_pair_iou_fwd(L.ptr(a), L.ptr(b), a.size(0), kind, L.ptr(out), L.stream_ptr()))
         ctx.save_for_backward(a, b)
         ctx.kind = kind
         return out
@@ -26,11 +28,13 @@ class _PairOverlap(torch.autograd.Function):
         go = L.f32c(grad_out)
         g1 = torch.empty_like(a) if ctx.needs_input_grad[0] else None
         g2 = torch.empty_like(b) if ctx.needs_input_grad[1] else None
-        L.check(L.lib().sbod_pair_iou_bwd(L.ptr(a), L.ptr(b), L.ptr(go), a.size(0), ctx.kind, L.ptr(g1),
-                                          L.ptr(g2), L.stream_ptr()))
+        with torch.cuda.device(a.device):
+            L.check(L.lib().sbod_pair_iou_bwd(L.ptr(a), L.ptr(b), L.ptr(go), a.size(0), ctx.kind, L.ptr(g1),
+                                              L.ptr(g2), L.stream_ptr()))
         return g1, g2, None
 
 
+@L.on_device
 def _pair(bboxes1, bboxes2, kind):
     rows, cols = bboxes1.shape[0], bboxes2.shape[0]
     if rows * cols == 0:  # the reference returns its (rows, cols) scratch tensor here (iou_utils.py:9-11)
@@ -59,23 +63,16 @@ def bbox_overlaps_ciou(bboxes1, bboxes2):
 
 def point_form(boxes):
     """(cx, cy, w, h) -> (xmin, ymin, xmax, ymax); iou_utils.py:167-177."""
-    L.need_cuda(boxes)
-    x = L.f32c(boxes)
-    out = torch.empty_like(x)
-    L.check(L.lib().sbod_box_convert(L.ptr(x), L.ptr(out), x.size(0), L.BOX_CXCY_TO_XY, L.stream_ptr()))
-    return out
+    return B.convert(boxes, L.BOX_CXCY_TO_XY)
 
 
 def center_size(boxes):
     """(xmin, ymin, xmax, ymax) -> (cx, cy, w, h). The reference's version (iou_utils.py:180-189)
     raises on its malformed torch.cat call; this is the intended conversion."""
-    L.need_cuda(boxes)
-    x = L.f32c(boxes)
-    out = torch.empty_like(x)
-    L.check(L.lib().sbod_box_convert(L.ptr(x), L.ptr(out), x.size(0), L.BOX_XY_TO_CXCY, L.stream_ptr()))
-    return out
+    return B.convert(boxes, L.BOX_XY_TO_CXCY)
 
 
+@L.on_device
 def jaccard(box_a, box_b):
     """Dense IoU [A,B] without EPS or masking (0/0 -> NaN); iou_utils.py:215-233."""
     L.need_cuda(box_a, box_b)
@@ -87,6 +84,7 @@ def jaccard(box_a, box_b):
     return out
 
 
+@L.on_device
 def intersect(box_a, box_b):
     """Intersection area [A,B]; iou_utils.py:192-212."""
     L.need_cuda(box_a, box_b)
@@ -100,24 +98,15 @@ def intersect(box_a, box_b):
 
 def encode(matched, priors, variances):
     """iou_utils.py:324-345."""
-    L.need_cuda(matched, priors)
-    a, p = L.f32c(matched), L.f32c(priors)
-    out = torch.empty_like(a)
-    L.check(L.lib().sbod_box_encode(L.ptr(a), L.ptr(p), L.ptr(out), a.size(0), L.CODEC_IOU_UTILS,
-                                    float(variances[0]), float(variances[1]), L.stream_ptr()))
-    return out
+    return B.encode(matched, priors, L.CODEC_IOU_UTILS, variances[0], variances[1])
 
 
 def decode(loc, priors, variances):
-    """iou_utils.py:349-368 (returns xyxy)."""
-    L.need_cuda(loc, priors)
-    a, p = L.f32c(loc), L.f32c(priors)
-    out = torch.empty_like(a)
-    L.check(L.lib().sbod_box_decode(L.ptr(a), L.ptr(p), L.ptr(out), a.size(0), L.CODEC_IOU_UTILS,
-                                    float(variances[0]), float(variances[1]), L.stream_ptr()))
-    return out
+    """iou_utils.py:349-368 (returns xyxy); differentiable with respect to loc (IouLoss 'Center' mode)."""
+    return B.decode(loc, priors, L.CODEC_IOU_UTILS, variances[0], variances[1])
 
 
+@L.on_device
 def _match(threshold, truths, priors, variances, labels, loc_t, conf_t, idx, encode_loc):
     L.need_cuda(truths, priors, labels)
     dev = priors.device
@@ -127,7 +116,8 @@ def _match(threshold, truths, priors, variances, labels, loc_t, conf_t, idx, enc
     loc = torch.empty((P, 4), dtype=torch.float32, device=dev)
     conf = torch.empty((P,), dtype=torch.int64, device=dev)
     nbytes = L.lib().sbod_match_workspace_bytes(G, P)
-    ws = L.Workspace.get(dev, ("match", G, P), nbytes)
+    kbytes = (G * 8 + 255) // 256 * 256  # the per-object keys lead the workspace and carry the zero contract
+    ws = L.Workspace.get(dev, "match", nbytes, zero_bytes=kbytes, layout=(kbytes,))
     v0, v1 = (float(variances[0]), float(variances[1])) if variances is not None else (0.1, 0.2)
     L.check(L.lib().sbod_match(float(threshold), L.ptr(t), G, L.ptr(p), P, v0, v1, L.ptr(lab),
                                1 if encode_loc else 0, L.ptr(loc), L.ptr(conf), L.ptr(ws),
@@ -152,6 +142,7 @@ def log_sum_exp(x):
     return torch.log(torch.sum(torch.exp(x - x_max), 1, keepdim=True)) + x_max
 
 
+@L.on_device
 def _nms_device(boxes, scores, overlap, top_k, diou_beta=None):
     L.need_cuda(boxes, scores)
     n = scores.size(0)
@@ -159,7 +150,7 @@ def _nms_device(boxes, scores, overlap, top_k, diou_beta=None):
     keep = torch.zeros((n,), dtype=torch.int64, device=scores.device)
     count = torch.zeros((1,), dtype=torch.int32, device=scores.device)
     nbytes = L.lib().sbod_nms_workspace_bytes(n)
-    ws = L.Workspace.get(scores.device, ("nms", n), nbytes, zero_bytes=0)
+    ws = L.Workspace.get(scores.device, "nms", nbytes, zero_bytes=0)
     if diou_beta is None:
         L.check(L.lib().sbod_nms(L.ptr(b), L.ptr(s), n, float(overlap), int(top_k), L.ptr(keep), L.ptr(count),
                                  L.ptr(ws), C.c_size_t(nbytes), L.stream_ptr()))
