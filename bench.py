@@ -1,23 +1,29 @@
 #!/usr/bin/env python
 """bench.py — images/sec of the detection box pipeline (assign + loss fwd/bwd + NMS) on B200.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config 1..5]
 
-Workload (BASELINE.json configs[1]): SSD512 COCO-shaped synthetic batch — 24 564 priors, 81 classes,
-<= 100 GT boxes per image, 32 images PER GPU. One step = the train path (targets + loss forward +
-backward) on a train batch AND the eval path (decode + threshold + NMS + top-k) on an eval batch of the
-same 32 images-per-GPU size. value = images/sec of the whole job with inputs resident in HBM;
-e2e = the same through the public Python API with pinned HOST buffers (H2D of every input and D2H
-of the results inside the timed region). Multi-GPU: one process per GPU (torchrun), batch sharded
-by image, the only exchange is one all-reduce of four loss sums per step ("weak" scaling).
-The resident step is replayed as one CUDA graph (--no-graph: eager launches) with the train half and
-the eval half on two streams inside it (--no-overlap: one stream); both halves, all nine kernel
-launches and the all-reduce are inside the timed region either way.
+--config picks one of BASELINE.json's five configs (default 2, the one the metric is quoted on):
+  1 SSD300 VOC-shaped        8 732 priors x 21 classes, <= 20 GT, L1 + batch-global hard-negative mining
+  2 SSD512 COCO-shaped      24 564 priors x 81 classes, <= 100 GT, SmoothL1 + per-image mining      (default)
+  3 RetinaNet 640x640       76 725 anchors x 81 classes, softmax focal + GIoU, per-class top-1000 NMS
+  4 RefineDet512 DETRAC     16 320 priors, ARM (2 classes) + ODM (4 classes), <= 200 dense GT, refined anchors
+  5 FCOS 800x1333           22 300 locations x 81 columns, centre sampling + DIoU + NMS, 8 images per GPU
+                            (= batch 64 sharded over 8 GPUs)
+One step = the train path (targets + loss forward + backward) on a train batch AND the eval path (decode +
+threshold + NMS + top-k) on an eval batch of the same per-GPU size. value = images/sec of the whole job with
+inputs resident in HBM; e2e = the same through the public Python API with pinned HOST buffers (H2D of every
+input and D2H of the results inside the timed region, copies on a copy stream overlapping the compute).
+Multi-GPU: one process per GPU (torchrun), batch sharded by image, the only exchange is the loss sums
+(four doubles per criterion; "weak" scaling); config 1's batch-global mining does not shard: replicas only.
+The resident step is replayed as one CUDA graph (--no-graph: eager launches) with the train half and the eval
+half on two streams inside it (--no-overlap: one stream).
 
---impl reference times the CPU oracle port of the reference (oracle/box_pipeline.py — the reference
-is pure Python/PyTorch and is not present on the GPU box) on the host cores, on a bounded sample.
+--impl reference times the reference's own CPU implementation on the host cores (oracle/_ref when the build
+placed it there, else the oracle port), on a bounded sample of the same workload.
 """
 import argparse
+import ctypes as C
 import json
 import os
 import subprocess
@@ -30,12 +36,53 @@ import torch
 REPO = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, REPO)
 
-P_WORKLOAD = "ssd512_canonical"
-N_PER_GPU, N_CLASSES, GMAX = 32, 81, 100
-NMS = dict(min_score=0.01, max_overlap=0.45, top_k=200)
-WORKLOAD = ("SSD512 COCO-shaped synthetic: 24564 priors x 81 classes, <=100 GT/img, 32 img/GPU; step = "
-            "MultiBoxLoss512 (SmoothL1 + CE hard-negative mining) fwd+bwd on a train batch + detect "
-            "(0.01, 0.45, 200) on an eval batch")
+METRIC = "images/sec for assign+loss+NMS"
+
+CONFIGS = {
+    1: dict(name="ssd300_voc", priors="ssd300", C=21, gmax=20, n_per_gpu=32, nms=(0.01, 0.45, 200), shards=False,
+            cpu_sample=(8, 2),
+            workload="SSD300 VOC-shaped synthetic: 8732 priors x 21 classes, <=20 GT/img, 32 img/GPU; step = "
+                     "MultiBoxLoss300 (L1 + CE batch-global hard-negative mining) fwd+bwd on a train batch + detect "
+                     "(0.01, 0.45, 200) on an eval batch"),
+    2: dict(name="ssd512_coco", priors="ssd512_canonical", C=81, gmax=100, n_per_gpu=32, nms=(0.01, 0.45, 200),
+            shards=True, cpu_sample=(2, 1),
+            workload="SSD512 COCO-shaped synthetic: 24564 priors x 81 classes, <=100 GT/img, 32 img/GPU; step = "
+                     "MultiBoxLoss512 (SmoothL1 + CE hard-negative mining) fwd+bwd on a train batch + detect "
+                     "(0.01, 0.45, 200) on an eval batch"),
+    3: dict(name="retinanet640", priors="retinanet640", C=81, gmax=100, n_per_gpu=32, nms=(0.01, 0.45, 200),
+            shards=True, cpu_sample=(1, 1),
+            workload="RetinaNet 640x640 synthetic: 76725 anchors x 81 classes, <=100 GT/img, 32 img/GPU; step = "
+                     "RetinaFocalLoss (softmax focal + GIoU) fwd+bwd on a train batch + detect (0.01, 0.45, 200) "
+                     "with the per-class top-1000 candidate cap on an eval batch"),
+    4: dict(name="refinedet512_detrac", priors="refinedet512", C=4, gmax=200, n_per_gpu=32, nms=(0.01, 0.45, 200),
+            shards=True, cpu_sample=(2, 1),
+            workload="RefineDet512 DETRAC-shaped synthetic: 16320 priors, ARM 2 classes + ODM 4 classes, <=200 dense "
+                     "GT/img, 32 img/GPU; step = RefineDetLoss (ARM + ODM against refined anchors) fwd+bwd on a train "
+                     "batch + offset2bbox + detect_refine (0.01, 0.45, 200, second NMS 0.7) on an eval batch"),
+    5: dict(name="fcos_800x1333", priors=None, C=81, gmax=100, n_per_gpu=8, nms=(0.05, 0.45, 100), shards=True,
+            cpu_sample=(1, 1),
+            workload="FCOS 800x1333 COCO-shaped synthetic: 22300 locations x (80 classes + centerness), <=100 GT/img, "
+                     "8 img/GPU (batch 64 over 8 GPUs); step = FCOSLoss (centre-sampling assignment + sigmoid focal + "
+                     "centerness-weighted DIoU + BCE) fwd+bwd on a train batch + postprocess + detect (0.05, 0.45, 100) "
+                     "on an eval batch; reference FCOS code does not run: parity unpinned, CPU arm = oracle port"),
+}
+
+
+def config_entry(cid):
+    """The `config` object of the JSON line: identical on both arms (ours / reference) by construction."""
+    cf = CONFIGS[cid]
+    return {"workload": cf["workload"], "config_id": cid, "images_per_gpu": cf["n_per_gpu"], "l2": L2_NOTE[cid]}
+
+
+# per-step input bytes of a config vs the 126 MB L2 (timing rule: say whether the inputs exceed it)
+L2_NOTE = {
+    1: "inputs of a step (2 x 23.5 MB logits) FIT the 126 MB L2: this config is latency / issue bound, not HBM bound",
+    2: "inputs of a step (2 x 255 MB logits) exceed the 126 MB L2",
+    3: "inputs of a step (2 x 796 MB logits) exceed the 126 MB L2",
+    4: "inputs of a step (< 40 MB) FIT the 126 MB L2: this config is FP32-issue / latency bound (P x G pair evaluations)",
+    5: "inputs of a step (2 x 58 MB logits) are of the order of the 126 MB L2; consecutive steps alternate train and "
+       "eval buffers (231 MB touched per step)",
+}
 
 
 class Cfg(dict):
@@ -43,8 +90,8 @@ class Cfg(dict):
     __setattr__ = dict.__setitem__
 
 
-def make_cfg(device):
-    return Cfg(device=device, n_classes=N_CLASSES, reg_weights=1.0, reg_loss="", cls_loss="",
+def make_cfg(device, n_classes, reg="", cls=""):
+    return Cfg(device=device, n_classes=n_classes, reg_weights=1.0, reg_loss=reg, cls_loss=cls,
                model={"box_type": "offset"}, focal_type="softmax")
 
 
@@ -94,61 +141,118 @@ class ClockSampler:
 
 
 # ---------------------------------------------------------------------------------------------
-# CPU baseline: the oracle port of the reference, all host threads, bounded sample
+# synthetic inputs of a config (CPU tensors; SURVEY §8d distributions)
 # ---------------------------------------------------------------------------------------------
-def cpu_reference_step(pri, train, evalb, n_train, n_eval):
-    """One pass of the reference algorithm (oracle port) over n_train train images + n_eval eval images.
-    Returns seconds per image for (loss fwd+bwd) and (detect)."""
-    import torchvision
-    from oracle import box_pipeline as O
-    locs, scores, bx, lb = train
-    l_c = locs[:n_train].clone().requires_grad_(True)
-    s_c = scores[:n_train].clone().requires_grad_(True)
+def make_inputs(cid, n, seed_train, seed_eval):
+    """Returns (priors_or_locations, train dict, eval dict) of CPU tensors."""
+    from shape_based_object_detection_b200 import priors as PR, synth
+    cf = CONFIGS[cid]
+    Cn = cf["C"]
+    if cid == 5:
+        from shape_based_object_detection_b200.models import compute_location
+        locations = compute_location(image_size=(800, 1333))
+        P = sum(l.size(0) for l in locations)
+        gen = torch.Generator().manual_seed(seed_train)
+        bx, lb = synth.make_gt(n, cf["gmax"], Cn, gen)
+        train = dict(tensors=[torch.rand((n, P, 4), generator=gen) * 0.3 + 0.01, torch.randn((n, P, Cn), generator=gen),
+                              torch.randn((n, P), generator=gen)], boxes=bx, labels=lb)
+        gen = torch.Generator().manual_seed(seed_eval)
+        ev = dict(tensors=[torch.rand((n, P, 4), generator=gen) * 0.3 + 0.01,
+                           torch.randn((n, P, Cn), generator=gen) * 2.0 - 3.0, torch.randn((n, P), generator=gen)])
+        return locations, train, ev
+    pri = PR.PRIOR_TABLES[cf["priors"]]()
+    P = pri.size(0)
+    if cid == 4:
+        gen = torch.Generator().manual_seed(seed_train)
+        bx, lb = synth.make_gt(n, cf["gmax"], Cn, gen, dense=True)
+        train = dict(tensors=[torch.randn((n, P, 4), generator=gen) * 0.1, torch.randn((n, P, 2), generator=gen) * 2.0,
+                              torch.randn((n, P, 4), generator=gen) * 0.1, torch.randn((n, P, Cn), generator=gen)],
+                     boxes=bx, labels=lb)
+        gen = torch.Generator().manual_seed(seed_eval)
+        sc = torch.randn((n, P, Cn), generator=gen) * 2.0
+        sc[:, :, 0] += 4.0
+        ev = dict(tensors=[torch.randn((n, P, 4), generator=gen) * 0.3, torch.randn((n, P, 4), generator=gen) * 0.3, sc],
+                  arm_scores=torch.randn((n, P, 2), generator=gen) * 2.0)
+        return pri, train, ev
+    locs, scores, bx, lb = synth.make_train_batch(pri, n, Cn, cf["gmax"], seed_train)
+    elocs, escores = synth.make_eval_batch(pri, n, Cn, seed_eval)
+    return pri, dict(tensors=[locs, scores], boxes=bx, labels=lb), dict(tensors=[elocs, escores])
+
+
+def algorithmic_bytes(cid, n, P, T):
+    """SURVEY §8(d) per-step algorithmic bytes of a config (train fwd+bwd + eval), for the step-level check."""
+    Cn = CONFIGS[cid]["C"]
+    if cid == 4:  # ARM (2 classes) + ODM (Cn classes): logits, locs, per-image anchors, grads
+        per = P * ((2 + Cn) * 4 * 3 + 16 * 4 + 16)
+        return n * per + P * 16 + T * 24 * 2 + n * P * (Cn * 4 + 32)
+    if cid == 5:
+        return n * P * ((Cn * 4 + 16 + 4) * 3) + T * 24 + n * P * (Cn * 4 * 3 + 20)
+    train = n * P * (Cn * 4 * 3 + 16 * 2) + P * 16 + T * 24
+    ev = n * P * (Cn * 4 + 16) + P * 16
+    return train + ev
+
+
+# ---------------------------------------------------------------------------------------------
+# CPU arm: the reference's own implementation (oracle/_ref) or the oracle port, bounded sample
+# ---------------------------------------------------------------------------------------------
+def cpu_arm(cid, reps, warm):
+    """Times the CPU implementation of config `cid` on a bounded sample. Returns the cpu_baseline dict."""
+    from oracle import ref_runner as RR
+    cf = CONFIGS[cid]
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    n_train, n_eval = cf["cpu_sample"]
+    pri, train, ev = make_inputs(cid, max(n_train, n_eval), 1234 + cid, 4321 + cid)
+    runner = RR.Runner(cid, pri, cf["C"])
+    tt = [t[:n_train] for t in train["tensors"]]
+    et = [t[:n_eval] for t in ev["tensors"]]
+    keep = (ev["arm_scores"][:n_eval, :, 1] > 0.01) if cid == 4 else None
+
+    def once():
+        t0 = time.perf_counter()
+        runner.train(tt, train["boxes"][:n_train], train["labels"][:n_train])
+        t1 = time.perf_counter()
+        if cid == 4:
+            runner.eval(et, cf["nms"], keep)
+        else:
+            runner.eval(et, cf["nms"])
+        t2 = time.perf_counter()
+        return (t1 - t0) / n_train, (t2 - t1) / n_eval
+
+    for _ in range(warm):
+        once()
+    a, b = [], []
     t0 = time.perf_counter()
-    loss = O.multibox_loss("s512", pri, l_c, s_c, bx[:n_train], lb[:n_train])
-    loss.backward()
-    t1 = time.perf_counter()
-    O.detect(evalb[0][:n_eval].clone(), evalb[1][:n_eval], NMS["min_score"], NMS["max_overlap"], NMS["top_k"], pri,
-             nms_fn=torchvision.ops.nms)
-    t2 = time.perf_counter()
-    return (t1 - t0) / n_train, (t2 - t1) / n_eval
+    for _ in range(reps):
+        x, y = once()
+        a.append(x)
+        b.append(y)
+    wall = time.perf_counter() - t0
+    a.sort()
+    b.sort()
+    ta, tb = a[len(a) // 2], b[len(b) // 2]
+    value = 1.0 / (ta + tb)
+    src = ("the reference's own code (oracle/_ref, unmodified)" if runner.kind == "reference"
+           else "the oracle port of the reference (oracle/box_pipeline.py)")
+    sample = (f"{n_train} train image(s) (loss fwd+bwd) + {n_eval} eval image(s) (detect) of the same workload per "
+              f"pass, {src}, median of {reps} pass(es) after {warm} warm-up")
+    return {"value": value, "unit": "images/s", "cores": cores, "kind": runner.kind, "sample": sample,
+            "ms_per_image_loss_fwd_bwd": ta * 1e3, "ms_per_image_detect": tb * 1e3}, wall
 
 
 def run_reference(args, rank, world):
     """--impl reference: rank 0 alone times the CPU path."""
     if rank != 0:
         return
-    from shape_based_object_detection_b200 import priors as PR, synth
-    cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
-    pri = PR.PRIOR_TABLES[P_WORKLOAD]()
-    n_train, n_eval = 4, 1
-    train = synth.make_train_batch(pri, n_train, N_CLASSES, GMAX, 1234 + 2)
-    evalb = synth.make_eval_batch(pri, n_eval, N_CLASSES, 4321)
-    for _ in range(args.warmup):
-        cpu_reference_step(pri, train, evalb, n_train, n_eval)
-    t_tr, t_ev = [], []
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        a, b = cpu_reference_step(pri, train, evalb, n_train, n_eval)
-        t_tr.append(a)
-        t_ev.append(b)
-    wall = time.perf_counter() - t0
-    t_tr.sort()
-    t_ev.sort()
-    per_img = t_tr[len(t_tr) // 2] + t_ev[len(t_ev) // 2]
-    value = 1.0 / per_img
-    sample = (f"{n_train} train images (loss fwd+bwd) + {n_eval} eval image (detect) per step of the same "
-              f"workload; median over {args.steps} steps")
+    cf = CONFIGS[args.config]
+    base, wall = cpu_arm(args.config, max(args.steps, 1), max(args.warmup, 1))
     print(json.dumps({
-        "impl": "reference", "metric": "images/sec for assign+loss+NMS", "value": value, "unit": "images/s",
-        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": wall / args.steps * 1e3,
+        "impl": "reference", "metric": METRIC, "value": base["value"], "unit": "images/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": wall / max(args.steps, 1) * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "sample": sample},
-        "cpu_baseline": {"value": value, "unit": "images/s", "cores": cores, "kind": "port", "sample": sample,
-                         "ms_per_image_loss_fwd_bwd": t_tr[len(t_tr) // 2] * 1e3,
-                         "ms_per_image_detect": t_ev[len(t_ev) // 2] * 1e3},
-        "e2e": {"value": value, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "config": config_entry(args.config),
+        "cpu_baseline": base,
+        "e2e": {"value": base["value"], "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }))
 
@@ -168,19 +272,125 @@ def timed(fn, steps, sync):
     return e0.elapsed_time(e1) / steps
 
 
-def run_ours(args, rank, world, local_rank):
-    import ctypes as C
+def bind_to_gpu_numa(local_rank):
+    """Pin this process to the CPU cores next to its GPU before any pinned host buffer is allocated, so that the
+    H2D copies of the e2e leg do not cross sockets (eight ranks copying at once otherwise contend on the host)."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(local_rank)
+        words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, words)
+        cpus = [64 * i + b for i, w in enumerate(mask) for b in range(64) if (int(w) >> b) & 1]
+        cpus = [c for c in cpus if c in os.sched_getaffinity(0)]
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return len(cpus)
+    except Exception:
+        pass
+    return None
 
+
+class Workload:
+    """Device-side state of one config: criteria, resident tensors, the train / eval halves of a step."""
+
+    def __init__(self, cid, dev, rank, group):
+        import shape_based_object_detection_b200 as S
+        from shape_based_object_detection_b200 import models as M
+        self.S, self.cid, self.dev, self.cf = S, cid, dev, CONFIGS[cid]
+        cf = self.cf
+        self.N = cf["n_per_gpu"]
+        pri, train, ev = make_inputs(cid, self.N, 1234 + cid + 1000 * rank, 4321 + cid + 1000 * rank)
+        self.h_train = [t.pin_memory() for t in train["tensors"]]
+        self.h_eval = [t.pin_memory() for t in ev["tensors"]]
+        self.h_boxes = [b.pin_memory() for b in train["boxes"]]
+        self.h_labels = [l.pin_memory() for l in train["labels"]]
+        self.T = sum(int(b.size(0)) for b in train["boxes"])
+        self.d_train = [t.to(dev).requires_grad_(True) for t in self.h_train]
+        self.d_eval = [t.to(dev) for t in self.h_eval]
+        d_boxes, d_labels = [b.to(dev) for b in self.h_boxes], [l.to(dev) for l in self.h_labels]
+        self.gt = S.pack_ground_truth(d_boxes, d_labels, dev)
+        grp = group if cf["shards"] else None
+        if cid == 5:
+            self.locations = [l.to(dev) for l in pri]
+            self.P = sum(l.size(0) for l in pri)
+            self.crit = M.FCOSLoss(self.locations, make_cfg(dev, cf["C"]), image_size=(800, 1333))
+        else:
+            self.pri = pri.to(dev)
+            self.P = pri.size(0)
+            if cid == 1:
+                self.crit = M.MultiBoxLoss300(self.pri, make_cfg(dev, cf["C"]))
+            elif cid == 2:
+                self.crit = M.MultiBoxLoss512(self.pri, make_cfg(dev, cf["C"]))
+            elif cid == 3:
+                self.crit = M.RetinaFocalLoss(self.pri, make_cfg(dev, cf["C"], "GIOU", "FOCAL"))
+                self.crit.extended_reg_losses = True  # GIoU is an explicit opt-in (the reference only knows DIoU)
+            else:
+                self.crit = M.RefineDetLoss(self.pri, make_cfg(dev, cf["C"]))
+                self.h_arm_scores = ev["arm_scores"].pin_memory()
+                self.d_keep = (self.h_arm_scores.to(dev)[:, :, 1] > 0.01)  # RefineDet512.py:639 (raw logit > theta)
+        self.crit.process_group = grp
+        self.d_boxes, self.d_labels = d_boxes, d_labels
+
+    # ---- halves of a step on resident inputs ----
+    def train_half(self, tensors=None, boxes=None, labels=None):
+        ts = tensors if tensors is not None else self.d_train
+        for t in ts:
+            t.grad = None
+        if self.cid in (1, 2, 3) and tensors is None:
+            loss = self.crit.forward_packed(ts[0], ts[1], self.gt)  # GT packed once: inputs are resident
+        else:
+            loss = self.crit(*ts, boxes if boxes is not None else self.d_boxes,
+                             labels if labels is not None else self.d_labels)
+        loss.backward()
+        return loss
+
+    def eval_half(self, tensors=None, keep=None):
+        S, cf = self.S, self.cf
+        ts = tensors if tensors is not None else self.d_eval
+        ms, mo, tk = cf["nms"]
+        if self.cid in (1, 2):
+            return S.detect_batched(ts[0], ts[1], ms, mo, tk, self.pri)
+        if self.cid == 3:
+            return S.detect_batched(ts[0], ts[1], ms, mo, tk, self.pri, pre_nms_topk=1000)
+        if self.cid == 4:
+            from shape_based_object_detection_b200.models import offset2bbox
+            boxes = offset2bbox(ts[0], ts[1], self.pri)
+            return S.detect_batched(boxes, ts[2], ms, mo, tk, self.pri, box_type="corner", clamp_inplace=True,
+                                    prior_keep=keep if keep is not None else self.d_keep, second_nms_thr=0.7)
+        from shape_based_object_detection_b200.models import fcos_postprocess
+        bl, sc = fcos_postprocess(ts[0], ts[1], ts[2], self.locations)
+        return S.detect_batched(bl, sc, ms, mo, tk, None, act="none", box_type="corner", clamp_inplace=True)
+
+    def h2d_bytes(self):
+        n = sum(t.numel() * t.element_size() for t in self.h_train + self.h_eval) + self.T * 24
+        if self.cid == 4:
+            n += self.h_arm_scores.numel() * 4
+        return n
+
+    def d2h_bytes(self):
+        return 4 + self.N * self.cf["nms"][2] * (16 + 8 + 4) + self.N * 4
+
+    def launches_per_step(self, world):
+        """Kernels of libsbod.so launched per resident step (counted from the call sequence of each path)."""
+        ex = 1 if (world > 1 and self.cf["shards"]) else 0  # finalize after the all-reduce
+        det = 3  # bound pass, refine, NMS
+        return {1: 4 + det,            # match_lse, classify_mine, mine_batch, bwd_patch
+                2: 3 + ex + det,       # match_lse, classify_mine, bwd_patch
+                3: 3 + ex + det,       # match_lse, classify_mine, loss_bwd (dense)
+                4: 2 * (3 + ex) + 2 + det + 1,  # ARM + ODM, decode_arm + easy-negative mask, offset2bbox
+                5: 4 + ex + det + 1}[self.cid]  # assign, terms, finalize, backward terms, postprocess
+
+
+def run_ours(args, rank, world, local_rank):
     import torch.distributed as dist
 
     import shape_based_object_detection_b200 as S
     from shape_based_object_detection_b200 import _lib as L
-    from shape_based_object_detection_b200 import priors as PR, synth
-    from shape_based_object_detection_b200.models import MultiBoxLoss512
-    from shape_based_object_detection_b200.models import utils as MU
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device — the product path has no CPU fallback")
+    numa_cpus = bind_to_gpu_numa(local_rank)
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     L.lib()
@@ -195,75 +405,60 @@ def run_ours(args, rank, world, local_rank):
             dist.barrier()
             torch.cuda.synchronize()
 
-    pri = PR.PRIOR_TABLES[P_WORKLOAD]()
-    P = pri.size(0)
-    N = N_PER_GPU
-    # every rank owns its own 32 images (weak scaling); seeds differ per rank
-    train = synth.make_train_batch(pri, N, N_CLASSES, GMAX, 1234 + 2 + 1000 * rank)
-    evalb = synth.make_eval_batch(pri, N, N_CLASSES, 4321 + 1000 * rank)
-    pin = lambda t: t.pin_memory()
-    h_locs, h_scores = pin(train[0]), pin(train[1])
-    h_bx, h_lb = [pin(b) for b in train[2]], [pin(l) for l in train[3]]
-    h_elocs, h_escores = pin(evalb[0]), pin(evalb[1])
-    pri_d = pri.to(dev)
-    cfg = make_cfg(dev)
-    crit = MultiBoxLoss512(pri_d, cfg)
-    crit.process_group = group
-
-    d_locs = h_locs.to(dev).requires_grad_(True)
-    d_scores = h_scores.to(dev).requires_grad_(True)
-    d_bx, d_lb = [b.to(dev) for b in h_bx], [l.to(dev) for l in h_lb]
-    d_elocs, d_escores = h_elocs.to(dev), h_escores.to(dev)
-    gt = S.pack_ground_truth(d_bx, d_lb, dev)
-
-    # The train batch and the eval batch of a step are independent: by default the eval path runs on a
-    # second CUDA stream (both captured in the same graph); --no-overlap serialises them.
-    s_eval = torch.cuda.Stream(device=dev, priority=int(os.environ.get("SBOD_BENCH_SIDE_PRIO", "0")))
+    cid = args.config
+    cf = CONFIGS[cid]
+    W = Workload(cid, dev, rank, group)
+    N, P = W.N, W.P
+    s_eval = torch.cuda.Stream(device=dev)
+    s_copy = torch.cuda.Stream(device=dev)
 
     def step_resident():
-        d_locs.grad = None
-        d_scores.grad = None
         cur = torch.cuda.current_stream()
         if args.overlap:
             s_eval.wait_stream(cur)
             with torch.cuda.stream(s_eval):
-                out = S.detect_batched(d_elocs, d_escores, NMS["min_score"], NMS["max_overlap"], NMS["top_k"],
-                                       pri_d)
-        call = None
-        if not args.overlap and args.presample:
-            # the eval path's sampling pass (1/26 of the eval logits, one tile per CTA) is enqueued on
-            # a side stream: it fills the SMs that the small-grid kernels of the train path leave idle
-            call = S.detect_begin(d_elocs, d_escores, NMS["min_score"], NMS["max_overlap"], NMS["top_k"], pri_d,
-                                  side_stream=s_eval)
-        loss = crit.forward_packed(d_locs, d_scores, gt)  # GT packed once: inputs are resident
-        loss.backward()
-        if args.overlap:
+                out = W.eval_half()
+            W.train_half()
             cur.wait_stream(s_eval)
-        elif call is not None:
-            out = S.detect_end(call)
         else:
-            out = S.detect_batched(d_elocs, d_escores, NMS["min_score"], NMS["max_overlap"], NMS["top_k"], pri_d)
+            W.train_half()
+            out = W.eval_half()
         return out
 
     def step_e2e():
-        l = h_locs.to(dev, non_blocking=True).requires_grad_(True)
-        s = h_scores.to(dev, non_blocking=True).requires_grad_(True)
-        bx = [b.to(dev, non_blocking=True) for b in h_bx]
-        lb = [x.to(dev, non_blocking=True) for x in h_lb]
-        loss = crit(l, s, bx, lb)
-        loss.backward()
-        el = h_elocs.to(dev, non_blocking=True)
-        es = h_escores.to(dev, non_blocking=True)
-        out = S.detect_batched(el, es, NMS["min_score"], NMS["max_overlap"], NMS["top_k"], pri_d)
-        res = (loss.detach().cpu(), out[0].cpu(), out[1].cpu(), out[2].cpu(), out[4].cpu())
+        """Pinned host buffers in, results out. The copies run on a copy stream: the eval batch's H2D overlaps
+        the train half's compute, the train half's D2H overlaps the eval half."""
+        cur = torch.cuda.current_stream()
+        s_copy.wait_stream(cur)
+        with torch.cuda.stream(s_copy):
+            tr = [t.to(dev, non_blocking=True) for t in W.h_train]
+            bx = [b.to(dev, non_blocking=True) for b in W.h_boxes]
+            lb = [x.to(dev, non_blocking=True) for x in W.h_labels]
+            ev_train = torch.cuda.Event()
+            ev_train.record(s_copy)
+            evt = [t.to(dev, non_blocking=True) for t in W.h_eval]
+            keep = None
+            if cid == 4:
+                keep = W.h_arm_scores.to(dev, non_blocking=True)[:, :, 1] > 0.01
+            ev_eval = torch.cuda.Event()
+            ev_eval.record(s_copy)
+        cur.wait_event(ev_train)
+        for t in tr + bx + lb:
+            t.record_stream(cur)
+        loss = W.train_half([t.requires_grad_(True) for t in tr], bx, lb)
+        loss_h = loss.detach().to("cpu", non_blocking=True)
+        cur.wait_event(ev_eval)
+        for t in evt:
+            t.record_stream(cur)
+        out = W.eval_half(evt, keep)
+        res = (loss_h, out[0].cpu(), out[1].cpu(), out[2].cpu(), out[4].cpu())
         return res
 
     for _ in range(max(args.warmup, 3)):
         step_resident()
-    # The resident step is a fixed sequence of kernel launches: replay it as one CUDA graph so that the
-    # Python / launch overhead (~0.5 ms per step, more than the kernels themselves) leaves the timed loop.
     graph = g = None
     eager_step = step_resident
+    replay = step_resident
     if args.graph:
         try:
             torch.cuda.synchronize()
@@ -273,131 +468,177 @@ def run_ours(args, rank, world, local_rank):
             g.replay()
             torch.cuda.synchronize()
             graph = g
-            step_resident = g.replay
+            replay = g.replay
         except Exception as exc:  # capture is an optimisation, never a requirement
             print(f"bench.py: CUDA graph capture failed ({type(exc).__name__}: {exc}); running eagerly",
                   file=sys.stderr)
-            step_resident = eager_step
+            replay = eager_step
             torch.cuda.synchronize()
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    ms_step = timed(step_resident, args.steps, sync)
+    ms_step = timed(replay, args.steps, sync)
     clocks = sampler.stop() if rank == 0 else None
 
-    # ---- stage timings + the dominant kernel alone (CUDA events on the launching stream) ----
-    st = crit.last["state"]
-    ms_fwd = timed(lambda: st.forward(), args.steps, sync)
-    gl = torch.ones((), device=dev)
-    g_locs_buf, g_scores_buf = torch.empty_like(st.locs), torch.empty_like(st.scores)
-    ms_bwd = timed(lambda: st.backward_into(gl, g_locs_buf, g_scores_buf), args.steps, sync)
-    ms_det = timed(lambda: S.detect_batched(d_elocs, d_escores, NMS["min_score"], NMS["max_overlap"],
-                                            NMS["top_k"], pri_d), args.steps, sync)
-    stage = L.lib().sbod_loss_forward_stage
-    ms_match = timed(lambda: L.check(stage(C.byref(st.desc), 0, L.stream_ptr())), args.steps, sync)
-    L.check(stage(C.byref(st.desc), 1, L.stream_ptr()))  # leave the workspace clean
-    # the eval path's streaming kernel alone: build the descriptor once, then time stage 0 / stage 1 pairs
-    det_desc = S.core.make_detect_desc(d_elocs, d_escores, NMS["min_score"], NMS["max_overlap"], NMS["top_k"], pri_d)
+    # ---- halves and single kernels alone (CUDA events on the launching stream) ----
+    ms_train = timed(lambda: W.train_half(), args.steps, sync)
+    ms_eval = timed(lambda: W.eval_half(), args.steps, sync)
+    kernels = {}  # name -> (ms per launch, algorithmic bytes per launch, note)
+    Cn = cf["C"]
     dstage = L.lib().sbod_detect_stage
-    ms_dscore = 0.0
-    sync()
-    for _ in range(args.steps):
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        L.check(dstage(C.byref(det_desc["desc"]), 2, L.stream_ptr()))  # sampling pass (1/26 of the tiles)
-        e0.record()
-        L.check(dstage(C.byref(det_desc["desc"]), 3, L.stream_ptr()))  # the main score pass alone
-        e1.record()
-        L.check(dstage(C.byref(det_desc["desc"]), 1, L.stream_ptr()))
-        torch.cuda.synchronize()
-        ms_dscore += e0.elapsed_time(e1) / args.steps
+    if cid in (1, 2, 3, 4):
+        st = W.crit.last["state"] if cid != 4 else W.crit.last_odm["state"]
+        Cs = st.C
+        stage = L.lib().sbod_loss_forward_stage
+        prefill = bool(st.desc.grad_scores_prefill)
+        ms_match = ms_cm = 0.0  # pairs: classify_mine consumes what the match kernel left in the workspace
+        sync()
+        for _ in range(args.steps):
+            ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+            ev[0].record()
+            L.check(stage(C.byref(st.desc), 0, L.stream_ptr()))
+            ev[1].record()
+            L.check(stage(C.byref(st.desc), 1, L.stream_ptr()))
+            ev[2].record()
+            torch.cuda.synchronize()
+            ms_match += ev[0].elapsed_time(ev[1]) / args.steps
+            ms_cm += ev[1].elapsed_time(ev[2]) / args.steps
+        alg = N * P * Cs * 4 + P * 16 + W.T * 24 + (N * P * 16 if cid == 4 else 0)
+        kernels["match_lse_fast_kernel"] = dict(ms=ms_match, bytes=alg + (N * P * Cs * 4 if prefill else 0),
+                                                bytes_logits_only=alg, writes_gradient_zero_fill=prefill)
+        kernels["classify_mine_kernel"] = dict(ms=ms_cm, bytes=N * P * 17)
+        ms_fwd = timed(lambda: st.forward(), args.steps, sync)
+        gl = torch.ones((), device=dev)
+        g_l, g_s = torch.empty_like(st.locs), torch.empty_like(st.scores)
+        ms_bwd = timed(lambda: st.backward_into(gl, g_l, g_s), args.steps, sync)
+        if cid == 3:  # focal: dense backward, one kernel (logits in, gradient out)
+            kernels["loss_bwd_kernel"] = dict(ms=ms_bwd, bytes=2 * N * P * Cs * 4 + N * P * 16)
+        if cid == 4:
+            pairs = P * W.T  # prior x object pairs of one assignment pass
+            kernels["match_lse_fast_kernel"]["pair_evals_per_launch"] = pairs
+            kernels["match_lse_fast_kernel"]["pair_evals_per_s"] = pairs / (ms_match * 1e-3)
+    else:
+        ms_fwd = ms_bwd = None
+    # eval path: the streaming bound pass alone (stage 2), then refine (3) and NMS (1)
+    if True:
+        if cid in (1, 2, 3):
+            det = S.core.make_detect_desc(W.d_eval[0], W.d_eval[1], *cf["nms"], W.pri,
+                                          pre_nms_topk=1000 if cid == 3 else 0)
+            det_C = Cn
+        elif cid == 4:
+            from shape_based_object_detection_b200.models import offset2bbox
+            boxes4 = offset2bbox(W.d_eval[0], W.d_eval[1], W.pri)
+            det = S.core.make_detect_desc(boxes4, W.d_eval[2], *cf["nms"], W.pri, box_type="corner", clamp_inplace=True,
+                                          prior_keep=W.d_keep, second_nms_thr=0.7)
+            det_C = Cn
+        else:
+            from shape_based_object_detection_b200.models import fcos_postprocess
+            bl5, sc5 = fcos_postprocess(W.d_eval[0], W.d_eval[1], W.d_eval[2], W.locations)
+            det = S.core.make_detect_desc(bl5, sc5, *cf["nms"], None, act="none", box_type="corner", clamp_inplace=True)
+            det_C = Cn
+        acc = [0.0, 0.0, 0.0]
+        sync()
+        for _ in range(args.steps):
+            ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+            ev[0].record()
+            L.check(dstage(C.byref(det["desc"]), 2, L.stream_ptr()))
+            ev[1].record()
+            L.check(dstage(C.byref(det["desc"]), 3, L.stream_ptr()))
+            ev[2].record()
+            L.check(dstage(C.byref(det["desc"]), 1, L.stream_ptr()))
+            ev[3].record()
+            torch.cuda.synchronize()
+            for i in range(3):
+                acc[i] += ev[i].elapsed_time(ev[i + 1]) / args.steps
+        kernels["detect_bound_kernel"] = dict(ms=acc[0], bytes=N * P * det_C * 4 + N * P * 4)
+        kernels["detect_refine_kernel"] = dict(ms=acc[1], bytes=None)
+        kernels["detect_nms_kernel"] = dict(ms=acc[2], bytes=None)
+    if cid == 5:
+        from shape_based_object_detection_b200.models import fcos_postprocess
+        ms_pp = timed(lambda: fcos_postprocess(W.d_eval[0], W.d_eval[1], W.d_eval[2], W.locations), args.steps, sync)
+        kernels["fcos_postprocess_kernel"] = dict(ms=ms_pp, bytes=N * P * (Cn * 4 * 2 + 16 * 2 + 4))
 
-    # ---- e2e: pinned host buffers in, results out, every step ----
+    # ---- e2e ----
     for _ in range(2):
         step_e2e()
     e2e_steps = max(3, min(args.steps, 10))
     ms_e2e = timed(step_e2e, e2e_steps, sync)
+    # H2D alone (per rank, all ranks copying at once): is the e2e number a host-side limit?
+    def copy_only():
+        return [t.to(dev, non_blocking=True) for t in W.h_train + W.h_eval]
+    ms_h2d = timed(copy_only, e2e_steps, sync)
+    h2d_gbs = sum(t.numel() * t.element_size() for t in W.h_train + W.h_eval) / (ms_h2d * 1e-3) / 1e9
 
-    t = torch.tensor([ms_step, ms_e2e, ms_fwd, ms_bwd, ms_det, ms_match, ms_dscore], dtype=torch.float64, device=dev)
+    vals = [ms_step, ms_e2e, ms_train, ms_eval, ms_h2d] + [k["ms"] for k in kernels.values()]
+    t = torch.tensor(vals, dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_step, ms_e2e, ms_fwd, ms_bwd, ms_det, ms_match, ms_dscore = t.tolist()
+    vals = t.tolist()
+    ms_step, ms_e2e, ms_train, ms_eval, ms_h2d_max = vals[:5]
+    for k, v in zip(kernels.values(), vals[5:]):
+        k["ms"] = v
+    h2d_all = [None] * world
+    if world > 1:
+        dist.all_gather_object(h2d_all, round(h2d_gbs, 2))
+    else:
+        h2d_all = [round(h2d_gbs, 2)]
 
     if rank == 0:
-        T = int(gt[0].size(0))
-        h2d = (h_locs.numel() + h_scores.numel() + h_elocs.numel() + h_escores.numel()) * 4 + T * 24
-        d2h = 4 + N * NMS["top_k"] * (16 + 8 + 4) + N * 4
         peaks = {}
         try:
             peaks = json.load(open(os.path.join(REPO, "MEASURED_PEAKS.json")))
         except Exception:
             pass
         peak = float(peaks.get("hbm_gbs", 6650.0))
-        # algorithmic bytes per launch of the two streaming kernels (DESIGN.md "Kernels"):
-        #   train: logits once + priors once + GT, plus - when the backward follows - the zero-fill of
-        #          the logits' gradient, which this kernel writes on the way (no separate fill kernel);
-        #   eval:  logits once
-        prefill = st.grad_scores is not None or bool(st.desc.grad_scores_prefill)
-        alg_logits = N * P * N_CLASSES * 4 + P * 16 + T * 24
-        alg_match = alg_logits + (N * P * N_CLASSES * 4 if prefill else 0)
-        alg_dscore = N * P * N_CLASSES * 4
-        per_kernel = {
-            "match_lse_fast_kernel": {"ms": ms_match, "bytes": alg_match, "bytes_logits_only": alg_logits,
-                                      "writes_gradient_zero_fill": prefill},
-            "detect_score_fast_kernel": {"ms": ms_dscore, "bytes": alg_dscore},
-        }
-        for v in per_kernel.values():
-            v["achieved_gbs"] = v["bytes"] / (v["ms"] * 1e-3) / 1e9
-            v["frac"] = v["achieved_gbs"] / peak
-        dom = max(per_kernel, key=lambda k: per_kernel[k]["ms"])  # the dominant kernel of the step
-        alg_bytes, ms_dom = per_kernel[dom]["bytes"], per_kernel[dom]["ms"]
-        achieved = per_kernel[dom]["achieved_gbs"]
+        for v in kernels.values():
+            if v.get("bytes"):
+                v["achieved_gbs"] = v["bytes"] / (v["ms"] * 1e-3) / 1e9
+                v["frac"] = v["achieved_gbs"] / peak
+        with_bytes = {k: v for k, v in kernels.items() if v.get("bytes")}
+        dom = max(with_bytes, key=lambda k: with_bytes[k]["ms"])  # the dominant kernel of the step
         traffic = None
         try:
             tj = json.load(open(os.path.join(REPO, "profiles", "roofline_traffic.json")))
-            traffic = tj.get(dom + ("+zero_fill" if dom.startswith("match_lse") and prefill else ""), tj.get(dom))
+            traffic = tj.get("config%d" % cid, {}).get(dom)
         except Exception:
             pass
-        # CPU baseline beside it (bounded sample, all host cores)
-        cores = os.cpu_count() or 1
-        torch.set_num_threads(cores)
-        c_train = (train[0][:2], train[1][:2], train[2][:2], train[3][:2])
-        c_eval = (evalb[0][:1], evalb[1][:1])
-        cpu_reference_step(pri, c_train, c_eval, 2, 1)
-        a, b = cpu_reference_step(pri, c_train, c_eval, 2, 1)
-        cpu_value = 1.0 / (a + b)
+        cpu, _ = cpu_arm(cid, 1, 1)
+        step_bytes = algorithmic_bytes(cid, N, P, W.T)
         line = {
-            "metric": "images/sec for assign+loss+NMS", "value": N * world / (ms_step * 1e-3), "unit": "images/s",
+            "metric": METRIC, "value": N * world / (ms_step * 1e-3), "unit": "images/s",
             "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "images_per_gpu": N, "l2": "inputs (2 x 255 MB logits) exceed the 126 MB L2",
-                       "streams": "train and eval halves of the step on two CUDA streams" if args.overlap else (
-                           "one stream + the eval sampling pass on a side stream" if args.presample else "one stream"),
-                       "launch": "CUDA graph replay" if graph is not None else "eager Python launches",
-                       "ms_loss_fwd": ms_fwd, "ms_loss_bwd": ms_bwd, "ms_detect": ms_det,
-                       "images_per_s_loss_fwd": N * world / (ms_fwd * 1e-3),
-                       "images_per_s_loss_fwd_bwd": N * world / ((ms_fwd + ms_bwd) * 1e-3),
-                       "images_per_s_detect": N * world / (ms_det * 1e-3)},
-            "e2e": {"value": N * world / (ms_e2e * 1e-3), "unit": "images/s", "h2d_bytes_per_step": h2d,
-                    "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e},
-            # match_lse (+ gradient zero-fill), classify, mine, bwd_patch, detect sample, detect score,
-            # detect nms, + the two (normally empty) fallback launches
-            "gpu_launches": 9 * args.steps,
+            "config": config_entry(cid),
+            "details": {"streams": "train and eval halves of the step on two CUDA streams" if args.overlap else "one stream",
+                        "launch": "CUDA graph replay" if graph is not None else "eager Python launches",
+                        "sharding": "batch sharded by image, one all-reduce of the loss sums per criterion" if cf["shards"]
+                        else "independent replicas (batch-global mining does not shard)",
+                        "ms_train_half": ms_train, "ms_eval_half": ms_eval, "ms_loss_fwd": ms_fwd,
+                        "ms_loss_bwd_incl_zero_fill": ms_bwd, "ms_detect": ms_eval,
+                        "images_per_s_train_half": N * world / (ms_train * 1e-3),
+                        "images_per_s_detect": N * world / (ms_eval * 1e-3),
+                        "step_algorithmic_bytes": step_bytes, "step_gbs": step_bytes / (ms_step * 1e-3) / 1e9,
+                        "numa_cpus_bound": numa_cpus},
+            "e2e": {"value": N * world / (ms_e2e * 1e-3), "unit": "images/s", "h2d_bytes_per_step": W.h2d_bytes(),
+                    "d2h_bytes_per_step": W.d2h_bytes(), "ms_per_step": ms_e2e,
+                    "copy": "H2D on a copy stream (eval batch's copy overlaps the train half)",
+                    "h2d_gbs_per_rank_all_ranks_copying": h2d_all},
+            "gpu_launches": W.launches_per_step(world) * args.steps,
             "clocks": clocks,
-            "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak,
-                         "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+            "roofline": {"bound": "hbm", "kernel": dom, "achieved": kernels[dom]["achieved_gbs"], "peak": peak,
+                         "unit": "GB/s", "frac": kernels[dom]["achieved_gbs"] / peak, "traffic": traffic,
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured copy)" if peaks else "fallback 6650",
-                         "ms_per_launch": ms_dom, "algorithmic_bytes_per_launch": alg_bytes,
-                         "streaming_kernels": per_kernel},
-            "cpu_baseline": {"value": cpu_value, "unit": "images/s", "cores": cores, "kind": "port",
-                             "sample": "2 train images (loss fwd+bwd) + 1 eval image (detect), oracle port of the "
-                                       "reference on the host cores, second of two passes",
-                             "ms_per_image_loss_fwd_bwd": a * 1e3, "ms_per_image_detect": b * 1e3},
+                         "ms_per_launch": kernels[dom]["ms"], "algorithmic_bytes_per_launch": kernels[dom]["bytes"],
+                         "kernels": kernels},
+            "cpu_baseline": cpu,
         }
+        if cid in (1, 4):
+            line["roofline"]["note"] = ("the working set of this config fits the L2: its kernels are latency / issue "
+                                        "bound, the HBM fraction is reported for completeness")
         print(json.dumps(line), flush=True)
     if world > 1:
-        # the captured step holds NCCL kernel nodes: release the graph before the communicator goes away
-        step_resident = eager_step
-        graph = g = None
+        graph = g = None  # the captured step holds NCCL kernel nodes: release it before the communicator goes away
+        replay = eager_step
         torch.cuda.synchronize()
         dist.barrier()
         dist.destroy_process_group()
@@ -406,22 +647,21 @@ def run_ours(args, rank, world, local_rank):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=300)
+    ap.add_argument("--steps", type=int, default=None, help="timed steps (default 300; 10 for --impl reference)")
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", type=int, default=2, choices=sorted(CONFIGS),
+                    help="BASELINE.json config (1 SSD300, 2 SSD512 [default], 3 RetinaNet-640, 4 RefineDet512, 5 FCOS)")
     ap.add_argument("--no-graph", dest="graph", action="store_false",
                     help="launch the resident step eagerly instead of replaying a captured CUDA graph")
-    ap.add_argument("--no-presample", dest="presample", action="store_false",
-                    help="keep the eval path's sampling pass on the main stream")
     ap.add_argument("--no-overlap", dest="overlap", action="store_false",
-                    help="run the train half and the eval half of a step one after the other on one stream "
-                         "(default: on two CUDA streams inside the replayed graph - the two halves are independent, "
-                         "and the small-grid kernels of one (mining, NMS: one CTA per image) fill the SMs the other "
-                         "leaves idle: 0.253 ms vs 0.311 ms per step)")
+                    help="run the train half and the eval half of a step one after the other on one stream")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.steps is None:
+        args.steps = 10 if args.impl == "reference" else 300
     if args.impl == "reference":
         run_reference(args, rank, world)
     else:

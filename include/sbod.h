@@ -33,7 +33,7 @@ typedef void* sbod_stream_t; /* cudaStream_t */
 #define SBOD_API
 #endif
 
-#define SBOD_ABI_VERSION 1
+#define SBOD_ABI_VERSION 2
 
 #define SBOD_OK 0
 #define SBOD_ERR_INVALID (-1)     /* bad argument (null pointer, negative size, unknown enum) */
@@ -284,6 +284,10 @@ typedef struct sbod_detect_desc {
   int32_t top_k;
   float second_nms_thr;      /* < 0: off; detect_tools: 0.7 class-agnostic second NMS */
   int32_t pre_nms_topk;      /* <= 0: off; per-class candidate cap (BASELINE config 3) */
+  int32_t class_agnostic;    /* != 0: detect_objects (models/utils.py:87-178, detect_tools.py:10-97, intended
+                                semantics - the reference reaches exit()): every prior is one candidate scored
+                                with its best foreground probability, ONE class-agnostic NMS, label = arg-max
+                                class. PARITY UNPINNED. Excludes second_nms_thr >= 0 and pre_nms_topk > 0. */
   /* outputs; out_cap >= max(top_k, 1) rows per image */
   float* out_boxes;    /* [N,out_cap,4] */
   int64_t* out_labels; /* [N,out_cap] */
@@ -299,11 +303,12 @@ SBOD_API size_t sbod_detect_workspace_bytes(const sbod_detect_desc* d);
 /* leading bytes of the workspace that must be zero before the first call (sbod_workspace_init) */
 SBOD_API size_t sbod_detect_workspace_zero_bytes(const sbod_detect_desc* d);
 SBOD_API int sbod_detect(const sbod_detect_desc* d, sbod_stream_t stream);
-/* Stages of sbod_detect, for profiling and for callers that want to enqueue the cheap sampling pass
- * early (e.g. on a side stream, overlapped with unrelated work):
- *   0 = sampling pass + main score pass, 1 = NMS (+ exact fallback for flagged images),
- *   2 = sampling pass only (reads 1/26 of the logits, writes the per-image score-cutoff histogram),
- *   3 = main score pass only, 4 = main score pass + NMS (+ fallback), i.e. everything after stage 2.
+/* sbod_detect = three kernels: the bound pass (streams the logits once: per prior an upper bound of its best
+ * foreground probability), the refine pass (exact probabilities of the rows whose bound can matter, candidate
+ * keys) and the NMS kernel (lazy top-k NMS; it evaluates the remaining rows itself in the rare case that the
+ * first band of candidates runs out - exact, no host round trip, no extra launch).
+ * Stages, for profiling and for callers that want to enqueue the streaming pass early (e.g. on a side stream):
+ *   0 = bound pass + refine, 1 = NMS, 2 = bound pass only, 3 = refine only, 4 = refine + NMS.
  * sbod_detect == stage 2 followed by stage 4 in stream order. */
 SBOD_API int sbod_detect_stage(const sbod_detect_desc* d, int stage, sbod_stream_t stream);
 
@@ -370,9 +375,9 @@ SBOD_API int sbod_map(const float* det_boxes, const int64_t* det_labels, const f
              sbod_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
- * End-to-end helpers with HOST buffers (pinned or pageable): copy the inputs to the device,
- * run the device entry point above, copy the result back. Used by bench.py's e2e leg; the
- * device scratch is the caller's (dev_arena, arena_bytes from the *_arena_bytes query).
+ * End-to-end helper with HOST buffers (pinned or pageable): copy the inputs to the device, run
+ * sbod_loss_forward, copy the loss back - the call a C / cgo / JNI host would make.
+ * The device scratch is the caller's (dev_arena, arena_bytes from the *_arena_bytes query).
  * ---------------------------------------------------------------------------------------- */
 SBOD_API size_t sbod_loss_forward_host_arena_bytes(const sbod_loss_desc* d, int T);
 SBOD_API int sbod_loss_forward_host(const sbod_loss_desc* d_host /* input pointers are HOST pointers */,

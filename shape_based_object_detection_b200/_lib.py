@@ -61,7 +61,7 @@ class DetectDesc(C.Structure):
         ("N", C.c_int32), ("P", C.c_int32), ("C", C.c_int32),
         ("act_kind", C.c_int32), ("box_kind", C.c_int32), ("clamp_inplace", C.c_int32),
         ("min_score", C.c_float), ("max_overlap", C.c_float), ("top_k", C.c_int32),
-        ("second_nms_thr", C.c_float), ("pre_nms_topk", C.c_int32),
+        ("second_nms_thr", C.c_float), ("pre_nms_topk", C.c_int32), ("class_agnostic", C.c_int32),
         ("out_boxes", C.c_void_p), ("out_labels", C.c_void_p), ("out_scores", C.c_void_p),
         ("out_prior", C.c_void_p), ("out_counts", C.c_void_p), ("out_cap", C.c_int32),
         ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t),
@@ -161,7 +161,7 @@ def lib():
                         "shape_based_object_detection_b200/csrc/build.sh (no CPU fallback exists)")
                 handle = C.CDLL(LIB_PATH)
                 _declare(handle)
-                if handle.sbod_abi_version() != 1:
+                if handle.sbod_abi_version() != 2:
                     raise SbodError("libsbod.so ABI version mismatch")
                 _lib = handle
     return _lib

@@ -226,7 +226,7 @@ def assign(boxes, labels, anchors_xy, threshold=0.5, neg_margin=0.1, want_classe
 @L.on_device
 def make_detect_desc(predicted_locs, predicted_scores, min_score, max_overlap, top_k, priors_cxcy=None,
                      act="softmax", box_type="offset", clamp_inplace=False, prior_keep=None,
-                     second_nms_thr=-1.0, pre_nms_topk=0):
+                     second_nms_thr=-1.0, pre_nms_topk=0, class_agnostic=False):
     """Allocate the outputs / workspace of one sbod_detect call and fill its descriptor."""
     L.need_cuda(predicted_locs, predicted_scores)
     dev = predicted_scores.device
@@ -259,11 +259,12 @@ def make_detect_desc(predicted_locs, predicted_scores, min_score, max_overlap, t
     d.box_kind, d.clamp_inplace = box_kind, 1 if clamp_inplace else 0
     d.min_score, d.max_overlap, d.top_k = float(min_score), float(max_overlap), int(top_k)
     d.second_nms_thr, d.pre_nms_topk = float(second_nms_thr), int(pre_nms_topk)
+    d.class_agnostic = 1 if class_agnostic else 0
     d.out_boxes, d.out_labels, d.out_scores = out_boxes.data_ptr(), out_labels.data_ptr(), out_scores.data_ptr()
     d.out_prior, d.out_counts, d.out_cap = out_prior.data_ptr(), out_counts.data_ptr(), cap
     nbytes = L.lib().sbod_detect_workspace_bytes(C.byref(d))
     zbytes = L.lib().sbod_detect_workspace_zero_bytes(C.byref(d))
-    ws = L.Workspace.get(dev, "detect", nbytes, zero_bytes=zbytes, layout=(N, P, Cn, float(min_score)))
+    ws = L.Workspace.get(dev, "detect", nbytes, zero_bytes=zbytes, layout=(N, Cn))
     d.workspace, d.workspace_bytes = ws.data_ptr(), nbytes
     return {"desc": d, "outputs": (out_boxes, out_labels, out_scores, out_prior, out_counts),
             "alive": (locs, scores, pri, keep, ws)}
@@ -272,11 +273,12 @@ def make_detect_desc(predicted_locs, predicted_scores, min_score, max_overlap, t
 @L.on_device
 def detect_batched(predicted_locs, predicted_scores, min_score, max_overlap, top_k, priors_cxcy=None,
                    act="softmax", box_type="offset", clamp_inplace=False, prior_keep=None,
-                   second_nms_thr=-1.0, pre_nms_topk=0):
+                   second_nms_thr=-1.0, pre_nms_topk=0, class_agnostic=False):
     """Fused eval path. Returns padded outputs (boxes [N,K,4], labels [N,K], scores [N,K],
-    prior [N,K], counts [N]) — all on the device, no host synchronisation."""
+    prior [N,K], counts [N]) — all on the device, no host synchronisation.
+    class_agnostic: the detect_objects variant (one candidate per prior, one class-agnostic NMS)."""
     call = make_detect_desc(predicted_locs, predicted_scores, min_score, max_overlap, top_k, priors_cxcy, act,
-                            box_type, clamp_inplace, prior_keep, second_nms_thr, pre_nms_topk)
+                            box_type, clamp_inplace, prior_keep, second_nms_thr, pre_nms_topk, class_agnostic)
     L.check(L.lib().sbod_detect(C.byref(call["desc"]), L.stream_ptr()))
     return call["outputs"]
 
@@ -285,9 +287,9 @@ def detect_batched(predicted_locs, predicted_scores, min_score, max_overlap, top
 def detect_begin(predicted_locs, predicted_scores, min_score, max_overlap, top_k, priors_cxcy=None,
                  act="softmax", box_type="offset", clamp_inplace=False, prior_keep=None,
                  second_nms_thr=-1.0, pre_nms_topk=0, side_stream=None):
-    """Split-phase detect_batched: enqueue the sampling pass (the 1/26 of the tiles that fixes each
-    image's speculative score cutoff) on `side_stream` now, so that it overlaps whatever the caller runs
-    on the current stream before detect_end(). Same arguments / results as detect_batched."""
+    """Split-phase detect_batched: enqueue the bound pass (the kernel that streams the logits) on
+    `side_stream` now, so that it overlaps whatever the caller runs on the current stream before
+    detect_end(). Same arguments / results as detect_batched."""
     call = make_detect_desc(predicted_locs, predicted_scores, min_score, max_overlap, top_k, priors_cxcy, act,
                             box_type, clamp_inplace, prior_keep, second_nms_thr, pre_nms_topk)
     cur = torch.cuda.current_stream(predicted_scores.device)
@@ -301,7 +303,7 @@ def detect_begin(predicted_locs, predicted_scores, min_score, max_overlap, top_k
 
 
 def detect_end(call):
-    """Second half of detect_begin: main score pass + NMS on the current stream."""
+    """Second half of detect_begin: exact evaluation of the candidate rows + NMS on the current stream."""
     with torch.cuda.device(call["outputs"][0].device):
         if call.get("side") is not None:
             torch.cuda.current_stream().wait_stream(call["side"])
@@ -314,7 +316,8 @@ def unpad_detections(out_boxes, out_labels, out_scores, out_counts):
     One D2H read of the N counts (the reference syncs N*(C-1) times, models/utils.py:252)."""
     counts = out_counts.tolist()
     if any(c < 0 for c in counts):
-        raise L.SbodError("sbod_detect: candidate / kept-list capacity exceeded (code %s)" % min(counts))
+        raise L.SbodError("sbod_detect: kept-list capacity exceeded (code %s): the first NMS stage of detect_tools "
+                          "kept more than 65536 boxes in one image" % min(counts))
     boxes = [out_boxes[i, :c] for i, c in enumerate(counts)]
     labels = [out_labels[i, :c] for i, c in enumerate(counts)]
     scores = [out_scores[i, :c] for i, c in enumerate(counts)]

@@ -1,16 +1,15 @@
 // detect.cu — the eval path (sm_100a): activation + decode + clamp + score threshold +
 // per-class NMS + top-k, batched, no host round trips.
 //
-//   detect_score_fast_kernel<C>  2 <= C <= 128 (C = 81 / 21 compile-time): two threads per row, a
-//                        sampling pass fixes a per-image score cutoff, the main pass emits only the
-//                        candidates above it (exact: flagged images are redone without cutoff).
-//   detect_score_kernel  generic (C > 128); persistent; logits tiles streamed by bulk TMA (same ring as
-//                        the train kernel); one thread per prior row turns the row into probabilities in
-//                        place, and every (class, prior) above min_score is emitted as one 64-bit
-//                        key  [0x3F800000 - score_bits : 32][class : 12][prior : 20]  so that
+//   detect_bound_kernel  the streaming pass: logits HBM -> smem by bulk TMA exactly once, one thread per
+//                        prior row, maximum foreground logit -> upper bound of the row's best probability
+//                        (+ per-image histogram of the bounds). HBM-bound: two instructions per logit.
+//   detect_refine_kernel exact activation (as torch: max shift, accurate exp, division) of the rows whose
+//                        bound lies above the image's cutoff, a warp per row; every (class, prior) above
+//                        min_score and the cutoff is emitted as one 64-bit key
+//                        [0x3F800000 - score_bits : 32][class : 12][prior : 20]  so that
 //                        ascending key order == (score desc, class asc, prior asc) == the order in
 //                        which the reference's per-class NMS + stable top-k sort consumes them.
-//                        A per-image histogram of the key's top digit is built on the fly.
 //   detect_nms_kernel    one CTA per image. The reference runs NMS over every candidate of every
 //                        class and only then keeps the top_k best (models/utils.py:245-290). Greedy
 //                        NMS is prefix-stable, so the first top_k+1 survivors in global key order
@@ -28,7 +27,6 @@
 
 namespace sbod {
 
-constexpr int kDRows = 128;
 constexpr int kChunk = 1024;       // candidates per NMS round (== threads of detect_nms_kernel)
 constexpr int kNmsThreads = 1024;
 constexpr int kMaxBins = 2048;
@@ -47,6 +45,7 @@ struct DetParams {
   int top_k;
   float second_thr;
   int pre_nms_topk;
+  int agnostic;                 // detect_objects: one candidate per prior (best foreground class), class-agnostic NMS
   float* out_boxes;
   int64_t* out_labels;
   float* out_scores;
@@ -55,23 +54,24 @@ struct DetParams {
   int out_cap;
   // workspace
   unsigned int* cand_count;     // [N]
-  unsigned int* hist;           // [N, n_bins]
+  unsigned int* hist;           // [N, kMaxBins] level-0 digit histogram of the emitted candidate keys
   unsigned long long* cand;     // [N, cand_cap]
   unsigned int* class_seen;     // [N, C]  (pre-NMS per-class rank counters)
   long long cand_cap;
   int n_bins, shift0;           // level-0 digit = key >> shift0
   int kcap;                     // kept-list capacity in smem
-  int debug_skip;               // SBOD_DEBUG_SKIP (profiling): bit0 no emission, bit1 no exact refine, bit2 no cutoff
-  // speculative per-image score cutoff (exact: images whose candidates run out are redone in full)
-  int mode;                     // 0 = main pass, 1 = sampling pass, 2 = fallback pass (flagged images only)
-  unsigned int* shist;          // [N, n_bins] histogram of the sampled tiles
-  unsigned int* cutoff_k32;     // [N] emit only keys with k32 < cutoff (0xffffffff = no cutoff)
-  float* cutoff_floor;          // [N] score just below the cutoff (mask floor)
-  unsigned int* flags;          // [N] 1 = the cutoff was too strict, redo this image in full
+  // row bounds (exact two-step candidate generation, see detect_bound_kernel)
+  float* pbound;                // [N, P] upper bound of the best foreground probability of each prior
+  unsigned int* rhist;          // [N, kMaxBins] histogram of the row bounds (same bins as the candidate keys)
+  int rows_target;              // rows evaluated per image in the first band
+  int32_t* agn_label;           // [N, P] arg-max class of each prior (class-agnostic mode)
   unsigned int* nms_mask;       // [N, kChunk, kChunk/32] suppression bits of large class segments
-  int sample_stride, sample_target;
-  int speculate;                // the sampling pass ran: cutoffs come from shist
-  // tiling
+  // second-stage kept list spill (detect_tools: the first stage may keep more boxes than fit in smem)
+  unsigned long long* spill_key;  // [N, spill_cap]
+  float4* spill_box;              // [N, spill_cap]
+  uint8_t* spill_st2;             // [N, spill_cap]
+  int spill_cap;
+  // tiling of the bound pass
   int rows_per_tile, tiles_per_image, n_tiles, n_stages;
   uint32_t stage_floats;
 };
@@ -97,166 +97,144 @@ SBOD_DEVINL float4 decode_box(const DetParams& q, int n, int p) {
   return b;
 }
 
-struct DTile {
-  int n, p0, rows;
-};
-SBOD_DEVINL DTile dtile(const DetParams& q, int tile) {
-  DTile t;
-  t.n = tile / q.tiles_per_image;
-  t.p0 = (tile - t.n * q.tiles_per_image) * q.rows_per_tile;
-  t.rows = min(q.rows_per_tile, q.P - t.p0);
-  return t;
+// score -> upper 32 bits of the candidate key (ascending = better score first)
+SBOD_DEVINL uint32_t score_k32(float pr) {
+  const uint32_t bits = __float_as_uint(pr);
+  return bits > kOneBits ? 0u : kOneBits - bits;
+}
+SBOD_DEVINL int k32_bin(const DetParams& q, uint32_t k32) {
+  const int bin = int(k32 >> (q.shift0 - 32));
+  return bin < q.n_bins ? bin : q.n_bins - 1;
 }
 
-SBOD_DEVINL void issue_dtile(const DetParams& q, int tile, float* stage, uint64_t* bar) {
-  const DTile t = dtile(q, tile);
-  const size_t first = (size_t(t.n) * q.P + t.p0) * size_t(q.C);
-  const size_t total = size_t(q.N) * q.P * size_t(q.C);
-  const TileSpan s = make_tile_span(q.scores, first, size_t(t.rows) * q.C, total);
-  for (uint32_t i = 0; i < s.tail_floats; ++i)
-    stage[s.bulk_bytes / 4 + i] = q.scores[(s.src16 - q.scores) + s.bulk_bytes / 4 + i];
-  if (s.bulk_bytes) {
-    mbar_arrive_expect_tx(bar, s.bulk_bytes);
-    tma_load_1d(stage, s.src16, s.bulk_bytes, bar);
-  } else {
-    mbar_arrive(bar);
-  }
-}
+// ------------------------------------------------------------------------------------------
+// detect_bound_kernel — the streaming pass of the eval path. The logits go HBM -> shared memory exactly
+// once (bulk TMA through an mbarrier ring, same tiles as the train kernel); one thread per prior row
+// takes the maximum foreground logit and turns it into an UPPER BOUND of the row's best foreground
+// probability:  softmax: p_k = e^{x_k} / sum_j e^{x_j} <= e^{x_k} / (e^{x_0} + e^{x_k}) = sigmoid(x_k - x_0);
+// sigmoid: p_k = sigmoid(x_k); none: p_k = x_k. Two instructions per logit (load + max) instead of the
+// ~8 a full softmax costs, so the pass is bound by HBM, not by instruction issue. It writes the bound
+// (4 bytes per prior) and a per-image histogram of the bounds in the bins of the candidate keys.
+// The exact probabilities are then computed only for the rows whose bound can matter
+// (detect_refine_kernel), which is exact: a row's candidates all lie below its bound.
+// ------------------------------------------------------------------------------------------
+constexpr int kBThreads = 128;
+constexpr float kBoundSlack = 1.00002f;  // covers the rounding of the bound and of the exact probabilities
 
-__global__ void __launch_bounds__(kDRows) detect_score_kernel(const DetParams q) {
+__global__ void __launch_bounds__(kBThreads) detect_bound_kernel(const DetParams q) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   float* stages = reinterpret_cast<float*>(smem_raw);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + size_t(q.n_stages) * q.stage_floats * 4);
-  __shared__ unsigned int s_wtot[kDRows / 32];
-  __shared__ unsigned int s_base;
+  __shared__ unsigned int s_hist[kMaxBins];
 
-  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-  const int n_my = (q.n_tiles - int(blockIdx.x) + int(gridDim.x) - 1) / int(gridDim.x);
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int C = q.C;
+  int t0, t1;
+  tile_range(q.n_tiles, blockIdx.x, gridDim.x, t0, t1);
+  const int n_my = t1 - t0;
+  if (n_my <= 0) return;
   if (tid == 0) {
     for (int s = 0; s < q.n_stages; ++s) mbar_init(&bars[s], 1);
     fence_mbar_init();
   }
+  for (int b = tid; b < q.n_bins; b += kBThreads) s_hist[b] = 0u;
   __syncthreads();
   if (tid == 0) {
     for (int s = 0; s < q.n_stages && s < n_my; ++s)
-      issue_dtile(q, blockIdx.x + s * gridDim.x, stages + size_t(s) * q.stage_floats, &bars[s]);
+      stream_issue(q.scores, q.N, q.P, C, stream_tile(t0 + s, q.tiles_per_image, q.rows_per_tile, q.P),
+                   stages + size_t(s) * q.stage_floats, &bars[s]);
   }
+  // rotation that makes the per-thread row walk bank-conflict free for even C
   int gcd = 1;
-  while (gcd < 32 && (q.C % (gcd * 2)) == 0) gcd *= 2;
+  while (gcd < 32 && (C % (gcd * 2)) == 0) gcd *= 2;
   const int rot = (lane * gcd) >> 5;
-  const int C = q.C;
-  const float INF = __int_as_float(0x7f800000);
+  const float NEG = -__int_as_float(0x7f800000);
 
+  auto flush_hist = [&](int n) {
+    __syncthreads();
+    unsigned int* gh = q.rhist + size_t(n) * kMaxBins;
+    for (int b = tid; b < q.n_bins; b += kBThreads) {
+      const unsigned int v = s_hist[b];
+      if (v) {
+        atomicAdd(&gh[b], v);
+        s_hist[b] = 0u;
+      }
+    }
+    __syncthreads();
+  };
+
+  int cur_n = t0 / q.tiles_per_image;  // tile coordinates advance incrementally
+  int cur_t = t0 - cur_n * q.tiles_per_image;
+  int hist_n = -1;
+  int ring_s = 0;
+  uint32_t ring_parity = 0;
   for (int it = 0; it < n_my; ++it) {
-    const int tile = blockIdx.x + it * gridDim.x;
-    const DTile tc = dtile(q, tile);
-    const int n = tc.n;
-    const bool valid = tid < tc.rows;
-    const int p = tc.p0 + tid;
-    const size_t np = size_t(n) * q.P + (valid ? p : tc.p0);
-    const bool keep_row = valid && (q.prior_keep ? q.prior_keep[np] != 0 : true);
-
-    if (valid && q.clamp_inplace) {  // models/utils.py:224, detect_tools.py:264: clamp_ on the caller's tensor
-      float4* lp = reinterpret_cast<float4*>(q.locs) + np;
-      float4 b = *lp;
-      b.x = fminf(fmaxf(b.x, 0.f), 1.f); b.y = fminf(fmaxf(b.y, 0.f), 1.f);
-      b.z = fminf(fmaxf(b.z, 0.f), 1.f); b.w = fminf(fmaxf(b.w, 0.f), 1.f);
-      *lp = b;
+    const int n = cur_n;
+    const int p0 = cur_t * q.rows_per_tile;
+    const int rows = min(q.rows_per_tile, q.P - p0);
+    if (++cur_t == q.tiles_per_image) {
+      cur_t = 0;
+      ++cur_n;
     }
-
-    const int s = it % q.n_stages;
-    float* stage = stages + size_t(s) * q.stage_floats;
-    mbar_wait(&bars[s], (it / q.n_stages) & 1);
-    const size_t first = (size_t(n) * q.P + tc.p0) * size_t(C);
-    float* row = stage + (first & 3) + size_t(tid) * C;
-    unsigned int cnt = 0;
-    if (keep_row) {
-      if (q.act_kind == SBOD_ACT_SOFTMAX) {
-        float m0 = -INF, m1 = -INF, m2 = -INF, m3 = -INF;
-        int k = rot;
-        for (; k + 3 < C; k += 4) {
-          m0 = fmaxf(m0, row[k]); m1 = fmaxf(m1, row[k + 1]);
-          m2 = fmaxf(m2, row[k + 2]); m3 = fmaxf(m3, row[k + 3]);
-        }
-        for (; k < C; ++k) m0 = fmaxf(m0, row[k]);
-        for (k = 0; k < rot; ++k) m1 = fmaxf(m1, row[k]);
-        const float mx = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
-        float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-        k = rot;
-        for (; k + 3 < C; k += 4) {
-          const float e0 = __expf(row[k] - mx), e1 = __expf(row[k + 1] - mx);
-          const float e2 = __expf(row[k + 2] - mx), e3 = __expf(row[k + 3] - mx);
-          row[k] = e0; row[k + 1] = e1; row[k + 2] = e2; row[k + 3] = e3;
-          s0 += e0; s1 += e1; s2 += e2; s3 += e3;
-        }
-        for (; k < C; ++k) { const float e = __expf(row[k] - mx); row[k] = e; s0 += e; }
-        for (k = 0; k < rot; ++k) { const float e = __expf(row[k] - mx); row[k] = e; s1 += e; }
-        const float inv = __frcp_rn((s0 + s1) + (s2 + s3));
-        for (int kk = 0; kk < C; ++kk) {
-          k = kk + rot; if (k >= C) k -= C;
-          const float pr = row[k] * inv;
-          row[k] = pr;
-          cnt += (k > 0 && pr > q.min_score) ? 1u : 0u;
-        }
-      } else {
-        for (int kk = 0; kk < C; ++kk) {
-          int k = kk + rot; if (k >= C) k -= C;
-          const float pr = q.act_kind == SBOD_ACT_NONE ? row[k] : __frcp_rn(1.f + __expf(-row[k]));
-          row[k] = pr;
-          cnt += (k > 0 && pr > q.min_score) ? 1u : 0u;
-        }
+    if (n != hist_n) {
+      if (hist_n >= 0) flush_hist(hist_n);
+      hist_n = n;
+    }
+    float* stage = stages + size_t(ring_s) * q.stage_floats;
+    mbar_wait(&bars[ring_s], ring_parity);
+    const uint32_t head = ((uint32_t(n) * uint32_t(q.P) + uint32_t(p0)) * uint32_t(C)) & 3u;
+    for (int r = tid; r < rows; r += kBThreads) {
+      const int p = p0 + r;
+      const size_t np = size_t(n) * q.P + p;
+      if (q.clamp_inplace) {  // clamp_ on the caller's tensor (models/utils.py:224, detect_tools.py:264)
+        float4* lp = reinterpret_cast<float4*>(q.locs) + np;
+        float4 b = *lp;
+        b.x = fminf(fmaxf(b.x, 0.f), 1.f); b.y = fminf(fmaxf(b.y, 0.f), 1.f);
+        b.z = fminf(fmaxf(b.z, 0.f), 1.f); b.w = fminf(fmaxf(b.w, 0.f), 1.f);
+        *lp = b;
       }
-    }
-    // block-exclusive scan of the per-row candidate counts, one atomic per tile
-    unsigned int inc = cnt;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const unsigned int t = __shfl_up_sync(0xffffffffu, inc, o);
-      if (lane >= o) inc += t;
-    }
-    if (lane == 31) s_wtot[wid] = inc;
-    __syncthreads();
-    unsigned int off = inc - cnt, tot = 0;
-    for (int w = 0; w < kDRows / 32; ++w) {
-      if (w < wid) off += s_wtot[w];
-      tot += s_wtot[w];
-    }
-    if (tid == 0) s_base = tot ? atomicAdd(&q.cand_count[n], tot) : 0u;
-    __syncthreads();
-    if (cnt) {
-      long long slot = (long long)s_base + off;
-      unsigned long long* dst = q.cand + size_t(n) * q.cand_cap;
-      unsigned int* hist = q.hist + size_t(n) * q.n_bins;
-      for (int k = 1; k < C; ++k) {  // ascending class order inside the row
-        const float pr = row[k];
-        if (pr > q.min_score) {
-          uint32_t bits = __float_as_uint(pr);
-          const uint32_t k32 = bits > kOneBits ? 0u : kOneBits - bits;
-          const unsigned long long key = (static_cast<unsigned long long>(k32) << 32) |
-                                         (static_cast<unsigned long long>(k) << kPriorBits) |
-                                         static_cast<unsigned long long>(p);
-          if (slot < q.cand_cap) dst[slot] = key;
-          ++slot;
-          int bin = int(key >> q.shift0);
-          if (bin >= q.n_bins) bin = q.n_bins - 1;
-          atomicAdd(&hist[bin], 1u);
-        }
+      const float* row = stage + head + size_t(r) * C;
+      // maximum over the foreground logits, four independent chains, rotated start
+      float m0 = NEG, m1 = NEG, m2 = NEG, m3 = NEG;
+      int k = rot > 1 ? rot : 1;
+      for (; k + 3 < C; k += 4) {
+        m0 = fmaxf(m0, row[k]);
+        m1 = fmaxf(m1, row[k + 1]);
+        m2 = fmaxf(m2, row[k + 2]);
+        m3 = fmaxf(m3, row[k + 3]);
       }
+      for (; k < C; ++k) m0 = fmaxf(m0, row[k]);
+      for (k = 1; k < rot; ++k) m1 = fmaxf(m1, row[k]);
+      const float mx = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
+      float pb;
+      if (q.act_kind == SBOD_ACT_SOFTMAX) pb = __frcp_rn(1.f + __expf(row[0] - mx));
+      else if (q.act_kind == SBOD_ACT_SIGMOID) pb = __frcp_rn(1.f + __expf(-mx));
+      else pb = mx;
+      pb = pb * kBoundSlack;
+      if (!(pb == pb)) pb = 2.f;  // a NaN in the row: never skip it
+      if (q.prior_keep && q.prior_keep[np] == 0) pb = -1.f;  // filtered prior: never a candidate
+      q.pbound[np] = pb;
+      if (pb > q.min_score) atomicAdd(&s_hist[k32_bin(q, score_k32(pb))], 1u);
     }
-    fence_proxy_async();
-    __syncthreads();
+    __syncthreads();  // every thread is done with the stage
     if (tid == 0 && it + q.n_stages < n_my)
-      issue_dtile(q, blockIdx.x + (it + q.n_stages) * gridDim.x, stage, &bars[s]);
+      stream_issue(q.scores, q.N, q.P, C, stream_tile(t0 + it + q.n_stages, q.tiles_per_image, q.rows_per_tile, q.P),
+                   stage, &bars[ring_s]);
+    if (++ring_s == q.n_stages) {
+      ring_s = 0;
+      ring_parity ^= 1u;
+    }
   }
+  if (hist_n >= 0) flush_hist(hist_n);
 }
 
-// Per-image emission cutoff from the histogram of the sampled tiles: the score bin above which about
-// sample_target candidates are expected. Block-wide (any block size that is a multiple of 32);
-// every thread returns the same (k32 cutoff, score floor). scratch: >= 34 unsigned ints.
-__device__ void compute_cutoff(const DetParams& q, int n, unsigned int* scratch, unsigned int& k32_out,
-                               float& floor_out) {
+// Per-image cutoff from the histogram of the row bounds: the smallest bin count `cb` such that at least
+// rows_target rows have their bound in bins [0, cb) — only those rows are evaluated in the first band, and
+// only candidates with a key below the cutoff are emitted. Block-wide (any multiple of 32 threads); every
+// thread returns the same value (0xffffffff = no cutoff: everything above min_score). scratch: >= 34 uints.
+__device__ unsigned int compute_cutoff(const DetParams& q, int n, unsigned int* scratch) {
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, nt = blockDim.x;
-  const unsigned int* sh = q.shist + size_t(n) * q.n_bins;
+  const unsigned int* sh = q.rhist + size_t(n) * kMaxBins;
   const int per = (q.n_bins + nt - 1) / nt;  // contiguous bins per thread, best scores first
   unsigned int mine = 0;
   for (int j = 0; j < per; ++j) {
@@ -275,7 +253,7 @@ __device__ void compute_cutoff(const DetParams& q, int n, unsigned int* scratch,
   __syncthreads();
   unsigned int before = inc - mine;
   for (int w = 0; w < wid; ++w) before += scratch[w];
-  const unsigned int need = unsigned((q.sample_target + q.sample_stride - 1) / q.sample_stride);
+  const unsigned int need = unsigned(q.rows_target);
   if (before < need && before + mine >= need) {
     unsigned int acc = before;
     for (int j = 0; j < per; ++j) {
@@ -283,255 +261,175 @@ __device__ void compute_cutoff(const DetParams& q, int n, unsigned int* scratch,
       if (b >= q.n_bins) break;
       acc += sh[b];
       if (acc >= need) {
-        scratch[33] = unsigned(b + 1);  // emit bins [0, b]
+        scratch[33] = unsigned(b + 1);  // bins [0, b]
         break;
       }
     }
   }
   __syncthreads();
   const int cb = int(scratch[33]);
-  if (cb >= q.n_bins) {
-    k32_out = 0xffffffffu;
-    floor_out = q.min_score;
-  } else {
-    k32_out = unsigned(cb) << (q.shift0 - 32);
-    floor_out = fmaxf(q.min_score, __uint_as_float(kOneBits - min(k32_out, kOneBits)));
-  }
   __syncthreads();
+  if (cb >= q.n_bins) return 0xffffffffu;
+  return unsigned(cb) << (q.shift0 - 32);
 }
 
 // ------------------------------------------------------------------------------------------
-// detect_score_fast_kernel — odd C <= 128, softmax or sigmoid. Two threads per row (row_stream.cuh),
-// contiguous tile ranges per CTA. Pass 2 of the softmax also builds, per thread, a bit mask of the
-// classes whose un-normalised exp already exceeds min_score (a superset of the candidates, since the
-// row sum is >= 1); only those few are re-evaluated exactly and emitted. The per-image histogram
-// of the key's top digit is accumulated in shared memory and flushed once per image.
+// Exact evaluation of one prior row by one warp (lane k handles classes k, k + 32, ...): activation as
+// torch computes it (max shift, accurate exp, true division), then every (class, prior) whose probability
+// exceeds min_score and whose key lies in [k_lo, k_hi) is emitted through `reserve` (returns the first of
+// `count` consecutive slots, called by lane 0) / `put` (slot, key). Class-agnostic mode emits the row's
+// best foreground class once, with class field 1, and records the arg-max class.
 // ------------------------------------------------------------------------------------------
-template <int kC>  // kC > 0: compile-time class count (unrolled softmax passes)
-__global__ void __launch_bounds__(kStreamThreads, 2) detect_score_fast_kernel(const DetParams q) {
-  extern __shared__ __align__(128) unsigned char smem_raw[];
-  float* stages = reinterpret_cast<float*>(smem_raw);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + size_t(q.n_stages) * q.stage_floats * 4);
-  __shared__ unsigned int s_hist[kMaxBins + 40];  // + scratch of compute_cutoff
-  constexpr int kKeyBuf = 1024, kKeyFlush = 512;  // shared key buffer (see the slot reservation below)
-  __shared__ unsigned long long s_keys[kKeyBuf];
-  __shared__ unsigned int s_ncand, s_gbase;
-
-  const int tid = threadIdx.x, lane = tid & 31;
-  const int C = kC ? kC : q.C;
-  // tiles of this CTA: all of a contiguous range (modes 0, 2) or every sample_stride-th tile (mode 1)
-  const int stride = q.mode == 1 ? q.sample_stride : 1;
-  const int n_units = q.mode == 1 ? (q.n_tiles + stride - 1 - stride / 2) / stride : q.n_tiles;
-  int t0, t1;
-  tile_range(n_units, blockIdx.x, gridDim.x, t0, t1);
-  const int n_my = t1 - t0;
-  auto tile_of = [&](int idx) { return (t0 + idx) * stride + (q.mode == 1 ? stride / 2 : 0); };
-  auto image_active = [&](int n) { return q.mode != 2 || q.flags[n] != 0u; };
-  if (n_my <= 0) return;
-  if (q.mode == 2) {  // nothing flagged in my range: leave at once
-    bool any = false;
-    for (int n = tile_of(0) / q.tiles_per_image; n <= tile_of(n_my - 1) / q.tiles_per_image; ++n)
-      any = any || q.flags[n] != 0u;
-    if (!any) return;
+template <typename Reserve, typename Put>
+SBOD_DEVINL void eval_row(const DetParams& q, int n, int p, int lane, uint32_t k_lo, uint32_t k_hi,
+                          Reserve&& reserve, Put&& put) {
+  const int C = q.C;
+  const float* x = q.scores + (size_t(n) * q.P + p) * size_t(C);
+  const float NEG = -__int_as_float(0x7f800000);
+  float mx = 0.f, sum = 1.f;
+  if (q.act_kind == SBOD_ACT_SOFTMAX) {
+    float m = NEG;
+    for (int k = lane; k < C; k += 32) m = fmaxf(m, x[k]);
+    mx = warp_max(m);
+    float s = 0.f;
+    for (int k = lane; k < C; k += 32) s += expf(x[k] - mx);
+    sum = warp_sum(s);
   }
-  auto issue = [&](int idx, float* stage, uint64_t* bar) {
-    const StreamTile t = stream_tile(tile_of(idx), q.tiles_per_image, kTileRows, q.P);
-    if (image_active(t.n)) stream_issue(q.scores, q.N, q.P, C, t, stage, bar);
-    else mbar_arrive(bar);  // keep the ring's phase bookkeeping, move no data
+  auto prob = [&](int k) -> float {
+    const float v = x[k];
+    if (q.act_kind == SBOD_ACT_SOFTMAX) return __fdiv_rn(expf(v - mx), sum);
+    if (q.act_kind == SBOD_ACT_SIGMOID) return __fdiv_rn(1.f, 1.f + expf(-v));
+    return v;
   };
-  if (tid == 0) {
-    for (int s = 0; s < q.n_stages; ++s) mbar_init(&bars[s], 1);
-    fence_mbar_init();
+  if (q.agnostic) {
+    // best foreground class of the row, first index among ties (torch.max, models/utils.py:135)
+    unsigned long long best = 0ull;  // (probability bits : ~class): max = best probability, then lowest class
+    for (int k = lane; k < C; k += 32) {
+      if (k == 0) continue;
+      const float pr = prob(k);
+      if (pr > q.min_score) {
+        const unsigned long long key = (static_cast<unsigned long long>(__float_as_uint(pr)) << 32) | (0xffffffffu - unsigned(k));
+        if (key > best) best = key;
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const unsigned long long other = __shfl_xor_sync(0xffffffffu, best, o);
+      if (other > best) best = other;
+    }
+    if (best != 0ull) {
+      const float pr = __uint_as_float(uint32_t(best >> 32));
+      const int cls = int(0xffffffffu - uint32_t(best & 0xffffffffull));
+      const uint32_t k32 = score_k32(pr);
+      if (k32 >= k_lo && k32 < k_hi) {
+        unsigned int slot = 0;
+        if (lane == 0) {
+          slot = reserve(1u);
+          put(slot, (static_cast<unsigned long long>(k32) << 32) | (1ull << kPriorBits) | static_cast<unsigned long long>(p));
+          q.agn_label[size_t(n) * q.P + p] = cls;
+        }
+      }
+    }
+    return;
   }
-  for (int b = tid; b < q.n_bins; b += kStreamThreads) s_hist[b] = 0u;
-  if (tid == 0) s_ncand = 0u;
+  for (int kb = 0; kb < C; kb += 32) {
+    const int k = kb + lane;
+    float pr = 0.f;
+    bool is = false;
+    uint32_t k32 = 0;
+    if (k < C && k >= 1) {
+      pr = prob(k);
+      k32 = score_k32(pr);
+      is = pr > q.min_score && k32 >= k_lo && k32 < k_hi;
+    }
+    const unsigned bal = __ballot_sync(0xffffffffu, is);
+    if (bal) {
+      unsigned int base = 0;
+      if (lane == 0) base = reserve(unsigned(__popc(bal)));
+      base = __shfl_sync(0xffffffffu, base, 0);
+      if (is)
+        put(base + __popc(bal & ((1u << lane) - 1u)),
+            (static_cast<unsigned long long>(k32) << 32) | (static_cast<unsigned long long>(k) << kPriorBits) |
+                static_cast<unsigned long long>(p));
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// detect_refine_kernel: grid (ceil(P / kRefRows), N). Rows whose bound lies above the image's cutoff are
+// compacted and evaluated exactly, a warp per row; their candidates above the cutoff go to the image's
+// candidate list as sortable 64-bit keys  [0x3F800000 - score_bits : 32][class : 12][prior : 20]
+// (ascending key = score descending, class ascending, prior ascending = the order in which the reference's
+// per-class NMS + stable top-k sort consumes them) through a CTA-wide shared buffer: one shared-memory
+// atomic per warp and row, one global atomic per CTA. The histogram of the keys' leading digit is
+// accumulated in shared memory and flushed once.
+// ------------------------------------------------------------------------------------------
+constexpr int kRefThreads = 256;
+constexpr int kRefRows = 2048;
+constexpr int kRefKeyBuf = 3072;
+
+__global__ void __launch_bounds__(kRefThreads) detect_refine_kernel(const DetParams q) {
+  __shared__ unsigned int s_hist[kMaxBins];
+  __shared__ unsigned int s_scratch[40];
+  __shared__ unsigned long long s_keys[kRefKeyBuf];
+  __shared__ int s_rows[kRefRows];
+  __shared__ unsigned int s_nrows, s_ncand, s_gbase, s_hole;
+  const int n = blockIdx.y, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int p_lo = blockIdx.x * kRefRows, p_hi = min(q.P, p_lo + kRefRows);
+  for (int b = tid; b < q.n_bins; b += kRefThreads) s_hist[b] = 0u;
+  if (tid == 0) {
+    s_nrows = 0u;
+    s_ncand = 0u;
+    s_hole = 0xffffffffu;
+  }
+  const unsigned int cut = compute_cutoff(q, n, s_scratch);  // (contains the barriers that publish the zeroing)
+  // rows of this CTA whose bound is above the cutoff, in prior order
+  for (int pb = p_lo; pb < p_hi; pb += kRefThreads) {
+    const int p = pb + tid;
+    bool take = false;
+    if (p < p_hi) {
+      const float b = q.pbound[size_t(n) * q.P + p];
+      take = b > q.min_score && score_k32(b) < cut;
+    }
+    const unsigned bal = __ballot_sync(0xffffffffu, take);
+    unsigned int base = 0;
+    if (lane == 0 && bal) base = atomicAdd(&s_nrows, unsigned(__popc(bal)));
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (take) s_rows[base + __popc(bal & ((1u << lane) - 1u))] = p;
+  }
   __syncthreads();
-  if (tid == 0) {
-    for (int s = 0; s < q.n_stages && s < n_my; ++s) issue(s, stages + size_t(s) * q.stage_floats, &bars[s]);
-  }
-  int row, h;
-  stream_map(tid, row, h);
-  const int nh = (C + 1 - h) >> 1;
-  int hist_n = -1;
-  unsigned int cut_k32 = 0xffffffffu;
-  float cut_floor = q.min_score;
-
-  auto flush_hist = [&](int n) {
-    __syncthreads();
-    unsigned int* gh = (q.mode == 1 ? q.shist : q.hist) + size_t(n) * q.n_bins;
-    for (int b = tid; b < q.n_bins; b += kStreamThreads) {
-      const unsigned int v = s_hist[b];
-      if (v) {
-        atomicAdd(&gh[b], v);
-        s_hist[b] = 0u;
-      }
-    }
-    __syncthreads();
+  const int n_rows = int(s_nrows);
+  unsigned long long* g_list = q.cand + size_t(n) * q.cand_cap;
+  auto reserve = [&](unsigned int count) -> unsigned int {
+    const unsigned int at = atomicAdd(&s_ncand, count);
+    if (at + count <= unsigned(kRefKeyBuf)) return at;
+    // The shared buffer is full: this block of keys goes straight to the global list. The one reservation
+    // that straddles the capacity leaves a hole behind it: the buffered keys end where it starts.
+    if (at < unsigned(kRefKeyBuf)) s_hole = at;
+    return unsigned(kRefKeyBuf) + atomicAdd(&q.cand_count[n], count);
   };
-
-  // tile coordinates advance incrementally (no integer division in the loop)
-  int cur_n = tile_of(0) / q.tiles_per_image;
-  int cur_t = tile_of(0) - cur_n * q.tiles_per_image;
-  int ring_s = 0;
-  uint32_t ring_parity = 0;
-  for (int it = 0; it < n_my; ++it) {
-    StreamTile tc;
-    tc.n = cur_n;
-    tc.p0 = cur_t * kTileRows;
-    tc.rows = min(kTileRows, q.P - tc.p0);
-    cur_t += stride;
-    while (cur_t >= q.tiles_per_image) {
-      cur_t -= q.tiles_per_image;
-      ++cur_n;
-    }
-    const int n = tc.n;
-    if (n != hist_n) {
-      if (hist_n >= 0) flush_hist(hist_n);
-      hist_n = n;
-      if (q.mode == 0 && q.speculate) compute_cutoff(q, n, s_hist + kMaxBins, cut_k32, cut_floor);
-    }
-    const bool act = image_active(n);
-    const bool valid = row < tc.rows && act;
-    const int r = min(row, tc.rows - 1);
-    const int p = tc.p0 + r;
-    const size_t np = size_t(n) * q.P + p;
-    if (valid && h == 0 && q.clamp_inplace && q.mode == 0) {  // clamp_ on the caller's tensor (models/utils.py:224)
-      float4* lp = reinterpret_cast<float4*>(q.locs) + np;
-      float4 b = *lp;
-      b.x = fminf(fmaxf(b.x, 0.f), 1.f); b.y = fminf(fmaxf(b.y, 0.f), 1.f);
-      b.z = fminf(fmaxf(b.z, 0.f), 1.f); b.w = fminf(fmaxf(b.w, 0.f), 1.f);
-      *lp = b;
-    }
-    const bool keep_row = valid && (q.prior_keep ? q.prior_keep[np] != 0 : true);
-
-    const int s = ring_s;  // stage / phase advance incrementally (no integer division per tile)
-    float* stage = stages + size_t(s) * q.stage_floats;
-    mbar_wait(&bars[s], ring_parity);
-    if (++ring_s == q.n_stages) {
-      ring_s = 0;
-      ring_parity ^= 1u;
-    }
-    const uint32_t head = ((uint32_t(n) * uint32_t(q.P) + uint32_t(tc.p0)) * uint32_t(C)) & 3u;
-    const float* rp = stage + head + r * C + h;
-
-    uint32_t m0 = 0u, m1 = 0u;
-    float nmx2 = 0.f, inv = 1.f;
-    if (q.act_kind == SBOD_ACT_SOFTMAX) {
-      const float mx = kC ? pair_row_max_fixed<kC>(rp - h, h) : half_row_max(rp, nh);
-      nmx2 = -mx * kLog2e;
-      const float sum = kC ? pair_row_sumexp_mask_fixed<kC>(rp - h, h, nmx2, cut_floor, m0, m1)
-                           : half_row_sumexp_mask(rp, nh, nmx2, cut_floor, m0, m1);
-      inv = __frcp_rn(sum);
-    } else {
-      // sigmoid(x) > t  <=>  x > logit(t); keep a small margin, the exact test follows
-      const float t = fminf(fmaxf(cut_floor, 1e-30f), 1.f - 1e-7f);
-      const float lim = q.act_kind == SBOD_ACT_NONE ? cut_floor * (1.f - 1e-6f) : logf(t / (1.f - t)) - 1e-3f;
-      for (int j = 0; j < nh; ++j)
-        if (rp[2 * j] > lim) {
-          if (j < 32) m0 |= 1u << j;
-          else m1 |= 1u << (j - 32);
-        }
-    }
-    if (h == 0) m0 &= ~1u;  // class 0 (background) never yields a detection
-    if (q.debug_skip & 2) m0 = m1 = 0u;
-    if (!keep_row) m0 = m1 = 0u;
-    // exact test of the few flagged classes: prob = e * (1/sum) > min_score, as the emitted score
-    unsigned int cnt = 0;
-    {
-      uint32_t mm = m0;
-      while (mm) {
-        const int j = __ffs(mm) - 1;
-        mm &= mm - 1;
-        const float x = rp[2 * j];
-        const float pr = q.act_kind == SBOD_ACT_SOFTMAX ? ex2_approx(fmaf(x, kLog2e, nmx2)) * inv
-                         : (q.act_kind == SBOD_ACT_NONE ? x : __frcp_rn(1.f + __expf(-x)));
-        if (pr > q.min_score && (kOneBits - min(__float_as_uint(pr), kOneBits)) < cut_k32) ++cnt; else m0 &= ~(1u << j);
-      }
-      mm = m1;
-      while (mm) {
-        const int j = __ffs(mm) - 1;
-        mm &= mm - 1;
-        const float x = rp[2 * (j + 32)];
-        const float pr = q.act_kind == SBOD_ACT_SOFTMAX ? ex2_approx(fmaf(x, kLog2e, nmx2)) * inv
-                         : (q.act_kind == SBOD_ACT_NONE ? x : __frcp_rn(1.f + __expf(-x)));
-        if (pr > q.min_score && (kOneBits - min(__float_as_uint(pr), kOneBits)) < cut_k32) ++cnt; else m1 &= ~(1u << j);
-      }
-    }
-    // warp-exclusive scan of the per-thread counts; one global atomic per warp that has candidates
-    // (no CTA-wide barrier: while this warp waits for its slot the other warps keep streaming)
-    unsigned int inc = cnt;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const unsigned int t = __shfl_up_sync(0xffffffffu, inc, o);
-      if (lane >= o) inc += t;
-    }
-    const unsigned int wtot = __shfl_sync(0xffffffffu, inc, 31);
-    // Slots: the warp's keys go to a CTA-wide shared buffer (one shared-memory atomic per warp and
-    // tile) that is handed to global memory with ONE global atomic per flush; a warp never waits for
-    // a global atomic's round trip unless the buffer overflows (then the excess goes out directly).
-    unsigned int wbase = 0u, fits = 0u, gbase = 0u;
-    if (wtot && q.mode != 1) {
-      if (lane == 31) wbase = atomicAdd(&s_ncand, wtot);
-      wbase = __shfl_sync(0xffffffffu, wbase, 31);
-      fits = wbase >= unsigned(kKeyBuf) ? 0u : min(wtot, unsigned(kKeyBuf) - wbase);
-      if (fits < wtot) {
-        if (lane == 31) gbase = atomicAdd(&q.cand_count[n], wtot - fits);
-        gbase = __shfl_sync(0xffffffffu, gbase, 31);
-      }
-    }
-    const unsigned int off = inc - cnt;
-    if (cnt && !(q.debug_skip & 1)) {
-      unsigned int rank = off;  // position inside the warp's block of wtot keys
-      unsigned long long* dst = q.cand + size_t(n) * q.cand_cap;
-#pragma unroll
-      for (int half = 0; half < 2; ++half) {
-        uint32_t mm = half ? m1 : m0;
-        while (mm) {
-          const int j = __ffs(mm) - 1 + 32 * half;
-          mm &= mm - 1;
-          const int k = 2 * j + h;
-          const float x = rp[2 * j];
-          const float pr = q.act_kind == SBOD_ACT_SOFTMAX ? ex2_approx(fmaf(x, kLog2e, nmx2)) * inv
-                           : (q.act_kind == SBOD_ACT_NONE ? x : __frcp_rn(1.f + __expf(-x)));
-          const uint32_t bits = __float_as_uint(pr);
-          const uint32_t k32 = bits > kOneBits ? 0u : kOneBits - bits;
-          const unsigned long long key = (static_cast<unsigned long long>(k32) << 32) |
-                                         (static_cast<unsigned long long>(k) << kPriorBits) |
-                                         static_cast<unsigned long long>(p);
-          if (q.mode != 1) {
-            if (rank < fits) {
-              s_keys[wbase + rank] = key;
-            } else {
-              const long long slot = (long long)gbase + (rank - fits);
-              if (slot < q.cand_cap) dst[slot] = key;
-            }
-          }
-          ++rank;
-          int bin = int(key >> q.shift0);
-          if (bin >= q.n_bins) bin = q.n_bins - 1;
-          atomicAdd(&s_hist[bin], 1u);
-        }
-      }
-    }
-    __syncthreads();  // every thread is done with stage s
-    if (tid == 0 && it + q.n_stages < n_my) issue(it + q.n_stages, stage, &bars[s]);
-    // hand the buffered keys over when the buffer fills up, the image changes or the CTA is done
-    // (s_ncand is stable here: the barrier above is behind every append of this tile)
-    const unsigned int have = min(s_ncand, unsigned(kKeyBuf));
-    if (have && (have >= unsigned(kKeyFlush) || it == n_my - 1 || cur_n != n)) {
-      if (tid == 0) s_gbase = atomicAdd(&q.cand_count[n], have);
-      __syncthreads();
-      unsigned long long* dst = q.cand + size_t(n) * q.cand_cap;
-      for (unsigned int i = tid; i < have; i += kStreamThreads) {
-        const long long slot = (long long)s_gbase + i;
-        if (slot < q.cand_cap) dst[slot] = s_keys[i];
-      }
-      __syncthreads();
-      if (tid == 0) s_ncand = 0u;
-      __syncthreads();
+  auto put = [&](unsigned int slot, unsigned long long key) {
+    if (slot < unsigned(kRefKeyBuf)) s_keys[slot] = key;
+    else if ((long long)(slot - unsigned(kRefKeyBuf)) < q.cand_cap) g_list[slot - unsigned(kRefKeyBuf)] = key;
+    atomicAdd(&s_hist[k32_bin(q, uint32_t(key >> 32))], 1u);
+  };
+  for (int i = wid; i < n_rows; i += kRefThreads / 32) eval_row(q, n, s_rows[i], lane, 0u, cut, reserve, put);
+  __syncthreads();
+  // hand the buffered keys and the histogram over: one global atomic for the CTA's keys
+  const unsigned int have = s_hole != 0xffffffffu ? s_hole : min(s_ncand, unsigned(kRefKeyBuf));
+  if (have) {  // (CTA-uniform)
+    if (tid == 0) s_gbase = atomicAdd(&q.cand_count[n], have);
+    __syncthreads();
+    for (unsigned int i = tid; i < have; i += kRefThreads) {
+      const long long slot = (long long)s_gbase + i;
+      if (slot < q.cand_cap) g_list[slot] = s_keys[i];
     }
   }
-  if (hist_n >= 0) flush_hist(hist_n);
+  unsigned int* gh = q.hist + size_t(n) * kMaxBins;
+  for (int b = tid; b < q.n_bins; b += kRefThreads) {
+    const unsigned int v = s_hist[b];
+    if (v) atomicAdd(&gh[b], v);
+  }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -540,6 +438,10 @@ __global__ void __launch_bounds__(kStreamThreads, 2) detect_score_fast_kernel(co
 SBOD_DEVINL int key_class(unsigned long long k) { return int((k >> kPriorBits) & ((1u << kClassBits) - 1u)); }
 SBOD_DEVINL int key_prior(unsigned long long k) { return int(k & ((1u << kPriorBits) - 1u)); }
 SBOD_DEVINL float key_score(unsigned long long k) { return __uint_as_float(kOneBits - uint32_t(k >> 32)); }
+
+SBOD_DEVINL int64_t out_label(const DetParams& q, int n, unsigned long long k) {
+  return q.agnostic ? int64_t(q.agn_label[size_t(n) * q.P + key_prior(k)]) : int64_t(key_class(k));
+}
 
 // torchvision nms criterion: inter / (area_i + area_j - inter) > thr
 SBOD_DEVINL bool overlaps(const float4 a, const float4 b, float thr) {
@@ -581,29 +483,27 @@ __global__ void __launch_bounds__(kNmsThreads) detect_nms_kernel(const DetParams
   extern __shared__ __align__(128) unsigned char smem_raw[];
   NmsSmem& S = *reinterpret_cast<NmsSmem*>(smem_raw);
   unsigned char* dyn = smem_raw + ((sizeof(NmsSmem) + 127) & ~size_t(127));
+  // kept list: in shared memory; moved to the global spill buffer if the first stage of detect_tools keeps more
   unsigned long long* kkey = reinterpret_cast<unsigned long long*>(dyn);          // [kcap]
   float4* kbox = reinterpret_cast<float4*>(dyn + size_t(q.kcap) * 8);             // [kcap]
   uint8_t* kst2 = reinterpret_cast<uint8_t*>(dyn + size_t(q.kcap) * 24);          // [kcap]
   unsigned int* cls_off = reinterpret_cast<unsigned int*>(dyn + size_t(q.kcap) * 25 + 128 - (size_t(q.kcap) * 25) % 128);  // [C+1]
 
   const int n = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-  if (q.mode == 2 && q.flags[n] == 0u) return;  // fallback pass: only the flagged images
-  bool cutoff_active = false;
-  if (q.mode == 0 && q.speculate) {
-    unsigned int ck = 0xffffffffu;
-    float cf = 0.f;
-    compute_cutoff(q, n, S.wscan, ck, cf);  // same function of the same histogram as the score pass
-    cutoff_active = ck != 0xffffffffu;
-    unsigned int* sh = q.shist + size_t(n) * q.n_bins;
-    for (int b = tid; b < q.n_bins; b += kNmsThreads) sh[b] = 0u;  // clean for the next call
+  // same function of the same histogram as detect_refine_kernel: candidates below `cut` are complete
+  unsigned int cut = compute_cutoff(q, n, S.wscan);
+  {
+    unsigned int* rh = q.rhist + size_t(n) * kMaxBins;
+    for (int b = tid; b < q.n_bins; b += kNmsThreads) rh[b] = 0u;  // clean for the next call
   }
   const bool two_stage = q.second_thr >= 0.f;
-  unsigned int* g_hist = q.hist + size_t(n) * q.n_bins;
+  unsigned int* g_hist = q.hist + size_t(n) * kMaxBins;
   unsigned int* g_seen = q.class_seen + size_t(n) * q.C;
-  const unsigned long long* g_cand = q.cand + size_t(n) * q.cand_cap;
-  const unsigned int raw_total = q.cand_count[n];
-  const long long total = raw_total < (unsigned long long)q.cand_cap ? raw_total : q.cand_cap;
-  const bool overflow = raw_total > (unsigned long long)q.cand_cap;
+  unsigned long long* g_cand = q.cand + size_t(n) * q.cand_cap;
+  unsigned int raw_total = q.cand_count[n];
+  long long total = raw_total < (unsigned long long)q.cand_cap ? raw_total : q.cand_cap;
+  bool overflow = raw_total > (unsigned long long)q.cand_cap;
+  int kcap_now = q.kcap;  // capacity of the kept list (shared memory; the spill buffer once it has been switched to)
 
   int kept_n = 0;   // stage-1 survivors so far (kept list length)
   int kept2_n = 0;  // stage-2 survivors so far
@@ -620,6 +520,7 @@ __global__ void __launch_bounds__(kNmsThreads) detect_nms_kernel(const DetParams
     chunk_cap = 256;
     while (chunk_cap < 2 * stop_at && chunk_cap < kChunk) chunk_cap <<= 1;
   }
+  for (;;) {  // bands: first the candidates above the cutoff, then (rarely) everything else
   while (!exhausted && (two_stage ? kept2_n : kept_n) < stop_at && !status) {
     // ---- choose [lo_key, hi_key) holding at most chunk_cap candidates ----------------------
     int level = 0;
@@ -635,7 +536,7 @@ __global__ void __launch_bounds__(kNmsThreads) detect_nms_kernel(const DetParams
       const int up = (level == 0) ? 64 : level_shift(q, level - 1);
       const unsigned long long node_base = (up >= 64) ? 0ull : (lo_key >> up) << up;
       if (level == 0) {
-        for (int b = tid; b < nb; b += kNmsThreads) S.hist[b] = g_hist[b];
+        for (int b = tid; b < nb; b += kNmsThreads) S.hist[b] = __ldcg(&g_hist[b]);  // (L2: the second band adds to it)
       } else {
         for (int b = tid; b < nb; b += kNmsThreads) S.hist[b] = 0u;
         __syncthreads();
@@ -1041,7 +942,24 @@ __global__ void __launch_bounds__(kNmsThreads) detect_nms_kernel(const DetParams
       if (w < wid) pos += S.wscan[w];
       add += S.wscan[w];
     }
-    if (kept_n + add > q.kcap) {
+    if (kept_n + add > kcap_now && kcap_now == q.kcap && q.spill_key && kept_n + add <= q.spill_cap) {
+      // detect_tools only: the first stage kept more boxes than fit in shared memory -> the kept list moves to
+      // the global spill buffer (slower, exact; the reference has no limit here)
+      unsigned long long* gk = q.spill_key + size_t(n) * q.spill_cap;
+      float4* gb = q.spill_box + size_t(n) * q.spill_cap;
+      uint8_t* gs = q.spill_st2 + size_t(n) * q.spill_cap;
+      for (int i = tid; i < kept_n; i += kNmsThreads) {
+        gk[i] = kkey[i];
+        gb[i] = kbox[i];
+        gs[i] = kst2[i];
+      }
+      __syncthreads();
+      kkey = gk;
+      kbox = gb;
+      kst2 = gs;
+      kcap_now = q.spill_cap;
+    }
+    if (kept_n + add > kcap_now) {
       status = 1;
     } else {
       if (keep_me) {
@@ -1055,20 +973,36 @@ __global__ void __launch_bounds__(kNmsThreads) detect_nms_kernel(const DetParams
     __syncthreads();
   }
 
+    // The candidates above the cutoff ran out before top_k+1 boxes survived: the answer needs lower-scored
+    // candidates. Second band, exact: this CTA evaluates every row of its image and emits what lies below the
+    // cutoff (rare; the bound pass sized the first band for ~4x the boxes wanted).
+    if (exhausted && !status && !overflow && cut != 0xffffffffu && (two_stage ? kept2_n : kept_n) < stop_at) {
+      auto reserve = [&](unsigned int count) -> unsigned int { return atomicAdd(&q.cand_count[n], count); };
+      auto put = [&](unsigned int slot, unsigned long long key) {
+        if ((long long)slot < q.cand_cap) g_cand[slot] = key;
+        atomicAdd(&g_hist[k32_bin(q, uint32_t(key >> 32))], 1u);
+      };
+      for (int p = wid; p < q.P; p += kNmsThreads / 32)
+        if (q.pbound[size_t(n) * q.P + p] > q.min_score) eval_row(q, n, p, lane, cut, 0xffffffffu, reserve, put);
+      __threadfence();
+      __syncthreads();
+      raw_total = *reinterpret_cast<volatile unsigned int*>(&q.cand_count[n]);
+      total = raw_total < (unsigned long long)q.cand_cap ? raw_total : q.cand_cap;
+      overflow = raw_total > (unsigned long long)q.cand_cap;
+      lo_key = static_cast<unsigned long long>(cut) << 32;  // every key of the second band is >= this
+      cut = 0xffffffffu;
+      exhausted = false;
+      __syncthreads();
+      continue;
+    }
+    break;
+  }
+
   // ---- leave the workspace clean for the next call ----------------------------------------
+  __syncthreads();
   for (int b = tid; b < q.n_bins; b += kNmsThreads) g_hist[b] = 0u;
   for (int c = tid; c < q.C; c += kNmsThreads) g_seen[c] = 0u;
   if (tid == 0) q.cand_count[n] = 0u;
-  if (q.mode == 2 && tid == 0) q.flags[n] = 0u;
-  // The candidates above the speculative cutoff ran out before top_k+1 boxes survived: the answer
-  // needs lower-scored candidates that were not emitted. Flag the image; the fallback pass redoes it.
-  if (cutoff_active && !status && !overflow && (two_stage ? kept2_n : kept_n) < stop_at) {
-    if (tid == 0) {
-      q.flags[n] = 1u;
-      q.out_counts[n] = -3;
-    }
-    return;
-  }
 
   // ---- emit --------------------------------------------------------------------------------
   float4* ob = reinterpret_cast<float4*>(q.out_boxes) + size_t(n) * q.out_cap;
@@ -1094,7 +1028,7 @@ __global__ void __launch_bounds__(kNmsThreads) detect_nms_kernel(const DetParams
       // more than top_k survivors: the reference sorts by score (stable) and keeps the first top_k
       for (int i = tid; i < q.top_k; i += kNmsThreads) {
         const unsigned long long k = kkey[i];
-        ob[i] = kbox[i]; ol[i] = key_class(k); os[i] = key_score(k); op[i] = key_prior(k);
+        ob[i] = kbox[i]; ol[i] = out_label(q, n, k); os[i] = key_score(k); op[i] = key_prior(k);
       }
       if (tid == 0) q.out_counts[n] = q.top_k;
     } else {
@@ -1107,7 +1041,7 @@ __global__ void __launch_bounds__(kNmsThreads) detect_nms_kernel(const DetParams
           const int cj = key_class(kkey[j]);
           dst += (cj < c || (cj == c && j < i)) ? 1 : 0;
         }
-        ob[dst] = kbox[i]; ol[dst] = c; os[dst] = key_score(k); op[dst] = key_prior(k);
+        ob[dst] = kbox[i]; ol[dst] = out_label(q, n, k); os[dst] = key_score(k); op[dst] = key_prior(k);
       }
       if (tid == 0) q.out_counts[n] = kept_n;
     }
@@ -1124,7 +1058,7 @@ __global__ void __launch_bounds__(kNmsThreads) detect_nms_kernel(const DetParams
         const int dst = w + __popc(bal & ((1u << lane) - 1u));
         if (s2 && (!truncate || dst < q.top_k) && dst < q.out_cap) {
           const unsigned long long k = kkey[i];
-          ob[dst] = kbox[i]; ol[dst] = key_class(k); os[dst] = key_score(k); op[dst] = key_prior(k);
+          ob[dst] = kbox[i]; ol[dst] = out_label(q, n, k); os[dst] = key_score(k); op[dst] = key_prior(k);
         }
         w += __popc(bal);
       }
@@ -1134,24 +1068,6 @@ __global__ void __launch_bounds__(kNmsThreads) detect_nms_kernel(const DetParams
 }
 
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
-
-struct DTiling {
-  int rows, stages;
-  uint32_t stage_floats;
-  size_t smem;
-};
-static DTiling choose_dtiling(int C) {
-  DTiling t;
-  const size_t budget = 100 * 1024;
-  t.rows = kDRows;
-  while (t.rows > 4 && (size_t(t.rows) * C + 8) * 4 > budget) t.rows /= 2;
-  t.stage_floats = uint32_t(align_up(size_t(t.rows) * C + 8, 32));
-  t.stages = int(budget / (size_t(t.stage_floats) * 4));
-  if (t.stages > 4) t.stages = 4;
-  if (t.stages < 1) t.stages = 1;
-  t.smem = size_t(t.stages) * t.stage_floats * 4 + 4 * 8;
-  return t;
-}
 
 static void level0_layout(float min_score, int* shift0, int* n_bins) {
   // keys: (0x3F800000 - score_bits) << 32 | ...; score in (min_score, 1]
@@ -1167,13 +1083,47 @@ static void level0_layout(float min_score, int* shift0, int* n_bins) {
 }
 
 static long long cand_capacity(const sbod_detect_desc* d) {
+  if (d->class_agnostic) return (long long)d->P;
   return (long long)d->P * (long long)(d->C > 1 ? d->C - 1 : 1);
 }
+
+constexpr int kSpillCap = 65536;  // kept boxes per image of the detect_tools first stage before the call gives up
 
 static int kept_capacity(const sbod_detect_desc* d) {
   // multiple of 16 so that the float4 / u64 arrays carved after each other stay aligned
   if (d->second_nms_thr >= 0.f) return 4096 + kChunk;
   return (d->top_k + 1 + kChunk + 15) & ~15;
+}
+
+// workspace carve-up (the leading block carries the zero contract)
+struct DetLayout {
+  size_t cand_count, hist, class_seen, rhist, zero_end, pbound, agn_label, nms_mask, spill_key, spill_box, spill_st2,
+      cand, total;
+};
+static DetLayout det_layout(const sbod_detect_desc* d) {
+  DetLayout l;
+  size_t o = 0;
+  auto take = [&](size_t bytes) {
+    const size_t at = o;
+    o += align_up(bytes, 256);
+    return at;
+  };
+  const size_t N = size_t(d->N), P = size_t(d->P);
+  l.cand_count = take(N * 4);
+  l.hist = take(N * kMaxBins * 4);
+  l.class_seen = take(N * size_t(d->C) * 4);
+  l.rhist = take(N * kMaxBins * 4);
+  l.zero_end = o;
+  l.pbound = take(N * P * 4);
+  l.agn_label = take(d->class_agnostic ? N * P * 4 : 0);
+  l.nms_mask = take(N * kChunk * (kChunk / 32) * 4);
+  const bool spill = d->second_nms_thr >= 0.f;
+  l.spill_key = take(spill ? N * kSpillCap * 8 : 0);
+  l.spill_box = take(spill ? N * kSpillCap * 16 : 0);
+  l.spill_st2 = take(spill ? N * kSpillCap : 0);
+  l.cand = take(N * size_t(cand_capacity(d)) * 8);
+  l.total = o;
+  return l;
 }
 
 }  // namespace sbod
@@ -1182,26 +1132,13 @@ using namespace sbod;
 
 extern "C" size_t sbod_detect_workspace_bytes(const sbod_detect_desc* d) {
   if (!d) return 0;
-  int sh, nb;
-  level0_layout(d->min_score, &sh, &nb);
-  size_t b = 0;
-  b += align_up(size_t(d->N) * 4, 256);                       // cand_count
-  b += align_up(size_t(d->N) * kMaxBins * 4, 256);            // hist
-  b += align_up(size_t(d->N) * size_t(d->C) * 4, 256);        // class_seen
-  b += align_up(size_t(d->N) * kMaxBins * 4, 256);            // shist
-  b += align_up(size_t(d->N) * 4, 256);                       // flags
-  b += align_up(size_t(d->N) * 4, 256) * 2;                   // cutoff_k32, cutoff_floor
-  b += align_up(size_t(d->N) * kChunk * (kChunk / 32) * 4, 256);  // nms_mask
-  b += align_up(size_t(d->N) * size_t(cand_capacity(d)) * 8, 256);
-  return b;
+  return det_layout(d).total;
 }
 
 // bytes at the start of the workspace that must be zero before the first call
 extern "C" size_t sbod_detect_workspace_zero_bytes(const sbod_detect_desc* d) {
   if (!d) return 0;
-  return align_up(size_t(d->N) * 4, 256) + align_up(size_t(d->N) * kMaxBins * 4, 256) +
-         align_up(size_t(d->N) * size_t(d->C) * 4, 256) + align_up(size_t(d->N) * kMaxBins * 4, 256) +
-         align_up(size_t(d->N) * 4, 256);
+  return det_layout(d).zero_end;
 }
 
 static int detect_run(const sbod_detect_desc* d, sbod_stream_t stream, int stage_mask) {
@@ -1215,9 +1152,11 @@ static int detect_run(const sbod_detect_desc* d, sbod_stream_t stream, int stage
   if (d->P > (1 << kPriorBits) || d->C > (1 << kClassBits)) return SBOD_ERR_UNSUPPORTED;
   if (d->top_k > 4096) return SBOD_ERR_UNSUPPORTED;
   if (d->out_cap < (d->top_k > 1 ? d->top_k : 1)) return SBOD_ERR_INVALID;
+  if (d->class_agnostic && (d->second_nms_thr >= 0.f || d->pre_nms_topk > 0)) return SBOD_ERR_INVALID;
   if (reinterpret_cast<uintptr_t>(d->scores) & 15) return SBOD_ERR_ALIGNMENT;
   if (reinterpret_cast<uintptr_t>(d->locs) & 15) return SBOD_ERR_ALIGNMENT;
-  if (!d->workspace || d->workspace_bytes < sbod_detect_workspace_bytes(d)) return SBOD_ERR_WORKSPACE;
+  const DetLayout lay = det_layout(d);
+  if (!d->workspace || d->workspace_bytes < lay.total) return SBOD_ERR_WORKSPACE;
   if (reinterpret_cast<uintptr_t>(d->workspace) & 255) return SBOD_ERR_WORKSPACE;
 
   DetParams q;
@@ -1228,127 +1167,72 @@ static int detect_run(const sbod_detect_desc* d, sbod_stream_t stream, int stage
   q.act_kind = d->act_kind; q.box_kind = d->box_kind; q.clamp_inplace = d->clamp_inplace;
   q.min_score = d->min_score; q.max_overlap = d->max_overlap; q.top_k = d->top_k;
   q.second_thr = d->second_nms_thr; q.pre_nms_topk = d->pre_nms_topk;
+  q.agnostic = d->class_agnostic ? 1 : 0;
   q.out_boxes = d->out_boxes; q.out_labels = d->out_labels; q.out_scores = d->out_scores;
   q.out_prior = d->out_prior; q.out_counts = d->out_counts; q.out_cap = d->out_cap;
   level0_layout(d->min_score, &q.shift0, &q.n_bins);
   q.cand_cap = cand_capacity(d);
   q.kcap = kept_capacity(d);
-  q.debug_skip = 0;
-#ifdef SBOD_DEBUG_HOOKS  // profiling builds only: release builds never read the environment
-  {
-    const char* e = getenv("SBOD_DEBUG_SKIP");
-    q.debug_skip = e ? atoi(e) : 0;
-  }
-#endif
   unsigned char* w = static_cast<unsigned char*>(d->workspace);
-  q.cand_count = reinterpret_cast<unsigned int*>(w); w += align_up(size_t(q.N) * 4, 256);
-  q.hist = reinterpret_cast<unsigned int*>(w);       w += align_up(size_t(q.N) * kMaxBins * 4, 256);
-  q.class_seen = reinterpret_cast<unsigned int*>(w); w += align_up(size_t(q.N) * size_t(q.C) * 4, 256);
-  q.shist = reinterpret_cast<unsigned int*>(w);      w += align_up(size_t(q.N) * kMaxBins * 4, 256);
-  q.flags = reinterpret_cast<unsigned int*>(w);      w += align_up(size_t(q.N) * 4, 256);
-  q.cutoff_k32 = reinterpret_cast<unsigned int*>(w); w += align_up(size_t(q.N) * 4, 256);
-  q.cutoff_floor = reinterpret_cast<float*>(w);      w += align_up(size_t(q.N) * 4, 256);
-  q.nms_mask = reinterpret_cast<unsigned int*>(w);   w += align_up(size_t(q.N) * kChunk * (kChunk / 32) * 4, 256);
-  q.cand = reinterpret_cast<unsigned long long*>(w);
-  q.mode = 0;
-  q.speculate = 0;
-  q.sample_stride = 26;
-  q.sample_target = 4 * (q.top_k + 1) + 1024;
-#ifdef SBOD_DEBUG_HOOKS
-  if (getenv("SBOD_TARGET")) q.sample_target = atoi(getenv("SBOD_TARGET"));
-#endif
-  // hist rows are n_bins wide inside the kMaxBins-strided allocation
-  const DTiling t = choose_dtiling(q.C);
-  q.rows_per_tile = t.rows;
-  q.tiles_per_image = (q.P + t.rows - 1) / t.rows;
-  q.n_tiles = q.tiles_per_image * q.N;
-  q.n_stages = t.stages;
-  q.stage_floats = t.stage_floats;
+  q.cand_count = reinterpret_cast<unsigned int*>(w + lay.cand_count);
+  q.hist = reinterpret_cast<unsigned int*>(w + lay.hist);
+  q.class_seen = reinterpret_cast<unsigned int*>(w + lay.class_seen);
+  q.rhist = reinterpret_cast<unsigned int*>(w + lay.rhist);
+  q.pbound = reinterpret_cast<float*>(w + lay.pbound);
+  q.agn_label = reinterpret_cast<int32_t*>(w + lay.agn_label);
+  q.nms_mask = reinterpret_cast<unsigned int*>(w + lay.nms_mask);
+  const bool spill = d->second_nms_thr >= 0.f;
+  q.spill_key = spill ? reinterpret_cast<unsigned long long*>(w + lay.spill_key) : nullptr;
+  q.spill_box = spill ? reinterpret_cast<float4*>(w + lay.spill_box) : nullptr;
+  q.spill_st2 = spill ? reinterpret_cast<uint8_t*>(w + lay.spill_st2) : nullptr;
+  q.spill_cap = spill ? kSpillCap : 0;
+  q.cand = reinterpret_cast<unsigned long long*>(w + lay.cand);
+  // first band: about four times the boxes wanted plus a chunk of slack (rows; each holds >= 0 candidates)
+  q.rows_target = 4 * (q.top_k + 1) + 1024;
+  if (q.pre_nms_topk > 0 || q.second_thr >= 0.f) q.rows_target *= 2;
+
+  // bound pass tiling: 128-row tiles (one thread per row), several rows per thread when the rows are short,
+  // fewer rows when a tile would not fit; as many ring stages as fit in ~100 KB (two CTAs per SM)
+  {
+    const size_t row_bytes = size_t(q.C) * 4;
+    int rows = kBThreads;
+    while (rows < 1024 && size_t(rows) * 2 * row_bytes <= 24 * 1024) rows *= 2;
+    while (rows > 1 && size_t(rows) * row_bytes + 32 > 96 * 1024) rows /= 2;
+    q.rows_per_tile = rows;
+    q.stage_floats = uint32_t(align_up(size_t(rows) * q.C + 8, 32));
+    const size_t sb = size_t(q.stage_floats) * 4;
+    q.n_stages = int((100 * 1024) / sb);
+    if (q.n_stages > 4) q.n_stages = 4;
+    if (q.n_stages < 1) q.n_stages = 1;
+    q.tiles_per_image = (q.P + rows - 1) / rows;
+    q.n_tiles = q.tiles_per_image * q.N;
+  }
 
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   static DeviceOnce attr_once;
   if (attr_once.pending()) {
-    SBOD_CUDA_TRY(cudaFuncSetAttribute(detect_score_kernel,
-                                       cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    SBOD_CUDA_TRY(cudaFuncSetAttribute(detect_score_fast_kernel<81>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    SBOD_CUDA_TRY(cudaFuncSetAttribute(detect_score_fast_kernel<21>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    SBOD_CUDA_TRY(cudaFuncSetAttribute(detect_score_fast_kernel<0>,
-                                       cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024));
-    SBOD_CUDA_TRY(cudaFuncSetAttribute(detect_nms_kernel,
-                                       cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+    SBOD_CUDA_TRY(cudaFuncSetAttribute(detect_bound_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    SBOD_CUDA_TRY(cudaFuncSetAttribute(detect_nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
     attr_once.mark();
   }
-  int ctas_per_sm = int((220 * 1024) / (t.smem + 2 * 1024));
-  if (ctas_per_sm < 1) ctas_per_sm = 1;
-  if (ctas_per_sm > 8) ctas_per_sm = 8;
-  int grid = sm_count() * ctas_per_sm;
-  if (grid > q.n_tiles) grid = q.n_tiles;
-  const bool fast = q.C >= 2 && q.C <= 128;  // odd C is bank-conflict free, even C only slower in smem
-  if (fast) {
-    q.rows_per_tile = kTileRows;
-    q.stage_floats = uint32_t(align_up(size_t(kTileRows) * q.C + 8, 32));
-    const size_t sb = size_t(q.stage_floats) * 4;
-    int ctas = 2;
-    q.n_stages = int((96 * 1024) / sb);
-    if (q.n_stages < 2) {
-      q.n_stages = int((200 * 1024) / sb);
-      ctas = 1;
-    }
-    if (q.n_stages > 4) q.n_stages = 4;
-    q.tiles_per_image = (q.P + kTileRows - 1) / kTileRows;
-    q.n_tiles = q.tiles_per_image * q.N;
-    const size_t fsmem = size_t(q.n_stages) * sb + 4 * 8;
-    int fgrid = sm_count() * ctas;
-    if (fgrid > q.n_tiles) fgrid = q.n_tiles;
-    auto launch_score = [&](int g, const DetParams& qq) {
-      if (qq.C == 81) detect_score_fast_kernel<81><<<g, kStreamThreads, fsmem, st>>>(qq);       // COCO
-      else if (qq.C == 21) detect_score_fast_kernel<21><<<g, kStreamThreads, fsmem, st>>>(qq);  // VOC
-      else detect_score_fast_kernel<0><<<g, kStreamThreads, fsmem, st>>>(qq);
-    };
-    // Speculation pays when the sampled histogram is cheap relative to the main pass.
-    const bool speculate = q.tiles_per_image >= 2 * q.sample_stride && !(q.debug_skip & 4);
-    q.speculate = speculate ? 1 : 0;
-    if ((stage_mask & 1) && speculate) {
-      {
-        DetParams qs = q;
-        qs.mode = 1;
-        int sgrid = (q.n_tiles / q.sample_stride + 1);
-        if (sgrid > fgrid) sgrid = fgrid;
-        launch_score(sgrid, qs);
-        SBOD_LAUNCH_CHECK();
-      }
-    }
-    if (stage_mask & 4) {
-      launch_score(fgrid, q);
-      SBOD_LAUNCH_CHECK();
-    }
-    if (stage_mask & 2) {
-      const size_t nms_smem_f = ((sizeof(NmsSmem) + 127) & ~size_t(127)) + size_t(q.kcap) * 25 + 256 +
-                                size_t(q.C + 1) * 4;
-      if (nms_smem_f > 220 * 1024) return SBOD_ERR_UNSUPPORTED;
-      detect_nms_kernel<<<q.N, kNmsThreads, nms_smem_f, st>>>(q);
-      SBOD_LAUNCH_CHECK();
-      if (speculate) {  // exact fallback for the images whose candidates ran out (usually none)
-        DetParams qf = q;
-        qf.mode = 2;
-        launch_score(fgrid, qf);
-        SBOD_LAUNCH_CHECK();
-        detect_nms_kernel<<<q.N, kNmsThreads, nms_smem_f, st>>>(qf);
-        SBOD_LAUNCH_CHECK();
-      }
-      return SBOD_OK;
-    }
-    if (!(stage_mask & 2)) return SBOD_OK;
-  } else if (stage_mask & 4) {
-    detect_score_kernel<<<grid, kDRows, t.smem, st>>>(q);
+  if (stage_mask & 1) {  // bound pass
+    const size_t smem = size_t(q.n_stages) * q.stage_floats * 4 + 4 * 8;
+    int grid = sm_count() * 2;
+    if (grid > q.n_tiles) grid = q.n_tiles;
+    detect_bound_kernel<<<grid, kBThreads, smem, st>>>(q);
     SBOD_LAUNCH_CHECK();
   }
-  if (!(stage_mask & 2)) return SBOD_OK;
-  const size_t nms_smem = ((sizeof(NmsSmem) + 127) & ~size_t(127)) + size_t(q.kcap) * 25 + 256 +
-                          size_t(q.C + 1) * 4;
-  if (nms_smem > 220 * 1024) return SBOD_ERR_UNSUPPORTED;
-  detect_nms_kernel<<<q.N, kNmsThreads, nms_smem, st>>>(q);
-  SBOD_LAUNCH_CHECK();
+  if (stage_mask & 4) {  // exact evaluation of the rows above the cutoff
+    dim3 grid((q.P + kRefRows - 1) / kRefRows, q.N);
+    detect_refine_kernel<<<grid, kRefThreads, 0, st>>>(q);
+    SBOD_LAUNCH_CHECK();
+  }
+  if (stage_mask & 2) {  // NMS (+ in-kernel second band for the images that need it)
+    const size_t nms_smem = ((sizeof(NmsSmem) + 127) & ~size_t(127)) + size_t(q.kcap) * 25 + 256 + size_t(q.C + 1) * 4;
+    if (nms_smem > 220 * 1024) return SBOD_ERR_UNSUPPORTED;
+    detect_nms_kernel<<<q.N, kNmsThreads, nms_smem, st>>>(q);
+    SBOD_LAUNCH_CHECK();
+  }
   return SBOD_OK;
 }
 
@@ -1356,9 +1240,9 @@ extern "C" int sbod_detect(const sbod_detect_desc* d, sbod_stream_t stream) {
   return detect_run(d, stream, 7);
 }
 
-// Profiling / bench hook. stage 0 = sampling pass + main score pass, 1 = NMS kernel (+ fallback
-// passes), 2 = sampling pass only, 3 = main score pass only. Score passes must be followed by a
-// stage-1 launch before the next full sbod_detect (it consumes and cleans the workspace).
+// Profiling / bench hook. stage 0 = bound pass + refine, 1 = NMS kernel, 2 = bound pass only (the streaming
+// kernel), 3 = refine only, 4 = refine + NMS (everything after stage 2). A bound pass must be followed by the
+// later stages before the next full sbod_detect (the NMS kernel consumes and cleans the workspace).
 extern "C" int sbod_detect_stage(const sbod_detect_desc* d, int stage, sbod_stream_t stream) {
   static const int masks[5] = {1 | 4, 2, 1, 4, 4 | 2};
   if (stage < 0 || stage > 4) return SBOD_ERR_INVALID;

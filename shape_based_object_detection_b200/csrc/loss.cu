@@ -828,11 +828,22 @@ __device__ SelectResult cluster_topk_sum(cg::cluster_group& cluster, ClusterSele
     unsigned int* hist = S.hist[pass & 1];
     for (int b = tid; b < nb; b += nt) hist[b] = 0u;
     __syncthreads();
-    for (int i = tid; i < n_local; i += nt) {
-      const float v = vals[i];
-      if (v >= 0.f) {
-        const uint32_t bits = __float_as_uint(v);
-        if ((bits & mask) == prefix) atomicAdd(&hist[(bits >> shift) & dmask], 1u);
+    // (the leading digit of cross entropies takes a handful of values: lanes with the same digit add once)
+    for (int i0 = 0; i0 < n_local; i0 += nt) {
+      const int i = i0 + tid;
+      int digit = -1;
+      if (i < n_local) {
+        const float v = vals[i];
+        if (v >= 0.f) {
+          const uint32_t bits = __float_as_uint(v);
+          if ((bits & mask) == prefix) digit = int((bits >> shift) & dmask);
+        }
+      }
+      if (pass == 0) {
+        const unsigned peers = __match_any_sync(0xffffffffu, digit);
+        if (digit >= 0 && lane == __ffs(peers) - 1) atomicAdd(&hist[digit], unsigned(__popc(peers)));
+      } else if (digit >= 0) {
+        atomicAdd(&hist[digit], 1u);
       }
     }
     cluster.sync();  // every slice's histogram of this pass is complete
@@ -952,6 +963,8 @@ SBOD_DEVINL void finalize_loss(const LossParams& q, const double* sums, float* l
 // ------------------------------------------------------------------------------------------
 constexpr int kCmThreads = 512;
 constexpr int kCmMaxCluster = 8;
+constexpr int kCmUnroll = 4;      // priors per thread whose loads are in flight together
+constexpr int kCmFgCap = 4096;    // foreground-row list (entries); evaluated and reset when it could overflow
 
 struct CmShared {
   ClusterSelect sel;
@@ -960,8 +973,11 @@ struct CmShared {
   int warp_tot[kCmThreads / 32];
   int carry;
   int last;
-  uint16_t lidx[kCmThreads], lcls[kCmThreads];  // rows with a foreground class: local index, class (bit 15: positive)
-  uint16_t cnt[kCmThreads / 32];
+  int fg_n;
+  uint16_t cnt[kCmUnroll][kCmThreads / 32];
+  uint32_t fg_idx[kCmFgCap];   // foreground rows: prior index inside the slice
+  uint16_t fg_cls[kCmFgCap];   // ... class (bit 15: positive)
+  uint16_t fg_obj[kCmFgCap];   // ... object of the image
 };
 
 __global__ void __launch_bounds__(kCmThreads) classify_mine_kernel(const LossParams q) {
@@ -969,9 +985,11 @@ __global__ void __launch_bounds__(kCmThreads) classify_mine_kernel(const LossPar
   extern __shared__ __align__(128) unsigned char smem_raw[];
   CmShared& S = *reinterpret_cast<CmShared*>(smem_raw);
   unsigned char* dyn = smem_raw + ((sizeof(CmShared) + 127) & ~size_t(127));
-  uint32_t* s_prior = reinterpret_cast<uint32_t*>(dyn);            // [gmax]
+  float4* s_gbox = reinterpret_cast<float4*>(dyn);                 // [gmax] the image's objects
+  uint32_t* s_prior = reinterpret_cast<uint32_t*>(s_gbox + q.gmax);  // [gmax]
   int32_t* s_rank = reinterpret_cast<int32_t*>(s_prior + q.gmax);  // [gmax], -1 = filtered out
-  float* s_vals = reinterpret_cast<float*>(dyn + ((size_t(q.gmax) * 8 + 127) & ~size_t(127)));  // [slice] if cached
+  int32_t* s_label = s_rank + q.gmax;                              // [gmax] mapped labels
+  float* s_vals = reinterpret_cast<float*>(dyn + ((size_t(q.gmax) * 28 + 127) & ~size_t(127)));  // [slice] if cached
 
   const unsigned int n_ranks = cluster.num_blocks(), rank = cluster.block_rank();
   const int n = blockIdx.x / n_ranks, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
@@ -981,13 +999,19 @@ __global__ void __launch_bounds__(kCmThreads) classify_mine_kernel(const LossPar
   const size_t base = size_t(n) * q.P;
   const bool focal = q.cls_kind == SBOD_CLS_FOCAL_SUM || q.cls_kind == SBOD_CLS_FOCAL_NORM;
   const bool cached = q.mine_cache != 0;
-  if (tid == 0) S.carry = 0;
+  const int g0 = q.gt_offsets[n];  // (inputs of the call, not results of the match kernel)
+  const int G = q.gt_offsets[n + 1] - g0;
+  if (tid == 0) {
+    S.carry = 0;
+    S.fg_n = 0;
+  }
+  for (int g = tid; g < G; g += kCmThreads) {
+    s_gbox[g] = q.gt_boxes[g0 + g];
+    s_label[g] = int(map_label(q, q.gt_labels[g0 + g]));
+  }
 
   // everything above is independent of the match kernel's results; from here on they are needed
   asm volatile("griddepcontrol.wait;" ::: "memory");
-
-  const int g0 = q.gt_offsets[n];
-  const int G = q.gt_offsets[n + 1] - g0;
   __syncthreads();
   // ---- forced list: rank j of each object inside "objects whose best overlap is > 0" ----
   for (int gb = 0; gb < G; gb += kCmThreads) {
@@ -1027,74 +1051,114 @@ __global__ void __launch_bounds__(kCmThreads) classify_mine_kernel(const LossPar
   }
   __syncthreads();  // the patched overlaps / objects are visible to the whole CTA
 
-  // ---- phase A / B per 512 priors ----
   double a_loc = 0.0, a_pos = 0.0, a_neg = 0.0;
   int npos = 0;
-  for (int pb = p_lo; pb < p_hi; pb += kCmThreads) {
-    const int p = pb + tid;
-    int rec = 0;
-    int my_obj = 0;
-    if (p < p_hi) {
-      const float ov = q.ov[base + p];
-      my_obj = q.obj[base + p];
-      const float ce = q.ce[base + p];  // background CE from the streaming kernel
-      const bool ex = q.exclude ? q.exclude[base + p] != 0 : false;
-      int64_t cls = 0;
-      if (!(ov < q.thr_pos) && G > 0) cls = map_label(q, q.gt_labels[g0 + my_obj]);
-      const bool pos = cls > 0 && !ex;
-      const bool isneg = ov < q.thr_neg;
-      uint8_t selbits = pos ? 1 : 0;
-      float v = -1.f;
-      if (cls > 0) {
-        rec = min(int(cls), q.C - 1) | (pos ? 0x8000 : 0);  // C <= 16384 elsewhere; classes fit 15 bits
-      } else if (focal) {
-        if (isneg) {  // target class is 0 there (thr_neg < thr_pos)
-          selbits |= 2;
-          a_neg += double(focal_bg(q, ce));
-        }
-      } else if (q.cls_kind == SBOD_CLS_CE_MINE_NONPOS) {
-        if (!ex) v = ce;
-      } else {  // MINE_NEG, MINE_BATCH: only true_neg == -1 rows are candidates
-        if (isneg) v = ce;
-      }
-      if (!focal && v >= 0.f) a_neg += 1.0;  // mining modes: this partial counts the candidates (NaN CEs are none)
-      q.sel[base + p] = selbits;
-      q.cand[base + p] = v;
-      if (cached) s_vals[p - p_lo] = v;
-    }
-    // rows with a foreground class (2-3 % of the priors): recorded, then evaluated densely. The list order is
-    // deterministic (ballot ranks, warps in order), so the per-thread partial sums are reproducible.
-    const unsigned bal = __ballot_sync(0xffffffffu, rec != 0);
-    const int rrank = __popc(bal & ((1u << lane) - 1u));
-    if (lane == 0) S.cnt[wid] = uint16_t(__popc(bal));
-    __syncthreads();
-    int mine_base = 0, total = 0;
-    for (int w2 = 0; w2 < kCmThreads / 32; ++w2) {
-      const int c2 = S.cnt[w2];
-      if (w2 < wid) mine_base += c2;
-      total += c2;
-    }
-    if (rec) {
-      S.lidx[mine_base + rrank] = uint16_t(tid);
-      S.lcls[mine_base + rrank] = uint16_t(rec);
-    }
-    __syncthreads();
+  // Phase B: the recorded foreground rows (2-3 % of the priors), one per thread, every load of a row
+  // independent of the others (class, object and its box come from shared memory).
+  auto eval_foreground = [&]() {
+    const int total = S.fg_n;
     for (int i = tid; i < total; i += kCmThreads) {
-      const int pp = pb + S.lidx[i];
-      const int c = S.lcls[i] & 0x7fff;
-      const bool pos = (S.lcls[i] & 0x8000) != 0;
-      const float ce = q.lse[base + pp] - q.scores[(base + pp) * q.C + c];  // CE against the true class
+      const int pp = p_lo + int(S.fg_idx[i]);
+      const int c = S.fg_cls[i] & 0x7fff;
+      const bool pos = (S.fg_cls[i] & 0x8000) != 0;
+      const float lse = q.lse[base + pp];
+      const float xc = ld_stream_f32(q.scores + (base + pp) * q.C + c);
+      float4 pred = make_float4(0.f, 0.f, 0.f, 0.f), pcx = pred;
+      if (pos) {
+        pred = reinterpret_cast<const float4*>(q.locs)[base + pp];
+        pcx = prior_cxcy_of(q, n, pp);
+      }
+      const float ce = lse - xc;  // CE against the true class
       q.ce[base + pp] = ce;
       if (pos) {
         ++npos;
         a_pos += focal ? double(focal_fg(q, ce)) : double(ce);
-        const float4 pred = reinterpret_cast<const float4*>(q.locs)[base + pp];
-        const LocTerm lt = loc_term<false>(q, pred, prior_cxcy_of(q, n, pp), q.gt_boxes[g0 + q.obj[base + pp]]);
+        const LocTerm lt = loc_term<false>(q, pred, pcx, s_gbox[S.fg_obj[i]]);
         a_loc += double(lt.loss);
       }
     }
-    __syncthreads();  // the lists are free for the next 512 priors
+    __syncthreads();
+    if (tid == 0) S.fg_n = 0;
+    __syncthreads();
+  };
+
+  // Phase A: every prior of the slice, kCmUnroll per thread with all their loads in flight together:
+  // class, selection bits, mining candidate (kept in shared memory); foreground rows are recorded.
+  // The list order is deterministic (unroll slot, warp, ballot rank), so the sums are reproducible.
+  for (int pb = p_lo; pb < p_hi; pb += kCmThreads * kCmUnroll) {
+    float ov[kCmUnroll], ce[kCmUnroll];
+    int ob[kCmUnroll];
+    uint8_t ex[kCmUnroll];
+#pragma unroll
+    for (int u = 0; u < kCmUnroll; ++u) {
+      const int p = pb + u * kCmThreads + tid;
+      ov[u] = 0.f; ce[u] = 0.f; ob[u] = 0; ex[u] = 0;
+      if (p < p_hi) {
+        ov[u] = q.ov[base + p];
+        ob[u] = q.obj[base + p];
+        ce[u] = q.ce[base + p];  // background CE from the streaming kernel
+        if (q.exclude) ex[u] = q.exclude[base + p];
+      }
+    }
+    int rec[kCmUnroll], rrank[kCmUnroll];
+#pragma unroll
+    for (int u = 0; u < kCmUnroll; ++u) {
+      const int p = pb + u * kCmThreads + tid;
+      rec[u] = 0;
+      if (p < p_hi) {
+        int cls = 0;
+        if (!(ov[u] < q.thr_pos) && G > 0) cls = s_label[ob[u]];
+        const bool pos = cls > 0 && !ex[u];
+        const bool isneg = ov[u] < q.thr_neg;
+        uint8_t selbits = pos ? 1 : 0;
+        float v = -1.f;
+        if (cls > 0) {
+          rec[u] = min(cls, q.C - 1) | (pos ? 0x8000 : 0);  // C <= 16384 elsewhere; classes fit 15 bits
+        } else if (focal) {
+          if (isneg) {  // target class is 0 there (thr_neg < thr_pos)
+            selbits |= 2;
+            a_neg += double(focal_bg(q, ce[u]));
+          }
+        } else if (q.cls_kind == SBOD_CLS_CE_MINE_NONPOS) {
+          if (!ex[u]) v = ce[u];
+        } else {  // MINE_NEG, MINE_BATCH: only true_neg == -1 rows are candidates
+          if (isneg) v = ce[u];
+        }
+        if (!focal && v >= 0.f) a_neg += 1.0;  // mining modes: this partial counts the candidates (NaN CEs are none)
+        q.sel[base + p] = selbits;
+        q.cand[base + p] = v;
+        if (cached) s_vals[p - p_lo] = v;
+      }
+      const unsigned bal = __ballot_sync(0xffffffffu, rec[u] != 0);
+      rrank[u] = __popc(bal & ((1u << lane) - 1u));
+      if (lane == 0) S.cnt[u][wid] = uint16_t(__popc(bal));
+    }
+    __syncthreads();
+    {
+      int at = S.fg_n;
+#pragma unroll
+      for (int u = 0; u < kCmUnroll; ++u) {
+        int mine_base = at;
+        for (int w2 = 0; w2 < kCmThreads / 32; ++w2) {
+          const int c2 = S.cnt[u][w2];
+          if (w2 < wid) mine_base += c2;
+          at += c2;
+        }
+        if (rec[u]) {
+          const int slot = mine_base + rrank[u];
+          S.fg_idx[slot] = uint32_t(pb + u * kCmThreads + tid - p_lo);
+          S.fg_cls[slot] = uint16_t(rec[u]);
+          S.fg_obj[slot] = uint16_t(ob[u]);
+        }
+      }
+      __syncthreads();
+      if (tid == 0) S.fg_n = at;
+      __syncthreads();
+      if (at + kCmThreads * kCmUnroll > kCmFgCap) eval_foreground();  // CTA-uniform
+    }
   }
+  eval_foreground();
+
   double tot[4] = {a_loc, a_pos, a_neg, double(npos)};
   block_sum4_to_thread0(tot, S.red4);
   if (tid == 0) {
@@ -1531,7 +1595,7 @@ static Tiling choose_tiling(int C, int max_stages) {
 
 static size_t cm_smem_bytes(const LossParams& q, bool cached) {
   const size_t slice = (size_t(q.P) + q.cm_cluster - 1) / q.cm_cluster;
-  return ((sizeof(CmShared) + 127) & ~size_t(127)) + align_up(size_t(q.gmax) * 8, 128) + (cached ? slice * 4 : 0) + 128;
+  return ((sizeof(CmShared) + 127) & ~size_t(127)) + align_up(size_t(q.gmax) * 28, 128) + (cached ? slice * 4 : 0) + 128;
 }
 
 static int fill_params(const sbod_loss_desc* d, LossParams& q, bool need_scores) {

@@ -23,5 +23,9 @@ def detect_refine(predicted_locs, predicted_scores, min_score, max_overlap, top_
 
 
 def detect_objects(predicted_locs, predicted_scores, min_score, max_overlap, top_k, priors_cxcy):
-    """detect_tools.py:10-97 never returns (exit() at :69); parity UNPINNED — served by detect."""
-    return detect(predicted_locs, predicted_scores, min_score, max_overlap, top_k, priors_cxcy)
+    """detect_tools.py:10-97 never returns (exit() at :69); parity UNPINNED. Intended semantics as
+    models.utils.detect_objects: softmax, 'offset' decode, one candidate per prior (best foreground class),
+    one class-agnostic NMS, label = arg-max class."""
+    out = detect_batched(predicted_locs, predicted_scores, min_score, max_overlap, top_k, priors_cxcy,
+                         act="softmax", box_type="offset", class_agnostic=True)
+    return unpad_detections(out[0], out[1], out[2], out[4])

@@ -55,10 +55,10 @@ def compute_location(fmap_dims=FMAP_DIMS, device="cpu", image_size=None):
 def _cfg(config, key, default=None):
     try:
         return getattr(config, key)
-    except AttributeError:
+    except (AttributeError, KeyError):  # attribute-style dicts raise KeyError from __getattr__
         try:
             return config[key]
-        except (KeyError, TypeError):
+        except (KeyError, TypeError, IndexError):
             return default
 
 

@@ -13,10 +13,10 @@ from ..core import LossSpec, fused_loss
 def _cfg(config, key, default=None):
     try:
         return getattr(config, key)
-    except AttributeError:
+    except (AttributeError, KeyError):  # attribute-style dicts raise KeyError from __getattr__
         try:
             return config[key]
-        except (KeyError, TypeError):
+        except (KeyError, TypeError, IndexError):
             return default
 
 

@@ -9,7 +9,10 @@ def _cfg(config, key, default=None):
     try:
         return config[key]
     except (KeyError, TypeError, IndexError):
-        return getattr(config, key, default)
+        try:
+            return getattr(config, key)
+        except (AttributeError, KeyError):
+            return default
 
 
 def detect(predicted_locs, predicted_scores, min_score, max_overlap, top_k, priors_cxcy, config,
@@ -29,8 +32,16 @@ def detect(predicted_locs, predicted_scores, min_score, max_overlap, top_k, prio
 
 
 def detect_objects(predicted_locs, predicted_scores, min_score, max_overlap, top_k, priors_cxcy, config):
-    """Reference models/utils.py:87-178 is unreachable as written (IndexError at :136, index_select on
-    a 0/1 mask at :140-142, exit() at :152). Its intent — class-agnostic NMS on each prior's best
-    foreground score — has no runnable oracle, so parity is UNPINNED for this function. It is
-    served here by the per-class path the working models use (detect)."""
-    return detect(predicted_locs, predicted_scores, min_score, max_overlap, top_k, priors_cxcy, config)
+    """Reference models/utils.py:87-178 is unreachable as written (IndexError at :136, index_select on a
+    0/1 mask at :140-142, exit() at :152), so parity is UNPINNED. This is its intended semantics ("each
+    bounding box can only be assigned to one object", :92): every prior is ONE candidate scored with its best
+    foreground probability (:135); candidates above min_score go through one class-agnostic NMS (:145); a kept
+    box is labelled with its arg-max class (:147, read over the foreground columns: the class whose probability
+    ordered the NMS); [0,0,1,1]/0/0.0 placeholder and top_k as in detect (:154-172)."""
+    box_type = _cfg(config, "model")["box_type"]
+    focal_type = _cfg(config, "focal_type")
+    act = "sigmoid" if str(focal_type).lower() == "sigmoid" else "softmax"
+    clamp_inplace = box_type not in ("offset", "center")
+    out = detect_batched(predicted_locs, predicted_scores, min_score, max_overlap, top_k, priors_cxcy,
+                         act=act, box_type=box_type, clamp_inplace=clamp_inplace, class_agnostic=True)
+    return unpad_detections(out[0], out[1], out[2], out[4])

@@ -30,7 +30,7 @@ def test_header_symbols_are_exported(built):
     assert len(names) >= 25
     missing = [n for n in names if not hasattr(handle, n)]
     assert not missing, missing
-    assert handle.sbod_abi_version() == 1
+    assert handle.sbod_abi_version() == 2
 
 
 def test_binding_table_matches_header(built):

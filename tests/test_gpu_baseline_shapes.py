@@ -349,3 +349,84 @@ def test_second_device(dev):
     assert all(torch.equal(a, b) for a, b in zip(outs[0][2], outs[1][2]))
     with pytest.raises(S._lib.SbodError):  # mixed devices are rejected
         S.detect_batched(elocs.to(dev), escores.to(d1), 0.01, 0.45, 200, pri.to(dev))
+
+
+def test_detect_objects_class_agnostic(dev):
+    """detect_objects (models/utils.py:87-178, detect_tools.py:10-97): PARITY UNPINNED - the reference reaches
+    exit(); checked against the oracle's restatement of the intended semantics: one candidate per prior (best
+    foreground class), one class-agnostic NMS, label = arg-max class. SSD300 shape and config 2 shape."""
+    import torchvision
+    from oracle import box_pipeline as O
+    from shape_based_object_detection_b200 import priors as PR, synth
+    from shape_based_object_detection_b200.detect_scripts import detect_tools as DT
+    from shape_based_object_detection_b200.models import utils as MU
+    for table, Cn, N, bg, top_k in (("ssd300", 21, 3, 3.0, 200), ("ssd300", 21, 2, 3.0, 25), ("ssd512_canonical", 81, 2, 6.0, 200)):
+        pri = PR.PRIOR_TABLES[table]()
+        locs, scores = synth.make_eval_batch(pri, N, Cn, 97 + Cn, bg_bias=bg)
+        want = O.detect_objects(locs.clone(), scores, 0.05, 0.45, top_k, pri, nms_fn=torchvision.ops.nms)
+        got = MU.detect_objects(locs.to(dev), scores.to(dev), 0.05, 0.45, top_k, pri.to(dev), cfg(n_classes=Cn))
+        got2 = DT.detect_objects(locs.to(dev), scores.to(dev), 0.05, 0.45, top_k, pri.to(dev))
+        for i in range(N):
+            assert want[1][i].numel() > 5
+            for g in (got, got2):
+                assert torch.equal(g[1][i].cpu(), want[1][i]), (table, i)
+                assert torch.allclose(g[2][i].cpu(), want[2][i], rtol=1e-5, atol=1e-8)
+                assert torch.allclose(g[0][i].cpu(), want[0][i], rtol=1e-5, atol=1e-6)
+    # sigmoid scores, nothing above the threshold -> placeholder
+    pri = PR.ssd300_priors()
+    locs, scores = synth.make_eval_batch(pri, 2, 7, 5, bg_bias=0.0)
+    want = O.detect_objects(locs.clone(), scores - 12.0, 0.5, 0.45, 200, pri, focal_type="sigmoid")
+    got = MU.detect_objects(locs.to(dev), (scores - 12.0).to(dev), 0.5, 0.45, 200, pri.to(dev),
+                            cfg(n_classes=7, focal_type="sigmoid"))
+    for i in range(2):
+        assert got[1][i].tolist() == want[1][i].tolist() == [0]
+        assert got[0][i].cpu().tolist() == [[0.0, 0.0, 1.0, 1.0]]
+
+
+def test_second_band_when_candidates_run_out(dev):
+    """Config 2 shape, but every prior of two images decodes to one of a handful of boxes: NMS keeps a few boxes
+    per class, the first band of candidates (those above the per-image cutoff) runs out before top_k + 1 boxes
+    survive, and the NMS kernel must fetch the rest itself (second band) - exactly the reference's answer,
+    class-major because fewer than top_k boxes survive. A normal image sits between them."""
+    import torchvision
+    import shape_based_object_detection_b200 as S
+    from oracle import box_pipeline as O
+    from shape_based_object_detection_b200 import priors as PR, synth
+    pri = PR.ssd512_canonical_priors()
+    P = pri.size(0)
+    _, scores = synth.make_eval_batch(pri, 3, 81, 4321 + 9)
+    gen = torch.Generator().manual_seed(3)
+    base = torch.tensor([[0.10, 0.10, 0.30, 0.35], [0.55, 0.15, 0.90, 0.50]])  # two boxes: <= 160 survivors
+    locs = base[torch.randint(0, 2, (3, P), generator=gen)].contiguous()
+    locs[1] = torch.rand((P, 4), generator=gen) * 0.5
+    locs[1, :, 2:] += locs[1, :, :2] + 0.02  # a normal image: many distinct boxes
+    want = O.detect(locs.clone(), scores, 0.01, 0.45, 200, pri, box_type="corner", nms_fn=torchvision.ops.nms,
+                    return_priors=True)
+    for _ in range(2):  # twice: the workspace is left clean
+        got = S.detect_batched(locs.to(dev).contiguous(), scores.to(dev), 0.01, 0.45, 200, None, box_type="corner",
+                               clamp_inplace=True)
+        assert not _check_detect(got, want, 3)
+    assert want[1][0].numel() < 200 and want[1][2].numel() < 200 and want[1][1].numel() == 200
+
+
+def test_detect_tools_kept_list_spills_to_global_memory(dev):
+    """detect_tools: the FIRST (per-class) NMS stage may keep far more boxes than the second, class-agnostic one
+    lets through. 150 well-separated boxes x 80 classes, every class above min_score: 12 000 first-stage
+    survivors (more than the 5 120 that fit in shared memory) and 150 final boxes. The reference has no limit
+    here; the kept list spills to global memory."""
+    import torchvision
+    from oracle import box_pipeline as O
+    from shape_based_object_detection_b200.detect_scripts import detect_tools as DT
+    gen = torch.Generator().manual_seed(11)
+    n_pos, Cn = 150, 81
+    gx, gy = torch.meshgrid(torch.arange(15.), torch.arange(10.), indexing="ij")
+    x0, y0 = gx.reshape(-1) / 15.0, gy.reshape(-1) / 10.0
+    boxes = torch.stack([x0 + 0.005, y0 + 0.005, x0 + 0.055, y0 + 0.085], 1)[None].contiguous()  # [1,150,4]
+    scores = torch.randn((1, n_pos, Cn), generator=gen) * 0.05  # softmax ~ 1/81 = 0.0123 > 0.01 for (almost) all
+    want = O.detect(boxes.clone(), scores, 0.01, 0.45, 200, None, box_type="corner", second_nms=0.7,
+                    nms_fn=torchvision.ops.nms)
+    got = DT.detect_refine(boxes.to(dev).contiguous(), scores.to(dev), 0.01, 0.45, 200, None)
+    assert want[1][0].numel() == n_pos
+    assert torch.equal(got[1][0].cpu(), want[1][0])
+    assert torch.allclose(got[2][0].cpu(), want[2][0], rtol=1e-5, atol=1e-8)
+    assert torch.allclose(got[0][0].cpu(), want[0][0], rtol=1e-5, atol=1e-6)

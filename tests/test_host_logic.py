@@ -3,6 +3,7 @@
 import os
 
 import numpy as np
+import pytest
 import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
@@ -96,8 +97,30 @@ def test_bench_reference_arm_json_contract():
     assert "workload" in line["config"]
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0
     assert line["e2e"]["value"] == line["value"] and line["e2e"]["unit"] == line["unit"]
-    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    # "reference" when oracle/_ref holds the reference's own files (build container / shipped to the GPU box)
+    assert line["cpu_baseline"]["kind"] in ("port", "reference") and line["cpu_baseline"]["cores"] >= 1
     assert line["cpu_baseline"]["value"] == line["value"]
+    # both arms must describe the workload with the same `config` object
+    sys.path.insert(0, repo)
+    import bench
+    assert line["config"] == bench.config_entry(2)
+    for cid in bench.CONFIGS:
+        assert set(bench.config_entry(cid)) == {"workload", "config_id", "images_per_gpu", "l2"}
+
+
+def test_reference_runner_port_equals_reference_when_present():
+    """oracle/ref_runner.py: the reference's own code (oracle/_ref, when the build placed it there) and the
+    oracle port give the same loss on the same small batch, for every config the reference can run."""
+    from oracle import ref_runner as RR
+    from shape_based_object_detection_b200 import priors as PR, synth
+    if not RR.reference_available():
+        pytest.skip("oracle/_ref not present (the reference lives in the build container only)")
+    for cid, table, Cn, G in ((1, "ssd300", 21, 20), (2, "ssd512", 21, 30), (3, "retinanet", 21, 30)):
+        pri = PR.PRIOR_TABLES[table]()[::3].contiguous()
+        locs, scores, bx, lb = synth.make_train_batch(pri, 2, Cn, G, 50 + cid)
+        a = RR.Runner(cid, pri, Cn, use_reference=True).train((locs, scores), bx, lb)
+        b = RR.Runner(cid, pri, Cn, use_reference=False).train((locs, scores), bx, lb)
+        assert abs(a - b) <= 1e-6 * abs(a), (cid, a, b)
 
 
 def test_coco_format_results_matches_the_reference_loop():

@@ -79,17 +79,18 @@ d.locs, d.scores, d.priors_cxcy = el.data_ptr(), es.data_ptr(), pri_d.data_ptr()
 d.N, d.P, d.C = N, P, Cn
 d.act_kind, d.box_kind, d.clamp_inplace = 0, 0, 0
 d.min_score, d.max_overlap, d.top_k, d.second_nms_thr, d.pre_nms_topk = 0.01, 0.45, 200, -1.0, 0
+d.class_agnostic = 0
 d.out_boxes, d.out_labels, d.out_scores, d.out_prior, d.out_counts, d.out_cap = (
     ob.data_ptr(), ol.data_ptr(), osc.data_ptr(), op.data_ptr(), oc.data_ptr(), cap)
 nb = lib.sbod_detect_workspace_bytes(C.byref(d))
-ws = L.Workspace.get(dev, ("detect", N, P, Cn), nb, zero_bytes=lib.sbod_detect_workspace_zero_bytes(C.byref(d)))
+ws = L.Workspace.get(dev, "detect", nb, zero_bytes=lib.sbod_detect_workspace_zero_bytes(C.byref(d)), layout=(N, Cn))
 d.workspace, d.workspace_bytes = ws.data_ptr(), nb
 td = time_seq([lambda: L.check(lib.sbod_detect_stage(C.byref(d), 2, sp)),
                lambda: L.check(lib.sbod_detect_stage(C.byref(d), 3, sp)),
                lambda: L.check(lib.sbod_detect_stage(C.byref(d), 1, sp))])
 byt = N * P * Cn * 4
 print(f"shape {NAME} N={N} P={P} C={Cn} G<={G}  logits {byt/1e6:.1f} MB")
-for nm, ms in (("match_lse", t[0]), ("mine (+forced)", t[1]), ("fwd (2 kernels, python call)", tf[0]),
-               ("loss_bwd", tb[0]), ("detect sample pass", td[0]), ("detect_score main", td[1]),
-               ("detect_nms (+fallback)", td[2])):
+for nm, ms in (("match_lse", t[0]), ("classify_mine", t[1]), ("fwd (2 kernels, python call)", tf[0]),
+               ("loss_bwd", tb[0]), ("detect_bound (streaming)", td[0]), ("detect_refine", td[1]),
+               ("detect_nms", td[2])):
     print(f"{nm:32s} {ms*1e3:9.1f} us   {byt/ms/1e6:8.1f} GB/s of logits")
