@@ -47,6 +47,7 @@ SBOD_API const char* sbod_error_string(int code);
 /* Process-wide switches for A/B measurements (no reference counterpart). Defaults: all on. */
 #define SBOD_OPT_PDL 0           /* programmatic dependent launch between the kernels of one call */
 #define SBOD_OPT_PEER_EXCHANGE 1 /* one-shot NVLink exchange of the loss sums (sbod_comm_*) instead of the caller's all-reduce */
+#define SBOD_OPT_CM_CLUSTER 2    /* CTAs per image of the classify + mine kernel: 1, 2, 4, 8; 0 = automatic */
 SBOD_API int sbod_set_option(int key, int value);
 
 /* ------------------------------------------------------------------------------------------
@@ -238,6 +239,11 @@ typedef struct sbod_loss_desc {
    * under the logits stream). Passing the same pointer as grad_scores to sbod_loss_backward then
    * skips the zero-fill pass of the sparse backward. */
   float* grad_scores_prefill;
+  /* optional: device descriptor of a communicator (sbod_comm_device_ptr). If set, the forward all-reduces
+   * `sums` across the ranks of the communicator INSIDE its last kernel (one-shot exchange over NVLink peer
+   * memory) and forms `loss` from the global sums: no separate collective, no sbod_loss_finalize.
+   * Not allowed with SBOD_CLS_CE_MINE_BATCH (batch-global mining does not shard). */
+  const void* comm;
 } sbod_loss_desc;
 
 SBOD_API size_t sbod_loss_workspace_bytes(const sbod_loss_desc* d);
@@ -311,6 +317,14 @@ SBOD_API int sbod_detect(const sbod_detect_desc* d, sbod_stream_t stream);
  *   0 = bound pass + refine, 1 = NMS, 2 = bound pass only, 3 = refine only, 4 = refine + NMS.
  * sbod_detect == stage 2 followed by stage 4 in stream order. */
 SBOD_API int sbod_detect_stage(const sbod_detect_desc* d, int stage, sbod_stream_t stream);
+/* The class probabilities exactly as sbod_detect evaluates them (softmax / sigmoid over the C columns, as
+ * models/utils.py:201-204), scores [N,P,C] -> out [N,P,C]. The kept (class, prior) sequence of sbod_detect is
+ * bit-exact GIVEN these score bits; the bits themselves agree with torch's CPU softmax to a few ulp (an
+ * accurate exp and a true division, but another summation order), so two same-class candidates whose scores
+ * differ by an ulp or two can swap places with respect to a CPU run. Tests use this entry point to check the
+ * two statements separately. */
+SBOD_API int sbod_detect_probabilities(const float* scores, int N, int P, int C, int act_kind, float* out,
+                              sbod_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * Anchor-free (FCOS) targets + loss + post-processing. The reference's FCOSLoss / FCOS.postprocess
@@ -344,6 +358,7 @@ typedef struct sbod_fcos_desc {
   float* loss;    /* [4] total, conf, loc, center */
   void* workspace;
   size_t workspace_bytes;
+  const void* comm; /* optional communicator (see sbod_loss_desc.comm): sums all-reduced inside sbod_fcos_forward */
 } sbod_fcos_desc;
 SBOD_API size_t sbod_fcos_workspace_bytes(const sbod_fcos_desc* d);
 SBOD_API int sbod_fcos_forward(const sbod_fcos_desc* d, sbod_stream_t stream);
@@ -355,6 +370,27 @@ SBOD_API int sbod_fcos_backward(const sbod_fcos_desc* d, const float* grad_loss,
 SBOD_API int sbod_fcos_postprocess(const float* box_pred, const float* cls_pred, const float* center_pred,
                           const float* locations, int N, int P, int C, float* out_locs,
                           float* out_scores, sbod_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Communicator for the one exchange of the path: the loss sums of a batch that is
+ * sharded by image over the GPUs of one node, one process per GPU. No reference counterpart (the
+ * reference is single-GPU); it replaces the NCCL all-reduce a host would otherwise issue between the
+ * forward and the backward. Mailboxes in each GPU's HBM, mapped into every process with CUDA IPC; the
+ * kernels post their sums into all mailboxes with plain stores over NVLink / NVSwitch and add the
+ * contributions in rank order (bit-identical on every rank).
+ *   sbod_comm_create   on the current device; writes this rank's IPC handle (sbod_comm_handle_bytes() bytes,
+ *                      host memory) - gather the handles of all ranks (e.g. torch.distributed.all_gather) -
+ *   sbod_comm_connect  opens the peers' mailboxes; afterwards sbod_comm_device_ptr(comm) goes into
+ *                      sbod_loss_desc.comm / sbod_fcos_desc.comm.
+ *   sbod_comm_allreduce stand-alone sum of k <= 7 doubles (device pointer) through the same mailboxes (tests).
+ * Every rank must issue the same sequence of exchanging calls.
+ * ---------------------------------------------------------------------------------------- */
+SBOD_API size_t sbod_comm_handle_bytes(void);
+SBOD_API int sbod_comm_create(int rank, int world, void** comm_out, void* handle_out_host);
+SBOD_API int sbod_comm_connect(void* comm, const void* all_handles_host);
+SBOD_API const void* sbod_comm_device_ptr(void* comm);
+SBOD_API int sbod_comm_allreduce(void* comm, double* vals_dev, int k, sbod_stream_t stream);
+SBOD_API int sbod_comm_destroy(void* comm);
 
 /* ------------------------------------------------------------------------------------------
  * metrics.calculate_mAP (metrics.py:8-145): VOC07 11-point interpolated average precision per class

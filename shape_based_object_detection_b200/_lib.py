@@ -30,7 +30,9 @@ EXPORTS = [
     "sbod_match_workspace_bytes", "sbod_match", "sbod_loss_workspace_bytes", "sbod_loss_workspace_zero_bytes",
     "sbod_workspace_init", "sbod_set_option",
     "sbod_loss_forward", "sbod_loss_forward_stage", "sbod_detect_stage", "sbod_loss_finalize", "sbod_loss_backward", "sbod_loss_targets",
-    "sbod_detect_workspace_bytes", "sbod_detect_workspace_zero_bytes", "sbod_detect",
+    "sbod_detect_workspace_bytes", "sbod_detect_workspace_zero_bytes", "sbod_detect", "sbod_detect_probabilities",
+    "sbod_comm_handle_bytes", "sbod_comm_create", "sbod_comm_connect", "sbod_comm_device_ptr", "sbod_comm_allreduce",
+    "sbod_comm_destroy",
     "sbod_loss_forward_host_arena_bytes", "sbod_loss_forward_host",
     "sbod_fcos_workspace_bytes", "sbod_fcos_forward", "sbod_fcos_finalize", "sbod_fcos_backward", "sbod_fcos_postprocess",
     "sbod_selftest_div", "sbod_map_workspace_bytes", "sbod_map", "sbod_bce_focal", "sbod_diou_nms",
@@ -50,7 +52,7 @@ class LossDesc(C.Structure):
         ("ov", C.c_void_p), ("obj", C.c_void_p), ("lse", C.c_void_p), ("ce", C.c_void_p),
         ("sel", C.c_void_p), ("partials", C.c_void_p), ("sums", C.c_void_p), ("loss", C.c_void_p),
         ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t),
-        ("grad_scores_prefill", C.c_void_p),
+        ("grad_scores_prefill", C.c_void_p), ("comm", C.c_void_p),
     ]
 
 
@@ -75,7 +77,7 @@ class FcosDesc(C.Structure):
         ("N", C.c_int32), ("P", C.c_int32), ("C", C.c_int32), ("center_sample", C.c_int32),
         ("reg_weight", C.c_float), ("focal_alpha", C.c_float), ("focal_gamma", C.c_float),
         ("lab", C.c_void_p), ("tgt", C.c_void_p), ("sums", C.c_void_p), ("loss", C.c_void_p),
-        ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t),
+        ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t), ("comm", C.c_void_p),
     ]
 
 
@@ -122,6 +124,11 @@ def _declare(lib):
         "sbod_loss_backward": [C.POINTER(LossDesc), vp, vp, vp, vp],
         "sbod_loss_targets": [C.POINTER(LossDesc), vp, vp, vp],
         "sbod_detect": [C.POINTER(DetectDesc), vp],
+        "sbod_detect_probabilities": [vp, i32, i32, i32, i32, vp, vp],
+        "sbod_comm_create": [i32, i32, C.POINTER(vp), vp],
+        "sbod_comm_connect": [vp, vp],
+        "sbod_comm_allreduce": [vp, vp, i32, vp],
+        "sbod_comm_destroy": [vp],
         "sbod_loss_forward_host": [C.POINTER(LossDesc), i32, vp, vp, sz, vp],
         "sbod_fcos_forward": [C.POINTER(FcosDesc), vp],
         "sbod_fcos_finalize": [C.POINTER(FcosDesc), vp],
@@ -143,10 +150,16 @@ def _declare(lib):
         "sbod_loss_forward_host_arena_bytes": [C.POINTER(LossDesc), i32],
         "sbod_fcos_workspace_bytes": [C.POINTER(FcosDesc)],
         "sbod_map_workspace_bytes": [i32],
+        "sbod_comm_handle_bytes": [],
     }.items():
         fn = getattr(lib, name)
         fn.argtypes = args
         fn.restype = C.c_size_t
+
+
+def _declare_ptr_returns(lib):
+    lib.sbod_comm_device_ptr.argtypes = [C.c_void_p]
+    lib.sbod_comm_device_ptr.restype = C.c_void_p
 
 
 def lib():
@@ -161,6 +174,7 @@ def lib():
                         "shape_based_object_detection_b200/csrc/build.sh (no CPU fallback exists)")
                 handle = C.CDLL(LIB_PATH)
                 _declare(handle)
+                _declare_ptr_returns(handle)
                 if handle.sbod_abi_version() != 2:
                     raise SbodError("libsbod.so ABI version mismatch")
                 _lib = handle

@@ -47,7 +47,7 @@ class LossState:
     """Per-call device state of one fused loss evaluation (kept alive for backward / inspection)."""
 
     def __init__(self, spec, priors_cxcy, priors_xy, locs, scores, gt, anchors_xy=None, exclude=None,
-                 prefill_grad=False):
+                 prefill_grad=False, comm=None):
         self.spec = spec
         dev = scores.device
         N, P, Cn = scores.shape
@@ -92,6 +92,9 @@ class LossState:
         # the gradient wrt the logits is zero almost everywhere: let the forward stream zero-fill it
         self.grad_scores = torch.empty_like(scores) if prefill_grad else None
         d.grad_scores_prefill = self.grad_scores.data_ptr() if prefill_grad else None
+        # sharded batch: the forward's last kernel all-reduces `sums` itself over the NVLink mailboxes
+        self.comm = comm
+        d.comm = comm.ptr if comm is not None else None
         self.desc = d
 
     def forward(self):
@@ -148,8 +151,8 @@ class _FusedLossFn(torch.autograd.Function):
     def forward(ctx, locs, scores, holder):
         state = holder["make_state"](locs, scores)
         state.forward()
-        if holder.get("group") is not None:
-            _all_reduce_sums(state, holder["group"])
+        if holder.get("group") is not None and state.comm is None:
+            _all_reduce_sums(state, holder["group"])  # NCCL path (peer exchange disabled or unavailable)
         holder["state"] = state
         ctx.state = state
         return state.loss[0].clone()
@@ -185,9 +188,14 @@ def fused_loss(spec, priors_cxcy, priors_xy, predicted_locs, predicted_scores, b
     prefill = bool(predicted_scores.requires_grad and torch.is_grad_enabled()
                    and spec.cls_kind in (L.CLS_CE_MINE_NONPOS, L.CLS_CE_MINE_NEG, L.CLS_CE_MINE_BATCH))
 
+    comm = None
+    if group is not None:
+        from .parallel import peer_exchange
+        comm = peer_exchange(group, dev)
+
     def make_state(locs, scores):
         return LossState(spec, priors_cxcy, priors_xy, L.f32c(locs.detach()), L.f32c(scores.detach()), gt,
-                         anchors_xy=anchors_xy, exclude=exclude, prefill_grad=prefill)
+                         anchors_xy=anchors_xy, exclude=exclude, prefill_grad=prefill, comm=comm)
 
     holder["make_state"] = make_state
     return _FusedLossFn.apply(predicted_locs, predicted_scores, holder)

@@ -21,6 +21,7 @@
 //                        exactly as the reference does.
 #include <math.h>
 #include <stdlib.h>
+#include <string.h>
 
 #include "common.cuh"
 #include "row_stream.cuh"
@@ -109,26 +110,27 @@ SBOD_DEVINL int k32_bin(const DetParams& q, uint32_t k32) {
 
 // ------------------------------------------------------------------------------------------
 // detect_bound_kernel — the streaming pass of the eval path. The logits go HBM -> shared memory exactly
-// once (bulk TMA through an mbarrier ring, same tiles as the train kernel); one thread per prior row
-// takes the maximum foreground logit and turns it into an UPPER BOUND of the row's best foreground
-// probability:  softmax: p_k = e^{x_k} / sum_j e^{x_j} <= e^{x_k} / (e^{x_0} + e^{x_k}) = sigmoid(x_k - x_0);
-// sigmoid: p_k = sigmoid(x_k); none: p_k = x_k. Two instructions per logit (load + max) instead of the
-// ~8 a full softmax costs, so the pass is bound by HBM, not by instruction issue. It writes the bound
-// (4 bytes per prior) and a per-image histogram of the bounds in the bins of the candidate keys.
-// The exact probabilities are then computed only for the rows whose bound can matter
-// (detect_refine_kernel), which is exact: a row's candidates all lie below its bound.
+// once (bulk TMA through an mbarrier ring, same 128-row tiles and two-threads-per-row layout as the train
+// kernel). Per prior row it computes the row's BEST FOREGROUND PROBABILITY in one pass — softmax:
+// max_k exp(x_k - x_0) / sum_j exp(x_j - x_0), shifted by the row's own background logit so that neither a
+// separate max pass nor a per-class compare / mask is needed (5 instructions per logit instead of ~8);
+// sigmoid: sigmoid(max_k x_k); none: max_k x_k — inflated by a small slack so that it is an UPPER BOUND of
+// every probability the exact evaluation can produce for the row. It writes the bound (4 bytes per prior)
+// and a per-image histogram of the bounds in the bins of the candidate keys. The exact probabilities are
+// then computed only for the rows whose bound can matter (detect_refine_kernel) — exact, because a row's
+// candidates all lie below its bound.
 // ------------------------------------------------------------------------------------------
-constexpr int kBThreads = 128;
-constexpr float kBoundSlack = 1.00002f;  // covers the rounding of the bound and of the exact probabilities
+constexpr float kBoundSlack = 1.00002f;  // covers ex2.approx / summation-order differences to the exact evaluation
 
-__global__ void __launch_bounds__(kBThreads) detect_bound_kernel(const DetParams q) {
+template <int kC>  // kC > 0: compile-time class count (unrolled); 0: run-time
+__global__ void __launch_bounds__(kStreamThreads, 2) detect_bound_kernel(const DetParams q) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   float* stages = reinterpret_cast<float*>(smem_raw);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + size_t(q.n_stages) * q.stage_floats * 4);
   __shared__ unsigned int s_hist[kMaxBins];
 
-  const int tid = threadIdx.x, lane = tid & 31;
-  const int C = q.C;
+  const int tid = threadIdx.x;
+  const int C = kC ? kC : q.C;
   int t0, t1;
   tile_range(q.n_tiles, blockIdx.x, gridDim.x, t0, t1);
   const int n_my = t1 - t0;
@@ -137,23 +139,22 @@ __global__ void __launch_bounds__(kBThreads) detect_bound_kernel(const DetParams
     for (int s = 0; s < q.n_stages; ++s) mbar_init(&bars[s], 1);
     fence_mbar_init();
   }
-  for (int b = tid; b < q.n_bins; b += kBThreads) s_hist[b] = 0u;
+  for (int b = tid; b < q.n_bins; b += kStreamThreads) s_hist[b] = 0u;
   __syncthreads();
   if (tid == 0) {
     for (int s = 0; s < q.n_stages && s < n_my; ++s)
-      stream_issue(q.scores, q.N, q.P, C, stream_tile(t0 + s, q.tiles_per_image, q.rows_per_tile, q.P),
+      stream_issue(q.scores, q.N, q.P, C, stream_tile(t0 + s, q.tiles_per_image, kTileRows, q.P),
                    stages + size_t(s) * q.stage_floats, &bars[s]);
   }
-  // rotation that makes the per-thread row walk bank-conflict free for even C
-  int gcd = 1;
-  while (gcd < 32 && (C % (gcd * 2)) == 0) gcd *= 2;
-  const int rot = (lane * gcd) >> 5;
-  const float NEG = -__int_as_float(0x7f800000);
+  int row, h;
+  stream_map(tid, row, h);
+  const int nh = (C + 1 - h) >> 1;
+  const float INF = __int_as_float(0x7f800000);
 
   auto flush_hist = [&](int n) {
     __syncthreads();
     unsigned int* gh = q.rhist + size_t(n) * kMaxBins;
-    for (int b = tid; b < q.n_bins; b += kBThreads) {
+    for (int b = tid; b < q.n_bins; b += kStreamThreads) {
       const unsigned int v = s_hist[b];
       if (v) {
         atomicAdd(&gh[b], v);
@@ -170,8 +171,8 @@ __global__ void __launch_bounds__(kBThreads) detect_bound_kernel(const DetParams
   uint32_t ring_parity = 0;
   for (int it = 0; it < n_my; ++it) {
     const int n = cur_n;
-    const int p0 = cur_t * q.rows_per_tile;
-    const int rows = min(q.rows_per_tile, q.P - p0);
+    const int p0 = cur_t * kTileRows;
+    const int rows = min(kTileRows, q.P - p0);
     if (++cur_t == q.tiles_per_image) {
       cur_t = 0;
       ++cur_n;
@@ -180,52 +181,94 @@ __global__ void __launch_bounds__(kBThreads) detect_bound_kernel(const DetParams
       if (hist_n >= 0) flush_hist(hist_n);
       hist_n = n;
     }
+    const bool valid = row < rows;
+    const int r = min(row, rows - 1);  // keep every lane in the shuffles
+    const size_t np = size_t(n) * q.P + p0 + r;
+    if (valid && h == 0 && q.clamp_inplace) {  // clamp_ on the caller's tensor (models/utils.py:224, detect_tools.py:264)
+      float4* lp = reinterpret_cast<float4*>(q.locs) + np;
+      float4 b = *lp;
+      b.x = fminf(fmaxf(b.x, 0.f), 1.f); b.y = fminf(fmaxf(b.y, 0.f), 1.f);
+      b.z = fminf(fmaxf(b.z, 0.f), 1.f); b.w = fminf(fmaxf(b.w, 0.f), 1.f);
+      *lp = b;
+    }
     float* stage = stages + size_t(ring_s) * q.stage_floats;
     mbar_wait(&bars[ring_s], ring_parity);
     const uint32_t head = ((uint32_t(n) * uint32_t(q.P) + uint32_t(p0)) * uint32_t(C)) & 3u;
-    for (int r = tid; r < rows; r += kBThreads) {
-      const int p = p0 + r;
-      const size_t np = size_t(n) * q.P + p;
-      if (q.clamp_inplace) {  // clamp_ on the caller's tensor (models/utils.py:224, detect_tools.py:264)
-        float4* lp = reinterpret_cast<float4*>(q.locs) + np;
-        float4 b = *lp;
-        b.x = fminf(fmaxf(b.x, 0.f), 1.f); b.y = fminf(fmaxf(b.y, 0.f), 1.f);
-        b.z = fminf(fmaxf(b.z, 0.f), 1.f); b.w = fminf(fmaxf(b.w, 0.f), 1.f);
-        *lp = b;
-      }
-      const float* row = stage + head + size_t(r) * C;
-      // maximum over the foreground logits, four independent chains, rotated start
-      float m0 = NEG, m1 = NEG, m2 = NEG, m3 = NEG;
-      int k = rot > 1 ? rot : 1;
-      for (; k + 3 < C; k += 4) {
-        m0 = fmaxf(m0, row[k]);
-        m1 = fmaxf(m1, row[k + 1]);
-        m2 = fmaxf(m2, row[k + 2]);
-        m3 = fmaxf(m3, row[k + 3]);
-      }
-      for (; k < C; ++k) m0 = fmaxf(m0, row[k]);
-      for (k = 1; k < rot; ++k) m1 = fmaxf(m1, row[k]);
-      const float mx = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
-      float pb;
-      if (q.act_kind == SBOD_ACT_SOFTMAX) pb = __frcp_rn(1.f + __expf(row[0] - mx));
-      else if (q.act_kind == SBOD_ACT_SIGMOID) pb = __frcp_rn(1.f + __expf(-mx));
-      else pb = mx;
-      pb = pb * kBoundSlack;
-      if (!(pb == pb)) pb = 2.f;  // a NaN in the row: never skip it
+    const float* rbase = stage + head + r * C;
+    float pb;
+    if (q.act_kind == SBOD_ACT_SOFTMAX) {
+      const float x0 = rbase[0];
+      float sum, fgmax;
+      pair_row_sum_fgmax<kC>(rbase, h, C, -x0 * kLog2e, sum, fgmax);
+      pb = fgmax * __frcp_rn(sum);
+      if (!(sum < INF) || !(pb == pb)) pb = 2.f;  // overflow (a logit > background + 88) or NaN: always evaluate the row
+    } else {
+      // maximum foreground logit of this thread's elements rp[0], rp[2], ... (element 0 of parity 0 = background)
+      const float* rp = rbase + h;
+      float m = -INF;
+      for (int j = (h == 0 ? 1 : 0); j < nh; ++j) m = fmaxf(m, rp[2 * j]);
+      m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 1));
+      pb = q.act_kind == SBOD_ACT_SIGMOID ? __frcp_rn(1.f + __expf(-m)) : m;
+      if (!(pb == pb)) pb = 2.f;
+    }
+    pb = pb * kBoundSlack;
+    if (valid && h == 0) {
       if (q.prior_keep && q.prior_keep[np] == 0) pb = -1.f;  // filtered prior: never a candidate
       q.pbound[np] = pb;
       if (pb > q.min_score) atomicAdd(&s_hist[k32_bin(q, score_k32(pb))], 1u);
     }
     __syncthreads();  // every thread is done with the stage
     if (tid == 0 && it + q.n_stages < n_my)
-      stream_issue(q.scores, q.N, q.P, C, stream_tile(t0 + it + q.n_stages, q.tiles_per_image, q.rows_per_tile, q.P),
-                   stage, &bars[ring_s]);
+      stream_issue(q.scores, q.N, q.P, C, stream_tile(t0 + it + q.n_stages, q.tiles_per_image, kTileRows, q.P), stage,
+                   &bars[ring_s]);
     if (++ring_s == q.n_stages) {
       ring_s = 0;
       ring_parity ^= 1u;
     }
   }
   if (hist_n >= 0) flush_hist(hist_n);
+}
+
+// Generic bound pass (C > 128): one warp per prior row straight from global memory (coalesced over classes).
+__global__ void __launch_bounds__(256) detect_bound_generic_kernel(const DetParams q) {
+  const int lane = threadIdx.x & 31;
+  const size_t total = size_t(q.N) * q.P;
+  const float INF = __int_as_float(0x7f800000);
+  for (size_t np = (size_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5; np < total;
+       np += (size_t(gridDim.x) * blockDim.x) >> 5) {
+    const float* x = q.scores + np * size_t(q.C);
+    if (lane == 0 && q.clamp_inplace) {
+      float4* lp = reinterpret_cast<float4*>(q.locs) + np;
+      float4 b = *lp;
+      b.x = fminf(fmaxf(b.x, 0.f), 1.f); b.y = fminf(fmaxf(b.y, 0.f), 1.f);
+      b.z = fminf(fmaxf(b.z, 0.f), 1.f); b.w = fminf(fmaxf(b.w, 0.f), 1.f);
+      *lp = b;
+    }
+    float m = -INF, mall = -INF;
+    for (int k = lane; k < q.C; k += 32) {
+      const float v = x[k];
+      mall = fmaxf(mall, v);
+      if (k >= 1) m = fmaxf(m, v);
+    }
+    m = warp_max(m);
+    mall = warp_max(mall);
+    float pb;
+    if (q.act_kind == SBOD_ACT_SOFTMAX) {
+      float s = 0.f;
+      for (int k = lane; k < q.C; k += 32) s += __expf(x[k] - mall);
+      s = warp_sum(s);
+      pb = __expf(m - mall) / s;
+    } else {
+      pb = q.act_kind == SBOD_ACT_SIGMOID ? __frcp_rn(1.f + __expf(-m)) : m;
+    }
+    if (!(pb == pb)) pb = 2.f;
+    pb *= kBoundSlack;
+    if (lane == 0) {
+      if (q.prior_keep && q.prior_keep[np] == 0) pb = -1.f;
+      q.pbound[np] = pb;
+      if (pb > q.min_score) atomicAdd(&q.rhist[size_t(np / q.P) * kMaxBins + k32_bin(q, score_k32(pb))], 1u);
+    }
+  }
 }
 
 // Per-image cutoff from the histogram of the row bounds: the smallest bin count `cb` such that at least
@@ -280,33 +323,58 @@ __device__ unsigned int compute_cutoff(const DetParams& q, int n, unsigned int* 
 // `count` consecutive slots, called by lane 0) / `put` (slot, key). Class-agnostic mode emits the row's
 // best foreground class once, with class field 1, and records the arg-max class.
 // ------------------------------------------------------------------------------------------
+constexpr int kRowRegs = 4;  // classes per lane kept in registers (C <= 128); larger rows are re-read (L1)
+
+// the row's activation, as torch computes it: values of this lane's classes lane, lane + 32, ...
+struct RowProbs {
+  float x[kRowRegs];
+  float mx, sum;
+};
+SBOD_DEVINL void row_load(const DetParams& q, const float* __restrict__ x, int lane, RowProbs& R) {
+  const float NEG = -__int_as_float(0x7f800000);
+#pragma unroll
+  for (int j = 0; j < kRowRegs; ++j) {
+    const int k = lane + 32 * j;
+    R.x[j] = k < q.C ? ld_stream_f32(x + k) : NEG;
+  }
+}
+SBOD_DEVINL void row_prepare(const DetParams& q, const float* __restrict__ x, int lane, RowProbs& R) {
+  const float NEG = -__int_as_float(0x7f800000);
+  R.mx = 0.f;
+  R.sum = 1.f;
+  if (q.act_kind != SBOD_ACT_SOFTMAX) return;
+  float m = NEG;
+#pragma unroll
+  for (int j = 0; j < kRowRegs; ++j) m = fmaxf(m, R.x[j]);
+  for (int k = lane + 32 * kRowRegs; k < q.C; k += 32) m = fmaxf(m, x[k]);
+  R.mx = warp_max(m);
+  float s = 0.f;
+#pragma unroll
+  for (int j = 0; j < kRowRegs; ++j)
+    if (lane + 32 * j < q.C) s += expf(R.x[j] - R.mx);
+  for (int k = lane + 32 * kRowRegs; k < q.C; k += 32) s += expf(x[k] - R.mx);
+  R.sum = warp_sum(s);
+}
+SBOD_DEVINL float row_prob(const DetParams& q, const RowProbs& R, float v) {
+  if (q.act_kind == SBOD_ACT_SOFTMAX) return __fdiv_rn(expf(v - R.mx), R.sum);
+  if (q.act_kind == SBOD_ACT_SIGMOID) return __fdiv_rn(1.f, 1.f + expf(-v));
+  return v;
+}
+
 template <typename Reserve, typename Put>
-SBOD_DEVINL void eval_row(const DetParams& q, int n, int p, int lane, uint32_t k_lo, uint32_t k_hi,
+SBOD_DEVINL void eval_row(const DetParams& q, int n, int p, int lane, uint32_t k_lo, uint32_t k_hi, RowProbs& R,
                           Reserve&& reserve, Put&& put) {
   const int C = q.C;
   const float* x = q.scores + (size_t(n) * q.P + p) * size_t(C);
-  const float NEG = -__int_as_float(0x7f800000);
-  float mx = 0.f, sum = 1.f;
-  if (q.act_kind == SBOD_ACT_SOFTMAX) {
-    float m = NEG;
-    for (int k = lane; k < C; k += 32) m = fmaxf(m, x[k]);
-    mx = warp_max(m);
-    float s = 0.f;
-    for (int k = lane; k < C; k += 32) s += expf(x[k] - mx);
-    sum = warp_sum(s);
-  }
-  auto prob = [&](int k) -> float {
-    const float v = x[k];
-    if (q.act_kind == SBOD_ACT_SOFTMAX) return __fdiv_rn(expf(v - mx), sum);
-    if (q.act_kind == SBOD_ACT_SIGMOID) return __fdiv_rn(1.f, 1.f + expf(-v));
-    return v;
-  };
+  row_prepare(q, x, lane, R);
+  const int n_chunks = (C + 31) >> 5;
   if (q.agnostic) {
     // best foreground class of the row, first index among ties (torch.max, models/utils.py:135)
     unsigned long long best = 0ull;  // (probability bits : ~class): max = best probability, then lowest class
-    for (int k = lane; k < C; k += 32) {
-      if (k == 0) continue;
-      const float pr = prob(k);
+    for (int j = 0; j < n_chunks; ++j) {
+      const int k = lane + 32 * j;
+      if (k == 0 || k >= C) continue;
+      const float pr = row_prob(q, R, j < kRowRegs ? R.x[j < kRowRegs ? j : 0] : x[k]);
       if (pr > q.min_score) {
         const unsigned long long key = (static_cast<unsigned long long>(__float_as_uint(pr)) << 32) | (0xffffffffu - unsigned(k));
         if (key > best) best = key;
@@ -317,28 +385,30 @@ SBOD_DEVINL void eval_row(const DetParams& q, int n, int p, int lane, uint32_t k
       const unsigned long long other = __shfl_xor_sync(0xffffffffu, best, o);
       if (other > best) best = other;
     }
-    if (best != 0ull) {
+    if (best != 0ull && lane == 0) {
       const float pr = __uint_as_float(uint32_t(best >> 32));
       const int cls = int(0xffffffffu - uint32_t(best & 0xffffffffull));
       const uint32_t k32 = score_k32(pr);
       if (k32 >= k_lo && k32 < k_hi) {
-        unsigned int slot = 0;
-        if (lane == 0) {
-          slot = reserve(1u);
-          put(slot, (static_cast<unsigned long long>(k32) << 32) | (1ull << kPriorBits) | static_cast<unsigned long long>(p));
-          q.agn_label[size_t(n) * q.P + p] = cls;
-        }
+        const unsigned int slot = reserve(1u);
+        put(slot, (static_cast<unsigned long long>(k32) << 32) | (1ull << kPriorBits) | static_cast<unsigned long long>(p));
+        q.agn_label[size_t(n) * q.P + p] = cls;
       }
     }
     return;
   }
-  for (int kb = 0; kb < C; kb += 32) {
-    const int k = kb + lane;
-    float pr = 0.f;
+  for (int j = 0; j < n_chunks; ++j) {
+    const int k = lane + 32 * j;
     bool is = false;
     uint32_t k32 = 0;
     if (k < C && k >= 1) {
-      pr = prob(k);
+      float v;
+      if (j == 0) v = R.x[0];
+      else if (j == 1) v = R.x[1];
+      else if (j == 2) v = R.x[2];
+      else if (j == 3) v = R.x[3];
+      else v = x[k];
+      const float pr = row_prob(q, R, v);
       k32 = score_k32(pr);
       is = pr > q.min_score && k32 >= k_lo && k32 < k_hi;
     }
@@ -365,7 +435,7 @@ SBOD_DEVINL void eval_row(const DetParams& q, int n, int p, int lane, uint32_t k
 // accumulated in shared memory and flushed once.
 // ------------------------------------------------------------------------------------------
 constexpr int kRefThreads = 256;
-constexpr int kRefRows = 2048;
+constexpr int kRefRows = 512;
 constexpr int kRefKeyBuf = 3072;
 
 __global__ void __launch_bounds__(kRefThreads) detect_refine_kernel(const DetParams q) {
@@ -413,7 +483,18 @@ __global__ void __launch_bounds__(kRefThreads) detect_refine_kernel(const DetPar
     else if ((long long)(slot - unsigned(kRefKeyBuf)) < q.cand_cap) g_list[slot - unsigned(kRefKeyBuf)] = key;
     atomicAdd(&s_hist[k32_bin(q, uint32_t(key >> 32))], 1u);
   };
-  for (int i = wid; i < n_rows; i += kRefThreads / 32) eval_row(q, n, s_rows[i], lane, 0u, cut, reserve, put);
+  // a warp per row; the next row's logits are requested before the current row is evaluated
+  {
+    RowProbs cur, nxt;
+    int i = wid;
+    if (i < n_rows) row_load(q, q.scores + (size_t(n) * q.P + s_rows[i]) * size_t(q.C), lane, cur);
+    for (; i < n_rows; i += kRefThreads / 32) {
+      const int i2 = i + kRefThreads / 32;
+      if (i2 < n_rows) row_load(q, q.scores + (size_t(n) * q.P + s_rows[i2]) * size_t(q.C), lane, nxt);
+      eval_row(q, n, s_rows[i], lane, 0u, cut, cur, reserve, put);
+      cur = nxt;
+    }
+  }
   __syncthreads();
   // hand the buffered keys and the histogram over: one global atomic for the CTA's keys
   const unsigned int have = s_hole != 0xffffffffu ? s_hole : min(s_ncand, unsigned(kRefKeyBuf));
@@ -983,7 +1064,11 @@ __global__ void __launch_bounds__(kNmsThreads) detect_nms_kernel(const DetParams
         atomicAdd(&g_hist[k32_bin(q, uint32_t(key >> 32))], 1u);
       };
       for (int p = wid; p < q.P; p += kNmsThreads / 32)
-        if (q.pbound[size_t(n) * q.P + p] > q.min_score) eval_row(q, n, p, lane, cut, 0xffffffffu, reserve, put);
+        if (q.pbound[size_t(n) * q.P + p] > q.min_score) {
+          RowProbs R;
+          row_load(q, q.scores + (size_t(n) * q.P + p) * size_t(q.C), lane, R);
+          eval_row(q, n, p, lane, cut, 0xffffffffu, R, reserve, put);
+        }
       __threadfence();
       __syncthreads();
       raw_total = *reinterpret_cast<volatile unsigned int*>(&q.cand_count[n]);
@@ -1191,35 +1276,39 @@ static int detect_run(const sbod_detect_desc* d, sbod_stream_t stream, int stage
   q.rows_target = 4 * (q.top_k + 1) + 1024;
   if (q.pre_nms_topk > 0 || q.second_thr >= 0.f) q.rows_target *= 2;
 
-  // bound pass tiling: 128-row tiles (one thread per row), several rows per thread when the rows are short,
-  // fewer rows when a tile would not fit; as many ring stages as fit in ~100 KB (two CTAs per SM)
+  // bound pass tiling: 128-row tiles, two threads per row; as many ring stages as fit in ~100 KB (two CTAs per SM)
+  const bool fast = q.C <= 128;
+  q.rows_per_tile = kTileRows;
+  q.stage_floats = uint32_t(align_up(size_t(kTileRows) * q.C + 8, 32));
   {
-    const size_t row_bytes = size_t(q.C) * 4;
-    int rows = kBThreads;
-    while (rows < 1024 && size_t(rows) * 2 * row_bytes <= 24 * 1024) rows *= 2;
-    while (rows > 1 && size_t(rows) * row_bytes + 32 > 96 * 1024) rows /= 2;
-    q.rows_per_tile = rows;
-    q.stage_floats = uint32_t(align_up(size_t(rows) * q.C + 8, 32));
     const size_t sb = size_t(q.stage_floats) * 4;
     q.n_stages = int((100 * 1024) / sb);
     if (q.n_stages > 4) q.n_stages = 4;
     if (q.n_stages < 1) q.n_stages = 1;
-    q.tiles_per_image = (q.P + rows - 1) / rows;
-    q.n_tiles = q.tiles_per_image * q.N;
   }
+  q.tiles_per_image = (q.P + kTileRows - 1) / kTileRows;
+  q.n_tiles = q.tiles_per_image * q.N;
 
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   static DeviceOnce attr_once;
   if (attr_once.pending()) {
-    SBOD_CUDA_TRY(cudaFuncSetAttribute(detect_bound_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    SBOD_CUDA_TRY(cudaFuncSetAttribute(detect_bound_kernel<81>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    SBOD_CUDA_TRY(cudaFuncSetAttribute(detect_bound_kernel<21>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    SBOD_CUDA_TRY(cudaFuncSetAttribute(detect_bound_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     SBOD_CUDA_TRY(cudaFuncSetAttribute(detect_nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
     attr_once.mark();
   }
   if (stage_mask & 1) {  // bound pass
-    const size_t smem = size_t(q.n_stages) * q.stage_floats * 4 + 4 * 8;
-    int grid = sm_count() * 2;
-    if (grid > q.n_tiles) grid = q.n_tiles;
-    detect_bound_kernel<<<grid, kBThreads, smem, st>>>(q);
+    if (fast) {
+      const size_t smem = size_t(q.n_stages) * q.stage_floats * 4 + 4 * 8;
+      int grid = sm_count() * 2;
+      if (grid > q.n_tiles) grid = q.n_tiles;
+      if (q.C == 81) detect_bound_kernel<81><<<grid, kStreamThreads, smem, st>>>(q);       // COCO
+      else if (q.C == 21) detect_bound_kernel<21><<<grid, kStreamThreads, smem, st>>>(q);  // VOC
+      else detect_bound_kernel<0><<<grid, kStreamThreads, smem, st>>>(q);
+    } else {
+      detect_bound_generic_kernel<<<sm_count() * 8, 256, 0, st>>>(q);
+    }
     SBOD_LAUNCH_CHECK();
   }
   if (stage_mask & 4) {  // exact evaluation of the rows above the cutoff
@@ -1233,6 +1322,36 @@ static int detect_run(const sbod_detect_desc* d, sbod_stream_t stream, int stage
     detect_nms_kernel<<<q.N, kNmsThreads, nms_smem, st>>>(q);
     SBOD_LAUNCH_CHECK();
   }
+  return SBOD_OK;
+}
+
+// The activation exactly as the refine pass evaluates it (same device functions, a warp per row), for every
+// (image, prior, class): lets a test separate "scores within 1e-5 of torch" from "kept indices bit-exact given
+// the scores".
+__global__ void __launch_bounds__(256) detect_probabilities_kernel(const DetParams q, float* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const size_t total = size_t(q.N) * q.P;
+  for (size_t np = (size_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5; np < total;
+       np += (size_t(gridDim.x) * blockDim.x) >> 5) {
+    const float* x = q.scores + np * size_t(q.C);
+    RowProbs R;
+    row_load(q, x, lane, R);
+    row_prepare(q, x, lane, R);
+    for (int k = lane; k < q.C; k += 32) out[np * size_t(q.C) + k] = row_prob(q, R, x[k]);
+  }
+}
+
+extern "C" int sbod_detect_probabilities(const float* scores, int N, int P, int C, int act_kind, float* out,
+                                         sbod_stream_t stream) {
+  if (!scores || !out || N <= 0 || P <= 0 || C <= 1) return SBOD_ERR_INVALID;
+  if (act_kind < SBOD_ACT_SOFTMAX || act_kind > SBOD_ACT_NONE) return SBOD_ERR_INVALID;
+  DetParams q;
+  memset(&q, 0, sizeof(q));
+  q.scores = scores;
+  q.N = N; q.P = P; q.C = C;
+  q.act_kind = act_kind;
+  detect_probabilities_kernel<<<sm_count() * 8, 256, 0, static_cast<cudaStream_t>(stream)>>>(q, out);
+  SBOD_LAUNCH_CHECK();
   return SBOD_OK;
 }
 

@@ -8,6 +8,7 @@
 // restatement only ("parity unpinned" with respect to the reference itself).
 #include <math.h>
 
+#include "comm.cuh"
 #include "common.cuh"
 #include "pair_iou.cuh"
 
@@ -33,6 +34,7 @@ struct FcosParams {
   double* blockpart;         // [N, nblk, 5]
   double* sums;              // [6]: focal, sum(l*w), sum(w), bce, n_pos, n_images
   float* loss;               // [4]: total, conf, loc, center
+  const CommDev* comm;       // in-kernel all-reduce of the six sums over the ranks (or null)
 };
 
 // ---- assignment: one thread per location, objects staged in shared memory ----------------------
@@ -230,6 +232,7 @@ __global__ void __launch_bounds__(256) fcos_finalize_kernel(const FcosParams q, 
   double tot[6];
   for (int k = 0; k < 5; ++k) tot[k] = block_sum(acc[k], s_red);
   tot[5] = double(q.N);
+  if (q.comm && threadIdx.x < 32) comm_allreduce_sum(q.comm, tot, 6);  // sharded batch: sums of all ranks, rank order
   if (threadIdx.x == 0) {
     for (int k = 0; k < 6; ++k) q.sums[k] = tot[k];
     fcos_finalize(q, tot);
@@ -284,6 +287,7 @@ static int fill_fcos(const sbod_fcos_desc* d, FcosParams& q, int* nblk) {
   q.blockpart = static_cast<double*>(d->workspace);
   q.sums = d->sums;
   q.loss = d->loss;
+  q.comm = static_cast<const CommDev*>(d->comm);
   return SBOD_OK;
 }
 

@@ -24,6 +24,7 @@
 
 #include <cooperative_groups.h>
 
+#include "comm.cuh"
 #include "common.cuh"
 #include "pair_iou.cuh"
 #include "row_stream.cuh"
@@ -74,6 +75,7 @@ struct LossParams {
   int ctas_per_sm;
   int debug_skip;  // SBOD_DEBUG_SKIP: bit0 = no stream role, bit1 = no match role (profiling only)
   float* prefill;  // grad wrt logits to zero-fill while streaming (or null)
+  const CommDev* comm;  // in-kernel all-reduce of the loss sums over the ranks (or null)
 };
 
 SBOD_DEVINL int64_t map_label(const LossParams& q, int64_t lab) {
@@ -1205,12 +1207,24 @@ __global__ void __launch_bounds__(kCmThreads) classify_mine_kernel(const LossPar
   }
   cluster.sync();  // rank 0 is done reading its peers' shared memory: they may exit
   if (rank != 0) return;
-  if (S.last && tid < 4) {  // the last image folds the batch in image order (deterministic)
+  if (S.last && tid < 32) {  // the last image folds the batch in image order (deterministic)
     __threadfence();
     double acc = 0.0;
-    const volatile double* pp = q.partials;
-    for (int i = 0; i < q.N; ++i) acc += pp[i * 4 + tid];
-    q.sums[tid] = acc;
+    if (tid < 4) {
+      const volatile double* pp = q.partials;
+      for (int i = 0; i < q.N; ++i) acc += pp[i * 4 + tid];
+    }
+    if (q.comm) {
+      // sharded batch: the four sums of this rank meet those of the other ranks through the NVLink mailboxes
+      // (every rank adds them in rank order); the loss is then formed from the global sums, and the backward
+      // scales by the global 1 / n_pos
+      double v[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) v[i] = __shfl_sync(0xffffffffu, acc, i);
+      comm_allreduce_sum(q.comm, v, 4);
+      acc = tid < 4 ? v[tid & 3] : 0.0;
+    }
+    if (tid < 4) q.sums[tid] = acc;
   }
   __syncthreads();
   if (S.last && tid == 0) {
@@ -1593,6 +1607,11 @@ static Tiling choose_tiling(int C, int max_stages) {
   return t;
 }
 
+// Process-wide switches (A/B measurements; defaults are the fast settings).
+static int g_opt_pdl = 1;           // programmatic dependent launch between the kernels of one call
+static int g_opt_peer_exchange = 1; // one-shot NVLink exchange of the loss sums when a communicator is attached
+static int g_opt_cm_cluster = 0;    // CTAs per image of classify_mine_kernel (0 = automatic)
+
 static size_t cm_smem_bytes(const LossParams& q, bool cached) {
   const size_t slice = (size_t(q.P) + q.cm_cluster - 1) / q.cm_cluster;
   return ((sizeof(CmShared) + 127) & ~size_t(127)) + align_up(size_t(q.gmax) * 28, 128) + (cached ? slice * 4 : 0) + 128;
@@ -1632,6 +1651,8 @@ static int fill_params(const sbod_loss_desc* d, LossParams& q, bool need_scores)
   q.ov = d->ov; q.obj = d->obj; q.lse = d->lse; q.ce = d->ce; q.sel = d->sel;
   q.partials = d->partials; q.sums = d->sums; q.loss = d->loss;
   q.prefill = d->grad_scores_prefill;
+  q.comm = (need_scores && g_opt_peer_exchange) ? static_cast<const CommDev*>(d->comm) : nullptr;
+  if (q.comm && d->cls_kind == SBOD_CLS_CE_MINE_BATCH) return SBOD_ERR_INVALID;
   if (q.prefill && (reinterpret_cast<uintptr_t>(q.prefill) & 15)) return SBOD_ERR_ALIGNMENT;
   // workspace carve-up
   const size_t need = sbod_loss_workspace_bytes(d);
@@ -1678,6 +1699,7 @@ static int fill_params(const sbod_loss_desc* d, LossParams& q, bool need_scores)
   q.cm_cluster = 1;
   while (q.cm_cluster < kCmMaxCluster && q.N * q.cm_cluster * 2 <= sm_count() && q.P / (q.cm_cluster * 2) >= 2048)
     q.cm_cluster *= 2;
+  if (g_opt_cm_cluster) q.cm_cluster = g_opt_cm_cluster;
   q.mine_cache = (cm_smem_bytes(q, true) <= 200 * 1024) ? 1 : 0;
   return SBOD_OK;
 }
@@ -1700,12 +1722,10 @@ extern "C" size_t sbod_loss_workspace_zero_bytes(const sbod_loss_desc* d) {
   return 256 + align_up(size_t(d->N) * gmax * 8, 256) + align_up(size_t(d->N) * 4, 256);
 }
 
-// Process-wide switches (A/B measurements; defaults are the fast settings).
-static int g_opt_pdl = 1;           // programmatic dependent launch between the kernels of one call
-static int g_opt_peer_exchange = 1; // one-shot NVLink exchange of the loss sums when a communicator is attached
 extern "C" int sbod_set_option(int key, int value) {
   if (key == SBOD_OPT_PDL) g_opt_pdl = value ? 1 : 0;
   else if (key == SBOD_OPT_PEER_EXCHANGE) g_opt_peer_exchange = value ? 1 : 0;
+  else if (key == SBOD_OPT_CM_CLUSTER) g_opt_cm_cluster = (value == 1 || value == 2 || value == 4 || value == 8) ? value : 0;
   else return SBOD_ERR_INVALID;
   return SBOD_OK;
 }

@@ -195,6 +195,51 @@ SBOD_DEVINL float half_row_sumexp_mask(const float* rp, int nh, float nmx2, floa
   return s + __shfl_xor_sync(0xffffffffu, s, 1);
 }
 
+// Eval path, softmax rows: sum of exp(x - shift) over ALL elements of a row and the maximum of exp(x - shift)
+// over its FOREGROUND elements (k >= 1), shared by the two threads of a pair. kC > 0: compile-time class
+// count (fully unrolled, immediate offsets); kC == 0: run-time C. rbase = first logit of the row, h = element
+// parity of this thread, nshift2 = -shift * log2(e). The caller checks the sum for overflow.
+template <int kC>
+SBOD_DEVINL void pair_row_sum_fgmax(const float* rbase, int h, int C, float nshift2, float& sum, float& fgmax) {
+  const int Cc = kC ? kC : C;
+  const int both = Cc / 2;
+  const float* rp = rbase + h;
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+  float m0 = 0.f, m1 = 0.f;  // exp() > 0: 0 is the neutral element
+  if (kC) {
+#pragma unroll
+    for (int j = 0; j < kC / 2; ++j) {
+      const float e = ex2_approx(fmaf(rp[2 * j], kLog2e, nshift2));
+      if ((j & 3) == 0) s0 += e;
+      else if ((j & 3) == 1) s1 += e;
+      else if ((j & 3) == 2) s2 += e;
+      else s3 += e;
+      if (j == 0) {
+        if (h == 1) m0 = e;  // element 0 of parity 0 is the background
+      } else if (j & 1) {
+        m1 = fmaxf(m1, e);
+      } else {
+        m0 = fmaxf(m0, e);
+      }
+    }
+  } else {
+    for (int j = 0; j < both; ++j) {
+      const float e = ex2_approx(fmaf(rp[2 * j], kLog2e, nshift2));
+      s0 += e;
+      if (j > 0 || h == 1) m0 = fmaxf(m0, e);
+    }
+  }
+  if ((Cc & 1) && h == 0) {  // an odd C gives parity 0 one more element (never the background: Cc >= 3 then)
+    const float e = ex2_approx(fmaf(rp[2 * both], kLog2e, nshift2));
+    s1 += e;
+    if (both > 0) m1 = fmaxf(m1, e);
+  }
+  const float s = (s0 + s1) + (s2 + s3);
+  const float m = fmaxf(m0, m1);
+  sum = s + __shfl_xor_sync(0xffffffffu, s, 1);
+  fgmax = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 1));
+}
+
 // generic tile geometry shared by the streaming kernels
 struct StreamTile {
   int n, p0, rows;

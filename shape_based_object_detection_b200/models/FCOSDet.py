@@ -80,12 +80,17 @@ class _FcosFn(torch.autograd.Function):
         d.center_sample = 1 if mod.center_sample else 0
         d.reg_weight, d.focal_alpha, d.focal_gamma = float(mod.alpha), 0.25, 2.0
         d.lab, d.tgt, d.sums, d.loss = lab.data_ptr(), tgt.data_ptr(), sums.data_ptr(), loss.data_ptr()
+        comm = None
+        if mod.process_group is not None:
+            from ..parallel import peer_exchange
+            comm = peer_exchange(mod.process_group, dev)
+        d.comm = comm.ptr if comm is not None else None
         nbytes = L.lib().sbod_fcos_workspace_bytes(C.byref(d))
         ws = L.Workspace.get(dev, "fcos", nbytes, zero_bytes=0)
         d.workspace, d.workspace_bytes = ws.data_ptr(), nbytes
         with torch.cuda.device(dev):
             L.check(L.lib().sbod_fcos_forward(C.byref(d), L.stream_ptr()))
-            if mod.process_group is not None:
+            if mod.process_group is not None and comm is None:
                 # sharded by image: [focal, sum((1-diou)*w), sum(w), bce, n_pos, n_images] is all that crosses GPUs
                 import torch.distributed as dist
                 dist.all_reduce(sums, op=dist.ReduceOp.SUM, group=mod.process_group)
