@@ -89,6 +89,17 @@ SBOD_API int sbod_box_decode(const float* locs, const float* priors_cxcy, float*
 SBOD_API int sbod_box_op_bwd(int op, const float* in, const float* priors_cxcy, const float* grad_out,
                     float* grad_in, int n, float v0, float v1, sbod_stream_t stream);
 
+/* Prior / anchor / location tables on the device (the step before the path): the python triple loops of
+ * models/SSD300.py:389-443, SSD512.py:417-474, RetinaNet.py:261-300, RefineDet512.py:655-695 (level, row i,
+ * column j, box shape -> (cx, cy, w, h), clamp_(0, 1)) and FCOS.compute_location (FCOSDet.py:235-251, centres
+ * only: pass n_shapes[l] == 0 for every level, out is then [n_out, 2]). Same arithmetic as the reference
+ * (float64, rounded once to fp32). All array arguments are HOST arrays: rows / cols / n_shapes [n_levels],
+ * scale [n_levels][4] = (mul_x, div_x, mul_y, div_y) with cx = (j + 0.5) * mul_x / div_x, shapes
+ * [sum n_shapes][2] = (w, h). out: device, [n_out, 4] (or [n_out, 2]), n_out = sum rows * cols * n_shapes. */
+SBOD_API int sbod_prior_grid(int n_levels, const int32_t* rows, const int32_t* cols, const int32_t* n_shapes,
+                    const double* scale, const double* shapes, int clamp01, float* out, long long n_out,
+                    sbod_stream_t stream);
+
 /* RefineDet512.offset2bbox, models/RefineDet512.py:643-653: two-stage decode ARM -> ODM -> xyxy.
  * arm/odm: [N,P,4], priors_cxcy: [P,4], out: [N,P,4]. */
 SBOD_API int sbod_offset2bbox(const float* arm_locs, const float* odm_locs, const float* priors_cxcy,

@@ -24,7 +24,7 @@ BOX_OFFSET, BOX_CENTER, BOX_CORNER = 0, 1, 2
 
 EXPORTS = [
     "sbod_abi_version", "sbod_error_string", "sbod_iou_matrix", "sbod_box_convert",
-    "sbod_box_encode", "sbod_box_decode", "sbod_box_op_bwd", "sbod_offset2bbox", "sbod_arm_easy_negative", "sbod_pair_iou_fwd",
+    "sbod_box_encode", "sbod_box_decode", "sbod_box_op_bwd", "sbod_prior_grid", "sbod_offset2bbox", "sbod_arm_easy_negative", "sbod_pair_iou_fwd",
     "sbod_pair_iou_bwd", "sbod_smooth_l1", "sbod_softmax_focal", "sbod_sigmoid_focal",
     "sbod_nms_workspace_bytes", "sbod_nms", "sbod_assign_workspace_bytes", "sbod_assign",
     "sbod_match_workspace_bytes", "sbod_match", "sbod_loss_workspace_bytes", "sbod_loss_workspace_zero_bytes",
@@ -100,6 +100,7 @@ def _declare(lib):
         "sbod_box_encode": [vp, vp, vp, i32, i32, f32, f32, vp],
         "sbod_box_decode": [vp, vp, vp, i32, i32, f32, f32, vp],
         "sbod_box_op_bwd": [i32, vp, vp, vp, vp, i32, f32, f32, vp],
+        "sbod_prior_grid": [i32, vp, vp, vp, vp, vp, i32, vp, C.c_longlong, vp],
         "sbod_offset2bbox": [vp, vp, vp, vp, i32, i32, vp],
         "sbod_arm_easy_negative": [vp, C.c_longlong, f32, vp, vp],
         "sbod_selftest_div": [vp, vp, C.c_longlong, vp, vp, vp, vp],

@@ -165,6 +165,46 @@ __global__ void offset2bbox_kernel(const float4* __restrict__ arm, const float4*
   }
 }
 
+// ---- prior / anchor / location tables generated on the device ---------------------------------------
+// models/SSD300.py:389-443, SSD512.py:417-474, RetinaNet.py:261-300, RefineDet512.py:655-695 (python triple
+// loops: level, row i, column j, box shape) and FCOSDet.py:235-251 (cell centres). One thread per prior; the
+// arithmetic is the reference's: python floats (float64), rounded once to fp32, then clamp_(0, 1).
+constexpr int kGridMaxLevels = 8;
+constexpr int kGridMaxShapes = 64;
+struct GridSpec {
+  int n_levels;
+  int rows[kGridMaxLevels], cols[kGridMaxLevels], n_shapes[kGridMaxLevels], shape0[kGridMaxLevels];
+  long long offset[kGridMaxLevels + 1];  // first output row of each level
+  double mul_x[kGridMaxLevels], div_x[kGridMaxLevels], mul_y[kGridMaxLevels], div_y[kGridMaxLevels];
+  double shape_w[kGridMaxShapes], shape_h[kGridMaxShapes];
+  int clamp01, centres_only;
+};
+
+__global__ void prior_grid_kernel(const GridSpec g, float* __restrict__ out, long long total) {
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    int lv = 0;
+    while (lv + 1 < g.n_levels && idx >= g.offset[lv + 1]) ++lv;
+    const long long local = idx - g.offset[lv];
+    const int ns = g.centres_only ? 1 : g.n_shapes[lv];
+    const long long cell = local / ns;
+    const int sidx = int(local - cell * ns);
+    const int i = int(cell / g.cols[lv]), j = int(cell - (long long)i * g.cols[lv]);
+    float cx = float(__ddiv_rn(__dmul_rn(double(j) + 0.5, g.mul_x[lv]), g.div_x[lv]));
+    float cy = float(__ddiv_rn(__dmul_rn(double(i) + 0.5, g.mul_y[lv]), g.div_y[lv]));
+    if (g.centres_only) {
+      reinterpret_cast<float2*>(out)[idx] = make_float2(cx, cy);
+    } else {
+      float w = float(g.shape_w[g.shape0[lv] + sidx]), h = float(g.shape_h[g.shape0[lv] + sidx]);
+      if (g.clamp01) {
+        cx = fminf(fmaxf(cx, 0.f), 1.f); cy = fminf(fmaxf(cy, 0.f), 1.f);
+        w = fminf(fmaxf(w, 0.f), 1.f); h = fminf(fmaxf(h, 0.f), 1.f);
+      }
+      reinterpret_cast<float4*>(out)[idx] = make_float4(cx, cy, w, h);
+    }
+  }
+}
+
 // ---- RefineDet: ARM easy-negative mask  softmax(arm_scores)[:, 1] < theta  (RefineDet512.py:894-895)
 __global__ void arm_easy_negative_kernel(const float2* __restrict__ arm_scores, size_t n, float theta,
                                          uint8_t* __restrict__ out) {
@@ -577,6 +617,41 @@ extern "C" int sbod_box_decode(const float* locs, const float* priors_cxcy, floa
   box_decode_kernel<<<grid_for(n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       reinterpret_cast<const float4*>(locs), reinterpret_cast<const float4*>(priors_cxcy),
       reinterpret_cast<float4*>(out), n, flavour, v0, v1);
+  SBOD_LAUNCH_CHECK();
+  return SBOD_OK;
+}
+
+extern "C" int sbod_prior_grid(int n_levels, const int32_t* rows, const int32_t* cols, const int32_t* n_shapes,
+                               const double* scale, const double* shapes, int clamp01, float* out, long long n_out,
+                               sbod_stream_t stream) {
+  if (n_levels < 1 || n_levels > kGridMaxLevels || !rows || !cols || !n_shapes || !scale || !out) return SBOD_ERR_INVALID;
+  GridSpec g;
+  memset(&g, 0, sizeof(g));
+  g.n_levels = n_levels;
+  g.clamp01 = clamp01;
+  int total_shapes = 0;
+  bool centres = true;
+  for (int l = 0; l < n_levels; ++l) centres = centres && n_shapes[l] == 0;
+  g.centres_only = centres ? 1 : 0;
+  long long off = 0;
+  for (int l = 0; l < n_levels; ++l) {
+    if (rows[l] <= 0 || cols[l] <= 0 || n_shapes[l] < 0 || (!centres && n_shapes[l] == 0)) return SBOD_ERR_INVALID;
+    g.rows[l] = rows[l]; g.cols[l] = cols[l]; g.n_shapes[l] = n_shapes[l]; g.shape0[l] = total_shapes;
+    g.mul_x[l] = scale[4 * l]; g.div_x[l] = scale[4 * l + 1]; g.mul_y[l] = scale[4 * l + 2]; g.div_y[l] = scale[4 * l + 3];
+    g.offset[l] = off;
+    off += (long long)rows[l] * cols[l] * (centres ? 1 : n_shapes[l]);
+    if (total_shapes + n_shapes[l] > kGridMaxShapes) return SBOD_ERR_UNSUPPORTED;
+    for (int k = 0; k < n_shapes[l]; ++k) {
+      if (!shapes) return SBOD_ERR_INVALID;
+      g.shape_w[total_shapes + k] = shapes[2 * (total_shapes + k)];
+      g.shape_h[total_shapes + k] = shapes[2 * (total_shapes + k) + 1];
+    }
+    total_shapes += n_shapes[l];
+  }
+  g.offset[n_levels] = off;
+  if (off != n_out) return SBOD_ERR_INVALID;
+  if (reinterpret_cast<uintptr_t>(out) & 15) return SBOD_ERR_ALIGNMENT;
+  prior_grid_kernel<<<grid_for(size_t(off), 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(g, out, off);
   SBOD_LAUNCH_CHECK();
   return SBOD_OK;
 }

@@ -275,9 +275,11 @@ __global__ void __launch_bounds__(256) detect_bound_generic_kernel(const DetPara
 // rows_target rows have their bound in bins [0, cb) — only those rows are evaluated in the first band, and
 // only candidates with a key below the cutoff are emitted. Block-wide (any multiple of 32 threads); every
 // thread returns the same value (0xffffffff = no cutoff: everything above min_score). scratch: >= 34 uints.
-__device__ unsigned int compute_cutoff(const DetParams& q, int n, unsigned int* scratch) {
+// Starts with a barrier (the caller's copy of the histogram into shared memory is complete after it).
+__device__ unsigned int compute_cutoff(const DetParams& q, const unsigned int* sh /* histogram of the bounds (shared memory) */,
+                                       unsigned int* scratch) {
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, nt = blockDim.x;
-  const unsigned int* sh = q.rhist + size_t(n) * kMaxBins;
+  __syncthreads();
   const int per = (q.n_bins + nt - 1) / nt;  // contiguous bins per thread, best scores first
   unsigned int mine = 0;
   for (int j = 0; j < per; ++j) {
@@ -434,26 +436,29 @@ SBOD_DEVINL void eval_row(const DetParams& q, int n, int p, int lane, uint32_t k
 // atomic per warp and row, one global atomic per CTA. The histogram of the keys' leading digit is
 // accumulated in shared memory and flushed once.
 // ------------------------------------------------------------------------------------------
-constexpr int kRefThreads = 256;
-constexpr int kRefRows = 512;
-constexpr int kRefKeyBuf = 3072;
+constexpr int kRefThreads = 512;
+constexpr int kRefMaxRows = 2048;  // prior rows per CTA (host picks 512 .. 2048 so that the grid is a few waves)
+constexpr int kRefKeyBuf = kMaxBins / 2;  // keys buffered per CTA (shares its storage with the histogram copy)
 
-__global__ void __launch_bounds__(kRefThreads) detect_refine_kernel(const DetParams q) {
-  __shared__ unsigned int s_hist[kMaxBins];
+__global__ void __launch_bounds__(kRefThreads) detect_refine_kernel(const DetParams q, int rows_per_cta) {
   __shared__ unsigned int s_scratch[40];
-  __shared__ unsigned long long s_keys[kRefKeyBuf];
-  __shared__ int s_rows[kRefRows];
+  __shared__ __align__(16) unsigned long long s_keys[kRefKeyBuf];  // first: the image's bound histogram (kMaxBins uints)
+  __shared__ int s_rows[kRefMaxRows];
   __shared__ unsigned int s_nrows, s_ncand, s_gbase, s_hole;
   const int n = blockIdx.y, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-  const int p_lo = blockIdx.x * kRefRows, p_hi = min(q.P, p_lo + kRefRows);
-  for (int b = tid; b < q.n_bins; b += kRefThreads) s_hist[b] = 0u;
+  const int p_lo = blockIdx.x * rows_per_cta, p_hi = min(q.P, p_lo + rows_per_cta);
+  {
+    unsigned int* s_rh = reinterpret_cast<unsigned int*>(s_keys);
+    const unsigned int* rh = q.rhist + size_t(n) * kMaxBins;
+    for (int b = tid; b < q.n_bins; b += kRefThreads) s_rh[b] = rh[b];  // coalesced, L2
+  }
   if (tid == 0) {
     s_nrows = 0u;
     s_ncand = 0u;
     s_hole = 0xffffffffu;
   }
-  const unsigned int cut = compute_cutoff(q, n, s_scratch);  // (contains the barriers that publish the zeroing)
-  // rows of this CTA whose bound is above the cutoff, in prior order
+  const unsigned int cut = compute_cutoff(q, reinterpret_cast<unsigned int*>(s_keys), s_scratch);
+  // rows of this CTA whose bound is above the cutoff
   for (int pb = p_lo; pb < p_hi; pb += kRefThreads) {
     const int p = pb + tid;
     bool take = false;
@@ -467,9 +472,10 @@ __global__ void __launch_bounds__(kRefThreads) detect_refine_kernel(const DetPar
     base = __shfl_sync(0xffffffffu, base, 0);
     if (take) s_rows[base + __popc(bal & ((1u << lane) - 1u))] = p;
   }
-  __syncthreads();
+  __syncthreads();  // (also: everybody is done with the histogram copy that shares s_keys)
   const int n_rows = int(s_nrows);
   unsigned long long* g_list = q.cand + size_t(n) * q.cand_cap;
+  unsigned int* g_hist = q.hist + size_t(n) * kMaxBins;
   auto reserve = [&](unsigned int count) -> unsigned int {
     const unsigned int at = atomicAdd(&s_ncand, count);
     if (at + count <= unsigned(kRefKeyBuf)) return at;
@@ -481,7 +487,7 @@ __global__ void __launch_bounds__(kRefThreads) detect_refine_kernel(const DetPar
   auto put = [&](unsigned int slot, unsigned long long key) {
     if (slot < unsigned(kRefKeyBuf)) s_keys[slot] = key;
     else if ((long long)(slot - unsigned(kRefKeyBuf)) < q.cand_cap) g_list[slot - unsigned(kRefKeyBuf)] = key;
-    atomicAdd(&s_hist[k32_bin(q, uint32_t(key >> 32))], 1u);
+    atomicAdd(&g_hist[k32_bin(q, uint32_t(key >> 32))], 1u);  // a few dozen keys per CTA: straight to L2
   };
   // a warp per row; the next row's logits are requested before the current row is evaluated
   {
@@ -496,7 +502,7 @@ __global__ void __launch_bounds__(kRefThreads) detect_refine_kernel(const DetPar
     }
   }
   __syncthreads();
-  // hand the buffered keys and the histogram over: one global atomic for the CTA's keys
+  // hand the buffered keys over: one global atomic for the CTA's keys
   const unsigned int have = s_hole != 0xffffffffu ? s_hole : min(s_ncand, unsigned(kRefKeyBuf));
   if (have) {  // (CTA-uniform)
     if (tid == 0) s_gbase = atomicAdd(&q.cand_count[n], have);
@@ -505,11 +511,6 @@ __global__ void __launch_bounds__(kRefThreads) detect_refine_kernel(const DetPar
       const long long slot = (long long)s_gbase + i;
       if (slot < q.cand_cap) g_list[slot] = s_keys[i];
     }
-  }
-  unsigned int* gh = q.hist + size_t(n) * kMaxBins;
-  for (int b = tid; b < q.n_bins; b += kRefThreads) {
-    const unsigned int v = s_hist[b];
-    if (v) atomicAdd(&gh[b], v);
   }
 }
 
@@ -572,11 +573,14 @@ __global__ void __launch_bounds__(kNmsThreads) detect_nms_kernel(const DetParams
 
   const int n = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   // same function of the same histogram as detect_refine_kernel: candidates below `cut` are complete
-  unsigned int cut = compute_cutoff(q, n, S.wscan);
   {
     unsigned int* rh = q.rhist + size_t(n) * kMaxBins;
-    for (int b = tid; b < q.n_bins; b += kNmsThreads) rh[b] = 0u;  // clean for the next call
+    for (int b = tid; b < q.n_bins; b += kNmsThreads) {
+      S.hist[b] = rh[b];
+      rh[b] = 0u;  // clean for the next call
+    }
   }
+  unsigned int cut = compute_cutoff(q, S.hist, S.wscan);
   const bool two_stage = q.second_thr >= 0.f;
   unsigned int* g_hist = q.hist + size_t(n) * kMaxBins;
   unsigned int* g_seen = q.class_seen + size_t(n) * q.C;
@@ -1312,8 +1316,13 @@ static int detect_run(const sbod_detect_desc* d, sbod_stream_t stream, int stage
     SBOD_LAUNCH_CHECK();
   }
   if (stage_mask & 4) {  // exact evaluation of the rows above the cutoff
-    dim3 grid((q.P + kRefRows - 1) / kRefRows, q.N);
-    detect_refine_kernel<<<grid, kRefThreads, 0, st>>>(q);
+    // rows per CTA: 512 .. 2048, so that the grid is about eight CTAs per SM (fixed per-CTA cost vs parallelism)
+    int rows_per_cta = 512;
+    while (rows_per_cta < kRefMaxRows &&
+           (long long)q.N * ((q.P + rows_per_cta - 1) / rows_per_cta) > (long long)sm_count() * 8)
+      rows_per_cta *= 2;
+    dim3 grid((q.P + rows_per_cta - 1) / rows_per_cta, q.N);
+    detect_refine_kernel<<<grid, kRefThreads, 0, st>>>(q, rows_per_cta);
     SBOD_LAUNCH_CHECK();
   }
   if (stage_mask & 2) {  // NMS (+ in-kernel second band for the images that need it)

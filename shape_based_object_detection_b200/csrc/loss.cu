@@ -65,6 +65,7 @@ struct LossParams {
   float* cand;                // [N, P]
   unsigned int* counters;     // [4]
   unsigned int* match_q;      // [N] per-image chunk queues of the match role
+  unsigned int* sel_hist;     // [N, 3, kBins] digit histograms of the hard-negative radix select (zero between calls)
   // tiling
   int rows_per_tile, tiles_per_image, n_tiles, n_stages;
   uint32_t stage_floats;
@@ -123,7 +124,6 @@ __global__ void __launch_bounds__(kRows) match_lse_kernel(const LossParams q) {
 
   const int tid = threadIdx.x, lane = tid & 31;
   const int n_my = (q.n_tiles - int(blockIdx.x) + int(gridDim.x) - 1) / int(gridDim.x);
-  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");  // the next kernel may start its prologue
 
   if (q.with_scores) {
     if (tid == 0) {
@@ -327,7 +327,6 @@ __global__ void __launch_bounds__(kFastThreads, 2) match_lse_fast_kernel(const L
   tile_range(q.n_tiles, blockIdx.x, gridDim.x, t0, t1);
   const int n_my = t1 - t0;
   const int C = kC ? kC : q.C;
-  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");  // the next kernel may start its prologue
   if (tid == 0) {
     for (int s = 0; s < q.n_stages; ++s) mbar_init(&bars[s], 1);
     fence_mbar_init();
@@ -780,37 +779,39 @@ SBOD_DEVINL float focal_bg(const LossParams& q, float ce) {  // (1-alpha) * p0^g
 
 // ------------------------------------------------------------------------------------------
 // Cluster-wide radix select: sum of the k largest candidate values of an array that is split over the
-// CTAs of a thread-block cluster (candidates are >= 0, non-candidates < 0). MSD radix 12 + 12 + 8 bits;
-// every CTA histograms its own slice in shared memory, one cluster barrier later every CTA reads all
-// the slices' histograms through distributed shared memory and finds the digit on its own (same
-// integers, same result in every CTA: nothing has to be broadcast). Two histogram buffers alternate,
-// so one cluster barrier per pass is enough.
+// CTAs of a thread-block cluster (candidates are >= 0, non-candidates < 0). MSD radix 12 + 12 + 8 bits.
+// Every CTA histograms its own slice in shared memory and adds the non-empty bins to the image's
+// histogram of the pass in global memory (L2 atomics; measured: reading the peers' histograms through
+// distributed shared memory instead cost 45 % of the kernel). One cluster barrier later every CTA reads
+// the summed histogram back (coalesced, L2) and finds the digit on its own - same integers, same result in
+// every CTA, nothing to broadcast. Each pass has its own global histogram; rank 0 clears them at the end.
 // ------------------------------------------------------------------------------------------
 struct ClusterSelect {
-  unsigned int hist[2][kBins];  // this CTA's digit histograms (read by the peers)
-  double sumv;                  // this CTA's sum of the values above the threshold (read by rank 0)
-  unsigned int ties;            // this CTA's number of candidates equal to the threshold
+  unsigned int hist[kBins];  // this CTA's digit histogram of the pass, then the cluster-wide one
+  double sumv;               // this CTA's sum of the values above the threshold (read by rank 0)
+  unsigned int ties;         // this CTA's number of candidates equal to the threshold
   int misc[4];
   unsigned int wt[32];
   double red[34];
 };
 
 struct SelectResult {
-  double sum;         // valid in rank 0 only (whole cluster); other ranks hold their local part
+  double sum;         // this CTA's part (the caller adds the slices and take_ties * threshold)
   uint32_t thr_bits;  // value of the k-th largest
   int take_ties;      // how many values == thr are part of the top-k
   int n_ties;         // how many candidates == thr exist
   long long k_eff;
 };
 
-// vals: this CTA's slice (shared or global memory), n_local values; sel_out (may be null): selection
-// flags of the slice, bit 1 is set on the selected values (a candidate is never a positive, so the flag
-// byte is written without reading it). All threads of all CTAs of the cluster must call this.
+// vals: this CTA's slice (shared or global memory), n_local values; ghist: [3][kBins] global histogram of the
+// cluster (zero on entry, zero again on return); sel_out (may be null): selection flags of the slice, value 2
+// is stored on the selected values (a candidate is never a positive, so the flag byte is written without
+// reading it). All threads of all CTAs of the cluster must call this.
 __device__ SelectResult cluster_topk_sum(cg::cluster_group& cluster, ClusterSelect& S, const float* vals,
                                          int n_local, long long k_want, long long n_cand,
-                                         uint8_t* __restrict__ sel_out) {
+                                         unsigned int* __restrict__ ghist, uint8_t* __restrict__ sel_out) {
   const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, wid = tid >> 5;
-  const unsigned int n_ranks = cluster.num_blocks(), my_rank = cluster.block_rank();
+  const unsigned int my_rank = cluster.block_rank();
   SelectResult r;
   r.sum = 0.0; r.thr_bits = 0; r.take_ties = 0; r.n_ties = 0;
   const long long k = k_want < n_cand ? k_want : n_cand;
@@ -823,12 +824,13 @@ __device__ SelectResult cluster_topk_sum(cg::cluster_group& cluster, ClusterSele
   long long remaining = k;
   const int shifts[3] = {20, 8, 0};
   const int widths[3] = {12, 12, 8};
+#pragma unroll 1
   for (int pass = 0; pass < 3; ++pass) {
     const int shift = shifts[pass];
     const uint32_t dmask = (1u << widths[pass]) - 1u;
     const int nb = 1 << widths[pass];
-    unsigned int* hist = S.hist[pass & 1];
-    for (int b = tid; b < nb; b += nt) hist[b] = 0u;
+    unsigned int* gh = ghist + size_t(pass) * kBins;
+    for (int b = tid; b < nb; b += nt) S.hist[b] = 0u;
     __syncthreads();
     // (the leading digit of cross entropies takes a handful of values: lanes with the same digit add once)
     for (int i0 = 0; i0 < n_local; i0 += nt) {
@@ -843,29 +845,31 @@ __device__ SelectResult cluster_topk_sum(cg::cluster_group& cluster, ClusterSele
       }
       if (pass == 0) {
         const unsigned peers = __match_any_sync(0xffffffffu, digit);
-        if (digit >= 0 && lane == __ffs(peers) - 1) atomicAdd(&hist[digit], unsigned(__popc(peers)));
+        if (digit >= 0 && lane == __ffs(peers) - 1) atomicAdd(&S.hist[digit], unsigned(__popc(peers)));
       } else if (digit >= 0) {
-        atomicAdd(&hist[digit], 1u);
+        atomicAdd(&S.hist[digit], 1u);
       }
     }
-    cluster.sync();  // every slice's histogram of this pass is complete
+    __syncthreads();
+    for (int b = tid; b < nb; b += nt) {
+      const unsigned int v = S.hist[b];
+      if (v) atomicAdd(&gh[b], v);
+    }
+    __threadfence();
+    cluster.sync();  // every slice has added its histogram of this pass
+    for (int b = tid; b < nb; b += nt) S.hist[b] = __ldcg(&gh[b]);
+    __syncthreads();
     // digit d (from the top) with  count(> d) < remaining <= count(>= d); each thread owns a contiguous
-    // run of bins, highest bins first, summed over the slices through distributed shared memory
-    const int per = (nb + nt - 1) / nt;
+    // run of bins, highest bins first
+    const int per = (nb + nt - 1) / nt;  // <= 8: callers run >= 512 threads
     const int hi = nb - 1 - tid * per;
-    unsigned int cnt[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};  // per <= 8: callers run >= 512 threads (kBins / 8)
+    unsigned int cnt[8];
     unsigned int mine = 0;
-    for (unsigned int rk = 0; rk < n_ranks; ++rk) {
-      const unsigned int* rh = cluster.map_shared_rank(hist, rk);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const int b = hi - j;
-        if (j < per && b >= 0) {
-          const unsigned int h = rh[b];
-          cnt[j] += h;
-          mine += h;
-        }
-      }
+    for (int j = 0; j < 8; ++j) {
+      const int b = hi - j;
+      cnt[j] = (j < per && b >= 0) ? S.hist[b] : 0u;
+      mine += cnt[j];
     }
     unsigned int inc = mine;
 #pragma unroll
@@ -882,10 +886,9 @@ __device__ SelectResult cluster_topk_sum(cg::cluster_group& cluster, ClusterSele
       bool found = false;
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        const int b = hi - j;
-        const unsigned int h = (j < per && b >= 0) ? cnt[j] : 0u;
+        const unsigned int h = cnt[j];
         if (!found && acc < (unsigned long long)remaining && (unsigned long long)remaining <= acc + h) {
-          S.misc[0] = b;
+          S.misc[0] = hi - j;
           S.misc[1] = int((unsigned long long)remaining - acc);
           S.misc[2] = int(h);
           found = true;
@@ -919,6 +922,11 @@ __device__ SelectResult cluster_topk_sum(cg::cluster_group& cluster, ClusterSele
     S.ties = unsigned(nties_local + 0.5);
   }
   r.sum = local;
+  // Every CTA is past the barrier of pass 2, so nobody reads the histograms of passes 0 and 1 any more: rank 0
+  // leaves them clean for the next call. The histogram of pass 2 may still be being read by a slower CTA: the
+  // caller clears it after its next cluster barrier (cluster_topk_cleanup).
+  if (my_rank == 0)
+    for (int b = tid; b < 2 * kBins; b += nt) ghist[b] = 0u;
   if (!all_ties) {  // rare (cluster-uniform): the ties that belong to the top-k are the first ones by index
     cluster.sync();
     if (tid == 0 && sel_out) {
@@ -933,6 +941,11 @@ __device__ SelectResult cluster_topk_sum(cg::cluster_group& cluster, ClusterSele
     }
   }
   return r;
+}
+
+// second half of the cleaning: call by rank 0 after a cluster barrier that follows cluster_topk_sum
+SBOD_DEVINL void cluster_topk_cleanup(unsigned int* __restrict__ ghist) {
+  for (int b = threadIdx.x; b < 256; b += blockDim.x) ghist[2 * kBins + b] = 0u;
 }
 
 SBOD_DEVINL void finalize_loss(const LossParams& q, const double* sums, float* loss) {
@@ -960,8 +973,9 @@ SBOD_DEVINL void finalize_loss(const LossParams& q, const double* sums, float* l
 //      (SSD512.py:610-619 consumes only their sum), selection bits by plain stores;
 //   5. rank 0 writes the image's partial sums; the last image folds the batch in image order
 //      (deterministic) and finalises the loss.
-// Launched with programmatic dependent launch after the match kernel: the prologue (list of the
-// image's objects, shared-memory setup) overlaps the tail of the streaming kernel.
+// Launched with programmatic stream serialization behind the match kernel (which triggers implicitly when
+// its CTAs exit - an explicit early trigger made the waiting cluster CTAs take SM resources from the
+// streaming kernel: measured +60 us): launch latency and the object-list prologue overlap its tail.
 // ------------------------------------------------------------------------------------------
 constexpr int kCmThreads = 512;
 constexpr int kCmMaxCluster = 8;
@@ -1137,17 +1151,30 @@ __global__ void __launch_bounds__(kCmThreads) classify_mine_kernel(const LossPar
     }
     __syncthreads();
     {
-      int at = S.fg_n;
+      // list offsets of the (unroll slot, warp) pairs: one exclusive scan of the 64 counts by warp 0
+      if (wid == 0) {
+        constexpr int kPairs = kCmUnroll * (kCmThreads / 32);
+        static_assert(kPairs == 64, "two (slot, warp) pairs per lane");
+        uint16_t* flat = &S.cnt[0][0];
+        const int c0 = flat[2 * lane], c1 = flat[2 * lane + 1];
+        int inc = c0 + c1;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const int t = __shfl_up_sync(0xffffffffu, inc, o);
+          if (lane >= o) inc += t;
+        }
+        const int ex = inc - (c0 + c1);
+        flat[2 * lane] = uint16_t(ex);
+        flat[2 * lane + 1] = uint16_t(ex + c0);
+        if (lane == 31) S.carry = inc;  // entries added by this group of priors
+      }
+      __syncthreads();
+      const int at0 = S.fg_n;
+      const int at = at0 + S.carry;
 #pragma unroll
       for (int u = 0; u < kCmUnroll; ++u) {
-        int mine_base = at;
-        for (int w2 = 0; w2 < kCmThreads / 32; ++w2) {
-          const int c2 = S.cnt[u][w2];
-          if (w2 < wid) mine_base += c2;
-          at += c2;
-        }
         if (rec[u]) {
-          const int slot = mine_base + rrank[u];
+          const int slot = at0 + int(S.cnt[u][wid]) + rrank[u];
           S.fg_idx[slot] = uint32_t(pb + u * kCmThreads + tid - p_lo);
           S.fg_cls[slot] = uint16_t(rec[u]);
           S.fg_obj[slot] = uint16_t(ob[u]);
@@ -1183,11 +1210,13 @@ __global__ void __launch_bounds__(kCmThreads) classify_mine_kernel(const LossPar
   if (select) {
     const long long k = (long long)(q.ratio) * (long long)(img[3] + 0.5);
     const float* vals = cached ? s_vals : q.cand + base + p_lo;
-    r = cluster_topk_sum(cluster, S.sel, vals, n_local, k, (long long)(img[2] + 0.5), q.sel + base + p_lo);
+    r = cluster_topk_sum(cluster, S.sel, vals, n_local, k, (long long)(img[2] + 0.5),
+                         q.sel_hist + size_t(n) * 3 * kBins, q.sel + base + p_lo);
   } else if (tid == 0) {
     S.sel.sumv = 0.0;
   }
   cluster.sync();  // the slices' selected sums are published
+  if (select && rank == 0) cluster_topk_cleanup(q.sel_hist + size_t(n) * 3 * kBins);
   if (rank == 0 && tid == 0) {
     if (focal) {
       t_neg = img[2];
@@ -1245,8 +1274,9 @@ __global__ void __launch_bounds__(1024) mine_batch_kernel(const LossParams q) {
   const long long lo = min(total, (long long)rank * slice), hi = min(total, lo + slice);
   const long long k = (long long)(q.ratio) * (long long)(q.sums[3] + 0.5);
   const long long n_cand = (long long)(q.sums[2] + 0.5);  // candidates of the batch, counted by classify_mine_kernel
-  const SelectResult r = cluster_topk_sum(cluster, S, q.cand + lo, int(hi - lo), k, n_cand, q.sel + lo);
+  const SelectResult r = cluster_topk_sum(cluster, S, q.cand + lo, int(hi - lo), k, n_cand, q.sel_hist, q.sel + lo);
   cluster.sync();
+  if (rank == 0) cluster_topk_cleanup(q.sel_hist);
   if (rank == 0 && threadIdx.x == 0) {
     double t = 0.0;
     for (unsigned int rk = 0; rk < n_ranks; ++rk) t += *cluster.map_shared_rank(&S.sumv, rk);
@@ -1665,6 +1695,8 @@ static int fill_params(const sbod_loss_desc* d, LossParams& q, bool need_scores)
   w += align_up(size_t(q.N) * q.gmax * 8, 256);
   q.match_q = reinterpret_cast<unsigned int*>(w);
   w += align_up(size_t(q.N) * 4, 256);
+  q.sel_hist = reinterpret_cast<unsigned int*>(w);
+  w += align_up(size_t(q.N) * 3 * kBins * 4, 256);
   q.cand = reinterpret_cast<float*>(w);
   Tiling t = choose_tiling(need_scores ? d->C : 1, kMaxStages);
   // the two-threads-per-row layout is bank-conflict free only for odd C; even C is merely slower in smem
@@ -1712,7 +1744,7 @@ extern "C" size_t sbod_loss_workspace_bytes(const sbod_loss_desc* d) {
   if (!d) return 0;
   const int gmax = d->gmax > 0 ? d->gmax : 1;
   return 256 + align_up(size_t(d->N) * gmax * 8, 256) + align_up(size_t(d->N) * 4, 256) +
-         align_up(size_t(d->N) * d->P * 4, 256);
+         align_up(size_t(d->N) * 3 * kBins * 4, 256) + align_up(size_t(d->N) * d->P * 4, 256);
 }
 
 // leading bytes of the loss workspace that carry the zero contract: counters, per-object keys, ticket queues
@@ -2025,8 +2057,7 @@ extern "C" int sbod_loss_forward_host(const sbod_loss_desc* h, int T, float* los
     SBOD_CUDA_TRY(cudaMemcpyAsync(base + a.gtl, h->gt_labels, size_t(T) * 8, cudaMemcpyHostToDevice, st));
   }
   SBOD_CUDA_TRY(cudaMemcpyAsync(base + a.gto, h->gt_offsets, size_t(h->N + 1) * 4, cudaMemcpyHostToDevice, st));
-  SBOD_CUDA_TRY(cudaMemsetAsync(base + a.ws, 0, 256 + align_up(size_t(h->N) * (h->gmax > 0 ? h->gmax : 1) * 8, 256) +
-                                                    align_up(size_t(h->N) * 4, 256), st));
+  SBOD_CUDA_TRY(cudaMemsetAsync(base + a.ws, 0, sbod_loss_workspace_zero_bytes(h), st));
   sbod_loss_desc d = *h;
   d.grad_scores_prefill = nullptr;
   d.locs = reinterpret_cast<const float*>(base + a.locs);

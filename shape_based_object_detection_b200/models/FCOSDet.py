@@ -36,6 +36,8 @@ def compute_location(fmap_dims=FMAP_DIMS, device="cpu", image_size=None):
     d x d cells at ((j + .5) / d, (i + .5) / d)). image_size=(H, W) gives the rectangular generalisation the
     reference's hard-coded 512 grid lacks (BASELINE config 5, 800 x 1333 -> 22 300 locations): level k has
     ceil(H / s_k) x ceil(W / s_k) cells centred at ((j + .5) s_k / W, (i + .5) s_k / H)."""
+    if torch.device(device).type == "cuda":
+        return _compute_location_device(fmap_dims, torch.device(device), image_size)
     out = []
     if image_size is None:
         for d in fmap_dims:
@@ -50,6 +52,26 @@ def compute_location(fmap_dims=FMAP_DIMS, device="cpu", image_size=None):
         cy, cx = np.meshgrid(ys, xs, indexing="ij")
         out.append(torch.tensor(np.stack([cx.ravel(), cy.ravel()], 1).astype(np.float32)).to(device))
     return out
+
+
+def _compute_location_device(fmap_dims, device, image_size):
+    """compute_location on the GPU (sbod_prior_grid, centres only): bit-identical to the host tables."""
+    if image_size is None:
+        dims = [(d, d, 1.0, float(d), 1.0, float(d)) for d in fmap_dims]
+    else:
+        H, W = image_size
+        dims = [(-(-H // s), -(-W // s), float(s), float(W), float(s), float(H)) for s in PIXEL_STRIDES]
+    n = len(dims)
+    rows = (C.c_int32 * n)(*[d[0] for d in dims])
+    cols = (C.c_int32 * n)(*[d[1] for d in dims])
+    nsh = (C.c_int32 * n)(*([0] * n))
+    scale = (C.c_double * (4 * n))(*[v for d in dims for v in d[2:]])
+    total = sum(d[0] * d[1] for d in dims)
+    out = torch.empty((total, 2), dtype=torch.float32, device=device)
+    with torch.cuda.device(device):
+        L.check(L.lib().sbod_prior_grid(n, rows, cols, nsh, scale, None, 0, L.ptr(out), C.c_longlong(total),
+                                        L.stream_ptr()))
+    return list(out.split([d[0] * d[1] for d in dims], 0))
 
 
 def _cfg(config, key, default=None):

@@ -463,3 +463,20 @@ def test_config2_detect_indices_exact_given_score_bits(dev):
     got = S.detect_batched(locs.to(dev), s_d, 0.01, 0.45, 200, pri.to(dev))
     bad = _check_detect(got, want, 32)
     assert not bad, "kept sequence differs from the oracle run on identical score bits on images %s" % bad
+
+
+def test_prior_tables_generated_on_the_gpu(dev):
+    """the prior / anchor / location generators (models/SSD300.py:389-443 etc., python triple
+    loops at model construction) as one kernel: bit-identical to the host tables, which the CPU suite pins to
+    the reference's own generators."""
+    from shape_based_object_detection_b200 import priors as PR
+    from shape_based_object_detection_b200.models import compute_location
+    for name, fn in PR.PRIOR_TABLES.items():
+        host, gpu = fn(), fn(device=dev)
+        assert gpu.is_cuda and gpu.shape == host.shape, name
+        assert torch.equal(gpu.cpu(), host), name
+    for size in (None, (800, 1333)):
+        host = compute_location(image_size=size)
+        gpu = compute_location(device=dev, image_size=size)
+        assert len(host) == len(gpu) == 5
+        assert all(torch.equal(a, b.cpu()) for a, b in zip(host, gpu))
