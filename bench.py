@@ -261,7 +261,9 @@ def run_reference(args, rank, world):
 # ours
 # ---------------------------------------------------------------------------------------------
 def timed(fn, steps, sync):
-    """CUDA-event time of `steps` calls of fn on the current stream, in ms per call."""
+    """CUDA-event time of `steps` calls of fn on the current stream, in ms per call (after one untimed call:
+    scratch buffers are per stream and are allocated on first use)."""
+    fn()
     sync()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()

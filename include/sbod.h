@@ -47,7 +47,6 @@ SBOD_API const char* sbod_error_string(int code);
 /* Process-wide switches for A/B measurements (no reference counterpart). Defaults: all on. */
 #define SBOD_OPT_PDL 0           /* programmatic dependent launch between the kernels of one call */
 #define SBOD_OPT_PEER_EXCHANGE 1 /* one-shot NVLink exchange of the loss sums (sbod_comm_*) instead of the caller's all-reduce */
-#define SBOD_OPT_CM_CLUSTER 2    /* CTAs per image of the classify + mine kernel: 1, 2, 4, 8; 0 = automatic */
 SBOD_API int sbod_set_option(int key, int value);
 
 /* ------------------------------------------------------------------------------------------

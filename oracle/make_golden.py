@@ -17,6 +17,7 @@ _args = [a for a in sys.argv[1:] if not a.startswith("--")]
 REF = _args[0] if _args else "/root/reference"
 ONLY_MAP = "--only-map" in sys.argv  # regenerate tests/golden/map.npz and nothing else
 ONLY_EXTRAS = "--only-extras" in sys.argv  # regenerate tests/golden/extras.npz and nothing else
+ONLY_CROP = "--only-crop" in sys.argv  # regenerate tests/golden/crop.npz and nothing else
 sys.path.insert(0, REPO)
 sys.path.insert(0, REF)
 warnings.filterwarnings("ignore")
@@ -59,6 +60,27 @@ def golden_map():
     print("map ok", {k: float(v) for k, v in out.items() if k.endswith("_map")})
 
 
+def golden_crop():
+    """dataset/transforms.py:124-205 random_crop on CPU: outputs and the NEXT draw of python's random (the state
+    the function leaves behind) for 24 seeds."""
+    import random
+    sys.path.insert(0, os.path.join(REPO, "tests"))
+    from cases import crop_inputs  # noqa: E402
+    from dataset import transforms as ref_t
+    out = {}
+    for seed in range(24):
+        image, boxes, labels = crop_inputs(seed)
+        random.seed(1000 + seed)
+        ni, nb, nl = ref_t.random_crop(image, boxes.clone(), labels.clone())
+        out["s%d_shape" % seed] = np.array(ni.shape, dtype=np.int64)
+        out["s%d_sum" % seed] = np.float64(ni.double().sum().item())
+        out["s%d_boxes" % seed] = nb.numpy()
+        out["s%d_labels" % seed] = nl.numpy()
+        out["s%d_next" % seed] = np.float64(random.random())
+    np.savez_compressed(os.path.join(OUT, "crop.npz"), **out)
+    print("crop ok", sum(1 for s in range(24) if tuple(out["s%d_shape" % s]) != tuple(crop_inputs(s)[0].shape)), "of 24 cropped")
+
+
 def golden_extras():
     """Functions of the path that the reference defines but never calls."""
     sys.path.insert(0, os.path.join(REPO, "tests"))
@@ -88,6 +110,9 @@ def main():
         return
     if ONLY_EXTRAS:
         golden_extras()
+        return
+    if ONLY_CROP:
+        golden_crop()
         return
     sys.path.insert(0, os.path.join(REPO, "tests"))
     from cases import LOSS_CASES, DETECT_CASES, case_priors  # noqa: E402
@@ -271,6 +296,7 @@ def main():
     print("detect ok", {k: v.shape for k, v in dout.items() if "_s" in k})
     golden_map()
     golden_extras()
+    golden_crop()
 
 
 if __name__ == "__main__":

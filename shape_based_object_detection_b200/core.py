@@ -15,7 +15,11 @@ from . import _lib as L
 # GT packing: the reference passes python lists of per-image tensors (dataset/Datasets.py:58-86)
 # ---------------------------------------------------------------------------------------------
 def pack_ground_truth(boxes, labels, device):
-    """list[N] of [G_i,4] / [G_i]  ->  (boxes [T,4] f32, labels [T] i64, offsets [N+1] i32, gmax)."""
+    """list[N] of [G_i,4] / [G_i]  ->  (boxes [T,4] f32, labels [T] i64, offsets [N+1] i32, gmax).
+    Host lists are packed into one pinned buffer and moved with a single copy (dataset.collate.PackedGT)."""
+    if len(boxes) and all((not b.is_cuda) for b in boxes) and torch.device(device).type == "cuda":
+        from .dataset.collate import PackedGT
+        return PackedGT.from_lists(boxes, labels).to(device).as_tuple()
     counts = [int(b.shape[0]) for b in boxes]
     offs = np.zeros(len(counts) + 1, dtype=np.int32)
     np.cumsum(counts, out=offs[1:])
@@ -175,6 +179,9 @@ def fused_loss(spec, priors_cxcy, priors_xy, predicted_locs, predicted_scores, b
         raise ValueError("predicted_locs / predicted_scores must be [N,P,4] / [N,P,C]")
     n_priors = priors_cxcy.size(0)
     assert n_priors == predicted_locs.size(1) == predicted_scores.size(1)  # SSD512.py:523
+    from .dataset.collate import PackedGT
+    if packed_gt is None and isinstance(boxes, PackedGT):  # the whole batch in one buffer (dataset.collate)
+        packed_gt = (boxes if boxes.device == dev else boxes.to(dev)).as_tuple()
     gt = packed_gt if packed_gt is not None else pack_ground_truth(boxes, labels, dev)
     if group is not None and spec.cls_kind == L.CLS_CE_MINE_BATCH:
         # SSD300 mines its hard negatives over the WHOLE batch (SSD300.py:580-588): a rank's own top-k cannot

@@ -65,13 +65,15 @@ struct LossParams {
   float* cand;                // [N, P]
   unsigned int* counters;     // [4]
   unsigned int* match_q;      // [N] per-image chunk queues of the match role
-  unsigned int* sel_hist;     // [N, 3, kBins] digit histograms of the hard-negative radix select (zero between calls)
+  unsigned int* sel_hist;     // [N, kBins] leading-digit histograms of the hard-negative radix select (zero between calls)
+  unsigned int* batch_hist;   // [3, kBins] digit histograms of the batch-global select (zero between calls)
+  unsigned int* img_done;     // [N] per-image tickets of classify_mine_kernel (zero between calls)
+  double* blockpart;          // [N, slices, 4] partial sums of the slices
   // tiling
   int rows_per_tile, tiles_per_image, n_tiles, n_stages;
   uint32_t stage_floats;
   int with_scores;
-  int mine_cache;  // classify_mine_kernel keeps the candidate values of its slice in shared memory
-  int cm_cluster;  // CTAs per image of classify_mine_kernel
+  int mine_cache;  // (unused)
   int fast;        // odd C <= 128: warp-specialised two-threads-per-row kernels
   int ctas_per_sm;
   int debug_skip;  // SBOD_DEBUG_SKIP: bit0 = no stream role, bit1 = no match role (profiling only)
@@ -962,42 +964,233 @@ SBOD_DEVINL void finalize_loss(const LossParams& q, const double* sums, float* l
 }
 
 // ------------------------------------------------------------------------------------------
-// classify_mine_kernel: one thread-block CLUSTER per image (cluster size 1 / 2 / 4 / 8 CTAs, chosen so
-// that the whole batch is co-resident; each CTA owns a contiguous slice of the image's priors).
-//   1. every CTA rebuilds the image's short forced-match list from the per-object keys and applies it
-//      to its slice (rank inside the FILTERED list, last write wins - SSD512.py:546-553);
-//   2. per 512 priors: classes, selection bits, mining candidates (kept in shared memory); the rows with
-//      a foreground class are recorded and evaluated densely (true-class CE, loc term);
-//   3. the slices' partial sums meet through distributed shared memory -> n_pos of the image;
-//   4. hard-negative mining = cluster-wide radix select of the 3 * n_pos largest candidate CEs
-//      (SSD512.py:610-619 consumes only their sum), selection bits by plain stores;
-//   5. rank 0 writes the image's partial sums; the last image folds the batch in image order
-//      (deterministic) and finalises the loss.
-// Launched with programmatic stream serialization behind the match kernel (which triggers implicitly when
-// its CTAs exit - an explicit early trigger made the waiting cluster CTAs take SM resources from the
-// streaming kernel: measured +60 us): launch latency and the object-list prologue overlap its tail.
+// Block-wide search of the radix digit that holds the `remaining`-th largest value: hist[nb] (shared
+// memory) counts per digit; digit d (from the top) with count(> d) < remaining <= count(>= d). Every thread
+// gets the same answer through out[0..2] = (digit, remaining inside the digit, count of the digit).
+// Needs blockDim.x * 8 >= nb. scratch: >= 32 uints. Ends with a barrier.
 // ------------------------------------------------------------------------------------------
-constexpr int kCmThreads = 512;
-constexpr int kCmMaxCluster = 8;
+__device__ void block_find_digit(const unsigned int* hist, int nb, long long remaining, unsigned int* scratch,
+                                 int* out) {
+  const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, wid = tid >> 5;
+  const int per = (nb + nt - 1) / nt;  // <= 8
+  const int hi = nb - 1 - tid * per;   // my bins: hi, hi - 1, ... (highest bins first)
+  unsigned int cnt[8];
+  unsigned int mine = 0;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int b = hi - j;
+    cnt[j] = (j < per && b >= 0) ? hist[b] : 0u;
+    mine += cnt[j];
+  }
+  unsigned int inc = mine;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const unsigned int t = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += t;
+  }
+  if (lane == 31) scratch[wid] = inc;
+  __syncthreads();
+  unsigned long long before = inc - mine;
+  for (int w = 0; w < wid; ++w) before += scratch[w];
+  if (before < (unsigned long long)remaining && (unsigned long long)remaining <= before + mine) {
+    unsigned long long acc = before;
+    bool found = false;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const unsigned int h = cnt[j];
+      if (!found && acc < (unsigned long long)remaining && (unsigned long long)remaining <= acc + h) {
+        out[0] = hi - j;
+        out[1] = int((unsigned long long)remaining - acc);
+        out[2] = int(h);
+        found = true;
+      }
+      acc += h;
+    }
+  }
+  __syncthreads();
+}
+
+// ------------------------------------------------------------------------------------------
+// classify_mine_kernel: grid (slices per image, N), 1024 threads, each CTA owns a contiguous slice of an
+// image's priors.
+//   every CTA:  rebuilds the image's short forced-match list from the per-object keys and applies it to its
+//               slice (rank inside the FILTERED list, last write wins - SSD512.py:546-553); classes, selection
+//               bits, mining candidates (4 priors per thread, all loads in flight together); the rows with a
+//               foreground class are recorded and evaluated densely (true-class CE, loc term); the leading
+//               radix digit of its candidates goes into the image's histogram (warp-aggregated atomics);
+//               partial sums to global memory; then it takes a ticket of its image.
+//   the CTA that takes an image's LAST ticket mines the image while other CTAs still classify theirs:
+//               n_pos from the slices' partials (fixed order), radix select of the 3 * n_pos largest
+//               candidate CEs - the first digit's histogram is already there, two more passes over the
+//               image's candidates (L2) - their sum (SSD512.py:610-619 consumes only the sum), selection bits by
+//               plain stores; then a ticket of the batch: the last image folds the batch in image order
+//               (deterministic), exchanges the sums with the other ranks if the batch is sharded, and
+//               finalises the loss.
+// One launch, no cluster, no grid-wide barrier: the only serial part is the last image's tail.
+// ------------------------------------------------------------------------------------------
+constexpr int kCmThreads = 1024;
 constexpr int kCmUnroll = 4;      // priors per thread whose loads are in flight together
-constexpr int kCmFgCap = 4096;    // foreground-row list (entries); evaluated and reset when it could overflow
+constexpr int kCmSlice = kCmThreads * kCmUnroll;  // priors per CTA
+constexpr int kCmFgCap = kCmSlice;                // foreground-row list: at worst every prior of the slice
+constexpr int kCmMaxCluster = 8;                  // (mine_batch_kernel)
 
 struct CmShared {
-  ClusterSelect sel;
+  unsigned int hist[kBins];  // leading-digit histogram of the slice, then the digit histograms of the tail
   double red4[4 * 32];
-  double part[4];  // this CTA's partial sums: loc, conf over positives, candidates (mining) / focal negatives, n_pos
+  double red[34];
+  unsigned int wt[32];
   int warp_tot[kCmThreads / 32];
+  int misc[8];
   int carry;
   int last;
   int fg_n;
   uint16_t cnt[kCmUnroll][kCmThreads / 32];
-  uint32_t fg_idx[kCmFgCap];   // foreground rows: prior index inside the slice
+  uint16_t fg_idx[kCmFgCap];   // foreground rows: prior index inside the slice
   uint16_t fg_cls[kCmFgCap];   // ... class (bit 15: positive)
   uint16_t fg_obj[kCmFgCap];   // ... object of the image
 };
 
+// the tail of one image: runs in the CTA that took the image's last ticket
+__device__ void cm_image_tail(const LossParams& q, CmShared& S, int n, int slices) {
+  const int tid = threadIdx.x;
+  const size_t base = size_t(n) * q.P;
+  const bool focal = q.cls_kind == SBOD_CLS_FOCAL_SUM || q.cls_kind == SBOD_CLS_FOCAL_NORM;
+  const int g0 = q.gt_offsets[n];
+  const int G = q.gt_offsets[n + 1] - g0;
+  __threadfence();  // the other slices' results (published before their tickets) are visible from here on
+  // leave the per-object keys clean for the next call (every slice has read them)
+  for (int g = tid; g < G; g += kCmThreads) q.gtkey[size_t(n) * q.gmax + g] = 0ull;
+  double img[4] = {0.0, 0.0, 0.0, 0.0};
+  {
+    const double* bp = q.blockpart + size_t(n) * slices * 4;
+    for (int b = 0; b < slices; ++b) {  // slice order: deterministic
+#pragma unroll
+      for (int k = 0; k < 4; ++k) img[k] += __ldcg(bp + b * 4 + k);
+    }
+  }
+  double t_neg = img[2];  // focal: sum over the negatives; MINE_BATCH: number of candidates (see mine_batch_kernel)
+  unsigned int* gh = q.sel_hist + size_t(n) * kBins;
+  const bool select = !focal && q.cls_kind != SBOD_CLS_CE_MINE_BATCH;
+  if (select) {
+    const long long n_cand = (long long)(img[2] + 0.5);
+    long long k = (long long)(q.ratio) * (long long)(img[3] + 0.5);
+    if (k > n_cand) k = n_cand;
+    t_neg = 0.0;
+    // first digit (12 bits): histogram accumulated by the slices; read it and leave it clean
+    for (int b = tid; b < kBins; b += kCmThreads) {
+      S.hist[b] = __ldcg(&gh[b]);
+      gh[b] = 0u;
+    }
+    __syncthreads();
+    if (k > 0) {  // (CTA-uniform)
+      const float* vals = q.cand + base;
+      uint32_t prefix = 0, mask = 0;
+      long long remaining = k;
+      block_find_digit(S.hist, kBins, remaining, S.wt, S.misc);
+      prefix = uint32_t(S.misc[0]) << 20;
+      mask = 0xfffu << 20;
+      remaining = S.misc[1];
+      int n_ties = S.misc[2];
+      const int shifts[2] = {8, 0};
+      const int widths[2] = {12, 8};
+#pragma unroll 1
+      for (int pass = 0; pass < 2; ++pass) {
+        const int shift = shifts[pass];
+        const uint32_t dmask = (1u << widths[pass]) - 1u;
+        const int nb = 1 << widths[pass];
+        __syncthreads();
+        for (int b = tid; b < nb; b += kCmThreads) S.hist[b] = 0u;
+        __syncthreads();
+        for (int i0 = 0; i0 < q.P; i0 += kCmThreads * 8) {  // eight independent loads in flight per thread (L2)
+          float v[8];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            const int i = i0 + u * kCmThreads + tid;
+            v[u] = i < q.P ? __ldcg(vals + i) : -1.f;
+          }
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            const uint32_t bits = __float_as_uint(v[u]);
+            if (v[u] >= 0.f && (bits & mask) == prefix) atomicAdd(&S.hist[(bits >> shift) & dmask], 1u);
+          }
+        }
+        __syncthreads();
+        block_find_digit(S.hist, nb, remaining, S.wt, S.misc);
+        prefix |= uint32_t(S.misc[0]) << shift;
+        mask |= dmask << shift;
+        remaining = S.misc[1];
+        n_ties = S.misc[2];
+      }
+      const float thr = __uint_as_float(prefix);
+      const int take_ties = int(remaining);
+      const bool all_ties = take_ties >= n_ties;
+      uint8_t* sel_out = q.sel + base;
+      double acc = 0.0;
+      for (int i0 = 0; i0 < q.P; i0 += kCmThreads * 8) {
+        float v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int i = i0 + u * kCmThreads + tid;
+          v[u] = i < q.P ? __ldcg(vals + i) : -1.f;
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int i = i0 + u * kCmThreads + tid;
+          if (v[u] > thr) acc += double(v[u]);
+          // selected negatives: v > thr plus (normally all) the candidates equal to thr; a candidate is never a
+          // positive, so the flag byte is written without reading it
+          if (v[u] > thr || (all_ties && v[u] == thr)) sel_out[i] = 2;
+        }
+      }
+      t_neg = block_sum(acc, S.red) + double(take_ties) * double(thr);
+      if (!all_ties && tid == 0) {  // rare: the ties that belong to the top-k are the first ones by index
+        int left = take_ties;
+        for (int i = 0; i < q.P && left > 0; ++i)
+          if (__ldcg(vals + i) == thr) {
+            sel_out[i] = 2;
+            --left;
+          }
+      }
+    }
+  }
+  if (tid == 0) {
+    q.img_done[n] = 0u;  // clean for the next call
+    q.partials[n * 4 + 0] = img[0];
+    q.partials[n * 4 + 1] = img[1];
+    q.partials[n * 4 + 2] = t_neg;
+    q.partials[n * 4 + 3] = img[3];
+    __threadfence();
+    const unsigned int ticket = atomicAdd(&q.counters[0], 1u);
+    S.last = (ticket == unsigned(q.N) - 1u) ? 1 : 0;
+  }
+  __syncthreads();
+  if (S.last && tid < 32) {  // the last image folds the batch in image order (deterministic)
+    __threadfence();
+    double acc = 0.0;
+    if (tid < 4) {
+      const double* pp = q.partials;
+      for (int i = 0; i < q.N; ++i) acc += __ldcg(pp + i * 4 + tid);
+    }
+    if (q.comm) {
+      // sharded batch: the four sums of this rank meet those of the other ranks through the NVLink mailboxes
+      // (every rank adds them in rank order); the loss is then formed from the global sums, and the backward
+      // scales by the global 1 / n_pos
+      double v[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) v[i] = __shfl_sync(0xffffffffu, acc, i);
+      comm_allreduce_sum(q.comm, v, 4);
+      acc = tid < 4 ? v[tid & 3] : 0.0;
+    }
+    if (tid < 4) q.sums[tid] = acc;
+  }
+  __syncthreads();
+  if (S.last && tid == 0) {
+    q.counters[0] = 0u;
+    if (q.cls_kind != SBOD_CLS_CE_MINE_BATCH) finalize_loss(q, q.sums, q.loss);
+  }
+}
+
 __global__ void __launch_bounds__(kCmThreads) classify_mine_kernel(const LossParams q) {
-  cg::cluster_group cluster = cg::this_cluster();
   extern __shared__ __align__(128) unsigned char smem_raw[];
   CmShared& S = *reinterpret_cast<CmShared*>(smem_raw);
   unsigned char* dyn = smem_raw + ((sizeof(CmShared) + 127) & ~size_t(127));
@@ -1005,16 +1198,13 @@ __global__ void __launch_bounds__(kCmThreads) classify_mine_kernel(const LossPar
   uint32_t* s_prior = reinterpret_cast<uint32_t*>(s_gbox + q.gmax);  // [gmax]
   int32_t* s_rank = reinterpret_cast<int32_t*>(s_prior + q.gmax);  // [gmax], -1 = filtered out
   int32_t* s_label = s_rank + q.gmax;                              // [gmax] mapped labels
-  float* s_vals = reinterpret_cast<float*>(dyn + ((size_t(q.gmax) * 28 + 127) & ~size_t(127)));  // [slice] if cached
 
-  const unsigned int n_ranks = cluster.num_blocks(), rank = cluster.block_rank();
-  const int n = blockIdx.x / n_ranks, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-  const int slice = (q.P + n_ranks - 1) / n_ranks;
-  const int p_lo = min(q.P, int(rank) * slice), p_hi = min(q.P, p_lo + slice);
-  const int n_local = p_hi - p_lo;
+  const int n = blockIdx.y, slices = gridDim.x;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int p_lo = min(q.P, int(blockIdx.x) * kCmSlice), p_hi = min(q.P, p_lo + kCmSlice);
   const size_t base = size_t(n) * q.P;
   const bool focal = q.cls_kind == SBOD_CLS_FOCAL_SUM || q.cls_kind == SBOD_CLS_FOCAL_NORM;
-  const bool cached = q.mine_cache != 0;
+  const bool select = !focal && q.cls_kind != SBOD_CLS_CE_MINE_BATCH;
   const int g0 = q.gt_offsets[n];  // (inputs of the call, not results of the match kernel)
   const int G = q.gt_offsets[n + 1] - g0;
   if (tid == 0) {
@@ -1025,6 +1215,8 @@ __global__ void __launch_bounds__(kCmThreads) classify_mine_kernel(const LossPar
     s_gbox[g] = q.gt_boxes[g0 + g];
     s_label[g] = int(map_label(q, q.gt_labels[g0 + g]));
   }
+  if (select)
+    for (int b = tid; b < kBins; b += kCmThreads) S.hist[b] = 0u;
 
   // everything above is independent of the match kernel's results; from here on they are needed
   asm volatile("griddepcontrol.wait;" ::: "memory");
@@ -1067,11 +1259,106 @@ __global__ void __launch_bounds__(kCmThreads) classify_mine_kernel(const LossPar
   }
   __syncthreads();  // the patched overlaps / objects are visible to the whole CTA
 
+  // ---- phase A: every prior of the slice, all loads of a thread's four priors in flight together ----
   double a_loc = 0.0, a_pos = 0.0, a_neg = 0.0;
   int npos = 0;
-  // Phase B: the recorded foreground rows (2-3 % of the priors), one per thread, every load of a row
-  // independent of the others (class, object and its box come from shared memory).
-  auto eval_foreground = [&]() {
+  {
+    float ov[kCmUnroll], ce[kCmUnroll];
+    int ob[kCmUnroll];
+    uint8_t ex[kCmUnroll];
+#pragma unroll
+    for (int u = 0; u < kCmUnroll; ++u) {
+      const int p = p_lo + u * kCmThreads + tid;
+      ov[u] = 0.f; ce[u] = 0.f; ob[u] = 0; ex[u] = 0;
+      if (p < p_hi) {
+        ov[u] = q.ov[base + p];
+        ob[u] = q.obj[base + p];
+        ce[u] = q.ce[base + p];  // background CE from the streaming kernel
+        if (q.exclude) ex[u] = q.exclude[base + p];
+      }
+    }
+    int rec[kCmUnroll], rrank[kCmUnroll];
+#pragma unroll
+    for (int u = 0; u < kCmUnroll; ++u) {
+      const int p = p_lo + u * kCmThreads + tid;
+      rec[u] = 0;
+      int digit = -1;
+      if (p < p_hi) {
+        int cls = 0;
+        if (!(ov[u] < q.thr_pos) && G > 0) cls = s_label[ob[u]];
+        const bool pos = cls > 0 && !ex[u];
+        const bool isneg = ov[u] < q.thr_neg;
+        uint8_t selbits = pos ? 1 : 0;
+        float v = -1.f;
+        if (cls > 0) {
+          rec[u] = min(cls, q.C - 1) | (pos ? 0x8000 : 0);  // C <= 16384 elsewhere; classes fit 15 bits
+        } else if (focal) {
+          if (isneg) {  // target class is 0 there (thr_neg < thr_pos)
+            selbits |= 2;
+            a_neg += double(focal_bg(q, ce[u]));
+          }
+        } else if (q.cls_kind == SBOD_CLS_CE_MINE_NONPOS) {
+          if (!ex[u]) v = ce[u];
+        } else {  // MINE_NEG, MINE_BATCH: only true_neg == -1 rows are candidates
+          if (isneg) v = ce[u];
+        }
+        if (!focal && v >= 0.f) {
+          a_neg += 1.0;  // mining modes: this partial counts the candidates (NaN CEs are none)
+          digit = int(__float_as_uint(v) >> 20);
+        }
+        q.sel[base + p] = selbits;
+        q.cand[base + p] = v;
+      }
+      if (select) {  // leading digit of the candidate: lanes with the same digit add once
+        const unsigned peers = __match_any_sync(0xffffffffu, digit);
+        if (digit >= 0 && lane == __ffs(peers) - 1) atomicAdd(&S.hist[digit], unsigned(__popc(peers)));
+      }
+      const unsigned bal = __ballot_sync(0xffffffffu, rec[u] != 0);
+      rrank[u] = __popc(bal & ((1u << lane) - 1u));
+      if (lane == 0) S.cnt[u][wid] = uint16_t(__popc(bal));
+    }
+    __syncthreads();
+    // list offsets of the (unroll slot, warp) pairs: exclusive scan of the 128 counts by warp 0; the list
+    // order is deterministic (unroll slot, warp, ballot rank), so the sums are reproducible
+    if (wid == 0) {
+      constexpr int kPairs = kCmUnroll * (kCmThreads / 32);
+      static_assert(kPairs == 128, "four (slot, warp) pairs per lane");
+      uint16_t* flat = &S.cnt[0][0];
+      int c[4], tot = 0;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        c[j] = flat[4 * lane + j];
+        tot += c[j];
+      }
+      int inc = tot;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += t;
+      }
+      int ex0 = inc - tot;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        flat[4 * lane + j] = uint16_t(ex0);
+        ex0 += c[j];
+      }
+      if (lane == 31) S.fg_n = inc;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int u = 0; u < kCmUnroll; ++u) {
+      if (rec[u]) {
+        const int slot = int(S.cnt[u][wid]) + rrank[u];
+        S.fg_idx[slot] = uint16_t(u * kCmThreads + tid);
+        S.fg_cls[slot] = uint16_t(rec[u]);
+        S.fg_obj[slot] = uint16_t(ob[u]);
+      }
+    }
+    __syncthreads();
+  }
+  // ---- phase B: the recorded foreground rows (2-3 % of the priors), one per thread, every load of a row
+  // independent of the others (class, object and its box come from shared memory) ----
+  {
     const int total = S.fg_n;
     for (int i = tid; i < total; i += kCmThreads) {
       const int pp = p_lo + int(S.fg_idx[i]);
@@ -1093,173 +1380,27 @@ __global__ void __launch_bounds__(kCmThreads) classify_mine_kernel(const LossPar
         a_loc += double(lt.loss);
       }
     }
-    __syncthreads();
-    if (tid == 0) S.fg_n = 0;
-    __syncthreads();
-  };
-
-  // Phase A: every prior of the slice, kCmUnroll per thread with all their loads in flight together:
-  // class, selection bits, mining candidate (kept in shared memory); foreground rows are recorded.
-  // The list order is deterministic (unroll slot, warp, ballot rank), so the sums are reproducible.
-  for (int pb = p_lo; pb < p_hi; pb += kCmThreads * kCmUnroll) {
-    float ov[kCmUnroll], ce[kCmUnroll];
-    int ob[kCmUnroll];
-    uint8_t ex[kCmUnroll];
-#pragma unroll
-    for (int u = 0; u < kCmUnroll; ++u) {
-      const int p = pb + u * kCmThreads + tid;
-      ov[u] = 0.f; ce[u] = 0.f; ob[u] = 0; ex[u] = 0;
-      if (p < p_hi) {
-        ov[u] = q.ov[base + p];
-        ob[u] = q.obj[base + p];
-        ce[u] = q.ce[base + p];  // background CE from the streaming kernel
-        if (q.exclude) ex[u] = q.exclude[base + p];
-      }
-    }
-    int rec[kCmUnroll], rrank[kCmUnroll];
-#pragma unroll
-    for (int u = 0; u < kCmUnroll; ++u) {
-      const int p = pb + u * kCmThreads + tid;
-      rec[u] = 0;
-      if (p < p_hi) {
-        int cls = 0;
-        if (!(ov[u] < q.thr_pos) && G > 0) cls = s_label[ob[u]];
-        const bool pos = cls > 0 && !ex[u];
-        const bool isneg = ov[u] < q.thr_neg;
-        uint8_t selbits = pos ? 1 : 0;
-        float v = -1.f;
-        if (cls > 0) {
-          rec[u] = min(cls, q.C - 1) | (pos ? 0x8000 : 0);  // C <= 16384 elsewhere; classes fit 15 bits
-        } else if (focal) {
-          if (isneg) {  // target class is 0 there (thr_neg < thr_pos)
-            selbits |= 2;
-            a_neg += double(focal_bg(q, ce[u]));
-          }
-        } else if (q.cls_kind == SBOD_CLS_CE_MINE_NONPOS) {
-          if (!ex[u]) v = ce[u];
-        } else {  // MINE_NEG, MINE_BATCH: only true_neg == -1 rows are candidates
-          if (isneg) v = ce[u];
-        }
-        if (!focal && v >= 0.f) a_neg += 1.0;  // mining modes: this partial counts the candidates (NaN CEs are none)
-        q.sel[base + p] = selbits;
-        q.cand[base + p] = v;
-        if (cached) s_vals[p - p_lo] = v;
-      }
-      const unsigned bal = __ballot_sync(0xffffffffu, rec[u] != 0);
-      rrank[u] = __popc(bal & ((1u << lane) - 1u));
-      if (lane == 0) S.cnt[u][wid] = uint16_t(__popc(bal));
-    }
-    __syncthreads();
-    {
-      // list offsets of the (unroll slot, warp) pairs: one exclusive scan of the 64 counts by warp 0
-      if (wid == 0) {
-        constexpr int kPairs = kCmUnroll * (kCmThreads / 32);
-        static_assert(kPairs == 64, "two (slot, warp) pairs per lane");
-        uint16_t* flat = &S.cnt[0][0];
-        const int c0 = flat[2 * lane], c1 = flat[2 * lane + 1];
-        int inc = c0 + c1;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-          const int t = __shfl_up_sync(0xffffffffu, inc, o);
-          if (lane >= o) inc += t;
-        }
-        const int ex = inc - (c0 + c1);
-        flat[2 * lane] = uint16_t(ex);
-        flat[2 * lane + 1] = uint16_t(ex + c0);
-        if (lane == 31) S.carry = inc;  // entries added by this group of priors
-      }
-      __syncthreads();
-      const int at0 = S.fg_n;
-      const int at = at0 + S.carry;
-#pragma unroll
-      for (int u = 0; u < kCmUnroll; ++u) {
-        if (rec[u]) {
-          const int slot = at0 + int(S.cnt[u][wid]) + rrank[u];
-          S.fg_idx[slot] = uint32_t(pb + u * kCmThreads + tid - p_lo);
-          S.fg_cls[slot] = uint16_t(rec[u]);
-          S.fg_obj[slot] = uint16_t(ob[u]);
-        }
-      }
-      __syncthreads();
-      if (tid == 0) S.fg_n = at;
-      __syncthreads();
-      if (at + kCmThreads * kCmUnroll > kCmFgCap) eval_foreground();  // CTA-uniform
+  }
+  // ---- publish: leading-digit histogram, partial sums, ticket ----
+  if (select) {
+    unsigned int* gh = q.sel_hist + size_t(n) * kBins;
+    for (int b = tid; b < kBins; b += kCmThreads) {
+      const unsigned int v = S.hist[b];
+      if (v) atomicAdd(&gh[b], v);
     }
   }
-  eval_foreground();
-
   double tot[4] = {a_loc, a_pos, a_neg, double(npos)};
   block_sum4_to_thread0(tot, S.red4);
   if (tid == 0) {
-    S.part[0] = tot[0]; S.part[1] = tot[1]; S.part[2] = tot[2]; S.part[3] = tot[3];
+    double* bp = q.blockpart + (size_t(n) * slices + blockIdx.x) * 4;
+    bp[0] = tot[0]; bp[1] = tot[1]; bp[2] = tot[2]; bp[3] = tot[3];
   }
-  cluster.sync();  // every slice's partial sums are published; every CTA has read the object keys
-  double img[4] = {0.0, 0.0, 0.0, 0.0};
-  for (unsigned int rk = 0; rk < n_ranks; ++rk) {  // rank order: the same sums in every CTA
-    const double* pp = cluster.map_shared_rank(S.part, rk);
-    img[0] += pp[0]; img[1] += pp[1]; img[2] += pp[2]; img[3] += pp[3];
-  }
-  // leave the per-object keys clean for the next call
-  if (rank == 0)
-    for (int g = tid; g < G; g += kCmThreads) q.gtkey[size_t(n) * q.gmax + g] = 0ull;
-
-  double t_neg = 0.0;
-  SelectResult r;
-  r.take_ties = 0; r.thr_bits = 0; r.k_eff = 0;
-  const bool select = !focal && q.cls_kind != SBOD_CLS_CE_MINE_BATCH;
-  if (select) {
-    const long long k = (long long)(q.ratio) * (long long)(img[3] + 0.5);
-    const float* vals = cached ? s_vals : q.cand + base + p_lo;
-    r = cluster_topk_sum(cluster, S.sel, vals, n_local, k, (long long)(img[2] + 0.5),
-                         q.sel_hist + size_t(n) * 3 * kBins, q.sel + base + p_lo);
-  } else if (tid == 0) {
-    S.sel.sumv = 0.0;
-  }
-  cluster.sync();  // the slices' selected sums are published
-  if (select && rank == 0) cluster_topk_cleanup(q.sel_hist + size_t(n) * 3 * kBins);
-  if (rank == 0 && tid == 0) {
-    if (focal) {
-      t_neg = img[2];
-    } else if (q.cls_kind == SBOD_CLS_CE_MINE_BATCH) {
-      t_neg = img[2];  // number of candidates of the image; mine_batch_kernel turns the batch total into the mined sum
-    } else {
-      for (unsigned int rk = 0; rk < n_ranks; ++rk) t_neg += *cluster.map_shared_rank(&S.sel.sumv, rk);
-      if (r.k_eff > 0) t_neg += double(r.take_ties) * double(__uint_as_float(r.thr_bits));
-    }
-    q.partials[n * 4 + 0] = img[0];
-    q.partials[n * 4 + 1] = img[1];
-    q.partials[n * 4 + 2] = t_neg;
-    q.partials[n * 4 + 3] = img[3];
-    __threadfence();
-    const unsigned int ticket = atomicAdd(&q.counters[0], 1u);
-    S.last = (ticket == unsigned(q.N) - 1u) ? 1 : 0;
-  }
-  cluster.sync();  // rank 0 is done reading its peers' shared memory: they may exit
-  if (rank != 0) return;
-  if (S.last && tid < 32) {  // the last image folds the batch in image order (deterministic)
-    __threadfence();
-    double acc = 0.0;
-    if (tid < 4) {
-      const volatile double* pp = q.partials;
-      for (int i = 0; i < q.N; ++i) acc += pp[i * 4 + tid];
-    }
-    if (q.comm) {
-      // sharded batch: the four sums of this rank meet those of the other ranks through the NVLink mailboxes
-      // (every rank adds them in rank order); the loss is then formed from the global sums, and the backward
-      // scales by the global 1 / n_pos
-      double v[4];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) v[i] = __shfl_sync(0xffffffffu, acc, i);
-      comm_allreduce_sum(q.comm, v, 4);
-      acc = tid < 4 ? v[tid & 3] : 0.0;
-    }
-    if (tid < 4) q.sums[tid] = acc;
-  }
+  __threadfence();  // this slice's selection bits, candidates, histogram and partials before its ticket
   __syncthreads();
-  if (S.last && tid == 0) {
-    q.counters[0] = 0u;
-    if (q.cls_kind != SBOD_CLS_CE_MINE_BATCH) finalize_loss(q, q.sums, q.loss);
-  }
+  if (tid == 0) S.last = (atomicAdd(&q.img_done[n], 1u) == unsigned(slices) - 1u) ? 1 : 0;
+  __syncthreads();
+  if (!S.last) return;
+  cm_image_tail(q, S, n, slices);
 }
 
 // SSD300's batch-global mining (SSD300.py:580-588): the sum(3 * n_pos) largest CEs over every true_neg == -1
@@ -1274,9 +1415,9 @@ __global__ void __launch_bounds__(1024) mine_batch_kernel(const LossParams q) {
   const long long lo = min(total, (long long)rank * slice), hi = min(total, lo + slice);
   const long long k = (long long)(q.ratio) * (long long)(q.sums[3] + 0.5);
   const long long n_cand = (long long)(q.sums[2] + 0.5);  // candidates of the batch, counted by classify_mine_kernel
-  const SelectResult r = cluster_topk_sum(cluster, S, q.cand + lo, int(hi - lo), k, n_cand, q.sel_hist, q.sel + lo);
+  const SelectResult r = cluster_topk_sum(cluster, S, q.cand + lo, int(hi - lo), k, n_cand, q.batch_hist, q.sel + lo);
   cluster.sync();
-  if (rank == 0) cluster_topk_cleanup(q.sel_hist);
+  if (rank == 0) cluster_topk_cleanup(q.batch_hist);
   if (rank == 0 && threadIdx.x == 0) {
     double t = 0.0;
     for (unsigned int rk = 0; rk < n_ranks; ++rk) t += *cluster.map_shared_rank(&S.sumv, rk);
@@ -1640,12 +1781,11 @@ static Tiling choose_tiling(int C, int max_stages) {
 // Process-wide switches (A/B measurements; defaults are the fast settings).
 static int g_opt_pdl = 1;           // programmatic dependent launch between the kernels of one call
 static int g_opt_peer_exchange = 1; // one-shot NVLink exchange of the loss sums when a communicator is attached
-static int g_opt_cm_cluster = 0;    // CTAs per image of classify_mine_kernel (0 = automatic)
 
-static size_t cm_smem_bytes(const LossParams& q, bool cached) {
-  const size_t slice = (size_t(q.P) + q.cm_cluster - 1) / q.cm_cluster;
-  return ((sizeof(CmShared) + 127) & ~size_t(127)) + align_up(size_t(q.gmax) * 28, 128) + (cached ? slice * 4 : 0) + 128;
+static size_t cm_smem_bytes(const LossParams& q) {
+  return ((sizeof(CmShared) + 127) & ~size_t(127)) + align_up(size_t(q.gmax) * 28, 128) + 128;
 }
+static int cm_slices(int P) { return (P + kCmSlice - 1) / kCmSlice; }
 
 static int fill_params(const sbod_loss_desc* d, LossParams& q, bool need_scores) {
   if (!d) return SBOD_ERR_INVALID;
@@ -1696,8 +1836,14 @@ static int fill_params(const sbod_loss_desc* d, LossParams& q, bool need_scores)
   q.match_q = reinterpret_cast<unsigned int*>(w);
   w += align_up(size_t(q.N) * 4, 256);
   q.sel_hist = reinterpret_cast<unsigned int*>(w);
-  w += align_up(size_t(q.N) * 3 * kBins * 4, 256);
+  w += align_up(size_t(q.N) * kBins * 4, 256);
+  q.batch_hist = reinterpret_cast<unsigned int*>(w);
+  w += align_up(size_t(3) * kBins * 4, 256);
+  q.img_done = reinterpret_cast<unsigned int*>(w);
+  w += align_up(size_t(q.N) * 4, 256);
   q.cand = reinterpret_cast<float*>(w);
+  w += align_up(size_t(q.N) * q.P * 4, 256);
+  q.blockpart = reinterpret_cast<double*>(w);
   Tiling t = choose_tiling(need_scores ? d->C : 1, kMaxStages);
   // the two-threads-per-row layout is bank-conflict free only for odd C; even C is merely slower in smem
   q.fast = (need_scores && d->C >= 2 && d->C <= 128) ? 1 : 0;
@@ -1727,12 +1873,7 @@ static int fill_params(const sbod_loss_desc* d, LossParams& q, bool need_scores)
     q.debug_skip = e ? atoi(e) : 0;
   }
 #endif
-  // classify_mine_kernel: a cluster of CTAs per image, as large as keeps the whole batch co-resident
-  q.cm_cluster = 1;
-  while (q.cm_cluster < kCmMaxCluster && q.N * q.cm_cluster * 2 <= sm_count() && q.P / (q.cm_cluster * 2) >= 2048)
-    q.cm_cluster *= 2;
-  if (g_opt_cm_cluster) q.cm_cluster = g_opt_cm_cluster;
-  q.mine_cache = (cm_smem_bytes(q, true) <= 200 * 1024) ? 1 : 0;
+  q.mine_cache = 0;
   return SBOD_OK;
 }
 
@@ -1743,21 +1884,21 @@ using namespace sbod;
 extern "C" size_t sbod_loss_workspace_bytes(const sbod_loss_desc* d) {
   if (!d) return 0;
   const int gmax = d->gmax > 0 ? d->gmax : 1;
-  return 256 + align_up(size_t(d->N) * gmax * 8, 256) + align_up(size_t(d->N) * 4, 256) +
-         align_up(size_t(d->N) * 3 * kBins * 4, 256) + align_up(size_t(d->N) * d->P * 4, 256);
+  return sbod_loss_workspace_zero_bytes(d) + align_up(size_t(d->N) * d->P * 4, 256) +
+         align_up(size_t(d->N) * size_t(cm_slices(d->P)) * 32, 256);
 }
 
 // leading bytes of the loss workspace that carry the zero contract: counters, per-object keys, ticket queues
 extern "C" size_t sbod_loss_workspace_zero_bytes(const sbod_loss_desc* d) {
   if (!d) return 0;
   const int gmax = d->gmax > 0 ? d->gmax : 1;
-  return 256 + align_up(size_t(d->N) * gmax * 8, 256) + align_up(size_t(d->N) * 4, 256);
+  return 256 + align_up(size_t(d->N) * gmax * 8, 256) + align_up(size_t(d->N) * 4, 256) +
+         align_up(size_t(d->N) * kBins * 4, 256) + align_up(size_t(3) * kBins * 4, 256) + align_up(size_t(d->N) * 4, 256);
 }
 
 extern "C" int sbod_set_option(int key, int value) {
   if (key == SBOD_OPT_PDL) g_opt_pdl = value ? 1 : 0;
   else if (key == SBOD_OPT_PEER_EXCHANGE) g_opt_peer_exchange = value ? 1 : 0;
-  else if (key == SBOD_OPT_CM_CLUSTER) g_opt_cm_cluster = (value == 1 || value == 2 || value == 4 || value == 8) ? value : 0;
   else return SBOD_ERR_INVALID;
   return SBOD_OK;
 }
@@ -1818,19 +1959,15 @@ static int launch_mine(const LossParams& q, cudaStream_t st) {
   if (rc) return rc;
   {
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(unsigned(q.N) * unsigned(q.cm_cluster), 1, 1);
+    cfg.gridDim = dim3(unsigned(cm_slices(q.P)), unsigned(q.N), 1);
     cfg.blockDim = dim3(kCmThreads, 1, 1);
-    cfg.dynamicSmemBytes = cm_smem_bytes(q, q.mine_cache != 0);
+    cfg.dynamicSmemBytes = cm_smem_bytes(q);
     cfg.stream = st;
-    cudaLaunchAttribute attrs[2];
-    attrs[0].id = cudaLaunchAttributeClusterDimension;
-    attrs[0].val.clusterDim.x = unsigned(q.cm_cluster);
-    attrs[0].val.clusterDim.y = 1;
-    attrs[0].val.clusterDim.z = 1;
-    attrs[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attrs[1].val.programmaticStreamSerializationAllowed = 1;
+    cudaLaunchAttribute attrs[1];
+    attrs[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attrs[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attrs;
-    cfg.numAttrs = g_opt_pdl ? 2 : 1;
+    cfg.numAttrs = g_opt_pdl ? 1 : 0;
     SBOD_CUDA_TRY(cudaLaunchKernelEx(&cfg, classify_mine_kernel, q));
   }
   if (q.cls_kind == SBOD_CLS_CE_MINE_BATCH) {

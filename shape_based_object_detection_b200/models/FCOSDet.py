@@ -177,7 +177,11 @@ class FCOSLoss(nn.Module):
     def forward(self, predicted_locs, predicted_scores, predicted_centerness, boxes, labels):
         L.need_cuda(predicted_locs, predicted_scores, predicted_centerness)
         assert predicted_locs.size(1) == predicted_scores.size(1)  # FCOSDet.py:500
-        gt = pack_ground_truth(boxes, labels, predicted_scores.device)
+        from ..dataset.collate import PackedGT
+        if isinstance(boxes, PackedGT):
+            gt = (boxes if boxes.device == predicted_scores.device else boxes.to(predicted_scores.device)).as_tuple()
+        else:
+            gt = pack_ground_truth(boxes, labels, predicted_scores.device)
         return _FcosFn.apply(predicted_locs, predicted_scores, predicted_centerness, self, gt)
 
 

@@ -81,3 +81,21 @@ MAP_CASES = {
 def map_inputs(case):
     from shape_based_object_detection_b200 import synth
     return synth.make_map_case(case["n_images"], case["n_classes"], case["gmax"], case["dets"], case["seed"])
+
+
+def crop_inputs(seed):
+    import torch
+    """Seeded image / boxes / labels of the random_crop fixtures (shared with the tests through this module)."""
+    g = torch.Generator().manual_seed(seed)
+    h, w = 240 + 16 * (seed % 5), 320 - 8 * (seed % 7)
+    image = torch.rand((3, h, w), generator=g)
+    n = 3 + seed % 6
+    c = torch.rand((n, 2), generator=g) * torch.tensor([w * 0.8, h * 0.8]) + torch.tensor([w * 0.1, h * 0.1])
+    wh = torch.rand((n, 2), generator=g) * torch.tensor([w * 0.3, h * 0.3]) + 8.0
+    boxes = torch.cat([c - wh / 2, c + wh / 2], 1)
+    boxes[:, 0::2].clamp_(0, w - 1)
+    boxes[:, 1::2].clamp_(0, h - 1)
+    labels = torch.randint(1, 21, (n,), generator=g)
+    return image, boxes, labels
+
+

@@ -18,4 +18,4 @@ def golden():
     import numpy as np
     gdir = os.path.join(REPO, "tests", "golden")
     return {name: np.load(os.path.join(gdir, name + ".npz")) for name in ("operators", "losses", "detect",
-                                                                           "priors_meta", "map", "extras")}
+                                                                           "priors_meta", "map", "extras", "crop")}

@@ -480,3 +480,52 @@ def test_prior_tables_generated_on_the_gpu(dev):
         gpu = compute_location(device=dev, image_size=size)
         assert len(host) == len(gpu) == 5
         assert all(torch.equal(a, b.cpu()) for a, b in zip(host, gpu))
+
+
+def test_packed_ground_truth_single_copy(dev):
+    """the batch's ground truth in one pinned CSR buffer (dataset.collate), ONE H2D copy; the
+    loss modules take it in place of the `boxes` list and give the same loss and gradients bit for bit."""
+    from shape_based_object_detection_b200 import priors as PR, synth
+    from shape_based_object_detection_b200.dataset.collate import collate_fn
+    from shape_based_object_detection_b200.models import MultiBoxLoss512
+    pri = PR.ssd512_priors()
+    locs, scores, bx, lb = synth.make_train_batch(pri, 6, 21, 30, 9)
+    batch = [(torch.zeros(1), bx[i], lb[i], i, torch.zeros(bx[i].size(0), dtype=torch.uint8)) for i in range(6)]
+    _, boxes, labels, _, _ = collate_fn(batch)
+    assert boxes.packed.buf.is_pinned()
+    crit = MultiBoxLoss512(pri.to(dev), cfg(n_classes=21))
+    outs = []
+    for mode in ("lists_on_device", "lists_on_host", "packed"):
+        l_d, s_d = locs.to(dev).requires_grad_(True), scores.to(dev).requires_grad_(True)
+        if mode == "lists_on_device":
+            loss = crit(l_d, s_d, [b.to(dev) for b in boxes], [l.to(dev) for l in labels])
+        elif mode == "lists_on_host":
+            loss = crit(l_d, s_d, list(boxes), labels)
+        else:
+            loss = crit(l_d, s_d, boxes.packed.to(dev), None)
+        loss.backward()
+        outs.append((loss.item(), l_d.grad.clone(), s_d.grad.clone()))
+    for o in outs[1:]:
+        assert o[0] == outs[0][0] and torch.equal(o[1], outs[0][1]) and torch.equal(o[2], outs[0][2])
+
+
+def test_random_crop_matches_the_reference_and_its_random_stream(golden, dev):
+    """dataset/transforms.py:124-205 random_crop, the CPU user of find_jaccard_overlap, on CUDA
+    tensors: the overlaps of a round's trial crops come from one dense-IoU launch. Fixtures from the reference
+    itself (oracle/make_golden.py --only-crop): crop, boxes, labels and the NEXT draw of python's random."""
+    import random
+    from cases import crop_inputs
+    from shape_based_object_detection_b200.dataset.transforms import random_crop
+    G = golden["crop"]
+    cropped = 0
+    for seed in range(24):
+        image, boxes, labels = crop_inputs(seed)
+        random.seed(1000 + seed)
+        ni, nb, nl = random_crop(image.to(dev), boxes.to(dev), labels.to(dev))
+        assert tuple(ni.shape) == tuple(G["s%d_shape" % seed].tolist()), seed
+        assert abs(ni.double().sum().item() - float(G["s%d_sum" % seed])) <= 1e-6 * float(G["s%d_sum" % seed])
+        assert torch.equal(nb.cpu(), torch.from_numpy(G["s%d_boxes" % seed])), seed
+        assert torch.equal(nl.cpu(), torch.from_numpy(G["s%d_labels" % seed])), seed
+        assert random.random() == float(G["s%d_next" % seed]), seed
+        cropped += int(tuple(ni.shape) != tuple(image.shape))
+    assert cropped >= 10

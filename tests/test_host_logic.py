@@ -151,3 +151,30 @@ def test_coco_format_results_matches_the_reference_loop():
     assert got == want
     assert coco_format_results([torch.zeros((0, 4))], [torch.zeros((0,), dtype=torch.long)], [torch.zeros((0,))],
                                [1], [(10, 10)], cat) == []
+
+
+def test_collate_fn_packs_the_batch_into_one_csr_buffer():
+    """dataset.collate.collate_fn == the reference's Datasets.collate_fn (Datasets.py:58-86)
+    plus the whole batch's ground truth in one (pinned) CSR buffer: one H2D copy instead of 2N."""
+    from shape_based_object_detection_b200.dataset.collate import PackedGT, collate_fn
+    g = torch.Generator().manual_seed(4)
+    counts = [3, 0, 7, 1]
+    batch = [(torch.rand((3, 8, 8), generator=g), torch.rand((n, 4), generator=g),
+              torch.randint(1, 21, (n,), generator=g), 100 + i, torch.zeros(n, dtype=torch.uint8))
+             for i, n in enumerate(counts)]
+    images, boxes, labels, ids, diffs = collate_fn(batch)
+    assert images.shape == (4, 3, 8, 8) and ids == [100, 101, 102, 103] and len(diffs) == 4
+    assert isinstance(boxes, list) and all(torch.equal(a, b[1]) for a, b in zip(boxes, batch))  # reference semantics
+    p = boxes.packed
+    assert p.offsets.tolist() == [0, 3, 3, 10, 11] and p.gmax == 7 and p.total == 11
+    assert torch.equal(p.boxes, torch.cat([b[1] for b in batch])) and p.boxes.data_ptr() % 16 == 0
+    assert torch.equal(p.labels, torch.cat([b[2] for b in batch]))
+    bl, ll = p.lists()
+    assert all(torch.equal(a, b[1]) for a, b in zip(bl, batch)) and all(torch.equal(a, b[2]) for a, b in zip(ll, batch))
+    q = p.to("cpu")  # the single copy
+    assert torch.equal(q.boxes, p.boxes) and q.as_tuple()[3] == 7
+    # same CSR as the device-side packer of the fused loss
+    b2, l2, o2, gmax = core.pack_ground_truth([b[1] for b in batch], [b[2] for b in batch], torch.device("cpu"))
+    assert torch.equal(b2, p.boxes) and torch.equal(l2, p.labels) and torch.equal(o2, p.offsets) and gmax == p.gmax
+    empty = PackedGT.from_lists([torch.zeros((0, 4))], [torch.zeros((0,), dtype=torch.long)], pin=False)
+    assert empty.offsets.tolist() == [0, 0] and empty.boxes.shape == (1, 4)

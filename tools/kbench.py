@@ -30,7 +30,7 @@ spec = core.LossSpec(reg_kind=REG, cls_kind=CLS)
 st = core.LossState(spec, pri_d, pxy, locs.to(dev), scores.to(dev), gt, prefill_grad=bool(int(os.environ.get("KB_PREFILL", "0"))))
 lib = L.lib()
 sp = L.stream_ptr()
-for key, env in ((0, "KB_PDL"), (2, "KB_CM_CLUSTER")):  # sbod_set_option switches for A/B runs
+for key, env in ((0, "KB_PDL"),):  # sbod_set_option switches for A/B runs
     if env in os.environ:
         L.check(lib.sbod_set_option(key, int(os.environ[env])))
 
