@@ -64,6 +64,7 @@ struct DetParams {
   // row bounds (exact two-step candidate generation, see detect_bound_kernel)
   float* pbound;                // [N, P] upper bound of the best foreground probability of each prior
   unsigned int* rhist;          // [N, kMaxBins] histogram of the row bounds (same bins as the candidate keys)
+  unsigned int* cutoff;         // [N] first-band cutoff of each image (written by the refine pass, read by the NMS)
   int rows_target;              // rows evaluated per image in the first band
   int32_t* agn_label;           // [N, P] arg-max class of each prior (class-agnostic mode)
   unsigned int* nms_mask;       // [N, kChunk, kChunk/32] suppression bits of large class segments
@@ -319,112 +320,99 @@ __device__ unsigned int compute_cutoff(const DetParams& q, const unsigned int* s
 }
 
 // ------------------------------------------------------------------------------------------
-// Exact evaluation of one prior row by one warp (lane k handles classes k, k + 32, ...): activation as
-// torch computes it (max shift, accurate exp, true division), then every (class, prior) whose probability
-// exceeds min_score and whose key lies in [k_lo, k_hi) is emitted through `reserve` (returns the first of
-// `count` consecutive slots, called by lane 0) / `put` (slot, key). Class-agnostic mode emits the row's
-// best foreground class once, with class field 1, and records the arg-max class.
+// Exact evaluation of prior rows, FOUR rows per warp: an octet (8 lanes) owns a row, lane s of the octet
+// handles classes s, s + 8, ... (one 32-byte sector per row and step). A whole warp per row cost ~500 warp
+// instructions per row, nearly all of them control / shuffles replicated over 32 lanes (measured: the refine
+// pass was issue-bound at 30 M warp instructions); an octet per row needs about a quarter of that.
+// Activation as torch computes it (max shift, accurate exp, true division); a class is evaluated exactly only
+// if a cheap estimate says it can pass. Every (class, prior) whose probability exceeds min_score and whose key
+// lies in [k_lo, k_hi) is emitted through `emit(key)`. Class-agnostic mode emits the row's best foreground
+// class once, with class field 1, and records the arg-max class.
+// All 32 lanes must call this; `p` < 0 marks an idle octet.
 // ------------------------------------------------------------------------------------------
-constexpr int kRowRegs = 4;  // classes per lane kept in registers (C <= 128); larger rows are re-read (L1)
-
-// the row's activation, as torch computes it: values of this lane's classes lane, lane + 32, ...
-struct RowProbs {
-  float x[kRowRegs];
-  float mx, sum;
-};
-SBOD_DEVINL void row_load(const DetParams& q, const float* __restrict__ x, int lane, RowProbs& R) {
-  const float NEG = -__int_as_float(0x7f800000);
-#pragma unroll
-  for (int j = 0; j < kRowRegs; ++j) {
-    const int k = lane + 32 * j;
-    R.x[j] = k < q.C ? ld_stream_f32(x + k) : NEG;
-  }
+SBOD_DEVINL float octet_max(float v) {
+  v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 1));
+  v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 2));
+  return fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 4));
 }
-SBOD_DEVINL void row_prepare(const DetParams& q, const float* __restrict__ x, int lane, RowProbs& R) {
-  const float NEG = -__int_as_float(0x7f800000);
-  R.mx = 0.f;
-  R.sum = 1.f;
-  if (q.act_kind != SBOD_ACT_SOFTMAX) return;
-  float m = NEG;
-#pragma unroll
-  for (int j = 0; j < kRowRegs; ++j) m = fmaxf(m, R.x[j]);
-  for (int k = lane + 32 * kRowRegs; k < q.C; k += 32) m = fmaxf(m, x[k]);
-  R.mx = warp_max(m);
-  float s = 0.f;
-#pragma unroll
-  for (int j = 0; j < kRowRegs; ++j)
-    if (lane + 32 * j < q.C) s += expf(R.x[j] - R.mx);
-  for (int k = lane + 32 * kRowRegs; k < q.C; k += 32) s += expf(x[k] - R.mx);
-  R.sum = warp_sum(s);
-}
-SBOD_DEVINL float row_prob(const DetParams& q, const RowProbs& R, float v) {
-  if (q.act_kind == SBOD_ACT_SOFTMAX) return __fdiv_rn(expf(v - R.mx), R.sum);
-  if (q.act_kind == SBOD_ACT_SIGMOID) return __fdiv_rn(1.f, 1.f + expf(-v));
-  return v;
+SBOD_DEVINL float octet_sum(float v) {
+  v += __shfl_xor_sync(0xffffffffu, v, 1);
+  v += __shfl_xor_sync(0xffffffffu, v, 2);
+  return v + __shfl_xor_sync(0xffffffffu, v, 4);
 }
 
-template <typename Reserve, typename Put>
-SBOD_DEVINL void eval_row(const DetParams& q, int n, int p, int lane, uint32_t k_lo, uint32_t k_hi, RowProbs& R,
-                          Reserve&& reserve, Put&& put) {
+template <typename Emit>
+SBOD_DEVINL void eval_rows(const DetParams& q, int n, int p, int lane, uint32_t k_lo, uint32_t k_hi, Emit&& emit) {
   const int C = q.C;
-  const float* x = q.scores + (size_t(n) * q.P + p) * size_t(C);
-  row_prepare(q, x, lane, R);
-  const int n_chunks = (C + 31) >> 5;
+  const int s = lane & 7;
+  const bool on = p >= 0;
+  const float* x = q.scores + (size_t(n) * q.P + (on ? p : 0)) * size_t(C);
+  const float NEG = -__int_as_float(0x7f800000);
+  float mx = 0.f, sum = 1.f;
+  if (q.act_kind == SBOD_ACT_SOFTMAX) {
+    float m = NEG;
+    if (on)
+      for (int k = s; k < C; k += 8) m = fmaxf(m, __ldg(x + k));
+    mx = octet_max(m);
+    float acc = 0.f;
+    if (on)
+      for (int k = s; k < C; k += 8) acc += expf(__ldg(x + k) - mx);
+    sum = octet_sum(acc);
+  }
+  // lowest probability that can still be emitted (with a margin for the estimate below)
+  const float floor_p = fmaxf(q.min_score, k_hi > kOneBits ? 0.f : __uint_as_float(kOneBits - k_hi)) * 0.999f;
+  const float inv_est = q.act_kind == SBOD_ACT_SOFTMAX ? __frcp_rn(sum) : 1.f;
+  auto prob = [&](float v) -> float {
+    if (q.act_kind == SBOD_ACT_SOFTMAX) return __fdiv_rn(expf(v - mx), sum);
+    if (q.act_kind == SBOD_ACT_SIGMOID) return __fdiv_rn(1.f, 1.f + expf(-v));
+    return v;
+  };
+  auto estimate = [&](float v) -> float {  // within 1e-5 relative of prob()
+    if (q.act_kind == SBOD_ACT_SOFTMAX) return __expf(v - mx) * inv_est;
+    if (q.act_kind == SBOD_ACT_SIGMOID) return __frcp_rn(1.f + __expf(-v));
+    return v;
+  };
   if (q.agnostic) {
     // best foreground class of the row, first index among ties (torch.max, models/utils.py:135)
     unsigned long long best = 0ull;  // (probability bits : ~class): max = best probability, then lowest class
-    for (int j = 0; j < n_chunks; ++j) {
-      const int k = lane + 32 * j;
-      if (k == 0 || k >= C) continue;
-      const float pr = row_prob(q, R, j < kRowRegs ? R.x[j < kRowRegs ? j : 0] : x[k]);
-      if (pr > q.min_score) {
-        const unsigned long long key = (static_cast<unsigned long long>(__float_as_uint(pr)) << 32) | (0xffffffffu - unsigned(k));
-        if (key > best) best = key;
+    if (on)
+      for (int k = s; k < C; k += 8) {
+        if (k == 0) continue;
+        const float v = __ldg(x + k);
+        if (!(estimate(v) > floor_p)) continue;
+        const float pr = prob(v);
+        if (pr > q.min_score) {
+          const unsigned long long key = (static_cast<unsigned long long>(__float_as_uint(pr)) << 32) | (0xffffffffu - unsigned(k));
+          if (key > best) best = key;
+        }
       }
-    }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
+    for (int o = 1; o < 8; o <<= 1) {
       const unsigned long long other = __shfl_xor_sync(0xffffffffu, best, o);
       if (other > best) best = other;
     }
-    if (best != 0ull && lane == 0) {
+    if (on && s == 0 && best != 0ull) {
       const float pr = __uint_as_float(uint32_t(best >> 32));
       const int cls = int(0xffffffffu - uint32_t(best & 0xffffffffull));
       const uint32_t k32 = score_k32(pr);
       if (k32 >= k_lo && k32 < k_hi) {
-        const unsigned int slot = reserve(1u);
-        put(slot, (static_cast<unsigned long long>(k32) << 32) | (1ull << kPriorBits) | static_cast<unsigned long long>(p));
+        emit((static_cast<unsigned long long>(k32) << 32) | (1ull << kPriorBits) | static_cast<unsigned long long>(p));
         q.agn_label[size_t(n) * q.P + p] = cls;
       }
     }
     return;
   }
-  for (int j = 0; j < n_chunks; ++j) {
-    const int k = lane + 32 * j;
-    bool is = false;
-    uint32_t k32 = 0;
-    if (k < C && k >= 1) {
-      float v;
-      if (j == 0) v = R.x[0];
-      else if (j == 1) v = R.x[1];
-      else if (j == 2) v = R.x[2];
-      else if (j == 3) v = R.x[3];
-      else v = x[k];
-      const float pr = row_prob(q, R, v);
-      k32 = score_k32(pr);
-      is = pr > q.min_score && k32 >= k_lo && k32 < k_hi;
+  if (on)
+    for (int k = s; k < C; k += 8) {
+      if (k == 0) continue;
+      const float v = __ldg(x + k);
+      if (!(estimate(v) > floor_p)) continue;
+      const float pr = prob(v);
+      const uint32_t k32 = score_k32(pr);
+      if (pr > q.min_score && k32 >= k_lo && k32 < k_hi)
+        emit((static_cast<unsigned long long>(k32) << 32) | (static_cast<unsigned long long>(k) << kPriorBits) |
+             static_cast<unsigned long long>(p));
     }
-    const unsigned bal = __ballot_sync(0xffffffffu, is);
-    if (bal) {
-      unsigned int base = 0;
-      if (lane == 0) base = reserve(unsigned(__popc(bal)));
-      base = __shfl_sync(0xffffffffu, base, 0);
-      if (is)
-        put(base + __popc(bal & ((1u << lane) - 1u)),
-            (static_cast<unsigned long long>(k32) << 32) | (static_cast<unsigned long long>(k) << kPriorBits) |
-                static_cast<unsigned long long>(p));
-    }
-  }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -444,7 +432,7 @@ __global__ void __launch_bounds__(kRefThreads) detect_refine_kernel(const DetPar
   __shared__ unsigned int s_scratch[40];
   __shared__ __align__(16) unsigned long long s_keys[kRefKeyBuf];  // first: the image's bound histogram (kMaxBins uints)
   __shared__ int s_rows[kRefMaxRows];
-  __shared__ unsigned int s_nrows, s_ncand, s_gbase, s_hole;
+  __shared__ unsigned int s_nrows, s_ncand, s_gbase;
   const int n = blockIdx.y, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int p_lo = blockIdx.x * rows_per_cta, p_hi = min(q.P, p_lo + rows_per_cta);
   {
@@ -455,9 +443,9 @@ __global__ void __launch_bounds__(kRefThreads) detect_refine_kernel(const DetPar
   if (tid == 0) {
     s_nrows = 0u;
     s_ncand = 0u;
-    s_hole = 0xffffffffu;
   }
   const unsigned int cut = compute_cutoff(q, reinterpret_cast<unsigned int*>(s_keys), s_scratch);
+  if (blockIdx.x == 0 && tid == 0) q.cutoff[n] = cut;  // the NMS kernel reads it instead of recomputing it
   // rows of this CTA whose bound is above the cutoff
   for (int pb = p_lo; pb < p_hi; pb += kRefThreads) {
     const int p = pb + tid;
@@ -476,34 +464,24 @@ __global__ void __launch_bounds__(kRefThreads) detect_refine_kernel(const DetPar
   const int n_rows = int(s_nrows);
   unsigned long long* g_list = q.cand + size_t(n) * q.cand_cap;
   unsigned int* g_hist = q.hist + size_t(n) * kMaxBins;
-  auto reserve = [&](unsigned int count) -> unsigned int {
-    const unsigned int at = atomicAdd(&s_ncand, count);
-    if (at + count <= unsigned(kRefKeyBuf)) return at;
-    // The shared buffer is full: this block of keys goes straight to the global list. The one reservation
-    // that straddles the capacity leaves a hole behind it: the buffered keys end where it starts.
-    if (at < unsigned(kRefKeyBuf)) s_hole = at;
-    return unsigned(kRefKeyBuf) + atomicAdd(&q.cand_count[n], count);
-  };
-  auto put = [&](unsigned int slot, unsigned long long key) {
-    if (slot < unsigned(kRefKeyBuf)) s_keys[slot] = key;
-    else if ((long long)(slot - unsigned(kRefKeyBuf)) < q.cand_cap) g_list[slot - unsigned(kRefKeyBuf)] = key;
+  auto emit = [&](unsigned long long key) {
+    const unsigned int at = atomicAdd(&s_ncand, 1u);
+    if (at < unsigned(kRefKeyBuf)) {
+      s_keys[at] = key;
+    } else {  // the shared buffer is full (rare): straight to the global list
+      const unsigned int slot = atomicAdd(&q.cand_count[n], 1u);
+      if ((long long)slot < q.cand_cap) g_list[slot] = key;
+    }
     atomicAdd(&g_hist[k32_bin(q, uint32_t(key >> 32))], 1u);  // a few dozen keys per CTA: straight to L2
   };
-  // a warp per row; the next row's logits are requested before the current row is evaluated
-  {
-    RowProbs cur, nxt;
-    int i = wid;
-    if (i < n_rows) row_load(q, q.scores + (size_t(n) * q.P + s_rows[i]) * size_t(q.C), lane, cur);
-    for (; i < n_rows; i += kRefThreads / 32) {
-      const int i2 = i + kRefThreads / 32;
-      if (i2 < n_rows) row_load(q, q.scores + (size_t(n) * q.P + s_rows[i2]) * size_t(q.C), lane, nxt);
-      eval_row(q, n, s_rows[i], lane, 0u, cut, cur, reserve, put);
-      cur = nxt;
-    }
+  // four rows per warp (an octet each)
+  for (int i = wid * 4; i < n_rows; i += (kRefThreads / 32) * 4) {
+    const int r = i + (lane >> 3);
+    eval_rows(q, n, r < n_rows ? s_rows[r] : -1, lane, 0u, cut, emit);
   }
   __syncthreads();
   // hand the buffered keys over: one global atomic for the CTA's keys
-  const unsigned int have = s_hole != 0xffffffffu ? s_hole : min(s_ncand, unsigned(kRefKeyBuf));
+  const unsigned int have = min(s_ncand, unsigned(kRefKeyBuf));
   if (have) {  // (CTA-uniform)
     if (tid == 0) s_gbase = atomicAdd(&q.cand_count[n], have);
     __syncthreads();
@@ -575,12 +553,9 @@ __global__ void __launch_bounds__(kNmsThreads) detect_nms_kernel(const DetParams
   // same function of the same histogram as detect_refine_kernel: candidates below `cut` are complete
   {
     unsigned int* rh = q.rhist + size_t(n) * kMaxBins;
-    for (int b = tid; b < q.n_bins; b += kNmsThreads) {
-      S.hist[b] = rh[b];
-      rh[b] = 0u;  // clean for the next call
-    }
+    for (int b = tid; b < q.n_bins; b += kNmsThreads) rh[b] = 0u;  // clean for the next call
   }
-  unsigned int cut = compute_cutoff(q, S.hist, S.wscan);
+  unsigned int cut = q.cutoff[n];  // candidates below `cut` are complete (detect_refine_kernel)
   const bool two_stage = q.second_thr >= 0.f;
   unsigned int* g_hist = q.hist + size_t(n) * kMaxBins;
   unsigned int* g_seen = q.class_seen + size_t(n) * q.C;
@@ -602,8 +577,8 @@ __global__ void __launch_bounds__(kNmsThreads) detect_nms_kernel(const DetParams
   // cheaper; if it is not enough the following rounds take full chunks.
   int chunk_cap = kChunk;
   if (!two_stage) {
-    chunk_cap = 256;
-    while (chunk_cap < 2 * stop_at && chunk_cap < kChunk) chunk_cap <<= 1;
+    chunk_cap = 64;
+    while (4 * chunk_cap < 5 * stop_at && chunk_cap < kChunk) chunk_cap <<= 1;  // >= 1.25 x the boxes wanted
   }
   for (;;) {  // bands: first the candidates above the cutoff, then (rarely) everything else
   while (!exhausted && (two_stage ? kept2_n : kept_n) < stop_at && !status) {
@@ -1062,17 +1037,16 @@ __global__ void __launch_bounds__(kNmsThreads) detect_nms_kernel(const DetParams
     // candidates. Second band, exact: this CTA evaluates every row of its image and emits what lies below the
     // cutoff (rare; the bound pass sized the first band for ~4x the boxes wanted).
     if (exhausted && !status && !overflow && cut != 0xffffffffu && (two_stage ? kept2_n : kept_n) < stop_at) {
-      auto reserve = [&](unsigned int count) -> unsigned int { return atomicAdd(&q.cand_count[n], count); };
-      auto put = [&](unsigned int slot, unsigned long long key) {
+      auto emit = [&](unsigned long long key) {
+        const unsigned int slot = atomicAdd(&q.cand_count[n], 1u);
         if ((long long)slot < q.cand_cap) g_cand[slot] = key;
         atomicAdd(&g_hist[k32_bin(q, uint32_t(key >> 32))], 1u);
       };
-      for (int p = wid; p < q.P; p += kNmsThreads / 32)
-        if (q.pbound[size_t(n) * q.P + p] > q.min_score) {
-          RowProbs R;
-          row_load(q, q.scores + (size_t(n) * q.P + p) * size_t(q.C), lane, R);
-          eval_row(q, n, p, lane, cut, 0xffffffffu, R, reserve, put);
-        }
+      for (int p0 = wid * 4; p0 < q.P; p0 += (kNmsThreads / 32) * 4) {  // four rows per warp (an octet each)
+        const int p = p0 + (lane >> 3);
+        const bool take = p < q.P && q.pbound[size_t(n) * q.P + p] > q.min_score;
+        eval_rows(q, n, take ? p : -1, lane, cut, 0xffffffffu, emit);
+      }
       __threadfence();
       __syncthreads();
       raw_total = *reinterpret_cast<volatile unsigned int*>(&q.cand_count[n]);
@@ -1186,8 +1160,8 @@ static int kept_capacity(const sbod_detect_desc* d) {
 
 // workspace carve-up (the leading block carries the zero contract)
 struct DetLayout {
-  size_t cand_count, hist, class_seen, rhist, zero_end, pbound, agn_label, nms_mask, spill_key, spill_box, spill_st2,
-      cand, total;
+  size_t cand_count, hist, class_seen, rhist, zero_end, cutoff, pbound, agn_label, nms_mask, spill_key, spill_box,
+      spill_st2, cand, total;
 };
 static DetLayout det_layout(const sbod_detect_desc* d) {
   DetLayout l;
@@ -1203,6 +1177,7 @@ static DetLayout det_layout(const sbod_detect_desc* d) {
   l.class_seen = take(N * size_t(d->C) * 4);
   l.rhist = take(N * kMaxBins * 4);
   l.zero_end = o;
+  l.cutoff = take(N * 4);
   l.pbound = take(N * P * 4);
   l.agn_label = take(d->class_agnostic ? N * P * 4 : 0);
   l.nms_mask = take(N * kChunk * (kChunk / 32) * 4);
@@ -1267,6 +1242,7 @@ static int detect_run(const sbod_detect_desc* d, sbod_stream_t stream, int stage
   q.hist = reinterpret_cast<unsigned int*>(w + lay.hist);
   q.class_seen = reinterpret_cast<unsigned int*>(w + lay.class_seen);
   q.rhist = reinterpret_cast<unsigned int*>(w + lay.rhist);
+  q.cutoff = reinterpret_cast<unsigned int*>(w + lay.cutoff);
   q.pbound = reinterpret_cast<float*>(w + lay.pbound);
   q.agn_label = reinterpret_cast<int32_t*>(w + lay.agn_label);
   q.nms_mask = reinterpret_cast<unsigned int*>(w + lay.nms_mask);
@@ -1300,6 +1276,11 @@ static int detect_run(const sbod_detect_desc* d, sbod_stream_t stream, int stage
     SBOD_CUDA_TRY(cudaFuncSetAttribute(detect_bound_kernel<21>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     SBOD_CUDA_TRY(cudaFuncSetAttribute(detect_bound_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     SBOD_CUDA_TRY(cudaFuncSetAttribute(detect_nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+    // without a preference the driver picks the smallest shared-memory carve-out that fits ONE CTA
+    SBOD_CUDA_TRY(cudaFuncSetAttribute(detect_bound_kernel<81>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    SBOD_CUDA_TRY(cudaFuncSetAttribute(detect_bound_kernel<21>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    SBOD_CUDA_TRY(cudaFuncSetAttribute(detect_bound_kernel<0>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    SBOD_CUDA_TRY(cudaFuncSetAttribute(detect_refine_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     attr_once.mark();
   }
   if (stage_mask & 1) {  // bound pass
@@ -1338,15 +1319,33 @@ static int detect_run(const sbod_detect_desc* d, sbod_stream_t stream, int stage
 // (image, prior, class): lets a test separate "scores within 1e-5 of torch" from "kept indices bit-exact given
 // the scores".
 __global__ void __launch_bounds__(256) detect_probabilities_kernel(const DetParams q, float* __restrict__ out) {
-  const int lane = threadIdx.x & 31;
+  const int lane = threadIdx.x & 31, s = lane & 7;
   const size_t total = size_t(q.N) * q.P;
-  for (size_t np = (size_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5; np < total;
-       np += (size_t(gridDim.x) * blockDim.x) >> 5) {
-    const float* x = q.scores + np * size_t(q.C);
-    RowProbs R;
-    row_load(q, x, lane, R);
-    row_prepare(q, x, lane, R);
-    for (int k = lane; k < q.C; k += 32) out[np * size_t(q.C) + k] = row_prob(q, R, x[k]);
+  const size_t n_octets = (size_t(gridDim.x) * blockDim.x) >> 3;
+  const float NEG = -__int_as_float(0x7f800000);
+  for (size_t np0 = ((size_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5) * 4; np0 < total; np0 += (n_octets >> 2) * 4) {
+    const size_t np = np0 + (lane >> 3);
+    const bool on = np < total;
+    const float* x = q.scores + (on ? np : 0) * size_t(q.C);
+    float mx = 0.f, sum = 1.f;
+    if (q.act_kind == SBOD_ACT_SOFTMAX) {  // the same sequence of operations as eval_rows
+      float m = NEG;
+      if (on)
+        for (int k = s; k < q.C; k += 8) m = fmaxf(m, __ldg(x + k));
+      mx = octet_max(m);
+      float acc = 0.f;
+      if (on)
+        for (int k = s; k < q.C; k += 8) acc += expf(__ldg(x + k) - mx);
+      sum = octet_sum(acc);
+    }
+    if (on)
+      for (int k = s; k < q.C; k += 8) {
+        const float v = __ldg(x + k);
+        float pr = v;
+        if (q.act_kind == SBOD_ACT_SOFTMAX) pr = __fdiv_rn(expf(v - mx), sum);
+        else if (q.act_kind == SBOD_ACT_SIGMOID) pr = __fdiv_rn(1.f, 1.f + expf(-v));
+        out[np * size_t(q.C) + k] = pr;
+      }
   }
 }
 

@@ -1921,6 +1921,11 @@ static int set_kernel_attrs() {
   SBOD_CUDA_TRY(cudaFuncSetAttribute(loss_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   SBOD_CUDA_TRY(cudaFuncSetAttribute(forced_match_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
   SBOD_CUDA_TRY(cudaFuncSetAttribute(classify_mine_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024));
+  // without a preference the driver picks the smallest shared-memory carve-out that fits ONE CTA per SM
+  SBOD_CUDA_TRY(cudaFuncSetAttribute(classify_mine_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+  SBOD_CUDA_TRY(cudaFuncSetAttribute(match_lse_fast_kernel<0>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+  SBOD_CUDA_TRY(cudaFuncSetAttribute(match_lse_fast_kernel<81>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+  SBOD_CUDA_TRY(cudaFuncSetAttribute(match_lse_fast_kernel<21>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
   SBOD_CUDA_TRY(cudaFuncSetAttribute(mine_batch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
   attr_once.mark();
   return SBOD_OK;
