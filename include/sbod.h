@@ -238,7 +238,9 @@ typedef struct sbod_loss_desc {
   int32_t* obj;  /* object_for_each_prior */
   float* lse;    /* log-sum-exp of the logits row */
   float* ce;     /* cross entropy of the row against its true class */
-  uint8_t* sel;  /* bit0: positive, bit1: hard negative / focal negative */
+  uint8_t* sel;  /* bit0: positive, bit1: hard negative / focal negative, bit2: hard-negative mining candidate */
+  float* sel_thr; /* [N,2] per image: cross-entropy threshold of the mined negatives (a candidate row is mined iff
+                     its CE is above it, or equal to it when the second value is 1); written by forward */
   /* ---- outputs ---- */
   double* partials; /* [N,4]  per image: sum loc, sum conf over positives, sum conf over mined negatives, n_pos */
   double* sums;     /* [4]    batch sums of the same (the only data that crosses GPUs) */

@@ -50,7 +50,7 @@ class LossDesc(C.Structure):
         ("neg_pos_ratio", C.c_int32), ("reg_weight", C.c_float), ("smooth_l1_beta", C.c_float),
         ("focal_alpha", C.c_float), ("focal_gamma", C.c_float),
         ("ov", C.c_void_p), ("obj", C.c_void_p), ("lse", C.c_void_p), ("ce", C.c_void_p),
-        ("sel", C.c_void_p), ("partials", C.c_void_p), ("sums", C.c_void_p), ("loss", C.c_void_p),
+        ("sel", C.c_void_p), ("sel_thr", C.c_void_p), ("partials", C.c_void_p), ("sums", C.c_void_p), ("loss", C.c_void_p),
         ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t),
         ("grad_scores_prefill", C.c_void_p), ("comm", C.c_void_p),
     ]

@@ -65,6 +65,7 @@ class LossState:
         self.lse = torch.empty((N, P), dtype=torch.float32, device=dev)
         self.ce = torch.empty((N, P), dtype=torch.float32, device=dev)
         self.sel = torch.empty((N, P), dtype=torch.uint8, device=dev)
+        self.sel_thr = torch.empty((N, 2), dtype=torch.float32, device=dev)
         self.partials = torch.empty((N, 4), dtype=torch.float64, device=dev)
         self.sums = torch.empty((4,), dtype=torch.float64, device=dev)
         self.loss = torch.empty((4,), dtype=torch.float32, device=dev)
@@ -88,6 +89,7 @@ class LossState:
         d.focal_alpha, d.focal_gamma = float(spec.focal_alpha), float(spec.focal_gamma)
         d.ov, d.obj, d.lse, d.ce, d.sel = (self.ov.data_ptr(), self.obj.data_ptr(), self.lse.data_ptr(),
                                            self.ce.data_ptr(), self.sel.data_ptr())
+        d.sel_thr = self.sel_thr.data_ptr()
         d.partials, d.sums, d.loss = self.partials.data_ptr(), self.sums.data_ptr(), self.loss.data_ptr()
         nbytes = L.lib().sbod_loss_workspace_bytes(C.byref(d))
         zbytes = L.lib().sbod_loss_workspace_zero_bytes(C.byref(d))

@@ -57,6 +57,7 @@ struct LossParams {
   float* lse;
   float* ce;
   uint8_t* sel;
+  float* sel_thr;  // [N,2] per image: CE threshold of the mined negatives, 1 if every tie at the threshold is taken
   double* partials;
   double* sums;
   float* loss;
@@ -66,6 +67,7 @@ struct LossParams {
   unsigned int* counters;     // [4]
   unsigned int* match_q;      // [N] per-image chunk queues of the match role
   unsigned int* sel_hist;     // [N, kBins] leading-digit histograms of the hard-negative radix select (zero between calls)
+  unsigned long long* sel_msum;  // [N, kBins] per leading digit: sum of the candidates' mantissas (zero between calls)
   unsigned int* batch_hist;   // [3, kBins] digit histograms of the batch-global select (zero between calls)
   unsigned int* img_done;     // [N] per-image tickets of classify_mine_kernel (zero between calls)
   double* blockpart;          // [N, slices, 4] partial sums of the slices
@@ -1034,8 +1036,13 @@ constexpr int kCmSlice = kCmThreads * kCmUnroll;  // priors per CTA
 constexpr int kCmFgCap = kCmSlice;                // foreground-row list: at worst every prior of the slice
 constexpr int kCmMaxCluster = 8;                  // (mine_batch_kernel)
 
+constexpr int kCmValCap = 2 * kBins;  // candidate values of one leading digit kept in shared memory by the tail
+
 struct CmShared {
   unsigned int hist[kBins];  // leading-digit histogram of the slice, then the digit histograms of the tail
+  unsigned long long msum[kBins];  // per leading digit: sum of the candidates' 24-bit mantissas (exact integer
+                                   // arithmetic: all values of a digit share their exponent); the tail reuses the
+                                   // storage for the values of the digit that holds the k-th candidate
   double red4[4 * 32];
   double red[34];
   unsigned int wt[32];
@@ -1069,89 +1076,136 @@ __device__ void cm_image_tail(const LossParams& q, CmShared& S, int n, int slice
     }
   }
   double t_neg = img[2];  // focal: sum over the negatives; MINE_BATCH: number of candidates (see mine_batch_kernel)
-  unsigned int* gh = q.sel_hist + size_t(n) * kBins;
   const bool select = !focal && q.cls_kind != SBOD_CLS_CE_MINE_BATCH;
+  // what the backward needs to know about the image's mined negatives: a candidate row (flag bit 2) is mined
+  // iff its CE > thr, or == thr when every tie is taken; +inf = none
+  float sel_thr = __int_as_float(0x7f800000);
+  float sel_ties = 0.f;
   if (select) {
+    unsigned int* gh = q.sel_hist + size_t(n) * kBins;
+    unsigned long long* gm = q.sel_msum + size_t(n) * kBins;
     const long long n_cand = (long long)(img[2] + 0.5);
     long long k = (long long)(q.ratio) * (long long)(img[3] + 0.5);
     if (k > n_cand) k = n_cand;
     t_neg = 0.0;
-    // first digit (12 bits): histogram accumulated by the slices; read it and leave it clean
+    // first digit (12 bits): counts and mantissa sums accumulated by the slices; read them, leave them clean
     for (int b = tid; b < kBins; b += kCmThreads) {
       S.hist[b] = __ldcg(&gh[b]);
+      S.msum[b] = __ldcg(&gm[b]);
       gh[b] = 0u;
+      gm[b] = 0ull;
     }
     __syncthreads();
     if (k > 0) {  // (CTA-uniform)
       const float* vals = q.cand + base;
-      uint32_t prefix = 0, mask = 0;
-      long long remaining = k;
-      block_find_digit(S.hist, kBins, remaining, S.wt, S.misc);
-      prefix = uint32_t(S.misc[0]) << 20;
-      mask = 0xfffu << 20;
-      remaining = S.misc[1];
-      int n_ties = S.misc[2];
-      const int shifts[2] = {8, 0};
-      const int widths[2] = {12, 8};
+      block_find_digit(S.hist, kBins, k, S.wt, S.misc);
+      const int d0 = S.misc[0];
+      long long remaining = S.misc[1];
+      const int n0 = S.misc[2];
+      // sum of every candidate above the digit: exact per digit (integer mantissa sum x the digit's power of two)
+      double above = 0.0;
+      for (int b = tid; b < kBins; b += kCmThreads) {
+        if (b > d0 && S.hist[b]) {
+          const int e = b >> 3;  // exponent field of every value of the digit
+          above += ldexp(double(S.msum[b]), (e ? e : 1) - 150);
+        }
+      }
+      above = block_sum(above, S.red);
+      if (remaining >= n0) {
+        // the whole digit is taken: no pass over the candidates at all
+        const int e = d0 >> 3;
+        t_neg = above + ldexp(double(S.msum[d0]), (e ? e : 1) - 150);
+        sel_thr = __uint_as_float(uint32_t(d0) << 20);  // lowest value of the digit
+        sel_ties = 1.f;
+      } else {
+        // The k-th candidate lies inside digit d0 (n0 values): ONE pass over the image's candidates (L2) collects
+        // them into shared memory; the remaining digits are resolved there.
+        float* s_vals = reinterpret_cast<float*>(S.msum);  // (the mantissa sums are consumed)
+        const bool fits = n0 <= kCmValCap;
+        uint32_t prefix = uint32_t(d0) << 20, mask = 0xfffu << 20;
+        int n_ties = n0;
+        __syncthreads();
+        if (tid == 0) S.fg_n = 0;  // (list cursor)
+        const int shifts[2] = {8, 0};
+        const int widths[2] = {12, 8};
 #pragma unroll 1
-      for (int pass = 0; pass < 2; ++pass) {
-        const int shift = shifts[pass];
-        const uint32_t dmask = (1u << widths[pass]) - 1u;
-        const int nb = 1 << widths[pass];
-        __syncthreads();
-        for (int b = tid; b < nb; b += kCmThreads) S.hist[b] = 0u;
-        __syncthreads();
-        for (int i0 = 0; i0 < q.P; i0 += kCmThreads * 8) {  // eight independent loads in flight per thread (L2)
-          float v[8];
+        for (int pass = 0; pass < 2; ++pass) {
+          const int shift = shifts[pass];
+          const uint32_t dmask = (1u << widths[pass]) - 1u;
+          const int nb = 1 << widths[pass];
+          __syncthreads();
+          for (int b = tid; b < nb; b += kCmThreads) S.hist[b] = 0u;
+          __syncthreads();
+          if (pass == 0 || !fits) {
+            for (int i0 = 0; i0 < q.P; i0 += kCmThreads * 8) {  // eight independent loads in flight per thread
+              float v[8];
 #pragma unroll
-          for (int u = 0; u < 8; ++u) {
-            const int i = i0 + u * kCmThreads + tid;
-            v[u] = i < q.P ? __ldcg(vals + i) : -1.f;
+              for (int u = 0; u < 8; ++u) {
+                const int i = i0 + u * kCmThreads + tid;
+                v[u] = i < q.P ? __ldcg(vals + i) : -1.f;
+              }
+#pragma unroll
+              for (int u = 0; u < 8; ++u) {
+                const uint32_t bits = __float_as_uint(v[u]);
+                const bool hit = v[u] >= 0.f && (bits & mask) == prefix;
+                if (hit) atomicAdd(&S.hist[(bits >> shift) & dmask], 1u);
+                if (pass == 0 && fits) {  // keep the digit's values (any order: only sums and counts are formed)
+                  const unsigned bal = __ballot_sync(0xffffffffu, hit);
+                  int at = 0;
+                  const int lane = tid & 31;
+                  if (bal && lane == 0) at = atomicAdd(&S.fg_n, __popc(bal));
+                  at = __shfl_sync(0xffffffffu, at, 0);
+                  if (hit) s_vals[at + __popc(bal & ((1u << lane) - 1u))] = v[u];
+                }
+              }
+            }
+          } else {
+            for (int i = tid; i < n0; i += kCmThreads) {
+              const uint32_t bits = __float_as_uint(s_vals[i]);
+              if ((bits & mask) == prefix) atomicAdd(&S.hist[(bits >> shift) & dmask], 1u);
+            }
           }
-#pragma unroll
-          for (int u = 0; u < 8; ++u) {
-            const uint32_t bits = __float_as_uint(v[u]);
-            if (v[u] >= 0.f && (bits & mask) == prefix) atomicAdd(&S.hist[(bits >> shift) & dmask], 1u);
+          __syncthreads();
+          block_find_digit(S.hist, nb, remaining, S.wt, S.misc);
+          prefix |= uint32_t(S.misc[0]) << shift;
+          mask |= dmask << shift;
+          remaining = S.misc[1];
+          n_ties = S.misc[2];
+        }
+        const float thr = __uint_as_float(prefix);
+        const int take_ties = int(remaining);
+        const bool all_ties = take_ties >= n_ties;
+        // values of digit d0 above the threshold (fixed-order reduction of doubles: deterministic given the list;
+        // the list order depends on atomics, the SUM of these few values in double does not to 1e-16)
+        double acc = 0.0;
+        const uint32_t d0_lo = uint32_t(d0) << 20;
+        if (fits) {
+          for (int i = tid; i < n0; i += kCmThreads)
+            if (s_vals[i] > thr) acc += double(s_vals[i]);
+        } else {
+          for (int i = tid; i < q.P; i += kCmThreads) {
+            const float v = __ldcg(vals + i);
+            if (v > thr && (__float_as_uint(v) >> 20) == (d0_lo >> 20)) acc += double(v);
           }
         }
-        __syncthreads();
-        block_find_digit(S.hist, nb, remaining, S.wt, S.misc);
-        prefix |= uint32_t(S.misc[0]) << shift;
-        mask |= dmask << shift;
-        remaining = S.misc[1];
-        n_ties = S.misc[2];
-      }
-      const float thr = __uint_as_float(prefix);
-      const int take_ties = int(remaining);
-      const bool all_ties = take_ties >= n_ties;
-      uint8_t* sel_out = q.sel + base;
-      double acc = 0.0;
-      for (int i0 = 0; i0 < q.P; i0 += kCmThreads * 8) {
-        float v[8];
-#pragma unroll
-        for (int u = 0; u < 8; ++u) {
-          const int i = i0 + u * kCmThreads + tid;
-          v[u] = i < q.P ? __ldcg(vals + i) : -1.f;
+        t_neg = above + block_sum(acc, S.red) + double(take_ties) * double(thr);
+        sel_thr = thr;
+        sel_ties = all_ties ? 1.f : 0.f;
+        if (!all_ties && tid == 0) {  // rare: the ties that belong to the top-k are the first ones by index
+          uint8_t* sel_out = q.sel + base;
+          int left = take_ties;
+          for (int i = 0; i < q.P && left > 0; ++i)
+            if (__ldcg(vals + i) == thr) {
+              sel_out[i] = uint8_t(__ldcg(sel_out + i) | 2);
+              --left;
+            }
         }
-#pragma unroll
-        for (int u = 0; u < 8; ++u) {
-          const int i = i0 + u * kCmThreads + tid;
-          if (v[u] > thr) acc += double(v[u]);
-          // selected negatives: v > thr plus (normally all) the candidates equal to thr; a candidate is never a
-          // positive, so the flag byte is written without reading it
-          if (v[u] > thr || (all_ties && v[u] == thr)) sel_out[i] = 2;
-        }
-      }
-      t_neg = block_sum(acc, S.red) + double(take_ties) * double(thr);
-      if (!all_ties && tid == 0) {  // rare: the ties that belong to the top-k are the first ones by index
-        int left = take_ties;
-        for (int i = 0; i < q.P && left > 0; ++i)
-          if (__ldcg(vals + i) == thr) {
-            sel_out[i] = 2;
-            --left;
-          }
       }
     }
+  }
+  if (tid == 0 && q.sel_thr) {
+    q.sel_thr[2 * n] = sel_thr;
+    q.sel_thr[2 * n + 1] = sel_ties;
   }
   if (tid == 0) {
     q.img_done[n] = 0u;  // clean for the next call
@@ -1216,7 +1270,10 @@ __global__ void __launch_bounds__(kCmThreads) classify_mine_kernel(const LossPar
     s_label[g] = int(map_label(q, q.gt_labels[g0 + g]));
   }
   if (select)
-    for (int b = tid; b < kBins; b += kCmThreads) S.hist[b] = 0u;
+    for (int b = tid; b < kBins; b += kCmThreads) {
+      S.hist[b] = 0u;
+      S.msum[b] = 0ull;
+    }
 
   // everything above is independent of the match kernel's results; from here on they are needed
   asm volatile("griddepcontrol.wait;" ::: "memory");
@@ -1283,6 +1340,7 @@ __global__ void __launch_bounds__(kCmThreads) classify_mine_kernel(const LossPar
       const int p = p_lo + u * kCmThreads + tid;
       rec[u] = 0;
       int digit = -1;
+      unsigned int mant = 0u;
       if (p < p_hi) {
         int cls = 0;
         if (!(ov[u] < q.thr_pos) && G > 0) cls = s_label[ob[u]];
@@ -1304,14 +1362,22 @@ __global__ void __launch_bounds__(kCmThreads) classify_mine_kernel(const LossPar
         }
         if (!focal && v >= 0.f) {
           a_neg += 1.0;  // mining modes: this partial counts the candidates (NaN CEs are none)
-          digit = int(__float_as_uint(v) >> 20);
+          const uint32_t bits = __float_as_uint(v);
+          digit = int(bits >> 20);
+          mant = (bits & 0x7fffffu) | ((bits >> 23) ? 0x800000u : 0u);
+          selbits |= 4;  // "mining candidate": the backward compares its CE with the image's threshold
         }
         q.sel[base + p] = selbits;
         q.cand[base + p] = v;
       }
-      if (select) {  // leading digit of the candidate: lanes with the same digit add once
+      if (select) {
+        // leading digit of the candidate: lanes with the same digit add their count and mantissas once
         const unsigned peers = __match_any_sync(0xffffffffu, digit);
-        if (digit >= 0 && lane == __ffs(peers) - 1) atomicAdd(&S.hist[digit], unsigned(__popc(peers)));
+        const unsigned int msum = __reduce_add_sync(peers, mant);  // <= 32 * 2^24
+        if (digit >= 0 && lane == __ffs(peers) - 1) {
+          atomicAdd(&S.hist[digit], unsigned(__popc(peers)));
+          atomicAdd(&S.msum[digit], static_cast<unsigned long long>(msum));
+        }
       }
       const unsigned bal = __ballot_sync(0xffffffffu, rec[u] != 0);
       rrank[u] = __popc(bal & ((1u << lane) - 1u));
@@ -1384,9 +1450,13 @@ __global__ void __launch_bounds__(kCmThreads) classify_mine_kernel(const LossPar
   // ---- publish: leading-digit histogram, partial sums, ticket ----
   if (select) {
     unsigned int* gh = q.sel_hist + size_t(n) * kBins;
+    unsigned long long* gm = q.sel_msum + size_t(n) * kBins;
     for (int b = tid; b < kBins; b += kCmThreads) {
       const unsigned int v = S.hist[b];
-      if (v) atomicAdd(&gh[b], v);
+      if (v) {
+        atomicAdd(&gh[b], v);
+        atomicAdd(&gm[b], S.msum[b]);
+      }
     }
   }
   double tot[4] = {a_loc, a_pos, a_neg, double(npos)};
@@ -1639,25 +1709,36 @@ __global__ void __launch_bounds__(256, 4) bwd_patch_kernel(const LossParams q, c
                                 (q.reg_kind == SBOD_REG_L1_ELEM_MEAN ? 4.0 * npos_tot : npos_tot));
   const size_t warp0 = (size_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
   const size_t n_warps = (size_t(gridDim.x) * blockDim.x) >> 5;
-  // the selection flags and log-sum-exps of the next group are requested one iteration ahead
+  // the selection flags, log-sum-exps and background CEs of the next group are requested one iteration ahead
   uint8_t sel_next = 0;
-  float lse_next = 0.f;
+  float lse_next = 0.f, ce_next = 0.f;
   if (warp0 * 32 + lane < total) {
     sel_next = q.sel[warp0 * 32 + lane];
     lse_next = q.lse[warp0 * 32 + lane];
+    ce_next = q.ce[warp0 * 32 + lane];
   }
   for (size_t base = warp0 * 32; base < total; base += n_warps * 32) {
     const size_t i = base + lane;
     const bool in = i < total;
-    const uint8_t selbits = sel_next;
+    uint8_t selbits = sel_next;
     const float lse = lse_next;
+    const float ce_bg = ce_next;
     {
       const size_t inext = i + n_warps * 32;
       sel_next = 0;
       if (inext < total) {
         sel_next = q.sel[inext];
         lse_next = q.lse[inext];
+        ce_next = q.ce[inext];
       }
+    }
+    // flag bit 2: mining candidate - mined iff its (background) CE beats the image's threshold
+    // (classify_mine_kernel leaves the threshold instead of marking ~3 n_pos rows per image)
+    if (in && (selbits & 4)) {
+      const int n = int(i / q.P);
+      const float thr = q.sel_thr[2 * n], ties = q.sel_thr[2 * n + 1];
+      const bool mined = (selbits & 2) || ce_bg > thr || (ce_bg == thr && ties != 0.f);
+      selbits = mined ? 2 : 0;
     }
     // a mined negative has target class 0; only positives need their object's label and box
     int cls = 0;
@@ -1794,7 +1875,7 @@ static int fill_params(const sbod_loss_desc* d, LossParams& q, bool need_scores)
   if (!d->gt_boxes || !d->gt_labels || !d->gt_offsets || !d->priors_xy || !d->priors_cxcy)
     return SBOD_ERR_INVALID;
   if (!d->ov || !d->obj) return SBOD_ERR_INVALID;
-  if (need_scores && (!d->lse || !d->ce || !d->sel || !d->partials || !d->sums || !d->loss))
+  if (need_scores && (!d->lse || !d->ce || !d->sel || !d->sel_thr || !d->partials || !d->sums || !d->loss))
     return SBOD_ERR_INVALID;
   if (need_scores && (reinterpret_cast<uintptr_t>(d->scores) & 15)) return SBOD_ERR_ALIGNMENT;
   if (need_scores && (reinterpret_cast<uintptr_t>(d->locs) & 15)) return SBOD_ERR_ALIGNMENT;
@@ -1820,6 +1901,7 @@ static int fill_params(const sbod_loss_desc* d, LossParams& q, bool need_scores)
   q.falpha = d->focal_alpha; q.fgamma = d->focal_gamma;
   q.ov = d->ov; q.obj = d->obj; q.lse = d->lse; q.ce = d->ce; q.sel = d->sel;
   q.partials = d->partials; q.sums = d->sums; q.loss = d->loss;
+  q.sel_thr = d->sel_thr;
   q.prefill = d->grad_scores_prefill;
   q.comm = (need_scores && g_opt_peer_exchange) ? static_cast<const CommDev*>(d->comm) : nullptr;
   if (q.comm && d->cls_kind == SBOD_CLS_CE_MINE_BATCH) return SBOD_ERR_INVALID;
@@ -1837,6 +1919,8 @@ static int fill_params(const sbod_loss_desc* d, LossParams& q, bool need_scores)
   w += align_up(size_t(q.N) * 4, 256);
   q.sel_hist = reinterpret_cast<unsigned int*>(w);
   w += align_up(size_t(q.N) * kBins * 4, 256);
+  q.sel_msum = reinterpret_cast<unsigned long long*>(w);
+  w += align_up(size_t(q.N) * kBins * 8, 256);
   q.batch_hist = reinterpret_cast<unsigned int*>(w);
   w += align_up(size_t(3) * kBins * 4, 256);
   q.img_done = reinterpret_cast<unsigned int*>(w);
@@ -1893,7 +1977,8 @@ extern "C" size_t sbod_loss_workspace_zero_bytes(const sbod_loss_desc* d) {
   if (!d) return 0;
   const int gmax = d->gmax > 0 ? d->gmax : 1;
   return 256 + align_up(size_t(d->N) * gmax * 8, 256) + align_up(size_t(d->N) * 4, 256) +
-         align_up(size_t(d->N) * kBins * 4, 256) + align_up(size_t(3) * kBins * 4, 256) + align_up(size_t(d->N) * 4, 256);
+         align_up(size_t(d->N) * kBins * 4, 256) + align_up(size_t(d->N) * kBins * 8, 256) +
+         align_up(size_t(3) * kBins * 4, 256) + align_up(size_t(d->N) * 4, 256);
 }
 
 extern "C" int sbod_set_option(int key, int value) {
@@ -2147,7 +2232,7 @@ extern "C" int sbod_assign(const float* gt_boxes, const int64_t* gt_labels,
 // ---- end-to-end helper with HOST buffers (bench.py e2e leg) ----------------------------------
 namespace {
 struct HostArena {
-  size_t locs, scores, pcx, pxy, gtb, gtl, gto, ov, obj, lse, ce, sel, partials, sums, loss, ws, total;
+  size_t locs, scores, pcx, pxy, gtb, gtl, gto, ov, obj, lse, ce, sel, sel_thr, partials, sums, loss, ws, total;
 };
 HostArena host_arena_layout(const sbod_loss_desc* d, int T) {
   HostArena a;
@@ -2166,6 +2251,7 @@ HostArena host_arena_layout(const sbod_loss_desc* d, int T) {
   a.lse = take(NP * 4);
   a.ce = take(NP * 4);
   a.sel = take(NP);
+  a.sel_thr = take(size_t(d->N) * 8);
   a.partials = take(size_t(d->N) * 32);
   a.sums = take(32);
   a.loss = take(16);
@@ -2214,6 +2300,7 @@ extern "C" int sbod_loss_forward_host(const sbod_loss_desc* h, int T, float* los
   d.lse = reinterpret_cast<float*>(base + a.lse);
   d.ce = reinterpret_cast<float*>(base + a.ce);
   d.sel = reinterpret_cast<uint8_t*>(base + a.sel);
+  d.sel_thr = reinterpret_cast<float*>(base + a.sel_thr);
   d.partials = reinterpret_cast<double*>(base + a.partials);
   d.sums = reinterpret_cast<double*>(base + a.sums);
   d.loss = reinterpret_cast<float*>(base + a.loss);

@@ -529,3 +529,26 @@ def test_random_crop_matches_the_reference_and_its_random_stream(golden, dev):
         assert random.random() == float(G["s%d_next" % seed]), seed
         cropped += int(tuple(ni.shape) != tuple(image.shape))
     assert cropped >= 10
+
+
+def test_hard_negative_mining_with_massive_ties(dev):
+    """Hard-negative mining when (nearly) every candidate has the same cross entropy (constant logits): the k-th
+    candidate's leading digit then holds more values than the mining tail keeps in shared memory (its multi-pass
+    path), and only some of the ties at the threshold belong to the top-k (taken by ascending prior index, like
+    a stable sort). Loss against the oracle; the gradient touches exactly n_pos + 3 n_pos rows per image."""
+    from oracle import box_pipeline as O
+    from shape_based_object_detection_b200 import priors as PR, synth
+    from shape_based_object_detection_b200.models import MultiBoxLoss512, RetinaFocalLoss
+    pri = PR.ssd512_canonical_priors()
+    N, Cn = 2, 5
+    locs, scores, bx, lb = synth.make_train_batch(pri, N, Cn, 20, 31)
+    for variant, Mod, scale in (("s512", MultiBoxLoss512, 0.0), ("ret", RetinaFocalLoss, 0.0), ("s512", MultiBoxLoss512, 1e-3)):
+        sc = scores * scale  # 0: all CEs equal ln(5); 1e-3: all inside one leading radix digit, (almost) no exact ties
+        want, parts = O.multibox_loss(variant, pri, locs, sc, bx, lb, want_parts=True)
+        crit = Mod(pri.to(dev), cfg(n_classes=Cn))
+        l_d, s_d = locs.to(dev).requires_grad_(True), sc.to(dev).requires_grad_(True)
+        loss = crit(l_d, s_d, [b.to(dev) for b in bx], [l.to(dev) for l in lb])
+        loss.backward()
+        assert abs(loss.item() - want.item()) <= RTOL_LOSS * abs(want.item()), (variant, scale, loss.item(), want.item())
+        rows = (s_d.grad.abs().sum(2) > 0).sum(1).cpu()
+        assert torch.equal(rows, 4 * parts["n_pos"]), (rows, parts["n_pos"])
