@@ -10,33 +10,31 @@
 //   match_lse_kernel   generic fallback (C > 128, or no logits: sbod_assign): one thread per prior row.
 //   forced_match_kernel (sbod_assign) per image: the reference's "every object keeps its best prior"
 //                      override, including its filtered-index quirk (SSD512.py:546-553).
-//   classify_mine_kernel  one thread-block cluster per image: forced-match list rebuilt from the per-object keys
-//                      and applied, classes, true-class CE + loc term of the foreground rows, mining
-//                      candidates in shared memory, cluster-wide radix select (distributed shared memory
-//                      histograms) of the top-k candidate CEs, selection bits; the last image folds the
-//                      batch and finalises the loss. Programmatic dependent launch behind the match kernel.
-//   mine_batch_kernel  SSD300's batch-global mining (SSD300.py:580-588), one cluster of 8 CTAs.
+//   classify_kernel    2048 priors per CTA: forced-match list rebuilt from the per-object keys and applied,
+//                      classes, true-class CE + loc term of the foreground rows, mining candidates counted in
+//                      a fine per-image histogram, partial sums of the slice.
+//   mine_kernel        one CTA per image: sums its 3 * n_pos largest candidate CEs (histogram bin + one pass
+//                      over the candidates, no sort) and leaves the threshold for the backward; the last image
+//                      folds the batch (and mines it for SSD300's batch-global rule, SSD300.py:580-588),
+//                      exchanges the sums with the other ranks and finalises the loss.
+//                      (programmatic dependent launches: match -> classify -> mine)
 //   bwd_patch_kernel   sparse backward (CE + mining): softmax - onehot on the selected rows of a
 //                      zero-filled gradient (zero_fill_kernel when the forward did not fill it), grad wrt locs.
 //   loss_bwd_kernel    dense backward (focal): tile in by TMA, transformed in place, out by TMA store.
 #include <math.h>
 #include <stdlib.h>
 
-#include <cooperative_groups.h>
-
 #include "comm.cuh"
 #include "common.cuh"
 #include "pair_iou.cuh"
 #include "row_stream.cuh"
-
-namespace cg = cooperative_groups;
 
 namespace sbod {
 
 constexpr int kRows = 128;      // threads per CTA == max rows per streamed tile
 constexpr int kGtChunk = 256;   // GT boxes staged in smem at a time
 constexpr int kMaxStages = 4;
-constexpr int kBins = 4096;     // radix-select digit = 12 bits
+constexpr int kBins = 4096;     // bins of the mining-candidate histogram
 
 struct LossParams {
   const float* locs;
@@ -66,10 +64,7 @@ struct LossParams {
   float* cand;                // [N, P]
   unsigned int* counters;     // [4]
   unsigned int* match_q;      // [N] per-image chunk queues of the match role
-  unsigned int* sel_hist;     // [N, kBins] leading-digit histograms of the hard-negative radix select (zero between calls)
-  unsigned long long* sel_msum;  // [N, kBins] per leading digit: sum of the candidates' mantissas (zero between calls)
-  unsigned int* batch_hist;   // [3, kBins] digit histograms of the batch-global select (zero between calls)
-  unsigned int* img_done;     // [N] per-image tickets of classify_mine_kernel (zero between calls)
+  unsigned int* sel_hist;     // [N, kBins] per image: histogram of the mining candidates (sel_bin; zero between calls)
   double* blockpart;          // [N, slices, 4] partial sums of the slices
   // tiling
   int rows_per_tile, tiles_per_image, n_tiles, n_stages;
@@ -292,7 +287,7 @@ __global__ void __launch_bounds__(kRows) match_lse_kernel(const LossParams q) {
       q.obj[np] = bobj;
       q.lse[np] = mx + lg;
       // CE against class 0 (background) == -log_softmax[0] in torch's operation order; the few
-      // positive rows are re-evaluated against their true class by classify_mine_kernel.
+      // positive rows are re-evaluated against their true class by classify_kernel / mine_kernel.
       q.ce[np] = (mx - row[0]) + lg;
     }
     __syncthreads();  // every thread is done with stage s
@@ -782,174 +777,25 @@ SBOD_DEVINL float focal_bg(const LossParams& q, float ce) {  // (1-alpha) * p0^g
 }
 
 // ------------------------------------------------------------------------------------------
-// Cluster-wide radix select: sum of the k largest candidate values of an array that is split over the
-// CTAs of a thread-block cluster (candidates are >= 0, non-candidates < 0). MSD radix 12 + 12 + 8 bits.
-// Every CTA histograms its own slice in shared memory and adds the non-empty bins to the image's
-// histogram of the pass in global memory (L2 atomics; measured: reading the peers' histograms through
-// distributed shared memory instead cost 45 % of the kernel). One cluster barrier later every CTA reads
-// the summed histogram back (coalesced, L2) and finds the digit on its own - same integers, same result in
-// every CTA, nothing to broadcast. Each pass has its own global histogram; rank 0 clears them at the end.
+// Hard-negative mining without a sort: only the SUM of the k largest candidate cross entropies is consumed
+// (SSD512.py:610-619), plus the k-th value itself as the backward's threshold.
+//   * classify_kernel counts every candidate in a 4096-bin histogram of its image while it classifies the
+//     priors (shared-memory histogram per CTA, the non-empty bins added to the image's histogram by L2
+//     reductions). The bins are the leading 17 bits of the fp32 value over the 16 octaves [2^-10, 2^6) - 256
+//     bins per octave, so the bin that holds the k-th value holds a few hundred candidates at most; bin 0
+//     takes everything smaller, bin 4095 everything larger (order preserved).
+//   * select_topk_sum (one CTA of 1024 threads): finds that bin from the histogram, then ONE pass over the
+//     candidate values (L2-resident, 128-bit loads) adds up everything above the bin in double and collects the
+//     bin's values in shared memory - in a fixed order, so the sum is reproducible; the k-th value inside the
+//     bin is resolved there by 8-bit radix passes. A bin with more values than fit (long runs of equal values)
+//     takes the same passes over global memory instead.
 // ------------------------------------------------------------------------------------------
-struct ClusterSelect {
-  unsigned int hist[kBins];  // this CTA's digit histogram of the pass, then the cluster-wide one
-  double sumv;               // this CTA's sum of the values above the threshold (read by rank 0)
-  unsigned int ties;         // this CTA's number of candidates equal to the threshold
-  int misc[4];
-  unsigned int wt[32];
-  double red[34];
-};
+constexpr int kSelLo = 117 << 8;  // leading 17 bits (sign 0, exponent, 8 mantissa bits) of 2^-10
+constexpr int kSelCap = 4096;     // values of the threshold bin resolved in shared memory
 
-struct SelectResult {
-  double sum;         // this CTA's part (the caller adds the slices and take_ties * threshold)
-  uint32_t thr_bits;  // value of the k-th largest
-  int take_ties;      // how many values == thr are part of the top-k
-  int n_ties;         // how many candidates == thr exist
-  long long k_eff;
-};
-
-// vals: this CTA's slice (shared or global memory), n_local values; ghist: [3][kBins] global histogram of the
-// cluster (zero on entry, zero again on return); sel_out (may be null): selection flags of the slice, value 2
-// is stored on the selected values (a candidate is never a positive, so the flag byte is written without
-// reading it). All threads of all CTAs of the cluster must call this.
-__device__ SelectResult cluster_topk_sum(cg::cluster_group& cluster, ClusterSelect& S, const float* vals,
-                                         int n_local, long long k_want, long long n_cand,
-                                         unsigned int* __restrict__ ghist, uint8_t* __restrict__ sel_out) {
-  const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, wid = tid >> 5;
-  const unsigned int my_rank = cluster.block_rank();
-  SelectResult r;
-  r.sum = 0.0; r.thr_bits = 0; r.take_ties = 0; r.n_ties = 0;
-  const long long k = k_want < n_cand ? k_want : n_cand;
-  r.k_eff = k;
-  if (k <= 0) {  // cluster-uniform: nothing is selected
-    if (tid == 0) { S.sumv = 0.0; S.ties = 0u; }
-    return r;
-  }
-  uint32_t prefix = 0, mask = 0;
-  long long remaining = k;
-  const int shifts[3] = {20, 8, 0};
-  const int widths[3] = {12, 12, 8};
-#pragma unroll 1
-  for (int pass = 0; pass < 3; ++pass) {
-    const int shift = shifts[pass];
-    const uint32_t dmask = (1u << widths[pass]) - 1u;
-    const int nb = 1 << widths[pass];
-    unsigned int* gh = ghist + size_t(pass) * kBins;
-    for (int b = tid; b < nb; b += nt) S.hist[b] = 0u;
-    __syncthreads();
-    // (the leading digit of cross entropies takes a handful of values: lanes with the same digit add once)
-    for (int i0 = 0; i0 < n_local; i0 += nt) {
-      const int i = i0 + tid;
-      int digit = -1;
-      if (i < n_local) {
-        const float v = vals[i];
-        if (v >= 0.f) {
-          const uint32_t bits = __float_as_uint(v);
-          if ((bits & mask) == prefix) digit = int((bits >> shift) & dmask);
-        }
-      }
-      if (pass == 0) {
-        const unsigned peers = __match_any_sync(0xffffffffu, digit);
-        if (digit >= 0 && lane == __ffs(peers) - 1) atomicAdd(&S.hist[digit], unsigned(__popc(peers)));
-      } else if (digit >= 0) {
-        atomicAdd(&S.hist[digit], 1u);
-      }
-    }
-    __syncthreads();
-    for (int b = tid; b < nb; b += nt) {
-      const unsigned int v = S.hist[b];
-      if (v) atomicAdd(&gh[b], v);
-    }
-    __threadfence();
-    cluster.sync();  // every slice has added its histogram of this pass
-    for (int b = tid; b < nb; b += nt) S.hist[b] = __ldcg(&gh[b]);
-    __syncthreads();
-    // digit d (from the top) with  count(> d) < remaining <= count(>= d); each thread owns a contiguous
-    // run of bins, highest bins first
-    const int per = (nb + nt - 1) / nt;  // <= 8: callers run >= 512 threads
-    const int hi = nb - 1 - tid * per;
-    unsigned int cnt[8];
-    unsigned int mine = 0;
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int b = hi - j;
-      cnt[j] = (j < per && b >= 0) ? S.hist[b] : 0u;
-      mine += cnt[j];
-    }
-    unsigned int inc = mine;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const unsigned int t = __shfl_up_sync(0xffffffffu, inc, o);
-      if (lane >= o) inc += t;
-    }
-    if (lane == 31) S.wt[wid] = inc;
-    __syncthreads();
-    unsigned long long before = inc - mine;
-    for (int w = 0; w < wid; ++w) before += S.wt[w];
-    if (before < (unsigned long long)remaining && (unsigned long long)remaining <= before + mine) {
-      unsigned long long acc = before;
-      bool found = false;
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const unsigned int h = cnt[j];
-        if (!found && acc < (unsigned long long)remaining && (unsigned long long)remaining <= acc + h) {
-          S.misc[0] = hi - j;
-          S.misc[1] = int((unsigned long long)remaining - acc);
-          S.misc[2] = int(h);
-          found = true;
-        }
-        acc += h;
-      }
-    }
-    __syncthreads();
-    prefix |= uint32_t(S.misc[0]) << shift;
-    mask |= dmask << shift;
-    remaining = S.misc[1];
-    r.n_ties = S.misc[2];
-    __syncthreads();
-  }
-  r.thr_bits = prefix;
-  r.take_ties = int(remaining);
-  const float thr = __uint_as_float(prefix);
-  const bool all_ties = r.take_ties >= r.n_ties;
-  double acc = 0.0;
-  unsigned int my_ties = 0;
-  for (int i = tid; i < n_local; i += nt) {
-    const float v = vals[i];
-    if (v > thr) acc += double(v);
-    if (v == thr) ++my_ties;
-    if (sel_out && (v > thr || (all_ties && v == thr))) sel_out[i] = 2;
-  }
-  const double local = block_sum(acc, S.red);
-  const double nties_local = block_sum(double(my_ties), S.red);
-  if (tid == 0) {
-    S.sumv = local;
-    S.ties = unsigned(nties_local + 0.5);
-  }
-  r.sum = local;
-  // Every CTA is past the barrier of pass 2, so nobody reads the histograms of passes 0 and 1 any more: rank 0
-  // leaves them clean for the next call. The histogram of pass 2 may still be being read by a slower CTA: the
-  // caller clears it after its next cluster barrier (cluster_topk_cleanup).
-  if (my_rank == 0)
-    for (int b = tid; b < 2 * kBins; b += nt) ghist[b] = 0u;
-  if (!all_ties) {  // rare (cluster-uniform): the ties that belong to the top-k are the first ones by index
-    cluster.sync();
-    if (tid == 0 && sel_out) {
-      long long before = 0;
-      for (unsigned int rk = 0; rk < my_rank; ++rk) before += *cluster.map_shared_rank(&S.ties, rk);
-      long long left = (long long)r.take_ties - before;
-      for (int i = 0; i < n_local && left > 0; ++i)
-        if (vals[i] == thr) {
-          sel_out[i] = 2;
-          --left;
-        }
-    }
-  }
-  return r;
-}
-
-// second half of the cleaning: call by rank 0 after a cluster barrier that follows cluster_topk_sum
-SBOD_DEVINL void cluster_topk_cleanup(unsigned int* __restrict__ ghist) {
-  for (int b = threadIdx.x; b < 256; b += blockDim.x) ghist[2 * kBins + b] = 0u;
+SBOD_DEVINL int sel_bin(float v) {  // v >= 0 (or +inf)
+  const int b = int(__float_as_uint(v) >> 15) - kSelLo + 1;
+  return b < 1 ? 0 : (b > kBins - 1 ? kBins - 1 : b);
 }
 
 SBOD_DEVINL void finalize_loss(const LossParams& q, const double* sums, float* loss) {
@@ -965,250 +811,535 @@ SBOD_DEVINL void finalize_loss(const LossParams& q, const double* sums, float* l
   loss[3] = float(npos);
 }
 
-// ------------------------------------------------------------------------------------------
-// Block-wide search of the radix digit that holds the `remaining`-th largest value: hist[nb] (shared
-// memory) counts per digit; digit d (from the top) with count(> d) < remaining <= count(>= d). Every thread
-// gets the same answer through out[0..2] = (digit, remaining inside the digit, count of the digit).
-// Needs blockDim.x * 8 >= nb. scratch: >= 32 uints. Ends with a barrier.
-// ------------------------------------------------------------------------------------------
-__device__ void block_find_digit(const unsigned int* hist, int nb, long long remaining, unsigned int* scratch,
-                                 int* out) {
-  const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, wid = tid >> 5;
-  const int per = (nb + nt - 1) / nt;  // <= 8
-  const int hi = nb - 1 - tid * per;   // my bins: hi, hi - 1, ... (highest bins first)
-  unsigned int cnt[8];
-  unsigned int mine = 0;
-#pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    const int b = hi - j;
-    cnt[j] = (j < per && b >= 0) ? hist[b] : 0u;
-    mine += cnt[j];
-  }
-  unsigned int inc = mine;
+#ifdef SBOD_DEBUG_HOOKS  // phase time stamps of the classify / mine kernels (profiling builds only)
+__device__ unsigned long long g_cm_times[8 + 4 * 64];
+SBOD_DEVINL unsigned long long cm_now() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+#define CM_STAMP_MIN(i) do { if (threadIdx.x == 0) atomicMin(&g_cm_times[i], cm_now()); } while (0)
+#define CM_STAMP_MAX(i) do { if (threadIdx.x == 0) atomicMax(&g_cm_times[i], cm_now()); } while (0)
+#define CM_STAMP_SET(i) do { if (threadIdx.x == 0) g_cm_times[i] = cm_now(); } while (0)
+#else
+#define CM_STAMP_MIN(i)
+#define CM_STAMP_MAX(i)
+#define CM_STAMP_SET(i)
+#endif
+
+constexpr int kMineThreads = 1024;
+constexpr int kMineWarps = kMineThreads / 32;
+
+struct MineShared {
+  float vals[kSelCap];    // the threshold bin's candidate values
+  unsigned int dig[256];  // digit histogram of one radix pass
+  double red4[4];
+  double red[34];
+  unsigned int wt[32];
+  int warp_tot[kMineWarps];
+  int misc[8];
+  int last;
+};
+
+struct TopkSum {
+  double sum;   // sum of the k largest candidates
+  float thr;    // the k-th largest (+inf: nothing selected)
+  float ties;   // 1: every candidate equal to thr belongs to the selection
+};
+
+// exclusive prefix of one int per thread over the CTA (thread order); *total = sum over the CTA. Two barriers.
+SBOD_DEVINL int mine_excl_scan(int v, int* warp_tot, int* total) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  int inc = v;
 #pragma unroll
   for (int o = 1; o < 32; o <<= 1) {
-    const unsigned int t = __shfl_up_sync(0xffffffffu, inc, o);
+    const int t = __shfl_up_sync(0xffffffffu, inc, o);
     if (lane >= o) inc += t;
   }
-  if (lane == 31) scratch[wid] = inc;
+  __syncthreads();  // (warp_tot may still be read from the previous call)
+  if (lane == 31) warp_tot[wid] = inc;
   __syncthreads();
-  unsigned long long before = inc - mine;
-  for (int w = 0; w < wid; ++w) before += scratch[w];
-  if (before < (unsigned long long)remaining && (unsigned long long)remaining <= before + mine) {
-    unsigned long long acc = before;
-    bool found = false;
+  const int t = warp_tot[lane];  // kMineWarps == 32: one total per lane
+  int wsum = t;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const unsigned int h = cnt[j];
-      if (!found && acc < (unsigned long long)remaining && (unsigned long long)remaining <= acc + h) {
-        out[0] = hi - j;
-        out[1] = int((unsigned long long)remaining - acc);
-        out[2] = int(h);
-        found = true;
+  for (int o = 1; o < 32; o <<= 1) {
+    const int x = __shfl_up_sync(0xffffffffu, wsum, o);
+    if (lane >= o) wsum += x;
+  }
+  *total = __shfl_sync(0xffffffffu, wsum, 31);
+  const int before_warp = __shfl_sync(0xffffffffu, wsum - t, wid);
+  return before_warp + inc - v;
+}
+
+// Sum of the k largest candidates of vals[0, n) (candidates are >= 0, everything else is negative or NaN);
+// ghist[kBins] = their sel_bin histogram, read and left zero. 0 < k <= number of candidates, or k == 0
+// (nothing selected). sel (may be null): flag bytes of the values; only touched when some but not all values
+// equal to the threshold are selected (the first ones by index get bit 1). All kMineThreads threads call this.
+__device__ TopkSum select_topk_sum(MineShared& S, const float* __restrict__ vals, const long long n,
+                                   unsigned int* __restrict__ ghist, const long long k, uint8_t* __restrict__ sel) {
+  static_assert(kMineWarps == 32, "mine_excl_scan");
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  TopkSum r;
+  r.sum = 0.0;
+  r.thr = __int_as_float(0x7f800000);
+  r.ties = 0.f;
+  // ---- the bin that holds the k-th largest: every thread owns 4 consecutive bins, highest bins first ----
+  constexpr int kPer = kBins / kMineThreads;
+  static_assert(kPer == 4, "one 128-bit load per thread");
+  unsigned int cnt[kPer];
+  {
+    uint4* gp = reinterpret_cast<uint4*>(ghist + (kBins - kPer * (tid + 1)));
+    const uint4 v = __ldcg(gp);
+    cnt[0] = v.w; cnt[1] = v.z; cnt[2] = v.y; cnt[3] = v.x;
+    *gp = make_uint4(0u, 0u, 0u, 0u);  // clean for the next call
+  }
+  if (k <= 0) return r;  // (CTA-uniform)
+  {
+    unsigned int mine = 0;
+#pragma unroll
+    for (int j = 0; j < kPer; ++j) mine += cnt[j];
+    int tot;
+    const unsigned int before = unsigned(mine_excl_scan(int(mine), S.warp_tot, &tot));
+    if (before < (unsigned long long)k && (unsigned long long)k <= (unsigned long long)before + mine) {
+      unsigned long long acc = before;
+      bool found = false;
+#pragma unroll
+      for (int j = 0; j < kPer; ++j) {
+        const unsigned int h = cnt[j];
+        if (!found && acc < (unsigned long long)k && (unsigned long long)k <= acc + h) {
+          S.misc[0] = kBins - kPer * tid - 1 - j;
+          S.misc[1] = int((unsigned long long)k - acc);
+          S.misc[2] = int(h);
+          found = true;
+        }
+        acc += h;
       }
-      acc += h;
+    }
+    __syncthreads();
+  }
+  const int d0 = S.misc[0];
+  int remaining = S.misc[1];  // rank of the k-th value inside its bin (from the top, 1-based)
+  const int n0 = S.misc[2];   // candidates in the bin
+  const bool fits = n0 <= kSelCap;
+  CM_STAMP_SET(8 + 4 * (blockIdx.x & 63) + 1);
+  // ---- one pass: everything above the bin is summed, the bin's values are collected ----
+  double above = 0.0;
+  int filled = 0;  // (CTA-uniform) values placed so far
+  {
+    // 128-bit loads over the 16-byte aligned interior, the ragged ends by the first threads
+    const int head = int((4u - unsigned((reinterpret_cast<uintptr_t>(vals) >> 2) & 3u)) & 3u);
+    const long long nh = head < n ? head : n;
+    const long long n4 = (n - nh) >> 2;
+    const long long tail0 = nh + 4 * n4;
+    const float4* v4 = reinterpret_cast<const float4*>(vals + nh);
+    constexpr int kB = 6;  // 128-bit loads in flight per thread
+    bool ends_done = false;
+    for (long long i0 = 0; i0 < n4 || !ends_done; i0 += kB * kMineThreads) {
+      float4 v[kB];
+#pragma unroll
+      for (int u = 0; u < kB; ++u) {
+        const long long i = i0 + u * kMineThreads + tid;
+        v[u] = i < n4 ? __ldcg(v4 + i) : make_float4(-1.f, -1.f, -1.f, -1.f);
+      }
+      float ve = -1.f;  // the ragged ends ride along with the first round
+      if (!ends_done) {
+        if (tid < nh) ve = __ldcg(vals + tid);
+        else if (tid >= 32 && tail0 + (tid - 32) < n) ve = __ldcg(vals + tail0 + (tid - 32));
+      }
+      ends_done = true;
+      unsigned hits = 0;
+#pragma unroll
+      for (int u = 0; u < kB; ++u) {
+        const float e[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const int b = e[c] >= 0.f ? sel_bin(e[c]) : -1;
+          if (b > d0) above += double(e[c]);
+          if (b == d0) hits |= 1u << (4 * u + c);
+        }
+      }
+      {
+        const int b = ve >= 0.f ? sel_bin(ve) : -1;
+        if (b > d0) above += double(ve);
+        if (b == d0) hits |= 1u << (4 * kB);
+      }
+      int tot;
+      int at = filled + mine_excl_scan(__popc(hits), S.warp_tot, &tot);
+      if (fits && hits) {
+#pragma unroll
+        for (int u = 0; u < kB; ++u) {
+          const float e[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+#pragma unroll
+          for (int c = 0; c < 4; ++c)
+            if (hits & (1u << (4 * u + c))) S.vals[at++] = e[c];
+        }
+        if (hits & (1u << (4 * kB))) S.vals[at++] = ve;
+      }
+      filled += tot;
     }
   }
   __syncthreads();
+  CM_STAMP_SET(8 + 4 * (blockIdx.x & 63) + 2);
+  // ---- the k-th value inside the bin: 8-bit radix passes over the collected values (or over global memory) ----
+  const bool regular = d0 > 0 && d0 < kBins - 1;  // every value of a regular bin shares its leading 17 bits
+  uint32_t prefix = regular ? uint32_t(d0 - 1 + kSelLo) << 15 : 0u;
+  uint32_t mask = regular ? 0xffff8000u : 0u;
+  int n_ties = n0;
+  for (int shift = regular ? 7 : 24; shift >= 0; shift -= 8) {
+    const uint32_t dmask = shift == 7 ? 0xffu : (regular ? 0x7fu : 0xffu);
+    if (tid < 256) S.dig[tid] = 0u;
+    __syncthreads();
+    if (fits) {
+      for (int i = tid; i < n0; i += kMineThreads) {
+        const uint32_t bits = __float_as_uint(S.vals[i]);
+        if ((bits & mask) == prefix) atomicAdd(&S.dig[(bits >> shift) & dmask], 1u);
+      }
+    } else {
+      for (long long i = tid; i < n; i += kMineThreads) {
+        const float v = __ldcg(vals + i);
+        const uint32_t bits = __float_as_uint(v);
+        if (v >= 0.f && sel_bin(v) == d0 && (bits & mask) == prefix) atomicAdd(&S.dig[(bits >> shift) & dmask], 1u);
+      }
+    }
+    __syncthreads();
+    if (wid == 0) {  // lane l owns the digits 255 - 8 l ... 248 - 8 l, highest first
+      unsigned int c8[8];
+      unsigned int mine = 0;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        c8[j] = S.dig[255 - 8 * lane - j];
+        mine += c8[j];
+      }
+      unsigned int inc = mine;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const unsigned int t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += t;
+      }
+      unsigned int acc = inc - mine;
+      if (acc < unsigned(remaining) && unsigned(remaining) <= inc) {
+        bool found = false;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          if (!found && acc < unsigned(remaining) && unsigned(remaining) <= acc + c8[j]) {
+            S.misc[0] = 255 - 8 * lane - j;
+            S.misc[1] = int(unsigned(remaining) - acc);
+            S.misc[2] = int(c8[j]);
+            found = true;
+          }
+          acc += c8[j];
+        }
+      }
+    }
+    __syncthreads();
+    prefix |= uint32_t(S.misc[0]) << shift;
+    mask |= dmask << shift;
+    remaining = S.misc[1];
+    n_ties = S.misc[2];
+    __syncthreads();
+    if (shift == 7) shift = 8;  // (the last pass of a regular bin covers the low 7 bits: next shift = 0)
+  }
+  const float thr = __uint_as_float(prefix);
+  const int take_ties = remaining;
+  const bool all_ties = take_ties >= n_ties;
+  double inbin = 0.0;
+  if (fits) {
+    for (int i = tid; i < n0; i += kMineThreads)
+      if (S.vals[i] > thr) inbin += double(S.vals[i]);
+  } else {
+    for (long long i = tid; i < n; i += kMineThreads) {
+      const float v = __ldcg(vals + i);
+      if (v > thr && sel_bin(v) == d0) inbin += double(v);
+    }
+  }
+  r.sum = block_sum(above + inbin, S.red) + double(take_ties) * double(thr);
+  r.thr = thr;
+  r.ties = all_ties ? 1.f : 0.f;
+  if (!all_ties && sel) {
+    // rare: only some of the values equal to the threshold belong to the selection - the first ones by index.
+    // Every thread walks a contiguous run of the values; runs are ranked by an exclusive scan.
+    const long long per = (n + kMineThreads - 1) / kMineThreads;
+    const long long lo = per * tid < n ? per * tid : n, hi = lo + per < n ? lo + per : n;
+    int mine = 0;
+    for (long long i = lo; i < hi; ++i) mine += __ldcg(vals + i) == thr ? 1 : 0;
+    int tot;
+    int left = take_ties - mine_excl_scan(mine, S.warp_tot, &tot);
+    for (long long i = lo; i < hi && left > 0; ++i)
+      if (__ldcg(vals + i) == thr) {
+        sel[i] = uint8_t(sel[i] | 2);
+        --left;
+      }
+  }
+  return r;
 }
 
 // ------------------------------------------------------------------------------------------
-// classify_mine_kernel: grid (slices per image, N), 1024 threads, each CTA owns a contiguous slice of an
-// image's priors.
-//   every CTA:  rebuilds the image's short forced-match list from the per-object keys and applies it to its
-//               slice (rank inside the FILTERED list, last write wins - SSD512.py:546-553); classes, selection
-//               bits, mining candidates (4 priors per thread, all loads in flight together); the rows with a
-//               foreground class are recorded and evaluated densely (true-class CE, loc term); the leading
-//               radix digit of its candidates goes into the image's histogram (warp-aggregated atomics);
-//               partial sums to global memory; then it takes a ticket of its image.
-//   the CTA that takes an image's LAST ticket mines the image while other CTAs still classify theirs:
-//               n_pos from the slices' partials (fixed order), radix select of the 3 * n_pos largest
-//               candidate CEs - the first digit's histogram is already there, two more passes over the
-//               image's candidates (L2) - their sum (SSD512.py:610-619 consumes only the sum), selection bits by
-//               plain stores; then a ticket of the batch: the last image folds the batch in image order
-//               (deterministic), exchanges the sums with the other ranks if the batch is sharded, and
-//               finalises the loss.
-// One launch, no cluster, no grid-wide barrier: the only serial part is the last image's tail.
+// classify_kernel: grid (slices per image, N), 256 threads, each CTA owns 2048 consecutive priors of an image
+// (three CTAs per SM: the whole grid is resident at the SSD512 shape). Rebuilds the image's short forced-match
+// list from the per-object keys and applies it to its slice (rank inside the FILTERED list, last write wins -
+// SSD512.py:546-553); classes, selection bits, mining candidates (8 priors per thread, all loads in flight
+// together) and their histogram; the rows with a foreground class are recorded and evaluated densely
+// (true-class CE, loc term); partial sums of the slice to global memory. Programmatic dependent launch behind
+// the match kernel, and it releases mine_kernel's launch at once.
 // ------------------------------------------------------------------------------------------
-constexpr int kCmThreads = 1024;
-constexpr int kCmUnroll = 4;      // priors per thread whose loads are in flight together
+constexpr int kCmThreads = 256;
+constexpr int kCmWarps = kCmThreads / 32;
+constexpr int kCmUnroll = 8;                      // priors per thread whose loads are in flight together
 constexpr int kCmSlice = kCmThreads * kCmUnroll;  // priors per CTA
-constexpr int kCmFgCap = kCmSlice;                // foreground-row list: at worst every prior of the slice
-constexpr int kCmMaxCluster = 8;                  // (mine_batch_kernel)
-
-constexpr int kCmValCap = 2 * kBins;  // candidate values of one leading digit kept in shared memory by the tail
 
 struct CmShared {
-  unsigned int hist[kBins];  // leading-digit histogram of the slice, then the digit histograms of the tail
-  unsigned long long msum[kBins];  // per leading digit: sum of the candidates' 24-bit mantissas (exact integer
-                                   // arithmetic: all values of a digit share their exponent); the tail reuses the
-                                   // storage for the values of the digit that holds the k-th candidate
+  unsigned int hist[kBins];   // the slice's candidate histogram
   double red4[4 * 32];
-  double red[34];
-  unsigned int wt[32];
-  int warp_tot[kCmThreads / 32];
-  int misc[8];
+  int warp_tot[kCmWarps];
   int carry;
-  int last;
   int fg_n;
-  uint16_t cnt[kCmUnroll][kCmThreads / 32];
-  uint16_t fg_idx[kCmFgCap];   // foreground rows: prior index inside the slice
-  uint16_t fg_cls[kCmFgCap];   // ... class (bit 15: positive)
-  uint16_t fg_obj[kCmFgCap];   // ... object of the image
+  uint16_t cnt[kCmUnroll][kCmWarps];
+  uint16_t fg_idx[kCmSlice];  // foreground rows: prior index inside the slice
+  uint16_t fg_cls[kCmSlice];  // ... class (bit 15: positive)
+  uint16_t fg_obj[kCmSlice];  // ... object of the image
+  float fg_lse[kCmSlice];     // ... log-sum-exp of its logits
+  int patch[kCmSlice];        // forced matches of the slice: 1 + rank of the object that claims the prior, 0 = none
 };
 
-// the tail of one image: runs in the CTA that took the image's last ticket
-__device__ void cm_image_tail(const LossParams& q, CmShared& S, int n, int slices) {
-  const int tid = threadIdx.x;
+__global__ void __launch_bounds__(kCmThreads, 3) classify_kernel(const LossParams q) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  CmShared& S = *reinterpret_cast<CmShared*>(smem_raw);
+  int32_t* s_label = reinterpret_cast<int32_t*>(smem_raw + ((sizeof(CmShared) + 127) & ~size_t(127)));  // [gmax]
+
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");  // mine_kernel may take its place early
+  const int n = blockIdx.y, slices = gridDim.x;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int p_lo = min(q.P, int(blockIdx.x) * kCmSlice), p_hi = min(q.P, p_lo + kCmSlice);
   const size_t base = size_t(n) * q.P;
   const bool focal = q.cls_kind == SBOD_CLS_FOCAL_SUM || q.cls_kind == SBOD_CLS_FOCAL_NORM;
-  const int g0 = q.gt_offsets[n];
+  const int g0 = q.gt_offsets[n];  // (inputs of the call, not results of the match kernel)
   const int G = q.gt_offsets[n + 1] - g0;
-  __threadfence();  // the other slices' results (published before their tickets) are visible from here on
-  // leave the per-object keys clean for the next call (every slice has read them)
-  for (int g = tid; g < G; g += kCmThreads) q.gtkey[size_t(n) * q.gmax + g] = 0ull;
-  double img[4] = {0.0, 0.0, 0.0, 0.0};
-  {
-    const double* bp = q.blockpart + size_t(n) * slices * 4;
-    for (int b = 0; b < slices; ++b) {  // slice order: deterministic
+  CM_STAMP_MIN(0);
+  if (tid == 0) S.carry = 0;
+  for (int g = tid; g < G; g += kCmThreads) s_label[g] = int(map_label(q, q.gt_labels[g0 + g]));
+  for (int i = tid; i < kCmSlice; i += kCmThreads) S.patch[i] = 0;
+  if (!focal)
+    for (int i = tid; i < kBins; i += kCmThreads) S.hist[i] = 0u;
+  uint8_t ex[kCmUnroll];
 #pragma unroll
-      for (int k = 0; k < 4; ++k) img[k] += __ldcg(bp + b * 4 + k);
+  for (int u = 0; u < kCmUnroll; ++u) {
+    const int p = p_lo + u * kCmThreads + tid;
+    ex[u] = (q.exclude && p < p_hi) ? q.exclude[base + p] : uint8_t(0);
+  }
+  // the image's candidate histogram (SSD300 mines the batch: one histogram for all images)
+  unsigned int* gh = q.sel_hist + (q.cls_kind == SBOD_CLS_CE_MINE_BATCH ? size_t(0) : size_t(n) * kBins);
+
+  // everything above is independent of the match kernel's results; from here on they are needed
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  CM_STAMP_MIN(1);
+  // ---- every load of the slice is requested at once: the first per-object keys, then the per-prior state of
+  // 8 priors per thread ----
+  unsigned long long key0 = tid < G ? q.gtkey[size_t(n) * q.gmax + tid] : 0ull;
+  float ov[kCmUnroll], ce[kCmUnroll], lse[kCmUnroll];
+  int ob[kCmUnroll];
+#pragma unroll
+  for (int u = 0; u < kCmUnroll; ++u) {
+    const int p = p_lo + u * kCmThreads + tid;
+    ov[u] = 0.f; ce[u] = 0.f; lse[u] = 0.f; ob[u] = 0;
+    if (p < p_hi) {
+      ov[u] = q.ov[base + p];
+      ob[u] = q.obj[base + p];
+      ce[u] = q.ce[base + p];  // background CE from the streaming kernel
+      lse[u] = q.lse[base + p];
     }
   }
-  double t_neg = img[2];  // focal: sum over the negatives; MINE_BATCH: number of candidates (see mine_batch_kernel)
-  const bool select = !focal && q.cls_kind != SBOD_CLS_CE_MINE_BATCH;
+  __syncthreads();
+  // ---- forced list: rank j of each object inside "objects whose best overlap is > 0"; the entries that fall
+  // into this slice go into a table indexed by prior ("for j: obj[pr[j]] = j": the last j wins,
+  // SSD512.py:552-553 - ranks grow with the object index, so the largest rank wins) ----
+  for (int gb = 0; gb < G; gb += kCmThreads) {
+    const int g = gb + tid;
+    const unsigned long long key = gb == 0 ? key0 : (g < G ? q.gtkey[size_t(n) * q.gmax + g] : 0ull);
+    const bool f = key != 0ull;
+    const unsigned bal = __ballot_sync(0xffffffffu, f);
+    if (lane == 0) S.warp_tot[wid] = __popc(bal);
+    __syncthreads();
+    int off = S.carry, tot = 0;
+#pragma unroll
+    for (int w = 0; w < kCmWarps; ++w) {
+      const int t = S.warp_tot[w];
+      if (w < wid) off += t;
+      tot += t;
+    }
+    if (f) {
+      const uint32_t p = 0xffffffffu - uint32_t(key & 0xffffffffull);
+      const int j = off + __popc(bal & ((1u << lane) - 1u));
+      if (p >= uint32_t(p_lo) && p < uint32_t(p_hi)) atomicMax(&S.patch[p - p_lo], j + 1);
+    }
+    __syncthreads();
+    if (tid == 0) S.carry += tot;
+  }
+  __syncthreads();
+  CM_STAMP_MAX(2);
+
+  // ---- phase A: classes, selection bits, mining candidates ----
+  double a_loc = 0.0, a_pos = 0.0, a_neg = 0.0;
+  int npos = 0;
+  int rec[kCmUnroll], rrank[kCmUnroll];
+#pragma unroll
+  for (int u = 0; u < kCmUnroll; ++u) {
+    const int p = p_lo + u * kCmThreads + tid;
+    rec[u] = 0;
+    if (p < p_hi) {
+      const int forced = S.patch[u * kCmThreads + tid];
+      if (forced) {  // index_fill_(0, prior_for_each_object, 1.0) and the object override
+        ov[u] = 1.0f;
+        ob[u] = forced - 1;
+        q.ov[base + p] = 1.0f;
+        q.obj[base + p] = forced - 1;
+      }
+      int cls = 0;
+      if (!(ov[u] < q.thr_pos) && G > 0) cls = s_label[ob[u]];
+      const bool pos = cls > 0 && !ex[u];
+      const bool isneg = ov[u] < q.thr_neg;
+      uint8_t selbits = pos ? 1 : 0;
+      float v = -1.f;
+      if (cls > 0) {
+        rec[u] = min(cls, q.C - 1) | (pos ? 0x8000 : 0);  // C <= 16384 elsewhere; classes fit 15 bits
+      } else if (focal) {
+        if (isneg) {  // target class is 0 there (thr_neg < thr_pos)
+          selbits |= 2;
+          a_neg += double(focal_bg(q, ce[u]));
+        }
+      } else if (q.cls_kind == SBOD_CLS_CE_MINE_NONPOS) {
+        if (!ex[u]) v = ce[u];
+      } else {  // MINE_NEG, MINE_BATCH: only true_neg == -1 rows are candidates
+        if (isneg) v = ce[u];
+      }
+      if (!focal && v >= 0.f) {
+        a_neg += 1.0;  // mining modes: this partial counts the candidates (NaN CEs are none)
+        atomicAdd(&S.hist[sel_bin(v)], 1u);
+        selbits |= 4;  // "mining candidate": the backward compares its CE with the threshold
+      }
+      q.sel[base + p] = selbits;
+      if (!focal) q.cand[base + p] = v;
+    }
+    const unsigned bal = __ballot_sync(0xffffffffu, rec[u] != 0);
+    rrank[u] = __popc(bal & ((1u << lane) - 1u));
+    if (lane == 0) S.cnt[u][wid] = uint16_t(__popc(bal));
+  }
+  __syncthreads();
+  // list offsets of the (unroll slot, warp) pairs: exclusive scan of the 64 counts by warp 0; the list order
+  // is deterministic (unroll slot, warp, ballot rank), so the sums are reproducible
+  if (wid == 0) {
+    static_assert(kCmUnroll * kCmWarps == 64, "two (slot, warp) pairs per lane");
+    uint16_t* flat = &S.cnt[0][0];
+    const int c0 = flat[2 * lane], c1 = flat[2 * lane + 1];
+    int inc = c0 + c1;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, inc, o);
+      if (lane >= o) inc += t;
+    }
+    flat[2 * lane] = uint16_t(inc - c0 - c1);
+    flat[2 * lane + 1] = uint16_t(inc - c1);
+    if (lane == 31) S.fg_n = inc;
+  }
+  // the slice's histogram joins the image's: one L2 reduction per non-empty bin
+  if (!focal) {
+#pragma unroll 4
+    for (int i = tid; i < kBins; i += kCmThreads) {
+      const unsigned int c = S.hist[i];
+      if (c) atomicAdd(&gh[i], c);
+    }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int u = 0; u < kCmUnroll; ++u) {
+    if (rec[u]) {
+      const int slot = int(S.cnt[u][wid]) + rrank[u];
+      S.fg_idx[slot] = uint16_t(u * kCmThreads + tid);
+      S.fg_cls[slot] = uint16_t(rec[u]);
+      S.fg_obj[slot] = uint16_t(ob[u]);
+      S.fg_lse[slot] = lse[u];
+    }
+  }
+  __syncthreads();
+  CM_STAMP_MAX(3);
+  // ---- phase B: the recorded foreground rows (2-3 % of the priors), one per thread, every load of a row
+  // independent of the others ----
+  {
+    const int total = S.fg_n;
+    for (int i = tid; i < total; i += kCmThreads) {
+      const int pp = p_lo + int(S.fg_idx[i]);
+      const int c = S.fg_cls[i] & 0x7fff;
+      const bool pos = (S.fg_cls[i] & 0x8000) != 0;
+      const float xc = ld_stream_f32(q.scores + (base + pp) * q.C + c);
+      float4 pred = make_float4(0.f, 0.f, 0.f, 0.f), pcx = pred, gbox = pred;
+      if (pos) {
+        pred = reinterpret_cast<const float4*>(q.locs)[base + pp];
+        pcx = prior_cxcy_of(q, n, pp);
+        gbox = q.gt_boxes[g0 + S.fg_obj[i]];
+      }
+      const float cet = S.fg_lse[i] - xc;  // CE against the true class
+      q.ce[base + pp] = cet;
+      if (pos) {
+        ++npos;
+        a_pos += focal ? double(focal_fg(q, cet)) : double(cet);
+        const LocTerm lt = loc_term<false>(q, pred, pcx, gbox);
+        a_loc += double(lt.loss);
+      }
+    }
+  }
+  CM_STAMP_MAX(4);
+  // ---- partial sums of the slice ----
+  double tot[4] = {a_loc, a_pos, a_neg, double(npos)};
+  block_sum4_to_thread0(tot, S.red4);
+  if (tid == 0) {
+    double* bp = q.blockpart + (size_t(n) * slices + blockIdx.x) * 4;
+    bp[0] = tot[0]; bp[1] = tot[1]; bp[2] = tot[2]; bp[3] = tot[3];
+  }
+  CM_STAMP_MAX(5);
+}
+
+// ------------------------------------------------------------------------------------------
+// mine_kernel: one CTA of 1024 threads per image, programmatic dependent launch behind classify_kernel.
+// n_pos and the other sums of the image from the slices' partials (fixed order), sum of its 3 * n_pos largest
+// candidate CEs (select_topk_sum), the threshold for the backward; then a ticket of the batch: the last image
+// folds the batch in image order (deterministic), mines the batch when the criterion does that
+// (SSD300.py:580-588), exchanges the sums with the other ranks if the batch is sharded, and finalises the loss.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kMineThreads, 1) mine_kernel(const LossParams q, const int slices) {
+  __shared__ MineShared S;
+  const int n = blockIdx.x, tid = threadIdx.x;
+  const size_t base = size_t(n) * q.P;
+  const bool focal = q.cls_kind == SBOD_CLS_FOCAL_SUM || q.cls_kind == SBOD_CLS_FOCAL_NORM;
+  const int G = q.gt_offsets[n + 1] - q.gt_offsets[n];
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  CM_STAMP_SET(8 + 4 * (n & 63));
+  // leave the per-object keys clean for the next call (every slice has read them)
+  for (int g = tid; g < G; g += kMineThreads) q.gtkey[size_t(n) * q.gmax + g] = 0ull;
+  if (tid < 4) {
+    const double* bp = q.blockpart + size_t(n) * slices * 4 + tid;
+    double acc = 0.0;
+#pragma unroll 8
+    for (int b = 0; b < slices; ++b) acc += __ldcg(bp + b * 4);  // slice order: deterministic
+    S.red4[tid] = acc;
+  }
+  __syncthreads();
+  const double img[4] = {S.red4[0], S.red4[1], S.red4[2], S.red4[3]};
+  __syncthreads();
+  double t_neg = img[2];  // focal: sum over the negatives; MINE_BATCH: number of candidates (batch tail)
   // what the backward needs to know about the image's mined negatives: a candidate row (flag bit 2) is mined
   // iff its CE > thr, or == thr when every tie is taken; +inf = none
-  float sel_thr = __int_as_float(0x7f800000);
-  float sel_ties = 0.f;
-  if (select) {
-    unsigned int* gh = q.sel_hist + size_t(n) * kBins;
-    unsigned long long* gm = q.sel_msum + size_t(n) * kBins;
+  float sel_thr = __int_as_float(0x7f800000), sel_ties = 0.f;
+  if (!focal && q.cls_kind != SBOD_CLS_CE_MINE_BATCH) {
     const long long n_cand = (long long)(img[2] + 0.5);
     long long k = (long long)(q.ratio) * (long long)(img[3] + 0.5);
     if (k > n_cand) k = n_cand;
-    t_neg = 0.0;
-    // first digit (12 bits): counts and mantissa sums accumulated by the slices; read them, leave them clean
-    for (int b = tid; b < kBins; b += kCmThreads) {
-      S.hist[b] = __ldcg(&gh[b]);
-      S.msum[b] = __ldcg(&gm[b]);
-      gh[b] = 0u;
-      gm[b] = 0ull;
-    }
-    __syncthreads();
-    if (k > 0) {  // (CTA-uniform)
-      const float* vals = q.cand + base;
-      block_find_digit(S.hist, kBins, k, S.wt, S.misc);
-      const int d0 = S.misc[0];
-      long long remaining = S.misc[1];
-      const int n0 = S.misc[2];
-      // sum of every candidate above the digit: exact per digit (integer mantissa sum x the digit's power of two)
-      double above = 0.0;
-      for (int b = tid; b < kBins; b += kCmThreads) {
-        if (b > d0 && S.hist[b]) {
-          const int e = b >> 3;  // exponent field of every value of the digit
-          above += ldexp(double(S.msum[b]), (e ? e : 1) - 150);
-        }
-      }
-      above = block_sum(above, S.red);
-      if (remaining >= n0) {
-        // the whole digit is taken: no pass over the candidates at all
-        const int e = d0 >> 3;
-        t_neg = above + ldexp(double(S.msum[d0]), (e ? e : 1) - 150);
-        sel_thr = __uint_as_float(uint32_t(d0) << 20);  // lowest value of the digit
-        sel_ties = 1.f;
-      } else {
-        // The k-th candidate lies inside digit d0 (n0 values): ONE pass over the image's candidates (L2) collects
-        // them into shared memory; the remaining digits are resolved there.
-        float* s_vals = reinterpret_cast<float*>(S.msum);  // (the mantissa sums are consumed)
-        const bool fits = n0 <= kCmValCap;
-        uint32_t prefix = uint32_t(d0) << 20, mask = 0xfffu << 20;
-        int n_ties = n0;
-        __syncthreads();
-        if (tid == 0) S.fg_n = 0;  // (list cursor)
-        const int shifts[2] = {8, 0};
-        const int widths[2] = {12, 8};
-#pragma unroll 1
-        for (int pass = 0; pass < 2; ++pass) {
-          const int shift = shifts[pass];
-          const uint32_t dmask = (1u << widths[pass]) - 1u;
-          const int nb = 1 << widths[pass];
-          __syncthreads();
-          for (int b = tid; b < nb; b += kCmThreads) S.hist[b] = 0u;
-          __syncthreads();
-          if (pass == 0 || !fits) {
-            for (int i0 = 0; i0 < q.P; i0 += kCmThreads * 8) {  // eight independent loads in flight per thread
-              float v[8];
-#pragma unroll
-              for (int u = 0; u < 8; ++u) {
-                const int i = i0 + u * kCmThreads + tid;
-                v[u] = i < q.P ? __ldcg(vals + i) : -1.f;
-              }
-#pragma unroll
-              for (int u = 0; u < 8; ++u) {
-                const uint32_t bits = __float_as_uint(v[u]);
-                const bool hit = v[u] >= 0.f && (bits & mask) == prefix;
-                if (hit) atomicAdd(&S.hist[(bits >> shift) & dmask], 1u);
-                if (pass == 0 && fits) {  // keep the digit's values (any order: only sums and counts are formed)
-                  const unsigned bal = __ballot_sync(0xffffffffu, hit);
-                  int at = 0;
-                  const int lane = tid & 31;
-                  if (bal && lane == 0) at = atomicAdd(&S.fg_n, __popc(bal));
-                  at = __shfl_sync(0xffffffffu, at, 0);
-                  if (hit) s_vals[at + __popc(bal & ((1u << lane) - 1u))] = v[u];
-                }
-              }
-            }
-          } else {
-            for (int i = tid; i < n0; i += kCmThreads) {
-              const uint32_t bits = __float_as_uint(s_vals[i]);
-              if ((bits & mask) == prefix) atomicAdd(&S.hist[(bits >> shift) & dmask], 1u);
-            }
-          }
-          __syncthreads();
-          block_find_digit(S.hist, nb, remaining, S.wt, S.misc);
-          prefix |= uint32_t(S.misc[0]) << shift;
-          mask |= dmask << shift;
-          remaining = S.misc[1];
-          n_ties = S.misc[2];
-        }
-        const float thr = __uint_as_float(prefix);
-        const int take_ties = int(remaining);
-        const bool all_ties = take_ties >= n_ties;
-        // values of digit d0 above the threshold (fixed-order reduction of doubles: deterministic given the list;
-        // the list order depends on atomics, the SUM of these few values in double does not to 1e-16)
-        double acc = 0.0;
-        const uint32_t d0_lo = uint32_t(d0) << 20;
-        if (fits) {
-          for (int i = tid; i < n0; i += kCmThreads)
-            if (s_vals[i] > thr) acc += double(s_vals[i]);
-        } else {
-          for (int i = tid; i < q.P; i += kCmThreads) {
-            const float v = __ldcg(vals + i);
-            if (v > thr && (__float_as_uint(v) >> 20) == (d0_lo >> 20)) acc += double(v);
-          }
-        }
-        t_neg = above + block_sum(acc, S.red) + double(take_ties) * double(thr);
-        sel_thr = thr;
-        sel_ties = all_ties ? 1.f : 0.f;
-        if (!all_ties && tid == 0) {  // rare: the ties that belong to the top-k are the first ones by index
-          uint8_t* sel_out = q.sel + base;
-          int left = take_ties;
-          for (int i = 0; i < q.P && left > 0; ++i)
-            if (__ldcg(vals + i) == thr) {
-              sel_out[i] = uint8_t(__ldcg(sel_out + i) | 2);
-              --left;
-            }
-        }
-      }
-    }
-  }
-  if (tid == 0 && q.sel_thr) {
-    q.sel_thr[2 * n] = sel_thr;
-    q.sel_thr[2 * n + 1] = sel_ties;
+    const TopkSum r = select_topk_sum(S, q.cand + base, q.P, q.sel_hist + size_t(n) * kBins, k, q.sel + base);
+    t_neg = r.sum;
+    sel_thr = r.thr;
+    sel_ties = r.ties;
   }
   if (tid == 0) {
-    q.img_done[n] = 0u;  // clean for the next call
+    q.sel_thr[2 * n] = sel_thr;
+    q.sel_thr[2 * n + 1] = sel_ties;
     q.partials[n * 4 + 0] = img[0];
     q.partials[n * 4 + 1] = img[1];
     q.partials[n * 4 + 2] = t_neg;
@@ -1218,284 +1349,44 @@ __device__ void cm_image_tail(const LossParams& q, CmShared& S, int n, int slice
     S.last = (ticket == unsigned(q.N) - 1u) ? 1 : 0;
   }
   __syncthreads();
-  if (S.last && tid < 32) {  // the last image folds the batch in image order (deterministic)
-    __threadfence();
-    double acc = 0.0;
-    if (tid < 4) {
-      const double* pp = q.partials;
-      for (int i = 0; i < q.N; ++i) acc += __ldcg(pp + i * 4 + tid);
-    }
-    if (q.comm) {
-      // sharded batch: the four sums of this rank meet those of the other ranks through the NVLink mailboxes
-      // (every rank adds them in rank order); the loss is then formed from the global sums, and the backward
-      // scales by the global 1 / n_pos
-      double v[4];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) v[i] = __shfl_sync(0xffffffffu, acc, i);
-      comm_allreduce_sum(q.comm, v, 4);
-      acc = tid < 4 ? v[tid & 3] : 0.0;
-    }
-    if (tid < 4) q.sums[tid] = acc;
-  }
-  __syncthreads();
-  if (S.last && tid == 0) {
-    q.counters[0] = 0u;
-    if (q.cls_kind != SBOD_CLS_CE_MINE_BATCH) finalize_loss(q, q.sums, q.loss);
-  }
-}
-
-__global__ void __launch_bounds__(kCmThreads) classify_mine_kernel(const LossParams q) {
-  extern __shared__ __align__(128) unsigned char smem_raw[];
-  CmShared& S = *reinterpret_cast<CmShared*>(smem_raw);
-  unsigned char* dyn = smem_raw + ((sizeof(CmShared) + 127) & ~size_t(127));
-  float4* s_gbox = reinterpret_cast<float4*>(dyn);                 // [gmax] the image's objects
-  uint32_t* s_prior = reinterpret_cast<uint32_t*>(s_gbox + q.gmax);  // [gmax]
-  int32_t* s_rank = reinterpret_cast<int32_t*>(s_prior + q.gmax);  // [gmax], -1 = filtered out
-  int32_t* s_label = s_rank + q.gmax;                              // [gmax] mapped labels
-
-  const int n = blockIdx.y, slices = gridDim.x;
-  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-  const int p_lo = min(q.P, int(blockIdx.x) * kCmSlice), p_hi = min(q.P, p_lo + kCmSlice);
-  const size_t base = size_t(n) * q.P;
-  const bool focal = q.cls_kind == SBOD_CLS_FOCAL_SUM || q.cls_kind == SBOD_CLS_FOCAL_NORM;
-  const bool select = !focal && q.cls_kind != SBOD_CLS_CE_MINE_BATCH;
-  const int g0 = q.gt_offsets[n];  // (inputs of the call, not results of the match kernel)
-  const int G = q.gt_offsets[n + 1] - g0;
-  if (tid == 0) {
-    S.carry = 0;
-    S.fg_n = 0;
-  }
-  for (int g = tid; g < G; g += kCmThreads) {
-    s_gbox[g] = q.gt_boxes[g0 + g];
-    s_label[g] = int(map_label(q, q.gt_labels[g0 + g]));
-  }
-  if (select)
-    for (int b = tid; b < kBins; b += kCmThreads) {
-      S.hist[b] = 0u;
-      S.msum[b] = 0ull;
-    }
-
-  // everything above is independent of the match kernel's results; from here on they are needed
-  asm volatile("griddepcontrol.wait;" ::: "memory");
-  __syncthreads();
-  // ---- forced list: rank j of each object inside "objects whose best overlap is > 0" ----
-  for (int gb = 0; gb < G; gb += kCmThreads) {
-    const int g = gb + tid;
-    const unsigned long long key = g < G ? q.gtkey[size_t(n) * q.gmax + g] : 0ull;
-    const bool f = key != 0ull;
-    const unsigned bal = __ballot_sync(0xffffffffu, f);
-    if (lane == 0) S.warp_tot[wid] = __popc(bal);
-    __syncthreads();
-    int off = S.carry;
-    for (int w = 0; w < wid; ++w) off += S.warp_tot[w];
-    if (g < G) {
-      s_prior[g] = 0xffffffffu - uint32_t(key & 0xffffffffull);
-      s_rank[g] = f ? off + __popc(bal & ((1u << lane) - 1u)) : -1;
-    }
-    __syncthreads();
-    if (tid == 0) {
-      int t = 0;
-      for (int w = 0; w < kCmThreads / 32; ++w) t += S.warp_tot[w];
-      S.carry += t;
-    }
-    __syncthreads();
-  }
-  for (int g = tid; g < G; g += kCmThreads) {
-    const int j = s_rank[g];
-    if (j < 0) continue;
-    const uint32_t p = s_prior[g];
-    if (p < uint32_t(p_lo) || p >= uint32_t(p_hi)) continue;
-    bool winner = true;  // "for j: obj[pr[j]] = j" -> the last j wins (SSD512.py:552-553)
-    for (int h = g + 1; h < G; ++h)
-      if (s_rank[h] >= 0 && s_prior[h] == p) {
-        winner = false;
-        break;
-      }
-    q.ov[base + p] = 1.0f;  // index_fill_(0, prior_for_each_object, 1.0)
-    if (winner) q.obj[base + p] = j;
-  }
-  __syncthreads();  // the patched overlaps / objects are visible to the whole CTA
-
-  // ---- phase A: every prior of the slice, all loads of a thread's four priors in flight together ----
-  double a_loc = 0.0, a_pos = 0.0, a_neg = 0.0;
-  int npos = 0;
-  {
-    float ov[kCmUnroll], ce[kCmUnroll];
-    int ob[kCmUnroll];
-    uint8_t ex[kCmUnroll];
-#pragma unroll
-    for (int u = 0; u < kCmUnroll; ++u) {
-      const int p = p_lo + u * kCmThreads + tid;
-      ov[u] = 0.f; ce[u] = 0.f; ob[u] = 0; ex[u] = 0;
-      if (p < p_hi) {
-        ov[u] = q.ov[base + p];
-        ob[u] = q.obj[base + p];
-        ce[u] = q.ce[base + p];  // background CE from the streaming kernel
-        if (q.exclude) ex[u] = q.exclude[base + p];
-      }
-    }
-    int rec[kCmUnroll], rrank[kCmUnroll];
-#pragma unroll
-    for (int u = 0; u < kCmUnroll; ++u) {
-      const int p = p_lo + u * kCmThreads + tid;
-      rec[u] = 0;
-      int digit = -1;
-      unsigned int mant = 0u;
-      if (p < p_hi) {
-        int cls = 0;
-        if (!(ov[u] < q.thr_pos) && G > 0) cls = s_label[ob[u]];
-        const bool pos = cls > 0 && !ex[u];
-        const bool isneg = ov[u] < q.thr_neg;
-        uint8_t selbits = pos ? 1 : 0;
-        float v = -1.f;
-        if (cls > 0) {
-          rec[u] = min(cls, q.C - 1) | (pos ? 0x8000 : 0);  // C <= 16384 elsewhere; classes fit 15 bits
-        } else if (focal) {
-          if (isneg) {  // target class is 0 there (thr_neg < thr_pos)
-            selbits |= 2;
-            a_neg += double(focal_bg(q, ce[u]));
-          }
-        } else if (q.cls_kind == SBOD_CLS_CE_MINE_NONPOS) {
-          if (!ex[u]) v = ce[u];
-        } else {  // MINE_NEG, MINE_BATCH: only true_neg == -1 rows are candidates
-          if (isneg) v = ce[u];
-        }
-        if (!focal && v >= 0.f) {
-          a_neg += 1.0;  // mining modes: this partial counts the candidates (NaN CEs are none)
-          const uint32_t bits = __float_as_uint(v);
-          digit = int(bits >> 20);
-          mant = (bits & 0x7fffffu) | ((bits >> 23) ? 0x800000u : 0u);
-          selbits |= 4;  // "mining candidate": the backward compares its CE with the image's threshold
-        }
-        q.sel[base + p] = selbits;
-        q.cand[base + p] = v;
-      }
-      if (select) {
-        // leading digit of the candidate: lanes with the same digit add their count and mantissas once
-        const unsigned peers = __match_any_sync(0xffffffffu, digit);
-        const unsigned int msum = __reduce_add_sync(peers, mant);  // <= 32 * 2^24
-        if (digit >= 0 && lane == __ffs(peers) - 1) {
-          atomicAdd(&S.hist[digit], unsigned(__popc(peers)));
-          atomicAdd(&S.msum[digit], static_cast<unsigned long long>(msum));
-        }
-      }
-      const unsigned bal = __ballot_sync(0xffffffffu, rec[u] != 0);
-      rrank[u] = __popc(bal & ((1u << lane) - 1u));
-      if (lane == 0) S.cnt[u][wid] = uint16_t(__popc(bal));
-    }
-    __syncthreads();
-    // list offsets of the (unroll slot, warp) pairs: exclusive scan of the 128 counts by warp 0; the list
-    // order is deterministic (unroll slot, warp, ballot rank), so the sums are reproducible
-    if (wid == 0) {
-      constexpr int kPairs = kCmUnroll * (kCmThreads / 32);
-      static_assert(kPairs == 128, "four (slot, warp) pairs per lane");
-      uint16_t* flat = &S.cnt[0][0];
-      int c[4], tot = 0;
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        c[j] = flat[4 * lane + j];
-        tot += c[j];
-      }
-      int inc = tot;
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const int t = __shfl_up_sync(0xffffffffu, inc, o);
-        if (lane >= o) inc += t;
-      }
-      int ex0 = inc - tot;
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        flat[4 * lane + j] = uint16_t(ex0);
-        ex0 += c[j];
-      }
-      if (lane == 31) S.fg_n = inc;
-    }
-    __syncthreads();
-#pragma unroll
-    for (int u = 0; u < kCmUnroll; ++u) {
-      if (rec[u]) {
-        const int slot = int(S.cnt[u][wid]) + rrank[u];
-        S.fg_idx[slot] = uint16_t(u * kCmThreads + tid);
-        S.fg_cls[slot] = uint16_t(rec[u]);
-        S.fg_obj[slot] = uint16_t(ob[u]);
-      }
-    }
-    __syncthreads();
-  }
-  // ---- phase B: the recorded foreground rows (2-3 % of the priors), one per thread, every load of a row
-  // independent of the others (class, object and its box come from shared memory) ----
-  {
-    const int total = S.fg_n;
-    for (int i = tid; i < total; i += kCmThreads) {
-      const int pp = p_lo + int(S.fg_idx[i]);
-      const int c = S.fg_cls[i] & 0x7fff;
-      const bool pos = (S.fg_cls[i] & 0x8000) != 0;
-      const float lse = q.lse[base + pp];
-      const float xc = ld_stream_f32(q.scores + (base + pp) * q.C + c);
-      float4 pred = make_float4(0.f, 0.f, 0.f, 0.f), pcx = pred;
-      if (pos) {
-        pred = reinterpret_cast<const float4*>(q.locs)[base + pp];
-        pcx = prior_cxcy_of(q, n, pp);
-      }
-      const float ce = lse - xc;  // CE against the true class
-      q.ce[base + pp] = ce;
-      if (pos) {
-        ++npos;
-        a_pos += focal ? double(focal_fg(q, ce)) : double(ce);
-        const LocTerm lt = loc_term<false>(q, pred, pcx, s_gbox[S.fg_obj[i]]);
-        a_loc += double(lt.loss);
-      }
-    }
-  }
-  // ---- publish: leading-digit histogram, partial sums, ticket ----
-  if (select) {
-    unsigned int* gh = q.sel_hist + size_t(n) * kBins;
-    unsigned long long* gm = q.sel_msum + size_t(n) * kBins;
-    for (int b = tid; b < kBins; b += kCmThreads) {
-      const unsigned int v = S.hist[b];
-      if (v) {
-        atomicAdd(&gh[b], v);
-        atomicAdd(&gm[b], S.msum[b]);
-      }
-    }
-  }
-  double tot[4] = {a_loc, a_pos, a_neg, double(npos)};
-  block_sum4_to_thread0(tot, S.red4);
-  if (tid == 0) {
-    double* bp = q.blockpart + (size_t(n) * slices + blockIdx.x) * 4;
-    bp[0] = tot[0]; bp[1] = tot[1]; bp[2] = tot[2]; bp[3] = tot[3];
-  }
-  __threadfence();  // this slice's selection bits, candidates, histogram and partials before its ticket
-  __syncthreads();
-  if (tid == 0) S.last = (atomicAdd(&q.img_done[n], 1u) == unsigned(slices) - 1u) ? 1 : 0;
-  __syncthreads();
+  CM_STAMP_SET(8 + 4 * (n & 63) + 3);
   if (!S.last) return;
-  cm_image_tail(q, S, n, slices);
-}
-
-// SSD300's batch-global mining (SSD300.py:580-588): the sum(3 * n_pos) largest CEs over every true_neg == -1
-// row of the BATCH. One cluster of 8 CTAs; each owns a contiguous slice of the N*P candidate values.
-__global__ void __launch_bounds__(1024) mine_batch_kernel(const LossParams q) {
-  cg::cluster_group cluster = cg::this_cluster();
-  extern __shared__ __align__(128) unsigned char smem_raw[];
-  ClusterSelect& S = *reinterpret_cast<ClusterSelect*>(smem_raw);
-  const unsigned int n_ranks = cluster.num_blocks(), rank = cluster.block_rank();
-  const long long total = (long long)q.N * q.P;  // fits int for every supported shape (checked on the host)
-  const long long slice = (total + n_ranks - 1) / n_ranks;
-  const long long lo = min(total, (long long)rank * slice), hi = min(total, lo + slice);
-  const long long k = (long long)(q.ratio) * (long long)(q.sums[3] + 0.5);
-  const long long n_cand = (long long)(q.sums[2] + 0.5);  // candidates of the batch, counted by classify_mine_kernel
-  const SelectResult r = cluster_topk_sum(cluster, S, q.cand + lo, int(hi - lo), k, n_cand, q.batch_hist, q.sel + lo);
-  cluster.sync();
-  if (rank == 0) cluster_topk_cleanup(q.batch_hist);
-  if (rank == 0 && threadIdx.x == 0) {
-    double t = 0.0;
-    for (unsigned int rk = 0; rk < n_ranks; ++rk) t += *cluster.map_shared_rank(&S.sumv, rk);
-    if (r.k_eff > 0) t += double(r.take_ties) * double(__uint_as_float(r.thr_bits));
-    q.sums[2] = t;
-    finalize_loss(q, q.sums, q.loss);
+  // ---- the last image: fold the batch in image order (deterministic) ----
+  __threadfence();
+  if (tid < 4) {
+    double acc = 0.0;
+#pragma unroll 8
+    for (int i = 0; i < q.N; ++i) acc += __ldcg(q.partials + i * 4 + tid);
+    S.red4[tid] = acc;
   }
-  cluster.sync();
+  __syncthreads();
+  double tot[4] = {S.red4[0], S.red4[1], S.red4[2], S.red4[3]};
+  __syncthreads();
+  if (q.cls_kind == SBOD_CLS_CE_MINE_BATCH) {
+    // SSD300: the 3 * n_pos largest CEs over every candidate of the BATCH; one threshold for all images
+    const long long n_cand = (long long)(tot[2] + 0.5);
+    long long k = (long long)(q.ratio) * (long long)(tot[3] + 0.5);
+    if (k > n_cand) k = n_cand;
+    const TopkSum r = select_topk_sum(S, q.cand, (long long)q.N * q.P, q.sel_hist, k, q.sel);
+    tot[2] = r.sum;
+    for (int i = tid; i < q.N; i += kMineThreads) {
+      q.sel_thr[2 * i] = r.thr;
+      q.sel_thr[2 * i + 1] = r.ties;
+    }
+  }
+  if (tid < 32 && q.comm) {
+    // sharded batch: the four sums of this rank meet those of the other ranks through the NVLink mailboxes
+    // (every rank adds them in rank order); the loss is then formed from the global sums, and the backward
+    // scales by the global 1 / n_pos
+    comm_allreduce_sum(q.comm, tot, 4);
+  }
+  if (tid == 0) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) q.sums[i] = tot[i];
+    q.counters[0] = 0u;
+    finalize_loss(q, tot, q.loss);
+  }
+  CM_STAMP_MAX(7);
 }
 
 __global__ void finalize_kernel(const LossParams q) {
@@ -1733,7 +1624,7 @@ __global__ void __launch_bounds__(256, 4) bwd_patch_kernel(const LossParams q, c
       }
     }
     // flag bit 2: mining candidate - mined iff its (background) CE beats the image's threshold
-    // (classify_mine_kernel leaves the threshold instead of marking ~3 n_pos rows per image)
+    // (classify_kernel / mine_kernel leaves the threshold instead of marking ~3 n_pos rows per image)
     if (in && (selbits & 4)) {
       const int n = int(i / q.P);
       const float thr = q.sel_thr[2 * n], ties = q.sel_thr[2 * n + 1];
@@ -1864,7 +1755,7 @@ static int g_opt_pdl = 1;           // programmatic dependent launch between the
 static int g_opt_peer_exchange = 1; // one-shot NVLink exchange of the loss sums when a communicator is attached
 
 static size_t cm_smem_bytes(const LossParams& q) {
-  return ((sizeof(CmShared) + 127) & ~size_t(127)) + align_up(size_t(q.gmax) * 28, 128) + 128;
+  return ((sizeof(CmShared) + 127) & ~size_t(127)) + align_up(size_t(q.gmax) * 4, 128) + 128;
 }
 static int cm_slices(int P) { return (P + kCmSlice - 1) / kCmSlice; }
 
@@ -1919,12 +1810,6 @@ static int fill_params(const sbod_loss_desc* d, LossParams& q, bool need_scores)
   w += align_up(size_t(q.N) * 4, 256);
   q.sel_hist = reinterpret_cast<unsigned int*>(w);
   w += align_up(size_t(q.N) * kBins * 4, 256);
-  q.sel_msum = reinterpret_cast<unsigned long long*>(w);
-  w += align_up(size_t(q.N) * kBins * 8, 256);
-  q.batch_hist = reinterpret_cast<unsigned int*>(w);
-  w += align_up(size_t(3) * kBins * 4, 256);
-  q.img_done = reinterpret_cast<unsigned int*>(w);
-  w += align_up(size_t(q.N) * 4, 256);
   q.cand = reinterpret_cast<float*>(w);
   w += align_up(size_t(q.N) * q.P * 4, 256);
   q.blockpart = reinterpret_cast<double*>(w);
@@ -1977,8 +1862,7 @@ extern "C" size_t sbod_loss_workspace_zero_bytes(const sbod_loss_desc* d) {
   if (!d) return 0;
   const int gmax = d->gmax > 0 ? d->gmax : 1;
   return 256 + align_up(size_t(d->N) * gmax * 8, 256) + align_up(size_t(d->N) * 4, 256) +
-         align_up(size_t(d->N) * kBins * 4, 256) + align_up(size_t(d->N) * kBins * 8, 256) +
-         align_up(size_t(3) * kBins * 4, 256) + align_up(size_t(d->N) * 4, 256);
+         align_up(size_t(d->N) * kBins * 4, 256);
 }
 
 extern "C" int sbod_set_option(int key, int value) {
@@ -2005,13 +1889,12 @@ static int set_kernel_attrs() {
   SBOD_CUDA_TRY(cudaFuncSetAttribute(match_lse_fast_kernel<21>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   SBOD_CUDA_TRY(cudaFuncSetAttribute(loss_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   SBOD_CUDA_TRY(cudaFuncSetAttribute(forced_match_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-  SBOD_CUDA_TRY(cudaFuncSetAttribute(classify_mine_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024));
+  SBOD_CUDA_TRY(cudaFuncSetAttribute(classify_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
   // without a preference the driver picks the smallest shared-memory carve-out that fits ONE CTA per SM
-  SBOD_CUDA_TRY(cudaFuncSetAttribute(classify_mine_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+  SBOD_CUDA_TRY(cudaFuncSetAttribute(classify_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
   SBOD_CUDA_TRY(cudaFuncSetAttribute(match_lse_fast_kernel<0>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
   SBOD_CUDA_TRY(cudaFuncSetAttribute(match_lse_fast_kernel<81>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
   SBOD_CUDA_TRY(cudaFuncSetAttribute(match_lse_fast_kernel<21>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-  SBOD_CUDA_TRY(cudaFuncSetAttribute(mine_batch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
   attr_once.mark();
   return SBOD_OK;
 }
@@ -2058,22 +1941,11 @@ static int launch_mine(const LossParams& q, cudaStream_t st) {
     attrs[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attrs;
     cfg.numAttrs = g_opt_pdl ? 1 : 0;
-    SBOD_CUDA_TRY(cudaLaunchKernelEx(&cfg, classify_mine_kernel, q));
-  }
-  if (q.cls_kind == SBOD_CLS_CE_MINE_BATCH) {
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(kCmMaxCluster, 1, 1);
-    cfg.blockDim = dim3(1024, 1, 1);
-    cfg.dynamicSmemBytes = sizeof(ClusterSelect);
-    cfg.stream = st;
-    cudaLaunchAttribute attrs[1];
-    attrs[0].id = cudaLaunchAttributeClusterDimension;
-    attrs[0].val.clusterDim.x = kCmMaxCluster;
-    attrs[0].val.clusterDim.y = 1;
-    attrs[0].val.clusterDim.z = 1;
-    cfg.attrs = attrs;
-    cfg.numAttrs = 1;
-    SBOD_CUDA_TRY(cudaLaunchKernelEx(&cfg, mine_batch_kernel, q));
+    SBOD_CUDA_TRY(cudaLaunchKernelEx(&cfg, classify_kernel, q));
+    cfg.gridDim = dim3(unsigned(q.N), 1, 1);
+    cfg.blockDim = dim3(kMineThreads, 1, 1);
+    cfg.dynamicSmemBytes = 0;
+    SBOD_CUDA_TRY(cudaLaunchKernelEx(&cfg, mine_kernel, q, cm_slices(q.P)));
   }
   return SBOD_OK;
 }
@@ -2089,7 +1961,7 @@ extern "C" int sbod_loss_forward(const sbod_loss_desc* d, sbod_stream_t stream) 
 }
 
 // Profiling / bench hook: launch ONE stage of sbod_loss_forward: 0 = the match + log-sum-exp kernel,
-// 1 = classify_mine_kernel (forced-match override + classification + mining + reduction) [+ mine_batch_kernel]. Stage 0 may be
+// 1 = classify_kernel / mine_kernel (forced-match override + classification + mining + reduction). Stage 0 may be
 // repeated; stage 1 must follow before the workspace is used by a full forward again.
 extern "C" int sbod_loss_forward_stage(const sbod_loss_desc* d, int stage, sbod_stream_t stream) {
   LossParams q;
@@ -2100,6 +1972,18 @@ extern "C" int sbod_loss_forward_stage(const sbod_loss_desc* d, int stage, sbod_
   if (stage == 1) return launch_mine(q, st);
   return SBOD_ERR_INVALID;
 }
+
+#ifdef SBOD_DEBUG_HOOKS
+extern "C" __attribute__((visibility("default"))) int sbod_debug_cm_times(unsigned long long* out, int reset) {
+  if (out) cudaMemcpyFromSymbol(out, g_cm_times, sizeof(g_cm_times));
+  if (reset) {
+    unsigned long long init[8 + 4 * 64];
+    for (int i = 0; i < 8 + 4 * 64; ++i) init[i] = (i < 2) ? ~0ull : 0ull;
+    cudaMemcpyToSymbol(g_cm_times, init, sizeof(init));
+  }
+  return 0;
+}
+#endif
 
 extern "C" int sbod_loss_finalize(const sbod_loss_desc* d, sbod_stream_t stream) {
   LossParams q;

@@ -54,5 +54,7 @@ for b in sel:
         tot += n
         lines.append((n, num(r[si]), b["file"].split("/")[-1], r[0], r[1].strip()[:110]))
 print(sel[0]["func"] if sel else "?", "total warp instructions", tot)
-for n, s, f, ln, src in sorted(lines, reverse=True)[:top]:
+by_samples = len(sys.argv) > 4 and sys.argv[4] == "smp"
+print("total samples", sum(l[1] for l in lines))
+for n, s, f, ln, src in sorted(lines, key=(lambda l: -l[1]) if by_samples else (lambda l: -l[0]))[:top]:
     print(f"{n:>10} {100.0 * n / max(tot, 1):5.1f}% smp {s:>6}  {f}:{ln}  {src}")
