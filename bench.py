@@ -16,8 +16,13 @@ inputs resident in HBM; e2e = the same through the public Python API with pinned
 input and D2H of the results inside the timed region, copies on a copy stream overlapping the compute).
 Multi-GPU: one process per GPU (torchrun), batch sharded by image, the only exchange is the loss sums
 (four doubles per criterion; "weak" scaling); config 1's batch-global mining does not shard: replicas only.
-The resident step is replayed as one CUDA graph (--no-graph: eager launches) with the train half and the eval
-half on two streams inside it (--no-overlap: one stream).
+The resident steps are replayed as CUDA graphs (--no-graph: eager launches) with the train halves and the eval
+halves on two streams (--no-overlap: one stream). The two halves of a step work on independent batches, so the
+streams are joined once per captured graph of U steps (U = 10 by default), not once per step: the eval half of
+step i runs under the train half of step i+1 and the one-CTA-per-image tails of either half hide under the other
+half's streaming kernels. The timed region still brackets EXACTLY K steps with a full synchronisation on both
+sides; details.ms_per_step_joined is the same measurement with a join after every step (--join-every-step makes
+it the headline).
 
 --impl reference times the reference's own CPU implementation on the host cores (oracle/_ref when the build
 placed it there, else the oracle port), on a bounded sample of the same workload.
@@ -414,18 +419,31 @@ def run_ours(args, rank, world, local_rank):
     s_eval = torch.cuda.Stream(device=dev)
     s_copy = torch.cuda.Stream(device=dev)
 
-    def step_resident():
+    def steps_resident(u=1):
+        """u steps: the train halves on the current stream, the eval halves on the eval stream, one join."""
         cur = torch.cuda.current_stream()
+        out = None
         if args.overlap:
             s_eval.wait_stream(cur)
             with torch.cuda.stream(s_eval):
-                out = W.eval_half()
-            W.train_half()
+                for _ in range(u):
+                    out = W.eval_half()
+            for _ in range(u):
+                W.train_half()
             cur.wait_stream(s_eval)
         else:
-            W.train_half()
-            out = W.eval_half()
+            for _ in range(u):
+                W.train_half()
+                out = W.eval_half()
         return out
+
+    def step_resident():
+        return steps_resident(1)
+
+    # steps per captured graph (one stream join per graph); K must be a whole number of graphs
+    unit = 1
+    if not args.join_every_step:
+        unit = next(u for u in (10, 8, 6, 5, 4, 3, 2, 1) if args.steps % u == 0)
 
     def step_e2e():
         """Pinned host buffers in, results out. The copies run on a copy stream: the eval batch's H2D overlaps
@@ -458,33 +476,59 @@ def run_ours(args, rank, world, local_rank):
 
     for _ in range(max(args.warmup, 3)):
         step_resident()
-    graph = g = None
+    graph = g = g1 = None
     eager_step = step_resident
-    replay = step_resident
+    replay = lambda: steps_resident(unit)  # noqa: E731
+    replay1 = step_resident
     if args.graph:
         try:
             torch.cuda.synchronize()
-            g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):
+            g1 = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g1):
                 step_resident()
-            g.replay()
+            g1.replay()
+            g = g1
+            if unit > 1:
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    steps_resident(unit)
+                g.replay()
             torch.cuda.synchronize()
             graph = g
-            replay = g.replay
+            replay, replay1 = g.replay, g1.replay
         except Exception as exc:  # capture is an optimisation, never a requirement
             print(f"bench.py: CUDA graph capture failed ({type(exc).__name__}: {exc}); running eagerly",
                   file=sys.stderr)
-            replay = eager_step
             torch.cuda.synchronize()
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    ms_step = timed(replay, args.steps, sync)
+    ms_step = timed(replay, args.steps // unit, sync) / unit
     clocks = sampler.stop() if rank == 0 else None
+    ms_step_joined = timed(replay1, args.steps, sync) if unit > 1 else ms_step
 
     # ---- halves and single kernels alone (CUDA events on the launching stream) ----
-    ms_train = timed(lambda: W.train_half(), args.steps, sync)
-    ms_eval = timed(lambda: W.eval_half(), args.steps, sync)
+    def graphed(fn):
+        """fn captured in a CUDA graph of its own (device time without Python launch gaps); eager if that fails"""
+        if not args.graph:
+            return fn, None
+        try:
+            fn()
+            torch.cuda.synchronize()
+            gg = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(gg):
+                fn()
+            gg.replay()
+            torch.cuda.synchronize()
+            return gg.replay, gg
+        except Exception:
+            torch.cuda.synchronize()
+            return fn, None
+
+    run_train, g_train = graphed(lambda: W.train_half())
+    run_eval, g_eval = graphed(lambda: W.eval_half())
+    ms_train = timed(run_train, args.steps, sync)
+    ms_eval = timed(run_eval, args.steps, sync)
     kernels = {}  # name -> (ms per launch, algorithmic bytes per launch, note)
     Cn = cf["C"]
     dstage = L.lib().sbod_detect_stage
@@ -571,13 +615,13 @@ def run_ours(args, rank, world, local_rank):
     ms_h2d = timed(copy_only, e2e_steps, sync)
     h2d_gbs = sum(t.numel() * t.element_size() for t in W.h_train + W.h_eval) / (ms_h2d * 1e-3) / 1e9
 
-    vals = [ms_step, ms_e2e, ms_train, ms_eval, ms_h2d] + [k["ms"] for k in kernels.values()]
+    vals = [ms_step, ms_e2e, ms_train, ms_eval, ms_h2d, ms_step_joined] + [k["ms"] for k in kernels.values()]
     t = torch.tensor(vals, dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     vals = t.tolist()
-    ms_step, ms_e2e, ms_train, ms_eval, ms_h2d_max = vals[:5]
-    for k, v in zip(kernels.values(), vals[5:]):
+    ms_step, ms_e2e, ms_train, ms_eval, ms_h2d_max, ms_step_joined = vals[:6]
+    for k, v in zip(kernels.values(), vals[6:]):
         k["ms"] = v
     h2d_all = [None] * world
     if world > 1:
@@ -611,8 +655,11 @@ def run_ours(args, rank, world, local_rank):
             "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": config_entry(cid),
-            "details": {"streams": "train and eval halves of the step on two CUDA streams" if args.overlap else "one stream",
-                        "launch": "CUDA graph replay" if graph is not None else "eager Python launches",
+            "details": {"streams": ("train halves and eval halves on two CUDA streams, joined once per %d step(s)" % unit)
+                        if args.overlap else "one stream",
+                        "launch": ("CUDA graph replay, %d step(s) per graph" % unit) if graph is not None
+                        else "eager Python launches",
+                        "ms_per_step_joined": ms_step_joined,
                         "sharding": "batch sharded by image, one all-reduce of the loss sums per criterion" if cf["shards"]
                         else "independent replicas (batch-global mining does not shard)",
                         "ms_train_half": ms_train, "ms_eval_half": ms_eval, "ms_loss_fwd": ms_fwd,
@@ -639,7 +686,7 @@ def run_ours(args, rank, world, local_rank):
                                         "bound, the HBM fraction is reported for completeness")
         print(json.dumps(line), flush=True)
     if world > 1:
-        graph = g = None  # the captured step holds NCCL kernel nodes: release it before the communicator goes away
+        graph = g = g1 = g_train = g_eval = run_train = run_eval = None  # the captured steps hold NCCL kernel nodes: release it before the communicator goes away
         replay = eager_step
         torch.cuda.synchronize()
         dist.barrier()
@@ -656,6 +703,8 @@ def main():
                     help="BASELINE.json config (1 SSD300, 2 SSD512 [default], 3 RetinaNet-640, 4 RefineDet512, 5 FCOS)")
     ap.add_argument("--no-graph", dest="graph", action="store_false",
                     help="launch the resident step eagerly instead of replaying a captured CUDA graph")
+    ap.add_argument("--join-every-step", action="store_true",
+                    help="join the train and eval streams after every step instead of once per captured graph of steps")
     ap.add_argument("--no-overlap", dest="overlap", action="store_false",
                     help="run the train half and the eval half of a step one after the other on one stream")
     args = ap.parse_args()

@@ -272,53 +272,6 @@ __global__ void __launch_bounds__(256) detect_bound_generic_kernel(const DetPara
   }
 }
 
-// Per-image cutoff from the histogram of the row bounds: the smallest bin count `cb` such that at least
-// rows_target rows have their bound in bins [0, cb) — only those rows are evaluated in the first band, and
-// only candidates with a key below the cutoff are emitted. Block-wide (any multiple of 32 threads); every
-// thread returns the same value (0xffffffff = no cutoff: everything above min_score). scratch: >= 34 uints.
-// Starts with a barrier (the caller's copy of the histogram into shared memory is complete after it).
-__device__ unsigned int compute_cutoff(const DetParams& q, const unsigned int* sh /* histogram of the bounds (shared memory) */,
-                                       unsigned int* scratch) {
-  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, nt = blockDim.x;
-  __syncthreads();
-  const int per = (q.n_bins + nt - 1) / nt;  // contiguous bins per thread, best scores first
-  unsigned int mine = 0;
-  for (int j = 0; j < per; ++j) {
-    const int b = tid * per + j;
-    if (b < q.n_bins) mine += sh[b];
-  }
-  unsigned int inc = mine;
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    const unsigned int t = __shfl_up_sync(0xffffffffu, inc, o);
-    if (lane >= o) inc += t;
-  }
-  __syncthreads();
-  if (tid == 0) scratch[33] = unsigned(q.n_bins);
-  if (lane == 31) scratch[wid] = inc;
-  __syncthreads();
-  unsigned int before = inc - mine;
-  for (int w = 0; w < wid; ++w) before += scratch[w];
-  const unsigned int need = unsigned(q.rows_target);
-  if (before < need && before + mine >= need) {
-    unsigned int acc = before;
-    for (int j = 0; j < per; ++j) {
-      const int b = tid * per + j;
-      if (b >= q.n_bins) break;
-      acc += sh[b];
-      if (acc >= need) {
-        scratch[33] = unsigned(b + 1);  // bins [0, b]
-        break;
-      }
-    }
-  }
-  __syncthreads();
-  const int cb = int(scratch[33]);
-  __syncthreads();
-  if (cb >= q.n_bins) return 0xffffffffu;
-  return unsigned(cb) << (q.shift0 - 32);
-}
-
 // ------------------------------------------------------------------------------------------
 // Exact evaluation of prior rows, FOUR rows per warp: an octet (8 lanes) owns a row, lane s of the octet
 // handles classes s, s + 8, ... (one 32-byte sector per row and step). A whole warp per row cost ~500 warp
@@ -341,51 +294,77 @@ SBOD_DEVINL float octet_sum(float v) {
   return v + __shfl_xor_sync(0xffffffffu, v, 4);
 }
 
-template <typename Emit>
-SBOD_DEVINL void eval_rows(const DetParams& q, int n, int p, int lane, uint32_t k_lo, uint32_t k_hi, Emit&& emit) {
-  const int C = q.C;
+constexpr int kRowRegs = 16;  // logits per lane of an octet kept in registers: rows of up to 128 classes
+constexpr int kRowQueue = 64;  // per-warp queue of (row, class) pairs waiting for their exact evaluation
+
+// exp(x - mx) of the softmax denominator: the accurate expf, as torch evaluates it - with ex2.approx (2e-7
+// relative) one more image in 32 of the config-2 batch swaps two near-tied candidates against the CPU reference.
+// detect_probabilities_kernel uses the same function.
+SBOD_DEVINL float exp_term(float x, float mx) { return expf(x - mx); }
+
+// kC > 0: compile-time class count (immediate offsets, no bounds tests). kRegs: the row lives in registers.
+// wq: this warp's queue in shared memory (kRowQueue entries) or null. With a queue the classes that pass the
+// threshold test are first collected and then evaluated exactly by consecutive lanes, so the expensive part
+// (accurate exp, division, key, emit) runs once per ~32 classes instead of divergently.
+template <int kC, bool kRegs, typename Emit>
+SBOD_DEVINL void eval_rows_impl(const DetParams& q, int n, int p, int lane, uint32_t k_lo, uint32_t k_hi, Emit&& emit,
+                                uint2* wq) {
+  const int C = kC ? kC : q.C;
   const int s = lane & 7;
   const bool on = p >= 0;
-  const float* x = q.scores + (size_t(n) * q.P + (on ? p : 0)) * size_t(C);
+  const float* x = q.scores + (size_t(n) * q.P + (on ? p : 0)) * size_t(C) + s;
   const float NEG = -__int_as_float(0x7f800000);
+  constexpr int kNj = kC ? (kC + 7) / 8 : kRowRegs;
+  const int nj = kRegs ? kNj : (C + 7) / 8;
+  // class s + 8 j exists for this lane? (compile-time for all but the last step when kC is known)
+  auto has = [&](int j) -> bool { return kC ? (8 * j + 7 < kC || s < kC - 8 * j) : (s + 8 * j < C); };
+  // the lane's logits x[s], x[s + 8], ...: every load of the row in flight at once (kRegs), or re-read from
+  // memory in each of the three passes (rows of more than 128 classes)
+  float xv[kRegs ? kNj : 1];
+  if (kRegs) {
+#pragma unroll
+    for (int j = 0; j < kNj; ++j) xv[j] = (on && has(j)) ? __ldg(x + 8 * j) : NEG;
+  }
+  auto at = [&](int j) -> float { return kRegs ? xv[kRegs ? j : 0] : ((on && has(j)) ? __ldg(x + 8 * j) : NEG); };
   float mx = 0.f, sum = 1.f;
   if (q.act_kind == SBOD_ACT_SOFTMAX) {
     float m = NEG;
-    if (on)
-      for (int k = s; k < C; k += 8) m = fmaxf(m, __ldg(x + k));
+#pragma unroll
+    for (int j = 0; j < nj; ++j) m = fmaxf(m, at(j));
     mx = octet_max(m);
     float acc = 0.f;
-    if (on)
-      for (int k = s; k < C; k += 8) acc += expf(__ldg(x + k) - mx);
+#pragma unroll
+    for (int j = 0; j < nj; ++j)
+      if (on && has(j)) acc += exp_term(at(j), mx);
     sum = octet_sum(acc);
   }
-  // lowest probability that can still be emitted (with a margin for the estimate below)
+  // lowest probability that can still be emitted, with a margin, as a threshold on the logit
   const float floor_p = fmaxf(q.min_score, k_hi > kOneBits ? 0.f : __uint_as_float(kOneBits - k_hi)) * 0.999f;
-  const float inv_est = q.act_kind == SBOD_ACT_SOFTMAX ? __frcp_rn(sum) : 1.f;
-  auto prob = [&](float v) -> float {
-    if (q.act_kind == SBOD_ACT_SOFTMAX) return __fdiv_rn(expf(v - mx), sum);
+  float thr_logit;
+  if (q.act_kind == SBOD_ACT_SOFTMAX) thr_logit = mx + __logf(floor_p * sum) - 1e-3f;
+  else if (q.act_kind == SBOD_ACT_SIGMOID) thr_logit = floor_p < 1.f ? __logf(floor_p / (1.f - floor_p)) - 1e-3f : -NEG;
+  else thr_logit = floor_p;
+  if (!(thr_logit == thr_logit)) thr_logit = NEG;  // (NaN sums: evaluate everything)
+  auto prob = [&](float v, float mx_, float sum_) -> float {
+    if (q.act_kind == SBOD_ACT_SOFTMAX) return __fdiv_rn(expf(v - mx_), sum_);
     if (q.act_kind == SBOD_ACT_SIGMOID) return __fdiv_rn(1.f, 1.f + expf(-v));
-    return v;
-  };
-  auto estimate = [&](float v) -> float {  // within 1e-5 relative of prob()
-    if (q.act_kind == SBOD_ACT_SOFTMAX) return __expf(v - mx) * inv_est;
-    if (q.act_kind == SBOD_ACT_SIGMOID) return __frcp_rn(1.f + __expf(-v));
     return v;
   };
   if (q.agnostic) {
     // best foreground class of the row, first index among ties (torch.max, models/utils.py:135)
     unsigned long long best = 0ull;  // (probability bits : ~class): max = best probability, then lowest class
-    if (on)
-      for (int k = s; k < C; k += 8) {
-        if (k == 0) continue;
-        const float v = __ldg(x + k);
-        if (!(estimate(v) > floor_p)) continue;
-        const float pr = prob(v);
-        if (pr > q.min_score) {
-          const unsigned long long key = (static_cast<unsigned long long>(__float_as_uint(pr)) << 32) | (0xffffffffu - unsigned(k));
-          if (key > best) best = key;
-        }
+#pragma unroll
+    for (int j = 0; j < nj; ++j) {
+      const int k = s + 8 * j;
+      if (!on || k == 0 || !has(j)) continue;
+      const float v = at(j);
+      if (!(v > thr_logit)) continue;
+      const float pr = prob(v, mx, sum);
+      if (pr > q.min_score) {
+        const unsigned long long key = (static_cast<unsigned long long>(__float_as_uint(pr)) << 32) | (0xffffffffu - unsigned(k));
+        if (key > best) best = key;
       }
+    }
 #pragma unroll
     for (int o = 1; o < 8; o <<= 1) {
       const unsigned long long other = __shfl_xor_sync(0xffffffffu, best, o);
@@ -402,17 +381,68 @@ SBOD_DEVINL void eval_rows(const DetParams& q, int n, int p, int lane, uint32_t 
     }
     return;
   }
-  if (on)
-    for (int k = s; k < C; k += 8) {
-      if (k == 0) continue;
-      const float v = __ldg(x + k);
-      if (!(estimate(v) > floor_p)) continue;
-      const float pr = prob(v);
-      const uint32_t k32 = score_k32(pr);
-      if (pr > q.min_score && k32 >= k_lo && k32 < k_hi)
-        emit((static_cast<unsigned long long>(k32) << 32) | (static_cast<unsigned long long>(k) << kPriorBits) |
-             static_cast<unsigned long long>(p));
+  auto finish = [&](float v, int k, int pp, float mx_, float sum_) {
+    const float pr = prob(v, mx_, sum_);
+    const uint32_t k32 = score_k32(pr);
+    if (pr > q.min_score && k32 >= k_lo && k32 < k_hi)
+      emit((static_cast<unsigned long long>(k32) << 32) | (static_cast<unsigned long long>(k) << kPriorBits) |
+           static_cast<unsigned long long>(pp));
+  };
+  if (kRegs && wq) {
+    // which of the lane's classes pass (bit j = class s + 8 j), and where they go in the warp's queue
+    unsigned pm = 0;
+#pragma unroll
+    for (int j = 0; j < kNj; ++j) {
+      const bool pass = on && (j > 0 || s != 0) && has(j) && xv[kRegs ? j : 0] > thr_logit;
+      pm |= pass ? (1u << j) : 0u;
     }
+    const int c = __popc(pm);
+    int inc = c;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, inc, o);
+      if (lane >= o) inc += t;
+    }
+    const int total = __shfl_sync(0xffffffffu, inc, 31);
+    if (total == 0) return;        // (warp-uniform)
+    if (total <= kRowQueue) {
+      int pos = inc - c;
+#pragma unroll
+      for (int j = 0; j < kNj; ++j)
+        if (pm & (1u << j))
+          wq[pos++] = make_uint2(__float_as_uint(xv[kRegs ? j : 0]), unsigned(s + 8 * j) | (unsigned(lane >> 3) << 16));
+      __syncwarp();
+      for (int base = 0; base < total; base += 32) {
+        const int e = base + lane;
+        const uint2 ent = e < total ? wq[e] : make_uint2(0u, 0u);
+        const int src = int(ent.y >> 16) * 8;  // the octet that owns the row
+        const float mx_ = __shfl_sync(0xffffffffu, mx, src), sum_ = __shfl_sync(0xffffffffu, sum, src);
+        const int pp = __shfl_sync(0xffffffffu, p, src);
+        if (e < total) finish(__uint_as_float(ent.x), int(ent.y & 0xffffu), pp, mx_, sum_);
+      }
+      __syncwarp();
+      return;
+    }
+    // more passing classes than the queue holds (rows of many near-equal scores): in place
+#pragma unroll
+    for (int j = 0; j < kNj; ++j)
+      if (pm & (1u << j)) finish(xv[kRegs ? j : 0], s + 8 * j, p, mx, sum);
+    return;
+  }
+#pragma unroll
+  for (int j = 0; j < nj; ++j) {
+    const int k = s + 8 * j;
+    if (!on || k == 0 || !has(j)) continue;
+    const float v = at(j);
+    if (v > thr_logit) finish(v, k, p, mx, sum);
+  }
+}
+
+template <int kC, typename Emit>
+SBOD_DEVINL void eval_rows(const DetParams& q, int n, int p, int lane, uint32_t k_lo, uint32_t k_hi, Emit&& emit,
+                           uint2* wq = nullptr) {
+  if (kC || q.C <= 8 * kRowRegs) eval_rows_impl<kC, true>(q, n, p, lane, k_lo, k_hi, emit, wq);
+  else eval_rows_impl<0, false>(q, n, p, lane, k_lo, k_hi, emit, wq);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -424,44 +454,105 @@ SBOD_DEVINL void eval_rows(const DetParams& q, int n, int p, int lane, uint32_t 
 // atomic per warp and row, one global atomic per CTA. The histogram of the keys' leading digit is
 // accumulated in shared memory and flushed once.
 // ------------------------------------------------------------------------------------------
+#ifdef SBOD_DEBUG_HOOKS  // phase time stamps (profiling builds only)
+__device__ unsigned long long g_det_times[16];
+SBOD_DEVINL unsigned long long det_now() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+#define DET_STAMP_MIN(i) do { if (threadIdx.x == 0) atomicMin(&g_det_times[i], det_now()); } while (0)
+#define DET_STAMP_MAX(i) do { if (threadIdx.x == 0) atomicMax(&g_det_times[i], det_now()); } while (0)
+#else
+#define DET_STAMP_MIN(i)
+#define DET_STAMP_MAX(i)
+#endif
+
 constexpr int kRefThreads = 512;
 constexpr int kRefMaxRows = 2048;  // prior rows per CTA (host picks 512 .. 2048 so that the grid is a few waves)
 constexpr int kRefKeyBuf = kMaxBins / 2;  // keys buffered per CTA (shares its storage with the histogram copy)
 
-__global__ void __launch_bounds__(kRefThreads) detect_refine_kernel(const DetParams q, int rows_per_cta) {
-  __shared__ unsigned int s_scratch[40];
-  __shared__ __align__(16) unsigned long long s_keys[kRefKeyBuf];  // first: the image's bound histogram (kMaxBins uints)
+template <int kC>  // kC > 0: compile-time class count
+__global__ void __launch_bounds__(kRefThreads, 3) detect_refine_kernel(const DetParams q, int rows_per_cta) {
+  __shared__ __align__(16) unsigned long long s_keys[kRefKeyBuf];
   __shared__ int s_rows[kRefMaxRows];
   __shared__ unsigned int s_nrows, s_ncand, s_gbase;
+  __shared__ uint2 s_wq[kRefThreads / 32][kRowQueue];
   const int n = blockIdx.y, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-  const int p_lo = blockIdx.x * rows_per_cta, p_hi = min(q.P, p_lo + rows_per_cta);
-  {
-    unsigned int* s_rh = reinterpret_cast<unsigned int*>(s_keys);
-    const unsigned int* rh = q.rhist + size_t(n) * kMaxBins;
-    for (int b = tid; b < q.n_bins; b += kRefThreads) s_rh[b] = rh[b];  // coalesced, L2
+  // The CTAs of an image share its rows in interleaved blocks of 32 (block i belongs to CTA i mod gridDim.x):
+  // rows with a high bound cluster (neighbouring priors look at the same object), contiguous slices would give a
+  // few CTAs most of the work. The bounds of this CTA's rows are requested before anything else.
+  constexpr int kRefIters = kRefMaxRows / kRefThreads;
+  float pbv[kRefIters];
+#pragma unroll
+  for (int it = 0; it < kRefIters; ++it) {
+    const int p = ((it * (kRefThreads / 32) + wid) * int(gridDim.x) + int(blockIdx.x)) * 32 + lane;
+    pbv[it] = (it * kRefThreads < rows_per_cta && p < q.P) ? __ldcg(q.pbound + size_t(n) * q.P + p) : -1.f;
   }
+  DET_STAMP_MIN(0);
+  DET_STAMP_MAX(1);
+  // The image's cutoff from the histogram of the row bounds (every CTA of the image computes the same value):
+  // the smallest bin count cb such that at least rows_target rows have their bound in bins [0, cb). Four bins
+  // per thread straight from L2 (rows of the histogram are kMaxBins long, unused bins stay zero).
+  __shared__ unsigned int s_wt[kRefThreads / 32], s_cb;
+  static_assert(kRefThreads * 4 == kMaxBins, "four bins per thread");
+  const uint4 hc = __ldcg(reinterpret_cast<const uint4*>(q.rhist + size_t(n) * kMaxBins) + tid);
   if (tid == 0) {
     s_nrows = 0u;
     s_ncand = 0u;
+    s_cb = unsigned(q.n_bins);
   }
-  const unsigned int cut = compute_cutoff(q, reinterpret_cast<unsigned int*>(s_keys), s_scratch);
-  if (blockIdx.x == 0 && tid == 0) q.cutoff[n] = cut;  // the NMS kernel reads it instead of recomputing it
-  // rows of this CTA whose bound is above the cutoff
-  for (int pb = p_lo; pb < p_hi; pb += kRefThreads) {
-    const int p = pb + tid;
-    bool take = false;
-    if (p < p_hi) {
-      const float b = q.pbound[size_t(n) * q.P + p];
-      take = b > q.min_score && score_k32(b) < cut;
+  unsigned int cut;
+  {
+    const unsigned int mine = hc.x + hc.y + hc.z + hc.w;
+    unsigned int inc = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const unsigned int t = __shfl_up_sync(0xffffffffu, inc, o);
+      if (lane >= o) inc += t;
     }
+    if (lane == 31) s_wt[wid] = inc;
+    __syncthreads();
+    unsigned int before = inc - mine;
+#pragma unroll
+    for (int w = 0; w < kRefThreads / 32; ++w)
+      if (w < wid) before += s_wt[w];
+    const unsigned int need = unsigned(q.rows_target);
+    if (before < need && before + mine >= need) {
+      const unsigned int c4[4] = {hc.x, hc.y, hc.z, hc.w};
+      unsigned int acc = before;
+      bool found = false;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        acc += c4[j];
+        if (!found && acc >= need) {
+          s_cb = unsigned(4 * tid + j + 1);  // bins [0, 4 tid + j]
+          found = true;
+        }
+      }
+    }
+    __syncthreads();
+    const int cb = int(s_cb);
+    cut = cb >= q.n_bins ? 0xffffffffu : unsigned(cb) << (q.shift0 - 32);
+  }
+  if (blockIdx.x == 0 && tid == 0) q.cutoff[n] = cut;  // the NMS kernel reads it instead of recomputing it
+  DET_STAMP_MAX(2);
+  // rows of this CTA whose bound is above the cutoff
+#pragma unroll
+  for (int it = 0; it < kRefIters; ++it) {
+    if (it * kRefThreads >= rows_per_cta) break;  // (CTA-uniform)
+    const int p = ((it * (kRefThreads / 32) + wid) * int(gridDim.x) + int(blockIdx.x)) * 32 + lane;
+    const float b = pbv[it];
+    const bool take = b > q.min_score && score_k32(b) < cut;  // (rows past the end carry -1)
     const unsigned bal = __ballot_sync(0xffffffffu, take);
     unsigned int base = 0;
     if (lane == 0 && bal) base = atomicAdd(&s_nrows, unsigned(__popc(bal)));
     base = __shfl_sync(0xffffffffu, base, 0);
     if (take) s_rows[base + __popc(bal & ((1u << lane) - 1u))] = p;
   }
-  __syncthreads();  // (also: everybody is done with the histogram copy that shares s_keys)
+  __syncthreads();
   const int n_rows = int(s_nrows);
+  DET_STAMP_MAX(3);
   unsigned long long* g_list = q.cand + size_t(n) * q.cand_cap;
   unsigned int* g_hist = q.hist + size_t(n) * kMaxBins;
   auto emit = [&](unsigned long long key) {
@@ -477,9 +568,10 @@ __global__ void __launch_bounds__(kRefThreads) detect_refine_kernel(const DetPar
   // four rows per warp (an octet each)
   for (int i = wid * 4; i < n_rows; i += (kRefThreads / 32) * 4) {
     const int r = i + (lane >> 3);
-    eval_rows(q, n, r < n_rows ? s_rows[r] : -1, lane, 0u, cut, emit);
+    eval_rows<kC>(q, n, r < n_rows ? s_rows[r] : -1, lane, 0u, cut, emit, s_wq[wid]);
   }
   __syncthreads();
+  DET_STAMP_MAX(4);
   // hand the buffered keys over: one global atomic for the CTA's keys
   const unsigned int have = min(s_ncand, unsigned(kRefKeyBuf));
   if (have) {  // (CTA-uniform)
@@ -490,6 +582,7 @@ __global__ void __launch_bounds__(kRefThreads) detect_refine_kernel(const DetPar
       if (slot < q.cand_cap) g_list[slot] = s_keys[i];
     }
   }
+  DET_STAMP_MAX(5);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -550,6 +643,7 @@ __global__ void __launch_bounds__(kNmsThreads) detect_nms_kernel(const DetParams
   unsigned int* cls_off = reinterpret_cast<unsigned int*>(dyn + size_t(q.kcap) * 25 + 128 - (size_t(q.kcap) * 25) % 128);  // [C+1]
 
   const int n = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  DET_STAMP_MIN(8);
   // same function of the same histogram as detect_refine_kernel: candidates below `cut` are complete
   {
     unsigned int* rh = q.rhist + size_t(n) * kMaxBins;
@@ -656,6 +750,7 @@ __global__ void __launch_bounds__(kNmsThreads) detect_nms_kernel(const DetParams
       have_hi = true;
     }
 
+    DET_STAMP_MAX(9);
     // ---- gather the chunk -----------------------------------------------------------------
     if (tid == 0) S.misc[3] = 0;
     __syncthreads();
@@ -690,6 +785,7 @@ __global__ void __launch_bounds__(kNmsThreads) detect_nms_kernel(const DetParams
       __syncthreads();
       continue;
     }
+    DET_STAMP_MAX(10);
     // ---- sort by key (bitonic, padded with ~0) ----------------------------------------------
     // Each thread keeps its element in a register; partners less than 32 apart are reached by
     // shuffles (40 of the 55 steps, no block barrier), the others through shared memory, alternating
@@ -726,6 +822,7 @@ __global__ void __launch_bounds__(kNmsThreads) detect_nms_kernel(const DetParams
       S.ckey[tid] = v;
       __syncthreads();
     }
+    DET_STAMP_MAX(11);
     // ---- decode boxes, group by class -------------------------------------------------------
     for (int c = tid; c <= q.C; c += kNmsThreads) cls_off[c] = 0u;
     if (tid == 0) {
@@ -780,6 +877,7 @@ __global__ void __launch_bounds__(kNmsThreads) detect_nms_kernel(const DetParams
       // (visible to the class warps after the barrier that ends stage 1a)
     }
 
+    DET_STAMP_MAX(12);
     // ---- stage 1a: every candidate against the boxes kept in EARLIER rounds, one thread each ----
     // (parallel over the whole CTA whatever the number of classes; flag 3 = already suppressed).
     // With few classes the kept list is first grouped by class (counting sort in shared memory), so a
@@ -829,6 +927,7 @@ __global__ void __launch_bounds__(kNmsThreads) detect_nms_kernel(const DetParams
       if (sup) S.cflag[tid] = 3;
     }
     __syncthreads();
+    DET_STAMP_MAX(13);
     // ---- stage 1b: greedy suppression inside the chunk -------------------------------------------
     // Small class segments (<= kBigSeg candidates): one warp per class walks its segment and tests
     // each candidate against the boxes it kept so far (warp ballot).
@@ -991,6 +1090,7 @@ __global__ void __launch_bounds__(kNmsThreads) detect_nms_kernel(const DetParams
       __syncthreads();
     }
 
+    DET_STAMP_MAX(14);
     // ---- append the survivors to the kept list, in key order ---------------------------------
     const bool keep_me = tid < m && (S.cflag[tid] == 1 || S.cflag[tid] == 2);
     const unsigned bal = __ballot_sync(0xffffffffu, keep_me);
@@ -1045,7 +1145,7 @@ __global__ void __launch_bounds__(kNmsThreads) detect_nms_kernel(const DetParams
       for (int p0 = wid * 4; p0 < q.P; p0 += (kNmsThreads / 32) * 4) {  // four rows per warp (an octet each)
         const int p = p0 + (lane >> 3);
         const bool take = p < q.P && q.pbound[size_t(n) * q.P + p] > q.min_score;
-        eval_rows(q, n, take ? p : -1, lane, cut, 0xffffffffu, emit);
+        eval_rows<0>(q, n, take ? p : -1, lane, cut, 0xffffffffu, emit);
       }
       __threadfence();
       __syncthreads();
@@ -1067,6 +1167,7 @@ __global__ void __launch_bounds__(kNmsThreads) detect_nms_kernel(const DetParams
   for (int c = tid; c < q.C; c += kNmsThreads) g_seen[c] = 0u;
   if (tid == 0) q.cand_count[n] = 0u;
 
+  DET_STAMP_MAX(15);
   // ---- emit --------------------------------------------------------------------------------
   float4* ob = reinterpret_cast<float4*>(q.out_boxes) + size_t(n) * q.out_cap;
   int64_t* ol = q.out_labels + size_t(n) * q.out_cap;
@@ -1280,7 +1381,9 @@ static int detect_run(const sbod_detect_desc* d, sbod_stream_t stream, int stage
     SBOD_CUDA_TRY(cudaFuncSetAttribute(detect_bound_kernel<81>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     SBOD_CUDA_TRY(cudaFuncSetAttribute(detect_bound_kernel<21>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     SBOD_CUDA_TRY(cudaFuncSetAttribute(detect_bound_kernel<0>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-    SBOD_CUDA_TRY(cudaFuncSetAttribute(detect_refine_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    SBOD_CUDA_TRY(cudaFuncSetAttribute(detect_refine_kernel<81>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    SBOD_CUDA_TRY(cudaFuncSetAttribute(detect_refine_kernel<21>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    SBOD_CUDA_TRY(cudaFuncSetAttribute(detect_refine_kernel<0>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     attr_once.mark();
   }
   if (stage_mask & 1) {  // bound pass
@@ -1297,13 +1400,15 @@ static int detect_run(const sbod_detect_desc* d, sbod_stream_t stream, int stage
     SBOD_LAUNCH_CHECK();
   }
   if (stage_mask & 4) {  // exact evaluation of the rows above the cutoff
-    // rows per CTA: 512 .. 2048, so that the grid is about eight CTAs per SM (fixed per-CTA cost vs parallelism)
+    // rows per CTA: 512 .. 2048, so that the whole grid is resident (three CTAs per SM) whenever it can be
     int rows_per_cta = 512;
     while (rows_per_cta < kRefMaxRows &&
-           (long long)q.N * ((q.P + rows_per_cta - 1) / rows_per_cta) > (long long)sm_count() * 8)
+           (long long)q.N * ((q.P + rows_per_cta - 1) / rows_per_cta) > (long long)sm_count() * 3)
       rows_per_cta *= 2;
     dim3 grid((q.P + rows_per_cta - 1) / rows_per_cta, q.N);
-    detect_refine_kernel<<<grid, kRefThreads, 0, st>>>(q, rows_per_cta);
+    if (q.C == 81) detect_refine_kernel<81><<<grid, kRefThreads, 0, st>>>(q, rows_per_cta);
+    else if (q.C == 21) detect_refine_kernel<21><<<grid, kRefThreads, 0, st>>>(q, rows_per_cta);
+    else detect_refine_kernel<0><<<grid, kRefThreads, 0, st>>>(q, rows_per_cta);
     SBOD_LAUNCH_CHECK();
   }
   if (stage_mask & 2) {  // NMS (+ in-kernel second band for the images that need it)
@@ -1335,7 +1440,7 @@ __global__ void __launch_bounds__(256) detect_probabilities_kernel(const DetPara
       mx = octet_max(m);
       float acc = 0.f;
       if (on)
-        for (int k = s; k < q.C; k += 8) acc += expf(__ldg(x + k) - mx);
+        for (int k = s; k < q.C; k += 8) acc += exp_term(__ldg(x + k), mx);
       sum = octet_sum(acc);
     }
     if (on)
@@ -1362,6 +1467,18 @@ extern "C" int sbod_detect_probabilities(const float* scores, int N, int P, int 
   SBOD_LAUNCH_CHECK();
   return SBOD_OK;
 }
+
+#ifdef SBOD_DEBUG_HOOKS
+extern "C" __attribute__((visibility("default"))) int sbod_debug_det_times(unsigned long long* out, int reset) {
+  if (out) cudaMemcpyFromSymbol(out, g_det_times, sizeof(g_det_times));
+  if (reset) {
+    unsigned long long init[16];
+    for (int i = 0; i < 16; ++i) init[i] = (i == 0 || i == 8) ? ~0ull : 0ull;
+    cudaMemcpyToSymbol(g_det_times, init, sizeof(init));
+  }
+  return 0;
+}
+#endif
 
 extern "C" int sbod_detect(const sbod_detect_desc* d, sbod_stream_t stream) {
   return detect_run(d, stream, 7);
