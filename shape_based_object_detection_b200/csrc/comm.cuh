@@ -55,7 +55,7 @@ SBOD_DEVINL void comm_allreduce_sum(const CommDev* __restrict__ cp, double* vals
   if (lane < c.world) {  // lane r posts to rank r
     double* dst = c.peer_mailbox[lane] + slot_own;
     for (int i = 0; i < k; ++i) st_relaxed_sys_f64(dst + i, vals[i]);
-    __threadfence_system();
+    // (the release store orders this lane's payload stores before the flag: no separate system fence)
     st_release_sys_u64(reinterpret_cast<unsigned long long*>(dst + kCommSlotDoubles - 1), e);
   }
   __syncwarp();

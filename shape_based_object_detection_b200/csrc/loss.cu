@@ -876,7 +876,8 @@ SBOD_DEVINL int mine_excl_scan(int v, int* warp_tot, int* total) {
 // (nothing selected). sel (may be null): flag bytes of the values; only touched when some but not all values
 // equal to the threshold are selected (the first ones by index get bit 1). All kMineThreads threads call this.
 __device__ TopkSum select_topk_sum(MineShared& S, const float* __restrict__ vals, const long long n,
-                                   unsigned int* __restrict__ ghist, const long long k, uint8_t* __restrict__ sel) {
+                                   unsigned int* __restrict__ ghist, const long long k, uint8_t* __restrict__ sel,
+                                   const uint4* preloaded = nullptr /* this thread's four bins, already read */) {
   static_assert(kMineWarps == 32, "mine_excl_scan");
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   TopkSum r;
@@ -889,7 +890,7 @@ __device__ TopkSum select_topk_sum(MineShared& S, const float* __restrict__ vals
   unsigned int cnt[kPer];
   {
     uint4* gp = reinterpret_cast<uint4*>(ghist + (kBins - kPer * (tid + 1)));
-    const uint4 v = __ldcg(gp);
+    const uint4 v = preloaded ? *preloaded : __ldcg(gp);
     cnt[0] = v.w; cnt[1] = v.z; cnt[2] = v.y; cnt[3] = v.x;
     *gp = make_uint4(0u, 0u, 0u, 0u);  // clean for the next call
   }
@@ -1312,14 +1313,19 @@ __global__ void __launch_bounds__(kMineThreads, 1) mine_kernel(const LossParams 
   const int G = q.gt_offsets[n + 1] - q.gt_offsets[n];
   asm volatile("griddepcontrol.wait;" ::: "memory");
   CM_STAMP_SET(8 + 4 * (n & 63));
+  const bool select = !focal && q.cls_kind != SBOD_CLS_CE_MINE_BATCH;
+  // this thread's four histogram bins are requested before the partial sums (one round trip less in the chain)
+  uint4 hbins = make_uint4(0u, 0u, 0u, 0u);
+  if (select) hbins = __ldcg(reinterpret_cast<const uint4*>(q.sel_hist + size_t(n) * kBins + (kBins - 4 * (tid + 1))));
   // leave the per-object keys clean for the next call (every slice has read them)
   for (int g = tid; g < G; g += kMineThreads) q.gtkey[size_t(n) * q.gmax + g] = 0ull;
-  if (tid < 4) {
-    const double* bp = q.blockpart + size_t(n) * slices * 4 + tid;
+  if (tid < 128) {  // warp w adds component w of the slices' partials: lanes stride, then a fixed shuffle tree
+    const int comp = tid >> 5, l = tid & 31;
+    const double* bp = q.blockpart + size_t(n) * slices * 4 + comp;
     double acc = 0.0;
-#pragma unroll 8
-    for (int b = 0; b < slices; ++b) acc += __ldcg(bp + b * 4);  // slice order: deterministic
-    S.red4[tid] = acc;
+    for (int b = l; b < slices; b += 32) acc += __ldcg(bp + b * 4);
+    acc = warp_sum(acc);  // (deterministic: the same tree every run)
+    if (l == 0) S.red4[comp] = acc;
   }
   __syncthreads();
   const double img[4] = {S.red4[0], S.red4[1], S.red4[2], S.red4[3]};
@@ -1328,11 +1334,11 @@ __global__ void __launch_bounds__(kMineThreads, 1) mine_kernel(const LossParams 
   // what the backward needs to know about the image's mined negatives: a candidate row (flag bit 2) is mined
   // iff its CE > thr, or == thr when every tie is taken; +inf = none
   float sel_thr = __int_as_float(0x7f800000), sel_ties = 0.f;
-  if (!focal && q.cls_kind != SBOD_CLS_CE_MINE_BATCH) {
+  if (select) {
     const long long n_cand = (long long)(img[2] + 0.5);
     long long k = (long long)(q.ratio) * (long long)(img[3] + 0.5);
     if (k > n_cand) k = n_cand;
-    const TopkSum r = select_topk_sum(S, q.cand + base, q.P, q.sel_hist + size_t(n) * kBins, k, q.sel + base);
+    const TopkSum r = select_topk_sum(S, q.cand + base, q.P, q.sel_hist + size_t(n) * kBins, k, q.sel + base, &hbins);
     t_neg = r.sum;
     sel_thr = r.thr;
     sel_ties = r.ties;
@@ -1593,6 +1599,7 @@ __global__ void __launch_bounds__(256, 4) bwd_patch_kernel(const LossParams q, c
                                                         float* __restrict__ grad_scores) {
   const int lane = threadIdx.x & 31;
   const size_t total = size_t(q.N) * q.P;
+  asm volatile("griddepcontrol.wait;" ::: "memory");  // (programmatic dependent launch behind the forward)
   const double npos_tot = q.sums[3];
   const float gout = grad_loss ? *grad_loss : 1.f;
   const float conf_scale = float(double(gout) / npos_tot);
@@ -2035,8 +2042,17 @@ extern "C" int sbod_loss_backward(const sbod_loss_desc* d, const float* grad_los
     const size_t rows = size_t(q.N) * q.P;
     int pgrid = int((rows + 255) / 256);
     if (pgrid > sm_count() * 8) pgrid = sm_count() * 8;
-    bwd_patch_kernel<<<pgrid, 256, 0, st>>>(q, grad_loss, grad_locs, grad_scores);
-    SBOD_LAUNCH_CHECK();
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(unsigned(pgrid), 1, 1);
+    cfg.blockDim = dim3(256, 1, 1);
+    cfg.dynamicSmemBytes = 0;
+    cfg.stream = st;
+    cudaLaunchAttribute attrs[1];
+    attrs[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attrs[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attrs;
+    cfg.numAttrs = g_opt_pdl ? 1 : 0;
+    SBOD_CUDA_TRY(cudaLaunchKernelEx(&cfg, bwd_patch_kernel, q, grad_loss, grad_locs, grad_scores));
     return SBOD_OK;
   }
   loss_bwd_kernel<<<grid, kRows, smem, st>>>(bp);
