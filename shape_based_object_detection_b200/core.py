@@ -171,7 +171,7 @@ class _FusedLossFn(torch.autograd.Function):
 
 @L.on_device
 def fused_loss(spec, priors_cxcy, priors_xy, predicted_locs, predicted_scores, boxes, labels,
-               anchors_xy=None, exclude=None, group=None, holder=None, packed_gt=None):
+               anchors_xy=None, exclude=None, group=None, holder=None, packed_gt=None, lane=0):
     """Run the fused train path. Returns a 0-dim fp32 tensor with grad_fn.
     packed_gt: optional result of pack_ground_truth() (CSR ground truth already on the device, e.g.
     packed by the data loader) — then `boxes` / `labels` are ignored and no host work is done."""
@@ -200,7 +200,7 @@ def fused_loss(spec, priors_cxcy, priors_xy, predicted_locs, predicted_scores, b
     comm = None
     if group is not None:
         from .parallel import peer_exchange
-        comm = peer_exchange(group, dev)
+        comm = peer_exchange(group, dev, lane)
 
     def make_state(locs, scores):
         return LossState(spec, priors_cxcy, priors_xy, L.f32c(locs.detach()), L.f32c(scores.detach()), gt,

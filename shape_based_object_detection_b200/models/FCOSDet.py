@@ -105,7 +105,7 @@ class _FcosFn(torch.autograd.Function):
         comm = None
         if mod.process_group is not None:
             from ..parallel import peer_exchange
-            comm = peer_exchange(mod.process_group, dev)
+            comm = peer_exchange(mod.process_group, dev, getattr(mod, "exchange_lane", 0))
         d.comm = comm.ptr if comm is not None else None
         nbytes = L.lib().sbod_fcos_workspace_bytes(C.byref(d))
         ws = L.Workspace.get(dev, "fcos", nbytes, zero_bytes=0)

@@ -56,7 +56,7 @@ class RefineDetLoss(nn.Module):
         """Binary ARM loss against the static priors (RefineDet512.py:730-820)."""
         self.last_arm = {}
         return fused_loss(self._spec(True), self.priors_cxcy, self.priors_xy, arm_locs, arm_scores, boxes,
-                          labels, group=self.process_group, holder=self.last_arm)
+                          labels, group=self.process_group, lane=getattr(self, "exchange_lane", 0), holder=self.last_arm)
 
     def compute_odm_loss(self, arm_locs, arm_scores, odm_locs, odm_scores, boxes, labels):
         """ODM loss against the refined anchors (RefineDet512.py:822-939)."""
@@ -71,7 +71,7 @@ class RefineDetLoss(nn.Module):
                                                    L.ptr(exclude), L.stream_ptr()))
         self.last_odm = {}
         return fused_loss(self._spec(False), self.priors_cxcy, self.priors_xy, odm_locs, odm_scores, boxes,
-                          labels, anchors_xy=anchors_xy, exclude=exclude, group=self.process_group,
+                          labels, anchors_xy=anchors_xy, exclude=exclude, group=self.process_group, lane=getattr(self, "exchange_lane", 0),
                           holder=self.last_odm)
 
     def forward(self, arm_locs, arm_scores, odm_locs, odm_scores, boxes, labels):

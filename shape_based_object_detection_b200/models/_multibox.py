@@ -68,11 +68,11 @@ class FusedAnchorLoss(nn.Module):
     def forward(self, predicted_locs, predicted_scores, boxes, labels):
         self.last = {}
         return fused_loss(self._spec(), self.priors_cxcy, self.priors_xy, predicted_locs, predicted_scores,
-                          boxes, labels, group=self.process_group, holder=self.last)
+                          boxes, labels, group=self.process_group, lane=getattr(self, "exchange_lane", 0), holder=self.last)
 
     def forward_packed(self, predicted_locs, predicted_scores, packed_gt):
         """Same loss with the ground truth already packed on the device (core.pack_ground_truth):
         no host-side work, so the call can be captured in a CUDA graph."""
         self.last = {}
         return fused_loss(self._spec(), self.priors_cxcy, self.priors_xy, predicted_locs, predicted_scores,
-                          None, None, group=self.process_group, holder=self.last, packed_gt=packed_gt)
+                          None, None, group=self.process_group, lane=getattr(self, "exchange_lane", 0), holder=self.last, packed_gt=packed_gt)

@@ -15,7 +15,7 @@ import torch
 
 # ---------------------------------------------------------------------------------------------
 # In-kernel exchange of the loss sums (csrc/comm.cuh): mailboxes in every GPU's HBM, mapped into the
-# processes of the node with CUDA IPC. One communicator per (process group, device), created on first use.
+# processes of the node with CUDA IPC. One communicator per (process group, device, lane), created on first use.
 # SBOD_PEER_EXCHANGE=0 keeps the NCCL all-reduce (the checked reference path of the exchange).
 # ---------------------------------------------------------------------------------------------
 _comms = {}
@@ -65,12 +65,15 @@ class PeerExchange:
         return sums
 
 
-def peer_exchange(group, device):
-    """The PeerExchange of (group, device), or None when disabled / unavailable (then the caller all-reduces
-    with torch.distributed, i.e. NCCL)."""
+def peer_exchange(group, device, lane=0):
+    """The PeerExchange of (group, device, lane), or None when disabled / unavailable (then the caller all-reduces
+    with torch.distributed, i.e. NCCL). Calls on one communicator must come in the same order on every rank: criteria
+    that run concurrently on different streams (micro-batches in flight on two streams) take different lanes
+    (`criterion.exchange_lane`), each with its own mailboxes and epoch counter. A communicator is created
+    collectively on first use - not inside a CUDA graph capture."""
     if group is None or os.environ.get("SBOD_PEER_EXCHANGE", "1") == "0":
         return None
-    key = (id(group), device.index)
+    key = (id(group), device.index, int(lane))
     if key not in _comms:
         px = PeerExchange(group, device)
         if not px.ok:
