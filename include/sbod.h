@@ -266,8 +266,11 @@ SBOD_API size_t sbod_loss_workspace_zero_bytes(const sbod_loss_desc* d);
  * again); the same holds for the sbod_assign / sbod_detect workspaces. */
 SBOD_API int sbod_workspace_init(void* workspace, size_t bytes, sbod_stream_t stream);
 SBOD_API int sbod_loss_forward(const sbod_loss_desc* d, sbod_stream_t stream);
-/* Profiling / bench hook: launch one stage of the forward (0 = match + log-sum-exp kernel,
- * 1 = mine kernel: forced-match override + mining + batch reduction). */
+/* sbod_loss_forward = three kernels chained by programmatic dependent launches: the match + log-sum-exp kernel
+ * (streams the logits once), classify_kernel (forced-match override, classes, candidate histogram, foreground
+ * rows) and mine_kernel (top-k sum of the candidates without a sort, batch fold, cross-GPU exchange, loss).
+ * Profiling / bench hook: launch one stage of the forward (0 = the match kernel; 1 = classify + mine). Stage 0
+ * may be repeated; stage 1 must follow before the workspace is used by a full forward again. */
 SBOD_API int sbod_loss_forward_stage(const sbod_loss_desc* d, int stage, sbod_stream_t stream);
 /* Recompute d->loss from d->sums (after a cross-GPU all-reduce of d->sums). */
 SBOD_API int sbod_loss_finalize(const sbod_loss_desc* d, sbod_stream_t stream);
