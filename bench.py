@@ -472,9 +472,11 @@ def run_ours(args, rank, world, local_rank):
     if not args.join_every_step:
         unit = next(u for u in (10, 8, 6, 5, 4, 3, 2, 1) if args.steps % u == 0)
 
-    def e2e_copy_in():
-        """H2D of ONE step's inputs from the pinned host buffers, enqueued on the copy stream (fresh device
-        buffers: the caching allocator hands a block back only after the streams recorded on it are done)."""
+    def step_e2e():
+        """Pinned host buffers in, results out. The copies run on a copy stream: the eval batch's H2D overlaps
+        the train half's compute, the train half's D2H overlaps the eval half."""
+        cur = torch.cuda.current_stream()
+        s_copy.wait_stream(cur)
         with torch.cuda.stream(s_copy):
             tr = [t.to(dev, non_blocking=True) for t in W.h_train]
             bx = [b.to(dev, non_blocking=True) for b in W.h_boxes]
@@ -487,12 +489,6 @@ def run_ours(args, rank, world, local_rank):
                 keep = W.h_arm_scores.to(dev, non_blocking=True)[:, :, 1] > 0.01
             ev_eval = torch.cuda.Event()
             ev_eval.record(s_copy)
-        return tr, bx, lb, ev_train, evt, keep, ev_eval
-
-    def e2e_compute(inputs):
-        """The step on inputs that e2e_copy_in enqueued; returns the results on the host (D2H inside)."""
-        tr, bx, lb, ev_train, evt, keep, ev_eval = inputs
-        cur = torch.cuda.current_stream()
         cur.wait_event(ev_train)
         for t in tr + bx + lb:
             t.record_stream(cur)
@@ -503,18 +499,6 @@ def run_ours(args, rank, world, local_rank):
             t.record_stream(cur)
         out = W.eval_half(evt, keep)
         res = (loss_h, out[0].cpu(), out[1].cpu(), out[2].cpu(), out[4].cpu())
-        return res
-
-    def run_e2e(steps):
-        """`steps` end-to-end steps, double-buffered like a data loader: the H2D copy of step i+1 is enqueued before
-        the host blocks on the results of step i, so it runs under step i's compute and D2H. Every step's copy and
-        every step's results are inside the call."""
-        pending = e2e_copy_in()
-        res = None
-        for i in range(steps):
-            nxt = e2e_copy_in() if i + 1 < steps else None
-            res = e2e_compute(pending)
-            pending = nxt
         return res
 
     for _ in range(max(args.warmup, 3)):
@@ -670,15 +654,10 @@ def run_ours(args, rank, world, local_rank):
         kernels["fcos_postprocess_kernel"] = dict(ms=ms_pp, bytes=N * P * (Cn * 4 * 2 + 16 * 2 + 4))
 
     # ---- e2e ----
-    run_e2e(2)
+    for _ in range(2):
+        step_e2e()
     e2e_steps = max(3, min(args.steps, 10))
-    sync()
-    e2e_t0, e2e_t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e2e_t0.record()
-    run_e2e(e2e_steps)
-    e2e_t1.record()
-    sync()
-    ms_e2e = e2e_t0.elapsed_time(e2e_t1) / e2e_steps
+    ms_e2e = timed(step_e2e, e2e_steps, sync)
     # H2D alone (per rank, all ranks copying at once): is the e2e number a host-side limit?
     def copy_only():
         return [t.to(dev, non_blocking=True) for t in W.h_train + W.h_eval]
@@ -741,7 +720,7 @@ def run_ours(args, rank, world, local_rank):
                         "numa_cpus_bound": numa_cpus},
             "e2e": {"value": N * world / (ms_e2e * 1e-3), "unit": "images/s", "h2d_bytes_per_step": W.h2d_bytes(),
                     "d2h_bytes_per_step": W.d2h_bytes(), "ms_per_step": ms_e2e,
-                    "copy": "H2D on a copy stream, double-buffered (the next step's copy runs under this step's compute)",
+                    "copy": "H2D on a copy stream (eval batch's copy overlaps the train half)",
                     "h2d_gbs_per_rank_all_ranks_copying": h2d_all},
             "gpu_launches": W.launches_per_step(world) * args.steps,
             "clocks": clocks,
