@@ -1594,10 +1594,12 @@ __global__ void __launch_bounds__(128) zero_fill_kernel(float* __restrict__ dst,
 }
 
 struct BwdParams;
+template <int kC>  // kC > 0: compile-time class count (row offsets and chunk tests become immediates)
 __global__ void __launch_bounds__(256, 4) bwd_patch_kernel(const LossParams q, const float* __restrict__ grad_loss,
                                                         float* __restrict__ grad_locs,
                                                         float* __restrict__ grad_scores) {
   const int lane = threadIdx.x & 31;
+  const int C = kC ? kC : q.C;
   const size_t total = size_t(q.N) * q.P;
   asm volatile("griddepcontrol.wait;" ::: "memory");  // (programmatic dependent launch behind the forward)
   const double npos_tot = q.sums[3];
@@ -1633,7 +1635,9 @@ __global__ void __launch_bounds__(256, 4) bwd_patch_kernel(const LossParams q, c
     // flag bit 2: mining candidate - mined iff its (background) CE beats the image's threshold
     // (classify_kernel / mine_kernel leaves the threshold instead of marking ~3 n_pos rows per image)
     if (in && (selbits & 4)) {
-      const int n = int(i / q.P);
+      // (the image of the group's first row with one division per warp; a group rarely straddles two images)
+      const int n0 = int(base / q.P);
+      const int n = q.P < 32 ? int(i / q.P) : (i < size_t(n0 + 1) * q.P ? n0 : n0 + 1);
       const float thr = q.sel_thr[2 * n], ties = q.sel_thr[2 * n + 1];
       const bool mined = (selbits & 2) || ce_bg > thr || (ce_bg == thr && ties != 0.f);
       selbits = mined ? 2 : 0;
@@ -1646,7 +1650,7 @@ __global__ void __launch_bounds__(256, 4) bwd_patch_kernel(const LossParams q, c
       const int g0 = q.gt_offsets[n];
       const int obj = q.obj[i];
       cls = int(map_label(q, q.gt_labels[g0 + obj]));
-      cls = min(max(cls, 0), q.C - 1);
+      cls = min(max(cls, 0), C - 1);
       if (grad_locs) {
         const float4 pred = reinterpret_cast<const float4*>(q.locs)[i];
         const LocTerm lt = loc_term<true>(q, pred, prior_cxcy_of(q, n, p), q.gt_boxes[g0 + obj]);
@@ -1675,40 +1679,45 @@ __global__ void __launch_bounds__(256, 4) bwd_patch_kernel(const LossParams q, c
         rc[u] = __shfl_sync(0xffffffffu, cls, sl);
         rl[u] = __shfl_sync(0xffffffffu, lse, sl);
       }
-      if (q.C <= 4 * 32) {
-        float x[4][4];
+      // the lane's slice of each row: one 64-bit base per row, then immediate offsets (32 c floats per chunk)
+      const float* rp[4];
+      float* gp[4];
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          const int k = 32 * c + lane;
+      for (int u = 0; u < 4; ++u) {
+        const size_t off = (base + size_t(src[u] < 0 ? 0 : src[u])) * size_t(C) + lane;
+        rp[u] = q.scores + off;
+        gp[u] = grad_scores + off;
+      }
+      if (C <= 4 * 32) {
+        constexpr int kChunks = kC ? (kC + 31) / 32 : 4;
+        float x[kChunks][4];
+#pragma unroll
+        for (int c = 0; c < kChunks; ++c) {
+          // chunk c exists (warp-uniform) and the lane's class 32 c + lane is inside the row
+          const bool has = kC ? (32 * c + 31 < kC || lane < kC - 32 * c) : (32 * c + lane < C);
 #pragma unroll
           for (int u = 0; u < 4; ++u) {
             x[c][u] = 0.f;
-            if (32 * c < q.C && src[u] >= 0 && k < q.C)  // (first test warp-uniform: C = 81 uses three chunks)
-              x[c][u] = ld_stream_f32(q.scores + (base + src[u]) * q.C + k);
+            if (has && src[u] >= 0) x[c][u] = ld_stream_f32(rp[u] + 32 * c);
           }
         }
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
+        for (int c = 0; c < kChunks; ++c) {
+          const bool has = kC ? (32 * c + 31 < kC || lane < kC - 32 * c) : (32 * c + lane < C);
           const int k = 32 * c + lane;
-          if (32 * c >= q.C) break;
 #pragma unroll
           for (int u = 0; u < 4; ++u)
-            if (src[u] >= 0 && k < q.C)
-              grad_scores[(base + src[u]) * q.C + k] =
-                  conf_scale * (__expf(x[c][u] - rl[u]) - (k == rc[u] ? 1.f : 0.f));
+            if (has && src[u] >= 0) gp[u][32 * c] = conf_scale * (__expf(x[c][u] - rl[u]) - (k == rc[u] ? 1.f : 0.f));
         }
       } else {
-        for (int kb = 0; kb < q.C; kb += 32) {
+        for (int kb = 0; kb < C; kb += 32) {
           const int k = kb + lane;
           float x[4];
 #pragma unroll
-          for (int u = 0; u < 4; ++u)
-            x[u] = (src[u] >= 0 && k < q.C) ? q.scores[(base + src[u]) * q.C + k] : 0.f;
+          for (int u = 0; u < 4; ++u) x[u] = (src[u] >= 0 && k < C) ? rp[u][kb] : 0.f;
 #pragma unroll
           for (int u = 0; u < 4; ++u)
-            if (src[u] >= 0 && k < q.C)
-              grad_scores[(base + src[u]) * q.C + k] =
-                  conf_scale * (__expf(x[u] - rl[u]) - (k == rc[u] ? 1.f : 0.f));
+            if (src[u] >= 0 && k < C) gp[u][kb] = conf_scale * (__expf(x[u] - rl[u]) - (k == rc[u] ? 1.f : 0.f));
         }
       }
     }
@@ -2052,7 +2061,9 @@ extern "C" int sbod_loss_backward(const sbod_loss_desc* d, const float* grad_los
     attrs[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attrs;
     cfg.numAttrs = g_opt_pdl ? 1 : 0;
-    SBOD_CUDA_TRY(cudaLaunchKernelEx(&cfg, bwd_patch_kernel, q, grad_loss, grad_locs, grad_scores));
+    if (q.C == 81) SBOD_CUDA_TRY(cudaLaunchKernelEx(&cfg, bwd_patch_kernel<81>, q, grad_loss, grad_locs, grad_scores));
+    else if (q.C == 21) SBOD_CUDA_TRY(cudaLaunchKernelEx(&cfg, bwd_patch_kernel<21>, q, grad_loss, grad_locs, grad_scores));
+    else SBOD_CUDA_TRY(cudaLaunchKernelEx(&cfg, bwd_patch_kernel<0>, q, grad_loss, grad_locs, grad_scores));
     return SBOD_OK;
   }
   loss_bwd_kernel<<<grid, kRows, smem, st>>>(bp);
