@@ -972,9 +972,9 @@ __device__ TopkSum select_topk_sum(MineShared& S, const float* __restrict__ vals
           const float e[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
 #pragma unroll
           for (int c = 0; c < 4; ++c)
-            if (hits & (1u << (4 * u + c))) S.vals[at++] = e[c];
+            if ((hits & (1u << (4 * u + c))) && at < kSelCap) S.vals[at++] = e[c];  // (at < n0 by construction)
         }
-        if (hits & (1u << (4 * kB))) S.vals[at++] = ve;
+        if ((hits & (1u << (4 * kB))) && at < kSelCap) S.vals[at++] = ve;
       }
       filled += tot;
     }

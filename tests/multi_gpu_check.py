@@ -111,6 +111,32 @@ def main():
     assert out.item() == results["peer"][0], (out.item(), results["peer"][0])
     del g
 
+    # ---- two criteria in flight on two streams: each on its own exchange lane. The ranks enqueue them in
+    # OPPOSITE order, so a shared mailbox would pair the sums of different batches; with lanes both match. ----
+    crit_a, crit_b = MultiBoxLoss512(pri.to(dev), cfg(81)), MultiBoxLoss512(pri.to(dev), cfg(81))
+    crit_a.process_group = crit_b.process_group = group
+    crit_b.exchange_lane = 1
+    locs2, scores2, bx2, lb2 = synth.make_train_batch(pri, n_total, 81, 100, 78)
+    batches = {"a": (locs, scores, bx, lb), "b": (locs2, scores2, bx2, lb2)}
+    want = {}
+    for name, (lo_, sc_, bx_, lb_) in batches.items():  # whole batch, one process
+        ref = MultiBoxLoss512(pri.to(dev), cfg(81))
+        want[name] = ref(lo_.to(dev), sc_.to(dev), [x.to(dev) for x in bx_], [x.to(dev) for x in lb_]).item()
+    s_a, s_b = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+    got = {}
+    torch.cuda.synchronize()
+    order = ("a", "b") if rank % 2 == 0 else ("b", "a")
+    for rep in range(3):
+        for name in order:
+            lo_, sc_, bx_, lb_ = batches[name]
+            crit_x, stream_x = (crit_a, s_a) if name == "a" else (crit_b, s_b)
+            with torch.cuda.stream(stream_x):
+                got[name] = crit_x(lo_[lo:hi].to(dev), sc_[lo:hi].to(dev), [x.to(dev) for x in bx_[lo:hi]],
+                                   [x.to(dev) for x in lb_[lo:hi]])
+        torch.cuda.synchronize()
+        for name in ("a", "b"):
+            assert abs(got[name].item() - want[name]) <= 1e-6 * abs(want[name]), (rep, name, got[name].item(), want[name])
+
     # ---- RefineDet (two criteria share the communicator) and FCOS (six sums) ----
     prr = PR.refinedet512_priors()
     gen = torch.Generator().manual_seed(5)
