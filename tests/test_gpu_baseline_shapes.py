@@ -552,3 +552,52 @@ def test_hard_negative_mining_with_massive_ties(dev):
         assert abs(loss.item() - want.item()) <= RTOL_LOSS * abs(want.item()), (variant, scale, loss.item(), want.item())
         rows = (s_d.grad.abs().sum(2) > 0).sum(1).cpu()
         assert torch.equal(rows, 4 * parts["n_pos"]), (rows, parts["n_pos"])
+
+
+def test_hard_negative_mining_outside_the_histogram_range(dev):
+    """The mining histogram resolves the 16 octaves [2^-10, 2^6); everything smaller shares bin 0 and everything
+    larger bin 4095, where the k-th value is found by full 32-bit radix passes. Case "tiny": a confident model
+    (background logit + 12): nearly every candidate CE is below 2^-10, so the threshold lies in bin 0 (more values
+    than the shared list holds: the passes run over global memory). Case "huge": logits x 60: CEs of several
+    hundred, the threshold lies in bin 4095. Case "mixed": both tails populated, threshold in a regular bin.
+    Loss, gradients and the number of gradient rows against the oracle."""
+    from oracle import box_pipeline as O
+    from shape_based_object_detection_b200 import priors as PR, synth
+    from shape_based_object_detection_b200.models import MultiBoxLoss512
+    pri = PR.ssd512_canonical_priors()
+    N, Cn = 2, 7
+    locs, scores, bx, lb = synth.make_train_batch(pri, N, Cn, 30, 32)
+    cases = {}
+    tiny = scores.clone()
+    tiny[:, :, 0] += 12.0
+    cases["tiny"] = tiny
+    cases["huge"] = scores * 60.0
+    mixed = scores.clone()
+    mixed[:, ::3, 0] += 14.0
+    mixed[:, 1::3, :] *= 50.0
+    cases["mixed"] = mixed
+    for name, sc in cases.items():
+        l_c, s_c = locs.clone().requires_grad_(True), sc.clone().requires_grad_(True)
+        want, parts = O.multibox_loss("s512", pri, l_c, s_c, bx, lb, want_parts=True)
+        want.backward()
+        crit = MultiBoxLoss512(pri.to(dev), cfg(n_classes=Cn))
+        l_d, s_d = locs.to(dev).requires_grad_(True), sc.to(dev).requires_grad_(True)
+        loss = crit(l_d, s_d, [b.to(dev) for b in bx], [l.to(dev) for l in lb])
+        loss.backward()
+        assert abs(loss.item() - want.item()) <= RTOL_LOSS * abs(want.item()), (name, loss.item(), want.item())
+        assert torch.allclose(l_d.grad.cpu(), l_c.grad, rtol=RTOL_GRAD, atol=1e-7), name
+        got_g, want_g = s_d.grad.cpu(), s_c.grad
+        got_m, want_m = got_g.abs().sum(2) > 0, want_g.abs().sum(2) > 0
+        # (rows whose softmax - onehot underflows to exactly zero in every class do not count on either side)
+        assert torch.equal(got_m.sum(1), want_m.sum(1)), (name, got_m.sum(1), want_m.sum(1), parts["n_pos"])
+        # Cross entropies of ~1e-4 are only known to ~1e-7 absolute in fp32 (log of 1 + tiny) on either side, so two
+        # candidates that close at the threshold may be taken the other way round: at most one swap per image,
+        # between rows with the same gradient to 1e-3; every other row to the usual tolerance.
+        both = got_m & want_m
+        assert int((got_m ^ want_m).sum()) <= 2 * N, (name, int((got_m ^ want_m).sum()))
+        for n in range(N):
+            only_g, only_w = got_g[n][got_m[n] & ~want_m[n]], want_g[n][want_m[n] & ~got_m[n]]
+            assert only_g.shape == only_w.shape
+            if only_g.numel():
+                assert torch.allclose(only_g[:, 0].sort().values, only_w[:, 0].sort().values, rtol=1e-2, atol=1e-9), name
+        assert torch.allclose(got_g[both], want_g[both], rtol=RTOL_GRAD, atol=1e-7), name
