@@ -1186,6 +1186,7 @@ __global__ void __launch_bounds__(kCmThreads, 3) classify_kernel(const LossParam
   for (int u = 0; u < kCmUnroll; ++u) {
     const int p = p_lo + u * kCmThreads + tid;
     rec[u] = 0;
+    int bin = -1;
     if (p < p_hi) {
       const int forced = S.patch[u * kCmThreads + tid];
       if (forced) {  // index_fill_(0, prior_for_each_object, 1.0) and the object override
@@ -1214,11 +1215,17 @@ __global__ void __launch_bounds__(kCmThreads, 3) classify_kernel(const LossParam
       }
       if (!focal && v >= 0.f) {
         a_neg += 1.0;  // mining modes: this partial counts the candidates (NaN CEs are none)
-        atomicAdd(&S.hist[sel_bin(v)], 1u);
+        bin = sel_bin(v);
         selbits |= 4;  // "mining candidate": the backward compares its CE with the threshold
       }
       q.sel[base + p] = selbits;
       if (!focal) q.cand[base + p] = v;
+    }
+    if (!focal) {
+      // bin 0 holds everything below 2^-10 - most candidates of a trained model: one shared-memory atomic per warp
+      const unsigned low = __ballot_sync(0xffffffffu, bin == 0);
+      if (bin > 0) atomicAdd(&S.hist[bin], 1u);
+      else if (bin == 0 && lane == __ffs(low) - 1) atomicAdd(&S.hist[0], unsigned(__popc(low)));
     }
     const unsigned bal = __ballot_sync(0xffffffffu, rec[u] != 0);
     rrank[u] = __popc(bal & ((1u << lane) - 1u));
