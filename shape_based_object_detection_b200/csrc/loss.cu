@@ -1419,6 +1419,7 @@ struct BwdParams {
   int dense;
 };
 
+template <int kC>  // kC > 0 (odd): compile-time class count - the row transform is unrolled with immediate offsets
 __global__ void __launch_bounds__(kRows) loss_bwd_kernel(const BwdParams bp) {
   const LossParams& q = bp.q;
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -1540,11 +1541,25 @@ __global__ void __launch_bounds__(kRows) loss_bwd_kernel(const BwdParams bp) {
             coef_soft = coef_hot = conf_scale;
           }
         }
-        for (int kk = 0; kk < q.C; ++kk) {
-          int k = kk + rot;
-          if (k >= q.C) k -= q.C;
-          const float sm = __expf(row[k] - lse);
-          row[k] = coef_soft * sm - (k == cls ? coef_hot : 0.f);
+        if (kC) {
+          // odd class count: a warp's 32 rows start in 32 different banks, no rotation needed; five
+          // instructions per logit (LDS, FFMA, EX2, FMUL, STS), the one-hot term patched in afterwards
+          if (coef_soft == 0.f) {
+#pragma unroll
+            for (int k = 0; k < kC; ++k) row[k] = 0.f;
+          } else {
+            const float nl2 = -lse * kLog2e;
+#pragma unroll
+            for (int k = 0; k < kC; ++k) row[k] = coef_soft * ex2_approx(fmaf(row[k], kLog2e, nl2));
+            row[cls] -= coef_hot;
+          }
+        } else {
+          for (int kk = 0; kk < q.C; ++kk) {
+            int k = kk + rot;
+            if (k >= q.C) k -= q.C;
+            const float sm = __expf(row[k] - lse);
+            row[k] = coef_soft * sm - (k == cls ? coef_hot : 0.f);
+          }
         }
       }
     }
@@ -1910,7 +1925,9 @@ static int set_kernel_attrs() {
   SBOD_CUDA_TRY(cudaFuncSetAttribute(match_lse_fast_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   SBOD_CUDA_TRY(cudaFuncSetAttribute(match_lse_fast_kernel<81>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   SBOD_CUDA_TRY(cudaFuncSetAttribute(match_lse_fast_kernel<21>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-  SBOD_CUDA_TRY(cudaFuncSetAttribute(loss_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  SBOD_CUDA_TRY(cudaFuncSetAttribute(loss_bwd_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  SBOD_CUDA_TRY(cudaFuncSetAttribute(loss_bwd_kernel<81>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  SBOD_CUDA_TRY(cudaFuncSetAttribute(loss_bwd_kernel<21>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   SBOD_CUDA_TRY(cudaFuncSetAttribute(forced_match_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
   SBOD_CUDA_TRY(cudaFuncSetAttribute(classify_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
   // without a preference the driver picks the smallest shared-memory carve-out that fits ONE CTA per SM
@@ -2039,8 +2056,9 @@ extern "C" int sbod_loss_backward(const sbod_loss_desc* d, const float* grad_los
   const size_t smem = size_t(t.stage_floats) * 4 + 16;
   static DeviceOnce attr_once;
   if (attr_once.pending()) {
-    SBOD_CUDA_TRY(cudaFuncSetAttribute(loss_bwd_kernel,
-                                       cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    SBOD_CUDA_TRY(cudaFuncSetAttribute(loss_bwd_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    SBOD_CUDA_TRY(cudaFuncSetAttribute(loss_bwd_kernel<81>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    SBOD_CUDA_TRY(cudaFuncSetAttribute(loss_bwd_kernel<21>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     attr_once.mark();
   }
   int ctas_per_sm = int((220 * 1024) / (smem + 4 * 1024));
@@ -2073,7 +2091,9 @@ extern "C" int sbod_loss_backward(const sbod_loss_desc* d, const float* grad_los
     else SBOD_CUDA_TRY(cudaLaunchKernelEx(&cfg, bwd_patch_kernel<0>, q, grad_loss, grad_locs, grad_scores));
     return SBOD_OK;
   }
-  loss_bwd_kernel<<<grid, kRows, smem, st>>>(bp);
+  if (q.C == 81) loss_bwd_kernel<81><<<grid, kRows, smem, st>>>(bp);
+  else if (q.C == 21) loss_bwd_kernel<21><<<grid, kRows, smem, st>>>(bp);
+  else loss_bwd_kernel<0><<<grid, kRows, smem, st>>>(bp);
   SBOD_LAUNCH_CHECK();
   return SBOD_OK;
 }
