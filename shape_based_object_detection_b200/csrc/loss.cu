@@ -769,11 +769,11 @@ SBOD_DEVINL float4 prior_cxcy_of(const LossParams& q, int n, int p) {
 // softmax focal terms as functions of ce = -log p_t (Loss.py:9-38)
 SBOD_DEVINL float focal_fg(const LossParams& q, float ce) {  // alpha * (1-p)^gamma * ce
   const float pt = __expf(-ce);
-  return q.falpha * powf(1.f - pt, q.fgamma) * ce;
+  return q.falpha * pow_gamma(1.f - pt, q.fgamma) * ce;
 }
 SBOD_DEVINL float focal_bg(const LossParams& q, float ce) {  // (1-alpha) * p0^gamma * ce  (Loss.py:32)
   const float pt = __expf(-ce);
-  return (1.f - q.falpha) * powf(pt, q.fgamma) * ce;
+  return (1.f - q.falpha) * pow_gamma(pt, q.fgamma) * ce;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1530,11 +1530,11 @@ __global__ void __launch_bounds__(kRows) loss_bwd_kernel(const BwdParams bp) {
             float dL_dce;
             if (selbits & 1) {  // foreground: A=alpha, w = 1-pt  -> dw/dce = pt
               const float w = 1.f - pt;
-              dL_dce = q.falpha * (powf(w, q.fgamma) +
-                                   ce * q.fgamma * powf(w, q.fgamma - 1.f) * pt);
+              dL_dce = q.falpha * (pow_gamma(w, q.fgamma) +
+                                   ce * q.fgamma * pow_gamma(w, q.fgamma - 1.f) * pt);
             } else {  // background: A=1-alpha, w = pt -> dw/dce = -pt
-              dL_dce = (1.f - q.falpha) * (powf(pt, q.fgamma) -
-                                           ce * q.fgamma * powf(pt, q.fgamma - 1.f) * pt);
+              dL_dce = (1.f - q.falpha) * (pow_gamma(pt, q.fgamma) -
+                                           ce * q.fgamma * pow_gamma(pt, q.fgamma - 1.f) * pt);
             }
             coef_soft = coef_hot = conf_scale * dL_dce;
           } else {
