@@ -66,6 +66,9 @@ struct LossParams {
   unsigned int* match_q;      // [N] per-image chunk queues of the match role
   unsigned int* sel_hist;     // [N, kBins] per image: histogram of the mining candidates (sel_bin; zero between calls)
   double* blockpart;          // [N, slices, 4] partial sums of the slices
+  float* sel_seg;             // [N, kSelCap] batch-global mining: each image's candidates inside the batch's threshold bin
+  int* sel_segn;              // [N] ... their number (-1: the bin does not fit, whole-batch path)
+  double* sel_above;          // [N] ... and each image's sum of the candidates above the bin
   // tiling
   int rows_per_tile, tiles_per_image, n_tiles, n_stages;
   uint32_t stage_floats;
@@ -839,6 +842,7 @@ struct MineShared {
   int warp_tot[kMineWarps];
   int misc[8];
   int last;
+  int segoff[kMineThreads + 1];  // batch-global mining: where each image's segment goes in the merged list
 };
 
 struct TopkSum {
@@ -875,16 +879,15 @@ SBOD_DEVINL int mine_excl_scan(int v, int* warp_tot, int* total) {
 // ghist[kBins] = their sel_bin histogram, read and left zero. 0 < k <= number of candidates, or k == 0
 // (nothing selected). sel (may be null): flag bytes of the values; only touched when some but not all values
 // equal to the threshold are selected (the first ones by index get bit 1). All kMineThreads threads call this.
-__device__ TopkSum select_topk_sum(MineShared& S, const float* __restrict__ vals, const long long n,
-                                   unsigned int* __restrict__ ghist, const long long k, uint8_t* __restrict__ sel,
-                                   const uint4* preloaded = nullptr /* this thread's four bins, already read */) {
-  static_assert(kMineWarps == 32, "mine_excl_scan");
-  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-  TopkSum r;
-  r.sum = 0.0;
-  r.thr = __int_as_float(0x7f800000);
-  r.ties = 0.f;
-  // ---- the bin that holds the k-th largest: every thread owns 4 consecutive bins, highest bins first ----
+// --- the pieces of the top-k sum (all kMineThreads threads of one CTA call them) ---
+
+// The bin that holds the k-th largest candidate, from the histogram ghist[kBins] (every thread owns 4 consecutive
+// bins, highest bins first; `zero`: the bins are left clean for the next call). Results (CTA-uniform) in
+// S.misc[0..2] = bin, rank of the k-th value inside the bin (from the top, 1-based), candidates in the bin.
+// k > 0 and k <= number of candidates. Ends with a barrier.
+__device__ void find_threshold_bin(MineShared& S, unsigned int* __restrict__ ghist, const long long k, const bool zero,
+                                   const uint4* preloaded) {
+  const int tid = threadIdx.x;
   constexpr int kPer = kBins / kMineThreads;
   static_assert(kPer == 4, "one 128-bit load per thread");
   unsigned int cnt[kPer];
@@ -892,9 +895,9 @@ __device__ TopkSum select_topk_sum(MineShared& S, const float* __restrict__ vals
     uint4* gp = reinterpret_cast<uint4*>(ghist + (kBins - kPer * (tid + 1)));
     const uint4 v = preloaded ? *preloaded : __ldcg(gp);
     cnt[0] = v.w; cnt[1] = v.z; cnt[2] = v.y; cnt[3] = v.x;
-    *gp = make_uint4(0u, 0u, 0u, 0u);  // clean for the next call
+    if (zero) *gp = make_uint4(0u, 0u, 0u, 0u);
   }
-  if (k <= 0) return r;  // (CTA-uniform)
+  if (k <= 0) return;  // (CTA-uniform)
   {
     unsigned int mine = 0;
 #pragma unroll
@@ -918,13 +921,14 @@ __device__ TopkSum select_topk_sum(MineShared& S, const float* __restrict__ vals
     }
     __syncthreads();
   }
-  const int d0 = S.misc[0];
-  int remaining = S.misc[1];  // rank of the k-th value inside its bin (from the top, 1-based)
-  const int n0 = S.misc[2];   // candidates in the bin
-  const bool fits = n0 <= kSelCap;
-  CM_STAMP_SET(8 + 4 * (blockIdx.x & 63) + 1);
-  // ---- one pass: everything above the bin is summed, the bin's values are collected ----
-  double above = 0.0;
+}
+
+// One pass over vals[0, n): everything above bin d0 is added to `above` (per thread, double); the values of the bin
+// are collected in S.vals in a fixed order when `fits` (at most kSelCap of them). Returns the number of values of
+// the bin it met (CTA-uniform). Ends with a barrier.
+__device__ int scan_collect(MineShared& S, const float* __restrict__ vals, const long long n, const int d0,
+                            const bool fits, double& above) {
+  const int tid = threadIdx.x;
   int filled = 0;  // (CTA-uniform) values placed so far
   {
     // 128-bit loads over the 16-byte aligned interior, the ragged ends by the first threads
@@ -980,8 +984,21 @@ __device__ TopkSum select_topk_sum(MineShared& S, const float* __restrict__ vals
     }
   }
   __syncthreads();
-  CM_STAMP_SET(8 + 4 * (blockIdx.x & 63) + 2);
-  // ---- the k-th value inside the bin: 8-bit radix passes over the collected values (or over global memory) ----
+  return filled;
+}
+
+struct BinResolve {
+  float thr;       // the k-th largest value
+  int take_ties;   // how many values equal to thr belong to the selection
+  bool all_ties;   // ... all of them
+  double inbin;    // this thread's part of the sum of the bin's values above thr
+};
+
+// The k-th value inside bin d0 (n0 values, rank `remaining` from the top): 8-bit radix passes over the collected
+// values S.vals[0, n0) (fits) or over the bin's values in vals[0, n) (global memory).
+__device__ BinResolve resolve_in_bin(MineShared& S, const float* __restrict__ vals, const long long n, const int d0,
+                                     const int n0, const bool fits, int remaining) {
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const bool regular = d0 > 0 && d0 < kBins - 1;  // every value of a regular bin shares its leading 17 bits
   uint32_t prefix = regular ? uint32_t(d0 - 1 + kSelLo) << 15 : 0u;
   uint32_t mask = regular ? 0xffff8000u : 0u;
@@ -1053,24 +1070,55 @@ __device__ TopkSum select_topk_sum(MineShared& S, const float* __restrict__ vals
       if (v > thr && sel_bin(v) == d0) inbin += double(v);
     }
   }
-  r.sum = block_sum(above + inbin, S.red) + double(take_ties) * double(thr);
-  r.thr = thr;
-  r.ties = all_ties ? 1.f : 0.f;
-  if (!all_ties && sel) {
-    // rare: only some of the values equal to the threshold belong to the selection - the first ones by index.
-    // Every thread walks a contiguous run of the values; runs are ranked by an exclusive scan.
-    const long long per = (n + kMineThreads - 1) / kMineThreads;
-    const long long lo = per * tid < n ? per * tid : n, hi = lo + per < n ? lo + per : n;
-    int mine = 0;
-    for (long long i = lo; i < hi; ++i) mine += __ldcg(vals + i) == thr ? 1 : 0;
-    int tot;
-    int left = take_ties - mine_excl_scan(mine, S.warp_tot, &tot);
-    for (long long i = lo; i < hi && left > 0; ++i)
-      if (__ldcg(vals + i) == thr) {
-        sel[i] = uint8_t(sel[i] | 2);
-        --left;
-      }
-  }
+  BinResolve br;
+  br.thr = thr;
+  br.take_ties = take_ties;
+  br.all_ties = all_ties;
+  br.inbin = inbin;
+  return br;
+}
+
+// rare: only some of the values equal to the threshold belong to the selection - the first ones by index get flag
+// bit 1. Every thread walks a contiguous run of the values; runs are ranked by an exclusive scan.
+__device__ void mark_partial_ties(MineShared& S, const float* __restrict__ vals, const long long n, const float thr,
+                                  const int take_ties, uint8_t* __restrict__ sel) {
+  const int tid = threadIdx.x;
+  const long long per = (n + kMineThreads - 1) / kMineThreads;
+  const long long lo = per * tid < n ? per * tid : n, hi = lo + per < n ? lo + per : n;
+  int mine = 0;
+  for (long long i = lo; i < hi; ++i) mine += __ldcg(vals + i) == thr ? 1 : 0;
+  int tot;
+  int left = take_ties - mine_excl_scan(mine, S.warp_tot, &tot);
+  for (long long i = lo; i < hi && left > 0; ++i)
+    if (__ldcg(vals + i) == thr) {
+      sel[i] = uint8_t(sel[i] | 2);
+      --left;
+    }
+}
+
+__device__ TopkSum select_topk_sum(MineShared& S, const float* __restrict__ vals, const long long n,
+                                   unsigned int* __restrict__ ghist, const long long k, uint8_t* __restrict__ sel,
+                                   const uint4* preloaded = nullptr /* this thread's four bins, already read */) {
+  static_assert(kMineWarps == 32, "mine_excl_scan");
+  TopkSum r;
+  r.sum = 0.0;
+  r.thr = __int_as_float(0x7f800000);
+  r.ties = 0.f;
+  find_threshold_bin(S, ghist, k, true, preloaded);
+  if (k <= 0) return r;  // (CTA-uniform)
+  const int d0 = S.misc[0];
+  const int remaining = S.misc[1];
+  const int n0 = S.misc[2];
+  const bool fits = n0 <= kSelCap;
+  CM_STAMP_SET(8 + 4 * (blockIdx.x & 63) + 1);
+  double above = 0.0;
+  scan_collect(S, vals, n, d0, fits, above);
+  CM_STAMP_SET(8 + 4 * (blockIdx.x & 63) + 2);
+  const BinResolve br = resolve_in_bin(S, vals, n, d0, n0, fits, remaining);
+  r.sum = block_sum(above + br.inbin, S.red) + double(br.take_ties) * double(br.thr);
+  r.thr = br.thr;
+  r.ties = br.all_ties ? 1.f : 0.f;
+  if (!br.all_ties && sel) mark_partial_ties(S, vals, n, br.thr, br.take_ties, sel);
   return r;
 }
 
@@ -1350,6 +1398,46 @@ __global__ void __launch_bounds__(kMineThreads, 1) mine_kernel(const LossParams 
     sel_thr = r.thr;
     sel_ties = r.ties;
   }
+  const bool batch = q.cls_kind == SBOD_CLS_CE_MINE_BATCH;
+  if (batch) {
+    // SSD300 mines over the whole batch (SSD300.py:580-588). Every image's CTA can tell the batch's threshold bin
+    // on its own: the slices' partials and the (single) histogram are complete. It then does its image's share
+    // of the one pass - the sum above the bin, the bin's values - so the last image only merges 32 short lists
+    // instead of scanning N * P candidates alone.
+    double c2 = 0.0, c3 = 0.0;  // candidates / positives of the batch: integers, exact in any order
+    for (int e = tid; e < q.N * slices; e += kMineThreads) {
+      c2 += __ldcg(q.blockpart + size_t(e) * 4 + 2);
+      c3 += __ldcg(q.blockpart + size_t(e) * 4 + 3);
+    }
+    c2 = block_sum(c2, S.red);
+    c3 = block_sum(c3, S.red);
+    const long long n_cand_b = (long long)(c2 + 0.5);
+    long long k_b = (long long)(q.ratio) * (long long)(c3 + 0.5);
+    if (k_b > n_cand_b) k_b = n_cand_b;
+    int segn = 0;
+    double above_n = 0.0;
+    if (k_b > 0 && q.N <= kMineThreads) {
+      find_threshold_bin(S, q.sel_hist, k_b, false, nullptr);
+      const int d0 = S.misc[0], n0 = S.misc[2];
+      __syncthreads();
+      if (n0 <= kSelCap) {
+        double above = 0.0;
+        segn = scan_collect(S, q.cand + base, q.P, d0, true, above);
+        above_n = block_sum(above, S.red);
+        for (int i = tid; i < segn && i < kSelCap; i += kMineThreads) q.sel_seg[size_t(n) * kSelCap + i] = S.vals[i];
+      } else {
+        segn = -1;
+      }
+    } else if (k_b > 0) {
+      segn = -1;
+    }
+    if (tid == 0) {
+      q.sel_segn[n] = segn;
+      q.sel_above[n] = above_n;
+    }
+    __threadfence();  // the segment before this image's ticket
+    __syncthreads();
+  }
   if (tid == 0) {
     q.sel_thr[2 * n] = sel_thr;
     q.sel_thr[2 * n + 1] = sel_ties;
@@ -1380,7 +1468,44 @@ __global__ void __launch_bounds__(kMineThreads, 1) mine_kernel(const LossParams 
     const long long n_cand = (long long)(tot[2] + 0.5);
     long long k = (long long)(q.ratio) * (long long)(tot[3] + 0.5);
     if (k > n_cand) k = n_cand;
-    const TopkSum r = select_topk_sum(S, q.cand, (long long)q.N * q.P, q.sel_hist, k, q.sel);
+    TopkSum r;
+    r.sum = 0.0;
+    r.thr = __int_as_float(0x7f800000);
+    r.ties = 0.f;
+    bool merged = false;
+    if (k > 0 && q.N <= kMineThreads) {
+      find_threshold_bin(S, q.sel_hist, k, false, nullptr);  // (the same bin every image found)
+      const int d0 = S.misc[0], remaining = S.misc[1], n0 = S.misc[2];
+      __syncthreads();
+      if (n0 <= kSelCap) {
+        // merge the images' lists in image order (deterministic), then resolve the k-th value inside the bin
+        merged = true;
+        int tot_n;
+        const int c = tid < q.N ? __ldcg(q.sel_segn + tid) : 0;
+        const int off = mine_excl_scan(c, S.warp_tot, &tot_n);
+        if (tid < q.N) S.segoff[tid] = off;
+        if (tid == 0) S.segoff[q.N] = tot_n;
+        if (tid == 0) {
+          double a = 0.0;
+          for (int i = 0; i < q.N; ++i) a += __ldcg(q.sel_above + i);
+          S.red4[0] = a;
+        }
+        __syncthreads();
+        for (int i = 0; i < q.N; ++i) {
+          const int o = S.segoff[i], cn = S.segoff[i + 1] - o;
+          for (int j = tid; j < cn; j += kMineThreads) S.vals[o + j] = __ldcg(q.sel_seg + size_t(i) * kSelCap + j);
+        }
+        __syncthreads();
+        const double above = S.red4[0];
+        const BinResolve br = resolve_in_bin(S, nullptr, 0, d0, n0, true, remaining);
+        r.sum = above + block_sum(br.inbin, S.red) + double(br.take_ties) * double(br.thr);
+        r.thr = br.thr;
+        r.ties = br.all_ties ? 1.f : 0.f;
+        if (!br.all_ties) mark_partial_ties(S, q.cand, (long long)q.N * q.P, br.thr, br.take_ties, q.sel);
+        for (int b = tid; b < kBins; b += kMineThreads) q.sel_hist[b] = 0u;  // clean for the next call
+      }
+    }
+    if (!merged) r = select_topk_sum(S, q.cand, (long long)q.N * q.P, q.sel_hist, k, q.sel);  // the whole batch here
     tot[2] = r.sum;
     for (int i = tid; i < q.N; i += kMineThreads) {
       q.sel_thr[2 * i] = r.thr;
@@ -1851,6 +1976,12 @@ static int fill_params(const sbod_loss_desc* d, LossParams& q, bool need_scores)
   q.cand = reinterpret_cast<float*>(w);
   w += align_up(size_t(q.N) * q.P * 4, 256);
   q.blockpart = reinterpret_cast<double*>(w);
+  w += align_up(size_t(q.N) * size_t(cm_slices(q.P)) * 32, 256);
+  q.sel_seg = reinterpret_cast<float*>(w);
+  w += align_up(d->cls_kind == SBOD_CLS_CE_MINE_BATCH ? size_t(q.N) * kSelCap * 4 : 0, 256);
+  q.sel_segn = reinterpret_cast<int*>(w);
+  w += align_up(size_t(q.N) * 4, 256);
+  q.sel_above = reinterpret_cast<double*>(w);
   Tiling t = choose_tiling(need_scores ? d->C : 1, kMaxStages);
   // the two-threads-per-row layout is bank-conflict free only for odd C; even C is merely slower in smem
   q.fast = (need_scores && d->C >= 2 && d->C <= 128) ? 1 : 0;
@@ -1892,7 +2023,9 @@ extern "C" size_t sbod_loss_workspace_bytes(const sbod_loss_desc* d) {
   if (!d) return 0;
   const int gmax = d->gmax > 0 ? d->gmax : 1;
   return sbod_loss_workspace_zero_bytes(d) + align_up(size_t(d->N) * d->P * 4, 256) +
-         align_up(size_t(d->N) * size_t(cm_slices(d->P)) * 32, 256);
+         align_up(size_t(d->N) * size_t(cm_slices(d->P)) * 32, 256) +
+         align_up(d->cls_kind == SBOD_CLS_CE_MINE_BATCH ? size_t(d->N) * kSelCap * 4 : 0, 256) +
+         align_up(size_t(d->N) * 4, 256) + align_up(size_t(d->N) * 8, 256);
 }
 
 // leading bytes of the loss workspace that carry the zero contract: counters, per-object keys, ticket queues
