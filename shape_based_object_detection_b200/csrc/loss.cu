@@ -108,7 +108,7 @@ SBOD_DEVINL void issue_tile_load(const LossParams& q, int tile, float* stage, ui
     stage[s.bulk_bytes / 4 + i] = q.scores[(s.src16 - q.scores) + s.bulk_bytes / 4 + i];
   if (s.bulk_bytes) {
     mbar_arrive_expect_tx(bar, s.bulk_bytes);
-    tma_load_1d(stage, s.src16, s.bulk_bytes, bar);
+    tma_load_1d_hint(stage, s.src16, s.bulk_bytes, bar, l2_policy_evict_first());
   } else {
     mbar_arrive(bar);
   }
@@ -388,6 +388,7 @@ __global__ void __launch_bounds__(kFastThreads, 2) match_lse_fast_kernel(const L
         stream_issue(q.scores, q.N, q.P, C,
                      stream_tile(t0 + it + q.n_stages, q.tiles_per_image, kTileRows, q.P), stage, &bars[s]);
       if (tid == 32 && q.prefill) {
+        const uint64_t zero_policy = l2_policy_evict_first();
         // zero-fill this tile of the gradient buffer: 16-byte aligned interior by bulk stores from
         // the zero tile (fire and forget: the source never changes), ragged ends by plain stores
         const size_t e0 = (size_t(tc.n) * q.P + tc.p0) * size_t(C), e1 = e0 + size_t(tc.rows) * C;
@@ -396,7 +397,7 @@ __global__ void __launch_bounds__(kFastThreads, 2) match_lse_fast_kernel(const L
         for (size_t e = (a1 > a0 ? a1 : (a0 < e1 ? a0 : e1)); e < e1; ++e) q.prefill[e] = 0.f;
         for (size_t a = a0; a < a1; a += kZeroFloats) {
           const size_t len = (a1 - a) < size_t(kZeroFloats) ? (a1 - a) : size_t(kZeroFloats);
-          tma_store_1d(q.prefill + a, s_zero, uint32_t(len * 4));
+          tma_store_1d_hint(q.prefill + a, s_zero, uint32_t(len * 4), zero_policy);
         }
         tma_store_commit();
       }
@@ -1590,7 +1591,7 @@ __global__ void __launch_bounds__(kRows) loss_bwd_kernel(const BwdParams bp) {
         tilebuf[s.bulk_bytes / 4 + i] = q.scores[(s.src16 - q.scores) + s.bulk_bytes / 4 + i];
       if (s.bulk_bytes) {
         mbar_arrive_expect_tx(bar, s.bulk_bytes);
-        tma_load_1d(tilebuf, s.src16, s.bulk_bytes, bar);
+        tma_load_1d(tilebuf, s.src16, s.bulk_bytes, bar);  // (no L2 hint here: evict-first measured 350 vs 285 us)
       } else {
         mbar_arrive(bar);
       }
@@ -1732,7 +1733,7 @@ __global__ void __launch_bounds__(128) zero_fill_kernel(float* __restrict__ dst,
     for (size_t c = blockIdx.x; c < n_chunks; c += gridDim.x) {
       const size_t off = c * kZeroTileBytes;
       const size_t len = (bulk_bytes - off) < size_t(kZeroTileBytes) ? (bulk_bytes - off) : size_t(kZeroTileBytes);
-      tma_store_1d(base + off, s_zero, uint32_t(len));
+      tma_store_1d_hint(base + off, s_zero, uint32_t(len), l2_policy_evict_first());
       tma_store_commit();
     }
     tma_store_wait_all<0>();

@@ -262,7 +262,7 @@ SBOD_DEVINL void stream_issue(const float* base, int N, int P, int C, const Stre
     stage[s.bulk_bytes / 4 + i] = base[(s.src16 - base) + s.bulk_bytes / 4 + i];
   if (s.bulk_bytes) {
     mbar_arrive_expect_tx(bar, s.bulk_bytes);
-    tma_load_1d(stage, s.src16, s.bulk_bytes, bar);
+    tma_load_1d_hint(stage, s.src16, s.bulk_bytes, bar, l2_policy_evict_first());  // (streamed once)
   } else {
     mbar_arrive(bar);
   }
