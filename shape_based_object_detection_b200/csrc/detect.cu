@@ -1,11 +1,14 @@
 // detect.cu — the eval path (sm_100a): activation + decode + clamp + score threshold +
 // per-class NMS + top-k, batched, no host round trips.
 //
-//   detect_bound_kernel  the streaming pass: logits HBM -> smem by bulk TMA exactly once, one thread per
-//                        prior row, maximum foreground logit -> upper bound of the row's best probability
-//                        (+ per-image histogram of the bounds). HBM-bound: two instructions per logit.
+//   detect_bound_kernel  the streaming pass: logits HBM -> smem by bulk TMA exactly once (L2 evict-first), two
+//                        threads per prior row, ONE pass: best foreground probability of the row, inflated
+//                        to an upper bound of what the exact evaluation can produce (+ per-image histogram of
+//                        the bounds). HBM-bound: five instructions per logit, nothing else in the kernel.
 //   detect_refine_kernel exact activation (as torch: max shift, accurate exp, division) of the rows whose
-//                        bound lies above the image's cutoff, a warp per row; every (class, prior) above
+//                        bound lies above the image's cutoff: an octet of lanes per row, the row in
+//                        registers, class count a template parameter, classes above a logit threshold queued
+//                        per warp and evaluated by consecutive lanes; every (class, prior) above
 //                        min_score and the cutoff is emitted as one 64-bit key
 //                        [0x3F800000 - score_bits : 32][class : 12][prior : 20]  so that
 //                        ascending key order == (score desc, class asc, prior asc) == the order in
@@ -15,10 +18,12 @@
 //                        NMS is prefix-stable, so the first top_k+1 survivors in global key order
 //                        are all that is ever needed: candidates are pulled in key-ordered chunks
 //                        (histogram-guided, radix descent for oversized bins), sorted in smem,
-//                        suppressed per class by one warp per class (warp-ballot over the kept
-//                        list), and the loop stops as soon as top_k+1 boxes survive. If the
-//                        candidates run out first, everything is kept and emitted class-major,
-//                        exactly as the reference does.
+//                        suppressed per class (pairwise bit masks; large class segments and the
+//                        class-agnostic second stage of detect_tools as bitmask NMS over all warps),
+//                        and the loop stops as soon as top_k+1 boxes survive. If the candidates above
+//                        the cutoff run out first the CTA evaluates the image's remaining rows itself
+//                        (second band); if everything runs out, everything is kept and emitted
+//                        class-major, exactly as the reference does.
 #include <math.h>
 #include <stdlib.h>
 #include <string.h>

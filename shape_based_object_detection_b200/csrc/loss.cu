@@ -1,7 +1,7 @@
 // loss.cu — the fused train path: assignment + log-sum-exp + loc/conf losses + hard-negative
 // mining, forward and backward (sm_100a).
 //
-// Kernels (forward = match_lse* -> classify_mine; backward = bwd_patch, or loss_bwd for focal)
+// Kernels (forward = match_lse* -> classify -> mine; backward = bwd_patch, or loss_bwd for focal)
 //   match_lse_fast_kernel<C>  2 <= C <= 128 (C = 81 / 21 compile-time): warp-specialised, persistent.
 //                      Stream warps: logits tiles HBM->smem by 1-D bulk TMA through an mbarrier ring,
 //                      one-pass log-sum-exp + background CE, optional zero-fill of the logits gradient.
@@ -73,7 +73,6 @@ struct LossParams {
   int rows_per_tile, tiles_per_image, n_tiles, n_stages;
   uint32_t stage_floats;
   int with_scores;
-  int mine_cache;  // (unused)
   int fast;        // odd C <= 128: warp-specialised two-threads-per-row kernels
   int ctas_per_sm;
   int debug_skip;  // SBOD_DEBUG_SKIP: bit0 = no stream role, bit1 = no match role (profiling only)
@@ -2012,7 +2011,6 @@ static int fill_params(const sbod_loss_desc* d, LossParams& q, bool need_scores)
     q.debug_skip = e ? atoi(e) : 0;
   }
 #endif
-  q.mine_cache = 0;
   return SBOD_OK;
 }
 
@@ -2285,7 +2283,6 @@ extern "C" int sbod_assign(const float* gt_boxes, const int64_t* gt_labels,
   q.with_scores = 0;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   q.fast = 0;
-  q.mine_cache = 0;
   q.ctas_per_sm = 8;
   int rc = launch_match(q, st);
   if (rc) return rc;
