@@ -1146,7 +1146,6 @@ struct CmShared {
   uint16_t fg_idx[kCmSlice];  // foreground rows: prior index inside the slice
   uint16_t fg_cls[kCmSlice];  // ... class (bit 15: positive)
   uint16_t fg_obj[kCmSlice];  // ... object of the image
-  float fg_lse[kCmSlice];     // ... log-sum-exp of its logits
   int patch[kCmSlice];        // forced matches of the slice: 1 + rank of the object that claims the prior, 0 = none
 };
 
@@ -1184,17 +1183,16 @@ __global__ void __launch_bounds__(kCmThreads, 3) classify_kernel(const LossParam
   // ---- every load of the slice is requested at once: the first per-object keys, then the per-prior state of
   // 8 priors per thread ----
   unsigned long long key0 = tid < G ? q.gtkey[size_t(n) * q.gmax + tid] : 0ull;
-  float ov[kCmUnroll], ce[kCmUnroll], lse[kCmUnroll];
+  float ov[kCmUnroll], ce[kCmUnroll];
   int ob[kCmUnroll];
 #pragma unroll
   for (int u = 0; u < kCmUnroll; ++u) {
     const int p = p_lo + u * kCmThreads + tid;
-    ov[u] = 0.f; ce[u] = 0.f; lse[u] = 0.f; ob[u] = 0;
+    ov[u] = 0.f; ce[u] = 0.f; ob[u] = 0;
     if (p < p_hi) {
       ov[u] = q.ov[base + p];
       ob[u] = q.obj[base + p];
       ce[u] = q.ce[base + p];  // background CE from the streaming kernel
-      lse[u] = q.lse[base + p];
     }
   }
   __syncthreads();
@@ -1312,7 +1310,6 @@ __global__ void __launch_bounds__(kCmThreads, 3) classify_kernel(const LossParam
       S.fg_idx[slot] = uint16_t(u * kCmThreads + tid);
       S.fg_cls[slot] = uint16_t(rec[u]);
       S.fg_obj[slot] = uint16_t(ob[u]);
-      S.fg_lse[slot] = lse[u];
     }
   }
   __syncthreads();
@@ -1326,13 +1323,14 @@ __global__ void __launch_bounds__(kCmThreads, 3) classify_kernel(const LossParam
       const int c = S.fg_cls[i] & 0x7fff;
       const bool pos = (S.fg_cls[i] & 0x8000) != 0;
       const float xc = ld_stream_f32(q.scores + (base + pp) * q.C + c);
+      const float lse = q.lse[base + pp];  // (only the foreground rows need it: L2, in flight with the logit)
       float4 pred = make_float4(0.f, 0.f, 0.f, 0.f), pcx = pred, gbox = pred;
       if (pos) {
         pred = reinterpret_cast<const float4*>(q.locs)[base + pp];
         pcx = prior_cxcy_of(q, n, pp);
         gbox = q.gt_boxes[g0 + S.fg_obj[i]];
       }
-      const float cet = S.fg_lse[i] - xc;  // CE against the true class
+      const float cet = lse - xc;  // CE against the true class
       q.ce[base + pp] = cet;
       if (pos) {
         ++npos;
