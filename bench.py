@@ -370,6 +370,14 @@ class Workload:
         loss.backward()
         return loss
 
+    def forward_only(self):
+        """The criterion on the resident train batch without autograd (no backward follows)."""
+        with torch.no_grad():
+            ts = [t.detach() for t in self.d_train]
+            if self.cid in (1, 2, 3):
+                return self.crit.forward_packed(ts[0], ts[1], self.gt)
+            return self.crit(*ts, self.d_packed, None)
+
     def eval_half(self, tensors=None, keep=None):
         S, cf = self.S, self.cf
         ts = tensors if tensors is not None else self.d_eval
@@ -630,7 +638,17 @@ def run_ours(args, rank, world, local_rank):
                                                 bytes_logits_only=alg, writes_gradient_zero_fill=prefill,
                                                 ms_single_launch_between_events=ms_match_pair)
         kernels["classify_kernel+mine_kernel"] = dict(ms=ms_cm, bytes=N * P * 17)
-        ms_fwd = timed(lambda: st.forward(), args.steps, sync)
+        run_fwd, g_fwd = graphed(lambda: st.forward())
+        ms_fwd = timed(run_fwd, args.steps, sync)
+        # the forward alone as an inference of the loss would run it: no backward follows, so the streaming kernel
+        # does not zero-fill a gradient buffer
+        ms_fwd_only = None
+        if prefill:
+            W.forward_only()
+            st0 = W.crit.last["state"] if cid != 4 else W.crit.last_odm["state"]
+            if not bool(st0.desc.grad_scores_prefill):
+                run_fwd0, g_fwd0 = graphed(lambda: st0.forward())
+                ms_fwd_only = timed(run_fwd0, args.steps, sync)
         gl = torch.ones((), device=dev)
         g_l, g_s = torch.empty_like(st.locs), torch.empty_like(st.scores)
         ms_bwd = timed(lambda: st.backward_into(gl, g_l, g_s), args.steps, sync)
@@ -641,7 +659,7 @@ def run_ours(args, rank, world, local_rank):
             kernels["match_lse_fast_kernel"]["pair_evals_per_launch"] = pairs
             kernels["match_lse_fast_kernel"]["pair_evals_per_s"] = pairs / (ms_match * 1e-3)
     else:
-        ms_fwd = ms_bwd = None
+        ms_fwd = ms_bwd = ms_fwd_only = None
     # eval path: the streaming bound pass alone (stage 2), then refine (3) and NMS (1)
     if True:
         if cid in (1, 2, 3):
@@ -749,6 +767,7 @@ def run_ours(args, rank, world, local_rank):
                         "sharding": "batch sharded by image, one all-reduce of the loss sums per criterion" if cf["shards"]
                         else "independent replicas (batch-global mining does not shard)",
                         "ms_train_half": ms_train, "ms_eval_half": ms_eval, "ms_loss_fwd": ms_fwd,
+                        "ms_loss_fwd_without_gradient_zero_fill": ms_fwd_only,
                         "ms_loss_bwd_incl_zero_fill": ms_bwd, "ms_detect": ms_eval,
                         "images_per_s_train_half": N * world / (ms_train * 1e-3),
                         "images_per_s_detect": N * world / (ms_eval * 1e-3),
