@@ -509,7 +509,8 @@ __global__ void __launch_bounds__(kFastThreads, 2) match_lse_fast_kernel(const L
     const bool azero = anchor_is_zero(a);
     const bool active = valid && !azero;
     const bool a_ok = ((a.z >= a.x) && (a.w >= a.y)) || !valid;
-    const bool warp_a_ok = __all_sync(0xffffffffu, a_ok) != 0;
+    // (areas up to 2^59 keep every IoU denominator of the fast path below 2^60: see the division test below)
+    const bool warp_a_ok = __all_sync(0xffffffffu, a_ok && aa <= 5.76460752303e17f) != 0;
     // bounding box of the warp's priors
     const float bx1 = warp_min_redux(active ? a.x : INF), by1 = warp_min_redux(active ? a.y : INF);
     const float bx2 = warp_max_redux(active ? a.z : -INF), by2 = warp_max_redux(active ? a.w : -INF);
@@ -522,7 +523,8 @@ __global__ void __launch_bounds__(kFastThreads, 2) match_lse_fast_kernel(const L
       float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
       if (gi < G) g = q.gt_boxes[g0 + gi];
       const bool gskip = gi >= G || gt_is_zero(g);
-      const bool grp_ok = __all_sync(0xffffffffu, (g.z >= g.x) && (g.w >= g.y)) != 0;
+      const float ga_own = box_area_rn(g);
+      const bool grp_ok = __all_sync(0xffffffffu, (g.z >= g.x) && (g.w >= g.y) && ga_own <= 5.76460752303e17f) != 0;
       if (grp_ok && warp_a_ok) {
         // fast path: a pair that does not intersect is exactly +0, so only objects touching the
         // warp's bounding box are evaluated, two at a time (independent dependency chains)
@@ -532,7 +534,7 @@ __global__ void __launch_bounds__(kFastThreads, 2) match_lse_fast_kernel(const L
         int cidx = base;
         if (m) {
           sgt[lane] = g;
-          sga[lane] = box_area_rn(g);
+          sga[lane] = ga_own;
           __syncwarp();
           while (m) {
             const int sA = __ffs(m) - 1;
@@ -547,7 +549,11 @@ __global__ void __launch_bounds__(kFastThreads, 2) match_lse_fast_kernel(const L
             const float dA = __fadd_rn(__fsub_rn(__fadd_rn(gaA, aa), inA), kEps);
             const float dB = __fadd_rn(__fsub_rn(__fadd_rn(gaB, aa), inB), kEps);
             float qA, qB;
-            if (__all_sync(0xffffffffu, div_fast_ok(inA, dA) && div_fast_ok(inB, dB))) {
+            // div_fast_ok(in, d) wants in == 0 or 2^-60 <= in <= 2^60, and 2^-60 <= d <= 2^60. In this path every
+            // width and height is >= 0 and every area <= 2^59, so  in <= min(area) <= d,  EPS <= d <= 2^60  hold by
+            // construction (monotonic rounding): what is left per pair is "in is not a tiny positive number".
+            const float tiny = 8.67361737988e-19f;  // 2^-60
+            if (__all_sync(0xffffffffu, !(inA > 0.f && inA < tiny) && !(inB > 0.f && inB < tiny))) {
               qA = div_rn_fast(inA, dA);
               qB = div_rn_fast(inB, dB);
             } else {
