@@ -1651,11 +1651,16 @@ __global__ void __launch_bounds__(kRows) loss_bwd_kernel(const BwdParams bp) {
         while (gcd < 32 && (q.C % (gcd * 2)) == 0) gcd *= 2;
         const int rot = (lane * gcd) >> 5;
         float coef_soft = 0.f, coef_hot = 0.f;  // grad = coef_soft*softmax - coef_hot*onehot
+        // The row's cross entropy against its target class, as the forward left it: for the background rows it is
+        // log(1 + sum of the other terms) at full relative precision, so the target element softmax_t - 1 is formed
+        // as expm1(-ce) instead of exp(x_t - lse) - 1 (lse is an fp32 number of the magnitude of the logits: the
+        // difference of two nearly equal probabilities would keep 3 digits at |x| ~ 16).
+        const float ce_t = selbits ? q.ce[np] : 0.f;
         if (selbits) {
           if (focal) {
             // L = A * w(pt)^g * ce ; ce = -log pt ; d ce/dx_k = softmax_k - onehot_k ; d pt/dx_k = -pt*(..)
-            const float pt = __expf(q.scores[np * q.C + cls] - lse);
-            const float ce = q.ce[np];
+            const float pt = __expf(-ce_t);
+            const float ce = ce_t;
             float dL_dce;
             if (selbits & 1) {  // foreground: A=alpha, w = 1-pt  -> dw/dce = pt
               const float w = 1.f - pt;
@@ -1680,14 +1685,14 @@ __global__ void __launch_bounds__(kRows) loss_bwd_kernel(const BwdParams bp) {
             const float nl2 = -lse * kLog2e;
 #pragma unroll
             for (int k = 0; k < kC; ++k) row[k] = coef_soft * ex2_approx(fmaf(row[k], kLog2e, nl2));
-            row[cls] -= coef_hot;
+            row[cls] = coef_hot * expm1f(-ce_t);
           }
         } else {
           for (int kk = 0; kk < q.C; ++kk) {
             int k = kk + rot;
             if (k >= q.C) k -= q.C;
             const float sm = __expf(row[k] - lse);
-            row[k] = coef_soft * sm - (k == cls ? coef_hot : 0.f);
+            row[k] = k == cls ? coef_hot * expm1f(-ce_t) : coef_soft * sm;
           }
         }
       }
@@ -1812,13 +1817,17 @@ __global__ void __launch_bounds__(256, 4) bwd_patch_kernel(const LossParams q, c
       reinterpret_cast<float4*>(grad_locs)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
     if (!grad_scores) continue;
+    // The target element of a selected row, scale * (softmax_t - 1), from the row's cross entropy against its target
+    // (background CE of a mined negative, true-class CE of a positive: both in `ce`) as expm1(-ce): exp(x_t - lse) - 1
+    // would difference two nearly equal numbers when the row is confident.
+    const float g_target = selbits ? conf_scale * expm1f(-ce_bg) : 0.f;
     unsigned m = __ballot_sync(0xffffffffu, selbits != 0);
     // four selected rows per round, every 32-class chunk of them loaded before anything is stored
     // (loads and stores may alias as far as the compiler knows): up to 16 loads in flight per lane
     while (m) {
       int src[4];
       int rc[4];
-      float rl[4];
+      float rl[4], rt[4];
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
         src[u] = -1;
@@ -1829,6 +1838,7 @@ __global__ void __launch_bounds__(256, 4) bwd_patch_kernel(const LossParams q, c
         const int sl = src[u] < 0 ? 0 : src[u];
         rc[u] = __shfl_sync(0xffffffffu, cls, sl);
         rl[u] = __shfl_sync(0xffffffffu, lse, sl);
+        rt[u] = __shfl_sync(0xffffffffu, g_target, sl);
       }
       // the lane's slice of each row: one 64-bit base per row, then immediate offsets (32 c floats per chunk)
       const float* rp[4];
@@ -1858,7 +1868,7 @@ __global__ void __launch_bounds__(256, 4) bwd_patch_kernel(const LossParams q, c
           const int k = 32 * c + lane;
 #pragma unroll
           for (int u = 0; u < 4; ++u)
-            if (has && src[u] >= 0) gp[u][32 * c] = conf_scale * (__expf(x[c][u] - rl[u]) - (k == rc[u] ? 1.f : 0.f));
+            if (has && src[u] >= 0) gp[u][32 * c] = k == rc[u] ? rt[u] : conf_scale * __expf(x[c][u] - rl[u]);
         }
       } else {
         for (int kb = 0; kb < C; kb += 32) {
@@ -1868,7 +1878,7 @@ __global__ void __launch_bounds__(256, 4) bwd_patch_kernel(const LossParams q, c
           for (int u = 0; u < 4; ++u) x[u] = (src[u] >= 0 && k < C) ? rp[u][kb] : 0.f;
 #pragma unroll
           for (int u = 0; u < 4; ++u)
-            if (src[u] >= 0 && k < C) gp[u][kb] = conf_scale * (__expf(x[u] - rl[u]) - (k == rc[u] ? 1.f : 0.f));
+            if (src[u] >= 0 && k < C) gp[u][kb] = k == rc[u] ? rt[u] : conf_scale * __expf(x[u] - rl[u]);
         }
       }
     }
