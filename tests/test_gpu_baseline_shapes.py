@@ -601,3 +601,17 @@ def test_hard_negative_mining_outside_the_histogram_range(dev):
             if only_g.numel():
                 assert torch.allclose(only_g[:, 0].sort().values, only_w[:, 0].sort().values, rtol=1e-2, atol=1e-9), name
         assert torch.allclose(got_g[both], want_g[both], rtol=RTOL_GRAD, atol=1e-7), name
+
+
+def test_randomised_shapes_against_the_oracle():
+    """tools/stress.py on a few random cases: odd prior counts, class counts on both sides of the compile-time
+    specialisations (2 ... 130), zero to 300 objects per image, the four criteria, scaled logits; train path
+    (assignment bit-exact, loss 1e-5, gradients 1e-4) and eval path (labels exact, scores / boxes 1e-5)."""
+    import os
+    import subprocess
+    import sys
+    repo = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(repo, "tools", "stress.py"), "8", "7"], capture_output=True,
+                         text=True, timeout=600, cwd=repo)
+    assert out.returncode == 0, (out.stdout[-3000:], out.stderr[-2000:])
+    assert "stress: 0 mismatches in 8 cases" in out.stdout
