@@ -1685,14 +1685,14 @@ __global__ void __launch_bounds__(kRows) loss_bwd_kernel(const BwdParams bp) {
             const float nl2 = -lse * kLog2e;
 #pragma unroll
             for (int k = 0; k < kC; ++k) row[k] = coef_soft * ex2_approx(fmaf(row[k], kLog2e, nl2));
-            row[cls] = coef_hot * expm1f(-ce_t);
+            row[cls] = coef_hot * expm1_neg(ce_t);
           }
         } else {
           for (int kk = 0; kk < q.C; ++kk) {
             int k = kk + rot;
             if (k >= q.C) k -= q.C;
             const float sm = __expf(row[k] - lse);
-            row[k] = k == cls ? coef_hot * expm1f(-ce_t) : coef_soft * sm;
+            row[k] = k == cls ? coef_hot * expm1_neg(ce_t) : coef_soft * sm;
           }
         }
       }
@@ -1820,7 +1820,7 @@ __global__ void __launch_bounds__(256, 4) bwd_patch_kernel(const LossParams q, c
     // The target element of a selected row, scale * (softmax_t - 1), from the row's cross entropy against its target
     // (background CE of a mined negative, true-class CE of a positive: both in `ce`) as expm1(-ce): exp(x_t - lse) - 1
     // would difference two nearly equal numbers when the row is confident.
-    const float g_target = selbits ? conf_scale * expm1f(-ce_bg) : 0.f;
+    const float g_target = selbits ? conf_scale * expm1_neg(ce_bg) : 0.f;
     unsigned m = __ballot_sync(0xffffffffu, selbits != 0);
     // four selected rows per round, every 32-class chunk of them loaded before anything is stored
     // (loads and stores may alias as far as the compiler knows): up to 16 loads in flight per lane
