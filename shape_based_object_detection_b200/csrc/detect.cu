@@ -797,7 +797,25 @@ __global__ void __launch_bounds__(kNmsThreads) detect_nms_kernel(const DetParams
     // Each thread keeps its element in a register; partners less than 32 apart are reached by
     // shuffles (40 of the 55 steps, no block barrier), the others through shared memory, alternating
     // between ckey and the not yet used cbox array so that one barrier per step suffices.
-    {
+    if (m <= 256) {
+      // Short chunks (the usual first round): rank sort. Four threads per key count the keys below it (keys are
+      // unique: one per (class, prior)), interleaved so that a warp's reads fall into different banks; the key then
+      // goes straight to its rank. Two barriers instead of the bitonic network's six plus thirty shuffle steps.
+      unsigned long long* bufB = reinterpret_cast<unsigned long long*>(S.cbox);
+      __syncthreads();
+      const int i = tid >> 2, part = tid & 3;
+      const unsigned long long my = i < m ? S.ckey[i] : ~0ull;
+      int below = 0;
+      for (int j = part; j < m; j += 4) below += S.ckey[j] < my ? 1 : 0;
+      below += __shfl_xor_sync(0xffffffffu, below, 1);
+      below += __shfl_xor_sync(0xffffffffu, below, 2);
+      if (part == 0 && i < m) bufB[below] = my;
+      __syncthreads();
+      const unsigned long long v = tid < m ? bufB[tid] : ~0ull;
+      __syncthreads();  // (bufB is the box array of the next phase)
+      S.ckey[tid] = v;
+      __syncthreads();
+    } else {
       unsigned long long v = tid < m ? S.ckey[tid] : ~0ull;
       unsigned long long* bufA = S.ckey;
       unsigned long long* bufB = reinterpret_cast<unsigned long long*>(S.cbox);
