@@ -977,10 +977,10 @@ __global__ void __launch_bounds__(kNmsThreads) detect_nms_kernel(const DetParams
         }
         __syncwarp();
       }
-      const unsigned int seen = g_seen[c];  // candidates of this class consumed by earlier rounds
-      if (lane == 0) g_seen[c] = seen + (seg1 - seg0);
       unsigned int lim = seg1;               // pre-NMS per-class cap: later candidates are dropped
       if (q.pre_nms_topk > 0) {
+        const unsigned int seen = g_seen[c];  // candidates of this class consumed by earlier rounds (global
+        if (lane == 0) g_seen[c] = seen + (seg1 - seg0);  // memory: only touched when the cap is in use)
         const unsigned int room = seen >= unsigned(q.pre_nms_topk) ? 0u : unsigned(q.pre_nms_topk) - seen;
         lim = min(seg1, seg0 + room);
       }
